@@ -1,0 +1,101 @@
+"""ctypes binding of libchessvision_b200.so (the C-ABI in include/chessvision_b200.h).
+
+The library is the product: if it cannot be loaded this module raises -- there is no Python/PyTorch
+fallback for any compute entry point.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchessvision_b200.so")
+
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+LAYOUT_HWC, LAYOUT_CHW = 0, 1
+FEN_STRIDE = 80
+PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class LayerInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "cin", "cout", "k", "stride", "relu", "hin", "hout", "skip")] + \
+               [("w_offset", C.c_int64), ("b_offset", C.c_int64)]
+
+
+_lib = None
+
+
+def _sig(fn, res, *args):
+    fn.restype = res
+    fn.argtypes = list(args)
+
+
+def lib():
+    """Load (building first if the sources are newer) and return the ctypes library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import _build
+        _build.build()
+    try:
+        L = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise NativeError(f"cannot load {LIB_PATH}: {e} (chess_vision_b200 has no CPU fallback)") from e
+    vp, i32, i64, sz, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_uint32
+    _sig(L.cv_last_error, C.c_char_p)
+    _sig(L.cv_abi_version, i32)
+    _sig(L.cv_num_layers, i32)
+    _sig(L.cv_layer_info_get, i32, i32, C.POINTER(LayerInfo))
+    _sig(L.cv_weight_blob_floats, sz)
+    _sig(L.cv_square_create, i32, i32, C.POINTER(vp))
+    _sig(L.cv_square_destroy, i32, vp)
+    _sig(L.cv_square_load_weights, i32, vp, vp, sz, vp)
+    _sig(L.cv_square_set_norm_lut, i32, vp, vp)
+    _sig(L.cv_square_set_wave, i32, vp, i32)
+    _sig(L.cv_square_workspace_bytes, sz, vp, i32, i32, i32)
+    _sig(L.cv_square_forward_f32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp)
+    _sig(L.cv_square_forward_u8, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp)
+    _sig(L.cv_square_fen, i32, vp, vp, vp, vp, i32, vp, vp, vp)
+    _sig(L.cv_square_predict_u8, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, sz, vp)
+    _sig(L.cv_square_predict_host_u8, i32, vp, vp, i32, vp, i32, i32, i32, vp, vp)
+    _sig(L.cv_combine_type_color, i32, vp, vp, i64, vp, vp)
+    _sig(L.cv_crop_squares_f32, i32, vp, i32, i32, vp, vp)
+    _sig(L.cv_crop_squares_u8, i32, vp, i32, i32, i32, vp, vp)
+    _sig(L.cv_crop_index_table, i32, i32, vp, vp, vp)
+    _sig(L.cv_square_set_tap, i32, vp, i32, vp, sz)
+    _sig(L.cv_synth_boards, i32, vp, i32, i64, i32, i32, u32, i32, vp, vp)
+    _sig(L.cv_synth_boards_host, i32, vp, i32, i64, i32, i32, u32, i32, vp)
+    _sig(L.cv_fen_from_classes_host, i32, vp, C.c_float, vp, vp)
+    _sig(L.cv_square_launch_count, i64, vp)
+    if L.cv_abi_version() != 1:
+        raise NativeError("libchessvision_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeError(f"chessvision_b200 native call failed ({rc}): {lib().cv_last_error().decode()}")
+
+
+def layer_table():
+    L = lib()
+    out = []
+    for i in range(L.cv_num_layers()):
+        info = LayerInfo()
+        check(L.cv_layer_info_get(i, C.byref(info)))
+        out.append(info)
+    return out
+
+
+def ptr(t):
+    """Device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -1,0 +1,487 @@
+// C-ABI of libchessvision_b200.so: handle life cycle, weight loading, wave scheduler, forward / predict
+// entry points (include/chessvision_b200.h).  Host-side orchestration only; kernels live in the other
+// translation units.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "internal.h"
+#include "arch_table.inc"
+
+static thread_local char g_err[1024] = "";
+
+void cv_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const cv_layer_info* cv_layers() { return kLayers; }
+
+namespace {
+
+constexpr int NBUF_SMALL = 4;
+constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
+constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128;
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct cv_square {
+    int device = 0;
+    bool loaded = false;
+    float* blob = nullptr;        // fp32 packed weights (device, owned)
+    float* glob_wt = nullptr;     // global_head weight transposed to [30720][64] (device, owned)
+    float* head_w = nullptr;      // aligned copies of the small heads: head_w[10*480], head_b[10], glob_b[64], tc_w[320], tc_b[5]
+    float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
+    int wave = 0;                 // boards per wave, 0 = default per precision
+    int tap_layer = -1;
+    float* tap_dst = nullptr;
+    size_t tap_n = 0;
+    int64_t launches = 0;
+    int out_buf[CV_NUM_LAYERS];   // small-buffer index each layer writes (-1: dedicated stem buffer)
+    // host-pointer pipeline resources (lazily created)
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    void* stage[2] = {nullptr, nullptr};
+    uint8_t* stage_flip[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    void* own_ws = nullptr;
+    size_t own_ws_bytes = 0;
+    char* dev_fen = nullptr;
+    uint8_t* dev_fen_len = nullptr;
+    int dev_fen_cap = 0;
+};
+
+namespace {
+
+// Greedy assignment of the rotating small activation buffers: a layer's output stays live until its last
+// reader (the next layer, or the pw_proj that adds it back as a residual).
+void plan_buffers(cv_square* h) {
+    int last_use[CV_NUM_LAYERS];
+    for (int i = 0; i < CV_NUM_LAYERS; ++i) last_use[i] = i + 1;
+    for (int i = 0; i < CV_NUM_LAYERS; ++i)
+        if (kLayers[i].skip >= 0) last_use[kLayers[i].skip] = std::max(last_use[kLayers[i].skip], i);
+    int owner[NBUF_SMALL];
+    for (int b = 0; b < NBUF_SMALL; ++b) owner[b] = -1;
+    h->out_buf[0] = -1;
+    for (int i = 1; i < CV_NUM_LAYERS; ++i) {
+        int pick = -1;
+        for (int b = 0; b < NBUF_SMALL && pick < 0; ++b)
+            if (owner[b] < 0 || last_use[owner[b]] < i) pick = b;     // free once every reader has run
+        h->out_buf[i] = pick;                                           // never -1: 4 buffers suffice (checked at create)
+        if (pick >= 0) owner[pick] = i;
+    }
+}
+
+struct WavePlan {
+    int wave;
+    size_t es;                        // activation element size
+    size_t off_crops, off_stem, off_small[NBUF_SMALL], off_feat, off_sq, off_turn, off_cast, total;
+};
+
+WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
+    WavePlan p;
+    int def = precision == CV_PRECISION_FP32 ? DEFAULT_WAVE_FP32 : DEFAULT_WAVE_BF16;
+    p.wave = h->wave > 0 ? h->wave : def;
+    if (p.wave > max_boards) p.wave = std::max(max_boards, 1);
+    p.es = precision == CV_PRECISION_FP32 ? 4 : 2;
+    const size_t n = (size_t)p.wave * 64;
+    size_t off = 0;
+    p.off_crops = off; off = align_up(off + n * EL_CROPS * p.es);
+    p.off_stem = off; off = align_up(off + n * EL_STEM * p.es);
+    for (int b = 0; b < NBUF_SMALL; ++b) { p.off_small[b] = off; off = align_up(off + n * EL_SMALL * p.es); }
+    p.off_feat = off; off = align_up(off + n * 480 * sizeof(float));
+    // scratch logits for the predict entry points (whole batch)
+    p.off_sq = off; off = align_up(off + (size_t)max_boards * 832 * sizeof(float));
+    p.off_turn = off; off = align_up(off + (size_t)max_boards * sizeof(float));
+    p.off_cast = off; off = align_up(off + (size_t)max_boards * 4 * sizeof(float));
+    p.total = off;
+    return p;
+}
+
+template <typename T>
+int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* turn, float* castling,
+             float* features_user, bool first_wave, cudaStream_t s) {
+    const int64_t n = (int64_t)nb * 64;
+    T* crops = reinterpret_cast<T*>(ws + p.off_crops);
+    T* stem = reinterpret_cast<T*>(ws + p.off_stem);
+    T* small[NBUF_SMALL];
+    for (int b = 0; b < NBUF_SMALL; ++b) small[b] = reinterpret_cast<T*>(ws + p.off_small[b]);
+    float* feat = reinterpret_cast<float*>(ws + p.off_feat);
+    auto buf_of = [&](int layer) -> T* { return layer < 0 ? crops : (h->out_buf[layer] < 0 ? stem : small[h->out_buf[layer]]); };
+    for (int i = 0; i < CV_NUM_LAYERS; ++i) {
+        const cv_layer_info& L = kLayers[i];
+        const T* in = buf_of(i - 1);
+        T* out = buf_of(i);
+        const float* w = h->blob + L.w_offset;
+        const float* b = h->blob + L.b_offset;
+        int rc;
+        if (L.kind == CV_KIND_DEPTHWISE) rc = launch_depthwise_generic<T>(L, in, w, b, out, n, s);
+        else rc = launch_conv_generic<T>(L, in, w, b, L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, s);
+        if (rc) return rc;
+        ++h->launches;
+        if (first_wave && h->tap_layer == i && h->tap_dst) {
+            size_t cnt = std::min(h->tap_n, (size_t)n * L.hout * L.hout * L.cout);
+            rc = launch_to_f32<T>(out, h->tap_dst, cnt, s);
+            if (rc) return rc;
+        }
+    }
+    int rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, s);
+    if (rc) return rc;
+    rc = launch_global_head(feat, h->glob_wt, h->head_w + 4800 + 16, h->head_w + 4800 + 16 + 64, h->head_w + 4800 + 16 + 64 + 320,
+                            nb, turn, castling, s);
+    if (rc) return rc;
+    h->launches += 2;
+    return CV_OK;
+}
+
+template <typename T>
+int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layout, int B, int H, int precision,
+                 float* squares, float* turn, float* castling, float* features, void* workspace, size_t ws_bytes,
+                 cudaStream_t s) {
+    CropGeom g;
+    int rc = cv_make_crop_geom(H, &g);
+    if (rc) return rc;
+    WavePlan p = make_plan(h, B, precision);
+    if (ws_bytes < p.total) {
+        cv_set_error("workspace too small: need %zu bytes, got %zu", p.total, ws_bytes);
+        return CV_ERR_WORKSPACE;
+    }
+    char* ws = static_cast<char*>(workspace);
+    T* crops = reinterpret_cast<T*>(ws + p.off_crops);
+    for (int b0 = 0; b0 < B; b0 += p.wave) {
+        const int nb = std::min(p.wave, B - b0);
+        if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+        else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+        if (rc) return rc;
+        ++h->launches;
+        rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, turn + b0, castling + (size_t)b0 * 4,
+                         features ? features + (size_t)b0 * 64 * 480 : nullptr, b0 == 0, s);
+        if (rc) return rc;
+    }
+    return CV_OK;
+}
+
+int check_forward_args(const cv_square* h, const void* x, int B, int H, int precision, const void* squares,
+                       const void* turn, const void* castling, const void* ws) {
+    if (!h) { cv_set_error("null handle"); return CV_ERR_ARG; }
+    if (!h->loaded) { cv_set_error("weights not loaded: call cv_square_load_weights first"); return CV_ERR_STATE; }
+    if (B < 0) { cv_set_error("negative batch"); return CV_ERR_ARG; }
+    if (precision != CV_PRECISION_FP32 && precision != CV_PRECISION_BF16) { cv_set_error("bad precision %d", precision); return CV_ERR_ARG; }
+    if (H < 32 || H % 32) { cv_set_error("board side H=%d must be a positive multiple of 32", H); return CV_ERR_ARG; }
+    if (B > 0 && (!x || !squares || !turn || !castling || !ws)) { cv_set_error("null data pointer"); return CV_ERR_ARG; }
+    return CV_OK;
+}
+
+void default_lut(float* lut) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int c = 0; c < 3; ++c)
+        for (int u = 0; u < 256; ++u) {
+            volatile float t = (float)u / 255.0f;       // ToTensor: .div(255)
+            volatile float d = t - mean[c];             // Normalize: .sub_(mean)
+            lut[c * 256 + u] = d / stdv[c];             //            .div_(std)
+        }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* cv_last_error(void) { return g_err; }
+int cv_abi_version(void) { return CV_ABI_VERSION; }
+int cv_num_layers(void) { return CV_NUM_LAYERS; }
+size_t cv_weight_blob_floats(void) { return (size_t)CV_BLOB_FLOATS; }
+
+int cv_layer_info_get(int index, cv_layer_info* out) {
+    CV_ARG(out != nullptr, "null out");
+    CV_ARG(index >= 0 && index < CV_NUM_LAYERS, "layer index out of range");
+    *out = kLayers[index];
+    return CV_OK;
+}
+
+int cv_square_create(int device, cv_square** out) {
+    CV_ARG(out != nullptr, "null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cv_set_error("no CUDA device available (%s): chessvision_b200 has no CPU fallback", cudaGetErrorString(e));
+        return CV_ERR_CUDA;
+    }
+    CV_ARG(device >= 0 && device < count, "device index out of range");
+    CV_CUDA(cudaSetDevice(device));
+    cv_square* h = new cv_square();
+    h->device = device;
+    plan_buffers(h);
+    for (int i = 1; i < CV_NUM_LAYERS; ++i)
+        if (h->out_buf[i] < 0 || (int64_t)kLayers[i].hout * kLayers[i].hout * kLayers[i].cout > EL_SMALL) {
+            cv_set_error("internal: activation buffer plan failed at layer %d", i);
+            delete h;
+            return CV_ERR_STATE;
+        }
+    CV_CUDA(cudaMalloc(&h->blob, (size_t)CV_BLOB_FLOATS * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->glob_wt, (size_t)30720 * 64 * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
+    float lut[768];
+    default_lut(lut);
+    CV_CUDA(cudaMemcpy(h->lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    *out = h;
+    return CV_OK;
+}
+
+int cv_square_destroy(cv_square* h) {
+    if (!h) return CV_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut);
+    for (int i = 0; i < 2; ++i) {
+        if (h->stage[i]) cudaFree(h->stage[i]);
+        if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+    }
+    if (h->own_ws) cudaFree(h->own_ws);
+    if (h->dev_fen) cudaFree(h->dev_fen);
+    if (h->dev_fen_len) cudaFree(h->dev_fen_len);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->compute_stream) cudaStreamDestroy(h->compute_stream);
+    delete h;
+    return CV_OK;
+}
+
+int cv_square_set_norm_lut(cv_square* h, const float* lut_host) {
+    CV_ARG(h && lut_host, "null argument");
+    CV_CUDA(cudaSetDevice(h->device));
+    CV_CUDA(cudaMemcpy(h->lut, lut_host, 768 * sizeof(float), cudaMemcpyHostToDevice));
+    return CV_OK;
+}
+
+int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, void* stream) {
+    CV_ARG(h && blob, "null argument");
+    CV_ARG(n_floats == (size_t)CV_BLOB_FLOATS, "weight blob has the wrong number of floats");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CV_CUDA(cudaSetDevice(h->device));
+    CV_CUDA(cudaMemcpyAsync(h->blob, blob, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int rc = launch_transpose_f32(h->blob + CV_OFF_GLOB_W, h->glob_wt, 64, 30720, s);
+    if (rc) return rc;
+    float* hw = h->head_w;
+    CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(hw + 4800, h->blob + CV_OFF_HEAD_B, 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(hw + 4816, h->blob + CV_OFF_GLOB_B, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(hw + 4880, h->blob + CV_OFF_TC_W, 320 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(hw + 5200, h->blob + CV_OFF_TC_B, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaStreamSynchronize(s));
+    h->loaded = true;
+    return CV_OK;
+}
+
+int cv_square_set_wave(cv_square* h, int boards) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_ARG(boards >= 0 && boards <= 4096, "wave must be in [0,4096]");
+    h->wave = boards;
+    return CV_OK;
+}
+
+size_t cv_square_workspace_bytes(const cv_square* h, int max_boards, int H, int precision) {
+    (void)H;
+    if (!h || max_boards < 0) return 0;
+    return make_plan(h, std::max(max_boards, 1), precision).total;
+}
+
+int cv_square_forward_f32(cv_square* h, const float* x, int B, int H, int precision, float* squares, float* turn,
+                          float* castling, float* features, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_forward_args(h, x, B, H, precision, squares, turn, castling, ws);
+    if (rc) return rc;
+    if (B == 0) return CV_OK;
+    CV_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == CV_PRECISION_FP32)
+        return forward_impl<float>(h, x, nullptr, 0, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
+    return forward_impl<bf16>(h, x, nullptr, 0, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
+}
+
+int cv_square_forward_u8(cv_square* h, const uint8_t* boards, int layout, int B, int H, int precision, float* squares,
+                         float* turn, float* castling, float* features, void* ws, size_t ws_bytes, void* stream) {
+    int rc = check_forward_args(h, boards, B, H, precision, squares, turn, castling, ws);
+    if (rc) return rc;
+    CV_ARG(layout == CV_LAYOUT_HWC || layout == CV_LAYOUT_CHW, "bad layout");
+    if (B == 0) return CV_OK;
+    CV_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == CV_PRECISION_FP32)
+        return forward_impl<float>(h, nullptr, boards, layout, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
+    return forward_impl<bf16>(h, nullptr, boards, layout, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
+}
+
+int cv_square_fen(const float* squares, const float* turn, const float* castling, const uint8_t* flipped, int B,
+                  char* fen, uint8_t* fen_len, void* stream) {
+    CV_ARG(B >= 0, "negative batch");
+    if (B == 0) return CV_OK;
+    CV_ARG(squares && turn && castling && fen && fen_len, "null data pointer");
+    return launch_fen(squares, turn, castling, flipped, B, fen, fen_len, static_cast<cudaStream_t>(stream));
+}
+
+int cv_square_predict_u8(cv_square* h, const uint8_t* boards, int layout, const uint8_t* flipped, int B, int H,
+                         int precision, char* fen, uint8_t* fen_len, void* ws, size_t ws_bytes, void* stream) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_ARG(B >= 0, "negative batch");
+    if (B == 0) return CV_OK;
+    CV_ARG(fen && fen_len && ws, "null data pointer");
+    WavePlan p = make_plan(h, B, precision);
+    char* w = static_cast<char*>(ws);
+    float* sq = reinterpret_cast<float*>(w + p.off_sq);
+    float* tu = reinterpret_cast<float*>(w + p.off_turn);
+    float* ca = reinterpret_cast<float*>(w + p.off_cast);
+    int rc = cv_square_forward_u8(h, boards, layout, B, H, precision, sq, tu, ca, nullptr, ws, ws_bytes, stream);
+    if (rc) return rc;
+    rc = launch_fen(sq, tu, ca, flipped, B, fen, fen_len, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
+    ++h->launches;
+    return CV_OK;
+}
+
+// Host-buffer end-to-end: chunks of `chunk` boards are copied H2D on a copy stream into one of two staging
+// buffers while the previous chunk computes; FEN records come back with one D2H at the end.
+int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layout, const uint8_t* flipped_host, int B,
+                              int H, int precision, char* fen_host, uint8_t* fen_len_host) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_ARG(B >= 0, "negative batch");
+    if (!h->loaded) { cv_set_error("weights not loaded"); return CV_ERR_STATE; }
+    if (B == 0) return CV_OK;
+    CV_ARG(boards_host && fen_host && fen_len_host, "null host pointer");
+    CV_ARG(H >= 32 && H % 32 == 0, "H must be a positive multiple of 32");
+    CV_CUDA(cudaSetDevice(h->device));
+    if (!h->copy_stream) {
+        CV_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CV_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CV_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+            CV_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    const size_t per_board = (size_t)H * H * 3;
+    const int chunk = std::min(B, 512);
+    if (h->stage_bytes < chunk * per_board) {
+        for (int i = 0; i < 2; ++i) {
+            if (h->stage[i]) CV_CUDA(cudaFree(h->stage[i]));
+            if (h->stage_flip[i]) CV_CUDA(cudaFree(h->stage_flip[i]));
+            CV_CUDA(cudaMalloc(&h->stage[i], chunk * per_board));
+            CV_CUDA(cudaMalloc(&h->stage_flip[i], 512));
+        }
+        h->stage_bytes = chunk * per_board;
+    }
+    size_t need = cv_square_workspace_bytes(h, chunk, H, precision);
+    if (h->own_ws_bytes < need) {
+        if (h->own_ws) CV_CUDA(cudaFree(h->own_ws));
+        CV_CUDA(cudaMalloc(&h->own_ws, need));
+        h->own_ws_bytes = need;
+    }
+    if (h->dev_fen_cap < B) {
+        if (h->dev_fen) CV_CUDA(cudaFree(h->dev_fen));
+        if (h->dev_fen_len) CV_CUDA(cudaFree(h->dev_fen_len));
+        CV_CUDA(cudaMalloc(&h->dev_fen, (size_t)B * CV_FEN_STRIDE));
+        CV_CUDA(cudaMalloc(&h->dev_fen_len, (size_t)B));
+        h->dev_fen_cap = B;
+    }
+    int slot = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, slot ^= 1) {
+        const int nb = std::min(chunk, B - b0);
+        if (b0 >= 2 * chunk) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
+        CV_CUDA(cudaMemcpyAsync(h->stage[slot], boards_host + (size_t)b0 * per_board, nb * per_board,
+                                cudaMemcpyHostToDevice, h->copy_stream));
+        if (flipped_host)
+            CV_CUDA(cudaMemcpyAsync(h->stage_flip[slot], flipped_host + b0, nb, cudaMemcpyHostToDevice, h->copy_stream));
+        CV_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        CV_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_h2d[slot], 0));
+        int rc = cv_square_predict_u8(h, static_cast<const uint8_t*>(h->stage[slot]), layout,
+                                      flipped_host ? h->stage_flip[slot] : nullptr, nb, H, precision,
+                                      h->dev_fen + (size_t)b0 * CV_FEN_STRIDE, h->dev_fen_len + b0, h->own_ws,
+                                      h->own_ws_bytes, h->compute_stream);
+        if (rc) return rc;
+        CV_CUDA(cudaEventRecord(h->ev_done[slot], h->compute_stream));
+    }
+    CV_CUDA(cudaMemcpyAsync(fen_host, h->dev_fen, (size_t)B * CV_FEN_STRIDE, cudaMemcpyDeviceToHost, h->compute_stream));
+    CV_CUDA(cudaMemcpyAsync(fen_len_host, h->dev_fen_len, (size_t)B, cudaMemcpyDeviceToHost, h->compute_stream));
+    CV_CUDA(cudaStreamSynchronize(h->compute_stream));
+    return CV_OK;
+}
+
+int cv_combine_type_color(const float* t, const float* c, int64_t n, float* joint, void* stream) {
+    CV_ARG(n >= 0, "negative n");
+    if (n == 0) return CV_OK;
+    CV_ARG(t && c && joint, "null data pointer");
+    return launch_combine(t, c, n, joint, static_cast<cudaStream_t>(stream));
+}
+
+int cv_crop_squares_f32(const float* x, int B, int H, float* crops_nchw, void* stream) {
+    CV_ARG(B >= 0, "negative batch");
+    if (B == 0) return CV_OK;
+    CV_ARG(x && crops_nchw, "null data pointer");
+    CropGeom g;
+    int rc = cv_make_crop_geom(H, &g);
+    if (rc) return rc;
+    return launch_crop_f32<float>(x, B, H, g, nullptr, crops_nchw, static_cast<cudaStream_t>(stream));
+}
+
+int cv_crop_squares_u8(const uint8_t* boards, int layout, int B, int H, float* crops_nchw, void* stream) {
+    CV_ARG(B >= 0, "negative batch");
+    if (B == 0) return CV_OK;
+    CV_ARG(boards && crops_nchw, "null data pointer");
+    CV_ARG(layout == CV_LAYOUT_HWC || layout == CV_LAYOUT_CHW, "bad layout");
+    CropGeom g;
+    int rc = cv_make_crop_geom(H, &g);
+    if (rc) return rc;
+    float lut[768];
+    default_lut(lut);
+    float* dl = nullptr;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CV_CUDA(cudaMallocAsync(&dl, sizeof(lut), s));
+    CV_CUDA(cudaMemcpyAsync(dl, lut, sizeof(lut), cudaMemcpyHostToDevice, s));
+    rc = launch_crop_u8<float>(boards, layout, B, H, g, dl, nullptr, crops_nchw, s);
+    CV_CUDA(cudaStreamSynchronize(s));     // lut[] is a stack buffer
+    CV_CUDA(cudaFreeAsync(dl, s));
+    return rc;
+}
+
+// Host-side query of the crop source-index tables (pure integer/fp32 arithmetic, no GPU needed):
+// y0,y1: (8,64) board rows/cols after replicate-pad clamping; lam: (64).  Written to HOST memory.
+int cv_crop_index_table(int H, int32_t* y0, int32_t* y1, float* lam) {
+    CV_ARG(y0 && y1 && lam, "null output pointer");
+    CropGeom g;
+    int rc = cv_make_crop_geom(H, &g);
+    if (rc) return rc;
+    for (int r = 0; r < 8; ++r)
+        for (int d = 0; d < 64; ++d) {
+            int a = r * g.sq + g.i0[d] - g.pad, b = r * g.sq + g.i1[d] - g.pad;
+            y0[r * 64 + d] = std::min(std::max(a, 0), H - 1);
+            y1[r * 64 + d] = std::min(std::max(b, 0), H - 1);
+        }
+    for (int d = 0; d < 64; ++d) lam[d] = g.lam[d];
+    return CV_OK;
+}
+
+int cv_square_set_tap(cv_square* h, int layer, float* dst, size_t n_floats) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_ARG(layer < CV_NUM_LAYERS, "layer index out of range");
+    h->tap_layer = layer;
+    h->tap_dst = layer < 0 ? nullptr : dst;
+    h->tap_n = n_floats;
+    return CV_OK;
+}
+
+int cv_synth_boards(uint8_t* boards, int layout, int64_t first_board, int B, int H, uint32_t seed, int dist,
+                    uint8_t* flipped, void* stream) {
+    CV_ARG(B >= 0, "negative batch");
+    CV_ARG(H >= 32 && H % 32 == 0, "H must be a positive multiple of 32");
+    CV_ARG(layout == CV_LAYOUT_HWC || layout == CV_LAYOUT_CHW, "bad layout");
+    CV_ARG(dist == CV_DIST_UNIFORM || dist == CV_DIST_STRUCTURED, "bad distribution");
+    return launch_synth(boards, layout, first_board, B, H, seed, dist, flipped, static_cast<cudaStream_t>(stream));
+}
+
+int64_t cv_square_launch_count(const cv_square* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

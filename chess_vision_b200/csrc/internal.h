@@ -1,0 +1,75 @@
+// Internal declarations shared by the translation units of libchessvision_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/chessvision_b200.h"
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void cv_set_error(const char* fmt, ...);
+#define CV_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            cv_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return CV_ERR_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+#define CV_CHECK_LAUNCH() CV_CUDA(cudaGetLastError())
+#define CV_ARG(cond, msg)                                     \
+    do {                                                      \
+        if (!(cond)) {                                        \
+            cv_set_error("%s: %s", __func__, msg);            \
+            return CV_ERR_ARG;                                \
+        }                                                     \
+    } while (0)
+
+extern const cv_layer_info* cv_layers();   // the compiled-in table (arch_table.inc)
+
+// ---- crop geometry (models/square.py:53-55) + bilinear taps (ATen upsample_bilinear2d,
+//      align_corners=False), computed once on the host and passed by value to the kernels ----------
+struct CropGeom {
+    int H, sq, crop, pad;
+    int16_t i0[64], i1[64];   // crop-space taps per output pixel
+    float lam[64];
+};
+int cv_make_crop_geom(int H, CropGeom* g);
+
+struct NormLut { float v[3][256]; };   // (u8/255 - mean[c]) / std[c]
+
+// ---- generic (precision-templated) kernels: kernels_generic.cu ----------------------------------
+// All activations NHWC; T = float (CV_PRECISION_FP32) or bf16; accumulation always fp32.
+template <typename T>
+int launch_crop_f32(const float* x_nchw, int B, int H, const CropGeom& g, T* out_nhwc, float* out_nchw,
+                    cudaStream_t s);
+template <typename T>
+int launch_crop_u8(const uint8_t* boards, int layout, int B, int H, const CropGeom& g, const float* lut_dev,
+                   T* out_nhwc, float* out_nchw, cudaStream_t s);
+template <typename T>
+int launch_conv_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, const T* skip,
+                        T* out, int64_t n_crops, cudaStream_t s);
+template <typename T>
+int launch_depthwise_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, T* out,
+                             int64_t n_crops, cudaStream_t s);
+template <typename T>
+int launch_pool_heads(const T* feat_map /*[N,2,2,480]*/, const float* head_w, const float* head_b,
+                      int64_t n_crops, float* features /*[N,480]*/, float* features_user, float* squares,
+                      cudaStream_t s);
+int launch_global_head(const float* features /*[B,30720]*/, const float* glob_wt /*[30720,64]*/,
+                       const float* glob_b, const float* tc_w, const float* tc_b, int B, float* turn,
+                       float* castling, cudaStream_t s);
+template <typename T>
+int launch_to_f32(const T* src, float* dst, size_t n, cudaStream_t s);
+int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r]=src[r][c]
+
+// ---- fen.cu / synth.cu ---------------------------------------------------------------------------
+int launch_fen(const float* squares, const float* turn, const float* castling, const uint8_t* flipped, int B,
+               char* fen, uint8_t* fen_len, cudaStream_t s);
+int launch_synth(uint8_t* boards, int layout, int64_t first_board, int B, int H, uint32_t seed, int dist,
+                 uint8_t* flipped, cudaStream_t s);
+int launch_combine(const float* t, const float* c, int64_t n, float* joint, cudaStream_t s);

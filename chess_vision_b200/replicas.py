@@ -1,0 +1,49 @@
+"""Data-parallel replicas: one process per GPU, boards sharded by global index, weights broadcast once.
+
+The path has no exchange step: every board is independent.  The only collective is one
+broadcast of the packed fp32 weight blob from rank 0 at start-up (NCCL over NVLink/NVSwitch on GPUs, gloo
+in the CPU tests); an optional all_reduce of a checksum lets tests prove every rank holds the same bytes.
+"""
+import zlib
+
+import torch
+import torch.distributed as dist
+
+from . import arch, weights
+
+
+def shard_range(n_boards: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of the global board index range for ``rank``; sizes differ by at most 1."""
+    base, rem = divmod(n_boards, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def broadcast_packed_weights(model=None, src: int = 0, device=None) -> torch.Tensor:
+    """Rank ``src`` packs its model's state_dict (BN fold etc.) and broadcasts the blob; every rank returns
+    the blob on ``device``.  Without an initialised process group this is a local pack."""
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank() if distributed else 0
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    if rank == src:
+        blob = weights.pack_state_dict(model.state_dict()).to(device)
+    else:
+        blob = torch.empty(arch.BLOB_FLOATS, dtype=torch.float32, device=device)
+    if distributed:
+        dist.broadcast(blob, src=src)
+    return blob
+
+
+def blob_checksum(blob: torch.Tensor) -> int:
+    return zlib.crc32(blob.detach().cpu().numpy().tobytes())
+
+
+def all_ranks_agree(value: int) -> bool:
+    """True iff every rank passed the same integer (checksum of weights, of FEN records, ...)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return True
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([value, -value], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t[0].item()) == value and int(-t[1].item()) == value

@@ -1,0 +1,152 @@
+/*
+ * chessvision_b200 -- C-ABI of the B200-native ChessSquareCNN inference hot path.
+ *
+ * The reference (cloudui/chess-vision) is pure Python/PyTorch and has no FFI; the hot path is one
+ * Python call, `model(images)` -> ChessSquareCNN.forward (models/square.py:92-114), followed by the
+ * FEN assembly of predict.py:27-42.  This header is the boundary a maintainer binds instead of those
+ * Python bodies (ctypes stub in INTEGRATION.md).  Every entry point below cites the reference code
+ * it replaces.
+ *
+ * Conventions
+ *   - plain C types only; all `const void* / void*` data pointers are DEVICE pointers owned by the
+ *     caller unless the name says `host`;
+ *   - every call returns CV_OK (0) or a negative cv_status; cv_last_error() gives the text of the last
+ *     failure on the calling thread; nothing throws across the boundary;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work
+ *     on it -- no device synchronisation unless documented;
+ *   - one handle per device; a handle is not re-entrant, distinct handles are independent.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     CV_ERR_CUDA.
+ */
+#ifndef CHESSVISION_B200_H
+#define CHESSVISION_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CV_ABI_VERSION 1
+
+typedef enum cv_status {
+    CV_OK = 0,
+    CV_ERR_ARG = -1,        /* bad argument (null pointer, bad size, H not a multiple of 32, ...) */
+    CV_ERR_CUDA = -2,       /* CUDA runtime / launch failure; text in cv_last_error() */
+    CV_ERR_STATE = -3,      /* call order (e.g. forward before weights were loaded) */
+    CV_ERR_WORKSPACE = -4   /* workspace too small */
+} cv_status;
+
+enum { CV_PRECISION_FP32 = 0, CV_PRECISION_BF16 = 1 };
+enum { CV_LAYOUT_HWC = 0, CV_LAYOUT_CHW = 1 };           /* uint8 board layouts: (B,H,H,3) / (B,3,H,H) */
+enum { CV_DIST_UNIFORM = 0, CV_DIST_STRUCTURED = 1 };    /* synthetic board distributions */
+enum { CV_KIND_DENSE = 0, CV_KIND_POINTWISE = 1, CV_KIND_DEPTHWISE = 2 };
+enum { CV_FEN_STRIDE = 80 };                             /* bytes per FEN record, NUL padded (max 78) */
+enum { CV_NUM_SQUARES = 64, CV_NUM_CLASSES = 13, CV_FEATURE_DIM = 480 };
+
+typedef struct cv_square cv_square;                      /* opaque per-device model handle */
+
+/* One conv(+folded BN)(+ReLU)(+residual) layer of the trunk (timm mobilenetv4_conv_small_050
+ * forward_features as called at models/square.py:86). */
+typedef struct cv_layer_info {
+    int32_t kind, cin, cout, k, stride, relu, hin, hout, skip;
+    int64_t w_offset, b_offset;                          /* float offsets into the weight blob */
+} cv_layer_info;
+
+/* ---- library / table queries (no GPU needed) ------------------------------------------------- */
+const char* cv_last_error(void);
+int         cv_abi_version(void);
+int         cv_num_layers(void);                         /* 45 */
+int         cv_layer_info_get(int index, cv_layer_info* out);
+size_t      cv_weight_blob_floats(void);                 /* size of the packed fp32 weight blob */
+
+/* ---- handle life cycle: replaces build_square()/build_model() module construction
+ *      (models/square.py:117-138, models/__init__.py:8-30) on the device side ------------------ */
+int cv_square_create(int device, cv_square** out);
+int cv_square_destroy(cv_square* h);
+
+/* Weights: `blob` is a DEVICE pointer to cv_weight_blob_floats() fp32 values laid out as documented in
+ * chess_vision_b200/arch.py (BatchNorm already folded, eval mode eps=1e-5: models/square.py:83-84).
+ * Replaces model.load_state_dict(ckpt["model"]) (predict.py:57) for the device copy.  Derives the bf16
+ * tensor-core operand images.  Synchronises `stream` before returning. */
+int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, void* stream);
+
+/* Normalisation table lut[c*256+u] = (u/255 - mean[c]) / std[c] for the uint8 entry points; the default is
+ * the timm IMAGENET mean/std the reference reads from pretrained_cfg (dataset.py:157-160).  HOST pointer,
+ * 768 floats. */
+int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
+
+/* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */
+int cv_square_set_wave(cv_square* h, int boards);
+
+size_t cv_square_workspace_bytes(const cv_square* h, int max_boards, int H, int precision);
+
+/* ChessSquareCNN.forward (models/square.py:92-114) on an already-normalised fp32 NCHW batch
+ * x (B,3,H,H), H % 32 == 0 -- the tensor get_transform()'s eval branch produces (dataset.py:177-181).
+ * Outputs fp32: squares (B,832) index = square*13+class; turn (B,1); castling (B,4);
+ * features (B*64,480) optional (NULL to skip) = the pooled trunk output of square.py:90. */
+int cv_square_forward_f32(cv_square* h, const float* x_nchw, int B, int H, int precision,
+                          float* squares, float* turn, float* castling, float* features,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same forward from raw uint8 boards; ToTensor+Normalize (dataset.py:177-181) is fused into the crop
+ * gather: value = (u8/255 - mean[c]) / std[c] in fp32, mean/std = timm IMAGENET defaults. */
+int cv_square_forward_u8(cv_square* h, const uint8_t* boards, int layout, int B, int H, int precision,
+                         float* squares, float* turn, float* castling, float* features,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* FEN assembly (predict.py:27-42 + dataset.py:52-70 labels_to_fen), batched on the device:
+ * argmax over 13 (first max wins), run-length placement, turn>0 -> 'b', castling>0 -> subset of "KQkq"
+ * or "-".  `flipped` (B bytes or NULL): non-zero re-indexes the 64 labels by 63-i (board rendered from
+ * Black's side; datagen/render-worker.js:14-24).  fen: B records of CV_FEN_STRIDE bytes, NUL padded;
+ * fen_len: B bytes. */
+int cv_square_fen(const float* squares, const float* turn, const float* castling,
+                  const uint8_t* flipped, int B, char* fen, uint8_t* fen_len, void* stream);
+
+/* forward_u8 + fen in one call; squares/turn/castling scratch lives in the workspace. */
+int cv_square_predict_u8(cv_square* h, const uint8_t* boards, int layout, const uint8_t* flipped,
+                         int B, int H, int precision, char* fen, uint8_t* fen_len,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* End-to-end with HOST buffers (the call predict.py's user makes): boards_host -> chunked H2D on an
+ * internal copy stream overlapped with compute -> FEN records -> D2H into fen_host/fen_len_host.
+ * Blocks until the results are in host memory.  Host buffers should be pinned for full PCIe speed. */
+int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layout,
+                              const uint8_t* flipped_host, int B, int H, int precision,
+                              char* fen_host, uint8_t* fen_len_host);
+
+/* combine_type_color (models/common.py:10-24): joint[n][c] = type[n][T[c]] + color[n][C[c]]. */
+int cv_combine_type_color(const float* type_logits, const float* color_logits, int64_t n,
+                          float* joint, void* stream);
+
+/* Crop gather alone (ChessSquareCNN._crop_squares, models/square.py:43-74), NCHW fp32 output
+ * (B*64,3,64,64) like the reference, for parity tests; plus the integer source-index tables the kernel
+ * uses: y0,y1 are (8,64) int32 board rows/cols after replicate-pad clamping, lam (64) fp32 blend weights. */
+int cv_crop_squares_f32(const float* x_nchw, int B, int H, float* crops_nchw, void* stream);
+int cv_crop_squares_u8(const uint8_t* boards, int layout, int B, int H, float* crops_nchw, void* stream);
+int cv_crop_index_table(int H, int32_t* y0_host, int32_t* y1_host, float* lam_host);   /* HOST outputs, no GPU */
+
+/* Debug tap: after layer `layer` (0..44) of the NEXT forward, its output activation of the first wave is
+ * converted to fp32 NHWC and copied to `dst` (capacity n_floats).  layer < 0 clears the tap. */
+int cv_square_set_tap(cv_square* h, int layer, float* dst, size_t n_floats);
+
+/* Counter-based synthetic boards keyed by (seed, first_board + i), bit-identical to
+ * chess_vision_b200/synthetic.py.  flipped (B bytes) may be NULL. */
+int cv_synth_boards(uint8_t* boards, int layout, int64_t first_board, int B, int H, uint32_t seed,
+                    int dist, uint8_t* flipped, void* stream);
+
+/* Host mirrors used by the no-GPU tests (they run the same inline code as the kernels):
+ * cv_synth_boards_host fills HOST memory; cv_fen_from_classes_host encodes 64 class indices + turn/castling
+ * logits into one NUL-padded CV_FEN_STRIDE record and returns its length (or a negative cv_status). */
+int cv_synth_boards_host(uint8_t* boards_host, int layout, int64_t first_board, int B, int H, uint32_t seed,
+                         int dist, uint8_t* flipped_host);
+int cv_fen_from_classes_host(const int8_t* classes, float turn, const float* castling, char* rec80);
+
+/* Number of kernels this library has launched on behalf of `h` since creation (bench bookkeeping). */
+int64_t cv_square_launch_count(const cv_square* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHESSVISION_B200_H */
