@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the ChessSquareCNN inference hot path: boards/sec (FEN predictions/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # B200-native arm (this repo)
+    python bench.py --impl reference --steps K --warmup W     # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): ChessSquareCNN bf16 inference, 4096 synthetic 256x256 boards per step
+per GPU, with FEN string output.  One "step" = one pass of the hot path (crop gather -> trunk -> heads ->
+FEN records) over one batch.  `value` is timed with the uint8 boards already resident in HBM; `e2e` is the
+same metric through the host-buffer entry point (pinned host boards -> H2D -> path -> FEN records D2H).
+Multi-GPU: one process per GPU (torchrun), pure data parallel, weights broadcast once over NCCL, no
+per-batch collective; per-GPU work is fixed (weak scaling); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "boards/sec (FEN predictions/sec)"
+UNIT = "boards/s"
+WORKLOAD = "ChessSquareCNN bf16 inference, batch 4096 synthetic 256x256 boards per GPU, FEN string output (BASELINE.json configs[1])"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU side: the oracle port of the reference's path (reference python cannot travel to the GPU box)
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_run(state, boards_u8, steps, warmup):
+    """Times oracle.forward + FEN strings (fp32, all host threads) on `boards_u8` per step."""
+    from oracle import square_oracle as oracle
+    torch.set_num_threads(os.cpu_count())
+    times = []
+    fens = None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = oracle.forward(oracle.normalize_u8(boards_u8), state)
+            fens = oracle.fen_strings(out["squares"].numpy(), out["turn"].numpy(), out["castling"].numpy())
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, fens
+
+
+def make_state(model_state_template, calibrate_with=None):
+    from chess_vision_b200 import synthetic
+    return synthetic.init_state_dict(model_state_template, 0)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port, kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import chess_vision_b200 as cv
+    from chess_vision_b200 import synthetic
+    model = cv.build_model({"model": {"arch": "square", "pretrained": False}})
+    state = make_state(model.state_dict())
+    sample = args.cpu_sample
+    boards = synthetic.synth_boards(0, sample, args.size, 1, synthetic.DIST_STRUCTURED)
+    times, fens = cpu_reference_run(state, boards, args.steps, max(args.warmup, 1))
+    total = sum(times)
+    value = sample * len(times) / total
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "boards_per_step": sample, "board_size": args.size,
+                   "note": "CPU reference arm: each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} structured {args.size}x{args.size} boards per step, fp32, torch {torch.__version__} CPU, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "sample_fen": fens[0],
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------------
+def layer_bytes(layer, es):
+    """Algorithmic HBM bytes per CROP of one layer-granular kernel: input + output (+ residual) activations."""
+    b = (layer.in_elems + layer.out_elems) * es
+    if layer.skip >= 0:
+        b += layer.out_elems * es
+    return b
+
+
+def run_native(args):
+    import torch.distributed as dist
+    import chess_vision_b200 as cv
+    from chess_vision_b200 import _native, arch, replicas, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, H = args.batch, args.size
+    prec = args.precision
+
+    # ---- model: rank 0 owns the state_dict, packs once, broadcasts the blob over NCCL ------------------
+    model = cv.build_model({"model": {"arch": "square", "pretrained": False, "precision": prec}})
+    state = make_state(model.state_dict())
+    if rank == 0:
+        model.load_state_dict(state, strict=True)
+    model = model.to(dev).eval()
+    if args.wave:
+        model.set_wave(args.wave)
+    blob = replicas.broadcast_packed_weights(model if rank == 0 else None, src=0, device=dev)
+    model.load_packed_blob(blob)
+    weights_agree = replicas.all_ranks_agree(replicas.blob_checksum(blob))
+
+    # ---- inputs: this rank's shard of the global board stream, generated on the device ---------------
+    lo = rank * B                                             # weak scaling: B boards per rank per step
+    L = _native.lib()
+    boards = torch.empty((B, H, H, 3), dtype=torch.uint8, device=dev)
+    dist_kind = synthetic.DIST_STRUCTURED
+    _native.check(L.cv_synth_boards(_native.ptr(boards), 0, lo, B, H, 1, dist_kind, None, _native.stream_ptr(dev)))
+    host_boards = torch.empty((B, H, H, 3), dtype=torch.uint8).pin_memory()
+    host_boards.copy_(boards)
+    host_out = (torch.empty((B, _native.FEN_STRIDE), dtype=torch.uint8).pin_memory(),
+                torch.empty((B,), dtype=torch.uint8).pin_memory())
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (value) -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        fen, fen_len = model.predict_fen_device(boards)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = model.launch_count()
+    model.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        fen, fen_len = model.predict_fen_device(boards)
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    prof_ms, prof_cnt = model.profile_read()
+    model.profile(False)
+    launches = model.launch_count() - launches0
+    clocks = sampler.stop()
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the host-buffer entry point (e2e) ----------------------------------------
+    for _ in range(2):
+        model.predict_fen_host(host_boards, out=host_out)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        model.predict_fen_host(host_boards, out=host_out)      # blocks until FEN records are in host memory
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))              # events bracket the host-blocking calls
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    fens_host = model.decode_fen_records(host_out[0][:4], host_out[1][:4])
+    fens_dev = model.decode_fen_records(fen[:4], fen_len[:4])
+    same = fens_host == fens_dev
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------------
+    peaks = measured_peaks()
+    es = 2 if prec == "bf16" else 4
+    names = model.PROF_NAMES
+    top = int(np.argmax(prof_ms))
+    per_launch_ms = prof_ms[top] / max(prof_cnt[top], 1)
+    crops_per_launch = 64.0 * B * args.steps / max(prof_cnt[top], 1)
+    if 1 <= top <= 45:
+        layer = arch.LAYERS[top - 1]
+        alg_bytes = layer_bytes(layer, es) * crops_per_launch
+        alg_flops = 2.0 * layer.macs * crops_per_launch
+    elif top == 0:
+        alg_bytes = (H * H * 3 / 64.0 + 64 * 64 * 3 * es) * crops_per_launch
+        alg_flops = 0.0
+    else:
+        alg_bytes = (4 * 480 * es + 480 * 4 + 13 * 4) * crops_per_launch
+        alg_flops = 0.0
+    achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                "launch_ms": per_launch_ms, "share_of_step": float(prof_ms[top] / prof_ms.sum()),
+                "tflops": alg_flops / (per_launch_ms / 1e3) / 1e12,
+                "end_to_end_tensor_frac": value / world * 627.4e6 / (peaks["bf16_tflops_sustained"] * 1e12),
+                "end_to_end_hbm_frac": value / world * 196688.0 / (peaks["hbm_gbs"] * 1e9)}
+    order = np.argsort(-prof_ms)[:8]
+    breakdown = [{"kernel": names[i], "ms_per_step": float(prof_ms[i] / args.steps), "launches_per_step": int(prof_cnt[i] // args.steps)}
+                 for i in order]
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample
+        cb = synthetic.synth_boards(0, sample, H, 1, dist_kind)
+        times, cpu_fens = cpu_reference_run(state, cb, 3, 1)
+        cores = os.cpu_count()
+        v = sample / min(times)
+        gpu_fens32 = model.predict_fen(boards[:sample], precision="fp32")
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{sample} of the {B} boards, best of 3 after 1 warm-up, fp32, torch CPU {cores} threads",
+               "fen_agreement_fp32_vs_cpu": float(np.mean([a == b for a, b in zip(gpu_fens32, cpu_fens)]))}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": prec, "data": "synthetic",
+        "config": {"workload": WORKLOAD, "boards_per_step_per_gpu": B, "board_size": H, "precision": prec,
+                   "l2": f"inputs {B * H * H * 3 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
+                   "parallelism": f"dp{world} replicas, weights broadcast once (NCCL), no per-batch collective",
+                   "weights": "random-init (seed 0), BatchNorm statistics perturbed", "boards": "structured synthetic, seed 1"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 3),
+                "d2h_bytes_per_step": int(world * B * (_native.FEN_STRIDE + 1)), "ms_per_step": e2e_ms / args.steps,
+                "host_equals_device_fen": bool(same)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "kernel_breakdown": breakdown, "weights_agree_across_ranks": bool(weights_agree), "sample_fen": fens_dev[0],
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="boards per step per GPU")
+    ap.add_argument("--size", type=int, default=256, help="board side in pixels")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--wave", type=int, default=0, help="boards per internal wave (0 = library default)")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="boards per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_native(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

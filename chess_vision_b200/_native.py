@@ -70,6 +70,8 @@ def lib():
     _sig(L.cv_synth_boards_host, i32, vp, i32, i64, i32, i32, u32, i32, vp)
     _sig(L.cv_fen_from_classes_host, i32, vp, C.c_float, vp, vp)
     _sig(L.cv_square_launch_count, i64, vp)
+    _sig(L.cv_square_profile, i32, vp, i32)
+    _sig(L.cv_square_profile_read, i32, vp, vp, vp)
     if L.cv_abi_version() != 1:
         raise NativeError("libchessvision_b200.so ABI version mismatch")
     _lib = L

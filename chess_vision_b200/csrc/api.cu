@@ -42,6 +42,9 @@ struct cv_square {
     float* tap_dst = nullptr;
     size_t tap_n = 0;
     int64_t launches = 0;
+    bool profiling = false;                 // CUDA-event marks before every launch (cv_square_profile)
+    std::vector<cudaEvent_t> prof_pool;
+    std::vector<int> prof_slot;             // slot of the launch that FOLLOWS mark i (-1 = end of a call)
     int out_buf[CV_NUM_LAYERS];   // small-buffer index each layer writes (-1: dedicated stem buffer)
     // host-pointer pipeline resources (lazily created)
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
@@ -75,6 +78,20 @@ void plan_buffers(cv_square* h) {
         h->out_buf[i] = pick;                                           // never -1: 4 buffers suffice (checked at create)
         if (pick >= 0) owner[pick] = i;
     }
+}
+
+// Profiling mark: an event recorded on the launch stream right before the kernel(s) of `slot`.
+inline int prof_mark(cv_square* h, int slot, cudaStream_t s) {
+    if (!h->profiling) return CV_OK;
+    size_t i = h->prof_slot.size();
+    if (i >= h->prof_pool.size()) {
+        cudaEvent_t e;
+        CV_CUDA(cudaEventCreate(&e));
+        h->prof_pool.push_back(e);
+    }
+    CV_CUDA(cudaEventRecord(h->prof_pool[i], s));
+    h->prof_slot.push_back(slot);
+    return CV_OK;
 }
 
 struct WavePlan {
@@ -119,7 +136,8 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
         T* out = buf_of(i);
         const float* w = h->blob + L.w_offset;
         const float* b = h->blob + L.b_offset;
-        int rc;
+        int rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
+        if (rc) return rc;
         if (L.kind == CV_KIND_DEPTHWISE) rc = launch_depthwise_generic<T>(L, in, w, b, out, n, s);
         else rc = launch_conv_generic<T>(L, in, w, b, L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, s);
         if (rc) return rc;
@@ -130,7 +148,11 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
             if (rc) return rc;
         }
     }
-    int rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, s);
+    int rc = prof_mark(h, CV_PROF_POOL_HEADS, s);
+    if (rc) return rc;
+    rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, s);
+    if (rc) return rc;
+    rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
     if (rc) return rc;
     rc = launch_global_head(feat, h->glob_wt, h->head_w + 4800 + 16, h->head_w + 4800 + 16 + 64, h->head_w + 4800 + 16 + 64 + 320,
                             nb, turn, castling, s);
@@ -155,6 +177,8 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
     for (int b0 = 0; b0 < B; b0 += p.wave) {
         const int nb = std::min(p.wave, B - b0);
+        rc = prof_mark(h, CV_PROF_CROP, s);
+        if (rc) return rc;
         if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
         else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
         if (rc) return rc;
@@ -163,7 +187,7 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                          features ? features + (size_t)b0 * 64 * 480 : nullptr, b0 == 0, s);
         if (rc) return rc;
     }
-    return CV_OK;
+    return prof_mark(h, -1, s);
 }
 
 int check_forward_args(const cv_square* h, const void* x, int B, int H, int precision, const void* squares,
@@ -244,6 +268,7 @@ int cv_square_destroy(cv_square* h) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     }
+    for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->own_ws) cudaFree(h->own_ws);
     if (h->dev_fen) cudaFree(h->dev_fen);
     if (h->dev_fen_len) cudaFree(h->dev_fen_len);
@@ -338,10 +363,12 @@ int cv_square_predict_u8(cv_square* h, const uint8_t* boards, int layout, const 
     float* ca = reinterpret_cast<float*>(w + p.off_cast);
     int rc = cv_square_forward_u8(h, boards, layout, B, H, precision, sq, tu, ca, nullptr, ws, ws_bytes, stream);
     if (rc) return rc;
+    rc = prof_mark(h, CV_PROF_FEN, static_cast<cudaStream_t>(stream));
+    if (rc) return rc;
     rc = launch_fen(sq, tu, ca, flipped, B, fen, fen_len, static_cast<cudaStream_t>(stream));
     if (rc) return rc;
     ++h->launches;
-    return CV_OK;
+    return prof_mark(h, -1, static_cast<cudaStream_t>(stream));
 }
 
 // Host-buffer end-to-end: chunks of `chunk` boards are copied H2D on a copy stream into one of two staging
@@ -480,6 +507,30 @@ int cv_synth_boards(uint8_t* boards, int layout, int64_t first_board, int B, int
     CV_ARG(layout == CV_LAYOUT_HWC || layout == CV_LAYOUT_CHW, "bad layout");
     CV_ARG(dist == CV_DIST_UNIFORM || dist == CV_DIST_STRUCTURED, "bad distribution");
     return launch_synth(boards, layout, first_board, B, H, seed, dist, flipped, static_cast<cudaStream_t>(stream));
+}
+
+int cv_square_profile(cv_square* h, int enable) {
+    CV_ARG(h != nullptr, "null handle");
+    h->profiling = enable != 0;
+    h->prof_slot.clear();
+    return CV_OK;
+}
+
+int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts) {
+    CV_ARG(h && ms && counts, "null argument");
+    CV_CUDA(cudaSetDevice(h->device));
+    CV_CUDA(cudaDeviceSynchronize());
+    for (int i = 0; i < CV_PROF_SLOTS; ++i) { ms[i] = 0.0; counts[i] = 0; }
+    for (size_t i = 0; i + 1 < h->prof_slot.size(); ++i) {
+        int slot = h->prof_slot[i];
+        if (slot < 0) continue;
+        float t = 0.f;
+        CV_CUDA(cudaEventElapsedTime(&t, h->prof_pool[i], h->prof_pool[i + 1]));
+        ms[slot] += t;
+        ++counts[slot];
+    }
+    h->prof_slot.clear();
+    return CV_OK;
 }
 
 int64_t cv_square_launch_count(const cv_square* h) { return h ? h->launches : 0; }

@@ -267,6 +267,22 @@ class ChessSquareCNN(nn.Module):
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_native.lib().cv_square_launch_count(self._handle))
 
+    PROF_SLOTS = 49
+    PROF_NAMES = ["crop_gather"] + [f"L{l.index}:{l.key}" for l in arch.LAYERS] + ["pool_heads", "global_head", "fen"]
+
+    def profile(self, enable: bool):
+        """Record a CUDA event before every kernel of the path (``cv_square_profile``)."""
+        dev = self._device()
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().cv_square_profile(self._ensure_handle(dev), int(enable)))
+
+    def profile_read(self):
+        """-> (ms[49], launches[49]) summed since the last read; synchronises the device."""
+        ms = np.zeros(self.PROF_SLOTS, np.float64)
+        cnt = np.zeros(self.PROF_SLOTS, np.int64)
+        _native.check(_native.lib().cv_square_profile_read(self._handle, ms.ctypes.data, cnt.ctypes.data))
+        return ms, cnt
+
     def tap_layer(self, x, layer: int, precision=None):
         """Debug: run ``forward`` and return layer ``layer``'s output activation (N,h,w,C) fp32 NHWC for the
         first wave of crops (parity tests against the oracle's intermediate activations)."""

@@ -143,6 +143,15 @@ int cv_synth_boards_host(uint8_t* boards_host, int layout, int64_t first_board, 
                          int dist, uint8_t* flipped_host);
 int cv_fen_from_classes_host(const int8_t* classes, float turn, const float* castling, char* rec80);
 
+/* Per-kernel timing: while enabled, a CUDA event is recorded on the launch stream before every kernel of the
+ * path.  cv_square_profile_read synchronises the device and returns, per slot, the summed milliseconds and the
+ * number of launches since the last read: slot CV_PROF_CROP, CV_PROF_LAYER0 + layer (0..44),
+ * CV_PROF_POOL_HEADS, CV_PROF_GLOBAL_HEAD, CV_PROF_FEN.  ms/counts: HOST arrays of CV_PROF_SLOTS. */
+enum { CV_PROF_CROP = 0, CV_PROF_LAYER0 = 1, CV_PROF_POOL_HEADS = 46, CV_PROF_GLOBAL_HEAD = 47, CV_PROF_FEN = 48,
+       CV_PROF_SLOTS = 49 };
+int cv_square_profile(cv_square* h, int enable);
+int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts);
+
 /* Number of kernels this library has launched on behalf of `h` since creation (bench bookkeeping). */
 int64_t cv_square_launch_count(const cv_square* h);
 

@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle and the reference's golden outputs.
+
+Bars (BASELINE.json north_star): crop indices and FEN strings bit-exact; logits within 1e-5 (fp32 mode) and
+1e-2 (bf16 mode) of the reference, measured as max|delta| / max|reference|.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from chess_vision_b200 import _native, arch, dataset, synthetic
+from chess_vision_b200.models.common import combine_type_color
+from chess_vision_b200.predict import fen_from_outputs
+from oracle import square_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5          # north_star: "1e-5 in fp32"
+BF16_TOL = 1e-2          # north_star: "1e-2 relative in bf16"
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def boards_u8(H, n, seed=1, first=0, dist=synthetic.DIST_STRUCTURED):
+    return synthetic.synth_boards(first, n, H, seed, dist)
+
+
+# ------------------------------------------------------------------------------------------ synthetic
+@pytest.mark.parametrize("H,dist,layout", [(256, 1, 0), (256, 0, 1), (512, 1, 0), (64, 1, 1)])
+def test_synth_device_bit_exact(H, dist, layout):
+    n, first = 3, 2**33 + 5
+    shape = (n, H, H, 3) if layout == 0 else (n, 3, H, H)
+    dev = torch.empty(shape, dtype=torch.uint8, device="cuda")
+    fl = torch.empty(n, dtype=torch.uint8, device="cuda")
+    _native.check(_native.lib().cv_synth_boards(_native.ptr(dev), layout, first, n, H, 9, dist, _native.ptr(fl),
+                                                _native.stream_ptr(dev.device)))
+    assert np.array_equal(dev.cpu().numpy(), synthetic.synth_boards(first, n, H, 9, dist, layout))
+    assert np.array_equal(fl.cpu().numpy(), synthetic.synth_flipped(first, n, 9))
+
+
+# ------------------------------------------------------------------------------------------ crop stage
+@pytest.mark.parametrize("H", [256, 512, 64])
+def test_crop_gather_bit_exact(H):
+    L = _native.lib()
+    u8 = boards_u8(H, 2)
+    x = oracle.normalize_u8(u8)
+    want = oracle.crop_squares(x).numpy()
+    xd = x.cuda()
+    got = torch.empty((128, 3, 64, 64), dtype=torch.float32, device="cuda")
+    _native.check(L.cv_crop_squares_f32(_native.ptr(xd), 2, H, _native.ptr(got), _native.stream_ptr(xd.device)))
+    assert np.array_equal(got.cpu().numpy(), want), "fp32 crop gather must be bit-identical to the oracle"
+    for layout, arr in ((0, u8), (1, np.ascontiguousarray(u8.transpose(0, 3, 1, 2)))):
+        bd = torch.from_numpy(arr).cuda()
+        got8 = torch.empty_like(got)
+        _native.check(L.cv_crop_squares_u8(_native.ptr(bd), layout, 2, H, _native.ptr(got8), _native.stream_ptr(bd.device)))
+        assert np.array_equal(got8.cpu().numpy(), want), "fused uint8 normalise+crop must equal transform-then-crop"
+
+
+def test_crop_matches_reference_golden(golden):
+    arrays, meta = golden
+    L = _native.lib()
+    for H, n in ((256, 2), (512, 1)):
+        bd = torch.from_numpy(boards_u8(H, n, meta["board_seed"])).cuda()
+        got = torch.empty((n * 64, 3, 64, 64), dtype=torch.float32, device="cuda")
+        _native.check(L.cv_crop_squares_u8(_native.ptr(bd), 0, n, H, _native.ptr(got), _native.stream_ptr(bd.device)))
+        g = got.cpu().numpy()
+        np.testing.assert_allclose(g[[0, 7, 27, 63]], arrays[f"crops{H}_sample"], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(g.astype(np.float64).sum(axis=(1, 2, 3)), arrays[f"crops{H}_sum"], rtol=0, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------ per layer
+def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
+    x = oracle.normalize_u8(boards_u8(256, 2))
+    taps = {}
+    oracle.forward(x, gold_state, taps=taps)
+    xd = x.cuda()
+    worst = 0.0
+    for l in arch.LAYERS:
+        got = gpu_model.tap_layer(xd, l.index, precision="fp32").cpu().numpy()          # (N,h,w,C)
+        ref = taps[l.key].permute(0, 2, 3, 1).numpy()
+        assert got.shape == ref.shape, l.key
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        assert e < FP32_TOL, f"layer {l.index} {l.key}: rel err {e:.3e}"
+    print(f"worst per-layer fp32 rel err {worst:.3e}")
+
+
+def test_every_layer_matches_oracle_bf16(gpu_model, gold_state):
+    x = oracle.normalize_u8(boards_u8(256, 2))
+    taps = {}
+    oracle.forward(x, gold_state, taps=taps)
+    xd = x.cuda()
+    for l in arch.LAYERS:
+        got = gpu_model.tap_layer(xd, l.index, precision="bf16").cpu().numpy()
+        ref = taps[l.key].permute(0, 2, 3, 1).numpy()
+        e = rel_err(got, ref)
+        assert e < 3e-2, f"layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 storage, 45 layers deep
+
+
+# ------------------------------------------------------------------------------------------ full forward
+@pytest.mark.parametrize("H,n", [(256, 8), (512, 2)])
+def test_forward_fp32_matches_reference(gpu_model, golden, gold_state, H, n):
+    arrays, meta = golden
+    u8 = boards_u8(H, n, meta["board_seed"])
+    x = oracle.normalize_u8(u8)
+    out = gpu_model(x.cuda(), precision="fp32", return_features=True)
+    ref = oracle.forward(x, gold_state, return_features=True)
+    for k in ("squares", "turn", "castling", "features"):
+        assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32
+        assert rel_err(out[k].cpu().numpy(), ref[k].numpy()) < FP32_TOL, k
+    for k in ("squares", "turn", "castling"):
+        assert rel_err(out[k].cpu().numpy(), arrays[f"{k}{H}"]) < FP32_TOL, k        # the reference itself
+    assert fen_from_outputs(out) == meta[f"fen{H}"]                                  # 100 % FEN agreement
+    out8 = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="fp32")
+    for k in ("squares", "turn", "castling"):
+        assert torch.equal(out8[k], out[k]), "uint8 fused path must equal the float path bit for bit"
+    chw = torch.from_numpy(np.ascontiguousarray(u8.transpose(0, 3, 1, 2))).cuda()
+    assert torch.equal(gpu_model.forward_u8(chw, layout="chw", precision="fp32")["squares"], out["squares"])
+
+
+@pytest.mark.parametrize("H,n", [(256, 8), (512, 2)])
+def test_forward_bf16_within_tolerance(gpu_model, golden, gold_state, H, n):
+    arrays, meta = golden
+    u8 = boards_u8(H, n, meta["board_seed"])
+    out = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="bf16")
+    errs = {k: rel_err(out[k].cpu().numpy(), arrays[f"{k}{H}"]) for k in ("squares", "turn", "castling")}
+    print("bf16 rel err vs reference:", errs)
+    for k, e in errs.items():
+        assert e < BF16_TOL, (k, e)
+    # FEN agreement: raw, and on squares whose fp32 top-2 margin exceeds twice the observed logit error
+    ref_sq = arrays[f"squares{H}"].reshape(-1, 13)
+    got_sq = out["squares"].cpu().numpy().reshape(-1, 13)
+    agree = ref_sq.argmax(-1) == got_sq.argmax(-1)
+    srt = np.sort(ref_sq, -1)
+    margin = srt[:, -1] - srt[:, -2]
+    max_abs = np.abs(ref_sq - got_sq).max()
+    safe = margin > 2 * max_abs
+    print(f"bf16 square agreement raw {agree.mean():.4f}, margin-filtered {agree[safe].mean():.4f} on {safe.mean():.2%}")
+    assert agree[safe].all()
+    assert agree.mean() > 0.85          # raw agreement is margin-limited (torch's own bf16 gets 0.92)
+
+
+def test_ragged_waves_and_edge_batches(gpu_model):
+    u8 = torch.from_numpy(boards_u8(256, 5)).cuda()
+    base = gpu_model.forward_u8(u8, precision="fp32")
+    gpu_model.set_wave(2)                                   # 5 boards -> waves of 2,2,1
+    try:
+        rag = gpu_model.forward_u8(u8, precision="fp32")
+        one = gpu_model.forward_u8(u8[3:4], precision="fp32")
+        empty = gpu_model.forward_u8(u8[:0], precision="fp32")
+    finally:
+        gpu_model.set_wave(0)
+    for k in ("squares", "turn", "castling"):
+        assert torch.equal(rag[k], base[k])
+        assert torch.equal(one[k], base[k][3:4])
+    assert empty["squares"].shape == (0, 832) and empty["turn"].shape == (0, 1) and empty["castling"].shape == (0, 4)
+    assert gpu_model.predict_fen(u8[:0]) == []
+
+
+def test_argument_errors(gpu_model):
+    with pytest.raises(ValueError):
+        gpu_model(torch.zeros(1, 3, 256, 128, device="cuda"))
+    with pytest.raises(_native.NativeError, match="multiple of 32"):
+        gpu_model(torch.zeros(1, 3, 100, 100, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        gpu_model(torch.zeros(1, 3, 256, 256))
+    with pytest.raises(ValueError):
+        gpu_model.forward_u8(torch.zeros(1, 256, 256, 3, device="cuda"))        # float, not uint8
+
+
+# ------------------------------------------------------------------------------------------ FEN kernel
+def test_fen_kernel_against_oracle_random_logits():
+    rng = np.random.default_rng(5)
+    B = 777
+    sq = rng.standard_normal((B, 64, 13)).astype(np.float32)
+    sq[:, :, 0] += (rng.random((B, 64)) < 0.5) * 3.0                      # plenty of empty runs
+    sq[0] = 0.0                                                           # all ties -> class 0 everywhere
+    sq[1, :, :] = 0.0; sq[1, :, 12] = 1.0
+    sq[2, 10, 3] = sq[2, 10, 9] = 50.0                                    # tie between classes 3 and 9 -> 3
+    tu = rng.standard_normal(B).astype(np.float32); tu[3] = 0.0
+    ca = rng.standard_normal((B, 4)).astype(np.float32); ca[4] = 0.0
+    fl = (rng.random(B) < 0.5).astype(np.uint8)
+    out = {"squares": torch.from_numpy(sq.reshape(B, 832)).cuda(), "turn": torch.from_numpy(tu).view(B, 1).cuda(),
+           "castling": torch.from_numpy(ca).cuda()}
+    assert fen_from_outputs(out) == oracle.fen_strings(sq, tu, ca)
+    got_f = fen_from_outputs(out, flipped=torch.from_numpy(fl))
+    assert got_f == oracle.fen_strings(sq, tu, ca, flipped=fl)
+    assert got_f[0].split()[0] == "8/8/8/8/8/8/8/8"
+    lab = [dataset.fen_to_labels(s.split()[0]).tolist() for s in fen_from_outputs(out)]
+    lab_f = [dataset.fen_to_labels(s.split()[0]).tolist() for s in got_f]
+    for a, b, f in zip(lab, lab_f, fl):
+        assert b == (a[::-1] if f else a)
+
+
+def test_fen_records_are_nul_padded(gpu_model):
+    u8 = torch.from_numpy(boards_u8(256, 3)).cuda()
+    fen, fen_len = gpu_model.predict_fen_device(u8, precision="fp32")
+    raw, lens = fen.cpu().numpy(), fen_len.cpu().numpy()
+    assert raw.shape == (3, 80)
+    for i in range(3):
+        assert 19 <= lens[i] <= 78 and not raw[i, lens[i]:].any() and raw[i, :lens[i]].all()
+
+
+def test_combine_type_color_op():
+    t = torch.randn(5, 64, 7, device="cuda"); c = torch.randn(5, 64, 3, device="cuda")
+    got = combine_type_color(t, c, None, None)
+    want = oracle.combine_type_color(t.cpu(), c.cpu())
+    assert got.shape == (5, 64, 13) and torch.equal(got.cpu(), want)
+
+
+# ------------------------------------------------------------------------------------------ predict surfaces
+def test_predict_fen_paths_agree_with_reference(gpu_model, golden):
+    _, meta = golden
+    u8 = boards_u8(256, 8, meta["board_seed"])
+    dev = gpu_model.predict_fen(torch.from_numpy(u8).cuda(), precision="fp32")
+    host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), precision="fp32")
+    assert dev == host == meta["fen256"]
+    fl = torch.from_numpy(synthetic.synth_flipped(0, 8, 1))
+    assert gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), flipped=fl, precision="fp32") == \
+        gpu_model.predict_fen(torch.from_numpy(u8).cuda(), flipped=fl, precision="fp32")
+
+
+def test_predict_from_png_like_reference(gpu_model, golden, tmp_path):
+    from PIL import Image
+    import chess_vision_b200 as cv
+    _, meta = golden
+    u8 = boards_u8(256, 2, meta["board_seed"])
+    transform = cv.get_transform("mobilenetv4_conv_small_050.e3000_r224_in1k", False, 256)
+    gpu_model.precision = "fp32"
+    try:
+        for i in range(2):
+            p = tmp_path / f"b{i}.png"
+            Image.fromarray(u8[i]).save(p)
+            assert cv.predict(gpu_model, str(p), transform, torch.device("cuda")) == meta["predict_png_fen"][i]
+    finally:
+        gpu_model.precision = "bf16"
+
+
+def test_host_pipeline_many_chunks(gpu_model):
+    n = 1100                                                   # > 2 staging chunks of 512
+    u8 = torch.from_numpy(boards_u8(64, n, dist=synthetic.DIST_UNIFORM)).pin_memory()    # 64x64 boards keep it quick
+    host = gpu_model.predict_fen(u8, precision="bf16")
+    dev = gpu_model.predict_fen(u8.cuda(), precision="bf16")
+    assert host == dev and len(host) == n
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_batch_properties_bf16(gpu_model):
+    """BASELINE.json config 2 size (4096 boards, bf16): results must not depend on how the batch is split
+    (sharding over ranks = slicing the global index range), and the flip re-index is an involution."""
+    B = 4096
+    L = _native.lib()
+    boards = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device="cuda")
+    _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 0, B, 256, 1, 1, None, _native.stream_ptr(boards.device)))
+    fen, fen_len = gpu_model.predict_fen_device(boards, precision="bf16")
+    halves = [gpu_model.predict_fen_device(boards[i:i + B // 2].clone(), precision="bf16") for i in (0, B // 2)]
+    assert torch.equal(fen, torch.cat([h[0] for h in halves])) and torch.equal(fen_len, torch.cat([h[1] for h in halves]))
+    strs = gpu_model.decode_fen_records(fen, fen_len)
+    ones = torch.ones(B, dtype=torch.uint8)
+    fl = gpu_model.predict_fen(boards, flipped=ones, precision="bf16")
+    for a, b in zip(strs[:256], fl[:256]):
+        assert dataset.fen_to_labels(b.split()[0]).tolist() == dataset.fen_to_labels(a.split()[0]).tolist()[::-1]
+        assert a.split()[1:] == b.split()[1:]
+    classes = set()
+    for s in strs[:64]:
+        classes |= set(dataset.fen_to_labels(s.split()[0]).tolist())
+    assert len(classes) >= 10                                   # non-degenerate predictions
