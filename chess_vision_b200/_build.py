@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchessvision_b200.so")
-SOURCES = ["api.cu", "kernels_generic.cu", "fen.cu", "synth.cu"]
+SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "fen.cu", "synth.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         if verbose and out:
             print(out)
     link = [_nvcc(), "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-lcuda"]
+            ]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -55,6 +55,7 @@ def lib():
     _sig(L.cv_square_load_weights, i32, vp, vp, sz, vp)
     _sig(L.cv_square_set_norm_lut, i32, vp, vp)
     _sig(L.cv_square_set_wave, i32, vp, i32)
+    _sig(L.cv_square_set_impl, i32, vp, i32)
     _sig(L.cv_square_workspace_bytes, sz, vp, i32, i32, i32)
     _sig(L.cv_square_forward_f32, i32, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp)
     _sig(L.cv_square_forward_u8, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp)

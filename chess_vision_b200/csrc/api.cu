@@ -37,6 +37,9 @@ struct cv_square {
     float* glob_wt = nullptr;     // global_head weight transposed to [30720][64] (device, owned)
     float* head_w = nullptr;      // aligned copies of the small heads: head_w[10*480], head_b[10], glob_b[64], tc_w[320], tc_b[5]
     float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
+    bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
+    int num_sms = 148;
+    int impl = CV_IMPL_DEFAULT;   // which bf16 kernels run (cv_square_set_impl)
     int wave = 0;                 // boards per wave, 0 = default per precision
     int tap_layer = -1;
     float* tap_dst = nullptr;
@@ -121,8 +124,40 @@ WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
 }
 
 template <typename T>
+int run_layer(cv_square* h, int i, const T* in, const T* skip, T* out, int64_t n, bool t8, cudaStream_t s);
+
+template <>
+int run_layer<float>(cv_square* h, int i, const float* in, const float* skip, float* out, int64_t n, bool, cudaStream_t s) {
+    const cv_layer_info& L = kLayers[i];
+    const float* w = h->blob + L.w_offset;
+    const float* b = h->blob + L.b_offset;
+    if (L.kind == CV_KIND_DEPTHWISE) return launch_depthwise_generic<float>(L, in, w, b, out, n, false, s);
+    return launch_conv_generic<float>(L, in, w, b, skip, out, n, false, false, s);
+}
+
+// bf16 mode: T8 activations everywhere except the 3-channel crops feeding the stem.
+template <>
+int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16* out, int64_t n, bool, cudaStream_t s) {
+    const cv_layer_info& L = kLayers[i];
+    const float* w = h->blob + L.w_offset;
+    const float* b = h->blob + L.b_offset;
+    const bool in_t8 = i > 0;
+    if (L.kind == CV_KIND_DEPTHWISE) {
+        if (h->impl & CV_IMPL_DEPTHWISE_VEC) return launch_depthwise_t8(L, in, w, b, out, n, s);
+        return launch_depthwise_generic<bf16>(L, in, w, b, out, n, true, s);
+    }
+    const bf16* wi = h->wimg + umma_weight_image_offset(i);
+    if (L.kind == CV_KIND_POINTWISE && (h->impl & CV_IMPL_POINTWISE_UMMA))
+        return launch_pointwise_umma(L, in, wi, b, skip, out, n, h->num_sms, s);
+    if (L.kind == CV_KIND_DENSE && (h->impl & CV_IMPL_DENSE_UMMA))
+        return launch_dense_umma(L, in, !in_t8, wi, b, out, n, h->num_sms, s);
+    return launch_conv_generic<bf16>(L, in, w, b, skip, out, n, in_t8, true, s);
+}
+
+template <typename T>
 int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* turn, float* castling,
              float* features_user, bool first_wave, cudaStream_t s) {
+    const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
     T* stem = reinterpret_cast<T*>(ws + p.off_stem);
@@ -132,25 +167,21 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     auto buf_of = [&](int layer) -> T* { return layer < 0 ? crops : (h->out_buf[layer] < 0 ? stem : small[h->out_buf[layer]]); };
     for (int i = 0; i < CV_NUM_LAYERS; ++i) {
         const cv_layer_info& L = kLayers[i];
-        const T* in = buf_of(i - 1);
         T* out = buf_of(i);
-        const float* w = h->blob + L.w_offset;
-        const float* b = h->blob + L.b_offset;
         int rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
         if (rc) return rc;
-        if (L.kind == CV_KIND_DEPTHWISE) rc = launch_depthwise_generic<T>(L, in, w, b, out, n, s);
-        else rc = launch_conv_generic<T>(L, in, w, b, L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, s);
+        rc = run_layer<T>(h, i, buf_of(i - 1), L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, t8, s);
         if (rc) return rc;
         ++h->launches;
         if (first_wave && h->tap_layer == i && h->tap_dst) {
             size_t cnt = std::min(h->tap_n, (size_t)n * L.hout * L.hout * L.cout);
-            rc = launch_to_f32<T>(out, h->tap_dst, cnt, s);
+            rc = launch_to_f32<T>(out, h->tap_dst, cnt, L.cout, t8, s);
             if (rc) return rc;
         }
     }
     int rc = prof_mark(h, CV_PROF_POOL_HEADS, s);
     if (rc) return rc;
-    rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, s);
+    rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, t8, s);
     if (rc) return rc;
     rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
     if (rc) return rc;
@@ -251,6 +282,8 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->glob_wt, (size_t)30720 * 64 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->wimg, umma_weight_image_elems() * sizeof(bf16)));
+    CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     float lut[768];
     default_lut(lut);
     CV_CUDA(cudaMemcpy(h->lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
@@ -261,7 +294,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -293,6 +326,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     CV_CUDA(cudaMemcpyAsync(h->blob, blob, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
     int rc = launch_transpose_f32(h->blob + CV_OFF_GLOB_W, h->glob_wt, 64, 30720, s);
     if (rc) return rc;
+    rc = launch_umma_prep_weights(h->blob, h->wimg, s);
+    if (rc) return rc;
     float* hw = h->head_w;
     CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 4800, h->blob + CV_OFF_HEAD_B, 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -301,6 +336,13 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     CV_CUDA(cudaMemcpyAsync(hw + 5200, h->blob + CV_OFF_TC_B, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaStreamSynchronize(s));
     h->loaded = true;
+    return CV_OK;
+}
+
+int cv_square_set_impl(cv_square* h, int mask) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_ARG(mask >= 0 && mask <= CV_IMPL_DEFAULT, "bad implementation mask");
+    h->impl = mask;
     return CV_OK;
 }
 

@@ -31,6 +31,22 @@ void cv_set_error(const char* fmt, ...);
 
 extern const cv_layer_info* cv_layers();   // the compiled-in table (arch_table.inc)
 
+// ---- activation layouts ------------------------------------------------------------------------------
+// RowMajorL: NHWC, element (pixel-row m, channel ch) at m*C + ch.                       (fp32 path, crops)
+// T8L: "tiled-K8" -- rows grouped in tiles of 128, channels in chunks of 8 (16 bytes of bf16):
+//      offset = (((m/128)*(C/8) + ch/8)*128 + m%128)*8 + ch%8.
+//      One 128-row tile of a C-channel tensor is a contiguous 128*C*2-byte block that IS the shared-memory
+//      image of a K-major, no-swizzle UMMA A operand ([C/8] core-matrix columns x [128 rows] x 16 B), so a
+//      GEMM layer loads it with ONE TMA bulk copy, and epilogues store 16-byte chunks fully coalesced.
+struct RowMajorL {
+    __host__ __device__ static inline int64_t off(int64_t m, int ch, int C) { return m * C + ch; }
+};
+struct T8L {
+    __host__ __device__ static inline int64_t off(int64_t m, int ch, int C) {
+        return ((((m >> 7) * (C >> 3) + (ch >> 3)) << 7) + (m & 127)) * 8 + (ch & 7);
+    }
+};
+
 // ---- crop geometry (models/square.py:53-55) + bilinear taps (ATen upsample_bilinear2d,
 //      align_corners=False), computed once on the host and passed by value to the kernels ----------
 struct CropGeom {
@@ -52,19 +68,19 @@ int launch_crop_u8(const uint8_t* boards, int layout, int B, int H, const CropGe
                    T* out_nhwc, float* out_nchw, cudaStream_t s);
 template <typename T>
 int launch_conv_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, const T* skip,
-                        T* out, int64_t n_crops, cudaStream_t s);
+                        T* out, int64_t n_crops, bool in_t8, bool out_t8, cudaStream_t s);
 template <typename T>
 int launch_depthwise_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, T* out,
-                             int64_t n_crops, cudaStream_t s);
+                             int64_t n_crops, bool t8, cudaStream_t s);
 template <typename T>
 int launch_pool_heads(const T* feat_map /*[N,2,2,480]*/, const float* head_w, const float* head_b,
-                      int64_t n_crops, float* features /*[N,480]*/, float* features_user, float* squares,
+                      int64_t n_crops, float* features /*[N,480]*/, float* features_user, float* squares, bool t8,
                       cudaStream_t s);
 int launch_global_head(const float* features /*[B,30720]*/, const float* glob_wt /*[30720,64]*/,
                        const float* glob_b, const float* tc_w, const float* tc_b, int B, float* turn,
                        float* castling, cudaStream_t s);
 template <typename T>
-int launch_to_f32(const T* src, float* dst, size_t n, cudaStream_t s);
+int launch_to_f32(const T* src, float* dst, size_t n, int C, bool t8, cudaStream_t s);   // -> row-major fp32
 int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r]=src[r][c]
 
 // ---- fen.cu / synth.cu ---------------------------------------------------------------------------
@@ -73,3 +89,14 @@ int launch_fen(const float* squares, const float* turn, const float* castling, c
 int launch_synth(uint8_t* boards, int layout, int64_t first_board, int B, int H, uint32_t seed, int dist,
                  uint8_t* flipped, cudaStream_t s);
 int launch_combine(const float* t, const float* c, int64_t n, float* joint, cudaStream_t s);
+
+// ---- kernels_umma.cu: bf16 tensor-core path (tcgen05 / TMEM / TMA bulk copies), T8 activations ------------
+size_t umma_weight_image_elems();                      // bf16 elements of all GEMM-layer weight images
+int64_t umma_weight_image_offset(int layer);           // element offset of a layer's image (-1: not a GEMM layer)
+int launch_umma_prep_weights(const float* blob, bf16* wimg, cudaStream_t s);
+int launch_pointwise_umma(const cv_layer_info& L, const bf16* x, const bf16* wimg, const float* bias, const bf16* skip,
+                          bf16* y, int64_t n_crops, int num_sms, cudaStream_t s);
+int launch_dense_umma(const cv_layer_info& L, const bf16* x, bool in_rowmajor3, const bf16* wimg, const float* bias,
+                      bf16* y, int64_t n_crops, int num_sms, cudaStream_t s);
+int launch_depthwise_t8(const cv_layer_info& L, const bf16* x, const float* w, const float* bias, bf16* y,
+                        int64_t n_crops, cudaStream_t s);

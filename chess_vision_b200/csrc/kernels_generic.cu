@@ -94,7 +94,7 @@ CropTaps make_taps(const CropGeom& g) {
 
 // Dense KxK / 1x1 convolution.  Thread = (output pixel, group of CO_T output channels); lanes of a warp
 // share the pixel (input loads broadcast) and read contiguous weight vectors.
-template <typename T, int CO_T>
+template <typename T, int CO_T, typename LIn, typename LOut>
 __global__ void __launch_bounds__(256)
 conv_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                     const T* __restrict__ skip, T* __restrict__ out, int64_t total, int Hin, int Hout, int Cin,
@@ -115,10 +115,10 @@ conv_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, const
         for (int kx = 0; kx < K; ++kx) {
             int ix = ox * S - pad + kx;
             if (ix < 0 || ix >= Hin) continue;
-            const T* ip = in + ((n * Hin + iy) * Hin + ix) * Cin;
+            const int64_t pin = (n * Hin + iy) * Hin + ix;
             const float* wp = w + (int64_t)((ky * K + kx) * Cin) * Cout + g * CO_T;
             for (int ci = 0; ci < Cin; ++ci) {
-                float v = ldf<T>(ip + ci);
+                float v = ldf<T>(in + LIn::off(pin, ci, Cin));
                 const float4* w4 = reinterpret_cast<const float4*>(wp + (int64_t)ci * Cout);
 #pragma unroll
                 for (int j = 0; j < CO_T / 4; ++j) {
@@ -131,19 +131,18 @@ conv_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, const
             }
         }
     }
-    T* op = out + p * Cout + g * CO_T;
-    const T* sp = skip ? skip + p * Cout + g * CO_T : nullptr;
 #pragma unroll
     for (int j = 0; j < CO_T; ++j) {
+        const int64_t o = LOut::off(p, g * CO_T + j, Cout);
         float v = acc[j] + __ldg(bias + g * CO_T + j);
         if (relu) v = fmaxf(v, 0.f);
-        if (sp) v += ldf<T>(sp + j);
-        stf<T>(op + j, v);
+        if (skip) v += ldf<T>(skip + o);
+        stf<T>(out + o, v);
     }
 }
 
 // Depthwise KxK.  Thread = (output pixel, channel), channel fastest -> coalesced.
-template <typename T>
+template <typename T, typename L>
 __global__ void __launch_bounds__(256)
 depthwise_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                          T* __restrict__ out, int64_t total, int Hin, int Hout, int C, int K, int S, int pad,
@@ -161,19 +160,19 @@ depthwise_generic_kernel(const T* __restrict__ in, const float* __restrict__ w, 
         for (int kx = 0; kx < K; ++kx) {
             int ix = ox * S - pad + kx;
             if (ix < 0 || ix >= Hin) continue;
-            acc = fmaf(ldf<T>(in + ((n * Hin + iy) * Hin + ix) * C + c), __ldg(w + (ky * K + kx) * C + c), acc);
+            acc = fmaf(ldf<T>(in + L::off((n * Hin + iy) * Hin + ix, c, C)), __ldg(w + (ky * K + kx) * C + c), acc);
         }
     }
     acc += __ldg(bias + c);
     if (relu) acc = fmaxf(acc, 0.f);
-    stf<T>(out + idx, acc);
+    stf<T>(out + L::off(p, c, C), acc);
 }
 
 __constant__ int kClassToType[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6};    // dataset.py:31
 __constant__ int kClassToColor[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};   // dataset.py:32
 
 // One warp per crop: mean over the 2x2 map, the 7+3 head dot products, type+color -> 13 joint logits.
-template <typename T>
+template <typename T, typename L>
 __global__ void __launch_bounds__(256)
 pool_heads_kernel(const T* __restrict__ fmap, const float* __restrict__ head_w, const float* __restrict__ head_b,
                   int64_t n_crops, float* __restrict__ features, float* __restrict__ features_user,
@@ -181,12 +180,12 @@ pool_heads_kernel(const T* __restrict__ fmap, const float* __restrict__ head_w, 
     int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (n >= n_crops) return;
-    const T* f = fmap + n * 4 * 480;
     float part[10];
 #pragma unroll
     for (int r = 0; r < 10; ++r) part[r] = 0.f;
     for (int c = lane; c < 480; c += 32) {
-        float m = ((ldf<T>(f + c) + ldf<T>(f + 480 + c)) + (ldf<T>(f + 960 + c) + ldf<T>(f + 1440 + c))) * 0.25f;
+        float m = ((ldf<T>(fmap + L::off(n * 4, c, 480)) + ldf<T>(fmap + L::off(n * 4 + 1, c, 480))) +
+                   (ldf<T>(fmap + L::off(n * 4 + 2, c, 480)) + ldf<T>(fmap + L::off(n * 4 + 3, c, 480)))) * 0.25f;
         features[n * 480 + c] = m;
         if (features_user) features_user[n * 480 + c] = m;
 #pragma unroll
@@ -230,11 +229,16 @@ global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
             sf[bi][kk] = (b0 + bi < B) ? feat[(int64_t)(b0 + bi) * 30720 + k0 + kk] : 0.f;
         }
         __syncthreads();
+        float part[GB];                      // two-level summation keeps the 30720-term dot product within 1e-6
+#pragma unroll
+        for (int i = 0; i < GB; ++i) part[i] = 0.f;
         for (int kk = slice; kk < GK; kk += 4) {
             float wv = __ldg(wt + (int64_t)(k0 + kk) * 64 + j);
 #pragma unroll
-            for (int i = 0; i < GB; ++i) acc[i] = fmaf(sf[i][kk], wv, acc[i]);
+            for (int i = 0; i < GB; ++i) part[i] = fmaf(sf[i][kk], wv, part[i]);
         }
+#pragma unroll
+        for (int i = 0; i < GB; ++i) acc[i] += part[i];
         __syncthreads();
     }
 #pragma unroll
@@ -257,10 +261,10 @@ global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
     }
 }
 
-template <typename T>
-__global__ void to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, size_t n) {
+template <typename T, typename L>
+__global__ void to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, size_t n, int C) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (i < n) d[i] = ldf<T>(s + i);
+    if (i < n) d[i] = ldf<T>(s + L::off((int64_t)(i / C), (int)(i % C), C));
 }
 
 __global__ void transpose_kernel(const float* __restrict__ s, float* __restrict__ d, int rows, int cols) {
@@ -322,43 +326,61 @@ int launch_crop_u8(const uint8_t* boards, int layout, int B, int H, const CropGe
     return CV_OK;
 }
 
-template <typename T>
-int launch_conv_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, const T* skip, T* out,
-                        int64_t n_crops, cudaStream_t s) {
+template <typename T, typename LIn, typename LOut>
+static int launch_conv_l(const cv_layer_info& L, const T* in, const float* w, const float* bias, const T* skip, T* out,
+                         int64_t n_crops, cudaStream_t s) {
     int pad = ((L.stride - 1) + (L.k - 1)) / 2;
     int64_t px = n_crops * L.hout * L.hout;
     if (px == 0) return CV_OK;
     if (L.cout % 16 == 0 && L.cout >= 64) {
         int64_t total = px * (L.cout / 16);
-        conv_generic_kernel<T, 16><<<blocks_for(total, 256), 256, 0, s>>>(in, w, bias, skip, out, total, L.hin, L.hout,
-                                                                         L.cin, L.cout, L.k, L.stride, pad, L.relu);
+        conv_generic_kernel<T, 16, LIn, LOut><<<blocks_for(total, 256), 256, 0, s>>>(
+            in, w, bias, skip, out, total, L.hin, L.hout, L.cin, L.cout, L.k, L.stride, pad, L.relu);
     } else {
         int64_t total = px * (L.cout / 8);
-        conv_generic_kernel<T, 8><<<blocks_for(total, 256), 256, 0, s>>>(in, w, bias, skip, out, total, L.hin, L.hout,
-                                                                        L.cin, L.cout, L.k, L.stride, pad, L.relu);
+        conv_generic_kernel<T, 8, LIn, LOut><<<blocks_for(total, 256), 256, 0, s>>>(
+            in, w, bias, skip, out, total, L.hin, L.hout, L.cin, L.cout, L.k, L.stride, pad, L.relu);
     }
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
 
 template <typename T>
+int launch_conv_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, const T* skip, T* out,
+                        int64_t n_crops, bool in_t8, bool out_t8, cudaStream_t s) {
+    if (in_t8 && out_t8) return launch_conv_l<T, T8L, T8L>(L, in, w, bias, skip, out, n_crops, s);
+    if (!in_t8 && out_t8) return launch_conv_l<T, RowMajorL, T8L>(L, in, w, bias, skip, out, n_crops, s);
+    if (!in_t8 && !out_t8) return launch_conv_l<T, RowMajorL, RowMajorL>(L, in, w, bias, skip, out, n_crops, s);
+    cv_set_error("conv_generic: T8 -> row-major is not instantiated");
+    return CV_ERR_ARG;
+}
+
+template <typename T>
 int launch_depthwise_generic(const cv_layer_info& L, const T* in, const float* w, const float* bias, T* out,
-                             int64_t n_crops, cudaStream_t s) {
+                             int64_t n_crops, bool t8, cudaStream_t s) {
     int pad = ((L.stride - 1) + (L.k - 1)) / 2;
     int64_t total = n_crops * L.hout * L.hout * L.cout;
     if (total == 0) return CV_OK;
-    depthwise_generic_kernel<T><<<blocks_for(total, 256), 256, 0, s>>>(in, w, bias, out, total, L.hin, L.hout, L.cout,
-                                                                      L.k, L.stride, pad, L.relu);
+    if (t8)
+        depthwise_generic_kernel<T, T8L><<<blocks_for(total, 256), 256, 0, s>>>(in, w, bias, out, total, L.hin, L.hout,
+                                                                               L.cout, L.k, L.stride, pad, L.relu);
+    else
+        depthwise_generic_kernel<T, RowMajorL><<<blocks_for(total, 256), 256, 0, s>>>(in, w, bias, out, total, L.hin, L.hout,
+                                                                                     L.cout, L.k, L.stride, pad, L.relu);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
 
 template <typename T>
 int launch_pool_heads(const T* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features,
-                      float* features_user, float* squares, cudaStream_t s) {
+                      float* features_user, float* squares, bool t8, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
-    pool_heads_kernel<T><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features, features_user,
-                                                               squares);
+    if (t8)
+        pool_heads_kernel<T, T8L><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features,
+                                                                        features_user, squares);
+    else
+        pool_heads_kernel<T, RowMajorL><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features,
+                                                                              features_user, squares);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
@@ -372,9 +394,10 @@ int launch_global_head(const float* features, const float* glob_wt, const float*
 }
 
 template <typename T>
-int launch_to_f32(const T* src, float* dst, size_t n, cudaStream_t s) {
+int launch_to_f32(const T* src, float* dst, size_t n, int C, bool t8, cudaStream_t s) {
     if (n == 0) return CV_OK;
-    to_f32_kernel<T><<<blocks_for((int64_t)n, 256), 256, 0, s>>>(src, dst, n);
+    if (t8) to_f32_kernel<T, T8L><<<blocks_for((int64_t)n, 256), 256, 0, s>>>(src, dst, n, C);
+    else to_f32_kernel<T, RowMajorL><<<blocks_for((int64_t)n, 256), 256, 0, s>>>(src, dst, n, C);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
@@ -391,11 +414,11 @@ int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaS
     template int launch_crop_u8<T>(const uint8_t*, int, int, int, const CropGeom&, const float*, T*, float*,       \
                                    cudaStream_t);                                                                   \
     template int launch_conv_generic<T>(const cv_layer_info&, const T*, const float*, const float*, const T*, T*,  \
-                                        int64_t, cudaStream_t);                                                     \
+                                        int64_t, bool, bool, cudaStream_t);                                         \
     template int launch_depthwise_generic<T>(const cv_layer_info&, const T*, const float*, const float*, T*,       \
-                                             int64_t, cudaStream_t);                                                \
-    template int launch_pool_heads<T>(const T*, const float*, const float*, int64_t, float*, float*, float*,       \
+                                             int64_t, bool, cudaStream_t);                                          \
+    template int launch_pool_heads<T>(const T*, const float*, const float*, int64_t, float*, float*, float*, bool, \
                                       cudaStream_t);                                                                \
-    template int launch_to_f32<T>(const T*, float*, size_t, cudaStream_t);
+    template int launch_to_f32<T>(const T*, float*, size_t, int, bool, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(bf16)

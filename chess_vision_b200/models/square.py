@@ -75,6 +75,15 @@ class ChessSquareCNN(nn.Module):
         if self._handle is not None:
             _native.check(_native.lib().cv_square_set_wave(self._handle, self._wave))
 
+    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_DEFAULT = 1, 2, 4, 7
+
+    def set_impl(self, mask: int):
+        """Select the bf16 kernels (``cv_square_set_impl``); clearing a bit falls back to the plain CUDA-core
+        kernel of that layer class (cross-checks only)."""
+        dev = self._device()
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().cv_square_set_impl(self._ensure_handle(dev), int(mask)))
+
     def _device(self) -> torch.device:
         dev = self.turn_head.weight.device
         if dev.type != "cuda":

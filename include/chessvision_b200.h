@@ -77,6 +77,12 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
  * 768 floats. */
 int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
 
+/* Which kernels the bf16 path runs (bit mask; default = all): the tcgen05/TMEM GEMMs for the pointwise and dense
+ * 3x3 convolutions and the 16-byte-vectorised depthwise kernel.  Clearing a bit selects the plain CUDA-core
+ * kernel for that layer class instead -- used by the parity tests to cross-check the tensor-core path. */
+enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_DEFAULT = 7 };
+int cv_square_set_impl(cv_square* h, int mask);
+
 /* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */
 int cv_square_set_wave(cv_square* h, int boards);
 

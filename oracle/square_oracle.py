@@ -165,10 +165,15 @@ def trunk_features(crops, sd, prefix="backbone.", taps=None):
 # full forward (square.py:92-114) and FEN (predict.py:27-42, dataset.py:52-70)
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def forward(x, sd, overlap=1.5, square_input=64, taps=None, return_features=False):
-    """x: (B,3,H,H) fp32 normalized.  Returns dict(squares (B,832), turn (B,1), castling (B,4))."""
+def forward(x, sd, overlap=1.5, square_input=64, taps=None, return_features=False, dtype=torch.float32):
+    """x: (B,3,H,H) fp32 normalized.  Returns dict(squares (B,832), turn (B,1), castling (B,4)).
+
+    ``dtype=torch.bfloat16`` runs the same graph the way ``model.to(torch.bfloat16)`` would in PyTorch
+    (weights, activations and the input cast to bf16): the yard-stick for the bf16 kernels' error."""
     B = x.shape[0]
-    crops = crop_squares(x.float(), overlap, square_input)
+    if dtype != torch.float32:
+        sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+    crops = crop_squares(x.float(), overlap, square_input).to(dtype)
     if taps is not None:
         taps["crops"] = crops
     feat = trunk_features(crops, sd, taps=taps)
@@ -184,11 +189,12 @@ def forward(x, sd, overlap=1.5, square_input=64, taps=None, return_features=Fals
     }
     if return_features:
         out["features"] = features
-    return out
+    return {k: v.float() for k, v in out.items()}
 
 
 def combine_type_color(type_logits, color_logits):
     """joint[c] = type[T[c]] + color[C[c]] on RAW logits (common.py:24)."""
+    type_logits, color_logits = torch.as_tensor(type_logits), torch.as_tensor(color_logits)
     t = torch.as_tensor(CLASS_TO_TYPE); c = torch.as_tensor(CLASS_TO_COLOR)
     return type_logits[..., t] + color_logits[..., c]
 
