@@ -25,6 +25,7 @@ namespace {
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
 constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128;
+constexpr int MAX_CHUNK = 4096;      // boards whose pooled features are kept for one global-head launch
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -114,7 +115,8 @@ WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
     p.off_crops = off; off = align_up(off + n * EL_CROPS * p.es);
     p.off_stem = off; off = align_up(off + n * EL_STEM * p.es);
     for (int b = 0; b < NBUF_SMALL; ++b) { p.off_small[b] = off; off = align_up(off + n * EL_SMALL * p.es); }
-    p.off_feat = off; off = align_up(off + n * 480 * sizeof(float));
+    const size_t chunk = (size_t)std::min(std::max(max_boards, 1), MAX_CHUNK);
+    p.off_feat = off; off = align_up(off + chunk * 64 * 480 * sizeof(float));
     // scratch logits for the predict entry points (whole batch)
     p.off_sq = off; off = align_up(off + (size_t)max_boards * 832 * sizeof(float));
     p.off_turn = off; off = align_up(off + (size_t)max_boards * sizeof(float));
@@ -148,22 +150,21 @@ int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16*
     }
     const bf16* wi = h->wimg + umma_weight_image_offset(i);
     if (L.kind == CV_KIND_POINTWISE && (h->impl & CV_IMPL_POINTWISE_UMMA))
-        return launch_pointwise_umma(L, in, wi, b, skip, out, n, h->num_sms, s);
+        return launch_pointwise_umma(L, in, wi, b, skip, out, n, h->num_sms, (h->impl & CV_IMPL_SPLIT_WEIGHTS) != 0, s);
     if (L.kind == CV_KIND_DENSE && (h->impl & CV_IMPL_DENSE_UMMA))
-        return launch_dense_umma(L, in, !in_t8, wi, b, out, n, h->num_sms, s);
+        return launch_dense_umma(L, in, !in_t8, wi, b, out, n, h->num_sms, (h->impl & CV_IMPL_SPLIT_WEIGHTS) != 0, s);
     return launch_conv_generic<bf16>(L, in, w, b, skip, out, n, in_t8, true, s);
 }
 
 template <typename T>
-int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* turn, float* castling,
-             float* features_user, bool first_wave, cudaStream_t s) {
+int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, bool first_wave,
+             cudaStream_t s) {
     const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
     T* stem = reinterpret_cast<T*>(ws + p.off_stem);
     T* small[NBUF_SMALL];
     for (int b = 0; b < NBUF_SMALL; ++b) small[b] = reinterpret_cast<T*>(ws + p.off_small[b]);
-    float* feat = reinterpret_cast<float*>(ws + p.off_feat);
     auto buf_of = [&](int layer) -> T* { return layer < 0 ? crops : (h->out_buf[layer] < 0 ? stem : small[h->out_buf[layer]]); };
     for (int i = 0; i < CV_NUM_LAYERS; ++i) {
         const cv_layer_info& L = kLayers[i];
@@ -181,14 +182,9 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     }
     int rc = prof_mark(h, CV_PROF_POOL_HEADS, s);
     if (rc) return rc;
-    rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, features_user, squares, t8, s);
+    rc = launch_pool_heads<T>(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat, squares, t8, s);
     if (rc) return rc;
-    rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
-    if (rc) return rc;
-    rc = launch_global_head(feat, h->glob_wt, h->head_w + 4800 + 16, h->head_w + 4800 + 16 + 64, h->head_w + 4800 + 16 + 64 + 320,
-                            nb, turn, castling, s);
-    if (rc) return rc;
-    h->launches += 2;
+    ++h->launches;
     return CV_OK;
 }
 
@@ -206,17 +202,30 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     }
     char* ws = static_cast<char*>(workspace);
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
-    for (int b0 = 0; b0 < B; b0 += p.wave) {
-        const int nb = std::min(p.wave, B - b0);
-        rc = prof_mark(h, CV_PROF_CROP, s);
+    float* feat = reinterpret_cast<float*>(ws + p.off_feat);
+    for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {                    // chunk: one global-head launch
+        const int cb = std::min(MAX_CHUNK, B - c0);
+        for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: activations stay L2-resident
+            const int b0 = c0 + w0;
+            const int nb = std::min(p.wave, cb - w0);
+            rc = prof_mark(h, CV_PROF_CROP, s);
+            if (rc) return rc;
+            if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+            else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+            if (rc) return rc;
+            ++h->launches;
+            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, b0 == 0, s);
+            if (rc) return rc;
+        }
+        rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
         if (rc) return rc;
-        if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
-        else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+        rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0,
+                                castling + (size_t)c0 * 4, precision == CV_PRECISION_FP32, s);
         if (rc) return rc;
         ++h->launches;
-        rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, turn + b0, castling + (size_t)b0 * 4,
-                         features ? features + (size_t)b0 * 64 * 480 : nullptr, b0 == 0, s);
-        if (rc) return rc;
+        if (features)
+            CV_CUDA(cudaMemcpyAsync(features + (size_t)c0 * 30720, feat, (size_t)cb * 30720 * sizeof(float),
+                                    cudaMemcpyDeviceToDevice, s));
     }
     return prof_mark(h, -1, s);
 }
@@ -282,7 +291,7 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->glob_wt, (size_t)30720 * 64 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
-    CV_CUDA(cudaMalloc(&h->wimg, umma_weight_image_elems() * sizeof(bf16)));
+    CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     float lut[768];
     default_lut(lut);

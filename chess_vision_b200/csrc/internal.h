@@ -74,11 +74,10 @@ int launch_depthwise_generic(const cv_layer_info& L, const T* in, const float* w
                              int64_t n_crops, bool t8, cudaStream_t s);
 template <typename T>
 int launch_pool_heads(const T* feat_map /*[N,2,2,480]*/, const float* head_w, const float* head_b,
-                      int64_t n_crops, float* features /*[N,480]*/, float* features_user, float* squares, bool t8,
-                      cudaStream_t s);
+                      int64_t n_crops, float* features /*[N,480]*/, float* squares, bool t8, cudaStream_t s);
 int launch_global_head(const float* features /*[B,30720]*/, const float* glob_wt /*[30720,64]*/,
                        const float* glob_b, const float* tc_w, const float* tc_b, int B, float* turn,
-                       float* castling, cudaStream_t s);
+                       float* castling, bool exact_fp64_accumulate, cudaStream_t s);
 template <typename T>
 int launch_to_f32(const T* src, float* dst, size_t n, int C, bool t8, cudaStream_t s);   // -> row-major fp32
 int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r]=src[r][c]
@@ -95,8 +94,8 @@ size_t umma_weight_image_elems();                      // bf16 elements of all G
 int64_t umma_weight_image_offset(int layer);           // element offset of a layer's image (-1: not a GEMM layer)
 int launch_umma_prep_weights(const float* blob, bf16* wimg, cudaStream_t s);
 int launch_pointwise_umma(const cv_layer_info& L, const bf16* x, const bf16* wimg, const float* bias, const bf16* skip,
-                          bf16* y, int64_t n_crops, int num_sms, cudaStream_t s);
+                          bf16* y, int64_t n_crops, int num_sms, bool split_weights, cudaStream_t s);
 int launch_dense_umma(const cv_layer_info& L, const bf16* x, bool in_rowmajor3, const bf16* wimg, const float* bias,
-                      bf16* y, int64_t n_crops, int num_sms, cudaStream_t s);
+                      bf16* y, int64_t n_crops, int num_sms, bool split_weights, cudaStream_t s);
 int launch_depthwise_t8(const cv_layer_info& L, const bf16* x, const float* w, const float* bias, bf16* y,
                         int64_t n_crops, cudaStream_t s);

@@ -175,8 +175,7 @@ __constant__ int kClassToColor[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};   
 template <typename T, typename L>
 __global__ void __launch_bounds__(256)
 pool_heads_kernel(const T* __restrict__ fmap, const float* __restrict__ head_w, const float* __restrict__ head_b,
-                  int64_t n_crops, float* __restrict__ features, float* __restrict__ features_user,
-                  float* __restrict__ squares) {
+                  int64_t n_crops, float* __restrict__ features, float* __restrict__ squares) {
     int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (n >= n_crops) return;
@@ -187,7 +186,6 @@ pool_heads_kernel(const T* __restrict__ fmap, const float* __restrict__ head_w, 
         float m = ((ldf<T>(fmap + L::off(n * 4, c, 480)) + ldf<T>(fmap + L::off(n * 4 + 1, c, 480))) +
                    (ldf<T>(fmap + L::off(n * 4 + 2, c, 480)) + ldf<T>(fmap + L::off(n * 4 + 3, c, 480)))) * 0.25f;
         features[n * 480 + c] = m;
-        if (features_user) features_user[n * 480 + c] = m;
 #pragma unroll
         for (int r = 0; r < 10; ++r) part[r] = fmaf(m, __ldg(head_w + r * 480 + c), part[r]);
     }
@@ -209,36 +207,48 @@ pool_heads_kernel(const T* __restrict__ fmap, const float* __restrict__ head_w, 
 }
 
 // global_head Linear(30720,64)+ReLU -> turn(1)/castling(4).  Block = GB boards; 256 threads = 64 hidden
-// units x 4 K-slices; the board tile's features are staged through shared memory in K chunks.
+// units x 4 K-slices; the board tile's features are staged through shared memory in K chunks.  AccT = double
+// in the fp32 "exact" mode: the 30720-term dot products cancel heavily (bias = -W.mean), so fp32 summation order
+// alone moves the result by ~1e-5; fp64 accumulation makes this side exact to fp32 rounding.
 constexpr int GB = 8, GK = 512;
+template <typename AccT>
 __global__ void __launch_bounds__(256)
 global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt, const float* __restrict__ gb,
                    const float* __restrict__ tc_w, const float* __restrict__ tc_b, int B, float* __restrict__ turn,
                    float* __restrict__ castling) {
     __shared__ float sf[GB][GK];
-    __shared__ float red[4][GB][64];
+    __shared__ AccT red[4][GB][64];
     __shared__ float hid[GB][64];
     const int j = threadIdx.x & 63, slice = threadIdx.x >> 6;
     const int b0 = blockIdx.x * GB;
-    float acc[GB];
+    AccT acc[GB];
 #pragma unroll
-    for (int i = 0; i < GB; ++i) acc[i] = 0.f;
+    for (int i = 0; i < GB; ++i) acc[i] = 0;
     for (int k0 = 0; k0 < 30720; k0 += GK) {
-        for (int t = threadIdx.x; t < GB * GK; t += 256) {
-            int bi = t / GK, kk = t % GK;
-            sf[bi][kk] = (b0 + bi < B) ? feat[(int64_t)(b0 + bi) * 30720 + k0 + kk] : 0.f;
+        for (int t = threadIdx.x; t < GB * GK / 4; t += 256) {
+            int bi = t / (GK / 4), kk = t % (GK / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + bi < B) v = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)(b0 + bi) * 30720 + k0) + kk);
+            reinterpret_cast<float4*>(&sf[bi][0])[kk] = v;
         }
         __syncthreads();
-        float part[GB];                      // two-level summation keeps the 30720-term dot product within 1e-6
+        float part[GB];                      // two-level summation
 #pragma unroll
         for (int i = 0; i < GB; ++i) part[i] = 0.f;
         for (int kk = slice; kk < GK; kk += 4) {
             float wv = __ldg(wt + (int64_t)(k0 + kk) * 64 + j);
+            if (sizeof(AccT) == 8) {
 #pragma unroll
-            for (int i = 0; i < GB; ++i) part[i] = fmaf(sf[i][kk], wv, part[i]);
+                for (int i = 0; i < GB; ++i) acc[i] += (AccT)sf[i][kk] * (AccT)wv;
+            } else {
+#pragma unroll
+                for (int i = 0; i < GB; ++i) part[i] = fmaf(sf[i][kk], wv, part[i]);
+            }
         }
+        if (sizeof(AccT) != 8) {
 #pragma unroll
-        for (int i = 0; i < GB; ++i) acc[i] += part[i];
+            for (int i = 0; i < GB; ++i) acc[i] += part[i];
+        }
         __syncthreads();
     }
 #pragma unroll
@@ -246,17 +256,17 @@ global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
     __syncthreads();
     for (int t = threadIdx.x; t < GB * 64; t += 256) {
         int bi = t >> 6, jj = t & 63;
-        float v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) + gb[jj];
-        hid[bi][jj] = fmaxf(v, 0.f);
+        AccT v = ((red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj])) + (AccT)gb[jj];
+        hid[bi][jj] = fmaxf((float)v, 0.f);
     }
     __syncthreads();
     if (threadIdx.x < GB * 5) {
         int bi = threadIdx.x / 5, r = threadIdx.x % 5;
         if (b0 + bi < B) {
-            float v = 0.f;
-            for (int jj = 0; jj < 64; ++jj) v = fmaf(hid[bi][jj], tc_w[r * 64 + jj], v);
-            v += tc_b[r];
-            if (r == 0) turn[b0 + bi] = v; else castling[(int64_t)(b0 + bi) * 4 + (r - 1)] = v;
+            AccT v = 0;
+            for (int jj = 0; jj < 64; ++jj) v += (AccT)hid[bi][jj] * (AccT)tc_w[r * 64 + jj];
+            v += (AccT)tc_b[r];
+            if (r == 0) turn[b0 + bi] = (float)v; else castling[(int64_t)(b0 + bi) * 4 + (r - 1)] = (float)v;
         }
     }
 }
@@ -373,22 +383,24 @@ int launch_depthwise_generic(const cv_layer_info& L, const T* in, const float* w
 
 template <typename T>
 int launch_pool_heads(const T* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features,
-                      float* features_user, float* squares, bool t8, cudaStream_t s) {
+                      float* squares, bool t8, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (t8)
-        pool_heads_kernel<T, T8L><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features,
-                                                                        features_user, squares);
+        pool_heads_kernel<T, T8L><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features, squares);
     else
         pool_heads_kernel<T, RowMajorL><<<blocks_for(n_crops, 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features,
-                                                                              features_user, squares);
+                                                                              squares);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
 
 int launch_global_head(const float* features, const float* glob_wt, const float* glob_b, const float* tc_w,
-                       const float* tc_b, int B, float* turn, float* castling, cudaStream_t s) {
+                       const float* tc_b, int B, float* turn, float* castling, bool exact, cudaStream_t s) {
     if (B == 0) return CV_OK;
-    global_head_kernel<<<blocks_for(B, GB), 256, 0, s>>>(features, glob_wt, glob_b, tc_w, tc_b, B, turn, castling);
+    if (exact)
+        global_head_kernel<double><<<blocks_for(B, GB), 256, 0, s>>>(features, glob_wt, glob_b, tc_w, tc_b, B, turn, castling);
+    else
+        global_head_kernel<float><<<blocks_for(B, GB), 256, 0, s>>>(features, glob_wt, glob_b, tc_w, tc_b, B, turn, castling);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
@@ -417,7 +429,7 @@ int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaS
                                         int64_t, bool, bool, cudaStream_t);                                         \
     template int launch_depthwise_generic<T>(const cv_layer_info&, const T*, const float*, const float*, T*,       \
                                              int64_t, bool, cudaStream_t);                                          \
-    template int launch_pool_heads<T>(const T*, const float*, const float*, int64_t, float*, float*, float*, bool, \
+    template int launch_pool_heads<T>(const T*, const float*, const float*, int64_t, float*, float*, bool,         \
                                       cudaStream_t);                                                                \
     template int launch_to_f32<T>(const T*, float*, size_t, int, bool, cudaStream_t);
 INSTANTIATE(float)

@@ -33,15 +33,16 @@ struct GemmParams {
     const bf16* skip;     // T8 [M][N] or nullptr
     bf16* y;              // T8 [M][N]
     int m_tiles, K, N, relu, stages, n_split, n_tile, num_acc;
+    int w_parts;          // 1: bf16 weights; 2: W = W_hi + W_lo (two images back to back), two MMAs per k-step
     int hin, hout, cin;   // dense only
 };
 
 struct SmemPlan {
     uint32_t b_bytes, a_bytes, off_a, off_bias, off_bar, total;
 };
-__host__ __device__ inline SmemPlan plan_smem(int K, int N, int stages) {
+__host__ __device__ inline SmemPlan plan_smem(int K, int N, int stages, int w_parts) {
     SmemPlan s;
-    s.b_bytes = (uint32_t)N * K * 2;
+    s.b_bytes = (uint32_t)N * K * 2 * w_parts;
     s.a_bytes = (uint32_t)TILE_M * K * 2;
     s.off_a = (s.b_bytes + 127u) & ~127u;
     s.off_bias = s.off_a + stages * s.a_bytes;
@@ -58,7 +59,7 @@ struct Pipe {            // smem pointers shared by all roles
     uint32_t* tmem_slot;
 };
 __device__ __forceinline__ Pipe carve(uint8_t* smem, const GemmParams& p) {
-    SmemPlan s = plan_smem(p.K, p.N, p.stages);
+    SmemPlan s = plan_smem(p.K, p.N, p.stages, p.w_parts);
     Pipe q;
     q.b = smem;
     q.a = smem + s.off_a;
@@ -77,7 +78,7 @@ __device__ __forceinline__ Pipe carve(uint8_t* smem, const GemmParams& p) {
 __device__ __forceinline__ void mma_role(const GemmParams& p, const Pipe& q, uint32_t tmem_base, int lane) {
     const uint32_t idesc = make_idesc_bf16(TILE_M, p.n_tile);
     const uint32_t a_lbo = TILE_M * 16, b_lbo = (uint32_t)p.N * 16;   // byte distance between K-adjacent core matrices
-    const SmemPlan s = plan_smem(p.K, p.N, p.stages);
+    const SmemPlan s = plan_smem(p.K, p.N, p.stages, p.w_parts);
     mbar_wait(q.wbar, 0);                                             // weights landed
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
@@ -90,10 +91,13 @@ __device__ __forceinline__ void mma_role(const GemmParams& p, const Pipe& q, uin
             const uint32_t b_base = smem_u32(q.b);
             for (int nt = 0; nt < p.n_split; ++nt) {
                 const uint32_t d = tmem_base + (uint32_t)(acc * 256 + nt * p.n_tile);
+                const uint32_t part_bytes = (uint32_t)p.N * p.K * 2;
                 for (int k = 0; k < p.K / 16; ++k) {
                     const uint64_t ad = make_smem_desc(a_base + k * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t bd = make_smem_desc(b_base + k * 2 * b_lbo + nt * p.n_tile * 16, b_lbo, 128);
-                    mma_bf16_ss(d, ad, bd, idesc, k > 0 ? 1u : 0u);
+                    for (int part = 0; part < p.w_parts; ++part) {
+                        const uint64_t bd = make_smem_desc(b_base + part * part_bytes + k * 2 * b_lbo + nt * p.n_tile * 16, b_lbo, 128);
+                        mma_bf16_ss(d, ad, bd, idesc, (k | part) ? 1u : 0u);
+                    }
                 }
             }
             mma_commit(q.empty + stage);     // smem stage reusable once these MMAs have read it
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(192, 1) pointwise_umma_kernel(const __grid_con
     const Pipe q = carve(smem, p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_base = gemm_setup(p, q, warp, 5, 1);
-    const SmemPlan s = plan_smem(p.K, p.N, p.stages);
+    const SmemPlan s = plan_smem(p.K, p.N, p.stages, p.w_parts);
     if (warp == 4) {
         if (lane == 0) {
             mbar_arrive_expect_tx(q.wbar, s.b_bytes);
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(288, 1) dense_umma_kernel(const __grid_constan
     const Pipe q = carve(smem, p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_base = gemm_setup(p, q, warp, 8, 128);
-    const SmemPlan s = plan_smem(p.K, p.N, p.stages);
+    const SmemPlan s = plan_smem(p.K, p.N, p.stages, p.w_parts);
     if (warp >= 4 && warp < 8) {
         const int r = threadIdx.x - 128;
         if (r == 0) {
@@ -347,19 +351,24 @@ depthwise_t8_kernel(const bf16* __restrict__ x, const float* __restrict__ w, con
 }
 
 // =================================== weight images =============================================================
+// image element (n, k) at ((k/8)*N + n)*8 + k%8; hi image then lo image (w - bf16(w), itself rounded to bf16)
 __global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict__ img, int K, int Kpad, int N) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Kpad * N) return;
     const int kk = i & 7, n = (i >> 3) % N, chunk = (i >> 3) / N;
     const int k = chunk * 8 + kk;
-    img[i] = __float2bfloat16_rn(k < K ? w[(size_t)k * N + n] : 0.f);
+    const float v = k < K ? w[(size_t)k * N + n] : 0.f;
+    const bf16 hi = __float2bfloat16_rn(v);
+    img[i] = hi;
+    img[(size_t)Kpad * N + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 inline int gemm_k(const cv_layer_info& L) { return L.k * L.k * L.cin; }
 inline int gemm_kpad(const cv_layer_info& L) { return (gemm_k(L) + 15) / 16 * 16; }
 
-int fill_params(const cv_layer_info& L, GemmParams* p, int64_t n_crops) {
+int fill_params(const cv_layer_info& L, GemmParams* p, int64_t n_crops, bool split_weights) {
     p->K = gemm_kpad(L);
+    p->w_parts = split_weights ? 2 : 1;
     p->N = L.cout;
     p->relu = L.relu;
     const int64_t rows = n_crops * L.hout * L.hout;
@@ -369,7 +378,7 @@ int fill_params(const cv_layer_info& L, GemmParams* p, int64_t n_crops) {
     p->n_tile = p->N / p->n_split;
     if (p->n_tile % 16 != 0 || p->N % 16 != 0 || p->N > 512) { cv_set_error("umma: unsupported N=%d", p->N); return CV_ERR_ARG; }
     p->num_acc = p->N <= 256 ? 2 : 1;
-    const int a_bytes = TILE_M * p->K * 2, b_bytes = p->N * p->K * 2;
+    const int a_bytes = TILE_M * p->K * 2, b_bytes = p->N * p->K * 2 * p->w_parts;
     int stages = (SMEM_BUDGET - b_bytes - 4096) / a_bytes;
     p->stages = stages < 2 ? 2 : (stages > 6 ? 6 : stages);
     p->hin = L.hin; p->hout = L.hout; p->cin = L.cin;
@@ -391,7 +400,7 @@ int64_t umma_weight_image_offset(int layer) {
     if (layer < 0 || layer >= cv_num_layers() || L[layer].kind == CV_KIND_DEPTHWISE) return -1;
     int64_t n = 0;
     for (int i = 0; i < layer; ++i)
-        if (L[i].kind != CV_KIND_DEPTHWISE) n += (int64_t)gemm_kpad(L[i]) * L[i].cout;
+        if (L[i].kind != CV_KIND_DEPTHWISE) n += 2 * (int64_t)gemm_kpad(L[i]) * L[i].cout;    // hi + lo
     return n;          // every image size is a multiple of 8 elements -> 16-byte aligned
 }
 
@@ -407,13 +416,13 @@ int launch_umma_prep_weights(const float* blob, bf16* wimg, cudaStream_t s) {
 }
 
 int launch_pointwise_umma(const cv_layer_info& L, const bf16* x, const bf16* wimg, const float* bias, const bf16* skip,
-                          bf16* y, int64_t n_crops, int num_sms, cudaStream_t s) {
+                          bf16* y, int64_t n_crops, int num_sms, bool split_weights, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     GemmParams p{};
-    int rc = fill_params(L, &p, n_crops);
+    int rc = fill_params(L, &p, n_crops, split_weights);
     if (rc) return rc;
     p.x = x; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y;
-    const SmemPlan sp = plan_smem(p.K, p.N, p.stages);
+    const SmemPlan sp = plan_smem(p.K, p.N, p.stages, p.w_parts);
     CV_CUDA(cudaFuncSetAttribute(pointwise_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
     pointwise_umma_kernel<<<grid, 192, sp.total, s>>>(p);
@@ -422,14 +431,14 @@ int launch_pointwise_umma(const cv_layer_info& L, const bf16* x, const bf16* wim
 }
 
 int launch_dense_umma(const cv_layer_info& L, const bf16* x, bool in_rowmajor3, const bf16* wimg, const float* bias,
-                      bf16* y, int64_t n_crops, int num_sms, cudaStream_t s) {
+                      bf16* y, int64_t n_crops, int num_sms, bool split_weights, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (L.k != 3 || L.stride != 2) { cv_set_error("dense_umma: only 3x3 stride 2"); return CV_ERR_ARG; }
     GemmParams p{};
-    int rc = fill_params(L, &p, n_crops);
+    int rc = fill_params(L, &p, n_crops, split_weights);
     if (rc) return rc;
     p.x = x; p.wimg = wimg; p.bias = bias; p.skip = nullptr; p.y = y;
-    const SmemPlan sp = plan_smem(p.K, p.N, p.stages);
+    const SmemPlan sp = plan_smem(p.K, p.N, p.stages, p.w_parts);
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
 #define DENSE_LAUNCH(C8)                                                                                                   \
     {                                                                                                                      \

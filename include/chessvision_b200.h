@@ -79,8 +79,12 @@ int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
 
 /* Which kernels the bf16 path runs (bit mask; default = all): the tcgen05/TMEM GEMMs for the pointwise and dense
  * 3x3 convolutions and the 16-byte-vectorised depthwise kernel.  Clearing a bit selects the plain CUDA-core
- * kernel for that layer class instead -- used by the parity tests to cross-check the tensor-core path. */
-enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_DEFAULT = 7 };
+ * kernel for that layer class instead -- used by the parity tests to cross-check the tensor-core path.
+ * CV_IMPL_SPLIT_WEIGHTS: the GEMM weights are held as W = W_hi + W_lo (two bf16 images, resident in shared
+ * memory) and every k-step issues two MMAs, removing the weight-quantisation half of the bf16 error at no
+ * HBM cost (tensor throughput is far from the bound on this path). */
+enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_SPLIT_WEIGHTS = 8,
+       CV_IMPL_DEFAULT = 15 };
 int cv_square_set_impl(cv_square* h, int mask);
 
 /* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */

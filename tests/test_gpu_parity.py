@@ -89,10 +89,10 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("mask", [7, 0])
+@pytest.mark.parametrize("mask", [15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
-    """bf16 path, tensor-core kernels (mask 7: tcgen05 pointwise + dense GEMMs, vectorised depthwise) and the plain
-    CUDA-core kernels (mask 0) against the fp32 oracle's intermediate activations."""
+    """bf16 path: tensor-core kernels with split hi+lo weights (mask 15, the default), with plain bf16 weights
+    (mask 7), and the plain CUDA-core kernels (mask 0) against the fp32 oracle's intermediate activations."""
     x = oracle.normalize_u8(boards_u8(256, 2))
     taps = {}
     oracle.forward(x, gold_state, taps=taps)
@@ -105,7 +105,7 @@ def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
             e = rel_err(got, ref)
             assert e < 3e-2, f"mask {mask} layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 storage, 45 layers deep
     finally:
-        gpu_model.set_impl(7)
+        gpu_model.set_impl(15)
 
 
 def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
@@ -115,12 +115,11 @@ def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
     try:
         a = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
     finally:
-        gpu_model.set_impl(7)
+        gpu_model.set_impl(15)
     b = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
-    for k in ("features", "squares"):
-        e = rel_err(b[k].cpu().numpy(), a[k].cpu().numpy())
-        print(f"umma vs cuda-core bf16 {k}: {e:.3e}")
-        assert e < 3e-2, (k, e)
+    e = rel_err(b["features"].cpu().numpy(), a["features"].cpu().numpy())
+    print(f"umma vs cuda-core bf16 features: {e:.3e}")
+    assert e < 2e-2, e          # two bf16 pipelines, each ~1e-2 from the fp32 truth
 
 
 # ------------------------------------------------------------------------------------------ full forward
@@ -131,11 +130,14 @@ def test_forward_fp32_matches_reference(gpu_model, golden, gold_state, H, n):
     x = oracle.normalize_u8(u8)
     out = gpu_model(x.cuda(), precision="fp32", return_features=True)
     ref = oracle.forward(x, gold_state, return_features=True)
-    for k in ("squares", "turn", "castling", "features"):
+    errs = {k: rel_err(out[k].cpu().numpy(), ref[k].numpy()) for k in ("squares", "turn", "castling", "features")}
+    gerr = {k: rel_err(out[k].cpu().numpy(), arrays[f"{k}{H}"]) for k in ("squares", "turn", "castling")}
+    print("fp32 rel err vs oracle:", errs, "vs reference golden:", gerr)
+    for k in errs:
         assert out[k].shape == ref[k].shape and out[k].dtype == torch.float32
-        assert rel_err(out[k].cpu().numpy(), ref[k].numpy()) < FP32_TOL, k
-    for k in ("squares", "turn", "castling"):
-        assert rel_err(out[k].cpu().numpy(), arrays[f"{k}{H}"]) < FP32_TOL, k        # the reference itself
+        assert errs[k] < FP32_TOL, (k, errs[k])
+    for k in gerr:
+        assert gerr[k] < FP32_TOL, (k, gerr[k])                                       # the reference itself
     assert fen_from_outputs(out) == meta[f"fen{H}"]                                  # 100 % FEN agreement
     out8 = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="fp32")
     for k in ("squares", "turn", "castling"):

@@ -51,7 +51,7 @@ def main():
     if len(sys.argv) >= 3 and sys.argv[1] == "--child":
         child(int(sys.argv[2]), sys.argv[3])
         return
-    masks = [int(a) for a in sys.argv[1:]] or [0, 4, 5, 6, 7]
+    masks = [int(a) for a in sys.argv[1:]] or [0, 7, 15]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     results = []
     for mask in masks:
