@@ -296,6 +296,9 @@ def run_native(args):
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{sample} of the {B} boards, best of 3 after 1 warm-up, fp32, torch CPU {cores} threads",
                "fen_agreement_fp32_vs_cpu": float(np.mean([a == b for a, b in zip(gpu_fens32, cpu_fens)]))}
+        bad = [(a, b) for a, b in zip(gpu_fens32, cpu_fens) if a != b]
+        if bad:
+            cpu["fen_mismatch_example"] = {"gpu_fp32": bad[0][0], "cpu": bad[0][1]}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

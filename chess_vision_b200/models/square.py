@@ -59,6 +59,7 @@ class ChessSquareCNN(nn.Module):
         self._packed_sig = None
         self._blob_dev = None
         self._ws = None
+        self._lut = None
         self._wave = 0
 
     # ------------------------------------------------------------------ native handle / weights
@@ -91,43 +92,38 @@ class ChessSquareCNN(nn.Module):
                                "call .to('cuda') on a B200")
         return dev
 
-    def _ensure_handle(self, dev):
+    def _create_handle(self, dev):
         lib = _native.lib()
         idx = dev.index if dev.index is not None else torch.cuda.current_device()
-        if self._handle is None or self._handle_device != idx:
-            self.release()
-            h = C.c_void_p()
-            _native.check(lib.cv_square_create(idx, C.byref(h)))
-            self._handle, self._handle_device = h, idx
-            lut = weights.norm_lut()
-            _native.check(lib.cv_square_set_norm_lut(h, _native.ptr(lut)))
-            if self._wave:
-                _native.check(lib.cv_square_set_wave(h, self._wave))
+        if self._handle is not None and self._handle_device == idx:
+            return
+        self.release()
+        h = C.c_void_p()
+        _native.check(lib.cv_square_create(idx, C.byref(h)))
+        self._handle, self._handle_device = h, idx
+        self._lut = weights.norm_lut()                       # keep the host table alive across the C call
+        _native.check(lib.cv_square_set_norm_lut(h, _native.ptr(self._lut)))
+        if self._wave:
+            _native.check(lib.cv_square_set_wave(h, self._wave))
+
+    def _ensure_handle(self, dev):
+        self._create_handle(dev)
         sig = self._signature()
         if sig != self._packed_sig:
             blob = weights.pack_state_dict(self.state_dict())
             self.load_packed_blob(blob.to(dev, non_blocking=False))
-            self._packed_sig = sig
         return self._handle
 
     def load_packed_blob(self, blob_dev: torch.Tensor):
         """Install an already packed fp32 blob that lives on this model's device (e.g. received by NCCL
         broadcast, ``replicas.broadcast_packed_weights``) without re-packing from the state_dict."""
         dev = self._device()
-        lib = _native.lib()
-        if self._handle is None:
-            idx = dev.index if dev.index is not None else torch.cuda.current_device()
-            h = C.c_void_p()
-            _native.check(lib.cv_square_create(idx, C.byref(h)))
-            self._handle, self._handle_device = h, idx
-            _native.check(lib.cv_square_set_norm_lut(h, _native.ptr(weights.norm_lut())))
-            if self._wave:
-                _native.check(lib.cv_square_set_wave(h, self._wave))
+        self._create_handle(dev)
         assert blob_dev.is_cuda and blob_dev.dtype == torch.float32 and blob_dev.numel() == arch.BLOB_FLOATS
         blob_dev = blob_dev.contiguous()
         with torch.cuda.device(dev):
-            _native.check(lib.cv_square_load_weights(self._handle, _native.ptr(blob_dev), blob_dev.numel(),
-                                                     _native.stream_ptr(dev)))
+            _native.check(_native.lib().cv_square_load_weights(self._handle, _native.ptr(blob_dev), blob_dev.numel(),
+                                                               _native.stream_ptr(dev)))
         self._blob_dev = blob_dev
         self._packed_sig = self._signature()
 
@@ -234,7 +230,8 @@ class ChessSquareCNN(nn.Module):
             fl = None
             if flipped is not None:
                 fl = flipped.to(dev, torch.uint8).contiguous()
-            _native.check(lib.cv_square_predict_u8(h, _native.ptr(boards.contiguous()), lay, _native.ptr(fl), B, H, prec,
+            boards = boards.contiguous()
+            _native.check(lib.cv_square_predict_u8(h, _native.ptr(boards), lay, _native.ptr(fl), B, H, prec,
                                                    _native.ptr(fen), _native.ptr(fen_len), _native.ptr(ws), ws.numel(),
                                                    _native.stream_ptr(dev)))
         return fen, fen_len

@@ -46,11 +46,11 @@ def fen_from_outputs(outputs, flipped=None):
     fen = torch.empty((B, _native.FEN_STRIDE), dtype=torch.uint8, device=dev)
     fen_len = torch.empty((B,), dtype=torch.uint8, device=dev)
     fl = None if flipped is None else flipped.to(dev, torch.uint8).contiguous()
+    sq, tu, ca = sq.float().contiguous(), tu.float().contiguous(), ca.float().contiguous()   # keep alive across the call
     with torch.cuda.device(dev):
         _native.check(_native.lib().cv_square_fen(
-            _native.ptr(sq.float().contiguous()), _native.ptr(tu.float().contiguous()),
-            _native.ptr(ca.float().contiguous()), _native.ptr(fl), B, _native.ptr(fen), _native.ptr(fen_len),
-            _native.stream_ptr(dev)))
+            _native.ptr(sq), _native.ptr(tu), _native.ptr(ca), _native.ptr(fl), B, _native.ptr(fen),
+            _native.ptr(fen_len), _native.stream_ptr(dev)))
     raw, lens = fen.cpu().numpy(), fen_len.cpu().numpy()
     return [raw[i, :lens[i]].tobytes().decode("ascii") for i in range(B)]
 

@@ -171,7 +171,7 @@ def forward(x, sd, overlap=1.5, square_input=64, taps=None, return_features=Fals
     ``dtype=torch.bfloat16`` runs the same graph the way ``model.to(torch.bfloat16)`` would in PyTorch
     (weights, activations and the input cast to bf16): the yard-stick for the bf16 kernels' error."""
     B = x.shape[0]
-    if dtype != torch.float32:
+    if dtype != torch.float32:      # bf16: PyTorch-bf16 yard-stick; float64: "exact" evaluation of the same graph
         sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
     crops = crop_squares(x.float(), overlap, square_input).to(dtype)
     if taps is not None:
