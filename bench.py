@@ -187,6 +187,8 @@ def run_native(args):
     blob = replicas.broadcast_packed_weights(model if rank == 0 else None, src=0, device=dev)
     model.load_packed_blob(blob)
     weights_agree = replicas.all_ranks_agree(replicas.blob_checksum(blob))
+    if args.mask >= 0:
+        model.set_impl(args.mask)
 
     # ---- inputs: this rank's shard of the global board stream, generated on the device ---------------
     lo = rank * B                                             # weak scaling: B boards per rank per step
@@ -332,6 +334,7 @@ def main():
     ap.add_argument("--wave", type=int, default=0, help="boards per internal wave (0 = library default)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="boards per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mask", type=int, default=-1, help="kernel selection bit mask (cv_square_set_impl); -1 = library default")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

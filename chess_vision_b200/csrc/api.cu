@@ -39,6 +39,7 @@ struct cv_square {
     float* head_w = nullptr;      // aligned copies of the small heads: head_w[10*480], head_b[10], glob_b[64], tc_w[320], tc_b[5]
     float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
     bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
+    bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
     int num_sms = 148;
     int impl = CV_IMPL_DEFAULT;   // which bf16 kernels run (cv_square_set_impl)
     int wave = 0;                 // boards per wave, 0 = default per precision
@@ -158,7 +159,7 @@ int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16*
 
 template <typename T>
 int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, bool first_wave,
-             cudaStream_t s) {
+             int first_layer, cudaStream_t s) {
     const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
@@ -169,12 +170,15 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     for (int i = 0; i < CV_NUM_LAYERS; ++i) {
         const cv_layer_info& L = kLayers[i];
         T* out = buf_of(i);
-        int rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
-        if (rc) return rc;
-        rc = run_layer<T>(h, i, buf_of(i - 1), L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, t8, s);
-        if (rc) return rc;
-        ++h->launches;
-        if (first_wave && h->tap_layer == i && h->tap_dst) {
+        if (i >= first_layer) {
+            int rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
+            if (rc) return rc;
+            rc = run_layer<T>(h, i, buf_of(i - 1), L.skip >= 0 ? buf_of(L.skip) : nullptr, out, n, t8, s);
+            if (rc) return rc;
+            ++h->launches;
+        }
+        int rc;
+        if (i >= first_layer - 1 && first_wave && h->tap_layer == i && h->tap_dst) {
             size_t cnt = std::min(h->tap_n, (size_t)n * L.hout * L.hout * L.cout);
             rc = launch_to_f32<T>(out, h->tap_dst, cnt, L.cout, t8, s);
             if (rc) return rc;
@@ -203,18 +207,28 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     char* ws = static_cast<char*>(workspace);
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
     float* feat = reinterpret_cast<float*>(ws + p.off_feat);
+    // bf16: crop gather + conv_stem + blocks.0.0 fused in one tensor-core kernel (activations stay in smem)
+    const bool fused_front = sizeof(T) == 2 && (h->impl & CV_IMPL_FRONTEND);
+    bf16* front_out = fused_front ? reinterpret_cast<bf16*>(ws + p.off_small[h->out_buf[1]]) : nullptr;
     for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {                    // chunk: one global-head launch
         const int cb = std::min(MAX_CHUNK, B - c0);
         for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: activations stay L2-resident
             const int b0 = c0 + w0;
             const int nb = std::min(p.wave, cb - w0);
-            rc = prof_mark(h, CV_PROF_CROP, s);
+            rc = prof_mark(h, fused_front ? CV_PROF_FRONTEND : CV_PROF_CROP, s);
             if (rc) return rc;
-            if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+            if (fused_front) {
+                const void* src = x_u8 ? static_cast<const void*>(x_u8 + (size_t)b0 * H * H * 3)
+                                       : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
+                const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
+                rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset,
+                                     h->blob + kLayers[1].b_offset, front_out, h->num_sms, s);
+            } else if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
             else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
             if (rc) return rc;
             ++h->launches;
-            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, b0 == 0, s);
+            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, b0 == 0,
+                             fused_front ? 2 : 0, s);
             if (rc) return rc;
         }
         rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
@@ -292,6 +306,7 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
+    CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     float lut[768];
     default_lut(lut);
@@ -303,7 +318,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -336,6 +351,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     int rc = launch_transpose_f32(h->blob + CV_OFF_GLOB_W, h->glob_wt, 64, 30720, s);
     if (rc) return rc;
     rc = launch_umma_prep_weights(h->blob, h->wimg, s);
+    if (rc) return rc;
+    rc = launch_frontend_prep_weights(h->blob, h->fe_wimg, s);
     if (rc) return rc;
     float* hw = h->head_w;
     CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -56,7 +56,34 @@ struct CropGeom {
 };
 int cv_make_crop_geom(int H, CropGeom* g);
 
-struct NormLut { float v[3][256]; };   // (u8/255 - mean[c]) / std[c]
+// Per-axis bilinear taps in BOARD space (after replicate-pad clamping) for the 8 squares of a rank/file:
+// passed to the crop kernels by value as a __grid_constant__ parameter (2.3 KB).
+struct CropTaps {
+    int16_t p0[8][64], p1[8][64];
+    float lam[64];
+};
+inline CropTaps make_taps(const CropGeom& g) {
+    CropTaps t;
+    for (int r = 0; r < 8; ++r)
+        for (int d = 0; d < 64; ++d) {
+            int a = r * g.sq + g.i0[d] - g.pad, b = r * g.sq + g.i1[d] - g.pad;
+            a = a < 0 ? 0 : (a > g.H - 1 ? g.H - 1 : a);
+            b = b < 0 ? 0 : (b > g.H - 1 ? g.H - 1 : b);
+            t.p0[r][d] = (int16_t)a; t.p1[r][d] = (int16_t)b;
+        }
+    for (int d = 0; d < 64; ++d) t.lam[d] = g.lam[d];
+    return t;
+}
+#ifdef __CUDACC__
+// Blend order pinned to the oracle: (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11), no FMA
+// contraction, so fp32 crops are bit-identical to the CPU restatement.
+__device__ __forceinline__ float crop_blend(float v00, float v01, float v10, float v11, float lx, float ly) {
+    float wx0 = __fsub_rn(1.0f, lx), wy0 = __fsub_rn(1.0f, ly);
+    float top = __fadd_rn(__fmul_rn(wx0, v00), __fmul_rn(lx, v01));
+    float bot = __fadd_rn(__fmul_rn(wx0, v10), __fmul_rn(lx, v11));
+    return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot));
+}
+#endif
 
 // ---- generic (precision-templated) kernels: kernels_generic.cu ----------------------------------
 // All activations NHWC; T = float (CV_PRECISION_FP32) or bf16; accumulation always fp32.
@@ -99,3 +126,11 @@ int launch_dense_umma(const cv_layer_info& L, const bf16* x, bool in_rowmajor3, 
                       bf16* y, int64_t n_crops, int num_sms, bool split_weights, cudaStream_t s);
 int launch_depthwise_t8(const cv_layer_info& L, const bf16* x, const float* w, const float* bias, bf16* y,
                         int64_t n_crops, cudaStream_t s);
+
+// ---- kernels_frontend.cu: fused crop gather + conv_stem + blocks.0.0 (tcgen05), output T8 [crops*256][16] ----
+enum { CV_SRC_U8_HWC = 0, CV_SRC_U8_CHW = 1, CV_SRC_F32_NCHW = 2 };
+size_t frontend_weight_image_elems();
+int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s);
+int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev,
+                    const bf16* wimg, const float* bias_stem, const float* bias_b00, bf16* y, int num_sms,
+                    cudaStream_t s);

@@ -20,20 +20,6 @@ template <typename T> __device__ __forceinline__ void stf(T* p, float v);
 template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-struct CropTaps {          // per-axis taps in BOARD space for the 8 squares: kernel parameter (3 KB)
-    int16_t p0[8][64], p1[8][64];
-    float lam[64];
-};
-
-// Blend order pinned to the oracle: (1-ly)*((1-lx)*v00 + lx*v01) + ly*((1-lx)*v10 + lx*v11), no FMA
-// contraction, so fp32 crops are bit-identical to the CPU restatement.
-__device__ __forceinline__ float blend(float v00, float v01, float v10, float v11, float lx, float ly) {
-    float wx0 = __fsub_rn(1.0f, lx), wy0 = __fsub_rn(1.0f, ly);
-    float top = __fadd_rn(__fmul_rn(wx0, v00), __fmul_rn(lx, v01));
-    float bot = __fadd_rn(__fmul_rn(wx0, v10), __fmul_rn(lx, v11));
-    return __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot));
-}
-
 // One thread per (crop, oy, ox); 3 channels each.
 template <typename T, bool U8, bool CHW>
 __global__ void __launch_bounds__(256)
@@ -67,7 +53,7 @@ crop_kernel(const void* __restrict__ src, int64_t total, int H, const __grid_con
             v00 = pc[y0 * H + x0]; v01 = pc[y0 * H + x1];
             v10 = pc[y1 * H + x0]; v11 = pc[y1 * H + x1];
         }
-        r[c] = blend(v00, v01, v10, v11, lx, ly);
+        r[c] = crop_blend(v00, v01, v10, v11, lx, ly);
     }
     if (out_nhwc) {
         T* o = out_nhwc + idx * 3;
@@ -77,19 +63,6 @@ crop_kernel(const void* __restrict__ src, int64_t total, int H, const __grid_con
         float* o = out_nchw + n * 3 * 4096 + oy * 64 + ox;
         o[0] = r[0]; o[4096] = r[1]; o[8192] = r[2];
     }
-}
-
-CropTaps make_taps(const CropGeom& g) {
-    CropTaps t;
-    for (int r = 0; r < 8; ++r)
-        for (int d = 0; d < 64; ++d) {
-            int a = r * g.sq + g.i0[d] - g.pad, b = r * g.sq + g.i1[d] - g.pad;
-            a = a < 0 ? 0 : (a > g.H - 1 ? g.H - 1 : a);
-            b = b < 0 ? 0 : (b > g.H - 1 ? g.H - 1 : b);
-            t.p0[r][d] = (int16_t)a; t.p1[r][d] = (int16_t)b;
-        }
-    for (int d = 0; d < 64; ++d) t.lam[d] = g.lam[d];
-    return t;
 }
 
 // Dense KxK / 1x1 convolution.  Thread = (output pixel, group of CO_T output channels); lanes of a warp

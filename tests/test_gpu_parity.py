@@ -89,10 +89,12 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("mask", [15, 7, 0])
+@pytest.mark.parametrize("mask", [31, 15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
-    """bf16 path: tensor-core kernels with split hi+lo weights (mask 15, the default), with plain bf16 weights
-    (mask 7), and the plain CUDA-core kernels (mask 0) against the fp32 oracle's intermediate activations."""
+    """bf16 path: fused front end + tensor-core kernels (mask 31, the default), layer-granular tensor-core kernels
+    with split hi+lo weights (15), with plain bf16 weights (7), and the plain CUDA-core kernels (0) against the
+    fp32 oracle's intermediate activations.  With the fused front end the conv_stem output never reaches HBM, so
+    layer 0 has nothing to tap."""
     x = oracle.normalize_u8(boards_u8(256, 2))
     taps = {}
     oracle.forward(x, gold_state, taps=taps)
@@ -100,12 +102,14 @@ def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     gpu_model.set_impl(mask)
     try:
         for l in arch.LAYERS:
+            if (mask & 16) and l.index == 0:
+                continue
             got = gpu_model.tap_layer(xd, l.index, precision="bf16").cpu().numpy()
             ref = taps[l.key].permute(0, 2, 3, 1).numpy()
             e = rel_err(got, ref)
             assert e < 3e-2, f"mask {mask} layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 storage, 45 layers deep
     finally:
-        gpu_model.set_impl(15)
+        gpu_model.set_impl(31)
 
 
 def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
@@ -115,11 +119,37 @@ def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
     try:
         a = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
     finally:
-        gpu_model.set_impl(15)
+        gpu_model.set_impl(31)
     b = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
     e = rel_err(b["features"].cpu().numpy(), a["features"].cpu().numpy())
     print(f"umma vs cuda-core bf16 features: {e:.3e}")
     assert e < 2e-2, e          # two bf16 pipelines, each ~1e-2 from the fp32 truth
+
+
+@pytest.mark.parametrize("H,n", [(256, 5), (512, 3), (64, 3)])
+def test_fused_front_end_matches_layer_granular_kernels(gpu_model, gold_state, H, n):
+    """crop gather + conv_stem + blocks.0.0 in one tcgen05 kernel (bit 16) vs the three separate kernels, from
+    all three board sources (fp32 NCHW, uint8 HWC, uint8 CHW), several crops per persistent CTA (n*64 > 148)."""
+    u8 = boards_u8(H, n)
+    x = oracle.normalize_u8(u8)
+    taps = {}
+    oracle.forward(x, gold_state, taps=taps)
+    ref = taps[arch.LAYERS[1].key].permute(0, 2, 3, 1).numpy()
+    xd = x.cuda()
+    gpu_model.set_impl(15)
+    try:
+        sep = gpu_model.tap_layer(xd, 1, precision="bf16").cpu().numpy()
+    finally:
+        gpu_model.set_impl(31)
+    fused = gpu_model.tap_layer(xd, 1, precision="bf16").cpu().numpy()
+    e_f, e_s = rel_err(fused, ref), rel_err(sep, ref)
+    print(f"H={H}: blocks.0.0 output rel err fused {e_f:.3e}, layer-granular {e_s:.3e}")
+    assert e_f < 1e-2 and e_f <= 1.5 * e_s + 1e-3
+    # uint8 sources run the same kernel with the normalisation LUT fused in: identical bits
+    for layout, arr in (("hwc", u8), ("chw", np.ascontiguousarray(u8.transpose(0, 3, 1, 2)))):
+        a = gpu_model.forward_u8(torch.from_numpy(arr).cuda(), layout=layout, precision="bf16", return_features=True)
+        b = gpu_model(xd, precision="bf16", return_features=True)
+        assert torch.equal(a["features"], b["features"]), layout
 
 
 # ------------------------------------------------------------------------------------------ full forward
