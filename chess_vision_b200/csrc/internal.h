@@ -134,3 +134,13 @@ int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s);
 int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev,
                     const bf16* wimg, const float* bias_stem, const float* bias_b00, bf16* y, int num_sms,
                     cudaStream_t s);
+
+// ---- kernels_backend.cu: fused back-end stages (persistent tcgen05 kernels, activations in smem / TMEM) -----------------
+// stage D = blocks.3.* + blocks.4.0 + average pool + type/color heads + combine.  Input: "P8" tiles (128 rows = 8 crops,
+// row = pixel*8 + crop_local, 48 channels, T8 chunking); output: features [crops][480] fp32, squares [crops][13] fp32.
+enum { CV_STAGE_D_OPS = 24 };
+size_t stageD_image_bytes();
+int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
+int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, cudaStream_t s);
+int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes,
+                  float* features, float* squares, int num_sms, cudaStream_t s);

@@ -1,0 +1,567 @@
+// Fused back-end stages of the ChessSquareCNN trunk for sm_100a (timm mobilenetv4_conv_small_050 forward_features
+// as called at models/square.py:86, then global_pool + type/color heads + combine, square.py:87-104).
+//
+//   stage D ("tail")  blocks.3.0 .. blocks.3.5, blocks.4.0, 2x2 average pool, type/color heads, type+color combine:
+//                     21 conv layers + pooling + heads in ONE persistent kernel.  A CTA owns a tile of 32 crops; every
+//                     intermediate activation lives in shared memory (bf16 UMMA operand tiles) or tensor memory, only
+//                     the 1.5 KB/crop stage input is read from HBM and 1.9 KB/crop of pooled features + 13 logits are
+//                     written.  Pointwise convs are tcgen05.mma GEMMs (M = 128 rows = 32 crops x 2x2 pixels, weights
+//                     streamed L2 -> smem by TMA bulk copies one op ahead); depthwise convs run on the CUDA cores
+//                     in place on the shared-memory tile; the RESIDUAL STREAM of the inverted-bottleneck blocks never
+//                     leaves tensor memory: every pw_proj GEMM accumulates (fp32) onto the TMEM columns that hold the
+//                     block input, so skip connections cost nothing and are never rounded to bf16.
+//
+// Execution inside a CTA is op-synchronous (all 16 warps work on the same layer, __syncthreads between ops): the
+// per-layer work is dominated by CUDA-core epilogue / depthwise instructions, the MMAs are short.
+//
+// Row orders.  4x4-resolution tiles (stage input, blocks.3.0 head) are "P8": row = pixel*8 + crop_local, which makes
+// every depthwise neighbour access a contiguous, bank-conflict-free 16-byte-per-lane shared-memory read.  2x2-resolution
+// tiles are crop-major (row = crop*4 + pixel) so the 4 pixels of a crop sit in 4 adjacent lanes / TMEM lanes.
+#include "internal.h"
+#include "umma.cuh"
+#include "arch_table.inc"     // CV_OFF_* blob offsets (kLayers itself is reached through cv_layers())
+
+namespace {
+
+using namespace umma;
+
+constexpr int NT = 512;                 // 16 warps: warp w -> TMEM lane quadrant w&3, column slice w>>2
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+}
+__device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, const float* w) {
+    float x[8], ww[8];
+    unpack8(v, x);
+    load8(w, ww);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], ww[i], acc[i]);
+}
+
+// One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
+// A: shared-memory operand tile [K/8][128 rows][8] bf16 (K-major, no swizzle; LBO 2048 B, SBO 128 B).
+// B: weight image [K/8][n_total][8] bf16, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
+__device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_addr, int n_total, int n0, int n, uint32_t d_tmem,
+                                           bool accumulate) {
+    const uint32_t idesc = make_idesc_bf16(128, n);
+    const uint32_t b_lbo = (uint32_t)n_total * 16u;
+    for (int k = 0; k < K / 16; ++k) {
+        const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
+        const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 2u * b_lbo + (uint32_t)n0 * 16u, b_lbo, 128u);
+        mma_bf16_ss(d_tmem, ad, bd, idesc, (accumulate || k > 0) ? 1u : 0u);
+    }
+}
+
+// TMEM accumulator columns [col0, col0+ncols) of this thread's row -> (+bias, ReLU) -> bf16 -> operand tile
+// dst[(chunk0 + col/8)][row][8].  The 16-column groups are dealt round-robin to the 4 column-slice warps.
+template <bool RELU>
+__device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, const float* bias, uint8_t* dst, int chunk0, int row,
+                                            int cs) {
+    for (int g = cs; g < (ncols >> 4); g += 4) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[8];
+            load8(bias + g * 16 + j * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v[i] += __uint_as_float(r[8 * j + i]);
+                if (RELU) v[i] = fmaxf(v[i], 0.f);
+            }
+            *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) = pack8(v);
+        }
+    }
+}
+
+// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows (row = pix*8 + crop), 8 crops: src -> dst, both [C8][128][8].
+__device__ __forceinline__ void dw3x3_p8(const uint8_t* src, uint8_t* dst, int C8, const float* w, const float* bias, bool relu, int tid) {
+    const int C = C8 * 8;
+    for (int task = tid; task < 128 * C8; task += NT) {
+        const int c = task >> 7, r = task & 127, pix = r >> 3, y = pix >> 2, x = pix & 3;
+        float acc[8];
+        load8(bias + c * 8, acc);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = y - 1 + ky;
+            if (iy < 0 || iy > 3) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = x - 1 + kx;
+                if (ix < 0 || ix > 3) continue;
+                const int idx = c * 128 + r + ((ky - 1) * 4 + (kx - 1)) * 8;
+                const uint4 v = *reinterpret_cast<const uint4*>(src + ((size_t)idx << 4));
+                fma8(acc, v, w + (ky * 3 + kx) * C + c * 8);
+            }
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + (((size_t)c * 128 + r) << 4)) = pack8(acc);
+    }
+}
+
+// Depthwise 3x3 stride 2 (+ReLU) 4x4 -> 2x2: src [C8][128 P8 rows][8] (8 crops) -> dst rows row0 + crop*4 + p (crop-major),
+// chunks chunk0 + c of a [.][128][8] tile.  Lanes: p-major, crop fastest -> conflict-free reads.
+__device__ __forceinline__ void dw3x3s2_p8(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int row0, const float* w,
+                                           const float* bias, int tid) {
+    for (int task = tid; task < 32 * C8; task += NT) {
+        const int c = task >> 5, l = task & 31, p = l >> 3, crop = l & 7, oy = p >> 1, ox = p & 1;
+        const int cg = chunk0 + c;
+        float acc[8];
+        load8(bias + cg * 8, acc);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy > 3) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix > 3) continue;
+                const uint4 v = *reinterpret_cast<const uint4*>(src + (((size_t)c * 128 + (iy * 4 + ix) * 8 + crop) << 4));
+                fma8(acc, v, w + (ky * 3 + kx) * C_total + cg * 8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        *reinterpret_cast<uint4*>(dst + (((size_t)cg * 128 + row0 + crop * 4 + p) << 4)) = pack8(acc);
+    }
+}
+
+// Depthwise KxK stride 1 on 2x2 maps, IN PLACE on a crop-major tile [C8][128][8] (row = crop*4 + pixel).  Thread = row,
+// the 4 rows of a crop are 4 adjacent lanes: all loads of a chunk happen before the __syncwarp, the store after it.
+template <int K>
+__device__ __forceinline__ void dw2x2_inplace(uint8_t* buf, int C8, const float* w, const float* bias, bool relu, int tid) {
+    constexpr int PAD = (K - 1) / 2;
+    const int C = C8 * 8;
+    const int r = tid & 127, slice = tid >> 7, p = r & 3, py = p >> 1, px = p & 1, base = r & ~3;
+    for (int c = slice; c < C8; c += 4) {
+        float acc[8];
+        load8(bias + c * 8, acc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int tap = ((q >> 1) - py + PAD) * K + ((q & 1) - px + PAD);
+            const uint4 v = *reinterpret_cast<const uint4*>(buf + (((size_t)c * 128 + base + q) << 4));
+            fma8(acc, v, w + tap * C + c * 8);
+        }
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        }
+        __syncwarp();
+        *reinterpret_cast<uint4*>(buf + (((size_t)c * 128 + r) << 4)) = pack8(acc);
+    }
+}
+
+// =====================================================================================================================
+// stage D
+// =====================================================================================================================
+namespace sd {
+constexpr int NOPS = 24;
+// op:      0 dw24  1 pw25  2 dw26 | 3 pw27 | 4 dw28 5 pw29 6 dw30 7 pw31 | 8 pw32 9 dw33 10 pw34 | 11 pw35 12 dw36 13 pw37 |
+//          14 pw38 15 dw39 16 pw40 | 17 pw41 18 dw42 19 pw43 | 20,21,22 pw44 (three 160-column parts) | 23 heads
+constexpr int OFF_IN = 0;                       // 2 x 12288: stage-input sub-tile ring (128 P8 rows x 48 ch)
+constexpr int OFF_A24 = 24576;                  // 12288: blocks.3.0.dw_start output (A operand of pw_exp)
+constexpr int OFF_EH = 36864;                   // 36864: half (144 ch) of the blocks.3.0.pw_exp output | body: X16 (128 x 64) + head partials
+constexpr int OFF_BIG = 73728;                  // 73728: blocks.3.0.dw_mid output (128 x 288) | body: expanded activation (128 x <=256)
+constexpr int OFF_W = 147456;                   // weight arena: slot 0 at +0 (also the 3 resident head-phase blobs), slot 1 at +W_SLOT1
+constexpr int W_SLOT1 = 42496;
+constexpr int W_ARENA = W_SLOT1 + 37376;        // 79872
+constexpr int OFF_BAR = OFF_W + W_ARENA;        // 227328
+constexpr int SMEM = OFF_BAR + 64;
+static_assert(SMEM <= 227 * 1024, "stage D shared memory budget");
+constexpr int H_OFF1 = 1920, H_OFF2 = 30720;    // head-phase blobs inside slot 0: dw24 @0, pw25 @1920, dw26 @30720 (ends 42240)
+constexpr int S_COL = 448;                      // TMEM columns [448,512): fp32 residual stream (64 ch); [0,288): pw_exp / blocks.4.0 accumulators
+}  // namespace sd
+
+struct StageDParams {
+    const bf16* x;            // stage input: T8 tiles of 128 P8 rows x 48 ch (one tile = 8 crops)
+    const uint8_t* wimg;      // stage weight image (build_stageD_image)
+    float* features;          // [n_crops][480] pooled trunk features (square.py:90)
+    float* squares;           // [n_crops][13]  combined type+color logits (common.py:24)
+    int n_tiles;              // n_crops / 32
+    uint32_t off[sd::NOPS], bytes[sd::NOPS];
+};
+
+__constant__ int kTypeOf[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6};     // dataset.py:31
+__constant__ int kColorOf[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};    // dataset.py:32
+
+__global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ StageDParams p) {
+    using namespace sd;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* IN = smem + OFF_IN;
+    uint8_t* A24 = smem + OFF_A24;
+    uint8_t* EH = smem + OFF_EH;
+    uint8_t* BIG = smem + OFF_BIG;
+    uint8_t* WA = smem + OFF_W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* wbar = bars;           // [2] weight slots
+    uint64_t* inbar = bars + 2;      // [2] input ring
+    uint64_t* mbar = bars + 4;       // MMA completion
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, cs = warp >> 2, row = quad * 32 + lane;
+
+    if (tid == 0) {
+        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(inbar, 1); mbar_init(inbar + 1, 1); mbar_init(mbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t wph0 = 0, wph1 = 0, inph0 = 0, inph1 = 0, mph = 0;
+
+    auto load_head_weights = [&]() {            // thread 0: the three blobs that stay resident during the 4x4 phase
+        mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
+        bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
+        bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
+        bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
+    };
+    auto load_in = [&](int tile, int t) {       // thread 0: sub-tile t (8 crops) of `tile` into ring slot t&1
+        uint64_t* b = inbar + (t & 1);
+        mbar_arrive_expect_tx(b, 12288);
+        bulk_g2s(IN + (t & 1) * 12288, reinterpret_cast<const uint8_t*>(p.x) + ((size_t)tile * 4 + t) * 12288, 12288, b);
+    };
+    auto wait_in = [&](int s) {
+        if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
+    };
+    // body op `op` (3..23) lives in slot op&1; entering it prefetches op+1 into the other slot (free: op-1 is complete)
+    auto begin_op = [&](int op) -> uint8_t* {
+        if (tid == 0 && op + 1 < NOPS) {
+            uint64_t* b = wbar + ((op + 1) & 1);
+            mbar_arrive_expect_tx(b, p.bytes[op + 1]);
+            bulk_g2s(WA + (((op + 1) & 1) ? W_SLOT1 : 0), p.wimg + p.off[op + 1], p.bytes[op + 1], b);
+        }
+        if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
+        return WA + ((op & 1) ? W_SLOT1 : 0);
+    };
+    // generic-proxy smem writes + TMEM reads of all threads ordered before the MMAs the elected thread issues next
+    auto sync_before_mma = [&]() {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        mbar_wait(mbar, mph);
+        mph ^= 1u;
+        tc_fence_after();
+    };
+
+    if (tid == 0 && blockIdx.x < p.n_tiles) {
+        load_head_weights();
+        load_in(blockIdx.x, 0);
+    }
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // ------------------------------ blocks.3.0 at 4x4: four sub-tiles of 8 crops -----------------------------------
+        mbar_wait(wbar, wph0); wph0 ^= 1u;
+        const float* b24 = reinterpret_cast<const float*>(WA);
+        const float* w24 = b24 + 48;
+        const float* b25 = reinterpret_cast<const float*>(WA + H_OFF1);
+        const uint32_t w25 = smem_u32(WA + H_OFF1 + 288 * 4);
+        const float* b26 = reinterpret_cast<const float*>(WA + H_OFF2);
+        const float* w26 = b26 + 288;
+        if (tid == 0) {                          // blocks.3.0.pw_proj weights -> slot 1 while the 4x4 phase runs
+            mbar_arrive_expect_tx(wbar + 1, p.bytes[3]);
+            bulk_g2s(WA + W_SLOT1, p.wimg + p.off[3], p.bytes[3], wbar + 1);
+        }
+        for (int t = 0; t < 4; ++t) {
+            if (tid == 0 && t < 3) load_in(tile, t + 1);
+            wait_in(t & 1);
+            const uint8_t* in = IN + (t & 1) * 12288;
+            dw3x3_p8(in, A24, 6, w24, b24, false, tid);                                   // L24 dw_start (no act)
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_gemm(smem_u32(A24), 48, w25, 288, 0, 144, tmem, false);             // L25 pw_exp 48 -> 288
+                issue_gemm(smem_u32(A24), 48, w25, 288, 144, 144, tmem + 144, false);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            for (int h = 0; h < 2; ++h) {
+                epi_to_tile<true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs);
+                __syncthreads();
+                dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 32 * t, w26, b26, tid);               // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                __syncthreads();
+            }
+        }
+        // ------------------------------ 2x2 phase: 128 rows = 32 crops ------------------------------------------------------
+        uint8_t* X16 = EH;                       // block input as bf16 operand tile [8][128][8]
+        int op = 3;
+        {   // L27 blocks.3.0.pw_proj 288 -> 64: starts the residual stream in TMEM
+            uint8_t* wb = begin_op(op);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_gemm(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);
+            __syncthreads();
+            ++op;
+        }
+#pragma unroll 1
+        for (int blk = 1; blk <= 5; ++blk) {
+            const int cexp = blk == 3 ? 192 : 256;
+            const int kdw = blk <= 3 ? 5 : 3;
+            if (blk == 1) {                      // L28 blocks.3.1.dw_start 5x5 on the block input (no act)
+                uint8_t* wb = begin_op(op);
+                const float* b = reinterpret_cast<const float*>(wb);
+                dw2x2_inplace<5>(X16, 8, b + 64, b, false, tid);
+                __syncthreads();
+                ++op;
+            }
+            {   // pw_exp 64 -> cexp (+ReLU)
+                uint8_t* wb = begin_op(op);
+                sync_before_mma();
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
+                    mma_commit(mbar);
+                }
+                wait_mma();
+                epi_to_tile<true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs);
+                __syncthreads();
+                ++op;
+            }
+            {   // dw_mid KxK (+ReLU), in place
+                uint8_t* wb = begin_op(op);
+                const float* b = reinterpret_cast<const float*>(wb);
+                if (kdw == 5) dw2x2_inplace<5>(BIG, cexp >> 3, b + cexp, b, true, tid);
+                else dw2x2_inplace<3>(BIG, cexp >> 3, b + cexp, b, true, tid);
+                __syncthreads();                 // every warp is done with this slot's weights before the next prefetch targets it
+                ++op;
+            }
+            {   // pw_proj cexp -> 64, accumulated onto the residual stream in TMEM (skip connection)
+                uint8_t* wb = begin_op(op);
+                sync_before_mma();
+                if (tid == 0) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
+                    mma_commit(mbar);
+                }
+                wait_mma();
+                epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);   // + cumulative bias
+                __syncthreads();
+                ++op;
+            }
+        }
+        // ------------------------------ blocks.4.0 (64 -> 480, ReLU) + average pool + heads -------------------------------------
+        for (int part = 0; part < 3; ++part, ++op) {          // three 160-column weight parts (ops 20..22)
+            uint8_t* wb = begin_op(op);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_gemm(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
+                mma_commit(mbar);
+            }
+            wait_mma();
+        }
+        {
+            uint8_t* wb = begin_op(op);          // op 23 (slot 1): [head_b 16][head_w 10x480][blocks.4.0 bias 480] fp32
+            const float* hb = reinterpret_cast<const float*>(wb);
+            const float* hw = hb + 16;
+            const float* bias44 = hw + 4800;
+            float part_acc[10];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) part_acc[r] = 0.f;
+            const int crop_in_tile = row >> 2;
+            const int64_t crop = (int64_t)tile * 32 + crop_in_tile;
+            for (int g = cs; g < 30; g += 4) {
+                uint32_t rr[16];
+                tmem_ld16(trow + (uint32_t)(g * 16), rr);
+                tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(rr[i]) + bias44[g * 16 + i], 0.f);
+                // transposing reduction over the 4 pixel lanes of a crop: each lane ends with 4 of the 16 channels, summed
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float send = (lane & 2) ? v[i] : v[i + 8];
+                    const float keep = (lane & 2) ? v[i + 8] : v[i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+                float f4[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float send = (lane & 1) ? a[i] : a[i + 4];
+                    const float keep = (lane & 1) ? a[i + 4] : a[i];
+                    f4[i] = (keep + __shfl_xor_sync(0xffffffffu, send, 1)) * 0.25f;       // global_pool: mean over 2x2
+                }
+                const int ch = g * 16 + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
+                *reinterpret_cast<float4*>(p.features + crop * 480 + ch) = make_float4(f4[0], f4[1], f4[2], f4[3]);
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {                                             // type_head rows 0..6, color_head rows 7..9
+                    const float4 w4 = *reinterpret_cast<const float4*>(hw + r * 480 + ch);
+                    part_acc[r] = fmaf(f4[0], w4.x, fmaf(f4[1], w4.y, fmaf(f4[2], w4.z, fmaf(f4[3], w4.w, part_acc[r]))));
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                part_acc[r] += __shfl_xor_sync(0xffffffffu, part_acc[r], 1);
+                part_acc[r] += __shfl_xor_sync(0xffffffffu, part_acc[r], 2);
+            }
+            float* red = reinterpret_cast<float*>(EH + 16384);               // [4 column slices][32 crops][10]
+            if ((lane & 3) == 0) {
+#pragma unroll
+                for (int r = 0; r < 10; ++r) red[(cs * 32 + crop_in_tile) * 10 + r] = part_acc[r];
+            }
+            tc_fence_before();
+            __syncthreads();
+            if (tid < 32 * 13) {                                             // combine_type_color (common.py:24)
+                const int c = tid / 13, cls = tid - c * 13;
+                const int ti = kTypeOf[cls], ci = 7 + kColorOf[cls];
+                float t = hb[ti], cl = hb[ci];
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    t += red[(s * 32 + c) * 10 + ti];
+                    cl += red[(s * 32 + c) * 10 + ci];
+                }
+                p.squares[((int64_t)tile * 32 + c) * 13 + cls] = t + cl;
+            }
+            const int next = tile + gridDim.x;
+            __syncthreads();                     // heads blob and partials fully consumed
+            if (tid == 0 && next < p.n_tiles) {  // next tile's resident weights + first input sub-tile
+                load_head_weights();
+                load_in(next, 0);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// crop-major T8 tiles (row = crop*16 + pix) -> P8 tiles (row = pix*8 + crop_local); one thread per 16-byte chunk.
+__global__ void permute_p8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_chunks) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_chunks) return;
+    const int r = (int)(i & 127);
+    out[(i & ~(int64_t)127) + ((r & 15) * 8 + (r >> 4))] = in[i];
+}
+
+// ---- stage weight image construction --------------------------------------------------------------------------------------
+__global__ void prep_pw_part_kernel(const float* __restrict__ w, int K, int n_total, int n0, int n, bf16* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * n) return;
+    const int kk = i & 7, j = (i >> 3) % n, kc = (i >> 3) / n;
+    dst[i] = __float2bfloat16_rn(w[(size_t)(kc * 8 + kk) * n_total + n0 + j]);
+}
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (a ? a[i] : 0.f) + b[i];
+}
+
+struct DOp { int layer, kind; };   // kind 0 depthwise | 1 pointwise (own bias) | 2 pw_proj (cumulative bias of its residual chain) | 3 blocks.4.0 part | 4 heads
+const DOp kDOps[sd::NOPS] = {{24, 0}, {25, 1}, {26, 0}, {27, 2}, {28, 0}, {29, 1}, {30, 0}, {31, 2}, {32, 1}, {33, 0}, {34, 2}, {35, 1},
+                             {36, 0}, {37, 2}, {38, 1}, {39, 0}, {40, 2}, {41, 1}, {42, 0}, {43, 2}, {44, 3}, {44, 3}, {44, 3}, {-1, 4}};
+
+uint32_t dop_bytes(int op) {
+    const cv_layer_info* L = cv_layers();
+    const DOp& d = kDOps[op];
+    if (d.kind == 4) return (16 + 4800 + 480) * 4;
+    const cv_layer_info& l = L[d.layer];
+    if (d.kind == 0) return (uint32_t)(l.cout + l.k * l.k * l.cout) * 4;
+    if (d.kind == 3) return 64 * 160 * 2;
+    return (uint32_t)l.cout * 4 + (uint32_t)l.cin * l.cout * 2;
+}
+
+}  // namespace
+
+size_t stageD_image_bytes() {
+    size_t n = 0;
+    for (int op = 0; op < sd::NOPS; ++op) n += (dop_bytes(op) + 127) / 128 * 128;
+    return n;
+}
+
+// Builds the stage-D weight image from the packed fp32 blob (device) and fills off[]/bytes[] (host arrays of 24).
+int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s) {
+    const cv_layer_info* L = cv_layers();
+    size_t o = 0;
+    const float* prev_cum = nullptr;
+    int part = 0;
+    for (int op = 0; op < sd::NOPS; ++op) {
+        const DOp& d = kDOps[op];
+        off[op] = (uint32_t)o;
+        bytes[op] = dop_bytes(op);
+        if (bytes[op] % 16 != 0) { cv_set_error("stage D: blob %d size %u not a multiple of 16", op, bytes[op]); return CV_ERR_STATE; }
+        uint8_t* dst = img + o;
+        if (d.kind == 4) {
+            float* f = reinterpret_cast<float*>(dst);
+            CV_CUDA(cudaMemsetAsync(f, 0, 64, s));
+            CV_CUDA(cudaMemcpyAsync(f, blob + CV_OFF_HEAD_B, 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            CV_CUDA(cudaMemcpyAsync(f + 16, blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            CV_CUDA(cudaMemcpyAsync(f + 16 + 4800, blob + L[44].b_offset, 480 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        } else {
+            const cv_layer_info& l = L[d.layer];
+            if (d.kind == 0) {
+                float* f = reinterpret_cast<float*>(dst);
+                CV_CUDA(cudaMemcpyAsync(f, blob + l.b_offset, l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                CV_CUDA(cudaMemcpyAsync(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            } else if (d.kind == 3) {
+                prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 64, 480, 160 * part, 160, reinterpret_cast<bf16*>(dst));
+                CV_CHECK_LAUNCH();
+                ++part;
+            } else {
+                float* f = reinterpret_cast<float*>(dst);
+                if (d.kind == 2) {
+                    // residual chain: blocks.3.0.pw_proj (no skip) starts it, every later pw_proj adds its bias to the running sum
+                    add_f32_kernel<<<1, 64, 0, s>>>(f, l.skip >= 0 ? prev_cum : nullptr, blob + l.b_offset, l.cout);
+                    CV_CHECK_LAUNCH();
+                    prev_cum = f;
+                } else {
+                    CV_CUDA(cudaMemcpyAsync(f, blob + l.b_offset, l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                }
+                prep_pw_part_kernel<<<(l.cin * l.cout + 255) / 256, 256, 0, s>>>(blob + l.w_offset, l.cin, l.cout, 0, l.cout,
+                                                                                reinterpret_cast<bf16*>(dst + (size_t)l.cout * 4));
+                CV_CHECK_LAUNCH();
+            }
+        }
+        o += (bytes[op] + 127) / 128 * 128;
+    }
+    return CV_OK;
+}
+
+int launch_permute_p8(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStream_t s) {
+    const int64_t n_chunks = n_crops * 16 * (C / 8);
+    if (n_chunks == 0) return CV_OK;
+    permute_p8_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n_chunks);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, float* features,
+                  float* squares, int num_sms, cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    if (n_crops % 32 != 0) { cv_set_error("stage D: crop count %lld is not a multiple of 32", (long long)n_crops); return CV_ERR_ARG; }
+    StageDParams p{};
+    p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
+    for (int i = 0; i < sd::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
+    CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    stageD_kernel<<<grid, NT, sd::SMEM, s>>>(p);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}

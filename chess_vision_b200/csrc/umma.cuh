@@ -83,6 +83,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// (A and B must have the same 16-bit format: bf16 activations x fp16 weights raises an illegal-instruction fault on B200.)
 
 // ---- tcgen05.mma / commit / ld -----------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues on behalf of the CTA (SASS: UTCHMMA)
