@@ -16,7 +16,7 @@
 //
 // Row orders.  4x4-resolution tiles (stage input, blocks.3.0 head) are "P8": row = pixel*8 + crop_local, which makes
 // every depthwise neighbour access a contiguous, bank-conflict-free 16-byte-per-lane shared-memory read.  2x2-resolution
-// tiles are crop-major (row = crop*4 + pixel) so the 4 pixels of a crop sit in 4 adjacent lanes / TMEM lanes.
+// tiles are pixel-major as well (row = pixel*32 + crop): the in-place 2x2 depthwise then reads/writes contiguous rows per pixel.
 #include "internal.h"
 #include "umma.cuh"
 #include "arch_table.inc"     // CV_OFF_* blob offsets (kLayers itself is reached through cv_layers())
@@ -117,9 +117,9 @@ __device__ __forceinline__ void dw3x3_p8(const uint8_t* src, uint8_t* dst, int C
     }
 }
 
-// Depthwise 3x3 stride 2 (+ReLU) 4x4 -> 2x2: src [C8][128 P8 rows][8] (8 crops) -> dst rows row0 + crop*4 + p (crop-major),
-// chunks chunk0 + c of a [.][128][8] tile.  Lanes: p-major, crop fastest -> conflict-free reads.
-__device__ __forceinline__ void dw3x3s2_p8(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int row0, const float* w,
+// Depthwise 3x3 stride 2 (+ReLU) 4x4 -> 2x2: src [C8][128 P8 rows][8] (8 crops) -> dst rows p*32 + crop0 + crop (pixel-major
+// 2x2 tile of 32 crops), chunks chunk0 + c of a [.][128][8] tile.  Lanes: p-major, crop fastest -> conflict-free reads and writes.
+__device__ __forceinline__ void dw3x3s2_p8(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int crop0, const float* w,
                                            const float* bias, int tid) {
     for (int task = tid; task < 32 * C8; task += NT) {
         const int c = task >> 5, l = task & 31, p = l >> 3, crop = l & 7, oy = p >> 1, ox = p & 1;
@@ -140,32 +140,43 @@ __device__ __forceinline__ void dw3x3s2_p8(const uint8_t* src, uint8_t* dst, int
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-        *reinterpret_cast<uint4*>(dst + (((size_t)cg * 128 + row0 + crop * 4 + p) << 4)) = pack8(acc);
+        *reinterpret_cast<uint4*>(dst + (((size_t)cg * 128 + p * 32 + crop0 + crop) << 4)) = pack8(acc);
     }
 }
 
-// Depthwise KxK stride 1 on 2x2 maps, IN PLACE on a crop-major tile [C8][128][8] (row = crop*4 + pixel).  Thread = row,
-// the 4 rows of a crop are 4 adjacent lanes: all loads of a chunk happen before the __syncwarp, the store after it.
-template <int K>
-__device__ __forceinline__ void dw2x2_inplace(uint8_t* buf, int C8, const float* w, const float* bias, bool relu, int tid) {
-    constexpr int PAD = (K - 1) / 2;
-    const int C = C8 * 8;
-    const int r = tid & 127, slice = tid >> 7, p = r & 3, py = p >> 1, px = p & 1, base = r & ~3;
-    for (int c = slice; c < C8; c += 4) {
-        float acc[8];
-        load8(bias + c * 8, acc);
+// Depthwise KxK stride 1 on 2x2 maps, IN PLACE on a pixel-major tile [C8][128][8] (row = pixel*32 + crop, 32 crops).
+// Thread = (crop, 8-channel chunk): it reads the crop's 4 pixels, computes all 4 outputs (each output sees all 4 inputs
+// on a 2x2 map) and writes them back -- no other thread touches these 64 bytes, so no synchronisation is needed; a warp
+// is 32 crops of one chunk, so activation accesses are contiguous and the weight reads are warp-uniform broadcasts.
+// Weights: wq[chunk][p][q][8] fp32 = tap (q - p) of the KxK filter for output pixel p / input pixel q (prep_dw2x2_kernel).
+__device__ __forceinline__ void dw2x2_pm(uint8_t* buf, int C8, const float* wq, const float* bias, bool relu, int tid) {
+    for (int task = tid; task < 32 * C8; task += NT) {
+        const int c = task >> 5, crop = task & 31;
+        uint8_t* base = buf + (((size_t)c * 128 + crop) << 4);
+        float x[4][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int tap = ((q >> 1) - py + PAD) * K + ((q & 1) - px + PAD);
-            const uint4 v = *reinterpret_cast<const uint4*>(buf + (((size_t)c * 128 + base + q) << 4));
-            fma8(acc, v, w + tap * C + c * 8);
-        }
-        if (relu) {
+        for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(base + q * 512), x[q]);
+        float b[8];
+        load8(bias + c * 8, b);
+        const float* wc = wq + c * 128;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+        for (int pp = 0; pp < 4; ++pp) {
+            float acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = b[i];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float ww[8];
+                load8(wc + (pp * 4 + q) * 8, ww);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[q][i], ww[i], acc[i]);
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+            }
+            *reinterpret_cast<uint4*>(base + pp * 512) = pack8(acc);
         }
-        __syncwarp();
-        *reinterpret_cast<uint4*>(buf + (((size_t)c * 128 + r) << 4)) = pack8(acc);
     }
 }
 
@@ -300,7 +311,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             for (int h = 0; h < 2; ++h) {
                 epi_to_tile<true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs);
                 __syncthreads();
-                dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 32 * t, w26, b26, tid);               // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);               // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
                 __syncthreads();
             }
         }
@@ -323,11 +334,10 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 #pragma unroll 1
         for (int blk = 1; blk <= 5; ++blk) {
             const int cexp = blk == 3 ? 192 : 256;
-            const int kdw = blk <= 3 ? 5 : 3;
             if (blk == 1) {                      // L28 blocks.3.1.dw_start 5x5 on the block input (no act)
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                dw2x2_inplace<5>(X16, 8, b + 64, b, false, tid);
+                dw2x2_pm(X16, 8, b + 64, b, false, tid);
                 __syncthreads();
                 ++op;
             }
@@ -344,11 +354,10 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 __syncthreads();
                 ++op;
             }
-            {   // dw_mid KxK (+ReLU), in place
+            {   // dw_mid 5x5 / 3x3 (+ReLU), in place
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                if (kdw == 5) dw2x2_inplace<5>(BIG, cexp >> 3, b + cexp, b, true, tid);
-                else dw2x2_inplace<3>(BIG, cexp >> 3, b + cexp, b, true, tid);
+                dw2x2_pm(BIG, cexp >> 3, b + cexp, b, true, tid);
                 __syncthreads();                 // every warp is done with this slot's weights before the next prefetch targets it
                 ++op;
             }
@@ -382,51 +391,40 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             const float* hb = reinterpret_cast<const float*>(wb);
             const float* hw = hb + 16;
             const float* bias44 = hw + 4800;
+            // TMEM lane = pixel*32 + crop: warp (quad = pixel, cs) holds one pixel of 32 crops.  The 2x2 mean needs the 4
+            // pixel warps of a column slice to exchange through shared memory (named barrier per slice, 128 threads).
             float part_acc[10];
 #pragma unroll
             for (int r = 0; r < 10; ++r) part_acc[r] = 0.f;
-            const int crop_in_tile = row >> 2;
-            const int64_t crop = (int64_t)tile * 32 + crop_in_tile;
+            float* xbuf = reinterpret_cast<float*>(BIG) + (size_t)cs * 4 * 16 * 32;      // [pixel][16 ch][32 crops] of this slice
+            const int64_t crop = (int64_t)tile * 32 + lane;
             for (int g = cs; g < 30; g += 4) {
                 uint32_t rr[16];
                 tmem_ld16(trow + (uint32_t)(g * 16), rr);
                 tmem_ld_wait();
-                float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(__uint_as_float(rr[i]) + bias44[g * 16 + i], 0.f);
-                // transposing reduction over the 4 pixel lanes of a crop: each lane ends with 4 of the 16 channels, summed
-                float a[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float send = (lane & 2) ? v[i] : v[i + 8];
-                    const float keep = (lane & 2) ? v[i + 8] : v[i];
-                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-                }
-                float f4[4];
+                for (int i = 0; i < 16; ++i)
+                    xbuf[(quad * 16 + i) * 32 + lane] = fmaxf(__uint_as_float(rr[i]) + bias44[g * 16 + i], 0.f);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + cs) : "memory");
+                float f4[4];                                                             // channels g*16 + 4*quad + i of crop `lane`
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float send = (lane & 1) ? a[i] : a[i + 4];
-                    const float keep = (lane & 1) ? a[i + 4] : a[i];
-                    f4[i] = (keep + __shfl_xor_sync(0xffffffffu, send, 1)) * 0.25f;       // global_pool: mean over 2x2
+                    const int ch = 4 * quad + i;
+                    f4[i] = ((xbuf[(0 * 16 + ch) * 32 + lane] + xbuf[(1 * 16 + ch) * 32 + lane]) +
+                             (xbuf[(2 * 16 + ch) * 32 + lane] + xbuf[(3 * 16 + ch) * 32 + lane])) * 0.25f;   // global_pool: mean over 2x2
                 }
-                const int ch = g * 16 + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + cs) : "memory");
+                const int ch = g * 16 + 4 * quad;
                 *reinterpret_cast<float4*>(p.features + crop * 480 + ch) = make_float4(f4[0], f4[1], f4[2], f4[3]);
 #pragma unroll
-                for (int r = 0; r < 10; ++r) {                                             // type_head rows 0..6, color_head rows 7..9
+                for (int r = 0; r < 10; ++r) {                                           // type_head rows 0..6, color_head rows 7..9
                     const float4 w4 = *reinterpret_cast<const float4*>(hw + r * 480 + ch);
                     part_acc[r] = fmaf(f4[0], w4.x, fmaf(f4[1], w4.y, fmaf(f4[2], w4.z, fmaf(f4[3], w4.w, part_acc[r]))));
                 }
             }
+            float* red = reinterpret_cast<float*>(EH + 16384);               // [16 warps][32 crops][10]
 #pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                part_acc[r] += __shfl_xor_sync(0xffffffffu, part_acc[r], 1);
-                part_acc[r] += __shfl_xor_sync(0xffffffffu, part_acc[r], 2);
-            }
-            float* red = reinterpret_cast<float*>(EH + 16384);               // [4 column slices][32 crops][10]
-            if ((lane & 3) == 0) {
-#pragma unroll
-                for (int r = 0; r < 10; ++r) red[(cs * 32 + crop_in_tile) * 10 + r] = part_acc[r];
-            }
+            for (int r = 0; r < 10; ++r) red[(warp * 32 + lane) * 10 + r] = part_acc[r];
             tc_fence_before();
             __syncthreads();
             if (tid < 32 * 13) {                                             // combine_type_color (common.py:24)
@@ -434,9 +432,9 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 const int ti = kTypeOf[cls], ci = 7 + kColorOf[cls];
                 float t = hb[ti], cl = hb[ci];
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    t += red[(s * 32 + c) * 10 + ti];
-                    cl += red[(s * 32 + c) * 10 + ci];
+                for (int w = 0; w < 16; ++w) {
+                    t += red[(w * 32 + c) * 10 + ti];
+                    cl += red[(w * 32 + c) * 10 + ci];
                 }
                 p.squares[((int64_t)tile * 32 + c) * 13 + cls] = t + cl;
             }
@@ -469,6 +467,14 @@ __global__ void prep_pw_part_kernel(const float* __restrict__ w, int K, int n_to
     const int kk = i & 7, j = (i >> 3) % n, kc = (i >> 3) / n;
     dst[i] = __float2bfloat16_rn(w[(size_t)(kc * 8 + kk) * n_total + n0 + j]);
 }
+// 2x2-map depthwise weights: dst[((c8*4 + p)*4 + q)*8 + i] = w[tap(p,q)][c8*8 + i], tap = (qy-py+pad)*K + (qx-px+pad).
+__global__ void prep_dw2x2_kernel(const float* __restrict__ w, int K, int C, float* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 16 * C) return;
+    const int i = idx & 7, q = (idx >> 3) & 3, p = (idx >> 5) & 3, c8 = idx >> 7, pad = (K - 1) / 2;
+    const int tap = ((q >> 1) - (p >> 1) + pad) * K + ((q & 1) - (p & 1) + pad);
+    dst[idx] = w[(size_t)tap * C + c8 * 8 + i];
+}
 __global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = (a ? a[i] : 0.f) + b[i];
@@ -483,7 +489,7 @@ uint32_t dop_bytes(int op) {
     const DOp& d = kDOps[op];
     if (d.kind == 4) return (16 + 4800 + 480) * 4;
     const cv_layer_info& l = L[d.layer];
-    if (d.kind == 0) return (uint32_t)(l.cout + l.k * l.k * l.cout) * 4;
+    if (d.kind == 0) return (uint32_t)(l.cout + (l.hin == 2 ? 16 : l.k * l.k) * l.cout) * 4;      // 2x2 maps: [chunk][p][q][8] layout
     if (d.kind == 3) return 64 * 160 * 2;
     return (uint32_t)l.cout * 4 + (uint32_t)l.cin * l.cout * 2;
 }
@@ -519,7 +525,12 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
             if (d.kind == 0) {
                 float* f = reinterpret_cast<float*>(dst);
                 CV_CUDA(cudaMemcpyAsync(f, blob + l.b_offset, l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
-                CV_CUDA(cudaMemcpyAsync(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                if (l.hin == 2) {
+                    prep_dw2x2_kernel<<<(16 * l.cout + 255) / 256, 256, 0, s>>>(blob + l.w_offset, l.k, l.cout, f + l.cout);
+                    CV_CHECK_LAUNCH();
+                } else {
+                    CV_CUDA(cudaMemcpyAsync(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
+                }
             } else if (d.kind == 3) {
                 prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 64, 480, 160 * part, 160, reinterpret_cast<bf16*>(dst));
                 CV_CHECK_LAUNCH();
