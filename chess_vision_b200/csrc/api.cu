@@ -42,6 +42,8 @@ struct cv_square {
     bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
     uint8_t* sd_img = nullptr;    // weight image of the fused tail (stage D)
     uint32_t sd_off[CV_STAGE_D_OPS], sd_bytes[CV_STAGE_D_OPS];
+    uint8_t* sc_img = nullptr;    // weight image of the fused blocks.2 stage (stage C)
+    uint32_t sc_off[CV_STAGE_C_OPS], sc_bytes[CV_STAGE_C_OPS];
     int num_sms = 148;
     int impl = CV_IMPL_DEFAULT;   // which bf16 kernels run (cv_square_set_impl)
     int wave = 0;                 // boards per wave, 0 = default per precision
@@ -171,7 +173,8 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     auto buf_of = [&](int layer) -> T* { return layer < 0 ? crops : (h->out_buf[layer] < 0 ? stem : small[h->out_buf[layer]]); };
     // bf16: blocks.3.* + blocks.4.0 + pool + heads fused into one persistent kernel (stage D) fed by layer 23's output
     const bool fused_tail = sizeof(T) == 2 && (h->impl & CV_IMPL_TAIL);
-    const int end_layer = fused_tail ? 24 : CV_NUM_LAYERS;
+    const bool fused_mid = fused_tail && (h->impl & CV_IMPL_MID);          // blocks.2.* as one kernel too (stage C)
+    const int end_layer = fused_mid ? 5 : fused_tail ? 24 : CV_NUM_LAYERS;
     for (int i = 0; i < end_layer; ++i) {
         const cv_layer_info& L = kLayers[i];
         T* out = buf_of(i);
@@ -190,14 +193,32 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
         }
     }
     if (fused_tail) {
-        int rc = prof_mark(h, CV_PROF_TAIL, s);
-        if (rc) return rc;
-        T* p8 = small[(h->out_buf[23] + 1) % NBUF_SMALL];                 // any buffer but layer 23's own
-        rc = launch_permute_p8(reinterpret_cast<const bf16*>(buf_of(23)), reinterpret_cast<bf16*>(p8), n, 48, s);
-        if (rc) return rc;
+        int rc;
+        T* p8;
+        if (fused_mid) {
+            rc = prof_mark(h, CV_PROF_MID, s);
+            if (rc) return rc;
+            T* p2 = small[(h->out_buf[4] + 1) % NBUF_SMALL];               // any two buffers but layer 4's own
+            p8 = small[(h->out_buf[4] + 2) % NBUF_SMALL];
+            rc = launch_permute_p2(reinterpret_cast<const bf16*>(buf_of(4)), reinterpret_cast<bf16*>(p2), n, 32, s);
+            if (rc) return rc;
+            rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img, h->sc_off, h->sc_bytes, reinterpret_cast<bf16*>(p8),
+                               h->num_sms, s);
+            if (rc) return rc;
+            h->launches += 2;
+            rc = prof_mark(h, CV_PROF_TAIL, s);
+            if (rc) return rc;
+        } else {
+            rc = prof_mark(h, CV_PROF_TAIL, s);
+            if (rc) return rc;
+            p8 = small[(h->out_buf[23] + 1) % NBUF_SMALL];                 // any buffer but layer 23's own
+            rc = launch_permute_p8(reinterpret_cast<const bf16*>(buf_of(23)), reinterpret_cast<bf16*>(p8), n, 48, s);
+            if (rc) return rc;
+            ++h->launches;
+        }
         rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img, h->sd_off, h->sd_bytes, feat, squares, h->num_sms, s);
         if (rc) return rc;
-        h->launches += 2;
+        ++h->launches;
         return CV_OK;
     }
     int rc = prof_mark(h, CV_PROF_POOL_HEADS, s);
@@ -324,6 +345,7 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->sd_img, stageD_image_bytes()));
+    CV_CUDA(cudaMalloc(&h->sc_img, stageC_image_bytes()));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     float lut[768];
     default_lut(lut);
@@ -335,7 +357,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -372,6 +394,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     rc = launch_frontend_prep_weights(h->blob, h->fe_wimg, s);
     if (rc) return rc;
     rc = build_stageD_image(h->blob, h->sd_img, h->sd_off, h->sd_bytes, s);
+    if (rc) return rc;
+    rc = build_stageC_image(h->blob, h->sc_img, h->sc_off, h->sc_bytes, s);
     if (rc) return rc;
     float* hw = h->head_w;
     CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));

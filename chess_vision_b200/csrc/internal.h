@@ -144,3 +144,12 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
 int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, cudaStream_t s);
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes,
                   float* features, float* squares, int num_sms, cudaStream_t s);
+
+// stage C = blocks.2.* (19 conv layers).  Input: "P2" tiles (128 rows = 2 crops at 8x8, row = pixel*2 + crop_local, 32 ch);
+// output: the P8 tiles stage D consumes.
+enum { CV_STAGE_C_OPS = 20 };
+size_t stageC_image_bytes();
+int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
+int launch_permute_p2(const bf16* in_t8, bf16* out_p2, int64_t n_crops, int C, cudaStream_t s);
+int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8,
+                  int num_sms, cudaStream_t s);

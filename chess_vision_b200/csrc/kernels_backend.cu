@@ -55,14 +55,18 @@ __device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, const floa
 // One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
 // A: shared-memory operand tile [K/8][128 rows][8] bf16 (K-major, no swizzle; LBO 2048 B, SBO 128 B).
 // B: weight image [K/8][n_total][8] bf16, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
+// w_parts = 2: the image is W_hi followed by W_lo (W = W_hi + W_lo, both bf16): two MMAs per k-step on the same A.
 __device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_addr, int n_total, int n0, int n, uint32_t d_tmem,
-                                           bool accumulate) {
+                                           bool accumulate, int w_parts = 1) {
     const uint32_t idesc = make_idesc_bf16(128, n);
     const uint32_t b_lbo = (uint32_t)n_total * 16u;
+    const uint32_t part_bytes = (uint32_t)K * (uint32_t)n_total * 2u;
     for (int k = 0; k < K / 16; ++k) {
         const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
-        const uint64_t bd = make_smem_desc(b_addr + (uint32_t)k * 2u * b_lbo + (uint32_t)n0 * 16u, b_lbo, 128u);
-        mma_bf16_ss(d_tmem, ad, bd, idesc, (accumulate || k > 0) ? 1u : 0u);
+        for (int part = 0; part < w_parts; ++part) {
+            const uint64_t bd = make_smem_desc(b_addr + part * part_bytes + (uint32_t)k * 2u * b_lbo + (uint32_t)n0 * 16u, b_lbo, 128u);
+            mma_bf16_ss(d_tmem, ad, bd, idesc, (accumulate || k > 0 || part > 0) ? 1u : 0u);
+        }
     }
 }
 
@@ -70,8 +74,8 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_ad
 // dst[(chunk0 + col/8)][row][8].  The 16-column groups are dealt round-robin to the 4 column-slice warps.
 template <bool RELU>
 __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, const float* bias, uint8_t* dst, int chunk0, int row,
-                                            int cs) {
-    for (int g = cs; g < (ncols >> 4); g += 4) {
+                                            int cs, int n_slices = 4) {
+    for (int g = cs; g < (ncols >> 4); g += n_slices) {
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
         tmem_ld_wait();
@@ -452,6 +456,359 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 }
 
 
+// =====================================================================================================================
+// stage C: blocks.2.0 .. blocks.2.5 (19 conv layers), 8x8 -> 4x4 maps.  Tile = 16 crops.
+// =====================================================================================================================
+// Depthwise 5x5 stride 1 on 8x8 maps, "P2" rows (row = pix*2 + crop, 2 crops), 32 channels: 128 rows x 4 chunks = NT tasks.
+__device__ __forceinline__ void dw5x5_p2(const uint8_t* src, uint8_t* dst, const float* w, const float* bias, int tid) {
+    const int c = tid >> 7, r = tid & 127, pix = r >> 1, y = pix >> 3, x = pix & 7;
+    float acc[8];
+    load8(bias + c * 8, acc);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        const int iy = y - 2 + ky;
+        if (iy < 0 || iy > 7) continue;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            const int ix = x - 2 + kx;
+            if (ix < 0 || ix > 7) continue;
+            const int idx = c * 128 + r + ((ky - 2) * 8 + (kx - 2)) * 2;
+            fma8(acc, *reinterpret_cast<const uint4*>(src + ((size_t)idx << 4)), w + (ky * 5 + kx) * 32 + c * 8);
+        }
+    }
+    *reinterpret_cast<uint4*>(dst + ((size_t)tid << 4)) = pack8(acc);
+}
+
+// Depthwise 5x5 stride 2 (+ReLU) 8x8 -> 4x4, 96 channels: src [12][128 P2 rows][8] (2 crops) -> dst P8 tile rows
+// opix*8 + crop0 + crop of [12][128][8].  384 tasks; lanes: crop fastest, then output pixel.
+__device__ __forceinline__ void dw5x5s2_p2(const uint8_t* src, uint8_t* dst, int crop0, const float* w, const float* bias, int tid) {
+    if (tid >= 384) return;
+    const int c = tid >> 5, l = tid & 31, crop = l & 1, opix = l >> 1, oy = opix >> 2, ox = opix & 3;
+    float acc[8];
+    load8(bias + c * 8, acc);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        const int iy = 2 * oy - 2 + ky;
+        if (iy < 0 || iy > 7) continue;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+            const int ix = 2 * ox - 2 + kx;
+            if (ix < 0 || ix > 7) continue;
+            fma8(acc, *reinterpret_cast<const uint4*>(src + (((size_t)c * 128 + (iy * 8 + ix) * 2 + crop) << 4)), w + (ky * 5 + kx) * 96 + c * 8);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+    *reinterpret_cast<uint4*>(dst + (((size_t)c * 128 + opix * 8 + crop0 + crop) << 4)) = pack8(acc);
+}
+
+// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over N_MT consecutive 128-row tiles of C8 chunks each: every thread
+// computes its (<= MAXI) outputs into registers, the CTA synchronises, then the results are stored.
+template <int MAXI>
+__device__ __forceinline__ void dw3x3_p8_inplace(uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, bool relu, int tid) {
+    const int C = C8 * 8;
+    uint4 res[MAXI];
+#pragma unroll
+    for (int it = 0; it < MAXI; ++it) {
+        const int task = tid + it * NT;
+        if (task < n_tasks) {
+            const int r = task & 127, tc = task >> 7, c = tc % C8, pix = r >> 3, y = pix >> 2, x = pix & 3;
+            float acc[8];
+            load8(bias + c * 8, acc);
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int iy = y - 1 + ky;
+                if (iy < 0 || iy > 3) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = x - 1 + kx;
+                    if (ix < 0 || ix > 3) continue;
+                    const int idx = tc * 128 + r + ((ky - 1) * 4 + (kx - 1)) * 8;
+                    fma8(acc, *reinterpret_cast<const uint4*>(buf + ((size_t)idx << 4)), w + (ky * 3 + kx) * C + c * 8);
+                }
+            }
+            if (relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
+            }
+            res[it] = pack8(acc);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < MAXI; ++it) {
+        const int task = tid + it * NT;
+        if (task < n_tasks) *reinterpret_cast<uint4*>(buf + ((size_t)task << 4)) = res[it];
+    }
+}
+
+// TMEM accumulator columns -> (+bias) -> bf16 -> global T8-chunked tile dst[chunk][128 rows][8] (coalesced 16-byte stores).
+__device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int row, int cs, int n_slices) {
+    for (int g = cs; g < (ncols >> 4); g += n_slices) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[8];
+            load8(bias + g * 16 + j * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
+            dst[(size_t)(g * 2 + j) * 128 + row] = pack8(v);
+        }
+    }
+}
+
+namespace sc {
+constexpr int NOPS = 20;
+// op: 0 dw5  1 pw6  2 dw7 | 3 pw8 | 4+3j pw_exp  5+3j dw_mid  6+3j pw_proj (blocks.2.1..2.4, j = 0..3) |
+//     16 dw21 + pw22 (output columns 0..95)  17 pw22 (columns 96..191)  18 pw23 (K rows 0..95)  19 pw23 (K rows 96..191)
+constexpr int OFF_IN = 0;                 // 2 x 8192: stage-input ring, one sub-tile = 2 crops (128 P2 rows x 32 ch)
+constexpr int OFF_A5 = 16384;             // 8192: dw_start output
+constexpr int OFF_R = 24576;              // 73728: E6 (24576) | A7 (2 x 24576)   ||  body: E (2 x 24576)  ||  E22a (49152) | E22b runs into X16
+constexpr int OFF_X16 = 98304;            // 2 x 12288: block input operand tiles (2 M-tiles of 8 crops, P8 rows, 48 ch)
+constexpr int OFF_W = 122880;             // weight arena: slot 0 (26112; also the resident 8x8-phase blobs) | slot 1 (20992)
+constexpr int W_SLOT1 = 26112;
+constexpr int W_ARENA = W_SLOT1 + 20992;  // 47104
+constexpr int OFF_BAR = OFF_W + W_ARENA;  // 169984
+constexpr int SMEM = OFF_BAR + 64;
+constexpr int H_OFF1 = 3328, H_OFF2 = 16000;    // slot 0 during the 8x8 phase: dw5 @0 (3328) | pw6 @3328 (12672) | dw7 @16000 (9984)
+constexpr int ACC = 0;                    // TMEM: accumulators [0,384); residual stream (48 ch) of M-tile m at S_COL + 48 m
+constexpr int S_COL = 400;
+}  // namespace sc
+
+struct StageCParams {
+    const bf16* x;            // stage input: P2 tiles (128 rows = 2 crops, row = pix*2 + crop) x 32 ch, T8 chunking
+    const uint8_t* wimg;
+    bf16* y;                  // stage output: P8 tiles (128 rows = 8 crops, row = pix*8 + crop) x 48 ch  == stage D input
+    int n_tiles;              // n_crops / 16
+    uint32_t off[sc::NOPS], bytes[sc::NOPS];
+};
+
+__global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ StageCParams p) {
+    using namespace sc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* IN = smem + OFF_IN;
+    uint8_t* A5 = smem + OFF_A5;
+    uint8_t* R = smem + OFF_R;
+    uint8_t* E6 = R;
+    uint8_t* A7 = R + 24576;
+    uint8_t* X16 = smem + OFF_X16;
+    uint8_t* WA = smem + OFF_W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* wbar = bars;
+    uint64_t* inbar = bars + 2;
+    uint64_t* mbar = bars + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, cs = warp >> 2, row = quad * 32 + lane;
+    const int mt = cs & 1, half = cs >> 1;          // body epilogues: M-tile and column half handled by this warp
+
+    if (tid == 0) {
+        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(inbar, 1); mbar_init(inbar + 1, 1); mbar_init(mbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t wph0 = 0, wph1 = 0, inph0 = 0, inph1 = 0, mph = 0;
+
+    auto load_head_weights = [&]() {
+        mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
+        bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
+        bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
+        bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
+    };
+    auto load_in = [&](int tile, int t) {
+        uint64_t* b = inbar + (t & 1);
+        mbar_arrive_expect_tx(b, 8192);
+        bulk_g2s(IN + (t & 1) * 8192, reinterpret_cast<const uint8_t*>(p.x) + ((size_t)tile * 8 + t) * 8192, 8192, b);
+    };
+    auto wait_in = [&](int s) {
+        if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
+    };
+    auto begin_op = [&](int op) -> uint8_t* {
+        if (tid == 0 && op + 1 < NOPS) {
+            uint64_t* b = wbar + ((op + 1) & 1);
+            mbar_arrive_expect_tx(b, p.bytes[op + 1]);
+            bulk_g2s(WA + (((op + 1) & 1) ? W_SLOT1 : 0), p.wimg + p.off[op + 1], p.bytes[op + 1], b);
+        }
+        if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
+        return WA + ((op & 1) ? W_SLOT1 : 0);
+    };
+    auto sync_before_mma = [&]() {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+    auto wait_mma = [&]() {
+        mbar_wait(mbar, mph);
+        mph ^= 1u;
+        tc_fence_after();
+    };
+
+    if (tid == 0 && blockIdx.x < p.n_tiles) {
+        load_head_weights();
+        load_in(blockIdx.x, 0);
+    }
+
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        // ------------------------------ blocks.2.0 at 8x8: eight sub-tiles of 2 crops ------------------------------------------
+        mbar_wait(wbar, wph0); wph0 ^= 1u;
+        const float* b5 = reinterpret_cast<const float*>(WA);
+        const float* w5 = b5 + 32;
+        const float* b6 = reinterpret_cast<const float*>(WA + H_OFF1);
+        const uint32_t w6 = smem_u32(WA + H_OFF1 + 96 * 4);
+        const float* b7 = reinterpret_cast<const float*>(WA + H_OFF2);
+        const float* w7 = b7 + 96;
+        if (tid == 0) {
+            mbar_arrive_expect_tx(wbar + 1, p.bytes[3]);
+            bulk_g2s(WA + W_SLOT1, p.wimg + p.off[3], p.bytes[3], wbar + 1);
+        }
+        for (int t = 0; t < 8; ++t) {
+            if (tid == 0 && t < 7) load_in(tile, t + 1);
+            wait_in(t & 1);
+            dw5x5_p2(IN + (t & 1) * 8192, A5, w5, b5, tid);                                 // L5 dw_start 5x5 (no act)
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                issue_gemm(smem_u32(A5), 32, w6, 96, 0, 96, tmem + ACC, false, 2);           // L6 pw_exp 32 -> 96
+                mma_commit(mbar);
+            }
+            wait_mma();
+            epi_to_tile<true>(trow, ACC, 96, b6, E6, 0, row, cs);
+            __syncthreads();
+            dw5x5s2_p2(E6, A7 + (t >> 2) * 24576, (2 * t) & 7, w7, b7, tid);                 // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
+            __syncthreads();
+        }
+        // ------------------------------ 4x4 phase: 2 M-tiles of 8 crops -----------------------------------------------------------
+        int op = 3;
+        {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
+            uint8_t* wb = begin_op(op);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+            __syncthreads();
+            ++op;
+        }
+#pragma unroll 1
+        for (int blk = 1; blk <= 4; ++blk) {
+            {   // pw_exp 48 -> 96 (+ReLU)
+                uint8_t* wb = begin_op(op);
+                sync_before_mma();
+                if (tid == 0) {
+                    tc_fence_after();
+                    for (int m = 0; m < 2; ++m)
+                        issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
+                    mma_commit(mbar);
+                }
+                wait_mma();
+                epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
+                __syncthreads();
+                ++op;
+            }
+            {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
+                uint8_t* wb = begin_op(op);
+                const float* b = reinterpret_cast<const float*>(wb);
+                dw3x3_p8_inplace<6>(R, 2 * 128 * 12, 12, b + 96, b, true, tid);
+                __syncthreads();
+                ++op;
+            }
+            {   // pw_proj 96 -> 48 accumulated onto the residual stream
+                uint8_t* wb = begin_op(op);
+                sync_before_mma();
+                if (tid == 0) {
+                    tc_fence_after();
+                    for (int m = 0; m < 2; ++m)
+                        issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+                    mma_commit(mbar);
+                }
+                wait_mma();
+                epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+                __syncthreads();
+                ++op;
+            }
+        }
+        // ------------------------------ blocks.2.5: dw_start 3x3, pw_exp 48 -> 192 (two column halves), pw_proj 192 -> 48 ------------
+        uint8_t* E22a = R;
+        uint8_t* E22b = R + 49152;               // second half runs into the X16 region (dead once the L22 MMAs have read it)
+        {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
+            uint8_t* wb = begin_op(op);
+            const float* b21 = reinterpret_cast<const float*>(wb);
+            dw3x3_p8_inplace<3>(X16, 2 * 128 * 6, 6, b21 + 48, b21, false, tid);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
+            __syncthreads();
+            ++op;
+        }
+        {   // op 17: W22 columns 96..191
+            uint8_t* wb = begin_op(op);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
+            __syncthreads();
+            ++op;
+        }
+        const float* cum23;
+        {   // op 18: W23 K rows 0..95 (+ cumulative bias)
+            uint8_t* wb = begin_op(op);
+            cum23 = reinterpret_cast<const float*>(wb);
+            sync_before_mma();
+            if (tid == 0) {
+                tc_fence_after();
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+            }
+            ++op;
+        }
+        {   // op 19: W23 K rows 96..191, then the stage output
+            uint8_t* wb = begin_op(op);
+            if (tid == 0) {
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+                mma_commit(mbar);
+            }
+            wait_mma();
+            uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + mt) * 6 * 128;
+            epi_to_global(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2);
+            ++op;
+        }
+        const int next = tile + gridDim.x;
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0 && next < p.n_tiles) {
+            load_head_weights();
+            load_in(next, 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
 // crop-major T8 tiles (row = crop*16 + pix) -> P8 tiles (row = pix*8 + crop_local); one thread per 16-byte chunk.
 __global__ void permute_p8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_chunks) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -460,12 +817,25 @@ __global__ void permute_p8_kernel(const uint4* __restrict__ in, uint4* __restric
     out[(i & ~(int64_t)127) + ((r & 15) * 8 + (r >> 4))] = in[i];
 }
 
+// crop-major T8 tiles of 8x8 maps (128 rows = 2 crops, row = crop*64 + pix) -> P2 tiles (row = pix*2 + crop_local).
+__global__ void permute_p2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_chunks) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_chunks) return;
+    const int r = (int)(i & 127);
+    out[(i & ~(int64_t)127) + ((r & 63) * 2 + (r >> 6))] = in[i];
+}
+
 // ---- stage weight image construction --------------------------------------------------------------------------------------
-__global__ void prep_pw_part_kernel(const float* __restrict__ w, int K, int n_total, int n0, int n, bf16* __restrict__ dst) {
+// rows [k0, k0+K) x columns [n0, n0+n) of w[.][n_total] -> UMMA B image [K/8][n][8]; parts == 2 appends the lo image
+// (w - bf16(w), itself rounded to bf16) right after the hi image.
+__global__ void prep_pw_part_kernel(const float* __restrict__ w, int k0, int K, int n_total, int n0, int n, int parts, bf16* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * n) return;
     const int kk = i & 7, j = (i >> 3) % n, kc = (i >> 3) / n;
-    dst[i] = __float2bfloat16_rn(w[(size_t)(kc * 8 + kk) * n_total + n0 + j]);
+    const float v = w[(size_t)(k0 + kc * 8 + kk) * n_total + n0 + j];
+    const bf16 hi = __float2bfloat16_rn(v);
+    dst[i] = hi;
+    if (parts == 2) dst[(size_t)K * n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 // 2x2-map depthwise weights: dst[((c8*4 + p)*4 + q)*8 + i] = w[tap(p,q)][c8*8 + i], tap = (qy-py+pad)*K + (qx-px+pad).
 __global__ void prep_dw2x2_kernel(const float* __restrict__ w, int K, int C, float* __restrict__ dst) {
@@ -532,7 +902,7 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
                     CV_CUDA(cudaMemcpyAsync(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 }
             } else if (d.kind == 3) {
-                prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 64, 480, 160 * part, 160, reinterpret_cast<bf16*>(dst));
+                prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 0, 64, 480, 160 * part, 160, 1, reinterpret_cast<bf16*>(dst));
                 CV_CHECK_LAUNCH();
                 ++part;
             } else {
@@ -545,7 +915,7 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
                 } else {
                     CV_CUDA(cudaMemcpyAsync(f, blob + l.b_offset, l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 }
-                prep_pw_part_kernel<<<(l.cin * l.cout + 255) / 256, 256, 0, s>>>(blob + l.w_offset, l.cin, l.cout, 0, l.cout,
+                prep_pw_part_kernel<<<(l.cin * l.cout + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 0, l.cin, l.cout, 0, l.cout, 1,
                                                                                 reinterpret_cast<bf16*>(dst + (size_t)l.cout * 4));
                 CV_CHECK_LAUNCH();
             }
@@ -573,6 +943,109 @@ int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const 
     CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     stageD_kernel<<<grid, NT, sd::SMEM, s>>>(p);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+// ---- stage C image: every pointwise blob carries W_hi | W_lo -----------------------------------------------------------------
+namespace {
+struct COp { int layer, kind; };   // 0 dw | 1 pw own bias | 2 pw_proj cumulative bias | 5 dw21 + pw22 cols 0..95 | 6 pw22 cols 96..191 | 7 pw23 K 0..95 | 8 pw23 K 96..191
+const COp kCOps[sc::NOPS] = {{5, 0}, {6, 1}, {7, 0}, {8, 2}, {9, 1}, {10, 0}, {11, 2}, {12, 1}, {13, 0}, {14, 2}, {15, 1}, {16, 0}, {17, 2},
+                             {18, 1}, {19, 0}, {20, 2}, {22, 5}, {22, 6}, {23, 7}, {23, 8}};
+uint32_t cop_bytes(int op) {
+    const cv_layer_info* L = cv_layers();
+    const COp& d = kCOps[op];
+    const cv_layer_info& l = L[d.layer];
+    switch (d.kind) {
+        case 0: return (uint32_t)(l.cout + l.k * l.k * l.cout) * 4;
+        case 1: case 2: return (uint32_t)l.cout * 4 + (uint32_t)l.cin * l.cout * 4;
+        case 5: return 1920 + 96 * 4 + 48 * 96 * 4;
+        case 6: return 96 * 4 + 48 * 96 * 4;
+        case 7: return 48 * 4 + 96 * 48 * 4;
+        default: return 96 * 48 * 4;
+    }
+}
+}  // namespace
+
+size_t stageC_image_bytes() {
+    size_t n = 0;
+    for (int op = 0; op < sc::NOPS; ++op) n += (cop_bytes(op) + 127) / 128 * 128;
+    return n;
+}
+
+int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s) {
+    const cv_layer_info* L = cv_layers();
+    size_t o = 0;
+    const float* prev_cum = nullptr;
+    auto copy_f = [&](float* dst, const float* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s); };
+    auto pw = [&](const cv_layer_info& l, int k0, int K, int n0, int n, uint8_t* dst) {
+        prep_pw_part_kernel<<<(K * n + 255) / 256, 256, 0, s>>>(blob + l.w_offset, k0, K, l.cout, n0, n, 2, reinterpret_cast<bf16*>(dst));
+    };
+    for (int op = 0; op < sc::NOPS; ++op) {
+        const COp& d = kCOps[op];
+        const cv_layer_info& l = L[d.layer];
+        off[op] = (uint32_t)o;
+        bytes[op] = cop_bytes(op);
+        uint8_t* dst = img + o;
+        float* f = reinterpret_cast<float*>(dst);
+        switch (d.kind) {
+            case 0:
+                CV_CUDA(copy_f(f, blob + l.b_offset, l.cout));
+                CV_CUDA(copy_f(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout));
+                break;
+            case 1:
+                CV_CUDA(copy_f(f, blob + l.b_offset, l.cout));
+                pw(l, 0, l.cin, 0, l.cout, dst + (size_t)l.cout * 4);
+                break;
+            case 2:
+                add_f32_kernel<<<1, 64, 0, s>>>(f, l.skip >= 0 ? prev_cum : nullptr, blob + l.b_offset, l.cout);
+                prev_cum = f;
+                pw(l, 0, l.cin, 0, l.cout, dst + (size_t)l.cout * 4);
+                break;
+            case 5: {
+                const cv_layer_info& l21 = L[21];
+                CV_CUDA(copy_f(f, blob + l21.b_offset, 48));
+                CV_CUDA(copy_f(f + 48, blob + l21.w_offset, 9 * 48));
+                CV_CUDA(copy_f(f + 480, blob + l.b_offset, 96));
+                pw(l, 0, 48, 0, 96, dst + 1920 + 384);
+                break;
+            }
+            case 6:
+                CV_CUDA(copy_f(f, blob + l.b_offset + 96, 96));
+                pw(l, 0, 48, 96, 96, dst + 384);
+                break;
+            case 7:
+                add_f32_kernel<<<1, 64, 0, s>>>(f, prev_cum, blob + l.b_offset, 48);
+                pw(l, 0, 96, 0, 48, dst + 192);
+                break;
+            default:
+                pw(l, 96, 96, 0, 48, dst);
+                break;
+        }
+        CV_CHECK_LAUNCH();
+        o += (bytes[op] + 127) / 128 * 128;
+    }
+    return CV_OK;
+}
+
+int launch_permute_p2(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStream_t s) {
+    const int64_t n_chunks = n_crops * 64 * (C / 8);
+    if (n_chunks == 0) return CV_OK;
+    permute_p2_kernel<<<(unsigned)((n_chunks + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n_chunks);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8, int num_sms,
+                  cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
+    StageCParams p{};
+    p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16);
+    for (int i = 0; i < sc::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
+    CV_CUDA(cudaFuncSetAttribute(stageC_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
+    const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    stageC_kernel<<<grid, NT, sc::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
