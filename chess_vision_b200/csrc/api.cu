@@ -24,7 +24,7 @@ namespace {
 
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
-constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128;
+constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512;   // fused stages: persistent kernels want many tiles per SM
 constexpr int MAX_CHUNK = 4096;      // boards whose pooled features are kept for one global-head launch
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -42,6 +42,7 @@ struct cv_square {
     bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
     uint8_t* sd_img = nullptr;    // weight image of the fused tail (stage D)
     uint32_t sd_off[CV_STAGE_D_OPS], sd_bytes[CV_STAGE_D_OPS];
+    uint8_t* sb_img = nullptr;    // weight image of the fused blocks.0.1 + blocks.1 stage (stage B)
     uint8_t* sc_img = nullptr;    // weight image of the fused blocks.2 stage (stage C)
     uint32_t sc_off[CV_STAGE_C_OPS], sc_bytes[CV_STAGE_C_OPS];
     int num_sms = 148;
@@ -111,14 +112,16 @@ struct WavePlan {
 
 WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
     WavePlan p;
-    int def = precision == CV_PRECISION_FP32 ? DEFAULT_WAVE_FP32 : DEFAULT_WAVE_BF16;
+    const bool bf = precision != CV_PRECISION_FP32;
+    int def = !bf ? DEFAULT_WAVE_FP32 : (h->impl & CV_IMPL_TAIL) ? DEFAULT_WAVE_FUSED : DEFAULT_WAVE_BF16;
     p.wave = h->wave > 0 ? h->wave : def;
     if (p.wave > max_boards) p.wave = std::max(max_boards, 1);
-    p.es = precision == CV_PRECISION_FP32 ? 4 : 2;
+    p.es = bf ? 2 : 4;
     const size_t n = (size_t)p.wave * 64;
+    const bool fused_front = bf && (h->impl & CV_IMPL_FRONTEND);    // crops and stem output never reach HBM
     size_t off = 0;
-    p.off_crops = off; off = align_up(off + n * EL_CROPS * p.es);
-    p.off_stem = off; off = align_up(off + n * EL_STEM * p.es);
+    p.off_crops = off; off = align_up(off + (fused_front ? 0 : n * EL_CROPS * p.es));
+    p.off_stem = off; off = align_up(off + (fused_front ? 0 : n * EL_STEM * p.es));
     for (int b = 0; b < NBUF_SMALL; ++b) { p.off_small[b] = off; off = align_up(off + n * EL_SMALL * p.es); }
     const size_t chunk = (size_t)std::min(std::max(max_boards, 1), MAX_CHUNK);
     p.off_feat = off; off = align_up(off + chunk * 64 * 480 * sizeof(float));
@@ -174,7 +177,8 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     // bf16: blocks.3.* + blocks.4.0 + pool + heads fused into one persistent kernel (stage D) fed by layer 23's output
     const bool fused_tail = sizeof(T) == 2 && (h->impl & CV_IMPL_TAIL);
     const bool fused_mid = fused_tail && (h->impl & CV_IMPL_MID);          // blocks.2.* as one kernel too (stage C)
-    const int end_layer = fused_mid ? 5 : fused_tail ? 24 : CV_NUM_LAYERS;
+    const bool fused_early = fused_mid && (h->impl & CV_IMPL_EARLY) && first_layer == 2;   // blocks.0.1 + blocks.1.* (stage B) after the fused front end
+    const int end_layer = fused_early ? 2 : fused_mid ? 5 : fused_tail ? 24 : CV_NUM_LAYERS;
     for (int i = 0; i < end_layer; ++i) {
         const cv_layer_info& L = kLayers[i];
         T* out = buf_of(i);
@@ -196,16 +200,30 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
         int rc;
         T* p8;
         if (fused_mid) {
-            rc = prof_mark(h, CV_PROF_MID, s);
-            if (rc) return rc;
-            T* p2 = small[(h->out_buf[4] + 1) % NBUF_SMALL];               // any two buffers but layer 4's own
-            p8 = small[(h->out_buf[4] + 2) % NBUF_SMALL];
-            rc = launch_permute_p2(reinterpret_cast<const bf16*>(buf_of(4)), reinterpret_cast<bf16*>(p2), n, 32, s);
-            if (rc) return rc;
+            T* p2;
+            if (fused_early) {
+                rc = prof_mark(h, CV_PROF_EARLY, s);
+                if (rc) return rc;
+                p2 = small[(h->out_buf[1] + 1) % NBUF_SMALL];               // any two buffers but layer 1's own
+                p8 = small[(h->out_buf[1] + 2) % NBUF_SMALL];
+                rc = launch_stageB(reinterpret_cast<const bf16*>(buf_of(1)), n, h->sb_img, reinterpret_cast<bf16*>(p2), h->num_sms, s);
+                if (rc) return rc;
+                ++h->launches;
+                rc = prof_mark(h, CV_PROF_MID, s);
+                if (rc) return rc;
+            } else {
+                rc = prof_mark(h, CV_PROF_MID, s);
+                if (rc) return rc;
+                p2 = small[(h->out_buf[4] + 1) % NBUF_SMALL];               // any two buffers but layer 4's own
+                p8 = small[(h->out_buf[4] + 2) % NBUF_SMALL];
+                rc = launch_permute_p2(reinterpret_cast<const bf16*>(buf_of(4)), reinterpret_cast<bf16*>(p2), n, 32, s);
+                if (rc) return rc;
+                ++h->launches;
+            }
             rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img, h->sc_off, h->sc_bytes, reinterpret_cast<bf16*>(p8),
                                h->num_sms, s);
             if (rc) return rc;
-            h->launches += 2;
+            ++h->launches;
             rc = prof_mark(h, CV_PROF_TAIL, s);
             if (rc) return rc;
         } else {
@@ -346,6 +364,7 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->sd_img, stageD_image_bytes()));
     CV_CUDA(cudaMalloc(&h->sc_img, stageC_image_bytes()));
+    CV_CUDA(cudaMalloc(&h->sb_img, stageB_image_bytes()));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     float lut[768];
     default_lut(lut);
@@ -357,7 +376,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -396,6 +415,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     rc = build_stageD_image(h->blob, h->sd_img, h->sd_off, h->sd_bytes, s);
     if (rc) return rc;
     rc = build_stageC_image(h->blob, h->sc_img, h->sc_off, h->sc_bytes, s);
+    if (rc) return rc;
+    rc = build_stageB_image(h->blob, h->sb_img, s);
     if (rc) return rc;
     float* hw = h->head_w;
     CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -809,6 +809,165 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 }
 
 
+// =====================================================================================================================
+// stage B: blocks.0.1 (1x1 16->16 @16x16), blocks.1.0 (3x3 s2 16->48 -> 8x8), blocks.1.1 (1x1 48->32).  Tile = 2 crops,
+// 256 threads, ~103 KB smem and 256 TMEM columns per CTA so that TWO CTAs share an SM and overlap each other's
+// MMA / epilogue phases.  All weights (hi + lo) stay resident in shared memory for the whole kernel.
+// =====================================================================================================================
+namespace sb {
+constexpr int NTB = 256;
+constexpr int W_BYTES = 384 + 1024 + 27648 + 6144;     // [b2 16 | b3 48 | b4 32] fp32, W2 hi|lo, W3 hi|lo, W4 hi|lo
+constexpr int OFF_W = 0;
+constexpr int OFF_A3 = 35328;             // 36864: im2col image of the blocks.0.1 output = A operand of blocks.1.0 [18][128][8]
+constexpr int OFF_IN = OFF_A3 + 36864;    // 2 x 16384: input ring (2 crops = 4 T8 tiles of 128 rows x 16 ch); the consumed slot is reused as A4
+constexpr int OFF_BAR = OFF_IN + 32768;   // 104960
+constexpr int SMEM = OFF_BAR + 64;
+constexpr int W2_OFF = 384, W3_OFF = 1408, W4_OFF = 29056;
+}  // namespace sb
+
+struct StageBParams {
+    const bf16* x;            // front-end output: T8 tiles, rows = crop*256 + pixel (16x16), 16 ch
+    const uint8_t* wimg;      // sb::W_BYTES
+    bf16* y;                  // P2 tiles (128 rows = 2 crops at 8x8, row = pix*2 + crop) x 32 ch == stage C input
+    int n_tiles;              // n_crops / 2
+};
+
+__global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constant__ StageBParams p) {
+    using namespace sb;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* W = smem + OFF_W;
+    uint8_t* A3 = smem + OFF_A3;
+    uint8_t* IN = smem + OFF_IN;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t* wbar = bars;
+    uint64_t* inbar = bars + 1;       // [2]
+    uint64_t* mbar = bars + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, hi2 = warp >> 2, row = quad * 32 + lane;
+
+    if (tid == 0) {
+        mbar_init(wbar, 1); mbar_init(inbar, 1); mbar_init(inbar + 1, 1); mbar_init(mbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 256);
+    for (int i = tid; i < 36864 / 16; i += NTB) reinterpret_cast<uint4*>(A3)[i] = make_uint4(0, 0, 0, 0);   // padding taps stay zero
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+    uint32_t inph0 = 0, inph1 = 0, mph = 0;
+    const float* b2 = reinterpret_cast<const float*>(W);
+    const float* b3 = b2 + 16;
+    const float* b4 = b2 + 64;
+
+    auto load_in = [&](int tile, int s) {
+        mbar_arrive_expect_tx(inbar + s, 16384);
+        bulk_g2s(IN + s * 16384, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * 16384, 16384, inbar + s);
+    };
+    auto wait_mma = [&]() {
+        mbar_wait(mbar, mph);
+        mph ^= 1u;
+        tc_fence_after();
+    };
+    auto sync_before_mma = [&]() {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+    };
+    if (tid == 0) {
+        mbar_arrive_expect_tx(wbar, W_BYTES);
+        bulk_g2s(W, p.wimg, W_BYTES, wbar);
+        if (blockIdx.x < p.n_tiles) load_in(blockIdx.x, 0);
+    }
+    mbar_wait(wbar, 0);
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        uint8_t* in = IN + s * 16384;
+        if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) load_in(tile + gridDim.x, s ^ 1);
+        if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
+        // ---- blocks.0.1: 1x1 16 -> 16 (+ReLU) on 512 rows = 4 M-tiles
+        if (tid == 0) {
+            tc_fence_after();
+            for (int j = 0; j < 4; ++j) issue_gemm(smem_u32(in + j * 4096), 16, smem_u32(W + W2_OFF), 16, 0, 16, tmem + 16 * j, false, 2);
+            mma_commit(mbar);
+        }
+        wait_mma();
+        // epilogue: scatter every output pixel into the im2col image of the 3x3 stride-2 conv that follows
+        // (A3 chunk = tap*2 + channel-half, row = (oy*8+ox)*2 + crop): a pixel feeds 1, 2 or 4 (tap, output) pairs.
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int j = hi2 * 2 + jj;
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(16 * j), r);
+            tmem_ld_wait();
+            uint4 o[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * h + i]) + b2[8 * h + i], 0.f);
+                o[h] = pack8(v);
+            }
+            const int rg = j * 128 + row, crop = rg >> 8, iy = (rg >> 4) & 15, ix = rg & 15;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+                const int ty = iy + 1 - ky;
+                if ((ty & 1) || ty < 0 || ty > 14) continue;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int tx = ix + 1 - kx;
+                    if ((tx & 1) || tx < 0 || tx > 14) continue;
+                    const int ra = ((ty >> 1) * 8 + (tx >> 1)) * 2 + crop, ch = (ky * 3 + kx) * 2;
+                    *reinterpret_cast<uint4*>(A3 + (((size_t)ch * 128 + ra) << 4)) = o[0];
+                    *reinterpret_cast<uint4*>(A3 + (((size_t)(ch + 1) * 128 + ra) << 4)) = o[1];
+                }
+            }
+        }
+        sync_before_mma();
+        // ---- blocks.1.0: 3x3 s2 16 -> 48 (+ReLU) as one K = 144 GEMM on 128 rows (2 crops x 8x8, P2 order)
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(smem_u32(A3), 144, smem_u32(W + W3_OFF), 48, 0, 48, tmem + 64, false, 2);
+            mma_commit(mbar);
+        }
+        wait_mma();
+        uint8_t* A4 = in;                       // the input slot is dead (its MMAs completed): reuse it for the next operand
+        epi_to_tile<true>(trow, 64, 48, b3, A4, 0, row, hi2, 2);
+        sync_before_mma();
+        // ---- blocks.1.1: 1x1 48 -> 32 (+ReLU) -> global P2 tile
+        if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(smem_u32(A4), 48, smem_u32(W + W4_OFF), 32, 0, 32, tmem + 128, false, 2);
+            mma_commit(mbar);
+        }
+        wait_mma();
+        {
+            uint32_t r[16];
+            tmem_ld16(trow + (uint32_t)(128 + 16 * hi2), r);
+            tmem_ld_wait();
+            uint4* dst = reinterpret_cast<uint4*>(p.y) + (size_t)tile * 4 * 128;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * h + i]) + b4[16 * hi2 + 8 * h + i], 0.f);
+                dst[(size_t)(hi2 * 2 + h) * 128 + row] = pack8(v);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+
 // crop-major T8 tiles (row = crop*16 + pix) -> P8 tiles (row = pix*8 + crop_local); one thread per 16-byte chunk.
 __global__ void permute_p8_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_chunks) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1046,6 +1205,33 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
     CV_CUDA(cudaFuncSetAttribute(stageC_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     stageC_kernel<<<grid, NT, sc::SMEM, s>>>(p);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+// ---- stage B ----------------------------------------------------------------------------------------------------------------------
+size_t stageB_image_bytes() { return sb::W_BYTES; }
+
+int build_stageB_image(const float* blob, uint8_t* img, cudaStream_t s) {
+    const cv_layer_info* L = cv_layers();
+    float* f = reinterpret_cast<float*>(img);
+    CV_CUDA(cudaMemcpyAsync(f, blob + L[2].b_offset, 16 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(f + 16, blob + L[3].b_offset, 48 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CV_CUDA(cudaMemcpyAsync(f + 64, blob + L[4].b_offset, 32 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    prep_pw_part_kernel<<<1, 256, 0, s>>>(blob + L[2].w_offset, 0, 16, 16, 0, 16, 2, reinterpret_cast<bf16*>(img + sb::W2_OFF));
+    prep_pw_part_kernel<<<(144 * 48 + 255) / 256, 256, 0, s>>>(blob + L[3].w_offset, 0, 144, 48, 0, 48, 2, reinterpret_cast<bf16*>(img + sb::W3_OFF));
+    prep_pw_part_kernel<<<(48 * 32 + 255) / 256, 256, 0, s>>>(blob + L[4].w_offset, 0, 48, 32, 0, 32, 2, reinterpret_cast<bf16*>(img + sb::W4_OFF));
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_stageB(const bf16* x, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    if (n_crops % 2 != 0) { cv_set_error("stage B: odd crop count %lld", (long long)n_crops); return CV_ERR_ARG; }
+    StageBParams p{x, wimg, y_p2, (int)(n_crops / 2)};
+    CV_CUDA(cudaFuncSetAttribute(stageB_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::SMEM));
+    const int grid = p.n_tiles < 2 * num_sms ? p.n_tiles : 2 * num_sms;
+    stageB_kernel<<<grid, sb::NTB, sb::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }

@@ -76,7 +76,7 @@ class ChessSquareCNN(nn.Module):
         if self._handle is not None:
             _native.check(_native.lib().cv_square_set_wave(self._handle, self._wave))
 
-    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS, IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_DEFAULT = 1, 2, 4, 8, 16, 32, 64, 127
+    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS, IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_DEFAULT = 1, 2, 4, 8, 16, 32, 64, 128, 255
 
     def set_impl(self, mask: int):
         """Select the bf16 kernels (``cv_square_set_impl``); clearing a bit falls back to the plain CUDA-core
@@ -273,8 +273,8 @@ class ChessSquareCNN(nn.Module):
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_native.lib().cv_square_launch_count(self._handle))
 
-    PROF_SLOTS = 52
-    PROF_NAMES = ["crop_gather"] + [f"L{l.index}:{l.key}" for l in arch.LAYERS] + ["pool_heads", "global_head", "fen", "frontend(crop+stem+b0.0)", "tail(blocks.3+4+pool+heads)", "mid(blocks.2)"]
+    PROF_SLOTS = 53
+    PROF_NAMES = ["crop_gather"] + [f"L{l.index}:{l.key}" for l in arch.LAYERS] + ["pool_heads", "global_head", "fen", "frontend(crop+stem+b0.0)", "tail(blocks.3+4+pool+heads)", "mid(blocks.2)", "early(blocks.0.1+blocks.1)"]
 
     def profile(self, enable: bool):
         """Record a CUDA event before every kernel of the path (``cv_square_profile``)."""

