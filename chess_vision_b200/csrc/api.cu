@@ -36,6 +36,7 @@ struct cv_square {
     bool loaded = false;
     float* blob = nullptr;        // fp32 packed weights (device, owned)
     float* glob_wt = nullptr;     // global_head weight transposed to [30720][64] (device, owned)
+    float* glob_wtile = nullptr;  // global_head weight in the tf32 UMMA operand layout [30720/4][64][4] (kernels_head.cu)
     float* head_w = nullptr;      // aligned copies of the small heads: head_w[10*480], head_b[10], glob_b[64], tc_w[320], tc_b[5]
     float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
     bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
@@ -107,7 +108,7 @@ inline int prof_mark(cv_square* h, int slot, cudaStream_t s) {
 struct WavePlan {
     int wave;
     size_t es;                        // activation element size
-    size_t off_crops, off_stem, off_small[NBUF_SMALL], off_feat, off_sq, off_turn, off_cast, total;
+    size_t off_crops, off_stem, off_small[NBUF_SMALL], off_feat, off_partial, off_sq, off_turn, off_cast, total;
 };
 
 WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
@@ -124,7 +125,10 @@ WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
     p.off_stem = off; off = align_up(off + (fused_front ? 0 : n * EL_STEM * p.es));
     for (int b = 0; b < NBUF_SMALL; ++b) { p.off_small[b] = off; off = align_up(off + n * EL_SMALL * p.es); }
     const size_t chunk = (size_t)std::min(std::max(max_boards, 1), MAX_CHUNK);
-    p.off_feat = off; off = align_up(off + chunk * 64 * 480 * sizeof(float));
+    // pooled features of one chunk: row-major, or FT-tiled (whole 128-board tiles) for the tensor-core global head
+    const bool tiled = bf && (h->impl & CV_IMPL_TAIL);
+    p.off_feat = off; off = align_up(off + (tiled ? ft_floats((int)chunk) : chunk * 64 * 480) * sizeof(float));
+    p.off_partial = off; off = align_up(off + (tiled ? global_head_partial_floats((int)chunk, h->num_sms) * sizeof(float) : 0));
     // scratch logits for the predict entry points (whole batch)
     p.off_sq = off; off = align_up(off + (size_t)max_boards * 832 * sizeof(float));
     p.off_turn = off; off = align_up(off + (size_t)max_boards * sizeof(float));
@@ -165,8 +169,8 @@ int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16*
 }
 
 template <typename T>
-int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, bool first_wave,
-             int first_layer, cudaStream_t s) {
+int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, float* feat_chunk, int64_t crop_base,
+             bool first_wave, int first_layer, cudaStream_t s) {
     const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
@@ -234,7 +238,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
             if (rc) return rc;
             ++h->launches;
         }
-        rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img, h->sd_off, h->sd_bytes, feat, squares, h->num_sms, s);
+        rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img, h->sd_off, h->sd_bytes, feat_chunk, 1, crop_base, squares, h->num_sms, s);
         if (rc) return rc;
         ++h->launches;
         return CV_OK;
@@ -282,19 +286,30 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
             else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
             if (rc) return rc;
             ++h->launches;
-            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, b0 == 0,
+            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0,
                              fused_front ? 2 : 0, s);
             if (rc) return rc;
         }
         rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
         if (rc) return rc;
-        rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0,
-                                castling + (size_t)c0 * 4, precision == CV_PRECISION_FP32, s);
-        if (rc) return rc;
-        ++h->launches;
-        if (features)
-            CV_CUDA(cudaMemcpyAsync(features + (size_t)c0 * 30720, feat, (size_t)cb * 30720 * sizeof(float),
-                                    cudaMemcpyDeviceToDevice, s));
+        if (sizeof(T) == 2 && (h->impl & CV_IMPL_TAIL)) {          // features are FT-tiled: tensor-core split-K GEMM + finishing kernel
+            rc = launch_global_head_umma(feat, h->glob_wtile, reinterpret_cast<float*>(ws + p.off_partial), h->head_w + 4816,
+                                         h->head_w + 4880, h->head_w + 5200, cb, h->num_sms, turn + c0, castling + (size_t)c0 * 4, s);
+            if (rc) return rc;
+            h->launches += 2;
+            if (features) {
+                rc = launch_untile_features(feat, features + (size_t)c0 * 30720, cb, s);
+                if (rc) return rc;
+            }
+        } else {
+            rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0,
+                                    castling + (size_t)c0 * 4, precision == CV_PRECISION_FP32, s);
+            if (rc) return rc;
+            ++h->launches;
+            if (features)
+                CV_CUDA(cudaMemcpyAsync(features + (size_t)c0 * 30720, feat, (size_t)cb * 30720 * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, s));
+        }
     }
     return prof_mark(h, -1, s);
 }
@@ -358,6 +373,7 @@ int cv_square_create(int device, cv_square** out) {
         }
     CV_CUDA(cudaMalloc(&h->blob, (size_t)CV_BLOB_FLOATS * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->glob_wt, (size_t)30720 * 64 * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->glob_wtile, (size_t)30720 * 64 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
@@ -376,7 +392,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -407,6 +423,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     CV_CUDA(cudaSetDevice(h->device));
     CV_CUDA(cudaMemcpyAsync(h->blob, blob, n_floats * sizeof(float), cudaMemcpyDeviceToDevice, s));
     int rc = launch_transpose_f32(h->blob + CV_OFF_GLOB_W, h->glob_wt, 64, 30720, s);
+    if (rc) return rc;
+    rc = launch_tile_glob_w(h->blob + CV_OFF_GLOB_W, h->glob_wtile, s);
     if (rc) return rc;
     rc = launch_umma_prep_weights(h->blob, h->wimg, s);
     if (rc) return rc;

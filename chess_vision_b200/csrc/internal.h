@@ -142,8 +142,10 @@ enum { CV_STAGE_D_OPS = 24 };
 size_t stageD_image_bytes();
 int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
 int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, cudaStream_t s);
+// features: row-major [crops][480] (tiled == 0, indexed from this launch's first crop) or the FT operand layout of the
+// tensor-core global head (tiled == 1: `features` is the chunk's FT base and crop_base the launch's first crop in the chunk).
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes,
-                  float* features, float* squares, int num_sms, cudaStream_t s);
+                  float* features, int tiled, int64_t crop_base, float* squares, int num_sms, cudaStream_t s);
 
 // stage C = blocks.2.* (19 conv layers).  Input: "P2" tiles (128 rows = 2 crops at 8x8, row = pixel*2 + crop_local, 32 ch);
 // output: the P8 tiles stage D consumes.
@@ -158,3 +160,12 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
 size_t stageB_image_bytes();
 int build_stageB_image(const float* blob, uint8_t* img, cudaStream_t s);
 int launch_stageB(const bf16* x_t8, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, cudaStream_t s);
+
+// ---- kernels_head.cu: global_head as a split-K tcgen05 (kind::tf32) GEMM over FT-tiled features -----------------------------
+//   FT[m_tile][k/4][128 boards][4]: float index ((b/128 * 7680 + k/4) * 128 + b%128) * 4 + k%4,  k = square*480 + channel
+inline size_t ft_floats(int boards) { return (size_t)((boards + 127) / 128) * 128 * 30720; }
+int launch_tile_glob_w(const float* glob_w, float* wt, cudaStream_t s);
+size_t global_head_partial_floats(int B, int num_sms);
+int launch_global_head_umma(const float* ft, const float* wt, float* partial, const float* glob_b, const float* tc_w, const float* tc_b,
+                            int B, int num_sms, float* turn, float* castling, cudaStream_t s);
+int launch_untile_features(const float* ft, float* out_rowmajor, int B, cudaStream_t s);

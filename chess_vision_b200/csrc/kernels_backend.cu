@@ -208,9 +208,11 @@ constexpr int S_COL = 448;                      // TMEM columns [448,512): fp32 
 struct StageDParams {
     const bf16* x;            // stage input: T8 tiles of 128 P8 rows x 48 ch (one tile = 8 crops)
     const uint8_t* wimg;      // stage weight image (build_stageD_image)
-    float* features;          // [n_crops][480] pooled trunk features (square.py:90)
+    float* features;          // pooled trunk features (square.py:90): [n_crops][480], or the FT layout of kernels_head.cu (tiled)
     float* squares;           // [n_crops][13]  combined type+color logits (common.py:24)
     int n_tiles;              // n_crops / 32
+    int tiled;
+    long long crop_base;      // tiled: index of this launch's first crop inside the chunk that `features` (FT base) covers
     uint32_t off[sd::NOPS], bytes[sd::NOPS];
 };
 
@@ -419,7 +421,15 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + cs) : "memory");
                 const int ch = g * 16 + 4 * quad;
-                *reinterpret_cast<float4*>(p.features + crop * 480 + ch) = make_float4(f4[0], f4[1], f4[2], f4[3]);
+                if (p.tiled) {                                                           // operand layout of the global-head GEMM
+                    const long long cg = p.crop_base + crop;
+                    const long long b = cg >> 6;
+                    const int sq = (int)(cg & 63);
+                    reinterpret_cast<float4*>(p.features)[((b >> 7) * 7680 + sq * 120 + (ch >> 2)) * 128 + (b & 127)] =
+                        make_float4(f4[0], f4[1], f4[2], f4[3]);
+                } else {
+                    *reinterpret_cast<float4*>(p.features + crop * 480 + ch) = make_float4(f4[0], f4[1], f4[2], f4[3]);
+                }
 #pragma unroll
                 for (int r = 0; r < 10; ++r) {                                           // type_head rows 0..6, color_head rows 7..9
                     const float4 w4 = *reinterpret_cast<const float4*>(hw + r * 480 + ch);
@@ -1093,11 +1103,12 @@ int launch_permute_p8(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, float* features,
-                  float* squares, int num_sms, cudaStream_t s) {
+                  int tiled, int64_t crop_base, float* squares, int num_sms, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 32 != 0) { cv_set_error("stage D: crop count %lld is not a multiple of 32", (long long)n_crops); return CV_ERR_ARG; }
     StageDParams p{};
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
+    p.tiled = tiled; p.crop_base = crop_base;
     for (int i = 0; i < sd::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
     CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
