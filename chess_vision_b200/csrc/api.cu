@@ -41,6 +41,8 @@ struct cv_square {
     float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
     bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
     bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
+    bf16* fe2_wimg = nullptr;     // same for the second-generation front end
+    float lut_host[768];          // host copy of the normalisation table (affinity check of the second-generation front end)
     uint8_t* sd_img = nullptr;    // weight image of the fused tail (stage D)
     uint32_t sd_off[CV_STAGE_D_OPS], sd_bytes[CV_STAGE_D_OPS];
     uint8_t* sb_img = nullptr;    // weight image of the fused blocks.0.1 + blocks.1 stage (stage B)
@@ -280,8 +282,15 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 const void* src = x_u8 ? static_cast<const void*>(x_u8 + (size_t)b0 * H * H * 3)
                                        : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
                 const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
-                rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset,
-                                     h->blob + kLayers[1].b_offset, front_out, h->num_sms, s);
+                int done = 0;
+                if (kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
+                    rc = launch_frontend2(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe2_wimg,
+                                          h->blob + kLayers[0].b_offset, h->blob + kLayers[1].b_offset, front_out, h->num_sms, &done, s);
+                    if (rc) return rc;
+                }
+                if (!done)
+                    rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset,
+                                         h->blob + kLayers[1].b_offset, front_out, h->num_sms, s);
             } else if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
             else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
             if (rc) return rc;
@@ -378,13 +387,13 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
+    CV_CUDA(cudaMalloc(&h->fe2_wimg, frontend2_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->sd_img, stageD_image_bytes()));
     CV_CUDA(cudaMalloc(&h->sc_img, stageC_image_bytes()));
     CV_CUDA(cudaMalloc(&h->sb_img, stageB_image_bytes()));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
-    float lut[768];
-    default_lut(lut);
-    CV_CUDA(cudaMemcpy(h->lut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+    default_lut(h->lut_host);
+    CV_CUDA(cudaMemcpy(h->lut, h->lut_host, sizeof(h->lut_host), cudaMemcpyHostToDevice));
     *out = h;
     return CV_OK;
 }
@@ -392,7 +401,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe2_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -413,6 +422,7 @@ int cv_square_set_norm_lut(cv_square* h, const float* lut_host) {
     CV_ARG(h && lut_host, "null argument");
     CV_CUDA(cudaSetDevice(h->device));
     CV_CUDA(cudaMemcpy(h->lut, lut_host, 768 * sizeof(float), cudaMemcpyHostToDevice));
+    memcpy(h->lut_host, lut_host, sizeof(h->lut_host));
     return CV_OK;
 }
 
@@ -429,6 +439,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     rc = launch_umma_prep_weights(h->blob, h->wimg, s);
     if (rc) return rc;
     rc = launch_frontend_prep_weights(h->blob, h->fe_wimg, s);
+    if (rc) return rc;
+    rc = launch_frontend2_prep_weights(h->blob, h->fe2_wimg, s);
     if (rc) return rc;
     rc = build_stageD_image(h->blob, h->sd_img, h->sd_off, h->sd_bytes, s);
     if (rc) return rc;

@@ -169,3 +169,9 @@ size_t global_head_partial_floats(int B, int num_sms);
 int launch_global_head_umma(const float* ft, const float* wt, float* partial, const float* glob_b, const float* tc_w, const float* tc_b,
                             int B, int num_sms, float* turn, float* castling, cudaStream_t s);
 int launch_untile_features(const float* ft, float* out_rowmajor, int B, cudaStream_t s);
+
+// ---- kernels_frontend2.cu: second-generation fused front end for uint8 HWC boards (TMA-staged windows, separable resize) ----
+size_t frontend2_weight_image_elems();
+int launch_frontend2_prep_weights(const float* blob, bf16* img, cudaStream_t s);
+int launch_frontend2(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const bf16* wimg,
+                     const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s);

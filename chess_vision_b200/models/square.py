@@ -76,7 +76,7 @@ class ChessSquareCNN(nn.Module):
         if self._handle is not None:
             _native.check(_native.lib().cv_square_set_wave(self._handle, self._wave))
 
-    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS, IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_DEFAULT = 1, 2, 4, 8, 16, 32, 64, 128, 255
+    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS, IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_FRONTEND2, IMPL_DEFAULT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 511
 
     def set_impl(self, mask: int):
         """Select the bf16 kernels (``cv_square_set_impl``); clearing a bit falls back to the plain CUDA-core
