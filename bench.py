@@ -265,21 +265,39 @@ def run_native(args):
     top = int(np.argmax(prof_ms))
     per_launch_ms = prof_ms[top] / max(prof_cnt[top], 1)
     crops_per_launch = 64.0 * B * args.steps / max(prof_cnt[top], 1)
+    def span(lo, hi):          # fused kernel covering layers lo..hi: HBM in = first layer's input, out = last layer's output
+        ls = arch.LAYERS[lo:hi + 1]
+        return (ls[0].in_elems + ls[-1].out_elems) * es, 2.0 * sum(l.macs for l in ls)
     if 1 <= top <= 45:
         layer = arch.LAYERS[top - 1]
-        alg_bytes = layer_bytes(layer, es) * crops_per_launch
-        alg_flops = 2.0 * layer.macs * crops_per_launch
+        per_crop_bytes, per_crop_flops = layer_bytes(layer, es), 2.0 * layer.macs
     elif top == 0:
-        alg_bytes = (H * H * 3 / 64.0 + 64 * 64 * 3 * es) * crops_per_launch
-        alg_flops = 0.0
+        per_crop_bytes, per_crop_flops = H * H * 3 / 64.0 + 64 * 64 * 3 * es, 0.0
+    elif top == 49:            # fused front end: uint8 board bytes (each byte belongs to one square) -> blocks.0.0 output
+        per_crop_bytes = H * H * 3 / 64.0 + arch.LAYERS[1].out_elems * es
+        per_crop_flops = 2.0 * (arch.LAYERS[0].macs + arch.LAYERS[1].macs)
+    elif top == 52:
+        per_crop_bytes, per_crop_flops = span(2, 4)
+    elif top == 51:
+        per_crop_bytes, per_crop_flops = span(5, 23)
+    elif top == 50:            # fused tail: + pooled fp32 features and 13 logits out, + head dot products
+        b, f = span(24, 44)
+        per_crop_bytes = arch.LAYERS[24].in_elems * es + 480 * 4 + 13 * 4
+        per_crop_flops = f + 2.0 * 4800
+    elif top == 47:            # global head: per board 30720 fp32 features in, 5 logits out
+        per_crop_bytes, per_crop_flops = (30720 * 4 + 20) / 64.0, 2.0 * (30720 * 64 + 320) / 64.0
     else:
-        alg_bytes = (4 * 480 * es + 480 * 4 + 13 * 4) * crops_per_launch
-        alg_flops = 0.0
+        per_crop_bytes, per_crop_flops = 4 * 480 * es + 480 * 4 + 13 * 4, 0.0
+    alg_bytes, alg_flops = per_crop_bytes * crops_per_launch, per_crop_flops * crops_per_launch
     achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                 "launch_ms": per_launch_ms, "share_of_step": float(prof_ms[top] / prof_ms.sum()),
                 "tflops": alg_flops / (per_launch_ms / 1e3) / 1e12,
+                "tensor_frac_of_sustained": alg_flops / (per_launch_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
+                "algorithmic_bytes_per_crop": per_crop_bytes, "algorithmic_flops_per_crop": per_crop_flops,
+                "note": "fused kernels keep their intermediates in shared/tensor memory: they are bound by shared-memory "
+                        "bandwidth and instruction issue, neither HBM nor tensor peak (DESIGN.md section 6)",
                 "end_to_end_tensor_frac": value / world * 627.4e6 / (peaks["bf16_tflops_sustained"] * 1e12),
                 "end_to_end_hbm_frac": value / world * 196688.0 / (peaks["hbm_gbs"] * 1e9)}
     order = np.argsort(-prof_ms)[:8]
@@ -291,7 +309,7 @@ def run_native(args):
     if world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample
         cb = synthetic.synth_boards(0, sample, H, 1, dist_kind)
-        times, cpu_fens = cpu_reference_run(state, cb, 3, 1)
+        times, cpu_fens = cpu_reference_run(state, cb, 3, 1)            # ~10 s of CPU work in total
         cores = os.cpu_count()
         v = sample / min(times)
         gpu_fens32 = model.predict_fen(boards[:sample], precision="fp32")
@@ -332,7 +350,7 @@ def main():
     ap.add_argument("--size", type=int, default=256, help="board side in pixels")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--wave", type=int, default=0, help="boards per internal wave (0 = library default)")
-    ap.add_argument("--cpu-sample", type=int, default=64, help="boards per CPU-baseline step")
+    ap.add_argument("--cpu-sample", type=int, default=256, help="boards per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mask", type=int, default=-1, help="kernel selection bit mask (cv_square_set_impl); -1 = library default")
     args = ap.parse_args()
