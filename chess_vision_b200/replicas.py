@@ -47,3 +47,33 @@ def all_ranks_agree(value: int) -> bool:
     t = torch.tensor([value, -value], dtype=torch.int64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return int(t[0].item()) == value and int(-t[1].item()) == value
+
+
+def predict_stream(model, first_board: int, n_boards: int, size: int = 256, seed: int = 1, step: int = 4096,
+                   dist_kind: int = 1, with_flips: bool = False, precision=None, keep: bool = False):
+    """One rank's share of a synthetic board stream (BASELINE.json config 3): boards ``first_board ..
+    first_board+n_boards-1`` are generated on the device ``step`` at a time (counter-based, so any sharding of
+    the global index range yields the same boards), run through the fused uint8 -> FEN path, and folded into
+    an order-independent checksum (sum of per-record CRC32 mod 2^64) that ranks can all_reduce(SUM).
+    Returns (checksum, n_done, records) where ``records`` is the (n,80) uint8 host array if ``keep`` else None."""
+    import numpy as np
+    from . import _native
+    dev = model._device()
+    lib = _native.lib()
+    total = 0
+    kept = []
+    done = 0
+    boards = torch.empty((min(step, max(n_boards, 1)), size, size, 3), dtype=torch.uint8, device=dev)
+    flips = torch.empty((boards.shape[0],), dtype=torch.uint8, device=dev) if with_flips else None
+    while done < n_boards:
+        nb = min(step, n_boards - done)
+        with torch.cuda.device(dev):
+            _native.check(lib.cv_synth_boards(_native.ptr(boards), 0, first_board + done, nb, size, seed, dist_kind,
+                                              _native.ptr(flips), _native.stream_ptr(dev)))
+        fen, fen_len = model.predict_fen_device(boards[:nb], None if flips is None else flips[:nb], precision=precision)
+        rec = fen.cpu().numpy()
+        total = (total + sum(zlib.crc32(rec[i].tobytes()) for i in range(nb))) & 0xFFFFFFFFFFFFFFFF
+        if keep:
+            kept.append(rec)
+        done += nb
+    return total, done, (np.concatenate(kept) if keep and kept else None)

@@ -481,3 +481,91 @@ def test_full_batch_properties_bf16(gpu_model):
     for s in strs[:64]:
         classes |= set(dataset.fen_to_labels(s.split()[0]).tolist())
     assert len(classes) >= 10                                   # non-degenerate predictions
+
+
+# ------------------------------------------------------------------------------------------ BASELINE.json configs 1, 3, 4
+def test_config1_64_boards_fp32_fen_matches_cpu(gpu_model, gold_state):
+    """configs[0]: 64 synthetic 256x256 boards, fp32: every FEN string equals the CPU oracle's (100 % agreement)."""
+    u8 = boards_u8(256, 64, first=4000)
+    ref = oracle.forward(oracle.normalize_u8(u8), gold_state)
+    want = oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy())
+    got = gpu_model.predict_fen(torch.from_numpy(u8).cuda(), precision="fp32")
+    assert got == want
+    assert len(set(got)) == 64                              # non-degenerate: every board reads differently
+
+
+@pytest.mark.parametrize("B", [1, 2, 3, 17, 64, 257, 1000])
+def test_config4_batch_sweep_with_flips(gpu_model, gold_state, B):
+    """configs[3]: flipped-orientation boards + full FEN over a batch sweep.  fp32 mode is bit-exact against the oracle
+    for every batch size; in bf16 mode a board's record must not depend on the batch it travels in."""
+    first = 7000
+    u8 = boards_u8(256, B, first=first)
+    fl = synthetic.synth_flipped(first, B, 1)
+    n_ref = min(B, 64)                                      # the CPU oracle checks the first 64 boards of the batch
+    ref = oracle.forward(oracle.normalize_u8(u8[:n_ref]), gold_state)
+    want = oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy(), flipped=fl[:n_ref])
+    bd = torch.from_numpy(u8).cuda()
+    flt = torch.from_numpy(fl)
+    got32 = gpu_model.predict_fen(bd, flipped=flt, precision="fp32")
+    assert got32[:n_ref] == want
+    got16 = gpu_model.predict_fen(bd, flipped=flt, precision="bf16")
+    alone = gpu_model.predict_fen(bd[B - 1:B], flipped=flt[B - 1:B], precision="bf16")
+    assert alone[0] == got16[B - 1]
+    host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), flipped=flt, precision="bf16")
+    assert host == got16
+
+
+def test_config4_max_batch_65536_properties(gpu_model):
+    """configs[3] upper end: 65,536 boards (12.9 GB of uint8) in one call, with flips.  Size-independent properties:
+    any 4096-board window equals its own separate call; flipped records are the 63-i re-index of the unflipped ones."""
+    B = 65536
+    L = _native.lib()
+    boards = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device="cuda")
+    flips = torch.empty((B,), dtype=torch.uint8, device="cuda")
+    _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 10**6, B, 256, 1, 1, _native.ptr(flips), _native.stream_ptr(boards.device)))
+    fen, fen_len = gpu_model.predict_fen_device(boards, flips, precision="bf16")
+    for lo in (0, 28672, 61440):
+        f2, l2 = gpu_model.predict_fen_device(boards[lo:lo + 4096].clone(), flips[lo:lo + 4096].clone(), precision="bf16")
+        assert torch.equal(fen[lo:lo + 4096], f2) and torch.equal(fen_len[lo:lo + 4096], l2)
+    plain, plain_len = gpu_model.predict_fen_device(boards[:512], None, precision="bf16")
+    a = gpu_model.decode_fen_records(plain, plain_len)
+    b = gpu_model.decode_fen_records(fen[:512], fen_len[:512])
+    fl = flips[:512].cpu().numpy()
+    assert 100 < fl.sum() < 412
+    for x, y, f in zip(a, b, fl):
+        la, lb = dataset.fen_to_labels(x.split()[0]).tolist(), dataset.fen_to_labels(y.split()[0]).tolist()
+        assert lb == (la[::-1] if f else la) and x.split()[1:] == y.split()[1:]
+    del boards
+    torch.cuda.empty_cache()
+
+
+def test_config3_stream_sharding_is_rank_count_independent(gpu_model):
+    """configs[2]: a board stream sharded over ranks.  The ranks of a 1-, 2- and 3-way split are run one after the other
+    on this GPU; the order-independent checksum of all FEN records must not depend on the split."""
+    from chess_vision_b200 import replicas
+    n, first = 3000, 123456
+    whole, done, rec = replicas.predict_stream(gpu_model, first, n, step=1024, with_flips=True, keep=True)
+    assert done == n and rec.shape == (n, 80)
+    for world in (2, 3):
+        total, parts = 0, []
+        for rank in range(world):
+            lo, hi = replicas.shard_range(n, rank, world)
+            c, d, r = replicas.predict_stream(gpu_model, first + lo, hi - lo, step=700, with_flips=True, keep=True)
+            total = (total + c) & 0xFFFFFFFFFFFFFFFF
+            parts.append(r)
+        assert total == whole
+        assert np.array_equal(np.concatenate(parts), rec)
+
+
+def test_config5_512_boards_bf16(gpu_model, gold_state):
+    """configs[4]: 512x512 renders (96 -> 64 down-sampling crops), bf16, a batch larger than one wave."""
+    n = 600
+    L = _native.lib()
+    boards = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device="cuda")
+    _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 0, n, 512, 1, 1, None, _native.stream_ptr(boards.device)))
+    out = gpu_model.forward_u8(boards, precision="bf16", return_features=True)
+    u8 = boards[:6].cpu().numpy()
+    ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
+    assert rms_err(out["features"][:6 * 64].cpu().numpy(), ref["features"].numpy()) < BF16_TOL
+    tail = gpu_model.forward_u8(boards[-3:].clone(), precision="bf16", return_features=True)
+    assert torch.equal(tail["squares"], out["squares"][-3:]) and torch.equal(tail["turn"], out["turn"][-3:])
