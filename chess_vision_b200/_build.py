@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchessvision_b200.so")
-SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_frontend.cu", "kernels_frontend2.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu"]
+SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_frontend.cu", "kernels_frontend2.cu", "kernels_frontend3.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CV_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

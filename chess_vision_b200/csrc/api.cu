@@ -42,6 +42,8 @@ struct cv_square {
     bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
     bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
     bf16* fe2_wimg = nullptr;     // same for the second-generation front end
+    uint8_t* fe3_wimg = nullptr;  // third generation: fp16 stem image + bf16 hi|lo blocks.0.0 image, then an int "stem weights exceed fp16" flag
+    bool fe3_ok = false;          // the stem weights fit fp16 (checked when the weights are packed)
     float lut_host[768];          // host copy of the normalisation table (affinity check of the second-generation front end)
     uint8_t* sd_img = nullptr;    // weight image of the fused tail (stage D)
     uint32_t sd_off[CV_STAGE_D_OPS], sd_bytes[CV_STAGE_D_OPS];
@@ -283,7 +285,12 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                                        : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
                 const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
                 int done = 0;
-                if (kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
+                if (kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok) {
+                    rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset,
+                                          front_out, h->num_sms, &done, s);
+                    if (rc) return rc;
+                }
+                if (!done && kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
                     rc = launch_frontend2(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe2_wimg,
                                           h->blob + kLayers[0].b_offset, h->blob + kLayers[1].b_offset, front_out, h->num_sms, &done, s);
                     if (rc) return rc;
@@ -388,6 +395,7 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->fe2_wimg, frontend2_weight_image_elems() * sizeof(bf16)));
+    CV_CUDA(cudaMalloc(&h->fe3_wimg, frontend3_weight_image_bytes() + 16));
     CV_CUDA(cudaMalloc(&h->sd_img, stageD_image_bytes()));
     CV_CUDA(cudaMalloc(&h->sc_img, stageC_image_bytes()));
     CV_CUDA(cudaMalloc(&h->sb_img, stageB_image_bytes()));
@@ -401,7 +409,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe2_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe2_wimg); cudaFree(h->fe3_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
     for (int i = 0; i < 2; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
@@ -442,6 +450,9 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     if (rc) return rc;
     rc = launch_frontend2_prep_weights(h->blob, h->fe2_wimg, s);
     if (rc) return rc;
+    int* fe3_flag = reinterpret_cast<int*>(h->fe3_wimg + frontend3_weight_image_bytes());
+    rc = launch_frontend3_prep_weights(h->blob, h->fe3_wimg, fe3_flag, s);
+    if (rc) return rc;
     rc = build_stageD_image(h->blob, h->sd_img, h->sd_off, h->sd_bytes, s);
     if (rc) return rc;
     rc = build_stageC_image(h->blob, h->sc_img, h->sc_off, h->sc_bytes, s);
@@ -454,7 +465,10 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     CV_CUDA(cudaMemcpyAsync(hw + 4816, h->blob + CV_OFF_GLOB_B, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 4880, h->blob + CV_OFF_TC_W, 320 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 5200, h->blob + CV_OFF_TC_B, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    int fe3_overflow = 1;
+    CV_CUDA(cudaMemcpyAsync(&fe3_overflow, fe3_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
     CV_CUDA(cudaStreamSynchronize(s));
+    h->fe3_ok = fe3_overflow == 0;
     h->loaded = true;
     return CV_OK;
 }

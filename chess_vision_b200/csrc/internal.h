@@ -175,3 +175,9 @@ size_t frontend2_weight_image_elems();
 int launch_frontend2_prep_weights(const float* blob, bf16* img, cudaStream_t s);
 int launch_frontend2(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const bf16* wimg,
                      const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s);
+
+// ---- kernels_frontend3.cu: third generation (column-slab M tiles, fp16 stem operands, pipelined half images) ---------------
+size_t frontend3_weight_image_bytes();
+int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s);
+int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s);

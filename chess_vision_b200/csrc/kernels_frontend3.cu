@@ -1,0 +1,499 @@
+// Fused front end, third generation (uint8 HWC boards): crop gather + normalise + bilinear resize + conv_stem + blocks.0.0
+// in one persistent kernel (ChessSquareCNN._crop_squares, models/square.py:43-74, + the first two convs of the trunk, :86).
+//
+// Built on what the instrumented second generation and tools/ubench_umma.cu showed on B200:
+//   * a tcgen05.mma with M=128, K=16 costs ~48 cycles whatever N <= 64 is (the shared-memory fetch of the 4 KB A slab), so
+//     the tensor-pipe time of this kernel is (number of MMAs) x 48: the M tiles are cut as COLUMN SLABS of the activation
+//     image (8 pixels wide, 16 rows high: sixteen 8-row core matrices one image row apart, SBO = row pitch), which tiles the
+//     32x32 stem output in exactly 8 and the 16x16 blocks.0.0 output in exactly 2 tiles (9 and 3 with linear tiles);
+//   * the stem conv consumes the resized pixels as fp16 (they are bounded: |v| < 2.7) against fp16 weights: 2^-12 weight
+//     rounding instead of the bf16 W_hi + W_lo pair, so N = 32 instead of 64 -- half the TMEM traffic, no hi+lo adds in the
+//     epilogue -- and the vertical resize pass is pure half2 arithmetic writing the operand image directly; its folded-BN
+//     bias rides on a constant-one input channel; ReLU is folded into the bf16x2 conversion (cvt.rn.relu);
+//   * second generation serialised "epilogue of crop n -> blocks.0.0 MMAs of crop n -> epilogue of crop n+1" on the single
+//     stem-output image.  Here that image is split into LEFT / RIGHT halves (stem columns 0..15 / 16..31, each the input of
+//     one blocks.0.0 tile; column 15 is duplicated as the halo of the right half) rotating through three buffers, and the
+//     MMA warp interleaves  stem(n) left | b00(n-1) right | stem(n) right | b00(n) left.  The tensor pipe executes in issue
+//     order, so a stem tile's completion implies every earlier blocks.0.0 tile has finished reading its buffer: no
+//     "buffer empty" barriers are needed at all;
+//   * the issuing thread adds a constant to a precomputed descriptor word per MMA (its dependent-instruction latency is exposed).
+//
+// Warp roles (17 warps): 0-7 epilogue (group g = warp>>2 takes the stem tiles of image rows [16g, 16g+16) and blocks.0.0
+// tile g; TMEM lane quadrant = warp&3), 8-15 resize producers (warp 8 also issues the TMA row copies of the next crop),
+// 16 MMA issuer (+ TMEM owner).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_fp16.h>
+#include "internal.h"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int XP = 33, XLEAD = 8, XPOS = XLEAD + 33 * XP;      // stem operand image: 1097 positions per channel-chunk plane
+constexpr int X_CHUNK = XPOS * 16;                             // 17552
+constexpr int X_BYTES = 2 * X_CHUNK;                           // 35104
+constexpr int X_ALLOC = (X_BYTES + 127) & ~127;
+constexpr int YHP = 9, YLEAD = 8, YHPOS = YLEAD + 17 * YHP;    // half image of one parity plane: 17 rows x (halo + 8) positions
+constexpr int YH_CHUNK = YHPOS * 16;                           // 2576
+constexpr int YH_PLANE = 4 * YH_CHUNK;                         // 10304 (= 64 mod 128: the two x-parities hit different banks)
+constexpr int YH_BYTES = 4 * YH_PLANE;                         // 41216 per half
+constexpr int NYBUF = 3;
+constexpr int W_STEM_BYTES = 4 * 1024;                         // taps x [2 chunks][32 n][8] fp16
+constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) x [2 chunks][32 n = hi 16 | lo 16][8] bf16
+constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
+constexpr int HB_PITCH = 64 * 3 * 2;                           // fp16 row of 64 normalised pixels
+constexpr int NTHREADS = 17 * 32;
+constexpr int NPROD = 256;
+constexpr int TM_B00 = 256;                                    // TMEM: stem tile k at column 32 k, blocks.0.0 tile t at 256 + 32 t
+
+struct Front3Tables {                 // per launch, copied to shared memory
+    uint32_t vy[8][64];               // vertical taps of output row d for square row r: row0 | row1 << 8 | fp16(lambda) << 16
+    int16_t xo0[8][64], xo1[8][64];   // byte offsets inside a staged window row of output column d for square column c
+    float lam[64];
+    int32_t row0[8], nrows[8];        // first board row and number of rows staged for square row r
+    int32_t byte0[8], nbytes[8];      // first byte (16-aligned) and byte count (multiple of 16) of a staged row for square column c
+};
+
+struct Front3Params {
+    const uint8_t* boards;            // (B, H, H, 3) uint8
+    const uint8_t* wimg;
+    const float* bias_b00;
+    bf16* y;                          // T8 [crops*256 rows][16 ch]
+    int n_crops, H;
+    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf;
+    int off_raw, off_hb, off_y, off_w, off_tab, off_bar, smem_total;
+    float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
+    int debug;
+};
+
+// Timing experiments (-DCV_FE_PROFILE, CV_FE3_DEBUG & 256): cycles the lead lane of each role spends in each barrier wait.
+__device__ unsigned long long g_fe3_prof[4 * 16];
+#ifdef CV_FE_PROFILE
+#define TWAIT(k, call)                                                   \
+    do {                                                                 \
+        const long long _t = clock64();                                  \
+        call;                                                            \
+        if (prof_on) pacc[k] += clock64() - _t;                          \
+    } while (0)
+#else
+#define TWAIT(k, call) call
+#endif
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__ Front3Tables tab_param) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* X = smem;
+    uint8_t* RAW = smem + p.off_raw;                              // n_rawbuf x raw_bytes
+    uint8_t* HB = smem + p.off_hb;
+    uint8_t* Y = smem + p.off_y;                                  // NYBUF half images
+    uint8_t* W = smem + p.off_w;
+    const Front3Tables& tab = *reinterpret_cast<const Front3Tables*>(smem + p.off_tab);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    uint64_t *raw_full = bars, *x_full = bars + 2, *x_empty = bars + 3, *wbar = bars + 4, *yh_full = bars + 5 /*3*/, *e_full = bars + 8 /*2*/,
+             *e_empty = bars + 10 /*2*/, *d_full = bars + 12 /*8*/, *d_empty = bars + 20 /*8*/;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
+    for (int i = threadIdx.x; i < X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (NYBUF * YH_BYTES + 256) / 16; i += NTHREADS) reinterpret_cast<uint4*>(Y)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < (int)(sizeof(Front3Tables) / 4); i += NTHREADS)
+        reinterpret_cast<uint32_t*>(smem + p.off_tab)[i] = reinterpret_cast<const uint32_t*>(&tab_param)[i];
+    if (threadIdx.x == 0) {
+        mbar_init(raw_full, 1); mbar_init(raw_full + 1, 1);
+        mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(wbar, 1);
+        for (int i = 0; i < NYBUF; ++i) mbar_init(yh_full + i, 8);
+        for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_empty + i, 4); }
+        for (int i = 0; i < 8; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+        fence_barrier_init();
+    }
+    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int rawmask = p.n_rawbuf - 1;
+#ifdef CV_FE_PROFILE
+    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == 16);
+    long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_role0 = clock64();
+#endif
+
+    if (warp >= 8 && warp < 16) {
+        // =========================== resize producers (256 threads) ==========================================================
+        const int t = threadIdx.x - 256;
+        const float a0 = p.na[0], a1 = p.na[1], a2 = p.na[2], b0 = p.nb[0], b1 = p.nb[1], b2 = p.nb[2];
+        // stage the window rows of crop `nn` (iteration index iti) into RAW slot iti & rawmask: executed by warp 8 only.  The slot
+        // is free: its previous user is the horizontal pass of an earlier crop, which ended at a producer barrier.
+        auto stage_window = [&](int nn, uint32_t iti) {
+            const int slot = iti & rawmask;
+            const int64_t b = nn >> 6;
+            const int rr = (nn >> 3) & 7, cc = nn & 7;
+            const int nr = tab.nrows[rr], nbytes = tab.nbytes[cc];
+            if (lane == 0) mbar_arrive_expect_tx(raw_full + slot, (uint32_t)(nr * nbytes));
+            __syncwarp();
+            const uint8_t* src = p.boards + (b * p.H + tab.row0[rr]) * (int64_t)p.H * 3 + tab.byte0[cc];
+            uint8_t* dst = RAW + slot * p.raw_bytes;
+            for (int i = lane; i < nr; i += 32) bulk_g2s(dst + i * p.raw_pitch, src + (int64_t)i * p.H * 3, (uint32_t)nbytes, raw_full + slot);
+        };
+        if (warp == 8 && blockIdx.x < p.n_crops) stage_window(blockIdx.x, 0);
+        uint32_t it = 0;
+        for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+            const int r = (n >> 3) & 7, c = n & 7;
+            const int rslot = it & rawmask;
+            const uint8_t* raw = RAW + rslot * p.raw_bytes;
+            if (warp == 8 && p.n_rawbuf == 2 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // prefetch
+            TWAIT(0, mbar_wait(raw_full + rslot, (it / p.n_rawbuf) & 1u));
+            // ---- horizontal pass: window row i, output columns 2xp, 2xp+1 -> 6 fp16 (normalised) at HB[i][xp]
+            const int nrows = tab.nrows[r];
+            const int xp = t & 31;                               // fixed per thread: its 4 column taps are looked up once per crop
+            const int xoff[4] = {tab.xo0[c][2 * xp], tab.xo1[c][2 * xp], tab.xo0[c][2 * xp + 1], tab.xo1[c][2 * xp + 1]};
+            const float lxs[2] = {tab.lam[2 * xp], tab.lam[2 * xp + 1]};
+            for (int i = t >> 5; i < nrows; i += NPROD / 32) {
+                const uint8_t* rowp = raw + i * p.raw_pitch;
+                float v[6];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const uint8_t* q0 = rowp + xoff[2 * dx];
+                    const uint8_t* q1 = rowp + xoff[2 * dx + 1];
+                    const float lx = lxs[dx];
+                    const float u00 = (float)q0[0], u01 = (float)q0[1], u02 = (float)q0[2];
+                    const float u10 = (float)q1[0], u11 = (float)q1[1], u12 = (float)q1[2];
+                    v[dx * 3 + 0] = fmaf(a0, fmaf(lx, u10 - u00, u00), b0);
+                    v[dx * 3 + 1] = fmaf(a1, fmaf(lx, u11 - u01, u01), b1);
+                    v[dx * 3 + 2] = fmaf(a2, fmaf(lx, u12 - u02, u02), b2);
+                }
+                uint32_t* o = reinterpret_cast<uint32_t*>(HB + i * HB_PITCH + xp * 12);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                    o[k] = *reinterpret_cast<uint32_t*>(&h);
+                }
+            }
+            TWAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // HB complete, RAW slot consumed
+            if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
+            TWAIT(1, mbar_wait(x_empty, (it & 1u) ^ 1u));                                  // stem MMAs of the previous crop have read X
+            // ---- vertical pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const int sp = t + NPROD * k, py = sp >> 5, px = sp & 31;
+                uint32_t o[6];
+#pragma unroll
+                for (int dy = 0; dy < 2; ++dy) {
+                    const uint32_t vy = tab.vy[r][2 * py + dy];
+                    const uint32_t* h0 = reinterpret_cast<const uint32_t*>(HB + (vy & 255u) * HB_PITCH + px * 12);
+                    const uint32_t* h1 = reinterpret_cast<const uint32_t*>(HB + ((vy >> 8) & 255u) * HB_PITCH + px * 12);
+                    const uint32_t l2 = (vy >> 16) * 0x10001u;
+                    const __half2 ly = *reinterpret_cast<const __half2*>(&l2);
+#pragma unroll
+                    for (int w = 0; w < 3; ++w) {
+                        const uint32_t w0 = h0[w], w1 = h1[w];
+                        const __half2 f0 = *reinterpret_cast<const __half2*>(&w0), f1 = *reinterpret_cast<const __half2*>(&w1);
+                        const __half2 res = __hfma2(ly, __hsub2(f1, f0), f0);
+                        o[dy * 3 + w] = *reinterpret_cast<const uint32_t*>(&res);
+                    }
+                }
+                const int pos = XLEAD + (py + 1) * XP + px;
+                *reinterpret_cast<uint4*>(X + pos * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                // channel 12 = 1.0 (fp16 0x3C00): the centre tap's weight row 12 holds the folded-BN bias, so the GEMM adds it
+                *reinterpret_cast<uint4*>(X + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
+            }
+            fence_proxy_async_smem();
+            TWAIT(3, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // operand image complete; HB free again
+            if (t == 0) mbar_arrive(x_full);
+        }
+    } else if (warp == 16) {
+        // =========================== MMA issuer ===========================================================================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(wbar, W_BYTES);
+            bulk_g2s(W, p.wimg, W_BYTES, wbar);
+        }
+        mbar_wait(wbar, 0);
+        constexpr uint32_t idesc_s = make_idesc_f16(128, 32), idesc_1 = make_idesc_bf16(128, 32);
+        const uint32_t x_lo = desc_lo(smem_u32(X), X_CHUNK), y_lo = desc_lo(smem_u32(Y), YH_CHUNK);
+        const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), 32 * 16);
+        constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
+        // stem tiles k = 2 s + h of the crop in X: output columns [8s, 8s+8), rows [16h, 16h+16)
+        auto issue_stem = [&](int k0, uint32_t it) {
+#pragma unroll
+            for (int k = k0; k < k0 + 4; ++k) {
+                const int s = k >> 1, h = k & 1;
+                TWAIT(3, mbar_wait(d_empty + k, (it & 1u) ^ 1u));
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int tap = 0; tap < 4; ++tap) {
+                        const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
+                        mma_f16_ss2(tmem_base + k * 32, x_lo + (uint32_t)(XLEAD + (16 * h + 1 + Dy) * XP + 8 * s + Dx), x_hi, ws_lo + tap * 64, w_hi,
+                                    idesc_s, tap > 0 ? 1u : 0u);
+                    }
+                    mma_commit(d_full + k);
+                }
+                __syncwarp();
+            }
+        };
+        // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image 2 itb + t
+        auto issue_b00 = [&](int t, uint32_t itb) {
+            const uint32_t hidx = 2 * itb + t, buf = hidx % NYBUF;
+            TWAIT(0, mbar_wait(yh_full + buf, (hidx / NYBUF) & 1u));
+            TWAIT(1, mbar_wait(e_empty + t, (itb & 1u) ^ 1u));
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int ky = tap / 3, kx = tap % 3;
+                    const int plane = ((ky != 1) ? 2 : 0) + ((kx != 1) ? 1 : 0);
+                    const int Dy = ky == 0 ? -1 : 0, Dx = kx == 0 ? -1 : 0;
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        mma_f16_ss2(tmem_base + TM_B00 + t * 32,
+                                    yb_lo + (uint32_t)(plane * (YH_PLANE >> 4) + ks * 2 * YHPOS + YLEAD + (1 + Dy) * YHP + 1 + Dx), y_hi,
+                                    w1_lo + (tap * 2 + ks) * 64, w_hi, idesc_1, (tap | ks) ? 1u : 0u);
+                }
+                mma_commit(e_full + t);
+            }
+            __syncwarp();
+        };
+        uint32_t it = 0;
+        for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+            TWAIT(2, mbar_wait(x_full, it & 1u));
+            tc_fence_after();
+            issue_stem(0, it);                                   // left half of the stem output
+            if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
+            issue_stem(4, it);                                   // right half
+            if (lane == 0) mma_commit(x_empty);                  // operand image free once the stem MMAs have read it
+            __syncwarp();
+            issue_b00(0, it);                                    // this crop, left tile
+        }
+        if (it > 0) issue_b00(1, it - 1);
+    } else {
+        // =========================== epilogue warps 0-7 ====================================================================
+        const int g = warp >> 2, qd = warp & 3, i = qd * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(qd * 32) << 16);
+        float bb[16];                                            // blocks.0.0 bias in registers (the stem bias is folded into its GEMM)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) bb[k] = p.bias_b00[k];
+        // stem tile (s, h = g): this lane holds pixel y = 16 g + (i >> 3), x = 8 s + (i & 7)
+        const int y = 16 * g + (i >> 3), xl = i & 7;
+        const int yoff = ((y & 1) * 2 + (xl & 1)) * YH_PLANE + (YLEAD + ((y >> 1) + 1) * YHP + (xl >> 1) + 1) * 16;   // + 64 for odd s
+        const int halo_off = ((y & 1) * 2 + 1) * YH_PLANE + (YLEAD + ((y >> 1) + 1) * YHP) * 16;                        // column 0 of the odd-x plane
+        auto epilogue_b00 = [&](int n, uint32_t itb) {           // blocks.0.0 tile g of crop n -> global T8 tile rows
+            TWAIT(0, mbar_wait(e_full + g, itb & 1u));
+            tc_fence_after();
+            uint32_t eh[16], el[16];                             // hi | lo halves of the 16 output channels
+            tmem_ld16(trow + TM_B00 + g * 32, eh);
+            tmem_ld16(trow + TM_B00 + g * 32 + 16, el);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(e_empty + g);
+            const int64_t m = (int64_t)n * 256 + (i >> 3) * 16 + 8 * g + (i & 7);
+            uint4* dst = reinterpret_cast<uint4*>(p.y) + ((m >> 7) * 2) * 128 + (m & 127);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = 8 * c + 2 * q;
+                    w[q] = pack2_relu(__uint_as_float(eh[e]) + __uint_as_float(el[e]) + bb[e],
+                                      __uint_as_float(eh[e + 1]) + __uint_as_float(el[e + 1]) + bb[e + 1]);
+                }
+                dst[c * 128] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        };
+        uint32_t it = 0;
+        int prev_n = -1;
+        for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+            if (g == 0 && it > 0) epilogue_b00(prev_n, it - 1);  // left tile of the previous crop: issued at the end of its iteration
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int k = 2 * s + g;
+                const uint32_t hidx = 2 * it + (s >> 1);
+                uint8_t* yb = Y + (hidx % NYBUF) * YH_BYTES;
+                TWAIT(1, mbar_wait(d_full + k, it & 1u));
+                tc_fence_after();
+                uint32_t r0[16], r1[16];
+                tmem_ld16(trow + k * 32, r0);
+                tmem_ld16(trow + k * 32 + 16, r1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(d_empty + k);         // accumulator drained into registers
+                uint4 o[4];
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    o[c] = make_uint4(pack2_relu(__uint_as_float(r0[8 * c]), __uint_as_float(r0[8 * c + 1])),
+                                      pack2_relu(__uint_as_float(r0[8 * c + 2]), __uint_as_float(r0[8 * c + 3])),
+                                      pack2_relu(__uint_as_float(r0[8 * c + 4]), __uint_as_float(r0[8 * c + 5])),
+                                      pack2_relu(__uint_as_float(r0[8 * c + 6]), __uint_as_float(r0[8 * c + 7])));
+                    o[2 + c] = make_uint4(pack2_relu(__uint_as_float(r1[8 * c]), __uint_as_float(r1[8 * c + 1])),
+                                          pack2_relu(__uint_as_float(r1[8 * c + 2]), __uint_as_float(r1[8 * c + 3])),
+                                          pack2_relu(__uint_as_float(r1[8 * c + 4]), __uint_as_float(r1[8 * c + 5])),
+                                          pack2_relu(__uint_as_float(r1[8 * c + 6]), __uint_as_float(r1[8 * c + 7])));
+                }
+                uint8_t* dst = yb + yoff + (s & 1) * 64;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
+                if (s == 0 && xl == 0) {                         // left half: its halo column is x = -1 (the buffer held a right half before)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yb + halo_off + c * YH_CHUNK) = make_uint4(0, 0, 0, 0);
+                }
+                if (s == 1 && xl == 7) {                         // x = 15 is also the halo column of the right half
+                    uint8_t* yr = Y + ((hidx + 1) % NYBUF) * YH_BYTES + halo_off;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yr + c * YH_CHUNK) = o[c];
+                }
+                if (s & 1) {                                     // half image complete (this warp's share)
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(yh_full + hidx % NYBUF);
+                }
+            }
+            if (g == 1 && it > 0) epilogue_b00(prev_n, it - 1);  // right tile of the previous crop: issued in the middle of this iteration
+            prev_n = n;
+        }
+        if (it > 0) epilogue_b00(prev_n, it - 1);
+    }
+#ifdef CV_FE_PROFILE
+    if (prof_on) {
+        const int role = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : 3;
+        for (int k = 0; k < 8; ++k) g_fe3_prof[role * 16 + k] = (unsigned long long)pacc[k];
+        g_fe3_prof[role * 16 + 8] = (unsigned long long)(clock64() - t_role0);
+    }
+#endif
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 16) tmem_dealloc(tmem_base, 512);
+}
+
+// Weight images: conv_stem as a 2x2 conv on the space-to-depth crop (4 taps x K 16, fp16, bias in row 12 of the centre tap),
+// blocks.0.0 as 9 taps x 2 k-steps, bf16 W_hi | W_lo concatenated along N.  *flag is set when a stem weight does not fit fp16.
+__global__ void prep_frontend3_weights_kernel(const float* __restrict__ w_stem /*[27][32]*/, const float* __restrict__ b_stem /*[32]*/,
+                                              const float* __restrict__ w_b00 /*[288][16]*/, uint16_t* __restrict__ img, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W_BYTES / 2) return;
+    float v = 0.f;
+    if (i < W_STEM_BYTES / 2) {
+        const int kk = i & 7, n = (i >> 3) & 31, chunk = (i >> 8) & 1, tap = i >> 9;
+        const int k = chunk * 8 + kk;                                  // s2d channel = dy*6 + dx*3 + c
+        if (k < 12) {
+            const int dy = k / 6, dx = (k % 6) / 3, c = k % 3;
+            const int ky = 2 * ((tap >> 1) - 1) + dy + 1, kx = 2 * ((tap & 1) - 1) + dx + 1;
+            if (ky >= 0 && ky < 3 && kx >= 0 && kx < 3) v = w_stem[((ky * 3 + kx) * 3 + c) * 32 + n];
+        } else if (k == 12 && tap == 3) {
+            v = b_stem[n];                                             // bias row: multiplied by the constant-one channel of the centre tap
+        }
+        if (!(fabsf(v) <= 65504.f)) atomicOr(flag, 1);
+        img[i] = __half_as_ushort(__float2half_rn(v));
+    } else {
+        const int j = i - W_STEM_BYTES / 2;
+        const int kk = j & 7, n = (j >> 3) & 31, chunk = (j >> 8) & 1, ks = (j >> 9) & 1, tap = j >> 10;
+        const int ci = ks * 16 + chunk * 8 + kk;
+        v = w_b00[(tap * 32 + ci) * 16 + (n & 15)];
+        const bf16 hi = __float2bfloat16_rn(v);
+        img[i] = __bfloat16_as_ushort(n >= 16 ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi);
+    }
+}
+
+}  // namespace
+
+size_t frontend3_weight_image_bytes() { return W_BYTES; }
+
+int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s) {
+    const cv_layer_info* L = cv_layers();
+    CV_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
+    prep_frontend3_weights_kernel<<<(W_BYTES / 2 + 255) / 256, 256, 0, s>>>(blob + L[0].w_offset, blob + L[0].b_offset, blob + L[1].w_offset,
+                                                                            reinterpret_cast<uint16_t*>(img), flag_dev);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+// Returns CV_OK and sets *supported = 0 when this kernel cannot take the configuration (the caller then uses an earlier
+// generation): non-affine normalisation table, window too large for shared memory (512x512 boards), > 255 window rows.
+int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s) {
+    *supported = 0;
+    if (nb == 0) { *supported = 1; return CV_OK; }
+    Front3Params p{};
+    // normalisation must be affine in the byte value: v = na*u + nb (true for ToTensor + Normalize)
+    for (int c = 0; c < 3; ++c) {
+        const float* l = lut_host + c * 256;
+        p.nb[c] = l[0];
+        p.na[c] = (l[255] - l[0]) / 255.0f;
+        for (int u = 0; u < 256; ++u)
+            if (fabsf(p.na[c] * u + p.nb[c] - l[u]) > 1e-5f * (1.0f + fabsf(l[u]))) return CV_OK;
+        if (fabsf(l[0]) > 1000.f || fabsf(l[255]) > 1000.f) return CV_OK;      // the resized pixels are held in fp16
+    }
+    Front3Tables tab{};
+    const CropTaps tp = make_taps(g);
+    int max_rows = 0, max_bytes = 0;
+    for (int r = 0; r < 8; ++r) {
+        int lo = g.H, hi = -1;
+        for (int d = 0; d < 64; ++d) {
+            lo = lo < tp.p0[r][d] ? lo : tp.p0[r][d];
+            hi = hi > tp.p1[r][d] ? hi : tp.p1[r][d];
+        }
+        if (hi - lo > 255) return CV_OK;
+        tab.row0[r] = lo;
+        tab.nrows[r] = hi - lo + 1;
+        const int b0 = (lo * 3) & ~15, b1 = ((hi + 1) * 3 + 15) & ~15;     // row pitch H*3 is a multiple of 16 (H % 32 == 0): stays inside the row
+        tab.byte0[r] = b0;
+        tab.nbytes[r] = b1 - b0;
+        for (int d = 0; d < 64; ++d) {
+            const __half lh = __float2half_rn(g.lam[d]);
+            if (__half2float(lh) != g.lam[d]) return CV_OK;                 // the vertical weights must be exact in fp16 (they are k/128)
+            tab.vy[r][d] = (uint32_t)(tp.p0[r][d] - lo) | ((uint32_t)(tp.p1[r][d] - lo) << 8) | ((uint32_t)__half_as_ushort(lh) << 16);
+            tab.xo0[r][d] = (int16_t)(tp.p0[r][d] * 3 - b0);
+            tab.xo1[r][d] = (int16_t)(tp.p1[r][d] * 3 - b0);
+        }
+        max_rows = max_rows > tab.nrows[r] ? max_rows : tab.nrows[r];
+        max_bytes = max_bytes > tab.nbytes[r] ? max_bytes : tab.nbytes[r];
+    }
+    for (int d = 0; d < 64; ++d) tab.lam[d] = g.lam[d];
+    p.raw_pitch = max_bytes;
+    p.raw_bytes = (max_rows * max_bytes + 127) & ~127;
+    p.hb_bytes = (max_rows * HB_PITCH + 127) & ~127;
+    const int fixed = X_ALLOC + NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
+    p.n_rawbuf = 2;
+    auto total = [&]() { return p.n_rawbuf * p.raw_bytes + p.hb_bytes + fixed; };
+    if (total() > 227 * 1024) p.n_rawbuf = 1;
+    if (total() > 227 * 1024) return CV_OK;                       // window does not fit: not supported
+    int off = X_ALLOC;
+    p.off_raw = off; off += p.n_rawbuf * p.raw_bytes;
+    p.off_hb = off; off += p.hb_bytes;
+    off = (off + 127) & ~127; p.off_y = off; off += NYBUF * YH_BYTES + 256;
+    off = (off + 127) & ~127; p.off_w = off; off += W_BYTES;
+    p.off_tab = off; off += (int)sizeof(Front3Tables);
+    off = (off + 15) & ~15; p.off_bar = off; off += 256;
+    p.smem_total = off;
+    if (p.smem_total > 227 * 1024) return CV_OK;
+    p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
+    p.n_crops = nb * 64; p.H = H;
+    { const char* d = getenv("CV_FE3_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    *supported = 1;
+    CV_CUDA(cudaFuncSetAttribute(frontend3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total));
+    const int grid = p.n_crops < num_sms ? p.n_crops : num_sms;
+    frontend3_kernel<<<grid, NTHREADS, p.smem_total, s>>>(p, tab);
+    CV_CHECK_LAUNCH();
+#ifdef CV_FE_PROFILE
+    if (p.debug & 256) {                                          // timing experiment: print block 0's wait-cycle counters
+        unsigned long long h[64];
+        CV_CUDA(cudaStreamSynchronize(s));
+        CV_CUDA(cudaMemcpyFromSymbol(h, g_fe3_prof, sizeof(h)));
+        const int per_cta = (p.n_crops + grid - 1) / grid;
+        const char* names[4] = {"epilogue g0", "epilogue g1", "producer   ", "mma        "};
+        const char* what[4][4] = {{"e_full", "d_full", "-", "-"}, {"e_full", "d_full", "-", "-"},
+                                  {"raw_full", "x_empty", "bar A", "bar B"}, {"yh_full", "e_empty", "x_full", "d_empty"}};
+        for (int r = 0; r < 4; ++r) {
+            fprintf(stderr, "fe3 %s total %7.0f cyc/crop | waits:", names[r], (double)h[r * 16 + 8] / per_cta);
+            for (int k = 0; k < 4; ++k) fprintf(stderr, " %s %6.0f", what[r][k], (double)h[r * 16 + k] / per_cta);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
+    return CV_OK;
+}

@@ -41,10 +41,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_ns();
-    while (!mbar_try_wait(bar, parity))
-        if (global_ns() - t0 > kWaitTimeoutNs) __trap();
+    // Hot path: back-to-back try_wait (each may suspend the thread for a short, hardware-chosen time).  The global timer is
+    // slow to read, so the hang guard only looks at it once every 4096 failed polls.
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++polls & 4095u) == 0) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitTimeoutNs) __trap();
+        }
+    }
 }
 
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP) ---------------------------
@@ -84,6 +91,16 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // (A and B must have the same 16-bit format: bf16 activations x fp16 weights raises an illegal-instruction fault on B200.)
+// Same with A = B = fp16 (format code 0).
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Descriptor halves: lo = addr>>4 | (LBO>>4) << 16, hi = SBO>>4 | version.  An operand window that moves by whole 16-byte
+// rows is `lo + rows`: one integer add per MMA in the single issuing thread (whose dependent-instruction latency is exposed).
+__host__ __device__ constexpr uint32_t desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
 
 // ---- tcgen05.mma / commit / ld -----------------------------------------------------------------------------
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues on behalf of the CTA (SASS: UTCHMMA)
@@ -94,6 +111,24 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// same instruction, descriptors passed as 32-bit halves (kind::f16 covers fp16 x fp16 and bf16 x bf16; the idesc says which)
+__device__ __forceinline__ void mma_f16_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// two fp32 -> packed bf16x2 with ReLU in the conversion (lo -> bits [0,16), hi -> bits [16,32))
+__device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
 }
 // arrives on `bar` once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
