@@ -23,6 +23,7 @@
 // 16 MMA issuer (+ TMEM owner).
 #include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include "internal.h"
 #include "umma.cuh"
@@ -62,7 +63,7 @@ struct Front3Params {
     const float* bias_b00;
     bf16* y;                          // T8 [crops*256 rows][16 ch]
     int n_crops, H;
-    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf;
+    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf, box_bytes;
     int off_raw, off_hb, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
     int debug;
@@ -82,7 +83,7 @@ __device__ unsigned long long g_fe3_prof[4 * 16];
 #endif
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__ Front3Tables tab_param) {
+frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__ Front3Tables tab_param, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* X = smem;
     uint8_t* RAW = smem + p.off_raw;                              // n_rawbuf x raw_bytes
@@ -117,7 +118,8 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     const int rawmask = p.n_rawbuf - 1;
 #ifdef CV_FE_PROFILE
-    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 8 || warp == 16);
+    const int pw = (p.debug & 512) ? 12 : 8;                     // which producer warp is sampled
+    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == 16);
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_role0 = clock64();
 #endif
@@ -126,18 +128,19 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         // =========================== resize producers (256 threads) ==========================================================
         const int t = threadIdx.x - 256;
         const float a0 = p.na[0], a1 = p.na[1], a2 = p.na[2], b0 = p.nb[0], b1 = p.nb[1], b2 = p.nb[2];
-        // stage the window rows of crop `nn` (iteration index iti) into RAW slot iti & rawmask: executed by warp 8 only.  The slot
-        // is free: its previous user is the horizontal pass of an earlier crop, which ended at a producer barrier.
+        // stage the board window of crop `nn` (iteration index iti) into RAW slot iti & rawmask: ONE 2D TMA tile copy (rows x bytes box
+        // of the (B*H rows, H*3 bytes) board tensor at the clamped window origin; what lies beyond the window is never read), issued by
+        // one lane of warp 8.  The slot is free: its previous user is the horizontal pass of an earlier crop, which ended at a
+        // producer barrier.
         auto stage_window = [&](int nn, uint32_t iti) {
+            if (lane != 0) return;
             const int slot = iti & rawmask;
-            const int64_t b = nn >> 6;
-            const int rr = (nn >> 3) & 7, cc = nn & 7;
-            const int nr = tab.nrows[rr], nbytes = tab.nbytes[cc];
-            if (lane == 0) mbar_arrive_expect_tx(raw_full + slot, (uint32_t)(nr * nbytes));
-            __syncwarp();
-            const uint8_t* src = p.boards + (b * p.H + tab.row0[rr]) * (int64_t)p.H * 3 + tab.byte0[cc];
-            uint8_t* dst = RAW + slot * p.raw_bytes;
-            for (int i = lane; i < nr; i += 32) bulk_g2s(dst + i * p.raw_pitch, src + (int64_t)i * p.H * 3, (uint32_t)nbytes, raw_full + slot);
+            const int b = nn >> 6, rr = (nn >> 3) & 7, cc = nn & 7;
+            uint64_t* bar = raw_full + slot;
+            mbar_arrive_expect_tx(bar, (uint32_t)p.box_bytes);
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(smem_u32(RAW + slot * p.raw_bytes)), "l"(&tmap), "r"(tab.byte0[cc] >> 2), "r"(b * p.H + tab.row0[rr]), "r"(smem_u32(bar))
+                         : "memory");
         };
         if (warp == 8 && blockIdx.x < p.n_crops) stage_window(blockIdx.x, 0);
         uint32_t it = 0;
@@ -148,6 +151,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             if (warp == 8 && p.n_rawbuf == 2 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // prefetch
             TWAIT(0, mbar_wait(raw_full + rslot, (it / p.n_rawbuf) & 1u));
             // ---- horizontal pass: window row i, output columns 2xp, 2xp+1 -> 6 fp16 (normalised) at HB[i][xp]
+#ifdef CV_FE_PROFILE
+            const long long t_h0 = clock64();
+#endif
             const int nrows = tab.nrows[r];
             const int xp = t & 31;                               // fixed per thread: its 4 column taps are looked up once per crop
             const int xoff[4] = {tab.xo0[c][2 * xp], tab.xo1[c][2 * xp], tab.xo0[c][2 * xp + 1], tab.xo1[c][2 * xp + 1]};
@@ -173,9 +179,15 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     o[k] = *reinterpret_cast<uint32_t*>(&h);
                 }
             }
+#ifdef CV_FE_PROFILE
+            if (prof_on) pacc[4] += clock64() - t_h0;
+#endif
             TWAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // HB complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
             TWAIT(1, mbar_wait(x_empty, (it & 1u) ^ 1u));                                  // stem MMAs of the previous crop have read X
+#ifdef CV_FE_PROFILE
+            const long long t_v0 = clock64();
+#endif
             // ---- vertical pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
 #pragma unroll 1
             for (int k = 0; k < 4; ++k) {
@@ -202,6 +214,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 *reinterpret_cast<uint4*>(X + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
             }
             fence_proxy_async_smem();
+#ifdef CV_FE_PROFILE
+            if (prof_on) pacc[5] += clock64() - t_v0;
+#endif
             TWAIT(3, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // operand image complete; HB free again
             if (t == 0) mbar_arrive(x_full);
         }
@@ -308,7 +323,6 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         uint32_t it = 0;
         int prev_n = -1;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
-            if (g == 0 && it > 0) epilogue_b00(prev_n, it - 1);  // left tile of the previous crop: issued at the end of its iteration
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int k = 2 * s + g;
@@ -352,6 +366,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     __syncwarp();
                     if (lane == 0) mbar_arrive(yh_full + hidx % NYBUF);
                 }
+                // left tile of the previous crop: issued before this crop's stem tiles, so it has completed by now (the tensor
+                // pipe executes in order) -- no waiting, and the stem accumulators above were drained first
+                if (s == 1 && g == 0 && it > 0) epilogue_b00(prev_n, it - 1);
             }
             if (g == 1 && it > 0) epilogue_b00(prev_n, it - 1);  // right tile of the previous crop: issued in the middle of this iteration
             prev_n = n;
@@ -360,7 +377,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     }
 #ifdef CV_FE_PROFILE
     if (prof_on) {
-        const int role = warp == 0 ? 0 : warp == 4 ? 1 : warp == 8 ? 2 : 3;
+        const int role = warp == 0 ? 0 : warp == 4 ? 1 : warp == pw ? 2 : 3;
         for (int k = 0; k < 8; ++k) g_fe3_prof[role * 16 + k] = (unsigned long long)pacc[k];
         g_fe3_prof[role * 16 + 8] = (unsigned long long)(clock64() - t_role0);
     }
@@ -474,10 +491,32 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
     p.n_crops = nb * 64; p.H = H;
     { const char* d = getenv("CV_FE3_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    // 2D tensor map over the boards of this launch: (nb*H rows) x (H*3 bytes as uint32 elements); box = the largest window
+    if ((reinterpret_cast<uintptr_t>(boards_hwc) & 15) || (H * 3) % 16 || max_bytes / 4 > 256 || max_rows > 256) return CV_OK;
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CV_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !fn) return CV_OK;
+        encode = reinterpret_cast<EncodeFn>(fn);
+    }
+    alignas(64) CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)(H * 3 / 4), (cuuint64_t)nb * H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)H * 3};
+    const cuuint32_t box[2] = {(cuuint32_t)(max_bytes / 4), (cuuint32_t)max_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(boards_hwc), gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { cv_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return CV_ERR_CUDA; }
+    p.box_bytes = max_rows * max_bytes;
     *supported = 1;
     CV_CUDA(cudaFuncSetAttribute(frontend3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total));
     const int grid = p.n_crops < num_sms ? p.n_crops : num_sms;
-    frontend3_kernel<<<grid, NTHREADS, p.smem_total, s>>>(p, tab);
+    frontend3_kernel<<<grid, NTHREADS, p.smem_total, s>>>(p, tab, tmap);
     CV_CHECK_LAUNCH();
 #ifdef CV_FE_PROFILE
     if (p.debug & 256) {                                          // timing experiment: print block 0's wait-cycle counters
@@ -491,6 +530,7 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "fe3 %s total %7.0f cyc/crop | waits:", names[r], (double)h[r * 16 + 8] / per_cta);
             for (int k = 0; k < 4; ++k) fprintf(stderr, " %s %6.0f", what[r][k], (double)h[r * 16 + k] / per_cta);
+            if (r == 2) fprintf(stderr, " | horizontal %6.0f vertical %6.0f", (double)h[r * 16 + 4] / per_cta, (double)h[r * 16 + 5] / per_cta);
             fprintf(stderr, "\n");
         }
     }

@@ -49,6 +49,47 @@ __global__ void __launch_bounds__(128, 1) mma_bench(MmaCase c, long long* out) {
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// Several warps issue MMAs concurrently (one thread each, own accumulators, own barrier): is the 48-cycle floor the tensor pipe or
+// the single issuing thread?
+__global__ void __launch_bounds__(128, 1) mma_multi_bench(MmaCase c, int n_issuers, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar[4];
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { for (int i = 0; i < 4; ++i) mbar_init(bar + i, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0 && w < n_issuers) {
+        const uint32_t a0 = smem_u32(smem) + 1024 + c.a_shift_bytes + w * 32768, b0 = smem_u32(smem) + 160 * 1024;
+        const uint32_t idesc = make_idesc_bf16(128, c.N);
+        uint64_t ad[8], bd = make_smem_desc(b0, c.N * 16, 128);
+        uint32_t dc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ad[j] = make_smem_desc(a0 + j * c.a_stride, c.lbo, c.sbo); dc[j] = tm + w * 128 + (j % c.n_acc) * c.N; }
+        for (int rep = 0; rep < 3; ++rep) {
+            const long long t0 = clock64();
+            for (int i = 0; i < c.n_mma; i += 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mma_bf16_ss(dc[j], ad[j], bd, idesc, 1u);
+            }
+            const long long t1 = clock64();
+            mma_commit(&bar[w]);
+            mbar_wait(&bar[w], rep & 1);
+            const long long t2 = clock64();
+            out[2 * w] = t1 - t0;
+            out[2 * w + 1] = t2 - t0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 template <int X32>
 __global__ void __launch_bounds__(512, 1) ld_bench(int iters, long long* out) {
     __shared__ uint32_t slot;
@@ -85,20 +126,32 @@ int main() {
     cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const MmaCase cases[] = {
         // N, shift, lbo, sbo, n_acc, n_mma, a_stride
-        {64, 0, 17552, 128, 1, 64, 0},   {64, 16, 17552, 128, 1, 64, 0},  {64, 0, 17552, 128, 4, 64, 2048}, {64, 16, 17552, 128, 4, 64, 2048},
-        {32, 0, 4752, 128, 1, 64, 0},    {32, 16, 4752, 128, 1, 64, 0},   {32, 0, 4752, 128, 3, 64, 2048},  {32, 16, 4752, 128, 3, 64, 2048},
-        {32, 0, 4096, 128, 3, 64, 2048}, {32, 0, 2048, 128, 3, 64, 2048}, {16, 0, 2048, 128, 4, 64, 2048},  {16, 16, 2048, 128, 4, 64, 2048},
-        {128, 0, 2048, 128, 2, 64, 2048}, {128, 16, 2048, 128, 2, 64, 2048}, {256, 0, 2048, 128, 1, 64, 2048}, {256, 16, 2048, 128, 1, 64, 2048},
-        {64, 0, 2048, 128, 4, 64, 2048}, {64, 32, 2048, 128, 4, 64, 2048}, {64, 64, 2048, 128, 4, 64, 2048}, {32, 64, 2048, 128, 3, 64, 2048},
-        {96, 0, 2048, 128, 4, 64, 2048}, {192, 0, 2048, 128, 2, 64, 2048}, {48, 0, 2048, 128, 4, 64, 2048},  {8, 0, 2048, 128, 4, 64, 2048},
+        {32, 0, 17552, 128, 4, 64, 2048},  {32, 16, 17552, 128, 4, 64, 2048},   // contiguous core matrices (linear M tile)
+        {32, 0, 17552, 528, 4, 64, 2048},  {32, 16, 17552, 528, 4, 64, 2048},   // column slab of the stem image (row pitch 33 positions)
+        {32, 0, 17552, 512, 4, 64, 2048},  {32, 16, 17552, 512, 4, 64, 2048},   // row pitch 32 positions (128-byte aligned rows)
+        {32, 0, 17552, 640, 4, 64, 2048},  {32, 16, 17552, 640, 4, 64, 2048},   // row pitch 40 positions
+        {32, 0, 2576, 144, 4, 64, 2048},   {32, 16, 2576, 144, 4, 64, 2048},    // blocks.0.0 half image (row pitch 9 positions)
+        {32, 0, 2576, 256, 4, 64, 2048},   {32, 16, 2576, 256, 4, 64, 2048},    // row pitch 16 positions
+        {32, 0, 2048, 128, 4, 64, 2048},   {64, 0, 2048, 128, 4, 64, 2048},
     };
     for (const MmaCase& c : cases) {
         mma_bench<<<1, 128, 200 * 1024>>>(c, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mma N=%d: %s\n", c.N, cudaGetErrorString(e)); return 1; }
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d n_acc=%d a_stride=%4d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.n_acc,
+        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d sbo=%3d n_acc=%d a_stride=%4d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.sbo, c.n_acc,
                c.a_stride, (double)h[0] / c.n_mma, (double)h[1] / c.n_mma);
+    }
+    cudaFuncSetAttribute(mma_multi_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int N : {32, 64}) for (int ni : {1, 2, 4}) {
+        const MmaCase c = {N, 0, 2048, 128, 2, 64, 2048};
+        mma_multi_bench<<<1, 128, 200 * 1024>>>(c, ni, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("multi: %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h, d, 64, cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int w = 0; w < ni; ++w) mx = mx > h[2 * w + 1] ? mx : h[2 * w + 1];
+        printf("multi-issuer N=%d: %d warps x 64 MMAs -> %6.1f cyc per MMA overall (%.0f total)\n", N, ni, (double)mx / (64.0 * ni), (double)mx);
     }
     for (int nw : {1, 4, 8, 16}) {
         ld_bench<0><<<1, nw * 32>>>(256, d);
