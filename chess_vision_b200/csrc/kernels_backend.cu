@@ -470,90 +470,6 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 // =====================================================================================================================
 // stage C: blocks.2.0 .. blocks.2.5 (19 conv layers), 8x8 -> 4x4 maps.  Tile = 16 crops.
 // =====================================================================================================================
-// Depthwise 5x5 stride 1 on 8x8 maps, "P2" rows (row = pix*2 + crop, 2 crops), 32 channels: 128 rows x 4 chunks = NT tasks.
-__device__ __forceinline__ void dw5x5_p2(const uint8_t* src, uint8_t* dst, const float* w, const float* bias, int tid) {
-    const int c = tid >> 7, r = tid & 127, pix = r >> 1, y = pix >> 3, x = pix & 7;
-    float acc[8];
-    load8(bias + c * 8, acc);
-#pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-        const int iy = y - 2 + ky;
-        if (iy < 0 || iy > 7) continue;
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            const int ix = x - 2 + kx;
-            if (ix < 0 || ix > 7) continue;
-            const int idx = c * 128 + r + ((ky - 2) * 8 + (kx - 2)) * 2;
-            fma8(acc, *reinterpret_cast<const uint4*>(src + ((size_t)idx << 4)), w + (ky * 5 + kx) * 32 + c * 8);
-        }
-    }
-    *reinterpret_cast<uint4*>(dst + ((size_t)tid << 4)) = pack8(acc);
-}
-
-// Depthwise 5x5 stride 2 (+ReLU) 8x8 -> 4x4, 96 channels: src [12][128 P2 rows][8] (2 crops) -> dst P8 tile rows
-// opix*8 + crop0 + crop of [12][128][8].  384 tasks; lanes: crop fastest, then output pixel.
-__device__ __forceinline__ void dw5x5s2_p2(const uint8_t* src, uint8_t* dst, int crop0, const float* w, const float* bias, int tid) {
-    if (tid >= 384) return;
-    const int c = tid >> 5, l = tid & 31, crop = l & 1, opix = l >> 1, oy = opix >> 2, ox = opix & 3;
-    float acc[8];
-    load8(bias + c * 8, acc);
-#pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-        const int iy = 2 * oy - 2 + ky;
-        if (iy < 0 || iy > 7) continue;
-#pragma unroll
-        for (int kx = 0; kx < 5; ++kx) {
-            const int ix = 2 * ox - 2 + kx;
-            if (ix < 0 || ix > 7) continue;
-            fma8(acc, *reinterpret_cast<const uint4*>(src + (((size_t)c * 128 + (iy * 8 + ix) * 2 + crop) << 4)), w + (ky * 5 + kx) * 96 + c * 8);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-    *reinterpret_cast<uint4*>(dst + (((size_t)c * 128 + opix * 8 + crop0 + crop) << 4)) = pack8(acc);
-}
-
-// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over N_MT consecutive 128-row tiles of C8 chunks each: every thread
-// computes its (<= MAXI) outputs into registers, the CTA synchronises, then the results are stored.
-template <int MAXI>
-__device__ __forceinline__ void dw3x3_p8_inplace(uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, bool relu, int tid) {
-    const int C = C8 * 8;
-    uint4 res[MAXI];
-#pragma unroll
-    for (int it = 0; it < MAXI; ++it) {
-        const int task = tid + it * NT;
-        if (task < n_tasks) {
-            const int r = task & 127, tc = task >> 7, c = tc % C8, pix = r >> 3, y = pix >> 2, x = pix & 3;
-            float acc[8];
-            load8(bias + c * 8, acc);
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-                const int iy = y - 1 + ky;
-                if (iy < 0 || iy > 3) continue;
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int ix = x - 1 + kx;
-                    if (ix < 0 || ix > 3) continue;
-                    const int idx = tc * 128 + r + ((ky - 1) * 4 + (kx - 1)) * 8;
-                    fma8(acc, *reinterpret_cast<const uint4*>(buf + ((size_t)idx << 4)), w + (ky * 3 + kx) * C + c * 8);
-                }
-            }
-            if (relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-            }
-            res[it] = pack8(acc);
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < MAXI; ++it) {
-        const int task = tid + it * NT;
-        if (task < n_tasks) *reinterpret_cast<uint4*>(buf + ((size_t)task << 4)) = res[it];
-    }
-}
-
-
 // Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over consecutive 128-row tiles of C8 chunks, register tiled.
 // Task = (tile*C8 + chunk, crop, channel half): the thread loads the whole 4x4 map of 4 channels of one crop (16 x 8 bytes,
 // a half warp reads 128 contiguous bytes per pixel), converts it once, computes all 16 outputs from registers (static border
@@ -623,15 +539,136 @@ __device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols
     }
 }
 
+// ---- row-streaming 5x5 depthwise kernels of the 8x8 phase --------------------------------------------------------------------
+// Both take a task = (one output row, 4 channels): the thread streams over the (up to 5) input rows; each row is loaded once
+// (8 pixels x 8 bytes, every load issued before the first use), converted once, and feeds every output of the row from
+// registers with static column-border handling -- long runs of independent FMAs instead of load -> convert -> FMA chains with
+// a border branch per tap.  The source layouts are pixel-major with the (chunk, crop, channel-half) index fastest, so a half
+// warp reads 128 contiguous bytes per pixel: no bank conflicts.
+
+// blocks.2.0.dw_start: 5x5 stride 1, 32 channels, no activation.  src = stage input of the whole tile: 8 sub-tiles (2 crops each)
+// x [64 pixels][4 chunks][2 crops][8 ch]  ("P2X").  dst = 8 operand images [4 chunks][128 rows = pixel*2 + crop][8 ch].
+__device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, const float* w, const float* bias, int tid) {
+#pragma unroll 1
+    for (int task = tid; task < 1024; task += NT) {
+        const int l = task & 15, t = ((task >> 8) << 1) | ((task >> 4) & 1), y = (task >> 5) & 7;     // y is warp-uniform
+        const uint8_t* sp = src + t * 8192 + l * 8;
+        const int coff = (l >> 2) * 8 + (l & 1) * 4;             // first of this task's 4 channels
+        const float4 b = *reinterpret_cast<const float4*>(bias + coff);
+        float acc[8][4];
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox) { acc[ox][0] = b.x; acc[ox][1] = b.y; acc[ox][2] = b.z; acc[ox][3] = b.w; }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+            const int iy = y + ky - 2;
+            if (iy < 0 || iy > 7) continue;
+            uint2 in[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) in[x] = *reinterpret_cast<const uint2*>(sp + (iy * 8 + x) * 128);
+            float4 wt[5];
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 32 + coff);
+            float xv[8][4];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) {
+                xv[x][0] = __uint_as_float(in[x].x << 16); xv[x][1] = __uint_as_float(in[x].x & 0xffff0000u);
+                xv[x][2] = __uint_as_float(in[x].y << 16); xv[x][3] = __uint_as_float(in[x].y & 0xffff0000u);
+            }
+#pragma unroll
+            for (int ox = 0; ox < 8; ++ox) {
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    const int ix = ox + kx - 2;
+                    if (ix < 0 || ix > 7) continue;
+                    acc[ox][0] = fmaf(xv[ix][0], wt[kx].x, acc[ox][0]); acc[ox][1] = fmaf(xv[ix][1], wt[kx].y, acc[ox][1]);
+                    acc[ox][2] = fmaf(xv[ix][2], wt[kx].z, acc[ox][2]); acc[ox][3] = fmaf(xv[ix][3], wt[kx].w, acc[ox][3]);
+                }
+            }
+        }
+        uint8_t* dp = dst + t * 8192 + (l >> 2) * 2048 + ((l >> 1) & 1) * 16 + (l & 1) * 8 + y * 8 * 32;
+#pragma unroll
+        for (int ox = 0; ox < 8; ++ox) *reinterpret_cast<uint2*>(dp + ox * 32) = make_uint2(pack2(acc[ox][0], acc[ox][1]), pack2(acc[ox][2], acc[ox][3]));
+    }
+}
+
+// E6: the expanded 8x8 activation (96 ch) of one sub-tile (2 crops), pixel-major: byte = pixel*384 + ((chunk ^ (pixel & 3))*2 + crop)*16.
+// The XOR spreads the four pixels an epilogue quarter-warp writes over the four 32-byte bank groups; a group of four chunks
+// stays one contiguous 128-byte block per pixel for the depthwise reader.
+__device__ __forceinline__ int e6_off(int pix, int chunk, int crop) { return pix * 384 + (((chunk ^ (pix & 3)) << 1) | crop) * 16; }
+
+// TMEM accumulator columns [col0, col0+96) of this thread's row (= pixel*2 + crop) -> (+bias, ReLU) -> bf16 -> E6.
+__device__ __forceinline__ void epi_to_e6(uint32_t trow, int col0, const float* bias, uint8_t* dst, int row, int cs, int n_slices) {
+    const int pix = row >> 1, crop = row & 1;
+    for (int g = cs; g < 6; g += n_slices) {
+        uint32_t r[16];
+        tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float v[8];
+            load8(bias + g * 16 + j * 8, v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
+            *reinterpret_cast<uint4*>(dst + e6_off(pix, g * 2 + j, crop)) =
+                make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7]));
+        }
+    }
+}
+
+// blocks.2.0.dw_mid: 5x5 stride 2 (+ReLU) 8x8 -> 4x4, 96 channels, over two sub-tiles (4 crops): src0 / src1 in the E6 layout ->
+// dst P8 tile rows opix*8 + crop0 + 2*sub + crop of [12 chunks][128][8 ch].  384 tasks = (sub, output row, 4 channels).
+__device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t* src1, uint8_t* dst, int crop0, const float* w, const float* bias,
+                                             int tid) {
+    if (tid >= 384) return;
+    const int l = tid & 15, sub = (tid >> 4) & 1, oy = (tid >> 5) & 3, g = tid >> 7;          // oy and g are warp-uniform
+    const int chunk = g * 4 + (l >> 2), crop = (l >> 1) & 1, half = l & 1;
+    const uint8_t* sp = (sub ? src1 : src0) + half * 8;
+    const int coff = chunk * 8 + half * 4;
+    const float4 b = *reinterpret_cast<const float4*>(bias + coff);
+    float acc[4][4];
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) { acc[ox][0] = b.x; acc[ox][1] = b.y; acc[ox][2] = b.z; acc[ox][3] = b.w; }
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+        const int iy = 2 * oy + ky - 2;
+        if (iy < 0 || iy > 7) continue;
+        uint2 in[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) in[x] = *reinterpret_cast<const uint2*>(sp + e6_off(iy * 8 + x, chunk, crop));
+        float4 wt[5];
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 96 + coff);
+        float xv[8][4];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) {
+            xv[x][0] = __uint_as_float(in[x].x << 16); xv[x][1] = __uint_as_float(in[x].x & 0xffff0000u);
+            xv[x][2] = __uint_as_float(in[x].y << 16); xv[x][3] = __uint_as_float(in[x].y & 0xffff0000u);
+        }
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) {
+#pragma unroll
+            for (int kx = 0; kx < 5; ++kx) {
+                const int ix = 2 * ox + kx - 2;
+                if (ix < 0 || ix > 7) continue;
+                acc[ox][0] = fmaf(xv[ix][0], wt[kx].x, acc[ox][0]); acc[ox][1] = fmaf(xv[ix][1], wt[kx].y, acc[ox][1]);
+                acc[ox][2] = fmaf(xv[ix][2], wt[kx].z, acc[ox][2]); acc[ox][3] = fmaf(xv[ix][3], wt[kx].w, acc[ox][3]);
+            }
+        }
+    }
+    uint8_t* dp = dst + chunk * 2048 + (oy * 4 * 8 + crop0 + 2 * sub + crop) * 16 + half * 8;
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) *reinterpret_cast<uint2*>(dp + ox * 128) = make_uint2(pack2_relu(acc[ox][0], acc[ox][1]), pack2_relu(acc[ox][2], acc[ox][3]));
+}
+
 namespace sc {
 constexpr int NOPS = 20;
 // op: 0 dw5  1 pw6  2 dw7 | 3 pw8 | 4+3j pw_exp  5+3j dw_mid  6+3j pw_proj (blocks.2.1..2.4, j = 0..3) |
 //     16 dw21 + pw22 (output columns 0..95)  17 pw22 (columns 96..191)  18 pw23 (K rows 0..95)  19 pw23 (K rows 96..191)
-constexpr int OFF_IN = 0;                 // 2 x 8192: stage-input ring, one sub-tile = 2 crops (128 P2 rows x 32 ch)
-constexpr int OFF_A5 = 16384;             // 8192: dw_start output
-constexpr int OFF_R = 24576;              // 73728: E6 (24576) | A7 (2 x 24576)   ||  body: E (2 x 24576)  ||  E22a (49152) | E22b runs into X16
-constexpr int OFF_X16 = 98304;            // 2 x 12288: block input operand tiles (2 M-tiles of 8 crops, P8 rows, 48 ch)
-constexpr int OFF_W = 122880;             // weight arena: slot 0 (26112; also the resident 8x8-phase blobs) | slot 1 (20992)
+constexpr int OFF_A5 = 0;                 // 8 x 8192: blocks.2.0.dw_start output of the whole tile (one operand image per 2-crop sub-tile)
+constexpr int OFF_R = 65536;              // 73728: E6a (24576) | A7 (2 x 24576)   ||  body: E (2 x 24576)  ||  E22a (49152) | E22b runs into X16
+constexpr int OFF_X16 = 139264;           // 2 x 12288: block input operand tiles (2 M-tiles of 8 crops, P8 rows, 48 ch); E6b during the 8x8 phase
+constexpr int OFF_IN = OFF_R + 24576;     // 65536: the tile's stage input (8 sub-tiles, P2X) lies over A7 + X16, both dead until dw_start has consumed it
+constexpr int OFF_W = 163840;             // weight arena: slot 0 (26112; also the resident 8x8-phase blobs) | slot 1 (20992)
 constexpr int W_SLOT1 = 26112;
 constexpr int W_ARENA = W_SLOT1 + 20992;  // 47104
 constexpr int OFF_BAR = OFF_W + W_ARENA;  // 169984
@@ -679,7 +716,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t wph0 = 0, wph1 = 0, inph0 = 0, inph1 = 0, mph = 0;
+    uint32_t wph0 = 0, wph1 = 0, inph = 0, mph = 0;
 
     auto load_head_weights = [&]() {
         mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
@@ -687,13 +724,9 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
         bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
     };
-    auto load_in = [&](int tile, int t) {
-        uint64_t* b = inbar + (t & 1);
-        mbar_arrive_expect_tx(b, 8192);
-        bulk_g2s(IN + (t & 1) * 8192, reinterpret_cast<const uint8_t*>(p.x) + ((size_t)tile * 8 + t) * 8192, 8192, b);
-    };
-    auto wait_in = [&](int s) {
-        if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
+    auto load_in = [&](int tile) {             // the whole tile's stage input: 8 sub-tiles = one 64 KB bulk copy
+        mbar_arrive_expect_tx(inbar, 65536);
+        bulk_g2s(IN, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * 65536, 65536, inbar);
     };
     auto begin_op = [&](int op) -> uint8_t* {
         if (tid == 0 && op + 1 < NOPS) {
@@ -717,11 +750,11 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 
     if (tid == 0 && blockIdx.x < p.n_tiles) {
         load_head_weights();
-        load_in(blockIdx.x, 0);
+        load_in(blockIdx.x);
     }
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        // ------------------------------ blocks.2.0 at 8x8: eight sub-tiles of 2 crops ------------------------------------------
+        // ------------------------------ blocks.2.0 at 8x8: dw_start over the whole tile, then four pairs of 2-crop sub-tiles ----------
         mbar_wait(wbar, wph0); wph0 ^= 1u;
         const float* b5 = reinterpret_cast<const float*>(WA);
         const float* w5 = b5 + 32;
@@ -733,20 +766,21 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             mbar_arrive_expect_tx(wbar + 1, p.bytes[3]);
             bulk_g2s(WA + W_SLOT1, p.wimg + p.off[3], p.bytes[3], wbar + 1);
         }
-        for (int t = 0; t < 8; ++t) {
-            if (tid == 0 && t < 7) load_in(tile, t + 1);
-            wait_in(t & 1);
-            if (!(p.debug & 1)) dw5x5_p2(IN + (t & 1) * 8192, A5, w5, b5, tid);             // L5 dw_start 5x5 (no act)
-            sync_before_mma();
+        mbar_wait(inbar, inph); inph ^= 1u;
+        if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
+        sync_before_mma();
+        for (int j = 0; j < 4; ++j) {
             if (tid == 0) {
                 tc_fence_after();
-                issue_gemm(smem_u32(A5), 32, w6, 96, 0, 96, tmem + ACC, false, 2);           // L6 pw_exp 32 -> 96
+                for (int m = 0; m < 2; ++m)                                                  // L6 pw_exp 32 -> 96 on sub-tiles 2j, 2j+1
+                    issue_gemm(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 96 * m, false, 2);
                 mma_commit(mbar);
             }
             wait_mma();
-            epi_to_tile<true>(trow, ACC, 96, b6, E6, 0, row, cs);
+            epi_to_e6(trow, ACC + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
+            tc_fence_before();
             __syncthreads();
-            if (!(p.debug & 2)) dw5x5s2_p2(E6, A7 + (t >> 2) * 24576, (2 * t) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
+            if (!(p.debug & 2)) dw5x5s2_rows(E6, X16, A7 + (j >> 1) * 24576, (4 * j) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
             __syncthreads();
         }
         // ------------------------------ 4x4 phase: 2 M-tiles of 8 crops -----------------------------------------------------------
@@ -865,7 +899,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         __syncthreads();
         if (tid == 0 && next < p.n_tiles) {
             load_head_weights();
-            load_in(next, 0);
+            load_in(next);
         }
     }
     tc_fence_before();
@@ -1021,7 +1055,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * h + i]) + b4[16 * hi2 + 8 * h + i], 0.f);
-                dst[(size_t)(hi2 * 2 + h) * 128 + row] = pack8(v);
+                dst[(size_t)(row >> 1) * 8 + (hi2 * 2 + h) * 2 + (row & 1)] = pack8(v);      // P2X: [pixel][chunk][crop]
             }
         }
         tc_fence_before();
@@ -1041,12 +1075,13 @@ __global__ void permute_p8_kernel(const uint4* __restrict__ in, uint4* __restric
     out[(i & ~(int64_t)127) + ((r & 15) * 8 + (r >> 4))] = in[i];
 }
 
-// crop-major T8 tiles of 8x8 maps (128 rows = 2 crops, row = crop*64 + pix) -> P2 tiles (row = pix*2 + crop_local).
+// crop-major T8 tiles of 8x8 maps, 32 ch (128 rows = 2 crops, row = crop*64 + pix; 4 chunks) -> P2X sub-tiles
+// [64 pixels][4 chunks][2 crops] of 16-byte chunks (the stage C input layout).
 __global__ void permute_p2_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t n_chunks) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_chunks) return;
-    const int r = (int)(i & 127);
-    out[(i & ~(int64_t)127) + ((r & 63) * 2 + (r >> 6))] = in[i];
+    const int r = (int)(i & 127), chunk = (int)((i >> 7) & 3);
+    out[(i & ~(int64_t)511) + (r & 63) * 8 + chunk * 2 + (r >> 6)] = in[i];
 }
 
 // ---- stage weight image construction --------------------------------------------------------------------------------------
