@@ -215,6 +215,7 @@ struct StageDParams {
     int tiled;
     long long crop_base;      // tiled: index of this launch's first crop inside the chunk that `features` (FT base) covers
     uint32_t off[sd::NOPS], bytes[sd::NOPS];
+    int debug;                // CV_SD_DEBUG ablation bits (timing experiments only: results are wrong)
 };
 
 __constant__ int kTypeOf[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6};     // dataset.py:31
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             if (tid == 0 && t < 3) load_in(tile, t + 1);
             wait_in(t & 1);
             const uint8_t* in = IN + (t & 1) * 12288;
-            dw3x3_p8(in, A24, 6, w24, b24, false, tid);                                   // L24 dw_start (no act)
+            if (!(p.debug & 1)) dw3x3_p8(in, A24, 6, w24, b24, false, tid);               // L24 dw_start (no act)
             sync_before_mma();
             if (tid == 0) {
                 tc_fence_after();
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             for (int h = 0; h < 2; ++h) {
                 epi_to_tile<true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs);
                 __syncthreads();
-                dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);               // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                if (!(p.debug & 2)) dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
                 __syncthreads();
             }
         }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             if (blk == 1) {                      // L28 blocks.3.1.dw_start 5x5 on the block input (no act)
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                dw2x2_pm(X16, 8, b + 64, b, false, tid);
+                if (!(p.debug & 4)) dw2x2_pm(X16, 8, b + 64, b, false, tid);
                 __syncthreads();
                 ++op;
             }
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             {   // dw_mid 5x5 / 3x3 (+ReLU), in place
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                dw2x2_pm(BIG, cexp >> 3, b + cexp, b, true, tid);
+                if (!(p.debug & 4)) dw2x2_pm(BIG, cexp >> 3, b + cexp, b, true, tid);
                 __syncthreads();                 // every warp is done with this slot's weights before the next prefetch targets it
                 ++op;
             }
@@ -405,7 +406,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             for (int r = 0; r < 10; ++r) part_acc[r] = 0.f;
             float* xbuf = reinterpret_cast<float*>(BIG) + (size_t)cs * 4 * 16 * 32;      // [pixel][16 ch][32 crops] of this slice
             const int64_t crop = (int64_t)tile * 32 + lane;
-            for (int g = cs; g < 30; g += 4) {
+            for (int g = cs; g < ((p.debug & 8) ? 0 : 30); g += 4) {
                 uint32_t rr[16];
                 tmem_ld16(trow + (uint32_t)(g * 16), rr);
                 tmem_ld_wait();
@@ -1199,6 +1200,7 @@ int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const 
     StageDParams p{};
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
     p.tiled = tiled; p.crop_base = crop_base;
+    { const char* d = getenv("CV_SD_DEBUG"); p.debug = d ? atoi(d) : 0; }
     for (int i = 0; i < sd::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
     CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
