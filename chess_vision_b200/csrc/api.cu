@@ -590,10 +590,11 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
         CV_CUDA(cudaMalloc(&h->dev_fen_len, (size_t)B));
         h->dev_fen_cap = B;
     }
-    int slot = 0;
-    for (int b0 = 0; b0 < B; b0 += chunk, slot ^= 1) {
-        const int nb = std::min(chunk, B - b0);
-        if (b0 >= 2 * chunk) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
+    // Chunks grow 128, 128, 256, 512, 512, ...: the first copy is the only one nothing overlaps, so it is kept short
+    int slot = 0, it = 0;
+    for (int b0 = 0, nb = 0; b0 < B; b0 += nb, slot ^= 1, ++it) {
+        nb = std::min(std::min(chunk, it < 2 ? 128 : it == 2 ? 256 : 512), B - b0);
+        if (it >= 2) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
         CV_CUDA(cudaMemcpyAsync(h->stage[slot], boards_host + (size_t)b0 * per_board, nb * per_board,
                                 cudaMemcpyHostToDevice, h->copy_stream));
         if (flipped_host)

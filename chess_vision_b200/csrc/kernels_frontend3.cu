@@ -40,7 +40,8 @@ constexpr int YHP = 9, YLEAD = 8, YHPOS = YLEAD + 17 * YHP;    // half image of 
 constexpr int YH_CHUNK = YHPOS * 16;                           // 2576
 constexpr int YH_PLANE = 4 * YH_CHUNK;                         // 10304 (= 64 mod 128: the two x-parities hit different banks)
 constexpr int YH_BYTES = 4 * YH_PLANE;                         // 41216 per half
-constexpr int NYBUF = 3;
+constexpr int NYBUF = 2;                                       // left / right half images of the stem output
+constexpr int NXBUF = 2;                                       // stem operand image, double buffered
 constexpr int W_STEM_BYTES = 4 * 1024;                         // taps x [2 chunks][32 n][8] fp16
 constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) x [2 chunks][32 n = hi 16 | lo 16][8] bf16
 constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
@@ -92,19 +93,20 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     uint8_t* W = smem + p.off_w;
     const Front3Tables& tab = *reinterpret_cast<const Front3Tables*>(smem + p.off_tab);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-    uint64_t *raw_full = bars, *x_full = bars + 2, *x_empty = bars + 3, *wbar = bars + 4, *yh_full = bars + 5 /*3*/, *e_full = bars + 8 /*2*/,
-             *e_empty = bars + 10 /*2*/, *d_full = bars + 12 /*8*/, *d_empty = bars + 20 /*8*/;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+    uint64_t *raw_full = bars, *x_full = bars + 2, *x_empty = bars + 4, *wbar = bars + 6, *yh_full = bars + 7 /*2*/, *e_full = bars + 9 /*2*/,
+             *e_empty = bars + 11 /*2*/, *d_full = bars + 13 /*8*/, *d_empty = bars + 21 /*8*/;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
-    for (int i = threadIdx.x; i < X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < NXBUF * X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < (NYBUF * YH_BYTES + 256) / 16; i += NTHREADS) reinterpret_cast<uint4*>(Y)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < (int)(sizeof(Front3Tables) / 4); i += NTHREADS)
         reinterpret_cast<uint32_t*>(smem + p.off_tab)[i] = reinterpret_cast<const uint32_t*>(&tab_param)[i];
     if (threadIdx.x == 0) {
         mbar_init(raw_full, 1); mbar_init(raw_full + 1, 1);
-        mbar_init(x_full, 1); mbar_init(x_empty, 1); mbar_init(wbar, 1);
+        for (int i = 0; i < NXBUF; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
+        mbar_init(wbar, 1);
         for (int i = 0; i < NYBUF; ++i) mbar_init(yh_full + i, 8);
         for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_empty + i, 4); }
         for (int i = 0; i < 8; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
@@ -184,7 +186,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             TWAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // HB complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
-            TWAIT(1, mbar_wait(x_empty, (it & 1u) ^ 1u));                                  // stem MMAs of the previous crop have read X
+            const int xslot = it & 1;
+            uint8_t* Xb = X + xslot * X_ALLOC;
+            TWAIT(1, mbar_wait(x_empty + xslot, ((it >> 1) & 1u) ^ 1u));                   // stem MMAs of the crop before last have read this image
 #ifdef CV_FE_PROFILE
             const long long t_v0 = clock64();
 #endif
@@ -209,20 +213,20 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     }
                 }
                 const int pos = XLEAD + (py + 1) * XP + px;
-                *reinterpret_cast<uint4*>(X + pos * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(Xb + pos * 16) = make_uint4(o[0], o[1], o[2], o[3]);
                 // channel 12 = 1.0 (fp16 0x3C00): the centre tap's weight row 12 holds the folded-BN bias, so the GEMM adds it
-                *reinterpret_cast<uint4*>(X + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
+                *reinterpret_cast<uint4*>(Xb + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
             }
             fence_proxy_async_smem();
 #ifdef CV_FE_PROFILE
             if (prof_on) pacc[5] += clock64() - t_v0;
 #endif
             TWAIT(3, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // operand image complete; HB free again
-            if (t == 0) mbar_arrive(x_full);
+            if (t == 0) mbar_arrive(x_full + xslot);
         }
     } else if (warp == 16) {
         // =========================== MMA issuer ===========================================================================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(wbar, W_BYTES);
             bulk_g2s(W, p.wimg, W_BYTES, wbar);
         }
@@ -231,18 +235,19 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         const uint32_t x_lo = desc_lo(smem_u32(X), X_CHUNK), y_lo = desc_lo(smem_u32(Y), YH_CHUNK);
         const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), 32 * 16);
         constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
-        // stem tiles k = 2 s + h of the crop in X: output columns [8s, 8s+8), rows [16h, 16h+16)
-        auto issue_stem = [&](int k0, uint32_t it) {
+        // stem tiles k = 2 s + h, k in [k0, k1), of the crop in X slot `xs`: output columns [8s, 8s+8), rows [16h, 16h+16)
+        auto issue_stem = [&](int k0, int k1, uint32_t it) {
+            const uint32_t xb_lo = x_lo + (it & 1u) * (X_ALLOC >> 4);
 #pragma unroll
-            for (int k = k0; k < k0 + 4; ++k) {
+            for (int k = k0; k < k1; ++k) {
                 const int s = k >> 1, h = k & 1;
                 TWAIT(3, mbar_wait(d_empty + k, (it & 1u) ^ 1u));
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
                         const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
-                        mma_f16_ss2(tmem_base + k * 32, x_lo + (uint32_t)(XLEAD + (16 * h + 1 + Dy) * XP + 8 * s + Dx), x_hi, ws_lo + tap * 64, w_hi,
+                        mma_f16_ss2(tmem_base + k * 32, xb_lo + (uint32_t)(XLEAD + (16 * h + 1 + Dy) * XP + 8 * s + Dx), x_hi, ws_lo + tap * 64, w_hi,
                                     idesc_s, tap > 0 ? 1u : 0u);
                     }
                     mma_commit(d_full + k);
@@ -252,11 +257,11 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         };
         // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image 2 itb + t
         auto issue_b00 = [&](int t, uint32_t itb) {
-            const uint32_t hidx = 2 * itb + t, buf = hidx % NYBUF;
-            TWAIT(0, mbar_wait(yh_full + buf, (hidx / NYBUF) & 1u));
+            const uint32_t buf = t;
+            TWAIT(0, mbar_wait(yh_full + buf, itb & 1u));
             TWAIT(1, mbar_wait(e_empty + t, (itb & 1u) ^ 1u));
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
@@ -275,12 +280,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         };
         uint32_t it = 0;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
-            TWAIT(2, mbar_wait(x_full, it & 1u));
+            TWAIT(2, mbar_wait(x_full + (it & 1u), (it >> 1) & 1u));
             tc_fence_after();
-            issue_stem(0, it);                                   // left half of the stem output
+            // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
+            // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
+            issue_stem(0, 2, it);                                // slab 0
             if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
-            issue_stem(4, it);                                   // right half
-            if (lane == 0) mma_commit(x_empty);                  // operand image free once the stem MMAs have read it
+            issue_stem(2, 8, it);                                // slabs 1..3
+            if (elect_one()) mma_commit(x_empty + (it & 1u));      // operand image free once the stem MMAs have read it
             __syncwarp();
             issue_b00(0, it);                                    // this crop, left tile
         }
@@ -326,8 +333,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int k = 2 * s + g;
-                const uint32_t hidx = 2 * it + (s >> 1);
-                uint8_t* yb = Y + (hidx % NYBUF) * YH_BYTES;
+                uint8_t* yb = Y + (s >> 1) * YH_BYTES;
                 TWAIT(1, mbar_wait(d_full + k, it & 1u));
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
@@ -352,19 +358,15 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 uint8_t* dst = yb + yoff + (s & 1) * 64;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
-                if (s == 0 && xl == 0) {                         // left half: its halo column is x = -1 (the buffer held a right half before)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yb + halo_off + c * YH_CHUNK) = make_uint4(0, 0, 0, 0);
-                }
                 if (s == 1 && xl == 7) {                         // x = 15 is also the halo column of the right half
-                    uint8_t* yr = Y + ((hidx + 1) % NYBUF) * YH_BYTES + halo_off;
+                    uint8_t* yr = Y + YH_BYTES + halo_off;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yr + c * YH_CHUNK) = o[c];
                 }
                 if (s & 1) {                                     // half image complete (this warp's share)
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(yh_full + hidx % NYBUF);
+                    if (lane == 0) mbar_arrive(yh_full + (s >> 1));
                 }
                 // left tile of the previous crop: issued before this crop's stem tiles, so it has completed by now (the tensor
                 // pipe executes in order) -- no waiting, and the stem accumulators above were drained first
@@ -474,12 +476,12 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     p.raw_pitch = max_bytes;
     p.raw_bytes = (max_rows * max_bytes + 127) & ~127;
     p.hb_bytes = (max_rows * HB_PITCH + 127) & ~127;
-    const int fixed = X_ALLOC + NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
+    const int fixed = NXBUF * X_ALLOC + NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
     p.n_rawbuf = 2;
     auto total = [&]() { return p.n_rawbuf * p.raw_bytes + p.hb_bytes + fixed; };
     if (total() > 227 * 1024) p.n_rawbuf = 1;
     if (total() > 227 * 1024) return CV_OK;                       // window does not fit: not supported
-    int off = X_ALLOC;
+    int off = NXBUF * X_ALLOC;
     p.off_raw = off; off += p.n_rawbuf * p.raw_bytes;
     p.off_hb = off; off += p.hb_bytes;
     off = (off + 127) & ~127; p.off_y = off; off += NYBUF * YH_BYTES + 256;

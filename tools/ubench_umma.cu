@@ -8,21 +8,22 @@
 #include "umma.cuh"
 using namespace umma;
 
-struct MmaCase { int N, a_shift_bytes, lbo, sbo, n_acc, n_mma, a_stride; };
+struct MmaCase { int N, a_shift_bytes, lbo, sbo, n_acc, n_mma, a_stride; int lsu_warps = 0; int commit_every = 0; int use_elect = 0; };
 
-__global__ void __launch_bounds__(128, 1) mma_bench(MmaCase c, long long* out) {
+template <int COMMIT_EVERY, bool ELECT>
+__global__ void __launch_bounds__(544, 1) mma_bench(MmaCase c, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t slot;
     for (int i = threadIdx.x; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_init(&bar2, 1); fence_barrier_init(); }
     if (threadIdx.x < 32) tmem_alloc(&slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tm = slot;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32 && (ELECT ? elect_one() : threadIdx.x == 0)) {
         const uint32_t a0 = smem_u32(smem) + 1024 + c.a_shift_bytes, b0 = smem_u32(smem) + 160 * 1024;
         const uint32_t idesc = make_idesc_bf16(128, c.N);
         // descriptors and accumulator addresses precomputed: the issue loop is one UTCHMMA + nothing else per instruction
@@ -34,7 +35,10 @@ __global__ void __launch_bounds__(128, 1) mma_bench(MmaCase c, long long* out) {
             const long long t0 = clock64();
             for (int i = 0; i < c.n_mma; i += 8) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) mma_bf16_ss(dc[j], ad[j], bd, idesc, 1u);
+                for (int j = 0; j < 8; ++j) {
+                    mma_bf16_ss(dc[j], ad[j], bd, idesc, (COMMIT_EVERY && (j & 3) == 0) ? 0u : 1u);
+                    if (COMMIT_EVERY && (j & 3) == 3) mma_commit(&bar2);       // a barrier nobody waits on: cost of the commit itself
+                }
             }
             const long long t1 = clock64();
             mma_commit(&bar);
@@ -43,6 +47,17 @@ __global__ void __launch_bounds__(128, 1) mma_bench(MmaCase c, long long* out) {
             out[0] = t1 - t0;
             out[1] = t2 - t0;
         }
+    }
+    else if (threadIdx.x >= 32 && threadIdx.x < 32 + 32 * c.lsu_warps) {
+        // interference: conflict-free 16-byte loads + stores on a private region for the whole duration of the MMA loop
+        uint4* q = reinterpret_cast<uint4*>(smem + 100 * 1024) + (threadIdx.x - 32);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 3000; ++i) {
+            const uint4 a = q[(i & 3) * 512];
+            v.x += a.x; v.y ^= a.y;
+            q[((i + 1) & 3) * 512] = v;
+        }
+        if (v.x == 0x12345u) out[7] = v.y;
     }
     tc_fence_before();
     __syncthreads();
@@ -123,24 +138,25 @@ int main() {
     long long* d;
     cudaMalloc(&d, 64 * 8);
     long long h[64];
-    cudaFuncSetAttribute(mma_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mma_bench<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mma_bench<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(mma_bench<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const MmaCase cases[] = {
-        // N, shift, lbo, sbo, n_acc, n_mma, a_stride
-        {32, 0, 17552, 128, 4, 64, 2048},  {32, 16, 17552, 128, 4, 64, 2048},   // contiguous core matrices (linear M tile)
-        {32, 0, 17552, 528, 4, 64, 2048},  {32, 16, 17552, 528, 4, 64, 2048},   // column slab of the stem image (row pitch 33 positions)
-        {32, 0, 17552, 512, 4, 64, 2048},  {32, 16, 17552, 512, 4, 64, 2048},   // row pitch 32 positions (128-byte aligned rows)
-        {32, 0, 17552, 640, 4, 64, 2048},  {32, 16, 17552, 640, 4, 64, 2048},   // row pitch 40 positions
-        {32, 0, 2576, 144, 4, 64, 2048},   {32, 16, 2576, 144, 4, 64, 2048},    // blocks.0.0 half image (row pitch 9 positions)
-        {32, 0, 2576, 256, 4, 64, 2048},   {32, 16, 2576, 256, 4, 64, 2048},    // row pitch 16 positions
-        {32, 0, 2048, 128, 4, 64, 2048},   {64, 0, 2048, 128, 4, 64, 2048},
+        // N, shift, lbo, sbo, n_acc, n_mma, a_stride, lsu_warps, commit_every, use_elect
+        {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 1}, {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1},
+        {32, 0, 2048, 128, 4, 64, 2048, 8, 4, 1}, {64, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {96, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {128, 0, 2048, 128, 2, 64, 2048, 0, 4, 1},
+        {192, 0, 2048, 128, 2, 64, 2048, 0, 4, 1}, {256, 0, 2048, 128, 1, 64, 2048, 0, 4, 1}, {16, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {48, 0, 2048, 128, 4, 64, 2048, 0, 4, 1},
+        {32, 16, 17552, 528, 4, 64, 2048, 16, 4, 1},
     };
     for (const MmaCase& c : cases) {
-        mma_bench<<<1, 128, 200 * 1024>>>(c, d);
+        if (!c.use_elect) mma_bench<0, false><<<1, 32 + 32 * c.lsu_warps, 200 * 1024>>>(c, d);
+        else if (!c.commit_every) mma_bench<0, true><<<1, 32 + 32 * c.lsu_warps, 200 * 1024>>>(c, d);
+        else mma_bench<4, true><<<1, 32 + 32 * c.lsu_warps, 200 * 1024>>>(c, d);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mma N=%d: %s\n", c.N, cudaGetErrorString(e)); return 1; }
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d sbo=%3d n_acc=%d a_stride=%4d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.sbo, c.n_acc,
-               c.a_stride, (double)h[0] / c.n_mma, (double)h[1] / c.n_mma);
+        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d sbo=%3d n_acc=%d a_stride=%4d lsu_warps=%2d commit_every=%d elect=%d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.sbo, c.n_acc,
+               c.a_stride, c.lsu_warps, c.commit_every, c.use_elect, (double)h[0] / c.n_mma, (double)h[1] / c.n_mma);
     }
     cudaFuncSetAttribute(mma_multi_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int N : {32, 64}) for (int ni : {1, 2, 4}) {
