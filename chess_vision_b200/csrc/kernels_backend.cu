@@ -61,14 +61,12 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_ad
                                            bool accumulate, int w_parts = 1) {
     const uint32_t idesc = make_idesc_bf16(128, n);
     const uint32_t b_lbo = (uint32_t)n_total * 16u;
-    const uint32_t part_bytes = (uint32_t)K * (uint32_t)n_total * 2u;
-    for (int k = 0; k < K / 16; ++k) {
-        const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 4096u, 2048u, 128u);
-        for (int part = 0; part < w_parts; ++part) {
-            const uint64_t bd = make_smem_desc(b_addr + part * part_bytes + (uint32_t)k * 2u * b_lbo + (uint32_t)n0 * 16u, b_lbo, 128u);
-            mma_bf16_ss(d_tmem, ad, bd, idesc, (accumulate || k > 0 || part > 0) ? 1u : 0u);
-        }
-    }
+    const uint32_t part_rows = ((uint32_t)K * (uint32_t)n_total * 2u) >> 4;           // descriptor words count 16-byte units
+    uint32_t a_lo = desc_lo(a_addr, 2048u), b_lo = desc_lo(b_addr + (uint32_t)n0 * 16u, b_lbo);
+    constexpr uint32_t hi = desc_hi(128u);
+    for (int k = 0; k < K / 16; ++k, a_lo += 4096u >> 4, b_lo += (2u * b_lbo) >> 4)
+        for (int part = 0; part < w_parts; ++part)
+            mma_f16_ss2(d_tmem, a_lo, hi, b_lo + part * part_rows, hi, idesc, (accumulate || k > 0 || part > 0) ? 1u : 0u);
 }
 
 // TMEM accumulator columns [col0, col0+ncols) of this thread's row -> (+bias, ReLU) -> bf16 -> operand tile
@@ -309,7 +307,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             const uint8_t* in = IN + (t & 1) * 12288;
             if (!(p.debug & 1)) dw3x3_p8(in, A24, 6, w24, b24, false, tid);               // L24 dw_start (no act)
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm(smem_u32(A24), 48, w25, 288, 0, 144, tmem, false);             // L25 pw_exp 48 -> 288
                 issue_gemm(smem_u32(A24), 48, w25, 288, 144, 144, tmem + 144, false);
@@ -329,7 +327,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         {   // L27 blocks.3.0.pw_proj 288 -> 64: starts the residual stream in TMEM
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
                 mma_commit(mbar);
@@ -352,7 +350,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             {   // pw_exp 64 -> cexp (+ReLU)
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     issue_gemm(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
                     mma_commit(mbar);
@@ -372,7 +370,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             {   // pw_proj cexp -> 64, accumulated onto the residual stream in TMEM (skip connection)
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     issue_gemm(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
                     mma_commit(mbar);
@@ -387,7 +385,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         for (int part = 0; part < 3; ++part, ++op) {          // three 160-column weight parts (ops 20..22)
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
                 mma_commit(mbar);
@@ -771,7 +769,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
         sync_before_mma();
         for (int j = 0; j < 4; ++j) {
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)                                                  // L6 pw_exp 32 -> 96 on sub-tiles 2j, 2j+1
                     issue_gemm(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 96 * m, false, 2);
@@ -789,7 +787,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
@@ -805,7 +803,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // pw_exp 48 -> 96 (+ReLU)
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
@@ -826,7 +824,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // pw_proj 96 -> 48 accumulated onto the residual stream
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (tid == 0) {
+                if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
@@ -846,7 +844,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             const float* b21 = reinterpret_cast<const float*>(wb);
             if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
@@ -860,7 +858,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         {   // op 17: W22 columns 96..191
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
@@ -876,7 +874,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             uint8_t* wb = begin_op(op);
             cum23 = reinterpret_cast<const float*>(wb);
             sync_before_mma();
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
@@ -885,7 +883,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         }
         {   // op 19: W23 K rows 96..191, then the stage output
             uint8_t* wb = begin_op(op);
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
                 mma_commit(mbar);
@@ -991,7 +989,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) load_in(tile + gridDim.x, s ^ 1);
         if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
         // ---- blocks.0.1: 1x1 16 -> 16 (+ReLU) on 512 rows = 4 M-tiles
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             for (int j = 0; j < 4; ++j) issue_gemm(smem_u32(in + j * 4096), 16, smem_u32(W + W2_OFF), 16, 0, 16, tmem + 16 * j, false, 2);
             mma_commit(mbar);
@@ -1030,7 +1028,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         }
         sync_before_mma();
         // ---- blocks.1.0: 3x3 s2 16 -> 48 (+ReLU) as one K = 144 GEMM on 128 rows (2 crops x 8x8, P2 order)
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             issue_gemm(smem_u32(A3), 144, smem_u32(W + W3_OFF), 48, 0, 48, tmem + 64, false, 2);
             mma_commit(mbar);
@@ -1040,7 +1038,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         epi_to_tile<true>(trow, 64, 48, b3, A4, 0, row, hi2, 2);
         sync_before_mma();
         // ---- blocks.1.1: 1x1 48 -> 32 (+ReLU) -> global P2 tile
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {
             tc_fence_after();
             issue_gemm(smem_u32(A4), 48, smem_u32(W + W4_OFF), 32, 0, 32, tmem + 128, false, 2);
             mma_commit(mbar);

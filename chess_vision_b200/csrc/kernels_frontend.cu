@@ -193,7 +193,7 @@ frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ C
                 const uint32_t buf = tcount & (ND - 1), ph = (tcount / ND) & 1u;
                 mbar_wait(d_empty + buf, ph ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
                         const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
@@ -205,12 +205,12 @@ frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ C
                 }
                 __syncwarp();
             }
-            if (lane == 0) mma_commit(x_empty);            // crop buffer free once the stem MMAs have read it
+            if (elect_one()) mma_commit(x_empty);            // crop buffer free once the stem MMAs have read it
             __syncwarp();
             mbar_wait(y_full, it & 1u);
             mbar_wait(e_empty, (it & 1u) ^ 1u);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 for (int j = 0; j < 3; ++j) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {

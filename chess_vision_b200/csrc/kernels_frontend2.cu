@@ -200,7 +200,7 @@ frontend2_kernel(const __grid_constant__ Front2Params p, const __grid_constant__
             mbar_wait(y_full, itb & 1u);
             mbar_wait(e_empty, (itb & 1u) ^ 1u);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 for (int j = 0; j < B00_TILES; ++j) {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -230,7 +230,7 @@ frontend2_kernel(const __grid_constant__ Front2Params p, const __grid_constant__
                 const uint32_t buf = tcount & (ND - 1), ph = (tcount / ND) & 1u;
                 mbar_wait(d_empty + buf, ph ^ 1u);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
                         const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
@@ -242,7 +242,7 @@ frontend2_kernel(const __grid_constant__ Front2Params p, const __grid_constant__
                 }
                 __syncwarp();
             }
-            if (lane == 0) mma_commit(x_empty + xslot);          // operand image free once the stem MMAs have read it
+            if (elect_one()) mma_commit(x_empty + xslot);          // operand image free once the stem MMAs have read it
             __syncwarp();
         }
         if (it > 0) issue_b00(it - 1);

@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(192, 1) global_head_umma_kernel(const __grid_c
         for (int kb = 0; kb < blocks; ++kb) {
             mbar_wait(full + stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t a0 = smem_u32(smem + stage * A_STAGE), b0 = smem_u32(smem + OFF_B + stage * B_STAGE);
 #pragma unroll
                 for (int j = 0; j < KB_CHUNKS / 2; ++j)        // one MMA = K 8 tf32 = two 16-byte chunks
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(192, 1) global_head_umma_kernel(const __grid_c
             __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (lane == 0) mma_commit(done);
+        if (elect_one()) mma_commit(done);
         __syncwarp();
     } else {
         const int q = warp & 3, row = q * 32 + lane;              // TMEM lane quadrant a warp may read = warp id % 4

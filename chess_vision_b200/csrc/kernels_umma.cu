@@ -86,7 +86,7 @@ __device__ __forceinline__ void mma_role(const GemmParams& p, const Pipe& q, uin
         mbar_wait(q.full + stage, phase);
         mbar_wait(q.tempty + acc, acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t a_base = smem_u32(q.a + (size_t)stage * s.a_bytes);
             const uint32_t b_base = smem_u32(q.b);
             for (int nt = 0; nt < p.n_split; ++nt) {
