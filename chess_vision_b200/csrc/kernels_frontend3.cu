@@ -18,9 +18,9 @@
 //     "buffer empty" barriers are needed at all;
 //   * the issuing thread adds a constant to a precomputed descriptor word per MMA (its dependent-instruction latency is exposed).
 //
-// Warp roles (17 warps): 0-7 epilogue (group g = warp>>2 takes the stem tiles of image rows [16g, 16g+16) and blocks.0.0
-// tile g; TMEM lane quadrant = warp&3), 8-15 resize producers (warp 8 also issues the TMA row copies of the next crop),
-// 16 MMA issuer (+ TMEM owner).
+// Warp roles (21 warps): 0-7 epilogue (group g = warp>>2 takes the stem tiles of image rows [16g, 16g+16) and blocks.0.0
+// tile g; TMEM lane quadrant = warp&3), 8-19 resize producers (warp 8 also issues the TMA tile copy of the next crop),
+// 20 MMA issuer (+ TMEM owner).
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
@@ -46,8 +46,9 @@ constexpr int W_STEM_BYTES = 4 * 1024;                         // taps x [2 chun
 constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) x [2 chunks][32 n = hi 16 | lo 16][8] bf16
 constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
 constexpr int HB_PITCH = 64 * 3 * 2;                           // fp16 row of 64 normalised pixels
-constexpr int NTHREADS = 17 * 32;
-constexpr int NPROD = 256;
+constexpr int NPROD = 384;                                      // 12 resize producer warps (the resize is the longest per-crop job)
+constexpr int MMA_WARP = 8 + NPROD / 32;
+constexpr int NTHREADS = (MMA_WARP + 1) * 32;
 constexpr int TM_B00 = 256;                                    // TMEM: stem tile k at column 32 k, blocks.0.0 tile t at 256 + 32 t
 
 struct Front3Tables {                 // per launch, copied to shared memory
@@ -112,7 +113,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         for (int i = 0; i < 8; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
         fence_barrier_init();
     }
-    if (warp == 16) tmem_alloc(tmem_slot, 512);
+    if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -121,12 +122,12 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     const int rawmask = p.n_rawbuf - 1;
 #ifdef CV_FE_PROFILE
     const int pw = (p.debug & 512) ? 12 : 8;                     // which producer warp is sampled
-    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == 16);
+    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_role0 = clock64();
 #endif
 
-    if (warp >= 8 && warp < 16) {
+    if (warp >= 8 && warp < MMA_WARP) {
         // =========================== resize producers (256 threads) ==========================================================
         const int t = threadIdx.x - 256;
         const float a0 = p.na[0], a1 = p.na[1], a2 = p.na[2], b0 = p.nb[0], b1 = p.nb[1], b2 = p.nb[2];
@@ -184,7 +185,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #ifdef CV_FE_PROFILE
             if (prof_on) pacc[4] += clock64() - t_h0;
 #endif
-            TWAIT(2, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // HB complete, RAW slot consumed
+            TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // HB complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
             const int xslot = it & 1;
             uint8_t* Xb = X + xslot * X_ALLOC;
@@ -194,8 +195,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             // ---- vertical pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
                 const int sp = t + NPROD * k, py = sp >> 5, px = sp & 31;
+                if (sp >= 1024) break;
                 uint32_t o[6];
 #pragma unroll
                 for (int dy = 0; dy < 2; ++dy) {
@@ -221,10 +223,10 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #ifdef CV_FE_PROFILE
             if (prof_on) pacc[5] += clock64() - t_v0;
 #endif
-            TWAIT(3, asm volatile("bar.sync 1, 256;" ::: "memory"));                       // operand image complete; HB free again
+            TWAIT(3, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // operand image complete; HB free again
             if (t == 0) mbar_arrive(x_full + xslot);
         }
-    } else if (warp == 16) {
+    } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================================================================
         if (elect_one()) {
             mbar_arrive_expect_tx(wbar, W_BYTES);
@@ -386,7 +388,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
     tc_fence_before();
     __syncthreads();
-    if (warp == 16) tmem_dealloc(tmem_base, 512);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, 512);
 }
 
 // Weight images: conv_stem as a 2x2 conv on the space-to-depth crop (4 taps x K 16, fp16, bias in row 12 of the centre tap),
