@@ -83,11 +83,9 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
             float v[8];
             load8(bias + g * 16 + j * 8, v);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                v[i] += __uint_as_float(r[8 * j + i]);
-                if (RELU) v[i] = fmaxf(v[i], 0.f);
-            }
-            *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) = pack8(v);
+            for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
+            *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) =
+                RELU ? make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7])) : pack8(v);
         }
     }
 }
@@ -117,6 +115,59 @@ __device__ __forceinline__ void dw3x3_p8(const uint8_t* src, uint8_t* dst, int C
             for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
         }
         *reinterpret_cast<uint4*>(dst + (((size_t)c * 128 + r) << 4)) = pack8(acc);
+    }
+}
+
+// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over consecutive 128-row tiles of C8 chunks, register tiled.
+// Task = (tile*C8 + chunk, crop, channel half): the thread loads the whole 4x4 map of 4 channels of one crop (16 x 8 bytes,
+// a half warp reads 128 contiguous bytes per pixel), converts it once, computes all 16 outputs from registers (static border
+// handling: no branches, every load issued up front) and writes them back over its own inputs -- no other thread touches those
+// bytes, so no synchronisation is needed.  Against one task per output: 1.9x fewer instructions, 3x fewer LSU wavefronts.
+template <bool RELU>
+__device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, int tid) {
+    const int C = C8 * 8;
+    for (int task = tid; task < n_tasks; task += NT) {
+        const int l = task & 15, crop = l >> 1, half = l & 1, tc = task >> 4, c = tc % C8;
+        const uint8_t* sbase = src + (size_t)tc * 2048 + crop * 16 + half * 8;
+        uint8_t* base = buf + (size_t)tc * 2048 + crop * 16 + half * 8;
+        uint2 in[16];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) in[p] = *reinterpret_cast<const uint2*>(sbase + p * 128);
+        const float* wp = w + c * 8 + half * 4;
+        float4 wt[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(wp + t * C);
+        const float4 b = *reinterpret_cast<const float4*>(bias + c * 8 + half * 4);
+        float x[16][4];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            x[p][0] = __uint_as_float(in[p].x << 16); x[p][1] = __uint_as_float(in[p].x & 0xffff0000u);
+            x[p][2] = __uint_as_float(in[p].y << 16); x[p][3] = __uint_as_float(in[p].y & 0xffff0000u);
+        }
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox) {
+                float a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int iy = oy - 1 + ky;
+                    if (iy < 0 || iy > 3) continue;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = ox - 1 + kx;
+                        if (ix < 0 || ix > 3) continue;
+                        const float4 ww = wt[ky * 3 + kx];
+                        const float* xx = x[iy * 4 + ix];
+                        a0 = fmaf(xx[0], ww.x, a0); a1 = fmaf(xx[1], ww.y, a1); a2 = fmaf(xx[2], ww.z, a2); a3 = fmaf(xx[3], ww.w, a3);
+                    }
+                }
+                uint2 o;
+                if (RELU) { o.x = pack2_relu(a0, a1); o.y = pack2_relu(a2, a3); }
+                else { o.x = pack2(a0, a1); o.y = pack2(a2, a3); }
+                *reinterpret_cast<uint2*>(base + (oy * 4 + ox) * 128) = o;
+            }
+        }
     }
 }
 
@@ -305,7 +356,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             if (tid == 0 && t < 3) load_in(tile, t + 1);
             wait_in(t & 1);
             const uint8_t* in = IN + (t & 1) * 12288;
-            if (!(p.debug & 1)) dw3x3_p8(in, A24, 6, w24, b24, false, tid);               // L24 dw_start (no act)
+            if (!(p.debug & 1)) dw3x3_p8_rt<false>(in, A24, 6 * 16, 6, w24, b24, tid);    // L24 dw_start (no act)
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
@@ -469,58 +520,6 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 // =====================================================================================================================
 // stage C: blocks.2.0 .. blocks.2.5 (19 conv layers), 8x8 -> 4x4 maps.  Tile = 16 crops.
 // =====================================================================================================================
-// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over consecutive 128-row tiles of C8 chunks, register tiled.
-// Task = (tile*C8 + chunk, crop, channel half): the thread loads the whole 4x4 map of 4 channels of one crop (16 x 8 bytes,
-// a half warp reads 128 contiguous bytes per pixel), converts it once, computes all 16 outputs from registers (static border
-// handling: no branches, every load issued up front) and writes them back over its own inputs -- no other thread touches those
-// bytes, so no synchronisation is needed.  Against one task per output: 1.9x fewer instructions, 3x fewer LSU wavefronts.
-template <bool RELU>
-__device__ __forceinline__ void dw3x3_p8_rt(uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, int tid) {
-    const int C = C8 * 8;
-    for (int task = tid; task < n_tasks; task += NT) {
-        const int l = task & 15, crop = l >> 1, half = l & 1, tc = task >> 4, c = tc % C8;
-        uint8_t* base = buf + (size_t)tc * 2048 + crop * 16 + half * 8;
-        uint2 in[16];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) in[p] = *reinterpret_cast<const uint2*>(base + p * 128);
-        const float* wp = w + c * 8 + half * 4;
-        float4 wt[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(wp + t * C);
-        const float4 b = *reinterpret_cast<const float4*>(bias + c * 8 + half * 4);
-        float x[16][4];
-#pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            x[p][0] = __uint_as_float(in[p].x << 16); x[p][1] = __uint_as_float(in[p].x & 0xffff0000u);
-            x[p][2] = __uint_as_float(in[p].y << 16); x[p][3] = __uint_as_float(in[p].y & 0xffff0000u);
-        }
-#pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
-#pragma unroll
-            for (int ox = 0; ox < 4; ++ox) {
-                float a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
-#pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int iy = oy - 1 + ky;
-                    if (iy < 0 || iy > 3) continue;
-#pragma unroll
-                    for (int kx = 0; kx < 3; ++kx) {
-                        const int ix = ox - 1 + kx;
-                        if (ix < 0 || ix > 3) continue;
-                        const float4 ww = wt[ky * 3 + kx];
-                        const float* xx = x[iy * 4 + ix];
-                        a0 = fmaf(xx[0], ww.x, a0); a1 = fmaf(xx[1], ww.y, a1); a2 = fmaf(xx[2], ww.z, a2); a3 = fmaf(xx[3], ww.w, a3);
-                    }
-                }
-                uint2 o;
-                if (RELU) { o.x = pack2_relu(a0, a1); o.y = pack2_relu(a2, a3); }
-                else { o.x = pack2(a0, a1); o.y = pack2(a2, a3); }
-                *reinterpret_cast<uint2*>(base + (oy * 4 + ox) * 128) = o;
-            }
-        }
-    }
-}
-
 // TMEM accumulator columns -> (+bias) -> bf16 -> global T8-chunked tile dst[chunk][128 rows][8] (coalesced 16-byte stores).
 __device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int row, int cs, int n_slices) {
     for (int g = cs; g < (ncols >> 4); g += n_slices) {
@@ -817,7 +816,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                if (!(p.debug & 4)) dw3x3_p8_rt<true>(R, 2 * 12 * 16, 12, b + 96, b, tid);
+                if (!(p.debug & 4)) dw3x3_p8_rt<true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
                 __syncthreads();
                 ++op;
             }
@@ -842,7 +841,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
             uint8_t* wb = begin_op(op);
             const float* b21 = reinterpret_cast<const float*>(wb);
-            if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
+            if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
