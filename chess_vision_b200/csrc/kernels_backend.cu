@@ -45,14 +45,6 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-__device__ __forceinline__ void fma8(float (&acc)[8], const uint4& v, const float* w) {
-    float x[8], ww[8];
-    unpack8(v, x);
-    load8(w, ww);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[i], ww[i], acc[i]);
-}
-
 // One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
 // A: shared-memory operand tile [K/8][128 rows][8] bf16 (K-major, no swizzle; LBO 2048 B, SBO 128 B).
 // B: weight image [K/8][n_total][8] bf16, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
@@ -87,34 +79,6 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
             *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) =
                 RELU ? make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7])) : pack8(v);
         }
-    }
-}
-
-// Depthwise 3x3 stride 1 on 4x4 maps, P8 rows (row = pix*8 + crop), 8 crops: src -> dst, both [C8][128][8].
-__device__ __forceinline__ void dw3x3_p8(const uint8_t* src, uint8_t* dst, int C8, const float* w, const float* bias, bool relu, int tid) {
-    const int C = C8 * 8;
-    for (int task = tid; task < 128 * C8; task += NT) {
-        const int c = task >> 7, r = task & 127, pix = r >> 3, y = pix >> 2, x = pix & 3;
-        float acc[8];
-        load8(bias + c * 8, acc);
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = y - 1 + ky;
-            if (iy < 0 || iy > 3) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = x - 1 + kx;
-                if (ix < 0 || ix > 3) continue;
-                const int idx = c * 128 + r + ((ky - 1) * 4 + (kx - 1)) * 8;
-                const uint4 v = *reinterpret_cast<const uint4*>(src + ((size_t)idx << 4));
-                fma8(acc, v, w + (ky * 3 + kx) * C + c * 8);
-            }
-        }
-        if (relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-        }
-        *reinterpret_cast<uint4*>(dst + (((size_t)c * 128 + r) << 4)) = pack8(acc);
     }
 }
 
@@ -172,29 +136,50 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
 }
 
 // Depthwise 3x3 stride 2 (+ReLU) 4x4 -> 2x2: src [C8][128 P8 rows][8] (8 crops) -> dst rows p*32 + crop0 + crop (pixel-major
-// 2x2 tile of 32 crops), chunks chunk0 + c of a [.][128][8] tile.  Lanes: p-major, crop fastest -> conflict-free reads and writes.
-__device__ __forceinline__ void dw3x3s2_p8(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int crop0, const float* w,
-                                           const float* bias, int tid) {
-    for (int task = tid; task < 32 * C8; task += NT) {
-        const int c = task >> 5, l = task & 31, p = l >> 3, crop = l & 7, oy = p >> 1, ox = p & 1;
-        const int cg = chunk0 + c;
-        float acc[8];
-        load8(bias + cg * 8, acc);
+// 2x2 tile of 32 crops), chunks chunk0 + c of a [.][128][8] tile.
+// Register tiled: task = (chunk, crop, channel half) loads the crop's whole 4x4 map of 4 channels once (a half
+// warp reads 128 contiguous bytes per pixel), converts it once and computes the four stride-2 outputs with static border handling.
+__device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int crop0, const float* w,
+                                              const float* bias, int tid) {
+    for (int task = tid; task < 16 * C8; task += NT) {
+        const int l = task & 15, crop = l >> 1, half = l & 1, c = task >> 4, cg = chunk0 + c;
+        const uint8_t* sbase = src + (size_t)c * 2048 + crop * 16 + half * 8;
+        uint2 in[16];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int iy = 2 * oy - 1 + ky;
-            if (iy < 0 || iy > 3) continue;
+        for (int p = 0; p < 16; ++p) in[p] = *reinterpret_cast<const uint2*>(sbase + p * 128);
+        const float* wp = w + cg * 8 + half * 4;
+        float4 wt[9];
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int ix = 2 * ox - 1 + kx;
-                if (ix < 0 || ix > 3) continue;
-                const uint4 v = *reinterpret_cast<const uint4*>(src + (((size_t)c * 128 + (iy * 4 + ix) * 8 + crop) << 4));
-                fma8(acc, v, w + (ky * 3 + kx) * C_total + cg * 8);
+        for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(wp + t * C_total);
+        const float4 b = *reinterpret_cast<const float4*>(bias + cg * 8 + half * 4);
+        float x[16][4];
+#pragma unroll
+        for (int p = 0; p < 16; ++p) {
+            x[p][0] = __uint_as_float(in[p].x << 16); x[p][1] = __uint_as_float(in[p].x & 0xffff0000u);
+            x[p][2] = __uint_as_float(in[p].y << 16); x[p][3] = __uint_as_float(in[p].y & 0xffff0000u);
+        }
+        uint8_t* dbase = dst + (((size_t)cg * 128 + crop0 + crop) << 4) + half * 8;
+#pragma unroll
+        for (int oy = 0; oy < 2; ++oy) {
+#pragma unroll
+            for (int ox = 0; ox < 2; ++ox) {
+                float a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int iy = 2 * oy - 1 + ky;
+                    if (iy < 0 || iy > 3) continue;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = 2 * ox - 1 + kx;
+                        if (ix < 0 || ix > 3) continue;
+                        const float4 ww = wt[ky * 3 + kx];
+                        const float* xx = x[iy * 4 + ix];
+                        a0 = fmaf(xx[0], ww.x, a0); a1 = fmaf(xx[1], ww.y, a1); a2 = fmaf(xx[2], ww.z, a2); a3 = fmaf(xx[3], ww.w, a3);
+                    }
+                }
+                *reinterpret_cast<uint2*>(dbase + (oy * 2 + ox) * 512) = make_uint2(pack2_relu(a0, a1), pack2_relu(a2, a3));
             }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-        *reinterpret_cast<uint4*>(dst + (((size_t)cg * 128 + p * 32 + crop0 + crop) << 4)) = pack8(acc);
     }
 }
 
@@ -368,7 +353,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             for (int h = 0; h < 2; ++h) {
                 epi_to_tile<true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs);
                 __syncthreads();
-                if (!(p.debug & 2)) dw3x3s2_p8(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                if (!(p.debug & 2)) dw3x3s2_p8_rt(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
                 __syncthreads();
             }
         }

@@ -72,8 +72,8 @@ struct Front3Params {
 };
 
 // Timing experiments (-DCV_FE_PROFILE, CV_FE3_DEBUG & 256): cycles the lead lane of each role spends in each barrier wait.
-__device__ unsigned long long g_fe3_prof[4 * 16];
 #ifdef CV_FE_PROFILE
+__device__ unsigned long long g_fe3_prof[4 * 16];
 #define TWAIT(k, call)                                                   \
     do {                                                                 \
         const long long _t = clock64();                                  \
