@@ -590,10 +590,15 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
         CV_CUDA(cudaMalloc(&h->dev_fen_len, (size_t)B));
         h->dev_fen_cap = B;
     }
-    // Chunks grow 128, 128, 256, 512, 512, ...: the first copy is the only one nothing overlaps, so it is kept short
+    // Chunk sizes 128, 128, 256, 512, ..., 512, 256, 128, 128: the first copy and the last compute are the only parts nothing
+    // overlaps, so both are kept short
     int slot = 0, it = 0;
     for (int b0 = 0, nb = 0; b0 < B; b0 += nb, slot ^= 1, ++it) {
-        nb = std::min(std::min(chunk, it < 2 ? 128 : it == 2 ? 256 : 512), B - b0);
+        const int left = B - b0;
+        nb = it < 2 ? 128 : it == 2 ? 256 : 512;
+        if (left <= 256) nb = std::min(nb, 128);
+        else if (left <= 512 + 256) nb = std::min(nb, 256);
+        nb = std::min(std::min(nb, chunk), left);
         if (it >= 2) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
         CV_CUDA(cudaMemcpyAsync(h->stage[slot], boards_host + (size_t)b0 * per_board, nb * per_board,
                                 cudaMemcpyHostToDevice, h->copy_stream));
