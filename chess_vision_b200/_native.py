@@ -73,6 +73,7 @@ def lib():
     _sig(L.cv_square_launch_count, i64, vp)
     _sig(L.cv_square_profile, i32, vp, i32)
     _sig(L.cv_square_profile_read, i32, vp, vp, vp)
+    _sig(L.cv_eval_accumulate, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp)
     if L.cv_abi_version() != 1:
         raise NativeError("libchessvision_b200.so ABI version mismatch")
     _lib = L

@@ -177,6 +177,21 @@ int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts);
 /* Number of kernels this library has launched on behalf of `h` since creation (bench bookkeeping). */
 int64_t cv_square_launch_count(const cv_square* h);
 
+/* ---- on-device evaluation bookkeeping (replaces the per-batch host loop of evaluate.py:74-155) --------------------------
+ * One batch of logits (device, fp32: squares (B,832), turn (B,1), castling (B,4)) against labels (device, uint8: class per
+ * square (B,64), turn (B), castling bits (B,4), legal flag (B)) is ADDED to `counters` (device, int64[CV_EVAL_COUNTERS], the
+ * caller zeroes it once): exact integer counts, laid out as below (confusion: rows = true class, evaluate.py:132-133).
+ * per_sample (device, uint8 (B,4)): squares wrong, board correct, turn correct, castling-all correct (the last two are 255 for
+ * positions that are not legal: the reference stores None, evaluate.py:142-143).  board_loss (device, float (B)): the sum of the
+ * 64 per-square cross-entropies of each board (evaluate.py:95): loss = sum / (64 * boards). */
+enum { CV_EVAL_TOTAL_BOARDS = 0, CV_EVAL_TOTAL_SQUARES = 1, CV_EVAL_CORRECT_SQUARES = 2, CV_EVAL_CORRECT_BOARDS = 3,
+       CV_EVAL_TOTAL_LEGAL = 4, CV_EVAL_CORRECT_TURN = 5, CV_EVAL_CORRECT_CASTLING_RIGHT = 6 /* 4 */, CV_EVAL_CORRECT_CASTLING_ALL = 10,
+       CV_EVAL_CORRECT_FULL_FEN = 11, CV_EVAL_PIECE_CORRECT = 12 /* 13 */, CV_EVAL_PIECE_TOTAL = 25 /* 13 */,
+       CV_EVAL_CONFUSION = 38 /* 13 x 13 */, CV_EVAL_TURN_CONFUSION = 207 /* 2 x 2 */, CV_EVAL_COUNTERS = 211 };
+int cv_eval_accumulate(const float* squares, const float* turn, const float* castling, const uint8_t* sq_labels,
+                       const uint8_t* turn_labels, const uint8_t* castling_labels, const uint8_t* legal, int B,
+                       int64_t* counters, uint8_t* per_sample, float* board_loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
