@@ -41,49 +41,68 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled every 5 ms through NVML while the timed region runs (the region is tens of
+    milliseconds long: `nvidia-smi -lms 200` can miss it entirely); falls back to one nvidia-smi query if NVML is unusable."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index):
-        self.gpu, self.lines, self.proc = gpu_index, [], None
+        self.gpu, self.samples, self.stop_flag, self.thread, self.h, self.nv = gpu_index, [], False, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "200"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nv = None
+
+    def _one(self):
+        nv, h = self.nv, self.h
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        return (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
+                nv.nvmlDeviceGetPowerUsage(h) / 1000.0, reasons)
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        while not self.stop_flag:
+            try:
+                self.samples.append(self._one())
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
+        if self.nv is None:
+            return self._smi_once()
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        if not self.samples:
+            return self._smi_once()
+        sm = [x[0] for x in self.samples]
+        bits = 0
+        for x in self.samples:
+            bits |= int(x[3])
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(x[1] for x in self.samples)),
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "power_w_max": max(x[2] for x in self.samples),
+                "samples": len(sm), "source": "nvml, 5 ms period"}
+
+    def _smi_once(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,power.draw", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=10).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "power_w_max": float(out[2]), "samples": 1,
+                    "source": "one nvidia-smi query after the timed region (NVML unavailable)"}
+        except Exception:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -65,7 +65,7 @@ struct Front3Params {
     const float* bias_b00;
     bf16* y;                          // T8 [crops*256 rows][16 ch]
     int n_crops, H;
-    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf, box_bytes;
+    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf, n_xbuf, box_bytes;
     int off_raw, off_hb, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
     int debug;
@@ -100,7 +100,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
-    for (int i = threadIdx.x; i < NXBUF * X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < p.n_xbuf * X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < (NYBUF * YH_BYTES + 256) / 16; i += NTHREADS) reinterpret_cast<uint4*>(Y)[i] = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < (int)(sizeof(Front3Tables) / 4); i += NTHREADS)
         reinterpret_cast<uint32_t*>(smem + p.off_tab)[i] = reinterpret_cast<const uint32_t*>(&tab_param)[i];
@@ -119,7 +119,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int rawmask = p.n_rawbuf - 1;
+    const int rawmask = p.n_rawbuf - 1, xmask = p.n_xbuf - 1, xshift = p.n_xbuf - 1;   // 1 or 2 buffers: slot = it & mask, use = it >> shift
 #ifdef CV_FE_PROFILE
     const int pw = (p.debug & 512) ? 12 : 8;                     // which producer warp is sampled
     const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
@@ -187,9 +187,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // HB complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
-            const int xslot = it & 1;
+            const int xslot = it & xmask;
             uint8_t* Xb = X + xslot * X_ALLOC;
-            TWAIT(1, mbar_wait(x_empty + xslot, ((it >> 1) & 1u) ^ 1u));                   // stem MMAs of the crop before last have read this image
+            TWAIT(1, mbar_wait(x_empty + xslot, ((it >> xshift) & 1u) ^ 1u));                   // stem MMAs of the crop before last have read this image
 #ifdef CV_FE_PROFILE
             const long long t_v0 = clock64();
 #endif
@@ -239,7 +239,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
         // stem tiles k = 2 s + h, k in [k0, k1), of the crop in X slot `xs`: output columns [8s, 8s+8), rows [16h, 16h+16)
         auto issue_stem = [&](int k0, int k1, uint32_t it) {
-            const uint32_t xb_lo = x_lo + (it & 1u) * (X_ALLOC >> 4);
+            const uint32_t xb_lo = x_lo + (it & xmask) * (X_ALLOC >> 4);
 #pragma unroll
             for (int k = k0; k < k1; ++k) {
                 const int s = k >> 1, h = k & 1;
@@ -282,14 +282,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         };
         uint32_t it = 0;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
-            TWAIT(2, mbar_wait(x_full + (it & 1u), (it >> 1) & 1u));
+            TWAIT(2, mbar_wait(x_full + (it & xmask), (it >> xshift) & 1u));
             tc_fence_after();
             // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
             // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
             issue_stem(0, 2, it);                                // slab 0
             if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
             issue_stem(2, 8, it);                                // slabs 1..3
-            if (elect_one()) mma_commit(x_empty + (it & 1u));      // operand image free once the stem MMAs have read it
+            if (elect_one()) mma_commit(x_empty + (it & xmask));      // operand image free once the stem MMAs have read it
             __syncwarp();
             issue_b00(0, it);                                    // this crop, left tile
         }
@@ -478,12 +478,13 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     p.raw_pitch = max_bytes;
     p.raw_bytes = (max_rows * max_bytes + 127) & ~127;
     p.hb_bytes = (max_rows * HB_PITCH + 127) & ~127;
-    const int fixed = NXBUF * X_ALLOC + NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
-    p.n_rawbuf = 2;
-    auto total = [&]() { return p.n_rawbuf * p.raw_bytes + p.hb_bytes + fixed; };
-    if (total() > 227 * 1024) p.n_rawbuf = 1;
+    const int fixed = NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
+    p.n_rawbuf = 2; p.n_xbuf = NXBUF;
+    auto total = [&]() { return p.n_xbuf * X_ALLOC + p.n_rawbuf * p.raw_bytes + p.hb_bytes + fixed; };
+    if (total() > 227 * 1024) p.n_rawbuf = 1;                     // larger windows (512x512 boards): single window buffer,
+    if (total() > 227 * 1024) p.n_xbuf = 1;                       // then a single stem operand image
     if (total() > 227 * 1024) return CV_OK;                       // window does not fit: not supported
-    int off = NXBUF * X_ALLOC;
+    int off = p.n_xbuf * X_ALLOC;
     p.off_raw = off; off += p.n_rawbuf * p.raw_bytes;
     p.off_hb = off; off += p.hb_bytes;
     off = (off + 127) & ~127; p.off_y = off; off += NYBUF * YH_BYTES + 256;

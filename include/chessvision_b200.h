@@ -91,7 +91,7 @@ int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
  * CV_IMPL_EARLY (needs CV_IMPL_MID): blocks.0.1 + blocks.1.0 + blocks.1.1 as one persistent kernel (2 CTAs per SM).
  * CV_IMPL_FRONTEND2 (with CV_IMPL_FRONTEND, uint8 HWC boards): the front end stages board windows by TMA and resizes
  * separably from shared memory (kernels_frontend2.cu); other sources use the first-generation front end.
- * CV_IMPL_FRONTEND3 (with CV_IMPL_FRONTEND, uint8 HWC boards whose crop window fits shared memory, i.e. up to 256x256):
+ * CV_IMPL_FRONTEND3 (with CV_IMPL_FRONTEND, uint8 HWC boards whose crop window fits shared memory: 256x256 and 512x512 do):
  * column-slab M tiles, fp16 stem operands (the resized pixels are bounded), stem output pipelined as half images
  * (kernels_frontend3.cu); falls back to the second generation otherwise. */
 enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_SPLIT_WEIGHTS = 8,

@@ -221,7 +221,7 @@ def test_fused_front_end_matches_layer_granular_kernels(gpu_model, gold_state, H
     finally:
         gpu_model.set_impl(1023)
     # second / third generation front ends (uint8 HWC: TMA-staged windows, separable fp16 resize; third generation = fp16 stem
-    # operands, column-slab tiles; 512x512 windows do not fit it and take the second generation): same result up to bf16 rounding
+    # operands, column-slab tiles): same result up to bf16 rounding
     full = oracle.forward(x, gold_state, return_features=True)["features"].numpy()
     ud = torch.from_numpy(u8).cuda()
     v3 = gpu_model.forward_u8(ud, precision="bf16", return_features=True)["features"].cpu().numpy()
