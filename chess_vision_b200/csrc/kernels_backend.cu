@@ -17,6 +17,7 @@
 // Row orders.  4x4-resolution tiles (stage input, blocks.3.0 head) are "P8": row = pixel*8 + crop_local, which makes
 // every depthwise neighbour access a contiguous, bank-conflict-free 16-byte-per-lane shared-memory read.  2x2-resolution
 // tiles are pixel-major as well (row = pixel*32 + crop): the in-place 2x2 depthwise then reads/writes contiguous rows per pixel.
+#include <cstdio>
 #include <cstdlib>
 #include "internal.h"
 #include "umma.cuh"
@@ -651,9 +652,9 @@ constexpr int OFF_A5 = 0;                 // 8 x 8192: blocks.2.0.dw_start outpu
 constexpr int OFF_R = 65536;              // 73728: E6a (24576) | A7 (2 x 24576)   ||  body: E (2 x 24576)  ||  E22a (49152) | E22b runs into X16
 constexpr int OFF_X16 = 139264;           // 2 x 12288: block input operand tiles (2 M-tiles of 8 crops, P8 rows, 48 ch); E6b during the 8x8 phase
 constexpr int OFF_IN = OFF_R + 24576;     // 65536: the tile's stage input (8 sub-tiles, P2X) lies over A7 + X16, both dead until dw_start has consumed it
-constexpr int OFF_W = 163840;             // weight arena: slot 0 (26112; also the resident 8x8-phase blobs) | slot 1 (20992)
-constexpr int W_SLOT1 = 26112;
-constexpr int W_ARENA = W_SLOT1 + 20992;  // 47104
+constexpr int OFF_W = 163840;             // weight arena, a ring of three slots: 0 (26112; also the resident 8x8-phase blobs) | 1 | 2 (20992 each)
+constexpr int W_SLOT1 = 26112, W_SLOT2 = W_SLOT1 + 20992;
+constexpr int W_ARENA = W_SLOT2 + 20992;  // 68096
 constexpr int OFF_BAR = OFF_W + W_ARENA;  // 169984
 constexpr int SMEM = OFF_BAR + 64;
 constexpr int H_OFF1 = 3328, H_OFF2 = 16000;    // slot 0 during the 8x8 phase: dw5 @0 (3328) | pw6 @3328 (12672) | dw7 @16000 (9984)
@@ -670,6 +671,15 @@ struct StageCParams {
     int debug;                // CV_SC_DEBUG ablation bits (timing experiments only: results are wrong): 1 no dw5x5, 2 no dw5x5s2, 4 no dw3x3, 8 no epilogue stores
 };
 
+// Timing experiments (-DCV_SC_PROFILE, CV_SC_DEBUG & 256): cycles thread 0 of CTA 0 spends per section of a tile
+// (0 wait weights+input | 1 dw_start | 2 pw6 MMA wait | 3 pw6 epilogue | 4 dw_mid 5x5 s2 | 8+op: 4x4-phase op; 30 weight waits, 31 MMA waits).
+#ifdef CV_SC_PROFILE
+__device__ unsigned long long g_sc_prof[40];
+#define SC_MARK(k) do { if (prof_on) { const long long _n = clock64(); pacc[k] += _n - plast; plast = _n; } } while (0)
+#else
+#define SC_MARK(k)
+#endif
+
 __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ StageCParams p) {
     using namespace sc;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -681,8 +691,8 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     uint8_t* X16 = smem + OFF_X16;
     uint8_t* WA = smem + OFF_W;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* wbar = bars;
-    uint64_t* inbar = bars + 2;
+    uint64_t* wbar = bars;                          // one per weight slot
+    uint64_t* inbar = bars + 3;
     uint64_t* mbar = bars + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -690,7 +700,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     const int mt = cs & 1, half = cs >> 1;          // body epilogues: M-tile and column half handled by this warp
 
     if (tid == 0) {
-        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(inbar, 1); mbar_init(inbar + 1, 1); mbar_init(mbar, 1);
+        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(wbar + 2, 1); mbar_init(inbar, 1); mbar_init(mbar, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -699,7 +709,13 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t wph0 = 0, wph1 = 0, inph = 0, mph = 0;
+    uint32_t wph = 0, inph = 0, mph = 0;              // wph: phase bit per weight slot
+#ifdef CV_SC_PROFILE
+    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && tid == 0;
+    long long pacc[40];
+    for (int i = 0; i < 40; ++i) pacc[i] = 0;
+    long long plast = clock64();
+#endif
 
     auto load_head_weights = [&]() {
         mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
@@ -711,14 +727,25 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         mbar_arrive_expect_tx(inbar, 65536);
         bulk_g2s(IN, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * 65536, 65536, inbar);
     };
+    // Weights stream L2 -> smem TWO ops ahead through the three-slot ring (a blob is 4-21 KB and its fetch takes about as long
+    // as two of the short 4x4-phase ops: with one op of look-ahead every op waited for its weights).  Op `op` >= 3 lives in
+    // slot (op - 2) % 3; the slot being refilled at begin_op(op) held op - 1, whose last reader passed a CTA barrier.
+    auto slot_of = [&](int op) { return (op - 2) % 3; };
+    auto slot_ptr = [&](int slot) { return WA + (slot == 0 ? 0 : slot == 1 ? W_SLOT1 : W_SLOT2); };
+    auto prefetch = [&](int op) {
+        const int sl = slot_of(op);
+        mbar_arrive_expect_tx(wbar + sl, p.bytes[op]);
+        bulk_g2s(slot_ptr(sl), p.wimg + p.off[op], p.bytes[op], wbar + sl);
+    };
+    auto wait_slot = [&](int sl) {
+        mbar_wait(wbar + sl, (wph >> sl) & 1u);
+        wph ^= 1u << sl;
+    };
     auto begin_op = [&](int op) -> uint8_t* {
-        if (tid == 0 && op + 1 < NOPS) {
-            uint64_t* b = wbar + ((op + 1) & 1);
-            mbar_arrive_expect_tx(b, p.bytes[op + 1]);
-            bulk_g2s(WA + (((op + 1) & 1) ? W_SLOT1 : 0), p.wimg + p.off[op + 1], p.bytes[op + 1], b);
-        }
-        if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
-        return WA + ((op & 1) ? W_SLOT1 : 0);
+        if (tid == 0 && op + 2 < NOPS) prefetch(op + 2);
+        const int sl = slot_of(op);
+        wait_slot(sl);
+        return slot_ptr(sl);
     };
     auto sync_before_mma = [&]() {
         fence_proxy_async_smem();
@@ -726,7 +753,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         __syncthreads();
     };
     auto wait_mma = [&]() {
-        mbar_wait(mbar, mph);
+        if (p.debug & 16) mbar_wait_spin(mbar, mph); else mbar_wait(mbar, mph);
         mph ^= 1u;
         tc_fence_after();
     };
@@ -738,20 +765,20 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         // ------------------------------ blocks.2.0 at 8x8: dw_start over the whole tile, then four pairs of 2-crop sub-tiles ----------
-        mbar_wait(wbar, wph0); wph0 ^= 1u;
+        SC_MARK(39);
+        wait_slot(0);
         const float* b5 = reinterpret_cast<const float*>(WA);
         const float* w5 = b5 + 32;
         const float* b6 = reinterpret_cast<const float*>(WA + H_OFF1);
         const uint32_t w6 = smem_u32(WA + H_OFF1 + 96 * 4);
         const float* b7 = reinterpret_cast<const float*>(WA + H_OFF2);
         const float* w7 = b7 + 96;
-        if (tid == 0) {
-            mbar_arrive_expect_tx(wbar + 1, p.bytes[3]);
-            bulk_g2s(WA + W_SLOT1, p.wimg + p.off[3], p.bytes[3], wbar + 1);
-        }
+        if (tid == 0) { prefetch(3); prefetch(4); }     // first two ops of the 4x4 phase -> slots 1, 2 while the 8x8 phase runs
         mbar_wait(inbar, inph); inph ^= 1u;
+        SC_MARK(0);
         if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
         sync_before_mma();
+        SC_MARK(1);
         for (int j = 0; j < 4; ++j) {
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
@@ -760,11 +787,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 mma_commit(mbar);
             }
             wait_mma();
+            SC_MARK(2);
             epi_to_e6(trow, ACC + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
             tc_fence_before();
             __syncthreads();
+            SC_MARK(3);
             if (!(p.debug & 2)) dw5x5s2_rows(E6, X16, A7 + (j >> 1) * 24576, (4 * j) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
             __syncthreads();
+            SC_MARK(4);
         }
         // ------------------------------ 4x4 phase: 2 M-tiles of 8 crops -----------------------------------------------------------
         int op = 3;
@@ -780,7 +810,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             wait_mma();
             epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
             __syncthreads();
-            ++op;
+            SC_MARK(8 + op); ++op;
         }
 #pragma unroll 1
         for (int blk = 1; blk <= 4; ++blk) {
@@ -796,14 +826,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 wait_mma();
                 epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
                 __syncthreads();
-                ++op;
+                SC_MARK(8 + op); ++op;
             }
             {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw3x3_p8_rt<true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
                 __syncthreads();
-                ++op;
+                SC_MARK(8 + op); ++op;
             }
             {   // pw_proj 96 -> 48 accumulated onto the residual stream
                 uint8_t* wb = begin_op(op);
@@ -817,7 +847,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 wait_mma();
                 epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
                 __syncthreads();
-                ++op;
+                SC_MARK(8 + op); ++op;
             }
         }
         // ------------------------------ blocks.2.5: dw_start 3x3, pw_exp 48 -> 192 (two column halves), pw_proj 192 -> 48 ------------
@@ -837,7 +867,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             wait_mma();
             epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
             __syncthreads();
-            ++op;
+            SC_MARK(8 + op); ++op;
         }
         {   // op 17: W22 columns 96..191
             uint8_t* wb = begin_op(op);
@@ -851,7 +881,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             wait_mma();
             epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
             __syncthreads();
-            ++op;
+            SC_MARK(8 + op); ++op;
         }
         const float* cum23;
         {   // op 18: W23 K rows 0..95 (+ cumulative bias)
@@ -863,7 +893,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
             }
-            ++op;
+            SC_MARK(8 + op); ++op;
         }
         {   // op 19: W23 K rows 96..191, then the stage output
             uint8_t* wb = begin_op(op);
@@ -875,7 +905,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             wait_mma();
             uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + mt) * 6 * 128;
             epi_to_global(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2);
-            ++op;
+            SC_MARK(8 + op); ++op;
         }
         const int next = tile + gridDim.x;
         tc_fence_before();
@@ -885,6 +915,9 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             load_in(next);
         }
     }
+#ifdef CV_SC_PROFILE
+    if (prof_on) for (int i = 0; i < 40; ++i) g_sc_prof[i] = (unsigned long long)pacc[i];
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -1292,6 +1325,19 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     stageC_kernel<<<grid, NT, sc::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
+#ifdef CV_SC_PROFILE
+    if (p.debug & 256) {
+        unsigned long long h[40];
+        CV_CUDA(cudaStreamSynchronize(s));
+        CV_CUDA(cudaMemcpyFromSymbol(h, g_sc_prof, sizeof(h)));
+        const double tiles = (double)((p.n_tiles + grid - 1) / grid);
+        fprintf(stderr, "stageC cycles per 16-crop tile: wait in/w %.0f | dw_start %.0f | pw6 mma %.0f | pw6 epi %.0f | dw_mid s2 %.0f | tile turnaround %.0f\n   4x4 ops 3..19:",
+                h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles, h[39] / tiles);
+        double sum = 0;
+        for (int op = 3; op < 20; ++op) { fprintf(stderr, " %.0f", h[8 + op] / tiles); sum += h[8 + op] / tiles; }
+        fprintf(stderr, "  (sum %.0f)\n", sum);
+    }
+#endif
     return CV_OK;
 }
 

@@ -161,6 +161,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             const int xp = t & 31;                               // fixed per thread: its 4 column taps are looked up once per crop
             const int xoff[4] = {tab.xo0[c][2 * xp], tab.xo1[c][2 * xp], tab.xo0[c][2 * xp + 1], tab.xo1[c][2 * xp + 1]};
             const float lxs[2] = {tab.lam[2 * xp], tab.lam[2 * xp + 1]};
+#pragma unroll 2
             for (int i = t >> 5; i < nrows; i += NPROD / 32) {
                 const uint8_t* rowp = raw + i * p.raw_pitch;
                 float v[6];
@@ -194,7 +195,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             const long long t_v0 = clock64();
 #endif
             // ---- vertical pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
-#pragma unroll 1
+#pragma unroll
             for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
                 const int sp = t + NPROD * k, py = sp >> 5, px = sp & 31;
                 if (sp >= 1024) break;

@@ -62,6 +62,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Busy-polling variant (mbarrier.test_wait never suspends the thread): for waits on the critical path of an op-synchronous
+// kernel, where every other warp of the CTA is waiting for the same event anyway.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, polls = 0;
+    uint64_t t0 = 0;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!ok && (++polls & 0xFFFFu) == 0) {
+            const uint64_t now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > kWaitTimeoutNs) __trap();
+        }
+    } while (!ok);
+}
+
 // ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP) ---------------------------
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
