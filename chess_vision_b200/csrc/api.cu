@@ -229,7 +229,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
                 ++h->launches;
             }
             rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img, h->sc_off, h->sc_bytes, reinterpret_cast<bf16*>(p8),
-                               h->num_sms, s);
+                               h->num_sms, (h->impl & CV_IMPL_MID_SPLIT) != 0, s);
             if (rc) return rc;
             ++h->launches;
             rc = prof_mark(h, CV_PROF_TAIL, s);
@@ -475,7 +475,7 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
 
 int cv_square_set_impl(cv_square* h, int mask) {
     CV_ARG(h != nullptr, "null handle");
-    CV_ARG(mask >= 0 && mask <= CV_IMPL_DEFAULT, "bad implementation mask");
+    CV_ARG(mask >= 0 && mask <= CV_IMPL_ALL, "bad implementation mask");
     h->impl = mask;
     return CV_OK;
 }

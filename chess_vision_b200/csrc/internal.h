@@ -154,7 +154,7 @@ size_t stageC_image_bytes();
 int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
 int launch_permute_p2(const bf16* in_t8, bf16* out_p2, int64_t n_crops, int C, cudaStream_t s);
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8,
-                  int num_sms, cudaStream_t s);
+                  int num_sms, int split /* two independent 8-crop warp groups per CTA */, cudaStream_t s);
 
 // stage B = blocks.0.1 + blocks.1.0 + blocks.1.1.  Input: the front end's T8 output (rows = crop*256 + pixel, 16 ch); output: P2 tiles.
 size_t stageB_image_bytes();

@@ -89,9 +89,10 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
 // handling: no branches, every load issued up front) and writes them back over its own inputs -- no other thread touches those
 // bytes, so no synchronisation is needed.  Against one task per output: 1.9x fewer instructions, 3x fewer LSU wavefronts.
 template <bool RELU>
-__device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, int tid) {
+__device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, int tid,
+                                            int nt = NT) {
     const int C = C8 * 8;
-    for (int task = tid; task < n_tasks; task += NT) {
+    for (int task = tid; task < n_tasks; task += nt) {
         const int l = task & 15, crop = l >> 1, half = l & 1, tc = task >> 4, c = tc % C8;
         const uint8_t* sbase = src + (size_t)tc * 2048 + crop * 16 + half * 8;
         uint8_t* base = buf + (size_t)tc * 2048 + crop * 16 + half * 8;
@@ -672,7 +673,8 @@ struct StageCParams {
 };
 
 // Timing experiments (-DCV_SC_PROFILE, CV_SC_DEBUG & 256): cycles thread 0 of CTA 0 spends per section of a tile
-// (0 wait weights+input | 1 dw_start | 2 pw6 MMA wait | 3 pw6 epilogue | 4 dw_mid 5x5 s2 | 8+op: 4x4-phase op; 30 weight waits, 31 MMA waits).
+// (0 wait weights+input | 1 dw_start | 2 pw6 MMA | 3 pw6 epilogue | 4 dw_mid 5x5 s2 | 8+op: 4x4-phase op).  clock64 is not ordered
+// against bar.sync: a section can contain the barrier wait of its neighbour -- trust sums, not single sections.
 #ifdef CV_SC_PROFILE
 __device__ unsigned long long g_sc_prof[40];
 #define SC_MARK(k) do { if (prof_on) { const long long _n = clock64(); pacc[k] += _n - plast; plast = _n; } } while (0)
@@ -753,7 +755,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         __syncthreads();
     };
     auto wait_mma = [&]() {
-        if (p.debug & 16) mbar_wait_spin(mbar, mph); else mbar_wait(mbar, mph);
+        mbar_wait(mbar, mph);
         mph ^= 1u;
         tc_fence_after();
     };
@@ -918,6 +920,261 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 #ifdef CV_SC_PROFILE
     if (prof_on) for (int i = 0; i < 40; ++i) g_sc_prof[i] = (unsigned long long)pacc[i];
 #endif
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+// =====================================================================================================================
+// stage C, warp-group version: the same 19 layers, but the two 8-crop halves of a tile run as two INDEPENDENT op chains, one per
+// group of 8 warps (own named barrier, own MMA-completion mbarrier, own buffers and TMEM columns).  The per-section timers of
+// the op-synchronous kernel showed every pointwise op costing 2.4-2.7 k cycles for 0.5-1 k cycles of tensor-pipe work (issue
+// -> completion -> wake-up -> epilogue -> barrier, all 16 warps in lock step): with two chains one group's MMA round trip runs
+// under the other group's epilogue / depthwise work.  Weights are shared: a 17th warp streams them two ops ahead through the
+// three-slot ring and recycles a slot when BOTH groups have released it (mbarrier with two arrivals).
+//   buffers of group g:  A5 half g (4 sub-tile images) | E6_g = g ? X16 region : R[0:24K] (8x8 phase; its first 12 KB hold the
+//   group's block-input tile in the 4x4 phase) | A7_g = R + 24576 (1 + g) (8x8 -> 4x4 hand-off, then the expanded tile E) |
+//   E22b_g = A5 half g (blocks.2.5 second half; A5 is dead by then).  TMEM: accumulators 192 g .., residual stream 400 + 48 g.
+// =====================================================================================================================
+namespace sc2 {
+constexpr int NTH = 17 * 32;
+constexpr int OFF_BAR = sc::OFF_W + sc::W_ARENA;
+constexpr int SMEM = OFF_BAR + 128;
+}  // namespace sc2
+
+__global__ void __launch_bounds__(sc2::NTH, 1) stageC2_kernel(const __grid_constant__ StageCParams p) {
+    using namespace sc;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* IN = smem + OFF_IN;
+    uint8_t* A5 = smem + OFF_A5;
+    uint8_t* R = smem + OFF_R;
+    uint8_t* X16 = smem + OFF_X16;
+    uint8_t* WA = smem + OFF_W;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sc2::OFF_BAR);
+    uint64_t *wbar = bars /*3: slot full*/, *wdone = bars + 3 /*3: slot released by both groups*/, *inbar = bars + 6, *mbarg = bars + 7 /*2*/;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(wbar + i, 1); mbar_init(wdone + i, 2); }
+        mbar_init(inbar, 1); mbar_init(mbarg, 1); mbar_init(mbarg + 1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    auto slot_of = [&](int op) { return (op - 2) % 3; };
+    auto slot_ptr = [&](int slot) { return WA + (slot == 0 ? 0 : slot == 1 ? W_SLOT1 : W_SLOT2); };
+
+    if (warp == 16) {
+        // =========================== weight / input producer ===================================================================
+        auto prefetch = [&](int op) {
+            const int sl = slot_of(op);
+            mbar_arrive_expect_tx(wbar + sl, p.bytes[op]);
+            bulk_g2s(slot_ptr(sl), p.wimg + p.off[op], p.bytes[op], wbar + sl);
+        };
+        auto load_tile = [&](int tile) {            // resident 8x8-phase blobs -> slot 0, the tile's stage input (one 64 KB copy)
+            mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
+            bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
+            bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
+            bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
+            mbar_arrive_expect_tx(inbar, 65536);
+            bulk_g2s(IN, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * 65536, 65536, inbar);
+        };
+        if (lane == 0 && blockIdx.x < p.n_tiles) load_tile(blockIdx.x);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            if (lane == 0) {
+                prefetch(3); prefetch(4);            // slots 1, 2: everything of the previous tile is behind the end-of-tile barrier
+                uint32_t dph = 0;                    // each slot completes an even number of times per tile: parities restart at 0
+                for (int op = 5; op < NOPS; ++op) {
+                    const int sl = slot_of(op);
+                    mbar_wait(wdone + sl, (dph >> sl) & 1u);
+                    dph ^= 1u << sl;
+                    prefetch(op);
+                }
+            }
+            __syncwarp();
+            __syncthreads();                         // end of tile (all 17 warps)
+            const int next = tile + gridDim.x;
+            if (lane == 0 && next < p.n_tiles) load_tile(next);
+        }
+    } else {
+        // =========================== two compute groups of 8 warps ==============================================================
+        const int quad = warp & 3, g = (warp >> 2) & 1, half = warp >> 3;      // TMEM lane quadrant, group, column half
+        const int row = quad * 32 + lane, gtid = (half * 4 + quad) * 32 + lane;
+        const bool leader_warp = quad == 0 && half == 0;
+        const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
+        const uint32_t ACCg = ACC + 192 * g, Sg = S_COL + 48 * g;
+        uint8_t* E6g = g ? X16 : R;                  // 8x8 phase: expanded sub-tile; 4x4 phase: block-input operand tile (first 12 KB)
+        uint8_t* A7g = R + 24576 * (1 + g);          // dw_mid output (A of pw_proj L8), then the expanded 4x4 tile E
+        uint8_t* X16g = E6g;
+        uint8_t* E22bg = A5 + 32768 * g;
+        uint64_t* mb = mbarg + g;
+        uint32_t wph = 0, inph = 0, mph = 0;
+        auto gbar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
+        auto wait_slot = [&](int sl) {
+            mbar_wait(wbar + sl, (wph >> sl) & 1u);
+            wph ^= 1u << sl;
+        };
+        auto begin_op = [&](int op) -> uint8_t* {
+            const int sl = slot_of(op);
+            wait_slot(sl);
+            return slot_ptr(sl);
+        };
+        auto release = [&](int sl) {                 // after a group barrier: nobody of this group reads the slot any more
+            if (gtid == 0) mbar_arrive(wdone + sl);
+        };
+        auto sync_before_mma = [&]() {
+            fence_proxy_async_smem();
+            tc_fence_before();
+            gbar();
+        };
+        auto wait_mma = [&]() {
+            mbar_wait(mb, mph);
+            mph ^= 1u;
+            tc_fence_after();
+        };
+        auto end_op = [&](int op) {
+            tc_fence_before();
+            gbar();
+            release(slot_of(op));
+        };
+
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            // ---------------- blocks.2.0.dw_start over the whole tile (both groups together) --------------------------------
+            wait_slot(0);
+            const float* b5 = reinterpret_cast<const float*>(WA);
+            const float* w5 = b5 + 32;
+            const float* b6 = reinterpret_cast<const float*>(WA + H_OFF1);
+            const uint32_t w6 = smem_u32(WA + H_OFF1 + 96 * 4);
+            const float* b7 = reinterpret_cast<const float*>(WA + H_OFF2);
+            const float* w7 = b7 + 96;
+            mbar_wait(inbar, inph); inph ^= 1u;
+            if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);
+            fence_proxy_async_smem();
+            tc_fence_before();
+            asm volatile("bar.sync 3, 512;" ::: "memory");
+            // ---------------- 8x8 phase of this group's four sub-tiles ---------------------------------------------------------
+            for (int jj = 0; jj < 4; ++jj) {
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(A5 + (4 * g + jj) * 8192), 32, w6, 96, 0, 96, tmem + ACCg, false, 2);     // L6 pw_exp 32 -> 96
+                    mma_commit(mb);
+                }
+                wait_mma();
+                epi_to_e6(trow, ACCg, b6, E6g, row, half, 2);
+                tc_fence_before();
+                gbar();
+                if (!(p.debug & 2)) dw5x5s2_rows(E6g, E6g, A7g, 2 * jj, w7, b7, (gtid & 15) | ((gtid >> 4) << 5));   // L7: 192 tasks, sub = 0
+                gbar();
+            }
+            release(0);
+            // ---------------- 4x4 phase on this group's M-tile -------------------------------------------------------------------
+            int op = 3;
+            {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
+                uint8_t* wb = begin_op(op);
+                sync_before_mma();
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, false, 2);
+                    mma_commit(mb);
+                }
+                wait_mma();
+                epi_to_tile<false>(trow, Sg, 48, reinterpret_cast<const float*>(wb), X16g, 0, row, half, 2);
+                end_op(op); ++op;
+            }
+#pragma unroll 1
+            for (int blk = 1; blk <= 4; ++blk) {
+                {   // pw_exp 48 -> 96 (+ReLU)
+                    uint8_t* wb = begin_op(op);
+                    sync_before_mma();
+                    if (leader_warp && elect_one()) {
+                        tc_fence_after();
+                        issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACCg, false, 2);
+                        mma_commit(mb);
+                    }
+                    wait_mma();
+                    epi_to_tile<true>(trow, ACCg, 96, reinterpret_cast<const float*>(wb), A7g, 0, row, half, 2);
+                    end_op(op); ++op;
+                }
+                {   // dw_mid 3x3 (+ReLU), in place
+                    uint8_t* wb = begin_op(op);
+                    const float* b = reinterpret_cast<const float*>(wb);
+                    if (!(p.debug & 4)) dw3x3_p8_rt<true>(A7g, A7g, 12 * 16, 12, b + 96, b, gtid, 256);
+                    end_op(op); ++op;
+                }
+                {   // pw_proj 96 -> 48 accumulated onto the residual stream
+                    uint8_t* wb = begin_op(op);
+                    sync_before_mma();
+                    if (leader_warp && elect_one()) {
+                        tc_fence_after();
+                        issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, true, 2);
+                        mma_commit(mb);
+                    }
+                    wait_mma();
+                    epi_to_tile<false>(trow, Sg, 48, reinterpret_cast<const float*>(wb), X16g, 0, row, half, 2);
+                    end_op(op); ++op;
+                }
+            }
+            // ---------------- blocks.2.5: dw_start 3x3, pw_exp 48 -> 192 (two column halves), pw_proj 192 -> 48 -------------------
+            {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
+                uint8_t* wb = begin_op(op);
+                const float* b21 = reinterpret_cast<const float*>(wb);
+                if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16g, X16g, 6 * 16, 6, b21 + 48, b21, gtid, 256);
+                sync_before_mma();
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACCg, false, 2);
+                    mma_commit(mb);
+                }
+                wait_mma();
+                epi_to_tile<true>(trow, ACCg, 96, reinterpret_cast<const float*>(wb + 1920), A7g, 0, row, half, 2);
+                end_op(op); ++op;
+            }
+            {   // op 17: W22 columns 96..191
+                uint8_t* wb = begin_op(op);
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACCg + 96, false, 2);
+                    mma_commit(mb);
+                }
+                wait_mma();
+                epi_to_tile<true>(trow, ACCg + 96, 96, reinterpret_cast<const float*>(wb), E22bg, 0, row, half, 2);
+                end_op(op); ++op;
+            }
+            const float* cum23;
+            {   // op 18: W23 K rows 0..95 (+ cumulative bias)
+                uint8_t* wb = begin_op(op);
+                cum23 = reinterpret_cast<const float*>(wb);
+                sync_before_mma();
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, true, 2);
+                }
+                ++op;
+            }
+            {   // op 19: W23 K rows 96..191, then the stage output
+                uint8_t* wb = begin_op(op);
+                if (leader_warp && elect_one()) {
+                    issue_gemm(smem_u32(E22bg), 96, smem_u32(wb), 48, 0, 48, tmem + Sg, true, 2);
+                    mma_commit(mb);
+                }
+                wait_mma();
+                uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + g) * 6 * 128;
+                epi_to_global(trow, Sg, 48, cum23, dst, row, half, 2);
+                tc_fence_before();
+                gbar();
+                release(slot_of(18));
+                release(slot_of(19));
+            }
+            tc_fence_before();
+            __syncthreads();                         // end of tile (all 17 warps): the next tile's input overwrites A7 / X16
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -1314,7 +1571,7 @@ int launch_permute_p2(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8, int num_sms,
-                  cudaStream_t s) {
+                  int split, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
     StageCParams p{};
@@ -1323,6 +1580,12 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
     for (int i = 0; i < sc::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
     CV_CUDA(cudaFuncSetAttribute(stageC_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
+    if (split) {
+        CV_CUDA(cudaFuncSetAttribute(stageC2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc2::SMEM));
+        stageC2_kernel<<<grid, sc2::NTH, sc2::SMEM, s>>>(p);
+        CV_CHECK_LAUNCH();
+        return CV_OK;
+    }
     stageC_kernel<<<grid, NT, sc::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
 #ifdef CV_SC_PROFILE

@@ -93,10 +93,13 @@ int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
  * separably from shared memory (kernels_frontend2.cu); other sources use the first-generation front end.
  * CV_IMPL_FRONTEND3 (with CV_IMPL_FRONTEND, uint8 HWC boards whose crop window fits shared memory: 256x256 and 512x512 do):
  * column-slab M tiles, fp16 stem operands (the resized pixels are bounded), stem output pipelined as half images
- * (kernels_frontend3.cu); falls back to the second generation otherwise. */
+ * (kernels_frontend3.cu); falls back to the second generation otherwise.
+ * CV_IMPL_MID_SPLIT (with CV_IMPL_MID; NOT in the default mask): the blocks.2 kernel runs the two 8-crop halves of a tile as
+ * two independent warp groups with a dedicated weight-streaming warp (same arithmetic, same bits as the op-synchronous
+ * kernel).  Measured 3 % slower than the op-synchronous kernel on B200 -- kept as the experiment DESIGN.md section 6 cites. */
 enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_SPLIT_WEIGHTS = 8,
        CV_IMPL_FRONTEND = 16, CV_IMPL_TAIL = 32, CV_IMPL_MID = 64, CV_IMPL_EARLY = 128, CV_IMPL_FRONTEND2 = 256, CV_IMPL_FRONTEND3 = 512,
-       CV_IMPL_DEFAULT = 1023 };
+       CV_IMPL_MID_SPLIT = 1024, CV_IMPL_DEFAULT = 1023, CV_IMPL_ALL = 2047 };
 int cv_square_set_impl(cv_square* h, int mask);
 
 /* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */

@@ -89,7 +89,7 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("mask", [1023, 511, 255, 127, 63, 31, 15, 7, 0])
+@pytest.mark.parametrize("mask", [2047, 1023, 511, 255, 127, 63, 31, 15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     """bf16 path: fused front end + tensor-core kernels (mask 31, the default), layer-granular tensor-core kernels
     with split hi+lo weights (15), with plain bf16 weights (7), and the plain CUDA-core kernels (0) against the
@@ -147,6 +147,20 @@ def test_fused_early_stage_matches_layer_granular_kernels(gpu_model, gold_state,
         print(f"n={n} {k}: rel err fused early+mid+tail {e_f:.3e}, fused mid+tail {e_s:.3e}, default {e_d:.3e}")
         assert e_f <= 1.25 * e_s + 1e-3 and e_d <= 1.25 * e_s + 2e-3, (k, e_f, e_s, e_d)
     assert torch.equal(fused["features"], sep["features"]), "same arithmetic (bf16 storage, hi+lo weights, fp32 accumulate): identical bits expected"
+
+
+def test_split_mid_stage_equals_op_synchronous_kernel(gpu_model):
+    """blocks.2 as two independent 8-crop warp groups with a weight-streaming warp (bit 1024, opt-in) vs the op-synchronous kernel:
+    same arithmetic in the same order -> identical bits, for full and ragged tile counts."""
+    for n in (1, 5, 37):
+        bd = torch.from_numpy(boards_u8(256, n, first=400)).cuda()
+        a = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+        gpu_model.set_impl(2047)
+        try:
+            b = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+        finally:
+            gpu_model.set_impl(1023)
+        assert all(torch.equal(a[k], b[k]) for k in a), n
 
 
 @pytest.mark.parametrize("n", [1, 7, 80])
