@@ -63,9 +63,10 @@ struct cv_square {
     int out_buf[CV_NUM_LAYERS];   // small-buffer index each layer writes (-1: dedicated stem buffer)
     // host-pointer pipeline resources (lazily created)
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    void* stage[2] = {nullptr, nullptr};
-    uint8_t* stage_flip[2] = {nullptr, nullptr};
+    static constexpr int kStages = 3;     // staging slots of the host path: the copy stream may run two chunks ahead of the compute stream
+    cudaEvent_t ev_h2d[kStages] = {}, ev_done[kStages] = {};
+    void* stage[kStages] = {};
+    uint8_t* stage_flip[kStages] = {};
     size_t stage_bytes = 0;
     void* own_ws = nullptr;
     size_t own_ws_bytes = 0;
@@ -410,7 +411,7 @@ int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
     cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe2_wimg); cudaFree(h->fe3_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < cv_square::kStages; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
@@ -561,15 +562,17 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
     if (!h->copy_stream) {
         CV_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CV_CUDA(cudaStreamCreateWithFlags(&h->compute_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < cv_square::kStages; ++i) {
             CV_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
             CV_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
         }
     }
     const size_t per_board = (size_t)H * H * 3;
-    const int chunk = std::min(B, 512);
+    int max_chunk = 512;
+    if (const char* e = getenv("CV_HOST_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);      // tuning experiments
+    const int chunk = std::min(B, max_chunk);
     if (h->stage_bytes < chunk * per_board) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < cv_square::kStages; ++i) {
             if (h->stage[i]) CV_CUDA(cudaFree(h->stage[i]));
             if (h->stage_flip[i]) CV_CUDA(cudaFree(h->stage_flip[i]));
             CV_CUDA(cudaMalloc(&h->stage[i], chunk * per_board));
@@ -590,21 +593,25 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
         CV_CUDA(cudaMalloc(&h->dev_fen_len, (size_t)B));
         h->dev_fen_cap = B;
     }
-    // Chunk sizes 128, 128, 256, 512, ..., 512, 256, 128, 128: the first copy and the last compute are the only parts nothing
-    // overlaps, so both are kept short
+    // Chunk sizes 128, 128, 256, 512, 512, ...: the first copy is the only one nothing overlaps, so it is kept short.  (Compute and
+    // copy cost about the same per board, so the compute stream ends one chunk behind the copy stream whatever the sizes at the
+    // end are; shrinking the last chunks only adds their lower efficiency -- measured and simulated, tools/gpu_host_trace.py.)
+    // CV_HOST_TRACE=1: per-chunk timeline (copy end, compute end, ms since the first copy was enqueued) on stderr
+    const bool trace = getenv("CV_HOST_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr_copy, tr_comp;
+    std::vector<int> tr_nb;
+    cudaEvent_t tr0 = nullptr;
+    if (trace) { CV_CUDA(cudaEventCreate(&tr0)); CV_CUDA(cudaEventRecord(tr0, h->copy_stream)); }
     int slot = 0, it = 0;
-    for (int b0 = 0, nb = 0; b0 < B; b0 += nb, slot ^= 1, ++it) {
-        const int left = B - b0;
-        nb = it < 2 ? 128 : it == 2 ? 256 : 512;
-        if (left <= 256) nb = std::min(nb, 128);
-        else if (left <= 512 + 256) nb = std::min(nb, 256);
-        nb = std::min(std::min(nb, chunk), left);
-        if (it >= 2) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
+    for (int b0 = 0, nb = 0; b0 < B; b0 += nb, slot = (slot + 1) % cv_square::kStages, ++it) {
+        nb = std::min(std::min(it < 2 ? 128 : it == 2 ? 256 : max_chunk, chunk), B - b0);
+        if (it >= cv_square::kStages) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
         CV_CUDA(cudaMemcpyAsync(h->stage[slot], boards_host + (size_t)b0 * per_board, nb * per_board,
                                 cudaMemcpyHostToDevice, h->copy_stream));
         if (flipped_host)
             CV_CUDA(cudaMemcpyAsync(h->stage_flip[slot], flipped_host + b0, nb, cudaMemcpyHostToDevice, h->copy_stream));
         CV_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        if (trace) { cudaEvent_t e; CV_CUDA(cudaEventCreate(&e)); CV_CUDA(cudaEventRecord(e, h->copy_stream)); tr_copy.push_back(e); tr_nb.push_back(nb); }
         CV_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_h2d[slot], 0));
         int rc = cv_square_predict_u8(h, static_cast<const uint8_t*>(h->stage[slot]), layout,
                                       flipped_host ? h->stage_flip[slot] : nullptr, nb, H, precision,
@@ -612,10 +619,21 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
                                       h->own_ws_bytes, h->compute_stream);
         if (rc) return rc;
         CV_CUDA(cudaEventRecord(h->ev_done[slot], h->compute_stream));
+        if (trace) { cudaEvent_t e; CV_CUDA(cudaEventCreate(&e)); CV_CUDA(cudaEventRecord(e, h->compute_stream)); tr_comp.push_back(e); }
     }
     CV_CUDA(cudaMemcpyAsync(fen_host, h->dev_fen, (size_t)B * CV_FEN_STRIDE, cudaMemcpyDeviceToHost, h->compute_stream));
     CV_CUDA(cudaMemcpyAsync(fen_len_host, h->dev_fen_len, (size_t)B, cudaMemcpyDeviceToHost, h->compute_stream));
     CV_CUDA(cudaStreamSynchronize(h->compute_stream));
+    if (trace) {
+        for (size_t i = 0; i < tr_copy.size(); ++i) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, tr0, tr_copy[i]);
+            cudaEventElapsedTime(&b, tr0, tr_comp[i]);
+            fprintf(stderr, "chunk %2zu (%4d boards): copy done %7.3f ms, compute done %7.3f ms\n", i, tr_nb[i], a, b);
+            cudaEventDestroy(tr_copy[i]); cudaEventDestroy(tr_comp[i]);
+        }
+        cudaEventDestroy(tr0);
+    }
     return CV_OK;
 }
 
