@@ -33,6 +33,12 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// Two fp32 FMAs in one instruction (FFMA2, sm_100+): same FMA-pipe throughput as two FFMAs but ONE issue slot -- the depthwise
+// loops are issue-bound (FMAs share the slots with loads, conversions and packs), so this is where their time goes down.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 bf2(uint32_t packed) { return make_float2(__uint_as_float(packed << 16), __uint_as_float(packed & 0xffff0000u)); }
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
     f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
@@ -104,17 +110,14 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
 #pragma unroll
         for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(wp + t * C);
         const float4 b = *reinterpret_cast<const float4*>(bias + c * 8 + half * 4);
-        float x[16][4];
+        float2 x[16][2];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            x[p][0] = __uint_as_float(in[p].x << 16); x[p][1] = __uint_as_float(in[p].x & 0xffff0000u);
-            x[p][2] = __uint_as_float(in[p].y << 16); x[p][3] = __uint_as_float(in[p].y & 0xffff0000u);
-        }
+        for (int p = 0; p < 16; ++p) { x[p][0] = bf2(in[p].x); x[p][1] = bf2(in[p].y); }
 #pragma unroll
         for (int oy = 0; oy < 4; ++oy) {
 #pragma unroll
             for (int ox = 0; ox < 4; ++ox) {
-                float a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+                float2 a01 = lo2(b), a23 = hi2(b);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const int iy = oy - 1 + ky;
@@ -123,14 +126,13 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
                     for (int kx = 0; kx < 3; ++kx) {
                         const int ix = ox - 1 + kx;
                         if (ix < 0 || ix > 3) continue;
-                        const float4 ww = wt[ky * 3 + kx];
-                        const float* xx = x[iy * 4 + ix];
-                        a0 = fmaf(xx[0], ww.x, a0); a1 = fmaf(xx[1], ww.y, a1); a2 = fmaf(xx[2], ww.z, a2); a3 = fmaf(xx[3], ww.w, a3);
+                        a01 = fma2(x[iy * 4 + ix][0], lo2(wt[ky * 3 + kx]), a01);
+                        a23 = fma2(x[iy * 4 + ix][1], hi2(wt[ky * 3 + kx]), a23);
                     }
                 }
                 uint2 o;
-                if (RELU) { o.x = pack2_relu(a0, a1); o.y = pack2_relu(a2, a3); }
-                else { o.x = pack2(a0, a1); o.y = pack2(a2, a3); }
+                if (RELU) { o.x = pack2_relu(a01.x, a01.y); o.y = pack2_relu(a23.x, a23.y); }
+                else { o.x = pack2(a01.x, a01.y); o.y = pack2(a23.x, a23.y); }
                 *reinterpret_cast<uint2*>(base + (oy * 4 + ox) * 128) = o;
             }
         }
@@ -154,18 +156,15 @@ __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, 
 #pragma unroll
         for (int t = 0; t < 9; ++t) wt[t] = *reinterpret_cast<const float4*>(wp + t * C_total);
         const float4 b = *reinterpret_cast<const float4*>(bias + cg * 8 + half * 4);
-        float x[16][4];
+        float2 x[16][2];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) {
-            x[p][0] = __uint_as_float(in[p].x << 16); x[p][1] = __uint_as_float(in[p].x & 0xffff0000u);
-            x[p][2] = __uint_as_float(in[p].y << 16); x[p][3] = __uint_as_float(in[p].y & 0xffff0000u);
-        }
+        for (int p = 0; p < 16; ++p) { x[p][0] = bf2(in[p].x); x[p][1] = bf2(in[p].y); }
         uint8_t* dbase = dst + (((size_t)cg * 128 + crop0 + crop) << 4) + half * 8;
 #pragma unroll
         for (int oy = 0; oy < 2; ++oy) {
 #pragma unroll
             for (int ox = 0; ox < 2; ++ox) {
-                float a0 = b.x, a1 = b.y, a2 = b.z, a3 = b.w;
+                float2 a01 = lo2(b), a23 = hi2(b);
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const int iy = 2 * oy - 1 + ky;
@@ -174,12 +173,11 @@ __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, 
                     for (int kx = 0; kx < 3; ++kx) {
                         const int ix = 2 * ox - 1 + kx;
                         if (ix < 0 || ix > 3) continue;
-                        const float4 ww = wt[ky * 3 + kx];
-                        const float* xx = x[iy * 4 + ix];
-                        a0 = fmaf(xx[0], ww.x, a0); a1 = fmaf(xx[1], ww.y, a1); a2 = fmaf(xx[2], ww.z, a2); a3 = fmaf(xx[3], ww.w, a3);
+                        a01 = fma2(x[iy * 4 + ix][0], lo2(wt[ky * 3 + kx]), a01);
+                        a23 = fma2(x[iy * 4 + ix][1], hi2(wt[ky * 3 + kx]), a23);
                     }
                 }
-                *reinterpret_cast<uint2*>(dbase + (oy * 2 + ox) * 512) = make_uint2(pack2_relu(a0, a1), pack2_relu(a2, a3));
+                *reinterpret_cast<uint2*>(dbase + (oy * 2 + ox) * 512) = make_uint2(pack2_relu(a01.x, a01.y), pack2_relu(a23.x, a23.y));
             }
         }
     }
@@ -540,9 +538,9 @@ __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, con
         const uint8_t* sp = src + t * 8192 + l * 8;
         const int coff = (l >> 2) * 8 + (l & 1) * 4;             // first of this task's 4 channels
         const float4 b = *reinterpret_cast<const float4*>(bias + coff);
-        float acc[8][4];
+        float2 acc[8][2];
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) { acc[ox][0] = b.x; acc[ox][1] = b.y; acc[ox][2] = b.z; acc[ox][3] = b.w; }
+        for (int ox = 0; ox < 8; ++ox) { acc[ox][0] = lo2(b); acc[ox][1] = hi2(b); }
 #pragma unroll
         for (int ky = 0; ky < 5; ++ky) {
             const int iy = y + ky - 2;
@@ -553,26 +551,23 @@ __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, con
             float4 wt[5];
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 32 + coff);
-            float xv[8][4];
+            float2 xv[8][2];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) {
-                xv[x][0] = __uint_as_float(in[x].x << 16); xv[x][1] = __uint_as_float(in[x].x & 0xffff0000u);
-                xv[x][2] = __uint_as_float(in[x].y << 16); xv[x][3] = __uint_as_float(in[x].y & 0xffff0000u);
-            }
+            for (int x = 0; x < 8; ++x) { xv[x][0] = bf2(in[x].x); xv[x][1] = bf2(in[x].y); }
 #pragma unroll
             for (int ox = 0; ox < 8; ++ox) {
 #pragma unroll
                 for (int kx = 0; kx < 5; ++kx) {
                     const int ix = ox + kx - 2;
                     if (ix < 0 || ix > 7) continue;
-                    acc[ox][0] = fmaf(xv[ix][0], wt[kx].x, acc[ox][0]); acc[ox][1] = fmaf(xv[ix][1], wt[kx].y, acc[ox][1]);
-                    acc[ox][2] = fmaf(xv[ix][2], wt[kx].z, acc[ox][2]); acc[ox][3] = fmaf(xv[ix][3], wt[kx].w, acc[ox][3]);
+                    acc[ox][0] = fma2(xv[ix][0], lo2(wt[kx]), acc[ox][0]);
+                    acc[ox][1] = fma2(xv[ix][1], hi2(wt[kx]), acc[ox][1]);
                 }
             }
         }
         uint8_t* dp = dst + t * 8192 + (l >> 2) * 2048 + ((l >> 1) & 1) * 16 + (l & 1) * 8 + y * 8 * 32;
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) *reinterpret_cast<uint2*>(dp + ox * 32) = make_uint2(pack2(acc[ox][0], acc[ox][1]), pack2(acc[ox][2], acc[ox][3]));
+        for (int ox = 0; ox < 8; ++ox) *reinterpret_cast<uint2*>(dp + ox * 32) = make_uint2(pack2(acc[ox][0].x, acc[ox][0].y), pack2(acc[ox][1].x, acc[ox][1].y));
     }
 }
 
@@ -610,9 +605,9 @@ __device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t*
     const uint8_t* sp = (sub ? src1 : src0) + half * 8;
     const int coff = chunk * 8 + half * 4;
     const float4 b = *reinterpret_cast<const float4*>(bias + coff);
-    float acc[4][4];
+    float2 acc[4][2];
 #pragma unroll
-    for (int ox = 0; ox < 4; ++ox) { acc[ox][0] = b.x; acc[ox][1] = b.y; acc[ox][2] = b.z; acc[ox][3] = b.w; }
+    for (int ox = 0; ox < 4; ++ox) { acc[ox][0] = lo2(b); acc[ox][1] = hi2(b); }
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
         const int iy = 2 * oy + ky - 2;
@@ -623,26 +618,23 @@ __device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t*
         float4 wt[5];
 #pragma unroll
         for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 96 + coff);
-        float xv[8][4];
+        float2 xv[8][2];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) {
-            xv[x][0] = __uint_as_float(in[x].x << 16); xv[x][1] = __uint_as_float(in[x].x & 0xffff0000u);
-            xv[x][2] = __uint_as_float(in[x].y << 16); xv[x][3] = __uint_as_float(in[x].y & 0xffff0000u);
-        }
+        for (int x = 0; x < 8; ++x) { xv[x][0] = bf2(in[x].x); xv[x][1] = bf2(in[x].y); }
 #pragma unroll
         for (int ox = 0; ox < 4; ++ox) {
 #pragma unroll
             for (int kx = 0; kx < 5; ++kx) {
                 const int ix = 2 * ox + kx - 2;
                 if (ix < 0 || ix > 7) continue;
-                acc[ox][0] = fmaf(xv[ix][0], wt[kx].x, acc[ox][0]); acc[ox][1] = fmaf(xv[ix][1], wt[kx].y, acc[ox][1]);
-                acc[ox][2] = fmaf(xv[ix][2], wt[kx].z, acc[ox][2]); acc[ox][3] = fmaf(xv[ix][3], wt[kx].w, acc[ox][3]);
+                acc[ox][0] = fma2(xv[ix][0], lo2(wt[kx]), acc[ox][0]);
+                    acc[ox][1] = fma2(xv[ix][1], hi2(wt[kx]), acc[ox][1]);
             }
         }
     }
     uint8_t* dp = dst + chunk * 2048 + (oy * 4 * 8 + crop0 + 2 * sub + crop) * 16 + half * 8;
 #pragma unroll
-    for (int ox = 0; ox < 4; ++ox) *reinterpret_cast<uint2*>(dp + ox * 128) = make_uint2(pack2_relu(acc[ox][0], acc[ox][1]), pack2_relu(acc[ox][2], acc[ox][3]));
+    for (int ox = 0; ox < 4; ++ox) *reinterpret_cast<uint2*>(dp + ox * 128) = make_uint2(pack2_relu(acc[ox][0].x, acc[ox][0].y), pack2_relu(acc[ox][1].x, acc[ox][1].y));
 }
 
 namespace sc {
@@ -669,7 +661,8 @@ struct StageCParams {
     bf16* y;                  // stage output: P8 tiles (128 rows = 8 crops, row = pix*8 + crop) x 48 ch  == stage D input
     int n_tiles;              // n_crops / 16
     uint32_t off[sc::NOPS], bytes[sc::NOPS];
-    int debug;                // CV_SC_DEBUG ablation bits (timing experiments only: results are wrong): 1 no dw5x5, 2 no dw5x5s2, 4 no dw3x3, 8 no epilogue stores
+    int debug;                // CV_SC_DEBUG ablation bits (timing experiments only: results are wrong): 1 no dw5x5, 2 no dw5x5s2, 4 no dw3x3,
+                              // 32 no MMA / epilogue in the 4x4 phase (what is left is the per-op barrier + weight-stream cost), 256 section timers
 };
 
 // Timing experiments (-DCV_SC_PROFILE, CV_SC_DEBUG & 256): cycles thread 0 of CTA 0 spends per section of a tile
@@ -803,14 +796,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (warp == 0 && elect_one()) {
+            if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
                 mma_commit(mbar);
             }
-            wait_mma();
-            epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+            if (!(p.debug & 32)) wait_mma();
+            if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }
@@ -819,14 +812,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // pw_exp 48 -> 96 (+ReLU)
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (warp == 0 && elect_one()) {
+                if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
                     mma_commit(mbar);
                 }
-                wait_mma();
-                epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
+                if (!(p.debug & 32)) wait_mma();
+                if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
@@ -840,14 +833,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // pw_proj 96 -> 48 accumulated onto the residual stream
                 uint8_t* wb = begin_op(op);
                 sync_before_mma();
-                if (warp == 0 && elect_one()) {
+                if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
                     mma_commit(mbar);
                 }
-                wait_mma();
-                epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+                if (!(p.debug & 32)) wait_mma();
+                if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
@@ -860,28 +853,28 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             const float* b21 = reinterpret_cast<const float*>(wb);
             if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
             sync_before_mma();
-            if (warp == 0 && elect_one()) {
+            if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
                 mma_commit(mbar);
             }
-            wait_mma();
-            epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
+            if (!(p.debug & 32)) wait_mma();
+            if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }
         {   // op 17: W22 columns 96..191
             uint8_t* wb = begin_op(op);
             sync_before_mma();
-            if (warp == 0 && elect_one()) {
+            if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
                 mma_commit(mbar);
             }
-            wait_mma();
-            epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
+            if (!(p.debug & 32)) wait_mma();
+            if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }
@@ -890,7 +883,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             uint8_t* wb = begin_op(op);
             cum23 = reinterpret_cast<const float*>(wb);
             sync_before_mma();
-            if (warp == 0 && elect_one()) {
+            if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
@@ -899,14 +892,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         }
         {   // op 19: W23 K rows 96..191, then the stage output
             uint8_t* wb = begin_op(op);
-            if (warp == 0 && elect_one()) {
+            if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
                 mma_commit(mbar);
             }
-            wait_mma();
+            if (!(p.debug & 32)) wait_mma();
             uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + mt) * 6 * 128;
-            epi_to_global(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2);
+            if (!(p.debug & 32)) epi_to_global(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2);
             SC_MARK(8 + op); ++op;
         }
         const int next = tile + gridDim.x;
