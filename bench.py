@@ -69,16 +69,15 @@ class ClockSampler:
             reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
         except Exception:
             reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-        return (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM),
-                nv.nvmlDeviceGetPowerUsage(h) / 1000.0, reasons)
+        return (nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), self.smax, nv.nvmlDeviceGetPowerUsage(h) / 1000.0, reasons)
 
     def _pump(self):
-        while not self.stop_flag:
+        self.smax = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        while not self.stop_flag:                 # back to back: one NVML round trip is already several milliseconds
             try:
                 self.samples.append(self._one())
             except Exception:
-                pass
-            time.sleep(0.005)
+                time.sleep(0.002)
 
     def stop(self):
         if self.nv is None:
@@ -93,7 +92,7 @@ class ClockSampler:
             bits |= int(x[3])
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(x[1] for x in self.samples)),
                 "reasons": sorted(n for b, n in self.REASONS.items() if bits & b), "power_w_max": max(x[2] for x in self.samples),
-                "samples": len(sm), "source": "nvml, 5 ms period"}
+                "samples": len(sm), "source": "nvml, sampled back to back during the timed region"}
 
     def _smi_once(self):
         try:
@@ -234,11 +233,11 @@ def run_native(args):
         return float(t.item())
 
     # ---- device-resident timing (value) -------------------------------------------------------------
+    sampler = ClockSampler(local)          # started before the warm-up: NVML start-up stays out of the timed region, and every
+    sampler.start()                        # sample (warm-up + timed steps) is taken under the same load
     for _ in range(max(args.warmup, 3)):
         fen, fen_len = model.predict_fen_device(boards)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = model.launch_count()
     model.profile(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
