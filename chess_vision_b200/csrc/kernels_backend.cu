@@ -1465,7 +1465,9 @@ int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const 
     StageDParams p{};
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
     p.tiled = tiled; p.crop_base = crop_base;
+#ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SD_DEBUG"); p.debug = d ? atoi(d) : 0; }
+#endif
     for (int i = 0; i < sd::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
     CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
@@ -1569,7 +1571,9 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
     if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
     StageCParams p{};
     p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16);
+#ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SC_DEBUG"); p.debug = d ? atoi(d) : 0; }
+#endif
     for (int i = 0; i < sc::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
     CV_CUDA(cudaFuncSetAttribute(stageC_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
