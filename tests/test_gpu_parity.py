@@ -251,6 +251,20 @@ def test_fused_front_end_matches_layer_granular_kernels(gpu_model, gold_state, H
         assert not np.array_equal(v3, v2)       # the third generation really ran (different rounding points)
 
 
+@pytest.mark.parametrize("H", [96, 160, 352, 448])
+def test_other_board_sizes(gpu_model, gold_state, H):
+    """Every multiple of 32 is a legal board side (square.py:53-55 works for any H divisible by 8): the front-end tap tables,
+    TMA box and window buffers are derived per launch.  fp32: logits 1e-5 and FEN bit-exact; bf16: trunk features 1e-2."""
+    u8 = boards_u8(H, 3)
+    ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
+    bd = torch.from_numpy(u8).cuda()
+    o32 = gpu_model.forward_u8(bd, precision="fp32")
+    assert rel_err(o32["squares"].cpu().numpy(), ref["squares"].numpy()) < FP32_TOL
+    assert gpu_model.predict_fen(bd, precision="fp32") == oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy())
+    o16 = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
+    assert rel_err(o16["features"].cpu().numpy(), ref["features"].numpy()) < 1e-2
+
+
 # ------------------------------------------------------------------------------------------ full forward
 @pytest.mark.parametrize("H,n", [(256, 8), (512, 2)])
 def test_forward_fp32_matches_reference(gpu_model, golden, gold_state, H, n):
