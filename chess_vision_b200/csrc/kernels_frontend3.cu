@@ -45,7 +45,6 @@ constexpr int NXBUF = 2;                                       // stem operand i
 constexpr int W_STEM_BYTES = 4 * 1024;                         // taps x [2 chunks][32 n][8] fp16
 constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) x [2 chunks][32 n = hi 16 | lo 16][8] bf16
 constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
-constexpr int HB_PITCH = 64 * 3 * 2;                           // fp16 row of 64 normalised pixels
 constexpr int NPROD = 384;                                      // 12 resize producer warps (the resize is the longest per-crop job)
 constexpr int MMA_WARP = 8 + NPROD / 32;
 constexpr int NTHREADS = (MMA_WARP + 1) * 32;
@@ -53,10 +52,11 @@ constexpr int TM_B00 = 256;                                    // TMEM: stem til
 
 struct Front3Tables {                 // per launch, copied to shared memory
     uint32_t vy[8][64];               // vertical taps of output row d for square row r: row0 | row1 << 8 | fp16(lambda) << 16
-    int16_t xo0[8][64], xo1[8][64];   // byte offsets inside a staged window row of output column d for square column c
-    float lam[64];
+    uint8_t xh0[8][64], xh1[8][64];   // horizontal taps of output column d for square column c: pixel index in the staged window
+    uint16_t lamh[64];                // fp16(lambda) per output column
     int32_t row0[8], nrows[8];        // first board row and number of rows staged for square row r
-    int32_t byte0[8], nbytes[8];      // first byte (16-aligned) and byte count (multiple of 16) of a staged row for square column c
+    int32_t byte0[8], boff[8];        // square column c: first staged byte of a board row (16-byte aligned, as the TMA tile needs) and the offset of the
+                                      // first pixel GROUP inside the staged row (pixel index a multiple of 4 -> byte offset a multiple of 4: word-aligned groups)
 };
 
 struct Front3Params {
@@ -65,8 +65,8 @@ struct Front3Params {
     const float* bias_b00;
     bf16* y;                          // T8 [crops*256 rows][16 ch]
     int n_crops, H;
-    int raw_pitch, raw_bytes, hb_bytes, n_rawbuf, n_xbuf, box_bytes;
-    int off_raw, off_hb, off_y, off_w, off_tab, off_bar, smem_total;
+    int raw_pitch, raw_bytes, v_pitch, v_bytes, n_groups, g_magic, n_rawbuf, n_xbuf, box_bytes;
+    int off_raw, off_v, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
     int debug;
 };
@@ -89,7 +89,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* X = smem;
     uint8_t* RAW = smem + p.off_raw;                              // n_rawbuf x raw_bytes
-    uint8_t* HB = smem + p.off_hb;
+    uint8_t* V = smem + p.off_v;                                  // 64 rows x window pixels x [R G B -] fp16, vertically resized + normalised
     uint8_t* Y = smem + p.off_y;                                  // NYBUF half images
     uint8_t* W = smem + p.off_w;
     const Front3Tables& tab = *reinterpret_cast<const Front3Tables*>(smem + p.off_tab);
@@ -130,7 +130,10 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     if (warp >= 8 && warp < MMA_WARP) {
         // =========================== resize producers (256 threads) ==========================================================
         const int t = threadIdx.x - 256;
-        const float a0 = p.na[0], a1 = p.na[1], a2 = p.na[2], b0 = p.nb[0], b1 = p.nb[1], b2 = p.nb[2];
+        // normalisation v = na[c] * u8 + nb[c] as half2 constants for the channel pairs a pixel group runs through: (R,G) (B,R) (G,B)
+        const __half2 na2[3] = {__floats2half2_rn(p.na[0], p.na[1]), __floats2half2_rn(p.na[2], p.na[0]), __floats2half2_rn(p.na[1], p.na[2])};
+        const __half2 nb2[3] = {__floats2half2_rn(p.nb[0], p.nb[1]), __floats2half2_rn(p.nb[2], p.nb[0]), __floats2half2_rn(p.nb[1], p.nb[2])};
+        const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
         // stage the board window of crop `nn` (iteration index iti) into RAW slot iti & rawmask: ONE 2D TMA tile copy (rows x bytes box
         // of the (B*H rows, H*3 bytes) board tensor at the clamped window origin; what lies beyond the window is never read), issued by
         // one lane of warp 8.  The slot is free: its previous user is the horizontal pass of an earlier crop, which ended at a
@@ -153,40 +156,44 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             const uint8_t* raw = RAW + rslot * p.raw_bytes;
             if (warp == 8 && p.n_rawbuf == 2 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // prefetch
             TWAIT(0, mbar_wait(raw_full + rslot, (it / p.n_rawbuf) & 1u));
-            // ---- horizontal pass: window row i, output columns 2xp, 2xp+1 -> 6 fp16 (normalised) at HB[i][xp]
+            // ---- vertical pass first, on the raw bytes: item = (output row y, group of 4 window pixels = 12 bytes = 3 aligned words).
+            //      Bytes become fp16 pairs by PRMT (0x6400 | b = 1024 + b exactly), the lerp u0 + ly (u1 - u0) and the normalisation
+            //      a u + b run in half2 arithmetic; the 4 pixels are stored as [R G B -] (8 bytes each): V[y][pixel].
 #ifdef CV_FE_PROFILE
             const long long t_h0 = clock64();
 #endif
-            const int nrows = tab.nrows[r];
-            const int xp = t & 31;                               // fixed per thread: its 4 column taps are looked up once per crop
-            const int xoff[4] = {tab.xo0[c][2 * xp], tab.xo1[c][2 * xp], tab.xo0[c][2 * xp + 1], tab.xo1[c][2 * xp + 1]};
-            const float lxs[2] = {tab.lam[2 * xp], tab.lam[2 * xp + 1]};
-#pragma unroll 2
-            for (int i = t >> 5; i < nrows; i += NPROD / 32) {
-                const uint8_t* rowp = raw + i * p.raw_pitch;
-                float v[6];
+            {
+                const int n_items = 64 * p.n_groups, boff = tab.boff[c];
+                for (int item = t; item < ((p.debug & 1) ? 0 : n_items); item += NPROD) {
+                    const int y = __umulhi((unsigned)item, (unsigned)p.g_magic), gq = item - y * p.n_groups;
+                    const uint32_t vy = tab.vy[r][y];
+                    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(raw + (vy & 255u) * p.raw_pitch + boff + gq * 12);
+                    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(raw + ((vy >> 8) & 255u) * p.raw_pitch + boff + gq * 12);
+                    const uint32_t l2 = (vy >> 16) * 0x10001u;
+                    const __half2 ly = *reinterpret_cast<const __half2*>(&l2);
+                    uint32_t n[6];
 #pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const uint8_t* q0 = rowp + xoff[2 * dx];
-                    const uint8_t* q1 = rowp + xoff[2 * dx + 1];
-                    const float lx = lxs[dx];
-                    const float u00 = (float)q0[0], u01 = (float)q0[1], u02 = (float)q0[2];
-                    const float u10 = (float)q1[0], u11 = (float)q1[1], u12 = (float)q1[2];
-                    v[dx * 3 + 0] = fmaf(a0, fmaf(lx, u10 - u00, u00), b0);
-                    v[dx * 3 + 1] = fmaf(a1, fmaf(lx, u11 - u01, u01), b1);
-                    v[dx * 3 + 2] = fmaf(a2, fmaf(lx, u12 - u02, u02), b2);
-                }
-                uint32_t* o = reinterpret_cast<uint32_t*>(HB + i * HB_PITCH + xp * 12);
+                    for (int w = 0; w < 3; ++w) {
+                        const uint32_t a = r0[w], b = r1[w];
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    __half2 h = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
-                    o[k] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const uint32_t ma = __byte_perm(a, 0x64646464u, hh ? 0x4342u : 0x4140u), mb = __byte_perm(b, 0x64646464u, hh ? 0x4342u : 0x4140u);
+                            const __half2 m0 = *reinterpret_cast<const __half2*>(&ma), m1 = *reinterpret_cast<const __half2*>(&mb);
+                            const __half2 u = __hfma2(ly, __hsub2(m1, m0), __hsub2(m0, k1024));     // both differences are exact
+                            const int k = (2 * w + hh) % 3;                                        // channel pair (R,G) / (B,R) / (G,B)
+                            const __half2 v = __hfma2(na2[k], u, nb2[k]);
+                            n[2 * w + hh] = *reinterpret_cast<const uint32_t*>(&v);
+                        }
+                    }
+                    uint4* dst = reinterpret_cast<uint4*>(V + y * p.v_pitch + gq * 32);
+                    dst[0] = make_uint4(n[0], n[1] & 0xffffu, __byte_perm(n[1], n[2], 0x5432u), n[2] >> 16);
+                    dst[1] = make_uint4(n[3], n[4] & 0xffffu, __byte_perm(n[4], n[5], 0x5432u), n[5] >> 16);
                 }
             }
 #ifdef CV_FE_PROFILE
             if (prof_on) pacc[4] += clock64() - t_h0;
 #endif
-            TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // HB complete, RAW slot consumed
+            TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // V complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
             const int xslot = it & xmask;
             uint8_t* Xb = X + xslot * X_ALLOC;
@@ -194,31 +201,45 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #ifdef CV_FE_PROFILE
             const long long t_v0 = clock64();
 #endif
-            // ---- vertical pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
+            // ---- horizontal pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
+            {
+                const int px = t & 31;                               // fixed per thread: its column taps are looked up once per crop
+                int xa[2], xb[2];
+                __half2 lx[2];
 #pragma unroll
-            for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
-                const int sp = t + NPROD * k, py = sp >> 5, px = sp & 31;
-                if (sp >= 1024) break;
-                uint32_t o[6];
-#pragma unroll
-                for (int dy = 0; dy < 2; ++dy) {
-                    const uint32_t vy = tab.vy[r][2 * py + dy];
-                    const uint32_t* h0 = reinterpret_cast<const uint32_t*>(HB + (vy & 255u) * HB_PITCH + px * 12);
-                    const uint32_t* h1 = reinterpret_cast<const uint32_t*>(HB + ((vy >> 8) & 255u) * HB_PITCH + px * 12);
-                    const uint32_t l2 = (vy >> 16) * 0x10001u;
-                    const __half2 ly = *reinterpret_cast<const __half2*>(&l2);
-#pragma unroll
-                    for (int w = 0; w < 3; ++w) {
-                        const uint32_t w0 = h0[w], w1 = h1[w];
-                        const __half2 f0 = *reinterpret_cast<const __half2*>(&w0), f1 = *reinterpret_cast<const __half2*>(&w1);
-                        const __half2 res = __hfma2(ly, __hsub2(f1, f0), f0);
-                        o[dy * 3 + w] = *reinterpret_cast<const uint32_t*>(&res);
-                    }
+                for (int dx = 0; dx < 2; ++dx) {
+                    xa[dx] = tab.xh0[c][2 * px + dx] * 8;
+                    xb[dx] = tab.xh1[c][2 * px + dx] * 8;
+                    const uint32_t l2 = tab.lamh[2 * px + dx] * 0x10001u;
+                    lx[dx] = *reinterpret_cast<const __half2*>(&l2);
                 }
-                const int pos = XLEAD + (py + 1) * XP + px;
-                *reinterpret_cast<uint4*>(Xb + pos * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-                // channel 12 = 1.0 (fp16 0x3C00): the centre tap's weight row 12 holds the folded-BN bias, so the GEMM adds it
-                *reinterpret_cast<uint4*>(Xb + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
+#pragma unroll
+                for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
+                    const int py = (t >> 5) + (NPROD / 32) * k;
+                    if (py >= 32 || (p.debug & 2)) break;
+                    uint32_t o[6];
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy) {
+                        const uint8_t* rowb = V + (2 * py + dy) * p.v_pitch;
+                        uint32_t rg[2], bx[2];
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx) {
+                            const uint2 pa = *reinterpret_cast<const uint2*>(rowb + xa[dx]), pb = *reinterpret_cast<const uint2*>(rowb + xb[dx]);
+                            const __half2 a0 = *reinterpret_cast<const __half2*>(&pa.x), a1 = *reinterpret_cast<const __half2*>(&pa.y);
+                            const __half2 b0 = *reinterpret_cast<const __half2*>(&pb.x), b1 = *reinterpret_cast<const __half2*>(&pb.y);
+                            const __half2 v0 = __hfma2(lx[dx], __hsub2(b0, a0), a0), v1 = __hfma2(lx[dx], __hsub2(b1, a1), a1);
+                            rg[dx] = *reinterpret_cast<const uint32_t*>(&v0);
+                            bx[dx] = *reinterpret_cast<const uint32_t*>(&v1);
+                        }
+                        o[dy * 3 + 0] = rg[0];                                       // (R0, G0)
+                        o[dy * 3 + 1] = __byte_perm(bx[0], rg[1], 0x5410u);          // (B0, R1)
+                        o[dy * 3 + 2] = __byte_perm(rg[1], bx[1], 0x5432u);          // (G1, B1)
+                    }
+                    const int pos = XLEAD + (py + 1) * XP + px;
+                    *reinterpret_cast<uint4*>(Xb + pos * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+                    // channel 12 = 1.0 (fp16 0x3C00): the centre tap's weight row 12 holds the folded-BN bias, so the GEMM adds it
+                    *reinterpret_cast<uint4*>(Xb + X_CHUNK + pos * 16) = make_uint4(o[4], o[5], 0x3C00u, 0u);
+                }
             }
             fence_proxy_async_smem();
 #ifdef CV_FE_PROFILE
@@ -229,24 +250,25 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================================================================
+        // ONE thread runs the whole role (elected once): its barrier waits, descriptor adds and UTCHMMAs form one instruction stream
+        // without a warp-wide wait + election + reconvergence per tile.  With 4 MMAs (~160 cycles of tensor-pipe work) per stem tile,
+        // that per-block overhead (~150 cycles) had kept the pipe half idle: the pipe queue does not run far ahead of the issuer.
         if (elect_one()) {
             mbar_arrive_expect_tx(wbar, W_BYTES);
             bulk_g2s(W, p.wimg, W_BYTES, wbar);
-        }
-        mbar_wait(wbar, 0);
-        constexpr uint32_t idesc_s = make_idesc_f16(128, 32), idesc_1 = make_idesc_bf16(128, 32);
-        const uint32_t x_lo = desc_lo(smem_u32(X), X_CHUNK), y_lo = desc_lo(smem_u32(Y), YH_CHUNK);
-        const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), 32 * 16);
-        constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
-        // stem tiles k = 2 s + h, k in [k0, k1), of the crop in X slot `xs`: output columns [8s, 8s+8), rows [16h, 16h+16)
-        auto issue_stem = [&](int k0, int k1, uint32_t it) {
-            const uint32_t xb_lo = x_lo + (it & xmask) * (X_ALLOC >> 4);
+            mbar_wait_spin(wbar, 0);
+            constexpr uint32_t idesc_s = make_idesc_f16(128, 32), idesc_1 = make_idesc_bf16(128, 32);
+            const uint32_t x_lo = desc_lo(smem_u32(X), X_CHUNK), y_lo = desc_lo(smem_u32(Y), YH_CHUNK);
+            const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), 32 * 16);
+            constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
+            // stem tiles k = 2 s + h, k in [k0, k1), of the crop in X slot it & xmask: output columns [8s, 8s+8), rows [16h, 16h+16)
+            auto issue_stem = [&](int k0, int k1, uint32_t it) {
+                const uint32_t xb_lo = x_lo + (it & xmask) * (X_ALLOC >> 4);
 #pragma unroll
-            for (int k = k0; k < k1; ++k) {
-                const int s = k >> 1, h = k & 1;
-                TWAIT(3, mbar_wait(d_empty + k, (it & 1u) ^ 1u));
-                tc_fence_after();
-                if (elect_one()) {
+                for (int k = k0; k < k1; ++k) {
+                    const int s = k >> 1, h = k & 1;
+                    if (!(p.debug & 16)) TWAIT(3, mbar_wait_spin(d_empty + k, (it & 1u) ^ 1u));
+                    tc_fence_after();
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
                         const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
@@ -255,16 +277,13 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     }
                     mma_commit(d_full + k);
                 }
-                __syncwarp();
-            }
-        };
-        // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image 2 itb + t
-        auto issue_b00 = [&](int t, uint32_t itb) {
-            const uint32_t buf = t;
-            TWAIT(0, mbar_wait(yh_full + buf, itb & 1u));
-            TWAIT(1, mbar_wait(e_empty + t, (itb & 1u) ^ 1u));
-            tc_fence_after();
-            if (elect_one()) {
+            };
+            // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image t
+            auto issue_b00 = [&](int t, uint32_t itb) {
+                const uint32_t buf = t;
+                if (!(p.debug & 16)) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
+                if (!(p.debug & 16)) TWAIT(1, mbar_wait_spin(e_empty + t, (itb & 1u) ^ 1u));
+                tc_fence_after();
                 const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
@@ -278,23 +297,21 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                                     w1_lo + (tap * 2 + ks) * 64, w_hi, idesc_1, (tap | ks) ? 1u : 0u);
                 }
                 mma_commit(e_full + t);
+            };
+            uint32_t it = 0;
+            for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+                if (!(p.debug & 32)) TWAIT(2, mbar_wait_spin(x_full + (it & xmask), (it >> xshift) & 1u));
+                // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
+                // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
+                issue_stem(0, 2, it);                                // slab 0
+                if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
+                issue_stem(2, 8, it);                                // slabs 1..3
+                mma_commit(x_empty + (it & xmask));                  // operand image free once the stem MMAs have read it
+                issue_b00(0, it);                                    // this crop, left tile
             }
-            __syncwarp();
-        };
-        uint32_t it = 0;
-        for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
-            TWAIT(2, mbar_wait(x_full + (it & xmask), (it >> xshift) & 1u));
-            tc_fence_after();
-            // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
-            // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
-            issue_stem(0, 2, it);                                // slab 0
-            if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
-            issue_stem(2, 8, it);                                // slabs 1..3
-            if (elect_one()) mma_commit(x_empty + (it & xmask));      // operand image free once the stem MMAs have read it
-            __syncwarp();
-            issue_b00(0, it);                                    // this crop, left tile
+            if (it > 0) issue_b00(1, it - 1);
         }
-        if (it > 0) issue_b00(1, it - 1);
+        __syncwarp();
     } else {
         // =========================== epilogue warps 0-7 ====================================================================
         const int g = warp >> 2, qd = warp & 3, i = qd * 32 + lane;
@@ -337,12 +354,17 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             for (int s = 0; s < 4; ++s) {
                 const int k = 2 * s + g;
                 uint8_t* yb = Y + (s >> 1) * YH_BYTES;
-                TWAIT(1, mbar_wait(d_full + k, it & 1u));
+                if (p.debug & 64) { if (lane == 0) mbar_wait_spin(d_full + k, it & 1u); __syncwarp(); } else TWAIT(1, mbar_wait(d_full + k, it & 1u));
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
-                tmem_ld16(trow + k * 32, r0);
-                tmem_ld16(trow + k * 32 + 16, r1);
-                tmem_ld_wait();
+                if (!(p.debug & 4)) {
+                    tmem_ld16(trow + k * 32, r0);
+                    tmem_ld16(trow + k * 32 + 16, r1);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) r0[q] = r1[q] = 0x3f800000u;
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(d_empty + k);         // accumulator drained into registers
@@ -360,7 +382,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 }
                 uint8_t* dst = yb + yoff + (s & 1) * 64;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
+                for (int c = 0; c < 4; ++c) if (!(p.debug & 8) || c == 0) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
                 if (s == 1 && xl == 7) {                         // x = 15 is also the halo column of the right half
                     uint8_t* yr = Y + YH_BYTES + halo_off;
 #pragma unroll
@@ -452,45 +474,51 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     }
     Front3Tables tab{};
     const CropTaps tp = make_taps(g);
-    int max_rows = 0, max_bytes = 0;
-    for (int r = 0; r < 8; ++r) {
+    int max_rows = 0, max_px = 0, max_bytes = 0;
+    for (int r = 0; r < 8; ++r) {                                   // the same taps serve square rows (vertical) and square columns (horizontal)
         int lo = g.H, hi = -1;
         for (int d = 0; d < 64; ++d) {
             lo = lo < tp.p0[r][d] ? lo : tp.p0[r][d];
             hi = hi > tp.p1[r][d] ? hi : tp.p1[r][d];
         }
-        if (hi - lo > 255) return CV_OK;
+        if (hi - lo > 250) return CV_OK;
         tab.row0[r] = lo;
         tab.nrows[r] = hi - lo + 1;
-        const int b0 = (lo * 3) & ~15, b1 = ((hi + 1) * 3 + 15) & ~15;     // row pitch H*3 is a multiple of 16 (H % 32 == 0): stays inside the row
-        tab.byte0[r] = b0;
-        tab.nbytes[r] = b1 - b0;
+        const int lo4 = lo & ~3;                                    // staged rows start on a 4-pixel (12-byte) group: word-aligned pixel groups
+        tab.byte0[r] = (lo4 * 3) & ~15;
+        tab.boff[r] = lo4 * 3 - tab.byte0[r];                       // 0, 4, 8 or 12
+        const int npx = (hi - lo4 + 1 + 3) & ~3;
+        max_bytes = max_bytes > tab.boff[r] + npx * 3 ? max_bytes : tab.boff[r] + npx * 3;
         for (int d = 0; d < 64; ++d) {
             const __half lh = __float2half_rn(g.lam[d]);
-            if (__half2float(lh) != g.lam[d]) return CV_OK;                 // the vertical weights must be exact in fp16 (they are k/128)
+            if (__half2float(lh) != g.lam[d]) return CV_OK;                 // the interpolation weights must be exact in fp16 (they are k/128)
             tab.vy[r][d] = (uint32_t)(tp.p0[r][d] - lo) | ((uint32_t)(tp.p1[r][d] - lo) << 8) | ((uint32_t)__half_as_ushort(lh) << 16);
-            tab.xo0[r][d] = (int16_t)(tp.p0[r][d] * 3 - b0);
-            tab.xo1[r][d] = (int16_t)(tp.p1[r][d] * 3 - b0);
+            tab.xh0[r][d] = (uint8_t)(tp.p0[r][d] - lo4);
+            tab.xh1[r][d] = (uint8_t)(tp.p1[r][d] - lo4);
+            tab.lamh[d] = __half_as_ushort(lh);
         }
         max_rows = max_rows > tab.nrows[r] ? max_rows : tab.nrows[r];
-        max_bytes = max_bytes > tab.nbytes[r] ? max_bytes : tab.nbytes[r];
+        max_px = max_px > npx ? max_px : npx;
     }
-    for (int d = 0; d < 64; ++d) tab.lam[d] = g.lam[d];
+    max_bytes = (max_bytes + 15) & ~15;                             // TMA box: inner extent a multiple of 16 bytes
     p.raw_pitch = max_bytes;
     p.raw_bytes = (max_rows * max_bytes + 127) & ~127;
-    p.hb_bytes = (max_rows * HB_PITCH + 127) & ~127;
+    p.n_groups = max_px / 4;
+    p.g_magic = (int)((0x100000000ull + p.n_groups - 1) / p.n_groups);      // item / n_groups = umulhi(item, g_magic) for item < 2^16
+    p.v_pitch = max_px * 8;
+    p.v_bytes = (64 * p.v_pitch + 127) & ~127;
     const int fixed = NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
     p.n_rawbuf = 2; p.n_xbuf = NXBUF;
-    auto total = [&]() { return p.n_xbuf * X_ALLOC + p.n_rawbuf * p.raw_bytes + p.hb_bytes + fixed; };
+    auto total = [&]() { return p.n_xbuf * X_ALLOC + p.n_rawbuf * p.raw_bytes + p.v_bytes + fixed; };
     if (total() > 227 * 1024) p.n_rawbuf = 1;                     // larger windows (512x512 boards): single window buffer,
     if (total() > 227 * 1024) p.n_xbuf = 1;                       // then a single stem operand image
     if (total() > 227 * 1024) return CV_OK;                       // window does not fit: not supported
     int off = p.n_xbuf * X_ALLOC;
     p.off_raw = off; off += p.n_rawbuf * p.raw_bytes;
-    p.off_hb = off; off += p.hb_bytes;
+    off = (off + 127) & ~127; p.off_v = off; off += p.v_bytes;
     off = (off + 127) & ~127; p.off_y = off; off += NYBUF * YH_BYTES + 256;
     off = (off + 127) & ~127; p.off_w = off; off += W_BYTES;
-    p.off_tab = off; off += (int)sizeof(Front3Tables);
+    p.off_tab = off; off += ((int)sizeof(Front3Tables) + 15) & ~15;
     off = (off + 15) & ~15; p.off_bar = off; off += 256;
     p.smem_total = off;
     if (p.smem_total > 227 * 1024) return CV_OK;

@@ -8,7 +8,7 @@
 #include "umma.cuh"
 using namespace umma;
 
-struct MmaCase { int N, a_shift_bytes, lbo, sbo, n_acc, n_mma, a_stride; int lsu_warps = 0; int commit_every = 0; int use_elect = 0; };
+struct MmaCase { int N, a_shift_bytes, lbo, sbo, n_acc, n_mma, a_stride; int lsu_warps = 0; int commit_every = 0; int use_elect = 0; int alt = 0; int fence_every = 0; int wait_every = 0; };
 
 template <int COMMIT_EVERY, bool ELECT>
 __global__ void __launch_bounds__(544, 1) mma_bench(MmaCase c, long long* out) {
@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(544, 1) mma_bench(MmaCase c, long long* out) {
     const uint32_t tm = slot;
     if (threadIdx.x < 32 && (ELECT ? elect_one() : threadIdx.x == 0)) {
         const uint32_t a0 = smem_u32(smem) + 1024 + c.a_shift_bytes, b0 = smem_u32(smem) + 160 * 1024;
-        const uint32_t idesc = make_idesc_bf16(128, c.N);
+        const uint32_t idesc = make_idesc_bf16(128, c.N), idesc_h = c.alt ? make_idesc_f16(128, c.N) : idesc;
         // descriptors and accumulator addresses precomputed: the issue loop is one UTCHMMA + nothing else per instruction
         uint64_t ad[8], bd = make_smem_desc(b0, c.N * 16, 128);
         uint32_t dc[8];
@@ -36,7 +36,9 @@ __global__ void __launch_bounds__(544, 1) mma_bench(MmaCase c, long long* out) {
             for (int i = 0; i < c.n_mma; i += 8) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    mma_bf16_ss(dc[j], ad[j], bd, idesc, (COMMIT_EVERY && (j & 3) == 0) ? 0u : 1u);
+                    if (c.fence_every && (j & 3) == 0) tc_fence_after();
+                    if (c.wait_every && (j & 3) == 0) { (void)mbar_try_wait(&bar2, 1u); }      // one (satisfied) mbarrier poll per tile, like a real consumer wait
+                    mma_bf16_ss(dc[j], ad[j], bd, (j & 4) ? idesc_h : idesc, (COMMIT_EVERY && (j & 3) == 0) ? 0u : 1u);     // alt: kind flips every 4 MMAs
                     if (COMMIT_EVERY && (j & 3) == 3) mma_commit(&bar2);       // a barrier nobody waits on: cost of the commit itself
                 }
             }
@@ -142,11 +144,9 @@ int main() {
     cudaFuncSetAttribute(mma_bench<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     cudaFuncSetAttribute(mma_bench<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const MmaCase cases[] = {
-        // N, shift, lbo, sbo, n_acc, n_mma, a_stride, lsu_warps, commit_every, use_elect
-        {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 0, 1}, {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1},
-        {32, 0, 2048, 128, 4, 64, 2048, 8, 4, 1}, {64, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {96, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {128, 0, 2048, 128, 2, 64, 2048, 0, 4, 1},
-        {192, 0, 2048, 128, 2, 64, 2048, 0, 4, 1}, {256, 0, 2048, 128, 1, 64, 2048, 0, 4, 1}, {16, 0, 2048, 128, 4, 64, 2048, 0, 4, 1}, {48, 0, 2048, 128, 4, 64, 2048, 0, 4, 1},
-        {32, 16, 17552, 528, 4, 64, 2048, 16, 4, 1},
+        // N, shift, lbo, sbo, n_acc, n_mma, a_stride, lsu_warps, commit_every, use_elect, alt, fence_every, wait_every
+        {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1, 0, 0, 0}, {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1, 0, 1, 0},
+        {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1, 0, 0, 1}, {32, 0, 2048, 128, 4, 64, 2048, 0, 4, 1, 0, 1, 1},
     };
     for (const MmaCase& c : cases) {
         if (!c.use_elect) mma_bench<0, false><<<1, 32 + 32 * c.lsu_warps, 200 * 1024>>>(c, d);
@@ -155,8 +155,8 @@ int main() {
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("mma N=%d: %s\n", c.N, cudaGetErrorString(e)); return 1; }
         cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d sbo=%3d n_acc=%d a_stride=%4d lsu_warps=%2d commit_every=%d elect=%d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.sbo, c.n_acc,
-               c.a_stride, c.lsu_warps, c.commit_every, c.use_elect, (double)h[0] / c.n_mma, (double)h[1] / c.n_mma);
+        printf("mma M=128 N=%3d K=16 a_shift=%2d lbo=%5d sbo=%3d n_acc=%d a_stride=%4d lsu_warps=%2d commit_every=%d elect=%d alt=%d fence=%d wait=%d: issue %5.1f cyc/mma, complete %6.1f cyc/mma\n", c.N, c.a_shift_bytes, c.lbo, c.sbo, c.n_acc,
+               c.a_stride, c.lsu_warps, c.commit_every, c.use_elect, c.alt, c.fence_every, c.wait_every, (double)h[0] / c.n_mma, (double)h[1] / c.n_mma);
     }
     cudaFuncSetAttribute(mma_multi_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     for (int N : {32, 64}) for (int ni : {1, 2, 4}) {
