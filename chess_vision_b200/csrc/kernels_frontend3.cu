@@ -68,11 +68,14 @@ struct Front3Params {
     int raw_pitch, raw_bytes, v_pitch, v_bytes, n_groups, g_magic, n_rawbuf, n_xbuf, box_bytes;
     int off_raw, off_v, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
-    int debug;
+    int debug;                        // experiment builds (CV_FE3_DEBUG): 1 / 2 skip the resize passes, 4 / 8 skip epilogue TMEM loads / stores, 16 / 128 / 1024 /
+                                      // 2048 skip MMA-thread waits, 32 skip the x_full wait, 64 spin in the epilogue, 256 wait-cycle report, 512 event trace
 };
 
 // Timing experiments (-DCV_FE_PROFILE, CV_FE3_DEBUG & 256): cycles the lead lane of each role spends in each barrier wait.
 #ifdef CV_FE_PROFILE
+__device__ uint2 g_fe3_trace[4 * 1024];            // CV_FE3_DEBUG & 512: event trace (tag, clock) of CTA 0, crops 8..15: one lane per role
+#define TRACE(tag) do { if (trace_on && tr_n < 1024) { g_fe3_trace[tr_role * 1024 + tr_n] = make_uint2((uint32_t)(tag), (uint32_t)clock64()); ++tr_n; } } while (0)
 __device__ unsigned long long g_fe3_prof[4 * 16];
 #define TWAIT(k, call)                                                   \
     do {                                                                 \
@@ -82,6 +85,7 @@ __device__ unsigned long long g_fe3_prof[4 * 16];
     } while (0)
 #else
 #define TWAIT(k, call) call
+#define TRACE(tag)
 #endif
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -110,7 +114,8 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         mbar_init(wbar, 1);
         for (int i = 0; i < NYBUF; ++i) mbar_init(yh_full + i, 8);
         for (int i = 0; i < 2; ++i) { mbar_init(e_full + i, 1); mbar_init(e_empty + i, 4); }
-        for (int i = 0; i < 8; ++i) { mbar_init(d_full + i, 1); mbar_init(d_empty + i, 4); }
+        for (int i = 0; i < 8; ++i) mbar_init(d_full + i, 1);
+        mbar_init(d_empty, 8);                                   // one arrival per epilogue warp and crop: all its stem accumulators are drained
         fence_barrier_init();
     }
     if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -125,6 +130,12 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_role0 = clock64();
+    const int tr_role = warp == 0 ? 0 : warp == 4 ? 1 : warp == pw ? 2 : 3;
+    bool trace_on = false;
+    int tr_n = 0;
+#define TRACE_WINDOW(it_) trace_on = (p.debug & 512) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP) && (it_) >= 8 && (it_) < 16
+#else
+#define TRACE_WINDOW(it_)
 #endif
 
     if (warp >= 8 && warp < MMA_WARP) {
@@ -155,7 +166,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             const int rslot = it & rawmask;
             const uint8_t* raw = RAW + rslot * p.raw_bytes;
             if (warp == 8 && p.n_rawbuf == 2 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // prefetch
+            TRACE_WINDOW(it);
             TWAIT(0, mbar_wait(raw_full + rslot, (it / p.n_rawbuf) & 1u));
+            TRACE(0xB00);
             // ---- vertical pass first, on the raw bytes: item = (output row y, group of 4 window pixels = 12 bytes = 3 aligned words).
             //      Bytes become fp16 pairs by PRMT (0x6400 | b = 1024 + b exactly), the lerp u0 + ly (u1 - u0) and the normalisation
             //      a u + b run in half2 arithmetic; the 4 pixels are stored as [R G B -] (8 bytes each): V[y][pixel].
@@ -193,11 +206,13 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #ifdef CV_FE_PROFILE
             if (prof_on) pacc[4] += clock64() - t_h0;
 #endif
+            TRACE(0xB10);
             TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // V complete, RAW slot consumed
             if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
             const int xslot = it & xmask;
             uint8_t* Xb = X + xslot * X_ALLOC;
             TWAIT(1, mbar_wait(x_empty + xslot, ((it >> xshift) & 1u) ^ 1u));                   // stem MMAs of the crop before last have read this image
+            TRACE(0xB20);
 #ifdef CV_FE_PROFILE
             const long long t_v0 = clock64();
 #endif
@@ -247,6 +262,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             TWAIT(3, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // operand image complete; HB free again
             if (t == 0) mbar_arrive(x_full + xslot);
+            TRACE(0xB30);
         }
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================================================================
@@ -267,8 +283,6 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #pragma unroll
                 for (int k = k0; k < k1; ++k) {
                     const int s = k >> 1, h = k & 1;
-                    if (!(p.debug & 16)) TWAIT(3, mbar_wait_spin(d_empty + k, (it & 1u) ^ 1u));
-                    tc_fence_after();
 #pragma unroll
                     for (int tap = 0; tap < 4; ++tap) {
                         const int Dy = (tap >> 1) - 1, Dx = (tap & 1) - 1;
@@ -276,13 +290,16 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                                     idesc_s, tap > 0 ? 1u : 0u);
                     }
                     mma_commit(d_full + k);
+                    TRACE(0x200 + k);
                 }
             };
             // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image t
             auto issue_b00 = [&](int t, uint32_t itb) {
                 const uint32_t buf = t;
-                if (!(p.debug & 16)) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
-                if (!(p.debug & 16)) TWAIT(1, mbar_wait_spin(e_empty + t, (itb & 1u) ^ 1u));
+                if (!(p.debug & (16 | 1024))) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
+                TRACE(0x300 + t);
+                if (!(p.debug & (16 | 2048))) TWAIT(1, mbar_wait_spin(e_empty + t, (itb & 1u) ^ 1u));
+                TRACE(0x310 + t);
                 tc_fence_after();
                 const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
 #pragma unroll
@@ -297,10 +314,17 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                                     w1_lo + (tap * 2 + ks) * 64, w_hi, idesc_1, (tap | ks) ? 1u : 0u);
                 }
                 mma_commit(e_full + t);
+                TRACE(0x400 + t);
             };
             uint32_t it = 0;
             for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+                TRACE_WINDOW(it);
                 if (!(p.debug & 32)) TWAIT(2, mbar_wait_spin(x_full + (it & xmask), (it >> xshift) & 1u));
+                TRACE(0x500);
+                // one wait per crop for the eight stem accumulators (each wait costs the issuing thread ~100+ cycles of exposed latency
+                // even when it is satisfied: thirteen of them per crop had kept the tensor pipe at half rate)
+                if (!(p.debug & (16 | 128))) TWAIT(3, mbar_wait_spin(d_empty, (it & 1u) ^ 1u));
+                tc_fence_after();
                 // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
                 // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
                 issue_stem(0, 2, it);                                // slab 0
@@ -325,6 +349,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         const int halo_off = ((y & 1) * 2 + 1) * YH_PLANE + (YLEAD + ((y >> 1) + 1) * YHP) * 16;                        // column 0 of the odd-x plane
         auto epilogue_b00 = [&](int n, uint32_t itb) {           // blocks.0.0 tile g of crop n -> global T8 tile rows
             TWAIT(0, mbar_wait(e_full + g, itb & 1u));
+            TRACE(0xA00 + g);
             tc_fence_after();
             uint32_t eh[16], el[16];                             // hi | lo halves of the 16 output channels
             tmem_ld16(trow + TM_B00 + g * 32, eh);
@@ -333,6 +358,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(e_empty + g);
+            TRACE(0xA10 + g);
             const int64_t m = (int64_t)n * 256 + (i >> 3) * 16 + 8 * g + (i & 7);
             uint4* dst = reinterpret_cast<uint4*>(p.y) + ((m >> 7) * 2) * 128 + (m & 127);
 #pragma unroll
@@ -354,7 +380,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             for (int s = 0; s < 4; ++s) {
                 const int k = 2 * s + g;
                 uint8_t* yb = Y + (s >> 1) * YH_BYTES;
+                if (s == 0) TRACE_WINDOW(it);
                 if (p.debug & 64) { if (lane == 0) mbar_wait_spin(d_full + k, it & 1u); __syncwarp(); } else TWAIT(1, mbar_wait(d_full + k, it & 1u));
+                TRACE(0x600 + k);
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
                 if (!(p.debug & 4)) {
@@ -367,7 +395,8 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(d_empty + k);         // accumulator drained into registers
+                if (s == 3 && lane == 0) mbar_arrive(d_empty);   // this warp's four stem accumulators of the crop are drained
+                TRACE(0x700 + k);
                 uint4 o[4];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
@@ -392,6 +421,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(yh_full + (s >> 1));
+                    TRACE(0x900 + (s >> 1));
                 }
                 // left tile of the previous crop: issued before this crop's stem tiles, so it has completed by now (the tensor
                 // pipe executes in order) -- no waiting, and the stem accumulators above were drained first
@@ -524,7 +554,9 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     if (p.smem_total > 227 * 1024) return CV_OK;
     p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
     p.n_crops = nb * 64; p.H = H;
+#if defined(CV_EXPERIMENTS) || defined(CV_FE_PROFILE)   // ablation / timing / trace switches (some change the results): experiment builds only
     { const char* d = getenv("CV_FE3_DEBUG"); p.debug = d ? atoi(d) : 0; }
+#endif
     // 2D tensor map over the boards of this launch: (nb*H rows) x (H*3 bytes as uint32 elements); box = the largest window
     if ((reinterpret_cast<uintptr_t>(boards_hwc) & 15) || (H * 3) % 16 || max_bytes / 4 > 256 || max_rows > 256) return CV_OK;
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -561,6 +593,17 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
         const char* names[4] = {"epilogue g0", "epilogue g1", "producer   ", "mma        "};
         const char* what[4][4] = {{"e_full", "d_full", "-", "-"}, {"e_full", "d_full", "-", "-"},
                                   {"raw_full", "x_empty", "bar A", "bar B"}, {"yh_full", "e_empty", "x_full", "d_empty"}};
+        if (p.debug & 512) {
+            static uint2 tr[4 * 1024];
+            CV_CUDA(cudaMemcpyFromSymbol(tr, g_fe3_trace, sizeof(tr)));
+            FILE* tf = fopen("gpurun_out/fe3_trace.txt", "w");
+            if (tf) {
+                for (int r = 0; r < 4; ++r)
+                    for (int i = 0; i < 1024 && tr[r * 1024 + i].x; ++i) fprintf(tf, "%d %x %u\n", r, tr[r * 1024 + i].x, tr[r * 1024 + i].y);
+                fclose(tf);
+            }
+        }
+        fprintf(stderr, "fe3 config: n_xbuf %d n_rawbuf %d smem %d raw_bytes %d v_bytes %d groups %d\n", p.n_xbuf, p.n_rawbuf, p.smem_total, p.raw_bytes, p.v_bytes, p.n_groups);
         for (int r = 0; r < 4; ++r) {
             fprintf(stderr, "fe3 %s total %7.0f cyc/crop | waits:", names[r], (double)h[r * 16 + 8] / per_cta);
             for (int k = 0; k < 4; ++k) fprintf(stderr, " %s %6.0f", what[r][k], (double)h[r * 16 + k] / per_cta);
