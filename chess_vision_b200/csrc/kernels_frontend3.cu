@@ -298,8 +298,6 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 const uint32_t buf = t;
                 if (!(p.debug & (16 | 1024))) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
                 TRACE(0x300 + t);
-                if (!(p.debug & (16 | 2048))) TWAIT(1, mbar_wait_spin(e_empty + t, (itb & 1u) ^ 1u));
-                TRACE(0x310 + t);
                 tc_fence_after();
                 const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
 #pragma unroll
@@ -357,8 +355,6 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(e_empty + g);
-            TRACE(0xA10 + g);
             const int64_t m = (int64_t)n * 256 + (i >> 3) * 16 + 8 * g + (i & 7);
             uint4* dst = reinterpret_cast<uint4*>(p.y) + ((m >> 7) * 2) * 128 + (m & 127);
 #pragma unroll
@@ -418,16 +414,17 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yr + c * YH_CHUNK) = o[c];
                 }
                 if (s & 1) {                                     // half image complete (this warp's share)
+                    // First drain this group's blocks.0.0 tile of the PREVIOUS crop (tile g was issued before the stem tiles just
+                    // processed, so it has completed: the tensor pipe executes in order).  The half-image barrier below then also
+                    // tells the MMA thread that accumulator g is free -- the next writer of accumulator g is exactly the
+                    // blocks.0.0 tile that waits for half image g of this crop -- so no separate "accumulator empty" wait exists.
+                    if (it > 0 && (s >> 1) == g) epilogue_b00(prev_n, it - 1);
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(yh_full + (s >> 1));
                     TRACE(0x900 + (s >> 1));
                 }
-                // left tile of the previous crop: issued before this crop's stem tiles, so it has completed by now (the tensor
-                // pipe executes in order) -- no waiting, and the stem accumulators above were drained first
-                if (s == 1 && g == 0 && it > 0) epilogue_b00(prev_n, it - 1);
             }
-            if (g == 1 && it > 0) epilogue_b00(prev_n, it - 1);  // right tile of the previous crop: issued in the middle of this iteration
             prev_n = n;
         }
         if (it > 0) epilogue_b00(prev_n, it - 1);
