@@ -73,6 +73,11 @@ struct Front3Params {
 };
 
 // Timing experiments (-DCV_FE_PROFILE, CV_FE3_DEBUG & 256): cycles the lead lane of each role spends in each barrier wait.
+#if defined(CV_EXPERIMENTS) || defined(CV_FE_PROFILE)
+#define FE_DBG(bits) ((p.debug & (bits)) != 0)        // ablation switches exist in experiment builds only
+#else
+#define FE_DBG(bits) (0)
+#endif
 #ifdef CV_FE_PROFILE
 __device__ uint2 g_fe3_trace[4 * 1024];            // CV_FE3_DEBUG & 512: event trace (tag, clock) of CTA 0, crops 8..15: one lane per role
 #define TRACE(tag) do { if (trace_on && tr_n < 1024) { g_fe3_trace[tr_role * 1024 + tr_n] = make_uint2((uint32_t)(tag), (uint32_t)clock64()); ++tr_n; } } while (0)
@@ -126,14 +131,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
     const int rawmask = p.n_rawbuf - 1, xmask = p.n_xbuf - 1, xshift = p.n_xbuf - 1;   // 1 or 2 buffers: slot = it & mask, use = it >> shift
 #ifdef CV_FE_PROFILE
-    const int pw = (p.debug & 512) ? 12 : 8;                     // which producer warp is sampled
-    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
+    const int pw = FE_DBG(512) ? 12 : 8;                     // which producer warp is sampled
+    const bool prof_on = FE_DBG(256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
     long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const long long t_role0 = clock64();
     const int tr_role = warp == 0 ? 0 : warp == 4 ? 1 : warp == pw ? 2 : 3;
     bool trace_on = false;
     int tr_n = 0;
-#define TRACE_WINDOW(it_) trace_on = (p.debug & 512) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP) && (it_) >= 8 && (it_) < 16
+#define TRACE_WINDOW(it_) trace_on = FE_DBG(512) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP) && (it_) >= 8 && (it_) < 16
 #else
 #define TRACE_WINDOW(it_)
 #endif
@@ -177,7 +182,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             {
                 const int n_items = 64 * p.n_groups, boff = tab.boff[c];
-                for (int item = t; item < ((p.debug & 1) ? 0 : n_items); item += NPROD) {
+                for (int item = t; item < (FE_DBG(1) ? 0 : n_items); item += NPROD) {
                     const int y = __umulhi((unsigned)item, (unsigned)p.g_magic), gq = item - y * p.n_groups;
                     const uint32_t vy = tab.vy[r][y];
                     const uint32_t* r0 = reinterpret_cast<const uint32_t*>(raw + (vy & 255u) * p.raw_pitch + boff + gq * 12);
@@ -231,7 +236,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
                     const int py = (t >> 5) + (NPROD / 32) * k;
-                    if (py >= 32 || (p.debug & 2)) break;
+                    if (py >= 32 || FE_DBG(2)) break;
                     uint32_t o[6];
 #pragma unroll
                     for (int dy = 0; dy < 2; ++dy) {
@@ -296,7 +301,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             // blocks.0.0 tile t (output columns [8t, 8t+8), all 16 rows) of the crop with iteration index itb: reads half image t
             auto issue_b00 = [&](int t, uint32_t itb) {
                 const uint32_t buf = t;
-                if (!(p.debug & (16 | 1024))) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
+                if (!FE_DBG(16 | 1024)) TWAIT(0, mbar_wait_spin(yh_full + buf, itb & 1u));
                 TRACE(0x300 + t);
                 tc_fence_after();
                 const uint32_t yb_lo = y_lo + buf * (YH_BYTES >> 4);
@@ -317,11 +322,11 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             uint32_t it = 0;
             for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
                 TRACE_WINDOW(it);
-                if (!(p.debug & 32)) TWAIT(2, mbar_wait_spin(x_full + (it & xmask), (it >> xshift) & 1u));
+                if (!FE_DBG(32)) TWAIT(2, mbar_wait_spin(x_full + (it & xmask), (it >> xshift) & 1u));
                 TRACE(0x500);
                 // one wait per crop for the eight stem accumulators (each wait costs the issuing thread ~100+ cycles of exposed latency
                 // even when it is satisfied: thirteen of them per crop had kept the tensor pipe at half rate)
-                if (!(p.debug & (16 | 128))) TWAIT(3, mbar_wait_spin(d_empty, (it & 1u) ^ 1u));
+                if (!FE_DBG(16 | 128)) TWAIT(3, mbar_wait_spin(d_empty, (it & 1u) ^ 1u));
                 tc_fence_after();
                 // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
                 // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
@@ -377,11 +382,11 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 const int k = 2 * s + g;
                 uint8_t* yb = Y + (s >> 1) * YH_BYTES;
                 if (s == 0) TRACE_WINDOW(it);
-                if (p.debug & 64) { if (lane == 0) mbar_wait_spin(d_full + k, it & 1u); __syncwarp(); } else TWAIT(1, mbar_wait(d_full + k, it & 1u));
+                if (FE_DBG(64)) { if (lane == 0) mbar_wait_spin(d_full + k, it & 1u); __syncwarp(); } else TWAIT(1, mbar_wait(d_full + k, it & 1u));
                 TRACE(0x600 + k);
                 tc_fence_after();
                 uint32_t r0[16], r1[16];
-                if (!(p.debug & 4)) {
+                if (!FE_DBG(4)) {
                     tmem_ld16(trow + k * 32, r0);
                     tmem_ld16(trow + k * 32 + 16, r1);
                     tmem_ld_wait();
@@ -407,7 +412,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 }
                 uint8_t* dst = yb + yoff + (s & 1) * 64;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) if (!(p.debug & 8) || c == 0) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
+                for (int c = 0; c < 4; ++c) if (!FE_DBG(8) || c == 0) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
                 if (s == 1 && xl == 7) {                         // x = 15 is also the halo column of the right half
                     uint8_t* yr = Y + YH_BYTES + halo_off;
 #pragma unroll
