@@ -26,17 +26,29 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
+def build(force=False, verbose=False, variant=None, extra=()):
+    """Compile every .cu under csrc/ into one shared library.  Returns the library path.
+    variant="prof", extra=["-DCV_FE_PROFILE"] builds libchessvision_b200_prof.so beside it (experiments; see CV_B200_LIB)."""
+    global LIB
+    if variant:
+        saved = LIB
+        LIB = os.path.join(HERE, f"libchessvision_b200_{variant}.so")
+        try:
+            return _build(True, verbose, os.path.join(HERE, "build_" + variant), list(extra))
+        finally:
+            LIB = saved
     if not force and not _stale():
         return LIB
+    return _build(force, verbose, os.path.join(HERE, "build"), [])
+
+
+def _build(force, verbose, build_dir, extra):
     objs = []
-    build_dir = os.path.join(HERE, "build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CV_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("CV_NVCC_EXTRA", "").split(), *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -58,4 +70,6 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=var[0] if var else None,
+                extra=[a for a in sys.argv[1:] if a.startswith("-D")]))

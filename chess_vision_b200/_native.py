@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libchessvision_b200.so")
+# CV_B200_LIB: an experiment build of the same library (tools/, -DCV_FE_PROFILE ...); never a fallback
+LIB_PATH = os.environ.get("CV_B200_LIB") or os.path.join(_HERE, "libchessvision_b200.so")
 
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 LAYOUT_HWC, LAYOUT_CHW = 0, 1

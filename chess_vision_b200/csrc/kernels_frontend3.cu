@@ -203,9 +203,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                             n[2 * w + hh] = *reinterpret_cast<const uint32_t*>(&v);
                         }
                     }
+                    // V is dense (offset = item * 32), so consecutive lanes own consecutive 32-byte slots: lanes 0-3 of a quarter warp store
+                    // their first 16 bytes while lanes 4-7 store their second (and vice versa) -> every STS.128 covers all 32 banks once
                     uint4* dst = reinterpret_cast<uint4*>(V + y * p.v_pitch + gq * 32);
-                    dst[0] = make_uint4(n[0], n[1] & 0xffffu, __byte_perm(n[1], n[2], 0x5432u), n[2] >> 16);
-                    dst[1] = make_uint4(n[3], n[4] & 0xffffu, __byte_perm(n[4], n[5], 0x5432u), n[5] >> 16);
+                    const uint4 h0 = make_uint4(n[0], n[1] & 0xffffu, __byte_perm(n[1], n[2], 0x5432u), n[2] >> 16);
+                    const uint4 h1 = make_uint4(n[3], n[4] & 0xffffu, __byte_perm(n[4], n[5], 0x5432u), n[5] >> 16);
+                    const bool sw = (t & 4) != 0;
+                    dst[sw ? 1 : 0] = sw ? h1 : h0;
+                    dst[sw ? 0 : 1] = sw ? h0 : h1;
                 }
             }
 #ifdef CV_FE_PROFILE
@@ -224,15 +229,18 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             // ---- horizontal pass (half2): s2d position (py, px) -> 12 fp16 channels (dy*6 + dx*3 + c) + the constant-one channel
             {
                 const int px = t & 31;                               // fixed per thread: its column taps are looked up once per crop
-                int xa[2], xb[2];
+                // the four taps of output columns 2 px, 2 px + 1 lie in three consecutive window pixels (checked at launch): three
+                // 8-byte loads per row instead of four, the taps are selected in registers
                 __half2 lx[2];
 #pragma unroll
                 for (int dx = 0; dx < 2; ++dx) {
-                    xa[dx] = tab.xh0[c][2 * px + dx] * 8;
-                    xb[dx] = tab.xh1[c][2 * px + dx] * 8;
                     const uint32_t l2 = tab.lamh[2 * px + dx] * 0x10001u;
                     lx[dx] = *reinterpret_cast<const __half2*>(&l2);
                 }
+                const int xbase = tab.xh0[c][2 * px], xlast = p.n_groups * 4 - 1;
+                const int x0 = xbase * 8, x1 = min(xbase + 1, xlast) * 8, x2 = min(xbase + 2, xlast) * 8;
+                const bool sb0 = tab.xh1[c][2 * px] != xbase, sa1 = tab.xh0[c][2 * px + 1] != xbase;
+                const int sb1 = tab.xh1[c][2 * px + 1] - xbase;
 #pragma unroll
                 for (int k = 0; k < (1024 + NPROD - 1) / NPROD; ++k) {
                     const int py = (t >> 5) + (NPROD / 32) * k;
@@ -242,9 +250,12 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     for (int dy = 0; dy < 2; ++dy) {
                         const uint8_t* rowb = V + (2 * py + dy) * p.v_pitch;
                         uint32_t rg[2], bx[2];
+                        const uint2 q0 = *reinterpret_cast<const uint2*>(rowb + x0), q1 = *reinterpret_cast<const uint2*>(rowb + x1),
+                                    q2 = *reinterpret_cast<const uint2*>(rowb + x2);
 #pragma unroll
                         for (int dx = 0; dx < 2; ++dx) {
-                            const uint2 pa = *reinterpret_cast<const uint2*>(rowb + xa[dx]), pb = *reinterpret_cast<const uint2*>(rowb + xb[dx]);
+                            const uint2 pa = dx == 0 ? q0 : (sa1 ? q1 : q0);
+                            const uint2 pb = dx == 0 ? (sb0 ? q1 : q0) : (sb1 == 2 ? q2 : sb1 == 1 ? q1 : q0);
                             const __half2 a0 = *reinterpret_cast<const __half2*>(&pa.x), a1 = *reinterpret_cast<const __half2*>(&pa.y);
                             const __half2 b0 = *reinterpret_cast<const __half2*>(&pb.x), b1 = *reinterpret_cast<const __half2*>(&pb.y);
                             const __half2 v0 = __hfma2(lx[dx], __hsub2(b0, a0), a0), v1 = __hfma2(lx[dx], __hsub2(b1, a1), a1);
@@ -328,11 +339,13 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 // even when it is satisfied: thirteen of them per crop had kept the tensor pipe at half rate)
                 if (!FE_DBG(16 | 128)) TWAIT(3, mbar_wait_spin(d_empty, (it & 1u) ^ 1u));
                 tc_fence_after();
-                // Order matters for the two half images (see the header): column 15 of this crop is written into the right half's halo
-                // by the epilogue of slab 1, which must not pass the previous crop's right tile -- so that tile goes before slab 1.
-                issue_stem(0, 2, it);                                // slab 0
+                // stem left half | previous crop's right tile | stem right half | this crop's left tile: each blocks.0.0 tile has a whole
+                // other tile + half a stem (~1.4 k cycles of tensor-pipe work) queued between the stem tiles it depends on and itself, which
+                // covers the epilogue's round trip.  The right half image (and its halo column, which the epilogue of slab 1 holds back in
+                // registers until its first right-half tile has completed) is only written after the previous crop's right tile has read it.
+                issue_stem(0, 4, it);                                // slabs 0, 1: left half image
                 if (it > 0) issue_b00(1, it - 1);                    // previous crop, right tile
-                issue_stem(2, 8, it);                                // slabs 1..3
+                issue_stem(4, 8, it);                                // slabs 2, 3: right half image
                 mma_commit(x_empty + (it & xmask));                  // operand image free once the stem MMAs have read it
                 issue_b00(0, it);                                    // this crop, left tile
             }
@@ -377,6 +390,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         uint32_t it = 0;
         int prev_n = -1;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+            uint4 halo[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 const int k = 2 * s + g;
@@ -413,10 +427,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 uint8_t* dst = yb + yoff + (s & 1) * 64;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) if (!FE_DBG(8) || c == 0) *reinterpret_cast<uint4*>(dst + c * YH_CHUNK) = o[c];
-                if (s == 1 && xl == 7) {                         // x = 15 is also the halo column of the right half
+                if (s == 1) {                                    // x = 15 is also the halo column of the right half: held back until the
+#pragma unroll                                                   // previous crop's right tile has read that image (see the MMA role)
+                    for (int c = 0; c < 4; ++c) halo[c] = o[c];
+                }
+                if (s == 2 && xl == 7) {                         // tile 4 + g has completed, so has every MMA issued before it
                     uint8_t* yr = Y + YH_BYTES + halo_off;
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yr + c * YH_CHUNK) = o[c];
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(yr + c * YH_CHUNK) = halo[c];
                 }
                 if (s & 1) {                                     // half image complete (this warp's share)
                     // First drain this group's blocks.0.0 tile of the PREVIOUS crop (tile g was issued before the stem tiles just
@@ -532,6 +550,11 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
         max_rows = max_rows > tab.nrows[r] ? max_rows : tab.nrows[r];
         max_px = max_px > npx ? max_px : npx;
     }
+    for (int r = 0; r < 8; ++r)                                     // horizontal pass: the taps of an output column pair within three pixels
+        for (int px = 0; px < 32; ++px) {
+            const int a0 = tab.xh0[r][2 * px], b0 = tab.xh1[r][2 * px], a1 = tab.xh0[r][2 * px + 1], b1 = tab.xh1[r][2 * px + 1];
+            if (b0 < a0 || b0 > a0 + 1 || a1 < a0 || a1 > a0 + 1 || b1 < a0 || b1 > a0 + 2) return CV_OK;
+        }
     max_bytes = (max_bytes + 15) & ~15;                             // TMA box: inner extent a multiple of 16 bytes
     p.raw_pitch = max_bytes;
     p.raw_bytes = (max_rows * max_bytes + 127) & ~127;
