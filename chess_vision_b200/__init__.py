@@ -10,7 +10,8 @@ from .dataset import (CLASS_TO_COLOR, CLASS_TO_TYPE, INDEX_TO_PIECE, NUM_CLASSES
                       fen_to_labels, labels_to_fen, parse_full_fen)
 from .models import ChessSquareCNN, build_model, build_square
 from .predict import fen_from_outputs, get_transform, predict
+from .preprocess import predict_images, resize_boards
 
-__all__ = ["build_model", "build_square", "ChessSquareCNN", "predict", "fen_from_outputs", "get_transform",
+__all__ = ["build_model", "build_square", "ChessSquareCNN", "predict", "fen_from_outputs", "get_transform", "resize_boards", "predict_images",
            "labels_to_fen", "fen_to_labels", "parse_full_fen", "PIECE_TO_INDEX", "INDEX_TO_PIECE",
            "NUM_CLASSES", "NUM_SQUARES", "CLASS_TO_TYPE", "CLASS_TO_COLOR"]

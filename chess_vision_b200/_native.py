@@ -75,6 +75,8 @@ def lib():
     _sig(L.cv_square_profile, i32, vp, i32)
     _sig(L.cv_square_profile_read, i32, vp, vp, vp)
     _sig(L.cv_eval_accumulate, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp)
+    _sig(L.cv_resize_bilinear_u8, i32, vp, i32, i32, i32, vp, i32, i32, vp)
+    _sig(L.cv_resize_coeffs_host, i32, i32, i32, C.POINTER(C.c_int), vp, vp, i32)
     if L.cv_abi_version() != 1:
         raise NativeError("libchessvision_b200.so ABI version mismatch")
     _lib = L

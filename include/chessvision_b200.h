@@ -195,6 +195,16 @@ int cv_eval_accumulate(const float* squares, const float* turn, const float* cas
                        const uint8_t* turn_labels, const uint8_t* castling_labels, const uint8_t* legal, int B,
                        int64_t* counters, uint8_t* per_sample, float* board_loss, void* stream);
 
+/* ---- board resize of the input transform (replaces transforms.Resize((S, S)) on a PIL image, dataset.py:177-181 fed at
+ * predict.py:19-20, i.e. Pillow's Image.resize((S, S), BILINEAR): src/libImaging/Resample.c) --------------------------------
+ * src (device, uint8 (B, in_h, in_w, 3), decoded RGB images of one size) -> dst (device, uint8 (B, out_h, out_w, 3)), BIT-EXACT
+ * with Pillow 12.2: antialiased triangle filter, 22-bit fixed-point weights, uint8 rounding between the horizontal and the vertical
+ * pass; equal sizes copy.  dst is what cv_square_forward_u8 / cv_square_predict_u8 take (CV_LAYOUT_HWC): ToTensor + Normalize are
+ * fused there.  cv_resize_coeffs_host (no GPU needed) returns the per-axis tables the kernel uses: *ksize taps per output index,
+ * bounds_host (out_size, 2) = (first tap, tap count), coeffs_host (out_size, *ksize) int32 weights; either buffer may be NULL. */
+int cv_resize_bilinear_u8(const uint8_t* src, int B, int in_h, int in_w, uint8_t* dst, int out_h, int out_w, void* stream);
+int cv_resize_coeffs_host(int in_size, int out_size, int* ksize, int32_t* bounds_host, int32_t* coeffs_host, int coeffs_capacity);
+
 #ifdef __cplusplus
 }
 #endif
