@@ -6,9 +6,9 @@
 // Pillow itself).  ToTensor + Normalize stay fused into the crop gather of the hot path (cv_square_forward_u8).
 //
 // One kernel, HBM-bound: a CTA produces TY output rows of one image.  It (1) runs the horizontal pass over the input rows those
-// output rows need -- source bytes read straight from global memory (neighbouring threads share their taps through L1) -- into a
-// shared-memory image of uint8 rows, (2) runs the vertical pass from shared memory, four output bytes per thread, one 32-bit
-// coalesced store each.  Algorithmic bytes per image: in_h*in_w*3 read + out_h*out_w*3 written.
+// output rows need -- source bytes read straight from global memory as aligned 32-bit words (neighbouring threads share their
+// taps through L1), weights in registers -- into a shared-memory image of uint8 rows, (2) runs the vertical pass from shared
+// memory, eight output bytes per thread, one 64-bit coalesced store each.  Algorithmic bytes per image: in_h*in_w*3 read + out_h*out_w*3 written.
 #include <cmath>
 #include <map>
 #include <mutex>
@@ -62,10 +62,15 @@ struct ResizeParams {
     uint8_t* dst;
     const int32_t *xb, *xk, *yb, *yk;      // device tables: bounds (out, 2), weights (out, ksize)
     int in_h, in_w, out_h, out_w, kx, ky, ty, pitch;
+    size_t src_bytes;                       // whole source batch: word loads never start beyond its last byte
 };
 
 __device__ __forceinline__ uint32_t clip8(int v) { return (uint32_t)min(max(v >> PRECISION_BITS, 0), 255); }
 
+// KMAX > 0: at most KMAX taps per output column (checked on the host): a thread keeps the weights of its column in registers and
+// reads the 3*KMAX source bytes of a row as aligned 32-bit words (realigned with funnel shifts), i.e. (3*KMAX+6)/4 loads instead of
+// 3*KMAX byte loads -- the horizontal pass is bound by load/store instructions.  KMAX = 0: any tap count, byte loads.
+template <int KMAX>
 __global__ void __launch_bounds__(RS_THREADS) resize_bilinear_kernel(const ResizeParams p) {
     extern __shared__ __align__(16) uint8_t hbuf[];              // horizontal-pass rows [r0, r1) of this tile: pitch bytes each
     const int b = blockIdx.y;
@@ -73,28 +78,89 @@ __global__ void __launch_bounds__(RS_THREADS) resize_bilinear_kernel(const Resiz
     const int r0 = p.yb[2 * y0], r1 = p.yb[2 * (y1 - 1)] + p.yb[2 * (y1 - 1) + 1];
     const int nrows = r1 - r0;
     const uint8_t* img = p.src + (size_t)b * p.in_h * p.in_w * 3;
-    // ---- horizontal pass (ImagingResampleHorizontal_8bpc): one output pixel (3 channels) per thread and step
-    for (int idx = threadIdx.x; idx < nrows * p.out_w; idx += RS_THREADS) {
-        const int row = idx / p.out_w, x = idx - row * p.out_w;
-        const int xmin = __ldg(p.xb + 2 * x), n = __ldg(p.xb + 2 * x + 1);
-        const uint8_t* s = img + ((size_t)(r0 + row) * p.in_w + xmin) * 3;
-        const int32_t* k = p.xk + x * p.kx;
-        int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
-        for (int t = 0; t < n; ++t) {
-            const int c = __ldg(k + t);
-            a0 += (int)__ldg(s + 3 * t) * c;
-            a1 += (int)__ldg(s + 3 * t + 1) * c;
-            a2 += (int)__ldg(s + 3 * t + 2) * c;
+    // ---- horizontal pass (ImagingResampleHorizontal_8bpc)
+    if (KMAX > 0) {
+        constexpr int NW = ((3 * (KMAX > 0 ? KMAX : 1) - 1) >> 2) + 2;       // aligned words covering 3*KMAX bytes that start at any byte of the first
+        const uintptr_t last_word = (reinterpret_cast<uintptr_t>(p.src) + p.src_bytes - 1) & ~(uintptr_t)3;
+        // lanes run over output columns, the rest of the block over rows (narrow outputs keep every warp busy)
+        const int xg = min(RS_THREADS, (p.out_w + 31) & ~31), rgroups = RS_THREADS / xg;
+        const int rg = threadIdx.x / xg;
+        for (int x = threadIdx.x - rg * xg; x < p.out_w && rg < rgroups; x += xg) {
+            const int xmin = __ldg(p.xb + 2 * x), n = __ldg(p.xb + 2 * x + 1);
+            int c[KMAX > 0 ? KMAX : 1];
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) c[t] = t < n ? __ldg(p.xk + x * p.kx + t) : 0;
+            const uint8_t* s = img + ((size_t)(r0 + rg) * p.in_w + xmin) * 3;
+            uint8_t* d = hbuf + rg * p.pitch + x * 3;
+            for (int row = rg; row < nrows; row += rgroups, s += (size_t)rgroups * p.in_w * 3, d += rgroups * p.pitch) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+                const uintptr_t wa = a & ~(uintptr_t)3;
+                const uint32_t sh = (uint32_t)(a & 3) * 8;
+                uint32_t w[NW];
+#pragma unroll
+                for (int i = 0; i < NW; ++i) w[i] = wa + 4 * i <= last_word ? __ldg(reinterpret_cast<const uint32_t*>(wa) + i) : 0u;
+#pragma unroll
+                for (int i = 0; i + 1 < NW; ++i) w[i] = __funnelshift_r(w[i], w[i + 1], sh);   // byte j of the taps = byte j of w[]
+                int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+#pragma unroll
+                for (int t = 0; t < KMAX; ++t) {
+                    a0 += (int)((w[(3 * t) >> 2] >> (8 * ((3 * t) & 3))) & 255u) * c[t];
+                    a1 += (int)((w[(3 * t + 1) >> 2] >> (8 * ((3 * t + 1) & 3))) & 255u) * c[t];
+                    a2 += (int)((w[(3 * t + 2) >> 2] >> (8 * ((3 * t + 2) & 3))) & 255u) * c[t];
+                }
+                d[0] = (uint8_t)clip8(a0);
+                d[1] = (uint8_t)clip8(a1);
+                d[2] = (uint8_t)clip8(a2);
+            }
         }
-        uint8_t* d = hbuf + row * p.pitch + x * 3;
-        d[0] = (uint8_t)clip8(a0);
-        d[1] = (uint8_t)clip8(a1);
-        d[2] = (uint8_t)clip8(a2);
+    } else {
+        for (int idx = threadIdx.x; idx < nrows * p.out_w; idx += RS_THREADS) {      // one output pixel (3 channels) per thread and step
+            const int row = idx / p.out_w, x = idx - row * p.out_w;
+            const int xmin = __ldg(p.xb + 2 * x), n = __ldg(p.xb + 2 * x + 1);
+            const uint8_t* s = img + ((size_t)(r0 + row) * p.in_w + xmin) * 3;
+            const int32_t* k = p.xk + x * p.kx;
+            int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
+            for (int t = 0; t < n; ++t) {
+                const int c = __ldg(k + t);
+                a0 += (int)__ldg(s + 3 * t) * c;
+                a1 += (int)__ldg(s + 3 * t + 1) * c;
+                a2 += (int)__ldg(s + 3 * t + 2) * c;
+            }
+            uint8_t* d = hbuf + row * p.pitch + x * 3;
+            d[0] = (uint8_t)clip8(a0);
+            d[1] = (uint8_t)clip8(a1);
+            d[2] = (uint8_t)clip8(a2);
+        }
     }
     __syncthreads();
-    // ---- vertical pass (ImagingResampleVertical_8bpc): four consecutive output bytes per thread and step
-    const int rowbytes = p.out_w * 3, groups = (rowbytes + 3) >> 2;
+    // ---- vertical pass (ImagingResampleVertical_8bpc): eight (aligned rows) or four consecutive output bytes per thread and step
+    const int rowbytes = p.out_w * 3;
     uint8_t* out = p.dst + (size_t)b * p.out_h * rowbytes;
+    if (((reinterpret_cast<uintptr_t>(out) | (uintptr_t)rowbytes) & 7) == 0) {
+        const int groups = rowbytes >> 3;
+        for (int idx = threadIdx.x; idx < (y1 - y0) * groups; idx += RS_THREADS) {
+            const int yy = idx / groups, g = idx - yy * groups, y = y0 + yy;
+            const int ymin = __ldg(p.yb + 2 * y) - r0, n = __ldg(p.yb + 2 * y + 1);
+            const int32_t* k = p.yk + y * p.ky;
+            int a[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = 1 << (PRECISION_BITS - 1);
+            for (int t = 0; t < n; ++t) {
+                const int c = __ldg(k + t);
+                const uint2 w = *reinterpret_cast<const uint2*>(hbuf + (ymin + t) * p.pitch + 8 * g);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[j] += (int)((w.x >> (8 * j)) & 255u) * c;
+                    a[4 + j] += (int)((w.y >> (8 * j)) & 255u) * c;
+                }
+            }
+            *reinterpret_cast<uint2*>(out + (size_t)y * rowbytes + 8 * g) =
+                make_uint2(clip8(a[0]) | (clip8(a[1]) << 8) | (clip8(a[2]) << 16) | (clip8(a[3]) << 24),
+                           clip8(a[4]) | (clip8(a[5]) << 8) | (clip8(a[6]) << 16) | (clip8(a[7]) << 24));
+        }
+        return;
+    }
+    const int groups = (rowbytes + 3) >> 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(out) | (uintptr_t)rowbytes) & 3) == 0;
     for (int idx = threadIdx.x; idx < (y1 - y0) * groups; idx += RS_THREADS) {
         const int yy = idx / groups, g = idx - yy * groups, y = y0 + yy;
@@ -183,7 +249,10 @@ extern "C" int cv_resize_bilinear_u8(const uint8_t* src, int B, int in_h, int in
     p.src = src; p.dst = dst;
     p.xb = tx->d_bounds; p.xk = tx->d_kk; p.yb = ty->d_bounds; p.yk = ty->d_kk;
     p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.kx = tx->ksize; p.ky = ty->ksize;
-    p.pitch = (out_w * 3 + 3) & ~3;
+    p.pitch = (out_w * 3 + 7) & ~7;
+    p.src_bytes = (size_t)B * in_h * in_w * 3;
+    int max_taps = 0;
+    for (int x = 0; x < out_w; ++x) max_taps = std::max(max_taps, tx->bounds[2 * x + 1]);
     // rows per tile: as many as keep the horizontal-pass image of the tile within 64 KB of shared memory (>= 3 CTAs per SM)
     auto span = [&](int tyrows) {
         int m = 0;
@@ -193,13 +262,23 @@ extern "C" int cv_resize_bilinear_u8(const uint8_t* src, int B, int in_h, int in
         }
         return m;
     };
-    int rows = 16;
+    int rows = 32;
     while (rows > 1 && (size_t)span(rows) * p.pitch > 64 * 1024) rows >>= 1;
     const size_t smem = (size_t)span(rows) * p.pitch;
     if (smem > 200 * 1024) { cv_set_error("cv_resize_bilinear_u8: one output row needs %zu bytes of shared memory", smem); return CV_ERR_ARG; }
     p.ty = rows;
-    CV_CUDA(cudaFuncSetAttribute(resize_bilinear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    resize_bilinear_kernel<<<dim3((out_h + rows - 1) / rows, B), RS_THREADS, smem, s>>>(p);
+    const dim3 grid((out_h + rows - 1) / rows, B);
+#define CV_RESIZE_LAUNCH(K)                                                                                              \
+    do {                                                                                                                 \
+        CV_CUDA(cudaFuncSetAttribute(resize_bilinear_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        resize_bilinear_kernel<K><<<grid, RS_THREADS, smem, s>>>(p);                                                     \
+    } while (0)
+    if (max_taps <= 3) CV_RESIZE_LAUNCH(3);             // enlarging (two taps, three at a clipped border)
+    else if (max_taps <= 4) CV_RESIZE_LAUNCH(4);        // shrinking by up to 1.5x or so (400 -> 256)
+    else if (max_taps <= 5) CV_RESIZE_LAUNCH(5);        // shrinking by up to 2x (512 -> 256)
+    else if (max_taps <= 9) CV_RESIZE_LAUNCH(9);        // up to 4x
+    else CV_RESIZE_LAUNCH(0);
+#undef CV_RESIZE_LAUNCH
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
