@@ -65,6 +65,10 @@ struct cv_square {
     cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
     static constexpr int kStages = 3;     // staging slots of the host path: the copy stream may run two chunks ahead of the compute stream
     cudaEvent_t ev_h2d[kStages] = {}, ev_done[kStages] = {};
+    static constexpr int kPieces = 4;     // a chunk is copied in up to kPieces pieces: the front end starts on a piece as soon as it has landed
+    cudaEvent_t ev_piece[kStages][kPieces] = {};
+    const cudaEvent_t* piece_ev = nullptr;  // set by the host path around one forward: piece i (piece_boards boards) is ready after piece_ev[i]
+    int piece_boards = 0, n_pieces = 0;
     void* stage[kStages] = {};
     uint8_t* stage_flip[kStages] = {};
     size_t stage_bytes = 0;
@@ -274,6 +278,12 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     // bf16: crop gather + conv_stem + blocks.0.0 fused in one tensor-core kernel (activations stay in smem)
     const bool fused_front = sizeof(T) == 2 && (h->impl & CV_IMPL_FRONTEND);
     bf16* front_out = fused_front ? reinterpret_cast<bf16*>(ws + p.off_small[h->out_buf[1]]) : nullptr;
+    // host path: the boards of this call arrive in pieces (one event each, cv_square_predict_host_u8).  Only the third-generation front
+    // end of a single-wave call follows them piece by piece; every other configuration waits for the whole chunk first.
+    const bool by_pieces = h->n_pieces > 1 && fused_front && x_u8 && layout != CV_LAYOUT_CHW && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok &&
+                           B <= p.wave && B <= MAX_CHUNK;
+    if (h->n_pieces > 0 && !by_pieces)
+        for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
     for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {                    // chunk: one global-head launch
         const int cb = std::min(MAX_CHUNK, B - c0);
         for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: activations stay L2-resident
@@ -286,11 +296,27 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                                        : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
                 const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
                 int done = 0;
+                // by_pieces: the front end -- whose work unit is one crop, so short launches cost little -- runs piece by piece behind
+                // the copies, the later stages on the whole wave
                 if (kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok) {
-                    rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset,
-                                          front_out, h->num_sms, &done, s);
-                    if (rc) return rc;
+                    if (by_pieces) {
+                        for (int i = 0, q0 = 0; i < h->n_pieces && q0 < nb; ++i, q0 += h->piece_boards) {
+                            const int qn = std::min(h->piece_boards, nb - q0);
+                            CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+                            rc = launch_frontend3(static_cast<const uint8_t*>(src) + (size_t)q0 * H * H * 3, qn, H, g, h->lut_host, h->fe3_wimg,
+                                                  h->blob + kLayers[1].b_offset, front_out + (size_t)q0 * 64 * 256 * 16, h->num_sms, &done, s);
+                            if (rc) return rc;
+                            if (!done) break;                          // configuration not supported: nothing was launched
+                            if (i > 0) ++h->launches;
+                        }
+                    } else {
+                        rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset,
+                                              front_out, h->num_sms, &done, s);
+                        if (rc) return rc;
+                    }
                 }
+                if (!done && by_pieces)                                 // not supported after all: the other front ends read the whole chunk
+                    for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
                 if (!done && kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
                     rc = launch_frontend2(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe2_wimg,
                                           h->blob + kLayers[0].b_offset, h->blob + kLayers[1].b_offset, front_out, h->num_sms, &done, s);
@@ -548,7 +574,7 @@ int cv_square_predict_u8(cv_square* h, const uint8_t* boards, int layout, const 
     return prof_mark(h, -1, static_cast<cudaStream_t>(stream));
 }
 
-// Host-buffer end-to-end: chunks of `chunk` boards are copied H2D on a copy stream into one of two staging
+// Host-buffer end-to-end: chunks of `chunk` boards are copied H2D on a copy stream, piece by piece, into one of three staging
 // buffers while the previous chunk computes; FEN records come back with one D2H at the end.
 int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layout, const uint8_t* flipped_host, int B,
                               int H, int precision, char* fen_host, uint8_t* fen_len_host) {
@@ -565,11 +591,15 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
         for (int i = 0; i < cv_square::kStages; ++i) {
             CV_CUDA(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
             CV_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+            for (int j = 0; j < cv_square::kPieces; ++j) CV_CUDA(cudaEventCreateWithFlags(&h->ev_piece[i][j], cudaEventDisableTiming));
         }
     }
     const size_t per_board = (size_t)H * H * 3;
-    int max_chunk = 512;
+    int max_chunk = 512, piece = 128;
     if (const char* e = getenv("CV_HOST_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);      // tuning experiments
+    if (const char* e = getenv("CV_HOST_PIECE")) piece = std::max(32, atoi(e));
+    bool ramp_head = false, shrink_tail = false, tail256 = false;      // measured (tools/gpu_host_trace.py): flat 512-board chunks are best
+    if (const char* e = getenv("CV_HOST_SCHED")) { const int v = atoi(e); ramp_head = v & 1; shrink_tail = v & 2; tail256 = v & 4; }
     const int chunk = std::min(B, max_chunk);
     if (h->stage_bytes < chunk * per_board) {
         for (int i = 0; i < cv_square::kStages; ++i) {
@@ -593,8 +623,10 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
         CV_CUDA(cudaMalloc(&h->dev_fen_len, (size_t)B));
         h->dev_fen_cap = B;
     }
-    // Chunk sizes 128, 128, 256, 512, ..., 512, 256, 128, 128: the first copy and the last compute are the parts nothing overlaps, so
-    // both are kept short (measured: 17.0 ms per 4096 boards against 17.7 ms without the shrinking tail; tools/gpu_host_trace.py)
+    // Chunks of 512 boards (one wave), each copied in four pieces with an event per piece: the front end of a chunk follows the copy
+    // piece by piece, so what is exposed is the first piece's copy and, after the last piece has landed, one front-end piece plus
+    // stages B-D of the last chunk (measured per 4096 boards: 16.0 ms; 16.6 ms with whole-chunk events and growing / shrinking
+    // chunk sizes, 17.7 ms with equal chunks and whole-chunk events).  CV_HOST_SCHED: bit 0 growing head, bit 1 / 2 shrinking tails.
     // CV_HOST_TRACE=1: per-chunk timeline (copy end, compute end, ms since the first copy was enqueued) on stderr
     const bool trace = getenv("CV_HOST_TRACE") != nullptr;
     std::vector<cudaEvent_t> tr_copy, tr_comp;
@@ -604,22 +636,35 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
     int slot = 0, it = 0;
     for (int b0 = 0, nb = 0; b0 < B; b0 += nb, slot = (slot + 1) % cv_square::kStages, ++it) {
         const int left = B - b0;
-        nb = it < 2 ? 128 : it == 2 ? 256 : max_chunk;
-        if (left <= 256) nb = std::min(nb, 128);
-        else if (left <= 512 + 256) nb = std::min(nb, 256);
+        nb = max_chunk;
+        if (ramp_head) nb = it < 2 ? 128 : it == 2 ? 256 : max_chunk;
+        if (shrink_tail) {
+            if (left <= 256) nb = std::min(nb, 128);
+            else if (left <= 512 + 256) nb = std::min(nb, 256);
+        } else if (tail256 && left <= 512 && left > 256) nb = std::min(nb, 256);
         nb = std::min(std::min(nb, chunk), left);
         if (it >= cv_square::kStages) CV_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_done[slot], 0));   // staging slot free again
-        CV_CUDA(cudaMemcpyAsync(h->stage[slot], boards_host + (size_t)b0 * per_board, nb * per_board,
-                                cudaMemcpyHostToDevice, h->copy_stream));
         if (flipped_host)
             CV_CUDA(cudaMemcpyAsync(h->stage_flip[slot], flipped_host + b0, nb, cudaMemcpyHostToDevice, h->copy_stream));
-        CV_CUDA(cudaEventRecord(h->ev_h2d[slot], h->copy_stream));
+        // the chunk goes over in pieces of `piece` boards, one event each: the forward below waits for them one by one
+        const int n_pieces = std::min((nb + piece - 1) / piece, (int)cv_square::kPieces);
+        const int per_piece = n_pieces == cv_square::kPieces ? (nb + n_pieces - 1) / n_pieces : piece;
+        for (int i = 0, q0 = 0; i < n_pieces; ++i, q0 += per_piece) {
+            const int qn = std::min(per_piece, nb - q0);
+            CV_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(h->stage[slot]) + (size_t)q0 * per_board, boards_host + (size_t)(b0 + q0) * per_board,
+                                    qn * per_board, cudaMemcpyHostToDevice, h->copy_stream));
+            CV_CUDA(cudaEventRecord(h->ev_piece[slot][i], h->copy_stream));
+        }
         if (trace) { cudaEvent_t e; CV_CUDA(cudaEventCreate(&e)); CV_CUDA(cudaEventRecord(e, h->copy_stream)); tr_copy.push_back(e); tr_nb.push_back(nb); }
-        CV_CUDA(cudaStreamWaitEvent(h->compute_stream, h->ev_h2d[slot], 0));
+        h->piece_ev = h->ev_piece[slot];
+        h->piece_boards = per_piece;
+        h->n_pieces = n_pieces;
         int rc = cv_square_predict_u8(h, static_cast<const uint8_t*>(h->stage[slot]), layout,
                                       flipped_host ? h->stage_flip[slot] : nullptr, nb, H, precision,
                                       h->dev_fen + (size_t)b0 * CV_FEN_STRIDE, h->dev_fen_len + b0, h->own_ws,
                                       h->own_ws_bytes, h->compute_stream);
+        h->n_pieces = 0;
+        h->piece_ev = nullptr;
         if (rc) return rc;
         CV_CUDA(cudaEventRecord(h->ev_done[slot], h->compute_stream));
         if (trace) { cudaEvent_t e; CV_CUDA(cudaEventCreate(&e)); CV_CUDA(cudaEventRecord(e, h->compute_stream)); tr_comp.push_back(e); }
