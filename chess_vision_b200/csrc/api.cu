@@ -25,6 +25,9 @@ namespace {
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
 constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512;   // fused stages: persistent kernels want many tiles per SM
+// all four fused stages: only the 8 / 4 / 1.5 KB per crop hand-offs live in the workspace, and every kernel boundary costs ~13 us of
+// drained SMs, so a wave is a whole chunk (measured per 4096 boards: 13.81 ms at 512, 13.64 at 1024, 13.55 at 2048, 13.45 at 4096)
+constexpr int DEFAULT_WAVE_ALL_FUSED = 4096;
 constexpr int MAX_CHUNK = 4096;      // boards whose pooled features are kept for one global-head launch
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
@@ -123,7 +126,8 @@ struct WavePlan {
 WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
     WavePlan p;
     const bool bf = precision != CV_PRECISION_FP32;
-    int def = !bf ? DEFAULT_WAVE_FP32 : (h->impl & CV_IMPL_TAIL) ? DEFAULT_WAVE_FUSED : DEFAULT_WAVE_BF16;
+    const int all_fused = CV_IMPL_FRONTEND | CV_IMPL_EARLY | CV_IMPL_MID | CV_IMPL_TAIL;
+    int def = !bf ? DEFAULT_WAVE_FP32 : (h->impl & all_fused) == all_fused ? DEFAULT_WAVE_ALL_FUSED : (h->impl & CV_IMPL_TAIL) ? DEFAULT_WAVE_FUSED : DEFAULT_WAVE_BF16;
     p.wave = h->wave > 0 ? h->wave : def;
     if (p.wave > max_boards) p.wave = std::max(max_boards, 1);
     p.es = bf ? 2 : 4;
