@@ -18,9 +18,9 @@
 //     "buffer empty" barriers are needed at all;
 //   * the issuing thread adds a constant to a precomputed descriptor word per MMA (its dependent-instruction latency is exposed).
 //
-// Warp roles (21 warps): 0-7 epilogue (group g = warp>>2 takes the stem tiles of image rows [16g, 16g+16) and blocks.0.0
-// tile g; TMEM lane quadrant = warp&3), 8-19 resize producers (warp 8 also issues the TMA tile copy of the next crop),
-// 20 MMA issuer (+ TMEM owner).
+// Warp roles (22 warps): 0-7 epilogue (group g = warp>>2 takes the stem tiles of image rows [16g, 16g+16) and blocks.0.0
+// tile g; TMEM lane quadrant = warp&3), 8-19 resize producers, 20 MMA issuer (+ TMEM owner), 21 issues the TMA tile copies of the
+// board windows (on a producer warp that issue cost the whole producer group ~1 k cycles per crop at its barrier).
 #include <cstdio>
 #include <cstdlib>
 #include <cuda.h>
@@ -47,7 +47,8 @@ constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) 
 constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
 constexpr int NPROD = 384;                                      // 12 resize producer warps (the resize is the longest per-crop job)
 constexpr int MMA_WARP = 8 + NPROD / 32;
-constexpr int NTHREADS = (MMA_WARP + 1) * 32;
+constexpr int TMA_WARP = MMA_WARP + 1;                         // stages the board windows: the tile copy's issue latency stays off the producers' chain
+constexpr int NTHREADS = (TMA_WARP + 1) * 32;
 constexpr int TM_B00 = 256;                                    // TMEM: stem tile k at column 32 k, blocks.0.0 tile t at 256 + 32 t
 
 struct Front3Tables {                 // per launch, copied to shared memory
@@ -103,9 +104,10 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     uint8_t* W = smem + p.off_w;
     const Front3Tables& tab = *reinterpret_cast<const Front3Tables*>(smem + p.off_tab);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-    uint64_t *raw_full = bars, *x_full = bars + 2, *x_empty = bars + 4, *wbar = bars + 6, *yh_full = bars + 7 /*2*/, *e_full = bars + 9 /*2*/,
+    uint64_t *raw_full = bars + 32 /*3*/, *x_full = bars + 2, *x_empty = bars + 4, *wbar = bars + 6, *yh_full = bars + 7 /*2*/, *e_full = bars + 9 /*2*/,
              *e_empty = bars + 11 /*2*/, *d_full = bars + 13 /*8*/, *d_empty = bars + 21 /*8*/;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+    uint64_t* raw_empty = bars + 35 /*3*/;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
@@ -114,7 +116,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     for (int i = threadIdx.x; i < (int)(sizeof(Front3Tables) / 4); i += NTHREADS)
         reinterpret_cast<uint32_t*>(smem + p.off_tab)[i] = reinterpret_cast<const uint32_t*>(&tab_param)[i];
     if (threadIdx.x == 0) {
-        mbar_init(raw_full, 1); mbar_init(raw_full + 1, 1);
+        for (int i = 0; i < 3; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, 1); }
         for (int i = 0; i < NXBUF; ++i) { mbar_init(x_full + i, 1); mbar_init(x_empty + i, 1); }
         mbar_init(wbar, 1);
         for (int i = 0; i < NYBUF; ++i) mbar_init(yh_full + i, 8);
@@ -129,7 +131,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int rawmask = p.n_rawbuf - 1, xmask = p.n_xbuf - 1, xshift = p.n_xbuf - 1;   // 1 or 2 buffers: slot = it & mask, use = it >> shift
+    const int xmask = p.n_xbuf - 1, xshift = p.n_xbuf - 1;   // 1 or 2 operand images: slot = it & mask, use = it >> shift
 #ifdef CV_FE_PROFILE
     const int pw = FE_DBG(512) ? 12 : 8;                     // which producer warp is sampled
     const bool prof_on = FE_DBG(256) && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == pw || warp == MMA_WARP);
@@ -150,29 +152,13 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         const __half2 na2[3] = {__floats2half2_rn(p.na[0], p.na[1]), __floats2half2_rn(p.na[2], p.na[0]), __floats2half2_rn(p.na[1], p.na[2])};
         const __half2 nb2[3] = {__floats2half2_rn(p.nb[0], p.nb[1]), __floats2half2_rn(p.nb[2], p.nb[0]), __floats2half2_rn(p.nb[1], p.nb[2])};
         const __half2 k1024 = __floats2half2_rn(1024.f, 1024.f);
-        // stage the board window of crop `nn` (iteration index iti) into RAW slot iti & rawmask: ONE 2D TMA tile copy (rows x bytes box
-        // of the (B*H rows, H*3 bytes) board tensor at the clamped window origin; what lies beyond the window is never read), issued by
-        // one lane of warp 8.  The slot is free: its previous user is the horizontal pass of an earlier crop, which ended at a
-        // producer barrier.
-        auto stage_window = [&](int nn, uint32_t iti) {
-            if (lane != 0) return;
-            const int slot = iti & rawmask;
-            const int b = nn >> 6, rr = (nn >> 3) & 7, cc = nn & 7;
-            uint64_t* bar = raw_full + slot;
-            mbar_arrive_expect_tx(bar, (uint32_t)p.box_bytes);
-            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                         ::"r"(smem_u32(RAW + slot * p.raw_bytes)), "l"(&tmap), "r"(tab.byte0[cc] >> 2), "r"(b * p.H + tab.row0[rr]), "r"(smem_u32(bar))
-                         : "memory");
-        };
-        if (warp == 8 && blockIdx.x < p.n_crops) stage_window(blockIdx.x, 0);
-        uint32_t it = 0;
+        uint32_t it = 0, rphase = 0;
+        int rslot = 0;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
             const int r = (n >> 3) & 7, c = n & 7;
-            const int rslot = it & rawmask;
             const uint8_t* raw = RAW + rslot * p.raw_bytes;
-            if (warp == 8 && p.n_rawbuf == 2 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // prefetch
             TRACE_WINDOW(it);
-            TWAIT(0, mbar_wait(raw_full + rslot, (it / p.n_rawbuf) & 1u));
+            TWAIT(0, mbar_wait(raw_full + rslot, rphase));
             TRACE(0xB00);
             // ---- vertical pass first, on the raw bytes: item = (output row y, group of 4 window pixels = 12 bytes = 3 aligned words).
             //      Bytes become fp16 pairs by PRMT (0x6400 | b = 1024 + b exactly), the lerp u0 + ly (u1 - u0) and the normalisation
@@ -218,7 +204,8 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #endif
             TRACE(0xB10);
             TWAIT(2, asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory"));                       // V complete, RAW slot consumed
-            if (warp == 8 && p.n_rawbuf == 1 && n + (int)gridDim.x < p.n_crops) stage_window(n + gridDim.x, it + 1);   // single buffer: refill now
+            if (t == 0) mbar_arrive(raw_empty + rslot);                                             // the TMA warp may refill it
+            if (++rslot == p.n_rawbuf) { rslot = 0; rphase ^= 1u; }                                 // 1 to 3 window buffers, used round robin
             const int xslot = it & xmask;
             uint8_t* Xb = X + xslot * X_ALLOC;
             TWAIT(1, mbar_wait(x_empty + xslot, ((it >> xshift) & 1u) ^ 1u));                   // stem MMAs of the crop before last have read this image
@@ -280,6 +267,26 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             if (t == 0) mbar_arrive(x_full + xslot);
             TRACE(0xB30);
         }
+    } else if (warp == TMA_WARP) {
+        // =========================== board-window stager ==================================================================
+        // ONE 2D TMA tile copy per crop (rows x bytes box of the (B*H rows, H*3 bytes) board tensor at the clamped window origin; what
+        // lies beyond the window is never read) into the RAW slots round robin, as soon as the vertical pass of the slot's previous
+        // crop has ended: up to two crops ahead of the producers (a window is 48 short rows from as many DRAM pages: ~2-4 k cycles).
+        if (elect_one()) {
+            uint32_t it = 0, phase = 0;
+            int slot = 0;
+            for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
+                if ((int)it >= p.n_rawbuf) mbar_wait(raw_empty + slot, phase ^ 1u);      // the slot's previous use (one round ago) has been consumed
+                const int b = n >> 6, rr = (n >> 3) & 7, cc = n & 7;
+                uint64_t* bar = raw_full + slot;
+                mbar_arrive_expect_tx(bar, (uint32_t)p.box_bytes);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(RAW + slot * p.raw_bytes)), "l"(&tmap), "r"(tab.byte0[cc] >> 2), "r"(b * p.H + tab.row0[rr]), "r"(smem_u32(bar))
+                             : "memory");
+                if (++slot == p.n_rawbuf) { slot = 0; phase ^= 1u; }
+            }
+        }
+        __syncwarp();
     } else if (warp == MMA_WARP) {
         // =========================== MMA issuer ===========================================================================
         // ONE thread runs the whole role (elected once): its barrier waits, descriptor adds and UTCHMMAs form one instruction stream
@@ -562,9 +569,10 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     p.g_magic = (int)((0x100000000ull + p.n_groups - 1) / p.n_groups);      // item / n_groups = umulhi(item, g_magic) for item < 2^16
     p.v_pitch = max_px * 8;
     p.v_bytes = (64 * p.v_pitch + 127) & ~127;
-    const int fixed = NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 256 + 1024;
-    p.n_rawbuf = 2; p.n_xbuf = NXBUF;
+    const int fixed = NYBUF * YH_BYTES + 256 + W_BYTES + (int)sizeof(Front3Tables) + 384 + 1024;
+    p.n_rawbuf = 3; p.n_xbuf = NXBUF;
     auto total = [&]() { return p.n_xbuf * X_ALLOC + p.n_rawbuf * p.raw_bytes + p.v_bytes + fixed; };
+    if (total() > 227 * 1024) p.n_rawbuf = 2;
     if (total() > 227 * 1024) p.n_rawbuf = 1;                     // larger windows (512x512 boards): single window buffer,
     if (total() > 227 * 1024) p.n_xbuf = 1;                       // then a single stem operand image
     if (total() > 227 * 1024) return CV_OK;                       // window does not fit: not supported
@@ -574,7 +582,7 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     off = (off + 127) & ~127; p.off_y = off; off += NYBUF * YH_BYTES + 256;
     off = (off + 127) & ~127; p.off_w = off; off += W_BYTES;
     p.off_tab = off; off += ((int)sizeof(Front3Tables) + 15) & ~15;
-    off = (off + 15) & ~15; p.off_bar = off; off += 256;
+    off = (off + 15) & ~15; p.off_bar = off; off += 384;
     p.smem_total = off;
     if (p.smem_total > 227 * 1024) return CV_OK;
     p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
