@@ -736,8 +736,10 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         mbar_wait(wbar + sl, (wph >> sl) & 1u);
         wph ^= 1u << sl;
     };
-    auto begin_op = [&](int op) -> uint8_t* {
-        if (tid == 0 && op + 2 < NOPS) prefetch(op + 2);
+    // The bulk copy of op + 2 is issued by the MMA-issuing thread right after its tcgen05.commit (`pf` false here), so that the issue
+    // latency runs under the tensor-pipe round trip; ops without a GEMM issue it up front from thread 0.
+    auto begin_op = [&](int op, bool pf) -> uint8_t* {
+        if (pf && tid == 0 && op + 2 < NOPS) prefetch(op + 2);
         const int sl = slot_of(op);
         wait_slot(sl);
         return slot_ptr(sl);
@@ -794,13 +796,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         // ------------------------------ 4x4 phase: 2 M-tiles of 8 crops -----------------------------------------------------------
         int op = 3;
         {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
                 mma_commit(mbar);
+                if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) wait_mma();
             if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
@@ -810,13 +813,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 #pragma unroll 1
         for (int blk = 1; blk <= 4; ++blk) {
             {   // pw_exp 48 -> 96 (+ReLU)
-                uint8_t* wb = begin_op(op);
+                uint8_t* wb = begin_op(op, false);
                 sync_before_mma();
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
                     mma_commit(mbar);
+                    if (op + 2 < NOPS) prefetch(op + 2);
                 }
                 if (!(p.debug & 32)) wait_mma();
                 if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
@@ -824,20 +828,21 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 SC_MARK(8 + op); ++op;
             }
             {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
-                uint8_t* wb = begin_op(op);
+                uint8_t* wb = begin_op(op, true);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw3x3_p8_rt<true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
             {   // pw_proj 96 -> 48 accumulated onto the residual stream
-                uint8_t* wb = begin_op(op);
+                uint8_t* wb = begin_op(op, false);
                 sync_before_mma();
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m)
                         issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
                     mma_commit(mbar);
+                    if (op + 2 < NOPS) prefetch(op + 2);
                 }
                 if (!(p.debug & 32)) wait_mma();
                 if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
@@ -849,7 +854,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         uint8_t* E22a = R;
         uint8_t* E22b = R + 49152;               // second half runs into the X16 region (dead once the L22 MMAs have read it)
         {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             const float* b21 = reinterpret_cast<const float*>(wb);
             if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
             sync_before_mma();
@@ -858,6 +863,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
                 mma_commit(mbar);
+                if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) wait_mma();
             if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
@@ -865,13 +871,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             SC_MARK(8 + op); ++op;
         }
         {   // op 17: W22 columns 96..191
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
                 mma_commit(mbar);
+                if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) wait_mma();
             if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
@@ -880,7 +887,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         }
         const float* cum23;
         {   // op 18: W23 K rows 0..95 (+ cumulative bias)
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             cum23 = reinterpret_cast<const float*>(wb);
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
@@ -891,7 +898,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             SC_MARK(8 + op); ++op;
         }
         {   // op 19: W23 K rows 96..191, then the stage output
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 for (int m = 0; m < 2; ++m)
                     issue_gemm(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
