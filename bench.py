@@ -349,21 +349,21 @@ def run_native(args):
     alg_bytes, alg_flops = per_crop_bytes * crops_per_launch, per_crop_flops * crops_per_launch
     achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per crop of the fused kernels, from the `ncu --set full` capture of a 512-board
-    # launch at 256x256 (profiles/r01f_fused_kernels_ncu_summary.txt); scaled to this launch's crop count
-    ncu_traffic_per_crop = {49: (100.74e6 + 210.79e6) / 32768, 52: (268.49e6 + 106.28e6) / 32768, 51: (134.58e6 + 28.15e6) / 32768,
-                            50: (51.46e6 + 12.67e6) / 32768}
+    # launch at 256x256 (profiles/r01g_fused_kernels_ncu_summary.txt); scaled to this launch's crop count
+    ncu_traffic_per_crop = {49: (100.73e6 + 211.23e6) / 32768, 52: (268.49e6 + 107.89e6) / 32768, 51: (134.57e6 + 30.41e6) / 32768,
+                            50: (51.46e6 + 16.69e6) / 32768}
     traffic = ncu_traffic_per_crop[top] * crops_per_launch if (top in ncu_traffic_per_crop and H == 256 and prec == "bf16") else None
     roofline = {"bound": "hbm", "kernel": names[top], "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
-                "traffic_source": "ncu capture of one 512-board launch (profiles/r01f_fused_kernels_ncu_summary.txt), per crop x crops per launch",
+                "traffic_source": "ncu capture of one 512-board launch (profiles/r01g_fused_kernels_ncu_summary.txt), per crop x crops per launch",
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "launch_ms": per_launch_ms, "share_of_step": float(prof_ms[top] / prof_ms.sum()),
                 "tflops": alg_flops / (per_launch_ms / 1e3) / 1e12,
                 "tensor_frac_of_sustained": alg_flops / (per_launch_ms / 1e3) / 1e12 / peaks["bf16_tflops_sustained"],
                 "algorithmic_bytes_per_crop": per_crop_bytes, "algorithmic_flops_per_crop": per_crop_flops,
                 "note": "fused kernels keep their intermediates in shared/tensor memory: they are bound by the shared-memory pipes and "
-                        "instruction issue, neither HBM nor tensor peak (front end, ncu: LSU shared-memory wavefronts 65 % and tensor-core "
-                        "operand wavefronts 51 % of peak, issue slots 43 % busy, DRAM 7 %; DESIGN.md section 6)",
+                        "instruction issue, neither HBM nor tensor peak (front end, ncu: LSU shared-memory wavefronts 70 % and tensor-core "
+                        "operand wavefronts 57 % of peak, issue slots 46 % busy, DRAM 7 %; DESIGN.md section 6)",
                 "end_to_end_tensor_frac": value / world * 627.4e6 / (peaks["bf16_tflops_sustained"] * 1e12),
                 "end_to_end_hbm_frac": value / world * 196688.0 / (peaks["hbm_gbs"] * 1e9)}
     order = np.argsort(-prof_ms)[:8]

@@ -57,6 +57,19 @@ void make_coeffs(int in_size, int out_size, int* ksize_out, std::vector<int32_t>
     *ksize_out = ksize;
 }
 
+// What the kernels rely on to drop the clamp of clip8: weights >= 0 and row sums within 2^22 +- 2^12.
+bool coeffs_need_no_clamp(int out_size, int ksize, const std::vector<int32_t>& kk) {
+    for (int xx = 0; xx < out_size; ++xx) {
+        int64_t sum = 0;
+        for (int x = 0; x < ksize; ++x) {
+            if (kk[(size_t)xx * ksize + x] < 0) return false;
+            sum += kk[(size_t)xx * ksize + x];
+        }
+        if (sum > (1 << PRECISION_BITS) + 4096 || sum < (1 << PRECISION_BITS) - 4096) return false;
+    }
+    return true;
+}
+
 struct ResizeParams {
     const uint8_t* src;
     uint8_t* dst;
@@ -65,7 +78,10 @@ struct ResizeParams {
     size_t src_bytes;                       // whole source batch: word loads never start beyond its last byte
 };
 
-__device__ __forceinline__ uint32_t clip8(int v) { return (uint32_t)min(max(v >> PRECISION_BITS, 0), 255); }
+// Pillow's clip8().  The bilinear weights are non-negative and sum to 2^22 (+- rounding of <= ksize/2, checked when the table is
+// built), so 0 < acc < 256 * 2^22 always holds and the clamp of clip8 never acts: the shift alone is exact.
+__device__ __forceinline__ uint32_t clip8(int v) { return (uint32_t)v >> PRECISION_BITS; }
+__device__ __forceinline__ int byte_of(uint32_t w, int k) { return (int)__byte_perm(w, 0u, 0x4440u + (uint32_t)k); }   // one PRMT
 
 // KMAX > 0: at most KMAX taps per output column (checked on the host): a thread keeps the weights of its column in registers and
 // reads the 3*KMAX source bytes of a row as aligned 32-bit words (realigned with funnel shifts), i.e. (3*KMAX+6)/4 loads instead of
@@ -104,9 +120,9 @@ __global__ void __launch_bounds__(RS_THREADS) resize_bilinear_kernel(const Resiz
                 int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
 #pragma unroll
                 for (int t = 0; t < KMAX; ++t) {
-                    a0 += (int)((w[(3 * t) >> 2] >> (8 * ((3 * t) & 3))) & 255u) * c[t];
-                    a1 += (int)((w[(3 * t + 1) >> 2] >> (8 * ((3 * t + 1) & 3))) & 255u) * c[t];
-                    a2 += (int)((w[(3 * t + 2) >> 2] >> (8 * ((3 * t + 2) & 3))) & 255u) * c[t];
+                    a0 += byte_of(w[(3 * t) >> 2], (3 * t) & 3) * c[t];
+                    a1 += byte_of(w[(3 * t + 1) >> 2], (3 * t + 1) & 3) * c[t];
+                    a2 += byte_of(w[(3 * t + 2) >> 2], (3 * t + 2) & 3) * c[t];
                 }
                 d[0] = (uint8_t)clip8(a0);
                 d[1] = (uint8_t)clip8(a1);
@@ -150,8 +166,8 @@ __global__ void __launch_bounds__(RS_THREADS) resize_bilinear_kernel(const Resiz
                 const uint2 w = *reinterpret_cast<const uint2*>(hbuf + (ymin + t) * p.pitch + 8 * g);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    a[j] += (int)((w.x >> (8 * j)) & 255u) * c;
-                    a[4 + j] += (int)((w.y >> (8 * j)) & 255u) * c;
+                    a[j] += byte_of(w.x, j) * c;
+                    a[4 + j] += byte_of(w.y, j) * c;
                 }
             }
             *reinterpret_cast<uint2*>(out + (size_t)y * rowbytes + 8 * g) =
@@ -204,6 +220,11 @@ int get_table(int in_size, int out_size, Table** out) {
     if (it != g_tables.end()) { *out = it->second; return CV_OK; }
     Table* t = new Table();
     make_coeffs(in_size, out_size, &t->ksize, t->bounds, t->kk);
+    if (!coeffs_need_no_clamp(out_size, t->ksize, t->kk)) {
+        delete t;
+        cv_set_error("cv_resize_bilinear_u8: coefficient table %d -> %d outside the range the kernel assumes", in_size, out_size);
+        return CV_ERR_ARG;
+    }
     CV_CUDA(cudaMalloc(&t->d_bounds, t->bounds.size() * sizeof(int32_t)));
     CV_CUDA(cudaMalloc(&t->d_kk, t->kk.size() * sizeof(int32_t)));
     CV_CUDA(cudaMemcpy(t->d_bounds, t->bounds.data(), t->bounds.size() * sizeof(int32_t), cudaMemcpyHostToDevice));

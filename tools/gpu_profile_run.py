@@ -30,4 +30,9 @@ e0.record()
 for _ in range(iters):
     fen, fen_len = model.predict_fen_device(boards)
 e1.record(); torch.cuda.synchronize()
+if os.environ.get("CV_PROFILE_RESIZE", "1") != "0":          # the step before the path: one launch of the Pillow-exact resize kernel
+    from chess_vision_b200.preprocess import resize_boards
+    src = torch.randint(0, 256, (n, 400, 400, 3), dtype=torch.uint8, device="cuda")
+    resize_boards(src, 256)
+    torch.cuda.synchronize()
 print(f"{n} boards: {e0.elapsed_time(e1) / iters:.3f} ms/iter, {n * iters / e0.elapsed_time(e1) * 1e3:.0f} boards/s", model.decode_fen_records(fen[:1], fen_len[:1])[0])
