@@ -500,6 +500,24 @@ def test_host_pipeline_many_chunks(gpu_model):
     assert host == dev and len(host) == n
 
 
+def test_host_pipeline_pieces_and_fallbacks(gpu_model):
+    """The host path copies a chunk in pieces and launches the front end per piece.  Ragged sizes (last piece short, last chunk a
+    single piece), 256x256 boards, the CHW layout (front end v1: waits for the whole chunk), a custom wave smaller than a chunk and
+    fp32 mode must all give the strings of the device-resident call."""
+    for H, n in ((256, 700), (256, 130), (64, 513), (64, 1)):
+        u8 = torch.from_numpy(boards_u8(H, n)).pin_memory()
+        assert gpu_model.predict_fen(u8, precision="bf16") == gpu_model.predict_fen(u8.cuda(), precision="bf16")
+    u8 = torch.from_numpy(boards_u8(64, 600))
+    chw = u8.permute(0, 3, 1, 2).contiguous().pin_memory()
+    assert gpu_model.predict_fen(chw, layout="chw", precision="bf16") == gpu_model.predict_fen(chw.cuda(), layout="chw", precision="bf16")
+    assert gpu_model.predict_fen(u8.pin_memory(), precision="fp32") == gpu_model.predict_fen(u8.cuda(), precision="fp32")
+    gpu_model.set_wave(128)
+    try:
+        assert gpu_model.predict_fen(u8.pin_memory(), precision="bf16") == gpu_model.predict_fen(u8.cuda(), precision="bf16")
+    finally:
+        gpu_model.set_wave(0)
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_batch_properties_bf16(gpu_model):
     """BASELINE.json config 2 size (4096 boards, bf16): results must not depend on how the batch is split
