@@ -689,13 +689,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     uint64_t* wbar = bars;                          // one per weight slot
     uint64_t* inbar = bars + 3;
     uint64_t* mbar = bars + 4;
+    uint64_t* mbar2 = bars + 6;                     // 4x4 phase: second M-tile of a GEMM op (its own commit: see wait_mma2)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, cs = warp >> 2, row = quad * 32 + lane;
     const int mt = cs & 1, half = cs >> 1;          // body epilogues: M-tile and column half handled by this warp
 
     if (tid == 0) {
-        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(wbar + 2, 1); mbar_init(inbar, 1); mbar_init(mbar, 1);
+        mbar_init(wbar, 1); mbar_init(wbar + 1, 1); mbar_init(wbar + 2, 1); mbar_init(inbar, 1); mbar_init(mbar, 1); mbar_init(mbar2, 1);
         fence_barrier_init();
     }
     if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -704,7 +705,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-    uint32_t wph = 0, inph = 0, mph = 0;              // wph: phase bit per weight slot
+    uint32_t wph = 0, inph = 0, mph = 0, mph2 = 0;    // wph: phase bit per weight slot
 #ifdef CV_SC_PROFILE
     const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && tid == 0;
     long long pacc[40];
@@ -754,6 +755,15 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         mph ^= 1u;
         tc_fence_after();
     };
+    // 4x4 phase: the two M-tiles of a GEMM op are committed separately and ALL 16 warps run the epilogue of M-tile 0 (four column
+    // slices) while the tensor pipe still works on M-tile 1, then that of M-tile 1 (slices rotated by two, so that every warp gets the
+    // same number of 16-column groups over both): the epilogue starts one M-tile's worth of MMAs (~350 cycles) earlier per op.
+    auto wait_mma2 = [&]() {
+        mbar_wait(mbar2, mph2);
+        mph2 ^= 1u;
+        tc_fence_after();
+    };
+    const int cs2 = (cs + 2) & 3;
 
     if (tid == 0 && blockIdx.x < p.n_tiles) {
         load_head_weights();
@@ -800,13 +810,18 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
-                for (int m = 0; m < 2; ++m)
+                for (int m = 0; m < 2; ++m) {
                     issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
-                mma_commit(mbar);
+                    mma_commit(m ? mbar2 : mbar);
+                }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
-            if (!(p.debug & 32)) wait_mma();
-            if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+            if (!(p.debug & 32)) {
+                wait_mma();
+                epi_to_tile<false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4);
+                wait_mma2();
+                epi_to_tile<false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4);
+            }
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }
@@ -817,13 +832,18 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 sync_before_mma();
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
-                    for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < 2; ++m) {
                         issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
-                    mma_commit(mbar);
+                        mma_commit(m ? mbar2 : mbar);
+                    }
                     if (op + 2 < NOPS) prefetch(op + 2);
                 }
-                if (!(p.debug & 32)) wait_mma();
-                if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb), R + mt * 24576, 0, row, half, 2);
+                if (!(p.debug & 32)) {
+                    wait_mma();
+                    epi_to_tile<true>(trow, ACC, 96, reinterpret_cast<const float*>(wb), R, 0, row, cs, 4);
+                    wait_mma2();
+                    epi_to_tile<true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb), R + 24576, 0, row, cs2, 4);
+                }
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
@@ -839,13 +859,18 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 sync_before_mma();
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
-                    for (int m = 0; m < 2; ++m)
+                    for (int m = 0; m < 2; ++m) {
                         issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
-                    mma_commit(mbar);
+                        mma_commit(m ? mbar2 : mbar);
+                    }
                     if (op + 2 < NOPS) prefetch(op + 2);
                 }
-                if (!(p.debug & 32)) wait_mma();
-                if (!(p.debug & 32)) epi_to_tile<false>(trow, S_COL + 48 * mt, 48, reinterpret_cast<const float*>(wb), X16 + mt * 12288, 0, row, half, 2);
+                if (!(p.debug & 32)) {
+                    wait_mma();
+                    epi_to_tile<false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4);
+                    wait_mma2();
+                    epi_to_tile<false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4);
+                }
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
@@ -860,13 +885,18 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
-                for (int m = 0; m < 2; ++m)
+                for (int m = 0; m < 2; ++m) {
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
-                mma_commit(mbar);
+                    mma_commit(m ? mbar2 : mbar);
+                }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
-            if (!(p.debug & 32)) wait_mma();
-            if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 96 * mt, 96, reinterpret_cast<const float*>(wb + 1920), E22a + mt * 24576, 0, row, half, 2);
+            if (!(p.debug & 32)) {
+                wait_mma();
+                epi_to_tile<true>(trow, ACC, 96, reinterpret_cast<const float*>(wb + 1920), E22a, 0, row, cs, 4);
+                wait_mma2();
+                epi_to_tile<true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb + 1920), E22a + 24576, 0, row, cs2, 4);
+            }
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }
@@ -875,13 +905,18 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
-                for (int m = 0; m < 2; ++m)
+                for (int m = 0; m < 2; ++m) {
                     issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
-                mma_commit(mbar);
+                    mma_commit(m ? mbar2 : mbar);
+                }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
-            if (!(p.debug & 32)) wait_mma();
-            if (!(p.debug & 32)) epi_to_tile<true>(trow, ACC + 192 + 96 * mt, 96, reinterpret_cast<const float*>(wb), E22b + mt * 24576, 0, row, half, 2);
+            if (!(p.debug & 32)) {
+                wait_mma();
+                epi_to_tile<true>(trow, ACC + 192, 96, reinterpret_cast<const float*>(wb), E22b, 0, row, cs, 4);
+                wait_mma2();
+                epi_to_tile<true>(trow, ACC + 192 + 96, 96, reinterpret_cast<const float*>(wb), E22b + 24576, 0, row, cs2, 4);
+            }
             __syncthreads();
             SC_MARK(8 + op); ++op;
         }

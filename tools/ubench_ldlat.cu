@@ -75,6 +75,52 @@ __global__ void __launch_bounds__(160, 1) lat_bench(int mode, int burst, int rep
     if (threadIdx.x < 32) tmem_dealloc(tm, 512);
 }
 
+// Round trip of an op-synchronous GEMM step as the fused stages B-D run it: CTA barrier, one elected thread issues n_mma MMAs
+// (M=128, N, K=16) + commit, ALL warps wait on the mbarrier.  Reports cycles from the barrier to "awake" for thread 0 (issuer's warp)
+// and for the last warp.  mode 1: only warp 0 polls the mbarrier, the others wait at a second CTA barrier.
+__global__ void __launch_bounds__(512, 1) roundtrip_bench(int n_mma, int N, int mode, int reps, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t slot;
+    for (int i = threadIdx.x; i < 200 * 1024 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+    if (threadIdx.x < 32) tmem_alloc(&slot, 512);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tm = slot;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t a0 = smem_u32(smem) + 1024, b0 = smem_u32(smem) + 160 * 1024;
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint64_t bd = make_smem_desc(b0, N * 16, 128);
+    long long acc = 0, acc_issue = 0;
+    for (int r = 0; r < reps; ++r) {
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        const long long t0 = clock64();
+        long long t_issue = t0;
+        if (warp == 0 && elect_one()) {
+            tc_fence_after();
+            for (int j = 0; j < n_mma; ++j) mma_bf16_ss(tm + (j & 1) * N, make_smem_desc(a0 + (j & 7) * 2048, 2048, 128), bd, idesc, j > 1 ? 1u : 0u);
+            mma_commit(&bar);
+            t_issue = clock64();
+        }
+        if (mode == 0 || warp == 0) mbar_wait(&bar, r & 1);
+        if (mode == 1) __syncthreads();
+        tc_fence_after();
+        const long long t1 = clock64();
+        if (r > 0) { acc += t1 - t0; acc_issue += t_issue - t0; }
+    }
+    if (threadIdx.x == 0) { out[0] = acc / (reps - 1); }
+    if (threadIdx.x == 511) out[1] = acc / (reps - 1);
+    if (warp == 0 && acc_issue) out[2] = acc_issue / (reps - 1);
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x < 32) tmem_dealloc(tm, 512);
+}
+
 int main() {
     long long* d;
     cudaMalloc(&d, 64 * 8);
@@ -88,6 +134,16 @@ int main() {
         cudaMemcpy(h, d, 16 * 8, cudaMemcpyDeviceToHost);
         printf("%s waiter, %2d MMAs queued behind the tile: commit->wake %4lld cyc, fence+2xld16+wait %4lld cyc, 4xSTS.128+fence.proxy.async %4lld cyc (warp 1; warp 4: %lld / %lld / %lld)\n",
                (mode & 2) ? "spin    " : "try_wait", (mode & 1) ? burst : 0, h[0], h[1], h[2], h[12], h[13], h[14]);
+    }
+    cudaFuncSetAttribute(roundtrip_bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int mode : {0, 1}) for (int N : {48, 96}) for (int n : {0, 4, 8, 12, 24}) {
+        cudaMemset(d, 0, 64 * 8);
+        roundtrip_bench<<<1, 512, 200 * 1024>>>(n, N, mode, 32, d);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("roundtrip: %s\n", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h, d, 3 * 8, cudaMemcpyDeviceToHost);
+        printf("round trip, %s, %2d MMAs N=%2d: barrier -> awake %5lld cyc (thread 0), %5lld (last warp); issue + commit %4lld cyc\n",
+               mode ? "warp 0 polls + CTA barrier" : "all 16 warps poll         ", n, N, h[0], h[1], h[2]);
     }
     return 0;
 }
