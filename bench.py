@@ -228,6 +228,7 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device -- the B200 arm has no CPU fallback (use --impl reference)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    host_cpus = None if os.environ.get("CV_NO_BIND") else replicas.bind_host_to_gpu(local)   # pinned buffers next to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -401,7 +402,8 @@ def run_native(args):
                    "weights": "random-init (seed 0), BatchNorm statistics perturbed", "boards": "structured synthetic, seed 1"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 3),
                 "d2h_bytes_per_step": int(world * B * (_native.FEN_STRIDE + 1)), "ms_per_step": e2e_ms / args.steps,
-                "host_equals_device_fen": bool(same)},
+                "host_equals_device_fen": bool(same),
+                "host_cpus_bound_to_gpu": (len(host_cpus) if host_cpus else 0)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "weights_agree_across_ranks": bool(weights_agree), "sample_fen": fens_dev[0],
         "preprocess": pre,

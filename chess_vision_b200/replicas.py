@@ -77,3 +77,26 @@ def predict_stream(model, first_board: int, n_boards: int, size: int = 256, seed
             kept.append(rec)
         done += nb
     return total, done, (np.concatenate(kept) if keep and kept else None)
+
+
+def bind_host_to_gpu(device_index: int):
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (its NUMA node / PCIe root), so that the
+    pinned staging buffers allocated afterwards live in memory next to that GPU: with one process per GPU every host->device copy
+    then stays on its own socket.  Returns the CPU list, or None when NVML has no affinity information (VMs) or it covers every CPU."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) >= len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
