@@ -298,12 +298,15 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
     };
     // body op `op` (3..23) lives in slot op&1; entering it prefetches op+1 into the other slot (free: op-1 is complete)
-    auto begin_op = [&](int op) -> uint8_t* {
-        if (tid == 0 && op + 1 < NOPS) {
-            uint64_t* b = wbar + ((op + 1) & 1);
-            mbar_arrive_expect_tx(b, p.bytes[op + 1]);
-            bulk_g2s(WA + (((op + 1) & 1) ? W_SLOT1 : 0), p.wimg + p.off[op + 1], p.bytes[op + 1], b);
-        }
+    auto prefetch = [&](int nx) {                // any one thread: op nx -> slot nx & 1
+        uint64_t* b = wbar + (nx & 1);
+        mbar_arrive_expect_tx(b, p.bytes[nx]);
+        bulk_g2s(WA + ((nx & 1) ? W_SLOT1 : 0), p.wimg + p.off[nx], p.bytes[nx], b);
+    };
+    // pf false: the GEMM op issues the prefetch itself, behind its tcgen05.commit (the bulk copy's issue latency then runs under the
+    // tensor-pipe round trip instead of in front of the CTA barrier that precedes the MMA issue)
+    auto begin_op = [&](int op, bool pf = true) -> uint8_t* {
+        if (pf && tid == 0 && op + 1 < NOPS) prefetch(op + 1);
         if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
         return WA + ((op & 1) ? W_SLOT1 : 0);
     };
@@ -361,12 +364,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         uint8_t* X16 = EH;                       // block input as bf16 operand tile [8][128][8]
         int op = 3;
         {   // L27 blocks.3.0.pw_proj 288 -> 64: starts the residual stream in TMEM
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
                 mma_commit(mbar);
+                if (op + 1 < NOPS) prefetch(op + 1);
             }
             wait_mma();
             epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);
@@ -384,12 +388,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 ++op;
             }
             {   // pw_exp 64 -> cexp (+ReLU)
-                uint8_t* wb = begin_op(op);
+                uint8_t* wb = begin_op(op, false);
                 sync_before_mma();
                 if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     issue_gemm(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
                     mma_commit(mbar);
+                    if (op + 1 < NOPS) prefetch(op + 1);
                 }
                 wait_mma();
                 epi_to_tile<true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs);
@@ -404,12 +409,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 ++op;
             }
             {   // pw_proj cexp -> 64, accumulated onto the residual stream in TMEM (skip connection)
-                uint8_t* wb = begin_op(op);
+                uint8_t* wb = begin_op(op, false);
                 sync_before_mma();
                 if (warp == 0 && elect_one()) {
                     tc_fence_after();
                     issue_gemm(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
                     mma_commit(mbar);
+                    if (op + 1 < NOPS) prefetch(op + 1);
                 }
                 wait_mma();
                 epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);   // + cumulative bias
@@ -419,12 +425,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         }
         // ------------------------------ blocks.4.0 (64 -> 480, ReLU) + average pool + heads -------------------------------------
         for (int part = 0; part < 3; ++part, ++op) {          // three 160-column weight parts (ops 20..22)
-            uint8_t* wb = begin_op(op);
+            uint8_t* wb = begin_op(op, false);
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
                 mma_commit(mbar);
+                if (op + 1 < NOPS) prefetch(op + 1);
             }
             wait_mma();
         }
@@ -1298,6 +1305,8 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         if (tid == 0 && tile + (int)gridDim.x < p.n_tiles) load_in(tile + gridDim.x, s ^ 1);
         if (s) { mbar_wait(inbar + 1, inph1); inph1 ^= 1u; } else { mbar_wait(inbar, inph0); inph0 ^= 1u; }
         // ---- blocks.0.1: 1x1 16 -> 16 (+ReLU) on 512 rows = 4 M-tiles
+        //      (issuing this GEMM one stage early, behind the blocks.1.0 GEMM of the previous tile, was measured: no change -- with two
+        //      CTAs per SM its round trip already runs under the other CTA's work)
         if (warp == 0 && elect_one()) {
             tc_fence_after();
             for (int j = 0; j < 4; ++j) issue_gemm(smem_u32(in + j * 4096), 16, smem_u32(W + W2_OFF), 16, 0, 16, tmem + 16 * j, false, 2);
