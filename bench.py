@@ -216,6 +216,51 @@ def preprocess_leg(dev, peaks, n=1024, src=400, dst=256):
             "bit_exact_vs_oracle": exact, "cpu_baseline": cpu}
 
 
+def evaluate_leg(dev, peaks, n=4096):
+    """cv_eval_accumulate (on-device evaluation bookkeeping, the step after the hot path): CUDA-event time of one batch of n boards whose
+    logits and labels are resident in HBM, algorithmic bytes (logits + labels read, per-sample flags + loss written) against the measured HBM
+    peak, the counters checked against the CPU restatement, and that restatement (numpy port of evaluate.py:74-155) timed on the host."""
+    from chess_vision_b200 import _native
+    from oracle import eval_oracle
+    b = eval_oracle.synth_eval_batch(11, n)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt).contiguous()
+    sq, tu, ca = t(b["squares"], torch.float32), t(b["turn"].reshape(n), torch.float32), t(b["castling"], torch.float32)
+    lab, tl = t(b["sq_labels"], torch.uint8), t(b["turn_labels"].reshape(n) > 0.5, torch.uint8)
+    cl, lg = t(b["castling_labels"] > 0.5, torch.uint8), t(np.asarray(b["legal"]).reshape(n) > 0.5, torch.uint8)
+    per, loss = torch.empty((n, 4), dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.float32, device=dev)
+    counters = torch.zeros(eval_oracle.N_COUNTERS, dtype=torch.int64, device=dev)
+    p, L = _native.ptr, _native.lib()
+    run = lambda: _native.check(L.cv_eval_accumulate(p(sq), p(tu), p(ca), p(lab), p(tl), p(cl), p(lg), n, p(counters), p(per), p(loss),
+                                                     _native.stream_ptr(dev)))
+    run()
+    ref_c, _, _ = eval_oracle.evaluate_batch(b)
+    exact = bool(np.array_equal(counters.cpu().numpy(), ref_c))
+    for _ in range(3):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    per_board = 832 * 4 + 4 + 16 + 64 + 1 + 4 + 1 + 4 + 4
+    gbs = n * per_board / (ms / 1e3) / 1e9
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        eval_oracle.evaluate_batch(b)
+    cpu_v = reps * n / (time.perf_counter() - t0)
+    return {"kernel": "eval_accumulate", "boards": n, "ms": ms, "value": n / (ms / 1e3), "unit": "boards/s",
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "algorithmic_bytes_per_board": per_board,
+                         "note": "14 MB per launch: L2-resident and launch-latency-bound at this batch size"},
+            "counters_exact_vs_oracle": exact,
+            "cpu_baseline": {"value": cpu_v, "unit": "boards/s", "cores": 1, "kind": "port",
+                             "sample": f"{reps} x {n} boards, numpy restatement of evaluate.py:74-155"}}
+
+
 def run_native(args):
     import torch.distributed as dist
     import chess_vision_b200 as cv
@@ -388,9 +433,10 @@ def run_native(args):
             cpu["fen_mismatch_example"] = {"gpu_fp32": bad[0][0], "cpu": bad[0][1]}
 
     # ---- the step before the path: board resize kernel against its HBM roofline, Pillow beside it ----
-    pre = None
+    pre = post = None
     if world == 1 and not args.no_cpu_baseline:
         pre = preprocess_leg(dev, peaks)
+        post = evaluate_leg(dev, peaks)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -406,7 +452,7 @@ def run_native(args):
                 "host_cpus_bound_to_gpu": (len(host_cpus) if host_cpus else 0)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "weights_agree_across_ranks": bool(weights_agree), "sample_fen": fens_dev[0],
-        "preprocess": pre,
+        "preprocess": pre, "evaluate": post,
     }
     print(json.dumps(line))
     if world > 1:
