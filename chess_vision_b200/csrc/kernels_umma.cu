@@ -350,6 +350,76 @@ depthwise_t8_kernel(const bf16* __restrict__ x, const float* __restrict__ w, con
     reinterpret_cast<uint4*>(y)[idx] = o;
 }
 
+// Row-tiled version for the shapes of this trunk (square maps of side 8, 4 or 2): thread = one OUTPUT ROW of one crop and one
+// 8-channel chunk.  It loads each contributing input row once (HIN consecutive 16-byte chunks: rows of a crop are consecutive T8
+// rows) and each filter tap once, and feeds all HOUT outputs of the row from registers: HIN*K + 2*K*K loads for HOUT outputs
+// instead of HOUT * 3*K*K.  Same accumulation order per output as the kernel above (bias, then taps in (ky, kx) order): results are
+// bit-identical.  Consecutive threads own consecutive output rows of one chunk, so loads and stores stay coalesced.
+template <int K, int S, int HIN>
+__global__ void __launch_bounds__(128)
+depthwise_t8_rows_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                         bf16* __restrict__ y, int64_t total_rows, int C, int relu) {
+    constexpr int HOUT = HIN / S, PAD = ((S - 1) + (K - 1)) / 2, GROUPS = TILE_M / HOUT;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total_rows) return;
+    const int c8n = C >> 3;
+    const int g = (int)(t % GROUPS);
+    const int64_t tc = t / GROUPS;
+    const int c = (int)(tc % c8n);
+    const int64_t m_out = (tc / c8n) * TILE_M + (int64_t)g * HOUT;       // first output row-of-tile (pixel) this thread writes
+    const int64_t crop = m_out / (HOUT * HOUT);
+    const int oy = (int)(m_out - crop * (HOUT * HOUT)) / HOUT;
+    float acc[HOUT][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8) + 1);
+#pragma unroll
+        for (int ox = 0; ox < HOUT; ++ox) {
+            acc[ox][0] = b0.x; acc[ox][1] = b0.y; acc[ox][2] = b0.z; acc[ox][3] = b0.w;
+            acc[ox][4] = b1.x; acc[ox][5] = b1.y; acc[ox][6] = b1.z; acc[ox][7] = b1.w;
+        }
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x);
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - PAD + ky;
+        if (iy < 0 || iy >= HIN) continue;
+        const int64_t m_in = (crop * HIN + iy) * HIN;                      // HIN consecutive rows inside one tile
+        const uint4* row = src + ((size_t)(m_in >> 7) * c8n + c) * TILE_M + (m_in & 127);
+        uint4 px[HIN];
+#pragma unroll
+        for (int i = 0; i < HIN; ++i) px[i] = __ldg(row + i);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c * 8);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+#pragma unroll
+            for (int ox = 0; ox < HOUT; ++ox) {
+                const int ix = ox * S - PAD + kx;
+                if (ix < 0 || ix >= HIN) continue;
+                float v[8];
+                unpack_bf16x8(px[ix], v);
+                acc[ox][0] = fmaf(v[0], w0.x, acc[ox][0]); acc[ox][1] = fmaf(v[1], w0.y, acc[ox][1]);
+                acc[ox][2] = fmaf(v[2], w0.z, acc[ox][2]); acc[ox][3] = fmaf(v[3], w0.w, acc[ox][3]);
+                acc[ox][4] = fmaf(v[4], w1.x, acc[ox][4]); acc[ox][5] = fmaf(v[5], w1.y, acc[ox][5]);
+                acc[ox][6] = fmaf(v[6], w1.z, acc[ox][6]); acc[ox][7] = fmaf(v[7], w1.w, acc[ox][7]);
+            }
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(m_out >> 7) * c8n + c) * TILE_M + (m_out & 127);
+#pragma unroll
+    for (int ox = 0; ox < HOUT; ++ox) {
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[ox][i] = fmaxf(acc[ox][i], 0.f);
+        }
+        uint4 o;
+        o.x = pack_bf16x2(acc[ox][0], acc[ox][1]); o.y = pack_bf16x2(acc[ox][2], acc[ox][3]);
+        o.z = pack_bf16x2(acc[ox][4], acc[ox][5]); o.w = pack_bf16x2(acc[ox][6], acc[ox][7]);
+        dst[ox] = o;
+    }
+}
+
 // =================================== weight images =============================================================
 // image element (n, k) at ((k/8)*N + n)*8 + k%8; hi image then lo image (w - bf16(w), itself rounded to bf16)
 __global__ void prep_weight_kernel(const float* __restrict__ w, bf16* __restrict__ img, int K, int Kpad, int N) {
@@ -458,6 +528,19 @@ int launch_depthwise_t8(const cv_layer_info& L, const bf16* x, const float* w, c
                         cudaStream_t s) {
     const int64_t total = n_crops * L.hout * L.hout * (L.cout / 8);
     if (total == 0) return CV_OK;
+    // the trunk's own shapes: row-tiled kernel (a thread per output row); whole 128-row tiles only (n_crops * hout^2 % 128 == 0)
+    if ((n_crops * L.hout * L.hout) % TILE_M == 0 && L.hin == L.hout * L.stride) {
+        const int64_t rows = total / L.hout;
+        const unsigned rgrid = (unsigned)((rows + 127) / 128);
+#define DW_ROWS(KK, SS, HH)                                                                                             \
+        if (L.k == KK && L.stride == SS && L.hin == HH) {                                                               \
+            depthwise_t8_rows_kernel<KK, SS, HH><<<rgrid, 128, 0, s>>>(x, w, bias, y, rows, L.cout, L.relu);            \
+            CV_CHECK_LAUNCH();                                                                                          \
+            return CV_OK;                                                                                               \
+        }
+        DW_ROWS(5, 1, 8) DW_ROWS(5, 2, 8) DW_ROWS(3, 1, 4) DW_ROWS(3, 2, 4) DW_ROWS(5, 1, 2) DW_ROWS(3, 1, 2)
+#undef DW_ROWS
+    }
     const unsigned grid = (unsigned)((total + 255) / 256);
 #define DW_CASE(KK, SS)                                                                                                 \
     if (L.k == KK && L.stride == SS) {                                                                                  \
