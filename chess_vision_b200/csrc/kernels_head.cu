@@ -175,7 +175,10 @@ int launch_tile_glob_w(const float* glob_w, float* wt, cudaStream_t s) {
 
 // K is always cut into the same KSPLIT ranges, whatever the batch size: a board's logits do not depend on how many other
 // boards are in the call (and the fixed-order finishing sum keeps them bit-reproducible).
-constexpr int KSPLIT = 4;
+// 16 ranges of 30 K-blocks: a single board (one M tile) still spreads the 7.9 MB weight stream over 16 SMs (54 -> ~15 us, the largest
+// kernel of a one-board call), and a 4096-board chunk gets 512 CTAs instead of 128 on 148 SMs.
+constexpr int KSPLIT = 16;
+static_assert((KCH / KB_CHUNKS) % KSPLIT == 0, "K blocks must divide evenly over the splits");
 size_t global_head_partial_floats(int B, int num_sms) {
     (void)num_sms;
     return (size_t)KSPLIT * ((B + 127) / 128) * 128 * 64;

@@ -61,14 +61,31 @@ class ChessSquareCNN(nn.Module):
         self._ws = None
         self._lut = None
         self._wave = 0
+        self._sig_tensors = None
 
     # ------------------------------------------------------------------ native handle / weights
     def _signature(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        """Cheap change detector of the fp32 masters, evaluated on every call: the in-place version counters of the 288 state_dict
+        tensors (load_state_dict / optimizer steps bump them).  The tensor list itself is cached -- building ``state_dict()`` costs
+        ~250 us, more than a whole single-board forward -- and dropped whenever the module is moved or converted (``_apply``)."""
+        if self._sig_tensors is None:
+            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
+            self._sig_ptrs = tuple(t.data_ptr() for t in self._sig_tensors)
+        return self._sig_ptrs, tuple(t._version for t in self._sig_tensors)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._sig_tensors = None                               # .to() / .cuda() / .float() may replace the parameter tensors
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        self._sig_tensors = None                               # assign=True replaces tensors; the default copies (version bump)
+        return super().load_state_dict(state_dict, *args, **kwargs)
 
     def invalidate_packed_weights(self):
-        """Force a re-pack on the next call (needed only after editing ``.data`` in place without a version bump)."""
+        """Force a re-pack on the next call (needed only after editing ``.data`` in place without a version bump, or after replacing
+        a parameter object of a sub-module)."""
         self._packed_sig = None
+        self._sig_tensors = None
 
     def set_wave(self, boards: int):
         """Boards per internal wave (0 = library default); activations of one wave stay L2-resident."""
