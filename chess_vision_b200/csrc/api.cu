@@ -80,6 +80,10 @@ struct cv_square {
     char* dev_fen = nullptr;
     uint8_t* dev_fen_len = nullptr;
     int dev_fen_cap = 0;
+    // float entry point: uint8 image recovered from Normalize(ToTensor(uint8)) inputs (one wave) + the "not a uint8 image" flag
+    uint8_t* f2u_buf = nullptr;
+    size_t f2u_bytes = 0;
+    int* f2u_flag = nullptr;
 };
 
 namespace {
@@ -321,6 +325,28 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 }
                 if (!done && by_pieces)                                 // not supported after all: the other front ends read the whole chunk
                     for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+                // float source (the reference's own call, model(images)): recover the uint8 image the transform started from, run the
+                // third-generation front end on it and the first-generation one on the floats -- a device flag written by the recovery
+                // kernel makes exactly one of the two do the work (the other exits at once), so no host synchronisation is needed
+                const int* v1_run_flag = nullptr;
+                if (kind == CV_SRC_F32_NCHW && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok) {
+                    const size_t need = (size_t)nb * H * H * 3;
+                    if (h->f2u_bytes < need) {
+                        if (h->f2u_buf) CV_CUDA(cudaFree(h->f2u_buf));
+                        h->f2u_buf = nullptr; h->f2u_bytes = 0;
+                        CV_CUDA(cudaMalloc(&h->f2u_buf, need));
+                        h->f2u_bytes = need;
+                    }
+                    if (!h->f2u_flag) CV_CUDA(cudaMalloc(&h->f2u_flag, sizeof(int)));
+                    rc = launch_f32_to_u8_boards(static_cast<const float*>(src), nb, H, h->lut_host, h->f2u_buf, h->f2u_flag, s);
+                    if (rc) return rc;
+                    int took = 0;
+                    rc = launch_frontend3(h->f2u_buf, nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset, front_out, h->num_sms,
+                                          &took, s, h->f2u_flag);
+                    if (rc) return rc;
+                    h->launches += 1 + took;
+                    if (took) v1_run_flag = h->f2u_flag;              // otherwise (configuration not supported) the floats go the old way
+                }
                 if (!done && kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
                     rc = launch_frontend2(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe2_wimg,
                                           h->blob + kLayers[0].b_offset, h->blob + kLayers[1].b_offset, front_out, h->num_sms, &done, s);
@@ -328,7 +354,7 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 }
                 if (!done)
                     rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset,
-                                         h->blob + kLayers[1].b_offset, front_out, h->num_sms, s);
+                                         h->blob + kLayers[1].b_offset, front_out, h->num_sms, s, v1_run_flag);
             } else if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
             else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
             if (rc) return rc;
@@ -449,6 +475,8 @@ int cv_square_destroy(cv_square* h) {
     }
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->own_ws) cudaFree(h->own_ws);
+    if (h->f2u_buf) cudaFree(h->f2u_buf);
+    if (h->f2u_flag) cudaFree(h->f2u_flag);
     if (h->dev_fen) cudaFree(h->dev_fen);
     if (h->dev_fen_len) cudaFree(h->dev_fen_len);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);

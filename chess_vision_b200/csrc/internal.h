@@ -133,7 +133,7 @@ size_t frontend_weight_image_elems();
 int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s);
 int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev,
                     const bf16* wimg, const float* bias_stem, const float* bias_b00, bf16* y, int num_sms,
-                    cudaStream_t s);
+                    cudaStream_t s, const int* run_flag = nullptr);
 
 // ---- kernels_backend.cu: fused back-end stages (persistent tcgen05 kernels, activations in smem / TMEM) -----------------
 // stage D = blocks.3.* + blocks.4.0 + average pool + type/color heads + combine.  Input: "P8" tiles (128 rows = 8 crops,
@@ -180,4 +180,6 @@ int launch_frontend2(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
 size_t frontend3_weight_image_bytes();
 int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s);
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
-                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s);
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag = nullptr);
+// float NCHW boards that are Normalize(ToTensor(uint8)) -> the uint8 HWC image + a device flag (1 = some value is not on the uint8 grid)
+int launch_f32_to_u8_boards(const float* x_nchw, int nb, int H, const float* lut_host, uint8_t* out_hwc, int* flag_dev, cudaStream_t s);

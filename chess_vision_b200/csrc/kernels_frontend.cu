@@ -71,6 +71,7 @@ struct FrontParams {
     const float* bias_b00;
     bf16* y;
     int n_crops, H;
+    const int* run_flag;      // non-null: the kernel exits at once when *run_flag == 0 (the third-generation front end took the call)
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -111,6 +112,7 @@ template <int SRC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CropTaps tp_param) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (p.run_flag != nullptr && *p.run_flag == 0) return;       // uniform over the grid
     uint8_t* X = smem + OFF_X;
     uint8_t* Y = smem + OFF_Y;
     uint8_t* W = smem + OFF_W;
@@ -341,9 +343,9 @@ int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s) {
 }
 
 int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev, const bf16* wimg,
-                    const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, cudaStream_t s) {
+                    const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, cudaStream_t s, const int* run_flag) {
     if (nb == 0) return CV_OK;
-    FrontParams p{src, lut_dev, wimg, bias_stem, bias_b00, y, nb * 64, H};
+    FrontParams p{src, lut_dev, wimg, bias_stem, bias_b00, y, nb * 64, H, run_flag};
     const CropTaps tp = make_taps(g);
     const int grid = p.n_crops < num_sms ? p.n_crops : num_sms;
 #define FE_LAUNCH(KIND)                                                                                              \

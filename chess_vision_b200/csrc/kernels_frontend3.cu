@@ -69,6 +69,7 @@ struct Front3Params {
     int raw_pitch, raw_bytes, v_pitch, v_bytes, n_groups, g_magic, n_rawbuf, n_xbuf, box_bytes;
     int off_raw, off_v, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
+    const int* skip_flag;             // non-null: the kernel exits at once when *skip_flag != 0 (float source that is not a uint8 image, see below)
     int debug;                        // experiment builds (CV_FE3_DEBUG): 1 / 2 skip the resize passes, 4 / 8 skip epilogue TMEM loads / stores, 16 / 128 / 1024 /
                                       // 2048 skip MMA-thread waits, 32 skip the x_full wait, 64 spin in the epilogue, 256 wait-cycle report, 512 event trace
 };
@@ -109,6 +110,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
     uint64_t* raw_empty = bars + 35 /*3*/;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (p.skip_flag != nullptr && *p.skip_flag != 0) return;     // uniform over the grid: decided by an earlier kernel of the stream
 
     // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
     for (int i = threadIdx.x; i < p.n_xbuf * X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
@@ -516,7 +518,7 @@ int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev
 // Returns CV_OK and sets *supported = 0 when this kernel cannot take the configuration (the caller then uses an earlier
 // generation): non-affine normalisation table, window too large for shared memory (512x512 boards), > 255 window rows.
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
-                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s) {
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag) {
     *supported = 0;
     if (nb == 0) { *supported = 1; return CV_OK; }
     Front3Params p{};
@@ -587,6 +589,7 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     if (p.smem_total > 227 * 1024) return CV_OK;
     p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
     p.n_crops = nb * 64; p.H = H;
+    p.skip_flag = skip_flag;
 #if defined(CV_EXPERIMENTS) || defined(CV_FE_PROFILE)   // ablation / timing / trace switches (some change the results): experiment builds only
     { const char* d = getenv("CV_FE3_DEBUG"); p.debug = d ? atoi(d) : 0; }
 #endif
@@ -645,5 +648,59 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
         }
     }
 #endif
+    return CV_OK;
+}
+
+
+// ---- float source that is a uint8 image in disguise -------------------------------------------------------------------------------
+// The reference's own call is model(images) with images = Normalize(ToTensor(uint8 image)) (dataset.py:177-181): every value is
+// na[c] * u + nb[c] for an integer u in 0..255.  This kernel inverts that (4 pixels per thread: three float4 loads, three 32-bit stores,
+// NCHW float -> HWC uint8) and raises *flag when a value is NOT within 1e-5 of such a grid point (the grid step is ~0.017); the third-
+// generation front end then runs on the bytes (and exits at once if the flag is up), the first-generation one on the floats (and exits
+// at once if it is not): the float entry point gets the fast front end for what the reference actually feeds it, without a host sync.
+namespace {
+__global__ void __launch_bounds__(256) f32_nchw_to_u8_hwc_kernel(const float* __restrict__ x, int64_t n_quads, int HH, float3 na, float3 nb, float3 inv,
+                                                                 uint8_t* __restrict__ out, int* __restrict__ flag) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (q < n_quads) {
+        const int64_t px = q * 4, b = px / HH;
+        const int p0 = (int)(px - b * HH);
+        const float* base = x + b * 3 * (int64_t)HH + p0;
+        const float4 r = *reinterpret_cast<const float4*>(base), g = *reinterpret_cast<const float4*>(base + HH),
+                     bl = *reinterpret_cast<const float4*>(base + 2 * (int64_t)HH);
+        const float v[4][3] = {{r.x, g.x, bl.x}, {r.y, g.y, bl.y}, {r.z, g.z, bl.z}, {r.w, g.w, bl.w}};
+        const float a3[3] = {na.x, na.y, na.z}, b3[3] = {nb.x, nb.y, nb.z}, i3[3] = {inv.x, inv.y, inv.z};
+        uint32_t bytes[12];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float u = fminf(fmaxf(rintf((v[i][c] - b3[c]) * i3[c]), 0.f), 255.f);
+                bad |= !(fabsf(fmaf(a3[c], u, b3[c]) - v[i][c]) <= 1e-5f);
+                bytes[i * 3 + c] = (uint32_t)u;
+            }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + px * 3);
+#pragma unroll
+        for (int w = 0; w < 3; ++w) dst[w] = bytes[4 * w] | (bytes[4 * w + 1] << 8) | (bytes[4 * w + 2] << 16) | (bytes[4 * w + 3] << 24);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+}  // namespace
+
+int launch_f32_to_u8_boards(const float* x_nchw, int nb, int H, const float* lut_host, uint8_t* out_hwc, int* flag_dev, cudaStream_t s) {
+    if (nb == 0) return CV_OK;
+    float a[3], b[3], inv[3];
+    for (int c = 0; c < 3; ++c) {
+        b[c] = lut_host[c * 256];
+        a[c] = (lut_host[c * 256 + 255] - lut_host[c * 256]) / 255.0f;
+        inv[c] = a[c] != 0.f ? 1.0f / a[c] : 0.f;
+    }
+    CV_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
+    const int64_t n_quads = (int64_t)nb * H * H / 4;
+    f32_nchw_to_u8_hwc_kernel<<<(unsigned)((n_quads + 255) / 256), 256, 0, s>>>(x_nchw, n_quads, H * H, make_float3(a[0], a[1], a[2]),
+                                                                               make_float3(b[0], b[1], b[2]), make_float3(inv[0], inv[1], inv[2]),
+                                                                               out_hwc, flag_dev);
+    CV_CHECK_LAUNCH();
     return CV_OK;
 }

@@ -102,7 +102,7 @@ enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC
        CV_IMPL_MID_SPLIT = 1024, CV_IMPL_DEFAULT = 1023, CV_IMPL_ALL = 2047 };
 int cv_square_set_impl(cv_square* h, int mask);
 
-/* Boards per internal wave (activations of one wave stay L2-resident). 0 = library default. */
+/* Boards per internal wave (the stage hand-offs of one wave share the workspace). 0 = library default (4096 with the fused kernels). */
 int cv_square_set_wave(cv_square* h, int boards);
 
 size_t cv_square_workspace_bytes(const cv_square* h, int max_boards, int H, int precision);
@@ -110,7 +110,10 @@ size_t cv_square_workspace_bytes(const cv_square* h, int max_boards, int H, int 
 /* ChessSquareCNN.forward (models/square.py:92-114) on an already-normalised fp32 NCHW batch
  * x (B,3,H,H), H % 32 == 0 -- the tensor get_transform()'s eval branch produces (dataset.py:177-181).
  * Outputs fp32: squares (B,832) index = square*13+class; turn (B,1); castling (B,4);
- * features (B*64,480) optional (NULL to skip) = the pooled trunk output of square.py:90. */
+ * features (B*64,480) optional (NULL to skip) = the pooled trunk output of square.py:90.
+ * bf16 mode: when every value of x lies on the grid Normalize(ToTensor(u)) of a uint8 image (checked on the device, 1e-5), the call
+ * computes exactly what cv_square_forward_u8 computes on those bytes (the fast front end); otherwise the floats are used as they are.
+ * The handle keeps a scratch copy of one wave's bytes (B*H*H*3, allocated on first use: that first call synchronises the device). */
 int cv_square_forward_f32(cv_square* h, const float* x_nchw, int B, int H, int precision,
                           float* squares, float* turn, float* castling, float* features,
                           void* workspace, size_t workspace_bytes, void* stream);

@@ -518,6 +518,31 @@ def test_host_pipeline_pieces_and_fallbacks(gpu_model):
         gpu_model.set_wave(0)
 
 
+def test_float_entry_takes_the_fast_front_end_only_for_uint8_images(gpu_model):
+    """model(images) with images = Normalize(ToTensor(uint8)) (what the reference feeds it) must equal the uint8 entry point bit for
+    bit (the bytes are recovered on the device and go through the third-generation front end); a float input that is NOT on the uint8
+    grid -- even in a single value -- must give what the first-generation front end gives (mask without CV_IMPL_FRONTEND3)."""
+    from chess_vision_b200.dataset import NORM_MEAN, NORM_STD
+    u8 = torch.from_numpy(boards_u8(256, 6)).cuda()
+    mean = torch.tensor(NORM_MEAN, device="cuda").view(1, 3, 1, 1)
+    std = torch.tensor(NORM_STD, device="cuda").view(1, 3, 1, 1)
+    x = ((u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous()          # ToTensor + Normalize, dataset.py:177-181
+    a, b = gpu_model(x, precision="bf16"), gpu_model.forward_u8(u8, precision="bf16")
+    assert all(torch.equal(a[k], b[k]) for k in ("squares", "turn", "castling"))
+    y = x.clone()
+    y[3, 1, 100, 37] += 0.004                                                          # a quarter of a grey level off the grid
+    noisy = x + 0.003 * torch.randn_like(x)
+    for inp in (y, noisy):
+        got = gpu_model(inp, precision="bf16")
+        gpu_model.set_impl(1023 & ~512)
+        try:
+            want = gpu_model(inp, precision="bf16")
+        finally:
+            gpu_model.set_impl(1023)
+        assert all(torch.equal(got[k], want[k]) for k in ("squares", "turn", "castling"))
+    assert not torch.equal(gpu_model(y, precision="bf16")["squares"][3], a["squares"][3])   # and the perturbation is not ignored
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_batch_properties_bf16(gpu_model):
     """BASELINE.json config 2 size (4096 boards, bf16): results must not depend on how the batch is split
