@@ -543,6 +543,31 @@ def test_float_entry_takes_the_fast_front_end_only_for_uint8_images(gpu_model):
     assert not torch.equal(gpu_model(y, precision="bf16")["squares"][3], a["squares"][3])   # and the perturbation is not ignored
 
 
+def test_weight_changes_are_picked_up(square_cfg, gold_state):
+    """The packed device weights follow the fp32 masters: load_state_dict, an in-place edit under no_grad and a .float()/.to() round
+    trip after the first forward must all be seen by the next call (the change detector reads cached tensors' version counters)."""
+    from chess_vision_b200 import build_model, synthetic
+    u8 = torch.from_numpy(boards_u8(64, 8)).cuda()
+    m = build_model(square_cfg)
+    m.load_state_dict(gold_state, strict=True)
+    m = m.to("cuda").eval()
+    a = m.forward_u8(u8, precision="fp32")["squares"].clone()
+    other = synthetic.init_state_dict(m.state_dict(), 4321)
+    m.load_state_dict(other, strict=True)
+    b = m.forward_u8(u8, precision="fp32")["squares"].clone()
+    fresh = build_model(square_cfg)
+    fresh.load_state_dict(other, strict=True)
+    fresh = fresh.to("cuda").eval()
+    assert not torch.equal(a, b) and torch.equal(b, fresh.forward_u8(u8, precision="fp32")["squares"])
+    with torch.no_grad():
+        m.type_head[1].bias.add_(1.0)                                   # in-place edit: version bump
+    c = m.forward_u8(u8, precision="fp32")["squares"]
+    assert not torch.equal(b, c)
+    m = m.cpu().to("cuda")                                              # parameters re-created by _apply
+    m.load_state_dict(gold_state, strict=True)
+    assert torch.equal(m.forward_u8(u8, precision="fp32")["squares"], a)
+
+
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_batch_properties_bf16(gpu_model):
     """BASELINE.json config 2 size (4096 boards, bf16): results must not depend on how the batch is split
