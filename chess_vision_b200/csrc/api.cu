@@ -294,7 +294,7 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
         for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
     for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {                    // chunk: one global-head launch
         const int cb = std::min(MAX_CHUNK, B - c0);
-        for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: activations stay L2-resident
+        for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: the stage hand-offs share the workspace
             const int b0 = c0 + w0;
             const int nb = std::min(p.wave, cb - w0);
             rc = prof_mark(h, fused_front ? CV_PROF_FRONTEND : CV_PROF_CROP, s);
