@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchessvision_b200.so")
-SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_frontend.cu", "kernels_frontend2.cu", "kernels_frontend3.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu", "eval.cu", "resize.cu"]
+SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_frontend.cu", "kernels_frontend3.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu", "eval.cu", "resize.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 
@@ -18,12 +18,28 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libchessvision_b200.so cannot be built (there is no CPU fallback)")
 
 
+def _src_hash():
+    """Content hash of everything the library is compiled from (mtimes do not survive the copy to the GPU box)."""
+    import hashlib
+    hsh = hashlib.sha1()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "chessvision_b200.h")]
+    for f in files:
+        hsh.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            hsh.update(fh.read())
+    hsh.update(" ".join(NVCC_FLAGS + SOURCES).encode())
+    return hsh.hexdigest()
+
+
 def _stale():
+    """True when the library is missing or was built from other sources (hash stored beside it by _build)."""
     if not os.path.exists(LIB):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "chessvision_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(LIB + ".srchash") as fh:
+            return fh.read().strip() != _src_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False, variant=None, extra=()):
@@ -65,6 +81,9 @@ def _build(force, verbose, build_dir, extra):
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     os.replace(LIB + ".tmp", LIB)
+    if not extra and not os.environ.get("CV_NVCC_EXTRA"):
+        with open(LIB + ".srchash", "w") as fh:
+            fh.write(_src_hash())
     return LIB
 
 

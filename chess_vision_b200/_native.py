@@ -10,10 +10,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CV_B200_LIB: an experiment build of the same library (tools/, -DCV_FE_PROFILE ...); never a fallback
 LIB_PATH = os.environ.get("CV_B200_LIB") or os.path.join(_HERE, "libchessvision_b200.so")
 
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16, PRECISION_FP16 = 0, 1, 2
 LAYOUT_HWC, LAYOUT_CHW = 0, 1
 FEN_STRIDE = 80
-PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16}
+PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16,
+              "fp16": PRECISION_FP16, "float16": PRECISION_FP16}
+# cv_square_set_impl bits (include/chessvision_b200.h; kept in step by tests/test_boundary.py)
+IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS = 1, 2, 4, 8
+IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_FRONTEND3 = 16, 32, 64, 128, 512
+IMPL_DEFAULT, IMPL_ALL = 1023, 2047
 
 
 class NativeError(RuntimeError):
@@ -34,13 +39,18 @@ def _sig(fn, res, *args):
 
 
 def lib():
-    """Load (building first if the sources are newer) and return the ctypes library."""
+    """Load and return the ctypes library; the default in-tree library is (re)built first when it is missing or older than a
+    source under csrc/ and nvcc is available (a prebuilt library on a box without nvcc is used as it is)."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.environ.get("CV_B200_LIB"):
         from . import _build
-        _build.build()
+        try:
+            _build.build()                       # no-op unless stale
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):
+                raise
     try:
         L = C.CDLL(LIB_PATH)
     except OSError as e:  # pragma: no cover
@@ -72,6 +82,7 @@ def lib():
     _sig(L.cv_synth_boards_host, i32, vp, i32, i64, i32, i32, u32, i32, vp)
     _sig(L.cv_fen_from_classes_host, i32, vp, C.c_float, vp, vp)
     _sig(L.cv_square_launch_count, i64, vp)
+    _sig(L.cv_square_fp16_status, i32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int))
     _sig(L.cv_square_profile, i32, vp, i32)
     _sig(L.cv_square_profile_read, i32, vp, vp, vp)
     _sig(L.cv_eval_accumulate, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp)

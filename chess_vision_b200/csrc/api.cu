@@ -39,20 +39,23 @@ struct cv_square {
     bool loaded = false;
     float* blob = nullptr;        // fp32 packed weights (device, owned)
     float* glob_wt = nullptr;     // global_head weight transposed to [30720][64] (device, owned)
-    float* glob_wtile = nullptr;  // global_head weight in the tf32 UMMA operand layout [30720/4][64][4] (kernels_head.cu)
+    float* glob_wtile = nullptr;  // global_head weight in the tf32 UMMA operand layout [hi | lo][30720/4][64][4] (kernels_head.cu)
     float* head_w = nullptr;      // aligned copies of the small heads: head_w[10*480], head_b[10], glob_b[64], tc_w[320], tc_b[5]
     float* lut = nullptr;         // normalisation LUT [3][256] (device, owned)
     bf16* wimg = nullptr;         // bf16 UMMA weight images of the 30 GEMM layers (device, owned)
     bf16* fe_wimg = nullptr;      // hi|lo weight images of the fused front end (conv_stem + blocks.0.0)
-    bf16* fe2_wimg = nullptr;     // same for the second-generation front end
-    uint8_t* fe3_wimg = nullptr;  // third generation: fp16 stem image + bf16 hi|lo blocks.0.0 image, then an int "stem weights exceed fp16" flag
-    bool fe3_ok = false;          // the stem weights fit fp16 (checked when the weights are packed)
-    float lut_host[768];          // host copy of the normalisation table (affinity check of the second-generation front end)
-    uint8_t* sd_img = nullptr;    // weight image of the fused tail (stage D)
-    uint32_t sd_off[CV_STAGE_D_OPS], sd_bytes[CV_STAGE_D_OPS];
-    uint8_t* sb_img = nullptr;    // weight image of the fused blocks.0.1 + blocks.1 stage (stage B)
-    uint8_t* sc_img = nullptr;    // weight image of the fused blocks.2 stage (stage C)
-    uint32_t sc_off[CV_STAGE_C_OPS], sc_bytes[CV_STAGE_C_OPS];
+    uint8_t* fe3_wimg = nullptr;  // third generation: fp16 stem image + blocks.0.0 images (bf16 hi|lo, fp16), then an int "weights exceed fp16" flag
+    bool fe3_ok = false;          // the stem / blocks.0.0 weights fit fp16 (checked when the weights are packed)
+    float lut_host[768];          // host copy of the normalisation table (affinity check of the third-generation front end)
+    // weight images of the fused stages, index 0 = bf16 (stages B / C: W_hi | W_lo), 1 = fp16
+    uint8_t* sd_img[2] = {};      // fused tail (stage D)
+    uint32_t sd_off[2][CV_STAGE_D_OPS], sd_bytes[2][CV_STAGE_D_OPS];
+    uint8_t* sb_img[2] = {};      // fused blocks.0.1 + blocks.1 (stage B)
+    uint8_t* sc_img[2] = {};      // fused blocks.2 (stage C)
+    uint32_t sc_off[2][CV_STAGE_C_OPS], sc_bytes[2][CV_STAGE_C_OPS];
+    int* flags = nullptr;         // device ints: [0] a weight of stages B-D does not fit fp16, [1] fp16 overflow of the current call (StageGate),
+                                  // [2] float entry point: "the input is not a uint8 image"
+    bool f16_ok = false;          // every GEMM weight of the fused stages fits fp16 (checked when the weights are packed)
     int num_sms = 148;
     int impl = CV_IMPL_DEFAULT;   // which bf16 kernels run (cv_square_set_impl)
     int wave = 0;                 // boards per wave, 0 = default per precision
@@ -75,15 +78,12 @@ struct cv_square {
     void* stage[kStages] = {};
     uint8_t* stage_flip[kStages] = {};
     size_t stage_bytes = 0;
+    int stage_boards = 0;                 // boards a staging slot (and its flip buffer) holds
     void* own_ws = nullptr;
     size_t own_ws_bytes = 0;
     char* dev_fen = nullptr;
     uint8_t* dev_fen_len = nullptr;
     int dev_fen_cap = 0;
-    // float entry point: uint8 image recovered from Normalize(ToTensor(uint8)) inputs (one wave) + the "not a uint8 image" flag
-    uint8_t* f2u_buf = nullptr;
-    size_t f2u_bytes = 0;
-    int* f2u_flag = nullptr;
 };
 
 namespace {
@@ -124,10 +124,12 @@ inline int prof_mark(cv_square* h, int slot, cudaStream_t s) {
 struct WavePlan {
     int wave;
     size_t es;                        // activation element size
-    size_t off_crops, off_stem, off_small[NBUF_SMALL], off_feat, off_partial, off_sq, off_turn, off_cast, total;
+    size_t off_crops, off_stem, off_small[NBUF_SMALL], off_feat, off_partial, off_sq, off_turn, off_cast, off_f2u, f2u_bytes, total;
 };
 
-WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
+// H > 0 adds the scratch of the float entry point in the 16-bit modes (the uint8 image recovered from Normalize(ToTensor(uint8))
+// inputs, one wave of H x H x 3 bytes per board): it lives in the caller's workspace, so a forward never allocates.
+WavePlan make_plan(const cv_square* h, int max_boards, int precision, int H) {
     WavePlan p;
     const bool bf = precision != CV_PRECISION_FP32;
     const int all_fused = CV_IMPL_FRONTEND | CV_IMPL_EARLY | CV_IMPL_MID | CV_IMPL_TAIL;
@@ -150,6 +152,8 @@ WavePlan make_plan(const cv_square* h, int max_boards, int precision) {
     p.off_sq = off; off = align_up(off + (size_t)max_boards * 832 * sizeof(float));
     p.off_turn = off; off = align_up(off + (size_t)max_boards * sizeof(float));
     p.off_cast = off; off = align_up(off + (size_t)max_boards * 4 * sizeof(float));
+    p.f2u_bytes = (bf && (h->impl & CV_IMPL_FRONTEND) && (h->impl & CV_IMPL_FRONTEND3) && H > 0) ? (size_t)p.wave * H * H * 3 : 0;
+    p.off_f2u = off; off = align_up(off + p.f2u_bytes);
     p.total = off;
     return p;
 }
@@ -187,7 +191,8 @@ int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16*
 
 template <typename T>
 int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, float* feat_chunk, int64_t crop_base,
-             bool first_wave, int first_layer, cudaStream_t s) {
+             bool first_wave, int first_layer, const StageGate& gate, cudaStream_t s) {
+    const int fi = gate.f16 ? 1 : 0;                   // which weight images the fused stages read
     const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
@@ -227,7 +232,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
                 if (rc) return rc;
                 p2 = small[(h->out_buf[1] + 1) % NBUF_SMALL];               // any two buffers but layer 1's own
                 p8 = small[(h->out_buf[1] + 2) % NBUF_SMALL];
-                rc = launch_stageB(reinterpret_cast<const bf16*>(buf_of(1)), n, h->sb_img, reinterpret_cast<bf16*>(p2), h->num_sms, s);
+                rc = launch_stageB(reinterpret_cast<const bf16*>(buf_of(1)), n, h->sb_img[fi], reinterpret_cast<bf16*>(p2), h->num_sms, gate, s);
                 if (rc) return rc;
                 ++h->launches;
                 rc = prof_mark(h, CV_PROF_MID, s);
@@ -241,8 +246,8 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
                 if (rc) return rc;
                 ++h->launches;
             }
-            rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img, h->sc_off, h->sc_bytes, reinterpret_cast<bf16*>(p8),
-                               h->num_sms, (h->impl & CV_IMPL_MID_SPLIT) != 0, s);
+            rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img[fi], h->sc_off[fi], h->sc_bytes[fi], reinterpret_cast<bf16*>(p8),
+                               h->num_sms, gate, s);
             if (rc) return rc;
             ++h->launches;
             rc = prof_mark(h, CV_PROF_TAIL, s);
@@ -255,7 +260,8 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
             if (rc) return rc;
             ++h->launches;
         }
-        rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img, h->sd_off, h->sd_bytes, feat_chunk, 1, crop_base, squares, h->num_sms, s);
+        rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img[fi], h->sd_off[fi], h->sd_bytes[fi], feat_chunk, 1, crop_base, squares,
+                           h->num_sms, gate, s);
         if (rc) return rc;
         ++h->launches;
         return CV_OK;
@@ -268,6 +274,52 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
     return CV_OK;
 }
 
+// One front-end launch sequence for `nb` boards of a wave in the 16-bit modes (crop gather + conv_stem + blocks.0.0 -> front_out):
+// third generation for uint8 HWC boards (piece by piece behind the host path's copies when `by_pieces`), first generation for the
+// other sources and for windows the third cannot stage; float sources that are uint8 images in disguise take the third generation
+// on the recovered bytes (f2u: recovered by the caller once per wave; its device flag picks exactly one of the two kernels).
+int launch_front(cv_square* h, const void* src, int kind, int nb, int H, const CropGeom& g, bf16* front_out, bool by_pieces,
+                 const uint8_t* f2u, const int* f2u_flag, const StageGate& gate, cudaStream_t s) {
+    int rc = CV_OK, done = 0;
+    const bool v3 = (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok;
+    const float* bias_b00 = h->blob + kLayers[1].b_offset;
+    if (kind == CV_SRC_U8_HWC && v3) {
+        if (by_pieces) {
+            for (int i = 0, q0 = 0; i < h->n_pieces && q0 < nb; ++i, q0 += h->piece_boards) {
+                const int qn = std::min(h->piece_boards, nb - q0);
+                CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+                rc = launch_frontend3(static_cast<const uint8_t*>(src) + (size_t)q0 * H * H * 3, qn, H, g, h->lut_host, h->fe3_wimg, bias_b00,
+                                      front_out + (size_t)q0 * 64 * 256 * 16, h->num_sms, &done, s, nullptr, gate);
+                if (rc) return rc;
+                if (!done) break;                              // configuration not supported: nothing was launched
+                ++h->launches;
+            }
+            if (!done)                                         // not supported after all: the first generation reads the whole chunk
+                for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+        } else {
+            rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, bias_b00, front_out, h->num_sms, &done, s,
+                                  nullptr, gate);
+            if (rc) return rc;
+            h->launches += done;
+        }
+    }
+    const int* v1_run_flag = nullptr;
+    if (kind == CV_SRC_F32_NCHW && f2u != nullptr) {
+        int took = 0;
+        rc = launch_frontend3(f2u, nb, H, g, h->lut_host, h->fe3_wimg, bias_b00, front_out, h->num_sms, &took, s, f2u_flag, gate);
+        if (rc) return rc;
+        h->launches += took;
+        if (took) v1_run_flag = f2u_flag;                      // otherwise (configuration not supported) the floats go the old way
+    }
+    if (!done) {
+        rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset, bias_b00, front_out, h->num_sms, s,
+                             v1_run_flag, gate);
+        if (rc) return rc;
+        ++h->launches;
+    }
+    return CV_OK;
+}
+
 template <typename T>
 int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layout, int B, int H, int precision,
                  float* squares, float* turn, float* castling, float* features, void* workspace, size_t ws_bytes,
@@ -275,7 +327,7 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     CropGeom g;
     int rc = cv_make_crop_geom(H, &g);
     if (rc) return rc;
-    WavePlan p = make_plan(h, B, precision);
+    WavePlan p = make_plan(h, B, precision, x_f32 ? H : 0);
     if (ws_bytes < p.total) {
         cv_set_error("workspace too small: need %zu bytes, got %zu", p.total, ws_bytes);
         return CV_ERR_WORKSPACE;
@@ -283,85 +335,73 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     char* ws = static_cast<char*>(workspace);
     T* crops = reinterpret_cast<T*>(ws + p.off_crops);
     float* feat = reinterpret_cast<float*>(ws + p.off_feat);
-    // bf16: crop gather + conv_stem + blocks.0.0 fused in one tensor-core kernel (activations stay in smem)
+    // 16-bit modes: crop gather + conv_stem + blocks.0.0 fused in one tensor-core kernel (activations stay in smem)
     const bool fused_front = sizeof(T) == 2 && (h->impl & CV_IMPL_FRONTEND);
     bf16* front_out = fused_front ? reinterpret_cast<bf16*>(ws + p.off_small[h->out_buf[1]]) : nullptr;
+    // fp16 operands exist in the fused kernels only; weights that do not fit fp16 (checked at load time) make the mode run its bf16 kernels
+    const int all_fused = CV_IMPL_FRONTEND | CV_IMPL_EARLY | CV_IMPL_MID | CV_IMPL_TAIL;
+    const bool want_f16 = precision == CV_PRECISION_FP16;
+    if (want_f16 && (h->impl & all_fused) != all_fused) {
+        cv_set_error("CV_PRECISION_FP16 needs the fused kernels (CV_IMPL_FRONTEND | EARLY | MID | TAIL); the layer-granular kernels are bf16 / fp32");
+        return CV_ERR_STATE;
+    }
+    const bool f16 = want_f16 && h->f16_ok;
+    int* ovf = h->flags + 1;
+    StageGate passes[2];
+    int n_passes = 1;
+    if (f16) {
+        // both chains are enqueued: fp16 kernels run while *ovf == 0, the bf16 kernels after them only if it was raised
+        CV_CUDA(cudaMemsetAsync(ovf, 0, sizeof(int), s));
+        passes[0].f16 = true; passes[0].flag = ovf; passes[0].want = 0; passes[0].ovf = ovf;
+        passes[1].f16 = false; passes[1].flag = ovf; passes[1].want = 1;
+        n_passes = 2;
+    }
     // host path: the boards of this call arrive in pieces (one event each, cv_square_predict_host_u8).  Only the third-generation front
     // end of a single-wave call follows them piece by piece; every other configuration waits for the whole chunk first.
     const bool by_pieces = h->n_pieces > 1 && fused_front && x_u8 && layout != CV_LAYOUT_CHW && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok &&
                            B <= p.wave && B <= MAX_CHUNK;
     if (h->n_pieces > 0 && !by_pieces)
         for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+    // float source (the reference's own call, model(images)): recover the uint8 image the transform started from (one wave at a time,
+    // into the workspace); needs 16-byte aligned rows for the float4 loads of the recovery kernel
+    const bool recover = fused_front && x_f32 && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok && p.f2u_bytes > 0 &&
+                         (reinterpret_cast<uintptr_t>(x_f32) & 15) == 0 && (H * H) % 4 == 0;
+    uint8_t* f2u = recover ? reinterpret_cast<uint8_t*>(ws + p.off_f2u) : nullptr;
+    int* f2u_flag = h->flags + 2;
     for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {                    // chunk: one global-head launch
         const int cb = std::min(MAX_CHUNK, B - c0);
         for (int w0 = 0; w0 < cb; w0 += p.wave) {                  // wave: the stage hand-offs share the workspace
             const int b0 = c0 + w0;
             const int nb = std::min(p.wave, cb - w0);
-            rc = prof_mark(h, fused_front ? CV_PROF_FRONTEND : CV_PROF_CROP, s);
-            if (rc) return rc;
-            if (fused_front) {
-                const void* src = x_u8 ? static_cast<const void*>(x_u8 + (size_t)b0 * H * H * 3)
-                                       : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
-                const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
-                int done = 0;
-                // by_pieces: the front end -- whose work unit is one crop, so short launches cost little -- runs piece by piece behind
-                // the copies, the later stages on the whole wave
-                if (kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok) {
-                    if (by_pieces) {
-                        for (int i = 0, q0 = 0; i < h->n_pieces && q0 < nb; ++i, q0 += h->piece_boards) {
-                            const int qn = std::min(h->piece_boards, nb - q0);
-                            CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
-                            rc = launch_frontend3(static_cast<const uint8_t*>(src) + (size_t)q0 * H * H * 3, qn, H, g, h->lut_host, h->fe3_wimg,
-                                                  h->blob + kLayers[1].b_offset, front_out + (size_t)q0 * 64 * 256 * 16, h->num_sms, &done, s);
-                            if (rc) return rc;
-                            if (!done) break;                          // configuration not supported: nothing was launched
-                            if (i > 0) ++h->launches;
-                        }
-                    } else {
-                        rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset,
-                                              front_out, h->num_sms, &done, s);
-                        if (rc) return rc;
-                    }
-                }
-                if (!done && by_pieces)                                 // not supported after all: the other front ends read the whole chunk
-                    for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
-                // float source (the reference's own call, model(images)): recover the uint8 image the transform started from, run the
-                // third-generation front end on it and the first-generation one on the floats -- a device flag written by the recovery
-                // kernel makes exactly one of the two do the work (the other exits at once), so no host synchronisation is needed
-                const int* v1_run_flag = nullptr;
-                if (kind == CV_SRC_F32_NCHW && (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok) {
-                    const size_t need = (size_t)nb * H * H * 3;
-                    if (h->f2u_bytes < need) {
-                        if (h->f2u_buf) CV_CUDA(cudaFree(h->f2u_buf));
-                        h->f2u_buf = nullptr; h->f2u_bytes = 0;
-                        CV_CUDA(cudaMalloc(&h->f2u_buf, need));
-                        h->f2u_bytes = need;
-                    }
-                    if (!h->f2u_flag) CV_CUDA(cudaMalloc(&h->f2u_flag, sizeof(int)));
-                    rc = launch_f32_to_u8_boards(static_cast<const float*>(src), nb, H, h->lut_host, h->f2u_buf, h->f2u_flag, s);
-                    if (rc) return rc;
-                    int took = 0;
-                    rc = launch_frontend3(h->f2u_buf, nb, H, g, h->lut_host, h->fe3_wimg, h->blob + kLayers[1].b_offset, front_out, h->num_sms,
-                                          &took, s, h->f2u_flag);
-                    if (rc) return rc;
-                    h->launches += 1 + took;
-                    if (took) v1_run_flag = h->f2u_flag;              // otherwise (configuration not supported) the floats go the old way
-                }
-                if (!done && kind == CV_SRC_U8_HWC && (h->impl & CV_IMPL_FRONTEND2)) {
-                    rc = launch_frontend2(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe2_wimg,
-                                          h->blob + kLayers[0].b_offset, h->blob + kLayers[1].b_offset, front_out, h->num_sms, &done, s);
-                    if (rc) return rc;
-                }
-                if (!done)
-                    rc = launch_frontend(src, kind, nb, H, g, h->lut, h->fe_wimg, h->blob + kLayers[0].b_offset,
-                                         h->blob + kLayers[1].b_offset, front_out, h->num_sms, s, v1_run_flag);
-            } else if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
-            else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
-            if (rc) return rc;
-            ++h->launches;
-            rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0,
-                             fused_front ? 2 : 0, s);
-            if (rc) return rc;
+            if (!fused_front) {
+                rc = prof_mark(h, CV_PROF_CROP, s);
+                if (rc) return rc;
+                if (x_u8) rc = launch_crop_u8<T>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+                else rc = launch_crop_f32<T>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+                if (rc) return rc;
+                ++h->launches;
+                rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 0,
+                                 StageGate(), s);
+                if (rc) return rc;
+                continue;
+            }
+            const void* src = x_u8 ? static_cast<const void*>(x_u8 + (size_t)b0 * H * H * 3)
+                                   : static_cast<const void*>(x_f32 + (size_t)b0 * 3 * H * H);
+            const int kind = x_u8 ? (layout == CV_LAYOUT_CHW ? CV_SRC_U8_CHW : CV_SRC_U8_HWC) : CV_SRC_F32_NCHW;
+            if (recover) {
+                rc = launch_f32_to_u8_boards(static_cast<const float*>(src), nb, H, h->lut_host, f2u, f2u_flag, s);
+                if (rc) return rc;
+                ++h->launches;
+            }
+            for (int pass = 0; pass < n_passes; ++pass) {
+                rc = prof_mark(h, CV_PROF_FRONTEND, s);
+                if (rc) return rc;
+                rc = launch_front(h, src, kind, nb, H, g, front_out, by_pieces && pass == 0, f2u, f2u_flag, passes[pass], s);
+                if (rc) return rc;
+                rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 2,
+                                 passes[pass], s);
+                if (rc) return rc;
+            }
         }
         rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
         if (rc) return rc;
@@ -392,7 +432,7 @@ int check_forward_args(const cv_square* h, const void* x, int B, int H, int prec
     if (!h) { cv_set_error("null handle"); return CV_ERR_ARG; }
     if (!h->loaded) { cv_set_error("weights not loaded: call cv_square_load_weights first"); return CV_ERR_STATE; }
     if (B < 0) { cv_set_error("negative batch"); return CV_ERR_ARG; }
-    if (precision != CV_PRECISION_FP32 && precision != CV_PRECISION_BF16) { cv_set_error("bad precision %d", precision); return CV_ERR_ARG; }
+    if (precision != CV_PRECISION_FP32 && precision != CV_PRECISION_BF16 && precision != CV_PRECISION_FP16) { cv_set_error("bad precision %d", precision); return CV_ERR_ARG; }
     if (H < 32 || H % 32) { cv_set_error("board side H=%d must be a positive multiple of 32", H); return CV_ERR_ARG; }
     if (B > 0 && (!x || !squares || !turn || !castling || !ws)) { cv_set_error("null data pointer"); return CV_ERR_ARG; }
     return CV_OK;
@@ -446,16 +486,19 @@ int cv_square_create(int device, cv_square** out) {
         }
     CV_CUDA(cudaMalloc(&h->blob, (size_t)CV_BLOB_FLOATS * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->glob_wt, (size_t)30720 * 64 * sizeof(float)));
-    CV_CUDA(cudaMalloc(&h->glob_wtile, (size_t)30720 * 64 * sizeof(float)));
+    CV_CUDA(cudaMalloc(&h->glob_wtile, (size_t)2 * 30720 * 64 * sizeof(float)));     // hi | lo planes
     CV_CUDA(cudaMalloc(&h->head_w, (4800 + 16 + 64 + 320 + 8) * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->lut, 768 * sizeof(float)));
     CV_CUDA(cudaMalloc(&h->wimg, 2 * umma_weight_image_elems() * sizeof(bf16)));   // hi + lo images
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
-    CV_CUDA(cudaMalloc(&h->fe2_wimg, frontend2_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->fe3_wimg, frontend3_weight_image_bytes() + 16));
-    CV_CUDA(cudaMalloc(&h->sd_img, stageD_image_bytes()));
-    CV_CUDA(cudaMalloc(&h->sc_img, stageC_image_bytes()));
-    CV_CUDA(cudaMalloc(&h->sb_img, stageB_image_bytes()));
+    for (int f = 0; f < 2; ++f) {
+        CV_CUDA(cudaMalloc(&h->sd_img[f], stageD_image_bytes()));
+        CV_CUDA(cudaMalloc(&h->sc_img[f], stageC_image_bytes()));
+        CV_CUDA(cudaMalloc(&h->sb_img[f], stageB_image_bytes()));
+    }
+    CV_CUDA(cudaMalloc(&h->flags, 4 * sizeof(int)));
+    CV_CUDA(cudaMemset(h->flags, 0, 4 * sizeof(int)));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     default_lut(h->lut_host);
     CV_CUDA(cudaMemcpy(h->lut, h->lut_host, sizeof(h->lut_host), cudaMemcpyHostToDevice));
@@ -466,17 +509,18 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe2_wimg); cudaFree(h->fe3_wimg); cudaFree(h->sd_img); cudaFree(h->sc_img); cudaFree(h->sb_img);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe3_wimg); cudaFree(h->flags);
+    for (int f = 0; f < 2; ++f) { cudaFree(h->sd_img[f]); cudaFree(h->sc_img[f]); cudaFree(h->sb_img[f]); }
     for (int i = 0; i < cv_square::kStages; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
         if (h->stage_flip[i]) cudaFree(h->stage_flip[i]);
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
         if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
+        for (int j = 0; j < cv_square::kPieces; ++j)
+            if (h->ev_piece[i][j]) cudaEventDestroy(h->ev_piece[i][j]);
     }
     for (cudaEvent_t e : h->prof_pool) cudaEventDestroy(e);
     if (h->own_ws) cudaFree(h->own_ws);
-    if (h->f2u_buf) cudaFree(h->f2u_buf);
-    if (h->f2u_flag) cudaFree(h->f2u_flag);
     if (h->dev_fen) cudaFree(h->dev_fen);
     if (h->dev_fen_len) cudaFree(h->dev_fen_len);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -507,27 +551,31 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     if (rc) return rc;
     rc = launch_frontend_prep_weights(h->blob, h->fe_wimg, s);
     if (rc) return rc;
-    rc = launch_frontend2_prep_weights(h->blob, h->fe2_wimg, s);
-    if (rc) return rc;
     int* fe3_flag = reinterpret_cast<int*>(h->fe3_wimg + frontend3_weight_image_bytes());
     rc = launch_frontend3_prep_weights(h->blob, h->fe3_wimg, fe3_flag, s);
     if (rc) return rc;
-    rc = build_stageD_image(h->blob, h->sd_img, h->sd_off, h->sd_bytes, s);
-    if (rc) return rc;
-    rc = build_stageC_image(h->blob, h->sc_img, h->sc_off, h->sc_bytes, s);
-    if (rc) return rc;
-    rc = build_stageB_image(h->blob, h->sb_img, s);
-    if (rc) return rc;
+    CV_CUDA(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), s));
+    for (int f = 0; f < 2; ++f) {                 // bf16 images, then fp16 images (+ the fp16 range check of every GEMM weight)
+        int* chk = f ? h->flags : nullptr;
+        rc = build_stageD_image(h->blob, h->sd_img[f], h->sd_off[f], h->sd_bytes[f], chk, s);
+        if (rc) return rc;
+        rc = build_stageC_image(h->blob, h->sc_img[f], h->sc_off[f], h->sc_bytes[f], chk, s);
+        if (rc) return rc;
+        rc = build_stageB_image(h->blob, h->sb_img[f], chk, s);
+        if (rc) return rc;
+    }
     float* hw = h->head_w;
     CV_CUDA(cudaMemcpyAsync(hw, h->blob + CV_OFF_HEAD_W, 4800 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 4800, h->blob + CV_OFF_HEAD_B, 10 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 4816, h->blob + CV_OFF_GLOB_B, 64 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 4880, h->blob + CV_OFF_TC_W, 320 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(hw + 5200, h->blob + CV_OFF_TC_B, 5 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    int fe3_overflow = 1;
+    int fe3_overflow = 1, w_overflow = 1;
     CV_CUDA(cudaMemcpyAsync(&fe3_overflow, fe3_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CV_CUDA(cudaMemcpyAsync(&w_overflow, h->flags, sizeof(int), cudaMemcpyDeviceToHost, s));
     CV_CUDA(cudaStreamSynchronize(s));
     h->fe3_ok = fe3_overflow == 0;
+    h->f16_ok = w_overflow == 0 && h->fe3_ok;
     h->loaded = true;
     return CV_OK;
 }
@@ -547,9 +595,8 @@ int cv_square_set_wave(cv_square* h, int boards) {
 }
 
 size_t cv_square_workspace_bytes(const cv_square* h, int max_boards, int H, int precision) {
-    (void)H;
     if (!h || max_boards < 0) return 0;
-    return make_plan(h, std::max(max_boards, 1), precision).total;
+    return make_plan(h, std::max(max_boards, 1), precision, H).total;
 }
 
 int cv_square_forward_f32(cv_square* h, const float* x, int B, int H, int precision, float* squares, float* turn,
@@ -591,7 +638,7 @@ int cv_square_predict_u8(cv_square* h, const uint8_t* boards, int layout, const 
     CV_ARG(B >= 0, "negative batch");
     if (B == 0) return CV_OK;
     CV_ARG(fen && fen_len && ws, "null data pointer");
-    WavePlan p = make_plan(h, B, precision);
+    WavePlan p = make_plan(h, B, precision, 0);
     char* w = static_cast<char*>(ws);
     float* sq = reinterpret_cast<float*>(w + p.off_sq);
     float* tu = reinterpret_cast<float*>(w + p.off_turn);
@@ -628,19 +675,27 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
     }
     const size_t per_board = (size_t)H * H * 3;
     int max_chunk = 512, piece = 128;
-    if (const char* e = getenv("CV_HOST_CHUNK")) max_chunk = std::max(128, atoi(e) / 128 * 128);      // tuning experiments
-    if (const char* e = getenv("CV_HOST_PIECE")) piece = std::max(32, atoi(e));
     bool ramp_head = false, shrink_tail = false, tail256 = false;      // measured (tools/gpu_host_trace.py): flat 512-board chunks are best
+#ifdef CV_EXPERIMENTS                 // tuning knobs of the host pipeline: experiment builds only
+    if (const char* e = getenv("CV_HOST_CHUNK")) max_chunk = std::min(4096, std::max(128, atoi(e) / 128 * 128));
+    if (const char* e = getenv("CV_HOST_PIECE")) piece = std::max(32, atoi(e));
     if (const char* e = getenv("CV_HOST_SCHED")) { const int v = atoi(e); ramp_head = v & 1; shrink_tail = v & 2; tail256 = v & 4; }
+#endif
     const int chunk = std::min(B, max_chunk);
-    if (h->stage_bytes < chunk * per_board) {
+    if (h->stage_bytes < chunk * per_board || h->stage_boards < chunk) {
         for (int i = 0; i < cv_square::kStages; ++i) {
             if (h->stage[i]) CV_CUDA(cudaFree(h->stage[i]));
             if (h->stage_flip[i]) CV_CUDA(cudaFree(h->stage_flip[i]));
-            CV_CUDA(cudaMalloc(&h->stage[i], chunk * per_board));
-            CV_CUDA(cudaMalloc(&h->stage_flip[i], 512));
+            h->stage[i] = nullptr; h->stage_flip[i] = nullptr;
         }
-        h->stage_bytes = chunk * per_board;
+        h->stage_bytes = 0; h->stage_boards = 0;
+        const size_t bytes = std::max(h->stage_bytes, chunk * per_board);
+        for (int i = 0; i < cv_square::kStages; ++i) {
+            CV_CUDA(cudaMalloc(&h->stage[i], bytes));
+            CV_CUDA(cudaMalloc(&h->stage_flip[i], (size_t)max_chunk));       // one flag per board of the largest chunk
+        }
+        h->stage_bytes = bytes;
+        h->stage_boards = max_chunk;
     }
     size_t need = cv_square_workspace_bytes(h, chunk, H, precision);
     if (h->own_ws_bytes < need) {
@@ -660,7 +715,11 @@ int cv_square_predict_host_u8(cv_square* h, const uint8_t* boards_host, int layo
     // stages B-D of the last chunk (measured per 4096 boards: 16.0 ms; 16.6 ms with whole-chunk events and growing / shrinking
     // chunk sizes, 17.7 ms with equal chunks and whole-chunk events).  CV_HOST_SCHED: bit 0 growing head, bit 1 / 2 shrinking tails.
     // CV_HOST_TRACE=1: per-chunk timeline (copy end, compute end, ms since the first copy was enqueued) on stderr
+#ifdef CV_EXPERIMENTS
     const bool trace = getenv("CV_HOST_TRACE") != nullptr;
+#else
+    const bool trace = false;
+#endif
     std::vector<cudaEvent_t> tr_copy, tr_comp;
     std::vector<int> tr_nb;
     cudaEvent_t tr0 = nullptr;
@@ -814,5 +873,15 @@ int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts) {
 }
 
 int64_t cv_square_launch_count(const cv_square* h) { return h ? h->launches : 0; }
+
+int cv_square_fp16_status(cv_square* h, int* weights_fit, int* overflowed) {
+    CV_ARG(h != nullptr, "null handle");
+    CV_CUDA(cudaSetDevice(h->device));
+    int ovf = 0;
+    CV_CUDA(cudaMemcpy(&ovf, h->flags + 1, sizeof(int), cudaMemcpyDeviceToHost));     // synchronises with the null stream's work
+    if (weights_fit) *weights_fit = h->f16_ok ? 1 : 0;
+    if (overflowed) *overflowed = ovf;
+    return CV_OK;
+}
 
 }  // extern "C"

@@ -127,59 +127,70 @@ int launch_dense_umma(const cv_layer_info& L, const bf16* x, bool in_rowmajor3, 
 int launch_depthwise_t8(const cv_layer_info& L, const bf16* x, const float* w, const float* bias, bf16* y,
                         int64_t n_crops, cudaStream_t s);
 
+// ---- operand format and gating of the fused kernels -------------------------------------------------------------------------
+// The 16-bit modes run the same fused kernels in one of two operand formats: fp16 (CV_PRECISION_FP16: 11-bit significands, one
+// weight image, half the MMAs) or bf16 (W = W_hi + W_lo in stages B / C).  fp16 can overflow (|v| > 65504): the fp16 kernels raise
+// `ovf` when a non-finite value reaches a residual-stream copy, and a forward in fp16 mode enqueues BOTH chains per wave -- the
+// fp16 kernels gated on *flag == 0, then the bf16 kernels gated on *flag != 0 -- so the fall-back needs no host synchronisation
+// (a gated-off persistent kernel exits in its first instruction).
+struct StageGate {
+    bool f16 = false;             // operand format of this launch
+    const int* flag = nullptr;    // null: run unconditionally
+    int want = 0;                 // run iff (*flag != 0) == want
+    int* ovf = nullptr;           // fp16 launches: the overflow flag to raise (== flag)
+};
+
 // ---- kernels_frontend.cu: fused crop gather + conv_stem + blocks.0.0 (tcgen05), output T8 [crops*256][16] ----
 enum { CV_SRC_U8_HWC = 0, CV_SRC_U8_CHW = 1, CV_SRC_F32_NCHW = 2 };
 size_t frontend_weight_image_elems();
 int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s);
 int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev,
                     const bf16* wimg, const float* bias_stem, const float* bias_b00, bf16* y, int num_sms,
-                    cudaStream_t s, const int* run_flag = nullptr);
+                    cudaStream_t s, const int* run_flag = nullptr, const StageGate& gate = StageGate());
 
 // ---- kernels_backend.cu: fused back-end stages (persistent tcgen05 kernels, activations in smem / TMEM) -----------------
 // stage D = blocks.3.* + blocks.4.0 + average pool + type/color heads + combine.  Input: "P8" tiles (128 rows = 8 crops,
 // row = pixel*8 + crop_local, 48 channels, T8 chunking); output: features [crops][480] fp32, squares [crops][13] fp32.
 enum { CV_STAGE_D_OPS = 24 };
 size_t stageD_image_bytes();
-int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
+int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag /* non-null: fp16 images */, cudaStream_t s);
 int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, cudaStream_t s);
 // features: row-major [crops][480] (tiled == 0, indexed from this launch's first crop) or the FT operand layout of the
 // tensor-core global head (tiled == 1: `features` is the chunk's FT base and crop_base the launch's first crop in the chunk).
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes,
-                  float* features, int tiled, int64_t crop_base, float* squares, int num_sms, cudaStream_t s);
+                  float* features, int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate, cudaStream_t s);
 
 // stage C = blocks.2.* (19 conv layers).  Input: "P2" tiles (128 rows = 2 crops at 8x8, row = pixel*2 + crop_local, 32 ch);
 // output: the P8 tiles stage D consumes.
 enum { CV_STAGE_C_OPS = 20 };
 size_t stageC_image_bytes();
-int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s);
+int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag, cudaStream_t s);
 int launch_permute_p2(const bf16* in_t8, bf16* out_p2, int64_t n_crops, int C, cudaStream_t s);
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8,
-                  int num_sms, int split /* two independent 8-crop warp groups per CTA */, cudaStream_t s);
+                  int num_sms, const StageGate& gate, cudaStream_t s);
 
 // stage B = blocks.0.1 + blocks.1.0 + blocks.1.1.  Input: the front end's T8 output (rows = crop*256 + pixel, 16 ch); output: P2 tiles.
 size_t stageB_image_bytes();
-int build_stageB_image(const float* blob, uint8_t* img, cudaStream_t s);
-int launch_stageB(const bf16* x_t8, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, cudaStream_t s);
+int build_stageB_image(const float* blob, uint8_t* img, int* f16_flag, cudaStream_t s);
+int launch_stageB(const bf16* x_t8, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, const StageGate& gate, cudaStream_t s);
 
 // ---- kernels_head.cu: global_head as a split-K tcgen05 (kind::tf32) GEMM over FT-tiled features -----------------------------
-//   FT[m_tile][k/4][128 boards][4]: float index ((b/128 * 7680 + k/4) * 128 + b%128) * 4 + k%4,  k = square*480 + channel
-inline size_t ft_floats(int boards) { return (size_t)((boards + 127) / 128) * 128 * 30720; }
+//   FT[m_tile][plane][k/4][128 boards][4]: float index (((b/128 * 2 + plane) * 7680 + k/4) * 128 + b%128) * 4 + k%4,  k = square*480 + channel;
+//   plane 0 = x & 0xffffe000 (what the tensor core reads of a tf32 operand), plane 1 = the exact remainder
+inline size_t ft_floats(int boards) { return (size_t)((boards + 127) / 128) * 128 * 30720 * 2; }
 int launch_tile_glob_w(const float* glob_w, float* wt, cudaStream_t s);
 size_t global_head_partial_floats(int B, int num_sms);
 int launch_global_head_umma(const float* ft, const float* wt, float* partial, const float* glob_b, const float* tc_w, const float* tc_b,
                             int B, int num_sms, float* turn, float* castling, cudaStream_t s);
 int launch_untile_features(const float* ft, float* out_rowmajor, int B, cudaStream_t s);
 
-// ---- kernels_frontend2.cu: second-generation fused front end for uint8 HWC boards (TMA-staged windows, separable resize) ----
-size_t frontend2_weight_image_elems();
-int launch_frontend2_prep_weights(const float* blob, bf16* img, cudaStream_t s);
-int launch_frontend2(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const bf16* wimg,
-                     const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s);
-
 // ---- kernels_frontend3.cu: third generation (column-slab M tiles, fp16 stem operands, pipelined half images) ---------------
+// out_f16: the stem output image, the blocks.0.0 weights and the T8 output are fp16 (bf16 otherwise); the weight image holds both
+// blocks.0.0 variants.  skip_flag / gate: the kernel exits at once when *skip_flag != 0, or when gate says so (StageGate).
 size_t frontend3_weight_image_bytes();
 int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s);
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
-                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag = nullptr);
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag = nullptr,
+                     const StageGate& gate = StageGate());
 // float NCHW boards that are Normalize(ToTensor(uint8)) -> the uint8 HWC image + a device flag (1 = some value is not on the uint8 grid)
 int launch_f32_to_u8_boards(const float* x_nchw, int nb, int H, const float* lut_host, uint8_t* out_hwc, int* flag_dev, cudaStream_t s);

@@ -29,36 +29,34 @@ using namespace umma;
 
 constexpr int NT = 512;                 // 16 warps: warp w -> TMEM lane quadrant w&3, column slice w>>2
 
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
 // Two fp32 FMAs in one instruction (FFMA2, sm_100+): same FMA-pipe throughput as two FFMAs but ONE issue slot -- the depthwise
 // loops are issue-bound (FMAs share the slots with loads, conversions and packs), so this is where their time goes down.
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
-__device__ __forceinline__ float2 bf2(uint32_t packed) { return make_float2(__uint_as_float(packed << 16), __uint_as_float(packed & 0xffff0000u)); }
+// Every device function below is templated on the 16-bit operand format of the stage (umma.cuh: F16 = fp16, else bf16).
+template <bool F16>
 __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
-    f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
-    f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
-    f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
-    f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+    const float2 a = up2<F16>(v.x), b = up2<F16>(v.y), c = up2<F16>(v.z), d = up2<F16>(v.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+template <bool F16>
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-    return make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+    return make_uint4(pk2<F16>(f[0], f[1]), pk2<F16>(f[2], f[3]), pk2<F16>(f[4], f[5]), pk2<F16>(f[6], f[7]));
 }
 __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 // One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
-// A: shared-memory operand tile [K/8][128 rows][8] bf16 (K-major, no swizzle; LBO 2048 B, SBO 128 B).
-// B: weight image [K/8][n_total][8] bf16, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
-// w_parts = 2: the image is W_hi followed by W_lo (W = W_hi + W_lo, both bf16): two MMAs per k-step on the same A.
+// A: shared-memory operand tile [K/8][128 rows][8] 16-bit (K-major, no swizzle; LBO 2048 B, SBO 128 B).
+// B: weight image [K/8][n_total][8] 16-bit, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
+// w_parts = 2 (bf16 stages B / C): the image is W_hi followed by W_lo (W = W_hi + W_lo, both bf16): two MMAs per k-step on the
+// same A.  fp16 weights carry 11 significant bits and need no second image.
+template <bool F16>
 __device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_addr, int n_total, int n0, int n, uint32_t d_tmem,
                                            bool accumulate, int w_parts = 1) {
-    const uint32_t idesc = make_idesc_bf16(128, n);
+    const uint32_t idesc = make_idesc_16<F16>(128, n);
     const uint32_t b_lbo = (uint32_t)n_total * 16u;
     const uint32_t part_rows = ((uint32_t)K * (uint32_t)n_total * 2u) >> 4;           // descriptor words count 16-byte units
     uint32_t a_lo = desc_lo(a_addr, 2048u), b_lo = desc_lo(b_addr + (uint32_t)n0 * 16u, b_lbo);
@@ -68,11 +66,13 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_addr, int K, uint32_t b_ad
             mma_f16_ss2(d_tmem, a_lo, hi, b_lo + part * part_rows, hi, idesc, (accumulate || k > 0 || part > 0) ? 1u : 0u);
 }
 
-// TMEM accumulator columns [col0, col0+ncols) of this thread's row -> (+bias, ReLU) -> bf16 -> operand tile
+// TMEM accumulator columns [col0, col0+ncols) of this thread's row -> (+bias, ReLU) -> 16-bit -> operand tile
 // dst[(chunk0 + col/8)][row][8].  The 16-column groups are dealt round-robin to the 4 column-slice warps.
-template <bool RELU>
+// fp16 without ReLU (the copies of the fp32 residual stream): `bad` collects non-finite results -- the residual stream lives in
+// TMEM in fp32 for the whole stage, so whatever overflowed anywhere in a block ends up in one of these copies.
+template <bool F16, bool RELU>
 __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, const float* bias, uint8_t* dst, int chunk0, int row,
-                                            int cs, int n_slices = 4) {
+                                            int cs, int n_slices, uint32_t& bad) {
     for (int g = cs; g < (ncols >> 4); g += n_slices) {
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
@@ -83,8 +83,9 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
             load8(bias + g * 16 + j * 8, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
-            *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) =
-                RELU ? make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7])) : pack8(v);
+            const uint4 o = RELU ? make_uint4(pk2r<F16>(v[0], v[1]), pk2r<F16>(v[2], v[3]), pk2r<F16>(v[4], v[5]), pk2r<F16>(v[6], v[7])) : pack8<F16>(v);
+            if (F16 && !RELU) bad |= f16x2_nonfinite(o.x) | f16x2_nonfinite(o.y) | f16x2_nonfinite(o.z) | f16x2_nonfinite(o.w);
+            *reinterpret_cast<uint4*>(dst + (((size_t)(chunk0 + g * 2 + j) * 128 + row) << 4)) = o;
         }
     }
 }
@@ -94,7 +95,7 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
 // a half warp reads 128 contiguous bytes per pixel), converts it once, computes all 16 outputs from registers (static border
 // handling: no branches, every load issued up front) and writes them back over its own inputs -- no other thread touches those
 // bytes, so no synchronisation is needed.  Against one task per output: 1.9x fewer instructions, 3x fewer LSU wavefronts.
-template <bool RELU>
+template <bool F16, bool RELU>
 __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, int n_tasks, int C8, const float* w, const float* bias, int tid,
                                             int nt = NT) {
     const int C = C8 * 8;
@@ -112,7 +113,7 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
         const float4 b = *reinterpret_cast<const float4*>(bias + c * 8 + half * 4);
         float2 x[16][2];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { x[p][0] = bf2(in[p].x); x[p][1] = bf2(in[p].y); }
+        for (int p = 0; p < 16; ++p) { x[p][0] = up2<F16>(in[p].x); x[p][1] = up2<F16>(in[p].y); }
 #pragma unroll
         for (int oy = 0; oy < 4; ++oy) {
 #pragma unroll
@@ -131,8 +132,8 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
                     }
                 }
                 uint2 o;
-                if (RELU) { o.x = pack2_relu(a01.x, a01.y); o.y = pack2_relu(a23.x, a23.y); }
-                else { o.x = pack2(a01.x, a01.y); o.y = pack2(a23.x, a23.y); }
+                if (RELU) { o.x = pk2r<F16>(a01.x, a01.y); o.y = pk2r<F16>(a23.x, a23.y); }
+                else { o.x = pk2<F16>(a01.x, a01.y); o.y = pk2<F16>(a23.x, a23.y); }
                 *reinterpret_cast<uint2*>(base + (oy * 4 + ox) * 128) = o;
             }
         }
@@ -143,6 +144,7 @@ __device__ __forceinline__ void dw3x3_p8_rt(const uint8_t* src, uint8_t* buf, in
 // 2x2 tile of 32 crops), chunks chunk0 + c of a [.][128][8] tile.
 // Register tiled: task = (chunk, crop, channel half) loads the crop's whole 4x4 map of 4 channels once (a half
 // warp reads 128 contiguous bytes per pixel), converts it once and computes the four stride-2 outputs with static border handling.
+template <bool F16>
 __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, int C8, int C_total, int chunk0, int crop0, const float* w,
                                               const float* bias, int tid) {
     for (int task = tid; task < 16 * C8; task += NT) {
@@ -158,7 +160,7 @@ __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, 
         const float4 b = *reinterpret_cast<const float4*>(bias + cg * 8 + half * 4);
         float2 x[16][2];
 #pragma unroll
-        for (int p = 0; p < 16; ++p) { x[p][0] = bf2(in[p].x); x[p][1] = bf2(in[p].y); }
+        for (int p = 0; p < 16; ++p) { x[p][0] = up2<F16>(in[p].x); x[p][1] = up2<F16>(in[p].y); }
         uint8_t* dbase = dst + (((size_t)cg * 128 + crop0 + crop) << 4) + half * 8;
 #pragma unroll
         for (int oy = 0; oy < 2; ++oy) {
@@ -177,7 +179,7 @@ __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, 
                         a23 = fma2(x[iy * 4 + ix][1], hi2(wt[ky * 3 + kx]), a23);
                     }
                 }
-                *reinterpret_cast<uint2*>(dbase + (oy * 2 + ox) * 512) = make_uint2(pack2_relu(a01.x, a01.y), pack2_relu(a23.x, a23.y));
+                *reinterpret_cast<uint2*>(dbase + (oy * 2 + ox) * 512) = make_uint2(pk2r<F16>(a01.x, a01.y), pk2r<F16>(a23.x, a23.y));
             }
         }
     }
@@ -188,13 +190,14 @@ __device__ __forceinline__ void dw3x3s2_p8_rt(const uint8_t* src, uint8_t* dst, 
 // on a 2x2 map) and writes them back -- no other thread touches these 64 bytes, so no synchronisation is needed; a warp
 // is 32 crops of one chunk, so activation accesses are contiguous and the weight reads are warp-uniform broadcasts.
 // Weights: wq[chunk][p][q][8] fp32 = tap (q - p) of the KxK filter for output pixel p / input pixel q (prep_dw2x2_kernel).
+template <bool F16>
 __device__ __forceinline__ void dw2x2_pm(uint8_t* buf, int C8, const float* wq, const float* bias, bool relu, int tid) {
     for (int task = tid; task < 32 * C8; task += NT) {
         const int c = task >> 5, crop = task & 31;
         uint8_t* base = buf + (((size_t)c * 128 + crop) << 4);
         float x[4][8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) unpack8(*reinterpret_cast<const uint4*>(base + q * 512), x[q]);
+        for (int q = 0; q < 4; ++q) unpack8<F16>(*reinterpret_cast<const uint4*>(base + q * 512), x[q]);
         float b[8];
         load8(bias + c * 8, b);
         const float* wc = wq + c * 128;
@@ -214,7 +217,7 @@ __device__ __forceinline__ void dw2x2_pm(uint8_t* buf, int C8, const float* wq, 
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
             }
-            *reinterpret_cast<uint4*>(base + pp * 512) = pack8(acc);
+            *reinterpret_cast<uint4*>(base + pp * 512) = pack8<F16>(acc);
         }
     }
 }
@@ -250,14 +253,20 @@ struct StageDParams {
     long long crop_base;      // tiled: index of this launch's first crop inside the chunk that `features` (FT base) covers
     uint32_t off[sd::NOPS], bytes[sd::NOPS];
     int debug;                // CV_SD_DEBUG ablation bits (timing experiments only: results are wrong)
+    const int* gate;          // non-null: the kernel runs only when (*gate != 0) == gate_want (fp16 pass: want 0; bf16 fall-back pass: want 1)
+    int gate_want;
+    int* ovf;                 // fp16 pass: set to 1 when a residual-stream value left the fp16 range (the bf16 pass then redoes the wave)
 };
 
 __constant__ int kTypeOf[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6};     // dataset.py:31
 __constant__ int kColorOf[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};    // dataset.py:32
 
+template <bool F16>
 __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ StageDParams p) {
     using namespace sd;
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;      // uniform over the grid up to races that only skip redundant work
+    uint32_t bad = 0;
     uint8_t* IN = smem + OFF_IN;
     uint8_t* A24 = smem + OFF_A24;
     uint8_t* EH = smem + OFF_EH;
@@ -344,19 +353,19 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             if (tid == 0 && t < 3) load_in(tile, t + 1);
             wait_in(t & 1);
             const uint8_t* in = IN + (t & 1) * 12288;
-            if (!(p.debug & 1)) dw3x3_p8_rt<false>(in, A24, 6 * 16, 6, w24, b24, tid);    // L24 dw_start (no act)
+            if (!(p.debug & 1)) dw3x3_p8_rt<F16, false>(in, A24, 6 * 16, 6, w24, b24, tid);    // L24 dw_start (no act)
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                issue_gemm(smem_u32(A24), 48, w25, 288, 0, 144, tmem, false);             // L25 pw_exp 48 -> 288
-                issue_gemm(smem_u32(A24), 48, w25, 288, 144, 144, tmem + 144, false);
+                issue_gemm<F16>(smem_u32(A24), 48, w25, 288, 0, 144, tmem, false);             // L25 pw_exp 48 -> 288
+                issue_gemm<F16>(smem_u32(A24), 48, w25, 288, 144, 144, tmem + 144, false);
                 mma_commit(mbar);
             }
             wait_mma();
             for (int h = 0; h < 2; ++h) {
-                epi_to_tile<true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs);
+                epi_to_tile<F16, true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs, 4, bad);
                 __syncthreads();
-                if (!(p.debug & 2)) dw3x3s2_p8_rt(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                if (!(p.debug & 2)) dw3x3s2_p8_rt<F16>(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
                 __syncthreads();
             }
         }
@@ -368,12 +377,12 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                issue_gemm(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
+                issue_gemm<F16>(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
                 mma_commit(mbar);
                 if (op + 1 < NOPS) prefetch(op + 1);
             }
             wait_mma();
-            epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);
+            epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
             __syncthreads();
             ++op;
         }
@@ -383,7 +392,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             if (blk == 1) {                      // L28 blocks.3.1.dw_start 5x5 on the block input (no act)
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                if (!(p.debug & 4)) dw2x2_pm(X16, 8, b + 64, b, false, tid);
+                if (!(p.debug & 4)) dw2x2_pm<F16>(X16, 8, b + 64, b, false, tid);
                 __syncthreads();
                 ++op;
             }
@@ -392,19 +401,19 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 sync_before_mma();
                 if (warp == 0 && elect_one()) {
                     tc_fence_after();
-                    issue_gemm(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
+                    issue_gemm<F16>(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
                     mma_commit(mbar);
                     if (op + 1 < NOPS) prefetch(op + 1);
                 }
                 wait_mma();
-                epi_to_tile<true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs);
+                epi_to_tile<F16, true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs, 4, bad);
                 __syncthreads();
                 ++op;
             }
             {   // dw_mid 5x5 / 3x3 (+ReLU), in place
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
-                if (!(p.debug & 4)) dw2x2_pm(BIG, cexp >> 3, b + cexp, b, true, tid);
+                if (!(p.debug & 4)) dw2x2_pm<F16>(BIG, cexp >> 3, b + cexp, b, true, tid);
                 __syncthreads();                 // every warp is done with this slot's weights before the next prefetch targets it
                 ++op;
             }
@@ -413,12 +422,12 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 sync_before_mma();
                 if (warp == 0 && elect_one()) {
                     tc_fence_after();
-                    issue_gemm(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
+                    issue_gemm<F16>(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
                     mma_commit(mbar);
                     if (op + 1 < NOPS) prefetch(op + 1);
                 }
                 wait_mma();
-                epi_to_tile<false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs);   // + cumulative bias
+                epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);   // + cumulative bias
                 __syncthreads();
                 ++op;
             }
@@ -429,7 +438,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             sync_before_mma();
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                issue_gemm(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
+                issue_gemm<F16>(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
                 mma_commit(mbar);
                 if (op + 1 < NOPS) prefetch(op + 1);
             }
@@ -468,8 +477,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                     const long long cg = p.crop_base + crop;
                     const long long b = cg >> 6;
                     const int sq = (int)(cg & 63);
-                    reinterpret_cast<float4*>(p.features)[((b >> 7) * 7680 + sq * 120 + (ch >> 2)) * 128 + (b & 127)] =
-                        make_float4(f4[0], f4[1], f4[2], f4[3]);
+                    // two planes for the split-tf32 GEMM of the global head: hi = what a tf32 operand keeps, lo = the exact remainder
+                    float hi4[4], lo4[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { hi4[i] = __uint_as_float(__float_as_uint(f4[i]) & 0xffffe000u); lo4[i] = f4[i] - hi4[i]; }
+                    float4* ftp = reinterpret_cast<float4*>(p.features) + (((b >> 7) * 2) * 7680 + sq * 120 + (ch >> 2)) * 128 + (b & 127);
+                    ftp[0] = make_float4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    ftp[7680 * 128] = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
                 } else {
                     *reinterpret_cast<float4*>(p.features + crop * 480 + ch) = make_float4(f4[0], f4[1], f4[2], f4[3]);
                 }
@@ -503,6 +517,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             }
         }
     }
+    if (F16 && bad != 0) atomicOr(p.ovf, 1);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -512,8 +527,10 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 // =====================================================================================================================
 // stage C: blocks.2.0 .. blocks.2.5 (19 conv layers), 8x8 -> 4x4 maps.  Tile = 16 crops.
 // =====================================================================================================================
-// TMEM accumulator columns -> (+bias) -> bf16 -> global T8-chunked tile dst[chunk][128 rows][8] (coalesced 16-byte stores).
-__device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int row, int cs, int n_slices) {
+// TMEM accumulator columns -> (+bias) -> 16-bit -> global T8-chunked tile dst[chunk][128 rows][8] (coalesced 16-byte stores).
+template <bool F16>
+__device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int row, int cs, int n_slices,
+                                              uint32_t& bad) {
     for (int g = cs; g < (ncols >> 4); g += n_slices) {
         uint32_t r[16];
         tmem_ld16(trow + (uint32_t)(col0 + g * 16), r);
@@ -524,7 +541,9 @@ __device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols
             load8(bias + g * 16 + j * 8, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
-            dst[(size_t)(g * 2 + j) * 128 + row] = pack8(v);
+            const uint4 o = pack8<F16>(v);
+            if (F16) bad |= f16x2_nonfinite(o.x) | f16x2_nonfinite(o.y) | f16x2_nonfinite(o.z) | f16x2_nonfinite(o.w);
+            dst[(size_t)(g * 2 + j) * 128 + row] = o;
         }
     }
 }
@@ -538,6 +557,7 @@ __device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols
 
 // blocks.2.0.dw_start: 5x5 stride 1, 32 channels, no activation.  src = stage input of the whole tile: 8 sub-tiles (2 crops each)
 // x [64 pixels][4 chunks][2 crops][8 ch]  ("P2X").  dst = 8 operand images [4 chunks][128 rows = pixel*2 + crop][8 ch].
+template <bool F16>
 __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, const float* w, const float* bias, int tid) {
 #pragma unroll 1
     for (int task = tid; task < 1024; task += NT) {
@@ -560,7 +580,7 @@ __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, con
             for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 32 + coff);
             float2 xv[8][2];
 #pragma unroll
-            for (int x = 0; x < 8; ++x) { xv[x][0] = bf2(in[x].x); xv[x][1] = bf2(in[x].y); }
+            for (int x = 0; x < 8; ++x) { xv[x][0] = up2<F16>(in[x].x); xv[x][1] = up2<F16>(in[x].y); }
 #pragma unroll
             for (int ox = 0; ox < 8; ++ox) {
 #pragma unroll
@@ -574,7 +594,7 @@ __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, con
         }
         uint8_t* dp = dst + t * 8192 + (l >> 2) * 2048 + ((l >> 1) & 1) * 16 + (l & 1) * 8 + y * 8 * 32;
 #pragma unroll
-        for (int ox = 0; ox < 8; ++ox) *reinterpret_cast<uint2*>(dp + ox * 32) = make_uint2(pack2(acc[ox][0].x, acc[ox][0].y), pack2(acc[ox][1].x, acc[ox][1].y));
+        for (int ox = 0; ox < 8; ++ox) *reinterpret_cast<uint2*>(dp + ox * 32) = make_uint2(pk2<F16>(acc[ox][0].x, acc[ox][0].y), pk2<F16>(acc[ox][1].x, acc[ox][1].y));
     }
 }
 
@@ -584,6 +604,7 @@ __device__ __forceinline__ void dw5x5_rows(const uint8_t* src, uint8_t* dst, con
 __device__ __forceinline__ int e6_off(int pix, int chunk, int crop) { return pix * 384 + (((chunk ^ (pix & 3)) << 1) | crop) * 16; }
 
 // TMEM accumulator columns [col0, col0+96) of this thread's row (= pixel*2 + crop) -> (+bias, ReLU) -> bf16 -> E6.
+template <bool F16>
 __device__ __forceinline__ void epi_to_e6(uint32_t trow, int col0, const float* bias, uint8_t* dst, int row, int cs, int n_slices) {
     const int pix = row >> 1, crop = row & 1;
     for (int g = cs; g < 6; g += n_slices) {
@@ -597,13 +618,14 @@ __device__ __forceinline__ void epi_to_e6(uint32_t trow, int col0, const float* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
             *reinterpret_cast<uint4*>(dst + e6_off(pix, g * 2 + j, crop)) =
-                make_uint4(pack2_relu(v[0], v[1]), pack2_relu(v[2], v[3]), pack2_relu(v[4], v[5]), pack2_relu(v[6], v[7]));
+                make_uint4(pk2r<F16>(v[0], v[1]), pk2r<F16>(v[2], v[3]), pk2r<F16>(v[4], v[5]), pk2r<F16>(v[6], v[7]));
         }
     }
 }
 
 // blocks.2.0.dw_mid: 5x5 stride 2 (+ReLU) 8x8 -> 4x4, 96 channels, over two sub-tiles (4 crops): src0 / src1 in the E6 layout ->
 // dst P8 tile rows opix*8 + crop0 + 2*sub + crop of [12 chunks][128][8 ch].  384 tasks = (sub, output row, 4 channels).
+template <bool F16>
 __device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t* src1, uint8_t* dst, int crop0, const float* w, const float* bias,
                                              int tid) {
     if (tid >= 384) return;
@@ -627,7 +649,7 @@ __device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t*
         for (int kx = 0; kx < 5; ++kx) wt[kx] = *reinterpret_cast<const float4*>(w + (ky * 5 + kx) * 96 + coff);
         float2 xv[8][2];
 #pragma unroll
-        for (int x = 0; x < 8; ++x) { xv[x][0] = bf2(in[x].x); xv[x][1] = bf2(in[x].y); }
+        for (int x = 0; x < 8; ++x) { xv[x][0] = up2<F16>(in[x].x); xv[x][1] = up2<F16>(in[x].y); }
 #pragma unroll
         for (int ox = 0; ox < 4; ++ox) {
 #pragma unroll
@@ -641,7 +663,7 @@ __device__ __forceinline__ void dw5x5s2_rows(const uint8_t* src0, const uint8_t*
     }
     uint8_t* dp = dst + chunk * 2048 + (oy * 4 * 8 + crop0 + 2 * sub + crop) * 16 + half * 8;
 #pragma unroll
-    for (int ox = 0; ox < 4; ++ox) *reinterpret_cast<uint2*>(dp + ox * 128) = make_uint2(pack2_relu(acc[ox][0].x, acc[ox][0].y), pack2_relu(acc[ox][1].x, acc[ox][1].y));
+    for (int ox = 0; ox < 4; ++ox) *reinterpret_cast<uint2*>(dp + ox * 128) = make_uint2(pk2r<F16>(acc[ox][0].x, acc[ox][0].y), pk2r<F16>(acc[ox][1].x, acc[ox][1].y));
 }
 
 namespace sc {
@@ -670,6 +692,9 @@ struct StageCParams {
     uint32_t off[sc::NOPS], bytes[sc::NOPS];
     int debug;                // CV_SC_DEBUG ablation bits (timing experiments only: results are wrong): 1 no dw5x5, 2 no dw5x5s2, 4 no dw3x3,
                               // 32 no MMA / epilogue in the 4x4 phase (what is left is the per-op barrier + weight-stream cost), 256 section timers
+    const int* gate;          // non-null: the kernel runs only when (*gate != 0) == gate_want (fp16 pass: want 0; bf16 fall-back pass: want 1)
+    int gate_want;
+    int* ovf;                 // fp16 pass: set to 1 when a residual-stream value left the fp16 range (the bf16 pass then redoes the wave)
 };
 
 // Timing experiments (-DCV_SC_PROFILE, CV_SC_DEBUG & 256): cycles thread 0 of CTA 0 spends per section of a tile
@@ -682,9 +707,13 @@ __device__ unsigned long long g_sc_prof[40];
 #define SC_MARK(k)
 #endif
 
+template <bool F16>
 __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ StageCParams p) {
     using namespace sc;
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;
+    uint32_t bad = 0;
+    constexpr int WP = F16 ? 1 : 2;                 // weight images per pointwise blob: fp16 W | bf16 W_hi, W_lo
     uint8_t* IN = smem + OFF_IN;
     uint8_t* A5 = smem + OFF_A5;
     uint8_t* R = smem + OFF_R;
@@ -790,23 +819,23 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         if (tid == 0) { prefetch(3); prefetch(4); }     // first two ops of the 4x4 phase -> slots 1, 2 while the 8x8 phase runs
         mbar_wait(inbar, inph); inph ^= 1u;
         SC_MARK(0);
-        if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
+        if (!(p.debug & 1)) dw5x5_rows<F16>(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
         sync_before_mma();
         SC_MARK(1);
         for (int j = 0; j < 4; ++j) {
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)                                                  // L6 pw_exp 32 -> 96 on sub-tiles 2j, 2j+1
-                    issue_gemm(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 96 * m, false, 2);
+                    issue_gemm<F16>(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 96 * m, false, WP);
                 mma_commit(mbar);
             }
             wait_mma();
             SC_MARK(2);
-            epi_to_e6(trow, ACC + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
+            epi_to_e6<F16>(trow, ACC + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
             tc_fence_before();
             __syncthreads();
             SC_MARK(3);
-            if (!(p.debug & 2)) dw5x5s2_rows(E6, X16, A7 + (j >> 1) * 24576, (4 * j) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
+            if (!(p.debug & 2)) dw5x5s2_rows<F16>(E6, X16, A7 + (j >> 1) * 24576, (4 * j) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
             __syncthreads();
             SC_MARK(4);
         }
@@ -818,16 +847,16 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m) {
-                    issue_gemm(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, 2);
+                    issue_gemm<F16>(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) {
                 wait_mma();
-                epi_to_tile<false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4);
+                epi_to_tile<F16, false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
                 wait_mma2();
-                epi_to_tile<false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4);
+                epi_to_tile<F16, false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4, bad);
             }
             __syncthreads();
             SC_MARK(8 + op); ++op;
@@ -840,16 +869,16 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m) {
-                        issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
+                        issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, WP);
                         mma_commit(m ? mbar2 : mbar);
                     }
                     if (op + 2 < NOPS) prefetch(op + 2);
                 }
                 if (!(p.debug & 32)) {
                     wait_mma();
-                    epi_to_tile<true>(trow, ACC, 96, reinterpret_cast<const float*>(wb), R, 0, row, cs, 4);
+                    epi_to_tile<F16, true>(trow, ACC, 96, reinterpret_cast<const float*>(wb), R, 0, row, cs, 4, bad);
                     wait_mma2();
-                    epi_to_tile<true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb), R + 24576, 0, row, cs2, 4);
+                    epi_to_tile<F16, true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb), R + 24576, 0, row, cs2, 4, bad);
                 }
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
@@ -857,7 +886,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
                 uint8_t* wb = begin_op(op, true);
                 const float* b = reinterpret_cast<const float*>(wb);
-                if (!(p.debug & 4)) dw3x3_p8_rt<true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
+                if (!(p.debug & 4)) dw3x3_p8_rt<F16, true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
@@ -867,16 +896,16 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m) {
-                        issue_gemm(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+                        issue_gemm<F16>(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, WP);
                         mma_commit(m ? mbar2 : mbar);
                     }
                     if (op + 2 < NOPS) prefetch(op + 2);
                 }
                 if (!(p.debug & 32)) {
                     wait_mma();
-                    epi_to_tile<false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4);
+                    epi_to_tile<F16, false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
                     wait_mma2();
-                    epi_to_tile<false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4);
+                    epi_to_tile<F16, false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4, bad);
                 }
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
@@ -888,21 +917,21 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
             uint8_t* wb = begin_op(op, false);
             const float* b21 = reinterpret_cast<const float*>(wb);
-            if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16, X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
+            if (!(p.debug & 4)) dw3x3_p8_rt<F16, false>(X16, X16, 2 * 6 * 16, 6, b21 + 48, b21, tid);
             sync_before_mma();
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m) {
-                    issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, 2);
+                    issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) {
                 wait_mma();
-                epi_to_tile<true>(trow, ACC, 96, reinterpret_cast<const float*>(wb + 1920), E22a, 0, row, cs, 4);
+                epi_to_tile<F16, true>(trow, ACC, 96, reinterpret_cast<const float*>(wb + 1920), E22a, 0, row, cs, 4, bad);
                 wait_mma2();
-                epi_to_tile<true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb + 1920), E22a + 24576, 0, row, cs2, 4);
+                epi_to_tile<F16, true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb + 1920), E22a + 24576, 0, row, cs2, 4, bad);
             }
             __syncthreads();
             SC_MARK(8 + op); ++op;
@@ -913,16 +942,16 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m) {
-                    issue_gemm(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, 2);
+                    issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
                 if (op + 2 < NOPS) prefetch(op + 2);
             }
             if (!(p.debug & 32)) {
                 wait_mma();
-                epi_to_tile<true>(trow, ACC + 192, 96, reinterpret_cast<const float*>(wb), E22b, 0, row, cs, 4);
+                epi_to_tile<F16, true>(trow, ACC + 192, 96, reinterpret_cast<const float*>(wb), E22b, 0, row, cs, 4, bad);
                 wait_mma2();
-                epi_to_tile<true>(trow, ACC + 192 + 96, 96, reinterpret_cast<const float*>(wb), E22b + 24576, 0, row, cs2, 4);
+                epi_to_tile<F16, true>(trow, ACC + 192 + 96, 96, reinterpret_cast<const float*>(wb), E22b + 24576, 0, row, cs2, 4, bad);
             }
             __syncthreads();
             SC_MARK(8 + op); ++op;
@@ -935,7 +964,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 tc_fence_after();
                 for (int m = 0; m < 2; ++m)
-                    issue_gemm(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+                    issue_gemm<F16>(smem_u32(E22a + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, WP);
             }
             SC_MARK(8 + op); ++op;
         }
@@ -943,12 +972,12 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
             uint8_t* wb = begin_op(op, false);
             if (!(p.debug & 32) && warp == 0 && elect_one()) {
                 for (int m = 0; m < 2; ++m)
-                    issue_gemm(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, 2);
+                    issue_gemm<F16>(smem_u32(E22b + m * 24576), 96, smem_u32(wb), 48, 0, 48, tmem + S_COL + 48 * m, true, WP);
                 mma_commit(mbar);
             }
             if (!(p.debug & 32)) wait_mma();
             uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + mt) * 6 * 128;
-            if (!(p.debug & 32)) epi_to_global(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2);
+            if (!(p.debug & 32)) epi_to_global<F16>(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2, bad);
             SC_MARK(8 + op); ++op;
         }
         const int next = tile + gridDim.x;
@@ -962,261 +991,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 #ifdef CV_SC_PROFILE
     if (prof_on) for (int i = 0; i < 40; ++i) g_sc_prof[i] = (unsigned long long)pacc[i];
 #endif
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
-
-// =====================================================================================================================
-// stage C, warp-group version: the same 19 layers, but the two 8-crop halves of a tile run as two INDEPENDENT op chains, one per
-// group of 8 warps (own named barrier, own MMA-completion mbarrier, own buffers and TMEM columns).  The per-section timers of
-// the op-synchronous kernel showed every pointwise op costing 2.4-2.7 k cycles for 0.5-1 k cycles of tensor-pipe work (issue
-// -> completion -> wake-up -> epilogue -> barrier, all 16 warps in lock step): with two chains one group's MMA round trip runs
-// under the other group's epilogue / depthwise work.  Weights are shared: a 17th warp streams them two ops ahead through the
-// three-slot ring and recycles a slot when BOTH groups have released it (mbarrier with two arrivals).
-//   buffers of group g:  A5 half g (4 sub-tile images) | E6_g = g ? X16 region : R[0:24K] (8x8 phase; its first 12 KB hold the
-//   group's block-input tile in the 4x4 phase) | A7_g = R + 24576 (1 + g) (8x8 -> 4x4 hand-off, then the expanded tile E) |
-//   E22b_g = A5 half g (blocks.2.5 second half; A5 is dead by then).  TMEM: accumulators 192 g .., residual stream 400 + 48 g.
-// =====================================================================================================================
-namespace sc2 {
-constexpr int NTH = 17 * 32;
-constexpr int OFF_BAR = sc::OFF_W + sc::W_ARENA;
-constexpr int SMEM = OFF_BAR + 128;
-}  // namespace sc2
-
-__global__ void __launch_bounds__(sc2::NTH, 1) stageC2_kernel(const __grid_constant__ StageCParams p) {
-    using namespace sc;
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* IN = smem + OFF_IN;
-    uint8_t* A5 = smem + OFF_A5;
-    uint8_t* R = smem + OFF_R;
-    uint8_t* X16 = smem + OFF_X16;
-    uint8_t* WA = smem + OFF_W;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sc2::OFF_BAR);
-    uint64_t *wbar = bars /*3: slot full*/, *wdone = bars + 3 /*3: slot released by both groups*/, *inbar = bars + 6, *mbarg = bars + 7 /*2*/;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-    if (tid == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(wbar + i, 1); mbar_init(wdone + i, 2); }
-        mbar_init(inbar, 1); mbar_init(mbarg, 1); mbar_init(mbarg + 1, 1);
-        fence_barrier_init();
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    auto slot_of = [&](int op) { return (op - 2) % 3; };
-    auto slot_ptr = [&](int slot) { return WA + (slot == 0 ? 0 : slot == 1 ? W_SLOT1 : W_SLOT2); };
-
-    if (warp == 16) {
-        // =========================== weight / input producer ===================================================================
-        auto prefetch = [&](int op) {
-            const int sl = slot_of(op);
-            mbar_arrive_expect_tx(wbar + sl, p.bytes[op]);
-            bulk_g2s(slot_ptr(sl), p.wimg + p.off[op], p.bytes[op], wbar + sl);
-        };
-        auto load_tile = [&](int tile) {            // resident 8x8-phase blobs -> slot 0, the tile's stage input (one 64 KB copy)
-            mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
-            bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
-            bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
-            bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
-            mbar_arrive_expect_tx(inbar, 65536);
-            bulk_g2s(IN, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * 65536, 65536, inbar);
-        };
-        if (lane == 0 && blockIdx.x < p.n_tiles) load_tile(blockIdx.x);
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            if (lane == 0) {
-                prefetch(3); prefetch(4);            // slots 1, 2: everything of the previous tile is behind the end-of-tile barrier
-                uint32_t dph = 0;                    // each slot completes an even number of times per tile: parities restart at 0
-                for (int op = 5; op < NOPS; ++op) {
-                    const int sl = slot_of(op);
-                    mbar_wait(wdone + sl, (dph >> sl) & 1u);
-                    dph ^= 1u << sl;
-                    prefetch(op);
-                }
-            }
-            __syncwarp();
-            __syncthreads();                         // end of tile (all 17 warps)
-            const int next = tile + gridDim.x;
-            if (lane == 0 && next < p.n_tiles) load_tile(next);
-        }
-    } else {
-        // =========================== two compute groups of 8 warps ==============================================================
-        const int quad = warp & 3, g = (warp >> 2) & 1, half = warp >> 3;      // TMEM lane quadrant, group, column half
-        const int row = quad * 32 + lane, gtid = (half * 4 + quad) * 32 + lane;
-        const bool leader_warp = quad == 0 && half == 0;
-        const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
-        const uint32_t ACCg = ACC + 192 * g, Sg = S_COL + 48 * g;
-        uint8_t* E6g = g ? X16 : R;                  // 8x8 phase: expanded sub-tile; 4x4 phase: block-input operand tile (first 12 KB)
-        uint8_t* A7g = R + 24576 * (1 + g);          // dw_mid output (A of pw_proj L8), then the expanded 4x4 tile E
-        uint8_t* X16g = E6g;
-        uint8_t* E22bg = A5 + 32768 * g;
-        uint64_t* mb = mbarg + g;
-        uint32_t wph = 0, inph = 0, mph = 0;
-        auto gbar = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
-        auto wait_slot = [&](int sl) {
-            mbar_wait(wbar + sl, (wph >> sl) & 1u);
-            wph ^= 1u << sl;
-        };
-        auto begin_op = [&](int op) -> uint8_t* {
-            const int sl = slot_of(op);
-            wait_slot(sl);
-            return slot_ptr(sl);
-        };
-        auto release = [&](int sl) {                 // after a group barrier: nobody of this group reads the slot any more
-            if (gtid == 0) mbar_arrive(wdone + sl);
-        };
-        auto sync_before_mma = [&]() {
-            fence_proxy_async_smem();
-            tc_fence_before();
-            gbar();
-        };
-        auto wait_mma = [&]() {
-            mbar_wait(mb, mph);
-            mph ^= 1u;
-            tc_fence_after();
-        };
-        auto end_op = [&](int op) {
-            tc_fence_before();
-            gbar();
-            release(slot_of(op));
-        };
-
-        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-            // ---------------- blocks.2.0.dw_start over the whole tile (both groups together) --------------------------------
-            wait_slot(0);
-            const float* b5 = reinterpret_cast<const float*>(WA);
-            const float* w5 = b5 + 32;
-            const float* b6 = reinterpret_cast<const float*>(WA + H_OFF1);
-            const uint32_t w6 = smem_u32(WA + H_OFF1 + 96 * 4);
-            const float* b7 = reinterpret_cast<const float*>(WA + H_OFF2);
-            const float* w7 = b7 + 96;
-            mbar_wait(inbar, inph); inph ^= 1u;
-            if (!(p.debug & 1)) dw5x5_rows(IN, A5, w5, b5, tid);
-            fence_proxy_async_smem();
-            tc_fence_before();
-            asm volatile("bar.sync 3, 512;" ::: "memory");
-            // ---------------- 8x8 phase of this group's four sub-tiles ---------------------------------------------------------
-            for (int jj = 0; jj < 4; ++jj) {
-                if (leader_warp && elect_one()) {
-                    tc_fence_after();
-                    issue_gemm(smem_u32(A5 + (4 * g + jj) * 8192), 32, w6, 96, 0, 96, tmem + ACCg, false, 2);     // L6 pw_exp 32 -> 96
-                    mma_commit(mb);
-                }
-                wait_mma();
-                epi_to_e6(trow, ACCg, b6, E6g, row, half, 2);
-                tc_fence_before();
-                gbar();
-                if (!(p.debug & 2)) dw5x5s2_rows(E6g, E6g, A7g, 2 * jj, w7, b7, (gtid & 15) | ((gtid >> 4) << 5));   // L7: 192 tasks, sub = 0
-                gbar();
-            }
-            release(0);
-            // ---------------- 4x4 phase on this group's M-tile -------------------------------------------------------------------
-            int op = 3;
-            {   // L8 blocks.2.0.pw_proj 96 -> 48: starts the residual stream
-                uint8_t* wb = begin_op(op);
-                sync_before_mma();
-                if (leader_warp && elect_one()) {
-                    tc_fence_after();
-                    issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, false, 2);
-                    mma_commit(mb);
-                }
-                wait_mma();
-                epi_to_tile<false>(trow, Sg, 48, reinterpret_cast<const float*>(wb), X16g, 0, row, half, 2);
-                end_op(op); ++op;
-            }
-#pragma unroll 1
-            for (int blk = 1; blk <= 4; ++blk) {
-                {   // pw_exp 48 -> 96 (+ReLU)
-                    uint8_t* wb = begin_op(op);
-                    sync_before_mma();
-                    if (leader_warp && elect_one()) {
-                        tc_fence_after();
-                        issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACCg, false, 2);
-                        mma_commit(mb);
-                    }
-                    wait_mma();
-                    epi_to_tile<true>(trow, ACCg, 96, reinterpret_cast<const float*>(wb), A7g, 0, row, half, 2);
-                    end_op(op); ++op;
-                }
-                {   // dw_mid 3x3 (+ReLU), in place
-                    uint8_t* wb = begin_op(op);
-                    const float* b = reinterpret_cast<const float*>(wb);
-                    if (!(p.debug & 4)) dw3x3_p8_rt<true>(A7g, A7g, 12 * 16, 12, b + 96, b, gtid, 256);
-                    end_op(op); ++op;
-                }
-                {   // pw_proj 96 -> 48 accumulated onto the residual stream
-                    uint8_t* wb = begin_op(op);
-                    sync_before_mma();
-                    if (leader_warp && elect_one()) {
-                        tc_fence_after();
-                        issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, true, 2);
-                        mma_commit(mb);
-                    }
-                    wait_mma();
-                    epi_to_tile<false>(trow, Sg, 48, reinterpret_cast<const float*>(wb), X16g, 0, row, half, 2);
-                    end_op(op); ++op;
-                }
-            }
-            // ---------------- blocks.2.5: dw_start 3x3, pw_exp 48 -> 192 (two column halves), pw_proj 192 -> 48 -------------------
-            {   // op 16: [dw21 blob 1920 B][bias22[0:96] | W22 columns 0..95]
-                uint8_t* wb = begin_op(op);
-                const float* b21 = reinterpret_cast<const float*>(wb);
-                if (!(p.debug & 4)) dw3x3_p8_rt<false>(X16g, X16g, 6 * 16, 6, b21 + 48, b21, gtid, 256);
-                sync_before_mma();
-                if (leader_warp && elect_one()) {
-                    tc_fence_after();
-                    issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACCg, false, 2);
-                    mma_commit(mb);
-                }
-                wait_mma();
-                epi_to_tile<true>(trow, ACCg, 96, reinterpret_cast<const float*>(wb + 1920), A7g, 0, row, half, 2);
-                end_op(op); ++op;
-            }
-            {   // op 17: W22 columns 96..191
-                uint8_t* wb = begin_op(op);
-                if (leader_warp && elect_one()) {
-                    tc_fence_after();
-                    issue_gemm(smem_u32(X16g), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACCg + 96, false, 2);
-                    mma_commit(mb);
-                }
-                wait_mma();
-                epi_to_tile<true>(trow, ACCg + 96, 96, reinterpret_cast<const float*>(wb), E22bg, 0, row, half, 2);
-                end_op(op); ++op;
-            }
-            const float* cum23;
-            {   // op 18: W23 K rows 0..95 (+ cumulative bias)
-                uint8_t* wb = begin_op(op);
-                cum23 = reinterpret_cast<const float*>(wb);
-                sync_before_mma();
-                if (leader_warp && elect_one()) {
-                    tc_fence_after();
-                    issue_gemm(smem_u32(A7g), 96, smem_u32(wb + 192), 48, 0, 48, tmem + Sg, true, 2);
-                }
-                ++op;
-            }
-            {   // op 19: W23 K rows 96..191, then the stage output
-                uint8_t* wb = begin_op(op);
-                if (leader_warp && elect_one()) {
-                    issue_gemm(smem_u32(E22bg), 96, smem_u32(wb), 48, 0, 48, tmem + Sg, true, 2);
-                    mma_commit(mb);
-                }
-                wait_mma();
-                uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + g) * 6 * 128;
-                epi_to_global(trow, Sg, 48, cum23, dst, row, half, 2);
-                tc_fence_before();
-                gbar();
-                release(slot_of(18));
-                release(slot_of(19));
-            }
-            tc_fence_before();
-            __syncthreads();                         // end of tile (all 17 warps): the next tile's input overwrites A7 / X16
-        }
-    }
+    if (F16 && bad != 0) atomicOr(p.ovf, 1);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
@@ -1230,25 +1005,33 @@ __global__ void __launch_bounds__(sc2::NTH, 1) stageC2_kernel(const __grid_const
 // =====================================================================================================================
 namespace sb {
 constexpr int NTB = 256;
-constexpr int W_BYTES = 384 + 1024 + 27648 + 6144;     // [b2 16 | b3 48 | b4 32] fp32, W2 hi|lo, W3 hi|lo, W4 hi|lo
+constexpr int W_BYTES_MAX = 384 + 1024 + 27648 + 6144;     // [b2 16 | b3 48 | b4 32] fp32, then W2, W3, W4: bf16 hi|lo pairs (fp16: single images, half of it)
 constexpr int OFF_W = 0;
 constexpr int OFF_A3 = 35328;             // 36864: im2col image of the blocks.0.1 output = A operand of blocks.1.0 [18][128][8]
 constexpr int OFF_IN = OFF_A3 + 36864;    // 2 x 16384: input ring (2 crops = 4 T8 tiles of 128 rows x 16 ch); the consumed slot is reused as A4
 constexpr int OFF_BAR = OFF_IN + 32768;   // 104960
 constexpr int SMEM = OFF_BAR + 64;
-constexpr int W2_OFF = 384, W3_OFF = 1408, W4_OFF = 29056;
+constexpr int w_bytes(bool f16) { return 384 + (512 + 13824 + 3072) * (f16 ? 1 : 2); }
 }  // namespace sb
 
 struct StageBParams {
     const bf16* x;            // front-end output: T8 tiles, rows = crop*256 + pixel (16x16), 16 ch
-    const uint8_t* wimg;      // sb::W_BYTES
+    const uint8_t* wimg;      // sb::w_bytes(F16)
     bf16* y;                  // P2 tiles (128 rows = 2 crops at 8x8, row = pix*2 + crop) x 32 ch == stage C input
     int n_tiles;              // n_crops / 2
+    const int* gate;          // non-null: the kernel runs only when (*gate != 0) == gate_want (fp16 pass: want 0; bf16 fall-back pass: want 1)
+    int gate_want;
+    int* ovf;                 // fp16 pass: set to 1 when a residual-stream value left the fp16 range (the bf16 pass then redoes the wave)
 };
 
+template <bool F16>
 __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constant__ StageBParams p) {
     using namespace sb;
     extern __shared__ __align__(1024) uint8_t smem[];
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;
+    uint32_t bad = 0;                 // every output of this stage passes a ReLU conversion: nothing to check, +inf travels on to stage C
+    constexpr int WP = F16 ? 1 : 2;
+    constexpr int W2_OFF = 384, W3_OFF = W2_OFF + 512 * WP, W4_OFF = W3_OFF + 13824 * WP, W_BYTES = W4_OFF + 3072 * WP;
     uint8_t* W = smem + OFF_W;
     uint8_t* A3 = smem + OFF_A3;
     uint8_t* IN = smem + OFF_IN;
@@ -1309,7 +1092,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         //      CTAs per SM its round trip already runs under the other CTA's work)
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            for (int j = 0; j < 4; ++j) issue_gemm(smem_u32(in + j * 4096), 16, smem_u32(W + W2_OFF), 16, 0, 16, tmem + 16 * j, false, 2);
+            for (int j = 0; j < 4; ++j) issue_gemm<F16>(smem_u32(in + j * 4096), 16, smem_u32(W + W2_OFF), 16, 0, 16, tmem + 16 * j, false, WP);
             mma_commit(mbar);
         }
         wait_mma();
@@ -1327,7 +1110,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * h + i]) + b2[8 * h + i], 0.f);
-                o[h] = pack8(v);
+                o[h] = pack8<F16>(v);
             }
             const int rg = j * 128 + row, crop = rg >> 8, iy = (rg >> 4) & 15, ix = rg & 15;
 #pragma unroll
@@ -1348,17 +1131,17 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
         // ---- blocks.1.0: 3x3 s2 16 -> 48 (+ReLU) as one K = 144 GEMM on 128 rows (2 crops x 8x8, P2 order)
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            issue_gemm(smem_u32(A3), 144, smem_u32(W + W3_OFF), 48, 0, 48, tmem + 64, false, 2);
+            issue_gemm<F16>(smem_u32(A3), 144, smem_u32(W + W3_OFF), 48, 0, 48, tmem + 64, false, WP);
             mma_commit(mbar);
         }
         wait_mma();
         uint8_t* A4 = in;                       // the input slot is dead (its MMAs completed): reuse it for the next operand
-        epi_to_tile<true>(trow, 64, 48, b3, A4, 0, row, hi2, 2);
+        epi_to_tile<F16, true>(trow, 64, 48, b3, A4, 0, row, hi2, 2, bad);
         sync_before_mma();
         // ---- blocks.1.1: 1x1 48 -> 32 (+ReLU) -> global P2 tile
         if (warp == 0 && elect_one()) {
             tc_fence_after();
-            issue_gemm(smem_u32(A4), 48, smem_u32(W + W4_OFF), 32, 0, 32, tmem + 128, false, 2);
+            issue_gemm<F16>(smem_u32(A4), 48, smem_u32(W + W4_OFF), 32, 0, 32, tmem + 128, false, WP);
             mma_commit(mbar);
         }
         wait_mma();
@@ -1372,7 +1155,7 @@ __global__ void __launch_bounds__(sb::NTB, 2) stageB_kernel(const __grid_constan
                 float v[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] = fmaxf(__uint_as_float(r[8 * h + i]) + b4[16 * hi2 + 8 * h + i], 0.f);
-                dst[(size_t)(row >> 1) * 8 + (hi2 * 2 + h) * 2 + (row & 1)] = pack8(v);      // P2X: [pixel][chunk][crop]
+                dst[(size_t)(row >> 1) * 8 + (hi2 * 2 + h) * 2 + (row & 1)] = pack8<F16>(v);      // P2X: [pixel][chunk][crop]
             }
         }
         tc_fence_before();
@@ -1402,16 +1185,23 @@ __global__ void permute_p2_kernel(const uint4* __restrict__ in, uint4* __restric
 }
 
 // ---- stage weight image construction --------------------------------------------------------------------------------------
-// rows [k0, k0+K) x columns [n0, n0+n) of w[.][n_total] -> UMMA B image [K/8][n][8]; parts == 2 appends the lo image
-// (w - bf16(w), itself rounded to bf16) right after the hi image.
-__global__ void prep_pw_part_kernel(const float* __restrict__ w, int k0, int K, int n_total, int n0, int n, int parts, bf16* __restrict__ dst) {
+// rows [k0, k0+K) x columns [n0, n0+n) of w[.][n_total] -> UMMA B image [K/8][n][8].  bf16: parts == 2 appends the lo image
+// (w - bf16(w), itself rounded to bf16) right after the hi image.  fp16 (f16_flag non-null): one image; *f16_flag is raised when a
+// weight does not fit the fp16 range (the handle then never takes the fp16 kernels).
+__global__ void prep_pw_part_kernel(const float* __restrict__ w, int k0, int K, int n_total, int n0, int n, int parts, uint16_t* __restrict__ dst,
+                                    int* __restrict__ f16_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * n) return;
     const int kk = i & 7, j = (i >> 3) % n, kc = (i >> 3) / n;
     const float v = w[(size_t)(k0 + kc * 8 + kk) * n_total + n0 + j];
+    if (f16_flag != nullptr) {
+        if (!(fabsf(v) <= 65504.f)) atomicOr(f16_flag, 1);
+        dst[i] = __half_as_ushort(__float2half_rn(v));
+        return;
+    }
     const bf16 hi = __float2bfloat16_rn(v);
-    dst[i] = hi;
-    if (parts == 2) dst[(size_t)K * n + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    dst[i] = __bfloat16_as_ushort(hi);
+    if (parts == 2) dst[(size_t)K * n + i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(hi)));
 }
 // 2x2-map depthwise weights: dst[((c8*4 + p)*4 + q)*8 + i] = w[tap(p,q)][c8*8 + i], tap = (qy-py+pad)*K + (qx-px+pad).
 __global__ void prep_dw2x2_kernel(const float* __restrict__ w, int K, int C, float* __restrict__ dst) {
@@ -1449,7 +1239,8 @@ size_t stageD_image_bytes() {
 }
 
 // Builds the stage-D weight image from the packed fp32 blob (device) and fills off[]/bytes[] (host arrays of 24).
-int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s) {
+// f16_flag non-null: fp16 weight images (and the range check of prep_pw_part_kernel); null: bf16.
+int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag, cudaStream_t s) {
     const cv_layer_info* L = cv_layers();
     size_t o = 0;
     const float* prev_cum = nullptr;
@@ -1478,7 +1269,7 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
                     CV_CUDA(cudaMemcpyAsync(f + l.cout, blob + l.w_offset, (size_t)l.k * l.k * l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 }
             } else if (d.kind == 3) {
-                prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 0, 64, 480, 160 * part, 160, 1, reinterpret_cast<bf16*>(dst));
+                prep_pw_part_kernel<<<(64 * 160 + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 0, 64, 480, 160 * part, 160, 1, reinterpret_cast<uint16_t*>(dst), f16_flag);
                 CV_CHECK_LAUNCH();
                 ++part;
             } else {
@@ -1492,7 +1283,7 @@ int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t*
                     CV_CUDA(cudaMemcpyAsync(f, blob + l.b_offset, l.cout * sizeof(float), cudaMemcpyDeviceToDevice, s));
                 }
                 prep_pw_part_kernel<<<(l.cin * l.cout + 255) / 256, 256, 0, s>>>(blob + l.w_offset, 0, l.cin, l.cout, 0, l.cout, 1,
-                                                                                reinterpret_cast<bf16*>(dst + (size_t)l.cout * 4));
+                                                                                reinterpret_cast<uint16_t*>(dst + (size_t)l.cout * 4), f16_flag);
                 CV_CHECK_LAUNCH();
             }
         }
@@ -1510,62 +1301,66 @@ int launch_permute_p8(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, float* features,
-                  int tiled, int64_t crop_base, float* squares, int num_sms, cudaStream_t s) {
+                  int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 32 != 0) { cv_set_error("stage D: crop count %lld is not a multiple of 32", (long long)n_crops); return CV_ERR_ARG; }
     StageDParams p{};
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
     p.tiled = tiled; p.crop_base = crop_base;
+    p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
 #ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SD_DEBUG"); p.debug = d ? atoi(d) : 0; }
 #endif
     for (int i = 0; i < sd::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
-    CV_CUDA(cudaFuncSetAttribute(stageD_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
+    auto kern = gate.f16 ? stageD_kernel<true> : stageD_kernel<false>;
+    CV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sd::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-    stageD_kernel<<<grid, NT, sd::SMEM, s>>>(p);
+    kern<<<grid, NT, sd::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
 
-// ---- stage C image: every pointwise blob carries W_hi | W_lo -----------------------------------------------------------------
+// ---- stage C image: every pointwise blob carries W_hi | W_lo (bf16) or one fp16 image ------------------------------------------
 namespace {
 struct COp { int layer, kind; };   // 0 dw | 1 pw own bias | 2 pw_proj cumulative bias | 5 dw21 + pw22 cols 0..95 | 6 pw22 cols 96..191 | 7 pw23 K 0..95 | 8 pw23 K 96..191
 const COp kCOps[sc::NOPS] = {{5, 0}, {6, 1}, {7, 0}, {8, 2}, {9, 1}, {10, 0}, {11, 2}, {12, 1}, {13, 0}, {14, 2}, {15, 1}, {16, 0}, {17, 2},
                              {18, 1}, {19, 0}, {20, 2}, {22, 5}, {22, 6}, {23, 7}, {23, 8}};
-uint32_t cop_bytes(int op) {
+uint32_t cop_bytes(int op, bool f16) {
     const cv_layer_info* L = cv_layers();
     const COp& d = kCOps[op];
     const cv_layer_info& l = L[d.layer];
+    const uint32_t wb = f16 ? 2 : 4;            // bytes per weight: one fp16 image | bf16 hi + lo
     switch (d.kind) {
         case 0: return (uint32_t)(l.cout + l.k * l.k * l.cout) * 4;
-        case 1: case 2: return (uint32_t)l.cout * 4 + (uint32_t)l.cin * l.cout * 4;
-        case 5: return 1920 + 96 * 4 + 48 * 96 * 4;
-        case 6: return 96 * 4 + 48 * 96 * 4;
-        case 7: return 48 * 4 + 96 * 48 * 4;
-        default: return 96 * 48 * 4;
+        case 1: case 2: return (uint32_t)l.cout * 4 + (uint32_t)l.cin * l.cout * wb;
+        case 5: return 1920 + 96 * 4 + 48 * 96 * wb;
+        case 6: return 96 * 4 + 48 * 96 * wb;
+        case 7: return 48 * 4 + 96 * 48 * wb;
+        default: return 96 * 48 * wb;
     }
 }
 }  // namespace
 
-size_t stageC_image_bytes() {
+size_t stageC_image_bytes() {               // the larger (bf16) variant
     size_t n = 0;
-    for (int op = 0; op < sc::NOPS; ++op) n += (cop_bytes(op) + 127) / 128 * 128;
+    for (int op = 0; op < sc::NOPS; ++op) n += (cop_bytes(op, false) + 127) / 128 * 128;
     return n;
 }
 
-int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, cudaStream_t s) {
+int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag, cudaStream_t s) {
+    const bool f16 = f16_flag != nullptr;
     const cv_layer_info* L = cv_layers();
     size_t o = 0;
     const float* prev_cum = nullptr;
     auto copy_f = [&](float* dst, const float* src, size_t n) { return cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s); };
     auto pw = [&](const cv_layer_info& l, int k0, int K, int n0, int n, uint8_t* dst) {
-        prep_pw_part_kernel<<<(K * n + 255) / 256, 256, 0, s>>>(blob + l.w_offset, k0, K, l.cout, n0, n, 2, reinterpret_cast<bf16*>(dst));
+        prep_pw_part_kernel<<<(K * n + 255) / 256, 256, 0, s>>>(blob + l.w_offset, k0, K, l.cout, n0, n, 2, reinterpret_cast<uint16_t*>(dst), f16_flag);
     };
     for (int op = 0; op < sc::NOPS; ++op) {
         const COp& d = kCOps[op];
         const cv_layer_info& l = L[d.layer];
         off[op] = (uint32_t)o;
-        bytes[op] = cop_bytes(op);
+        bytes[op] = cop_bytes(op, f16);
         uint8_t* dst = img + o;
         float* f = reinterpret_cast<float*>(dst);
         switch (d.kind) {
@@ -1617,24 +1412,20 @@ int launch_permute_p2(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8, int num_sms,
-                  int split, cudaStream_t s) {
+                  const StageGate& gate, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
     StageCParams p{};
     p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16);
+    p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
 #ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SC_DEBUG"); p.debug = d ? atoi(d) : 0; }
 #endif
     for (int i = 0; i < sc::NOPS; ++i) { p.off[i] = off[i]; p.bytes[i] = bytes[i]; }
-    CV_CUDA(cudaFuncSetAttribute(stageC_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
+    auto kern = gate.f16 ? stageC_kernel<true> : stageC_kernel<false>;
+    CV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sc::SMEM));
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
-    if (split) {
-        CV_CUDA(cudaFuncSetAttribute(stageC2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc2::SMEM));
-        stageC2_kernel<<<grid, sc2::NTH, sc2::SMEM, s>>>(p);
-        CV_CHECK_LAUNCH();
-        return CV_OK;
-    }
-    stageC_kernel<<<grid, NT, sc::SMEM, s>>>(p);
+    kern<<<grid, NT, sc::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
 #ifdef CV_SC_PROFILE
     if (p.debug & 256) {
@@ -1653,28 +1444,31 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
 }
 
 // ---- stage B ----------------------------------------------------------------------------------------------------------------------
-size_t stageB_image_bytes() { return sb::W_BYTES; }
+size_t stageB_image_bytes() { return sb::w_bytes(false); }          // the larger (bf16 hi|lo) variant
 
-int build_stageB_image(const float* blob, uint8_t* img, cudaStream_t s) {
+int build_stageB_image(const float* blob, uint8_t* img, int* f16_flag, cudaStream_t s) {
     const cv_layer_info* L = cv_layers();
+    const int wp = f16_flag ? 1 : 2;
+    const int w2 = 384, w3 = w2 + 512 * wp, w4 = w3 + 13824 * wp;     // == the offsets stageB_kernel<F16> derives
     float* f = reinterpret_cast<float*>(img);
     CV_CUDA(cudaMemcpyAsync(f, blob + L[2].b_offset, 16 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(f + 16, blob + L[3].b_offset, 48 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     CV_CUDA(cudaMemcpyAsync(f + 64, blob + L[4].b_offset, 32 * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    prep_pw_part_kernel<<<1, 256, 0, s>>>(blob + L[2].w_offset, 0, 16, 16, 0, 16, 2, reinterpret_cast<bf16*>(img + sb::W2_OFF));
-    prep_pw_part_kernel<<<(144 * 48 + 255) / 256, 256, 0, s>>>(blob + L[3].w_offset, 0, 144, 48, 0, 48, 2, reinterpret_cast<bf16*>(img + sb::W3_OFF));
-    prep_pw_part_kernel<<<(48 * 32 + 255) / 256, 256, 0, s>>>(blob + L[4].w_offset, 0, 48, 32, 0, 32, 2, reinterpret_cast<bf16*>(img + sb::W4_OFF));
+    prep_pw_part_kernel<<<1, 256, 0, s>>>(blob + L[2].w_offset, 0, 16, 16, 0, 16, 2, reinterpret_cast<uint16_t*>(img + w2), f16_flag);
+    prep_pw_part_kernel<<<(144 * 48 + 255) / 256, 256, 0, s>>>(blob + L[3].w_offset, 0, 144, 48, 0, 48, 2, reinterpret_cast<uint16_t*>(img + w3), f16_flag);
+    prep_pw_part_kernel<<<(48 * 32 + 255) / 256, 256, 0, s>>>(blob + L[4].w_offset, 0, 48, 32, 0, 32, 2, reinterpret_cast<uint16_t*>(img + w4), f16_flag);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
 
-int launch_stageB(const bf16* x, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, cudaStream_t s) {
+int launch_stageB(const bf16* x, int64_t n_crops, const uint8_t* wimg, bf16* y_p2, int num_sms, const StageGate& gate, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 2 != 0) { cv_set_error("stage B: odd crop count %lld", (long long)n_crops); return CV_ERR_ARG; }
-    StageBParams p{x, wimg, y_p2, (int)(n_crops / 2)};
-    CV_CUDA(cudaFuncSetAttribute(stageB_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::SMEM));
+    StageBParams p{x, wimg, y_p2, (int)(n_crops / 2), gate.flag, gate.want, gate.ovf};
+    auto kern = gate.f16 ? stageB_kernel<true> : stageB_kernel<false>;
+    CV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sb::SMEM));
     const int grid = p.n_tiles < 2 * num_sms ? p.n_tiles : 2 * num_sms;
-    stageB_kernel<<<grid, sb::NTB, sb::SMEM, s>>>(p);
+    kern<<<grid, sb::NTB, sb::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }

@@ -72,6 +72,9 @@ struct FrontParams {
     bf16* y;
     int n_crops, H;
     const int* run_flag;      // non-null: the kernel exits at once when *run_flag == 0 (the third-generation front end took the call)
+    int out_f16;              // the T8 output is fp16 (feeds the fp16 stage B) instead of bf16; the convolutions themselves stay bf16 hi|lo
+    const int* gate;          // internal.h StageGate: run only when (*gate != 0) == gate_want
+    int gate_want;
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ CropTaps tp_param) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (p.run_flag != nullptr && *p.run_flag == 0) return;       // uniform over the grid
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;
     uint8_t* X = smem + OFF_X;
     uint8_t* Y = smem + OFF_Y;
     uint8_t* W = smem + OFF_W;
@@ -293,7 +297,8 @@ frontend_kernel(const __grid_constant__ FrontParams p, const __grid_constant__ C
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
                             v[k] = fmaxf(__uint_as_float(e[j][0][8 * c + k]) + __uint_as_float(e[j][1][8 * c + k]) + bias[32 + 8 * c + k], 0.f);
-                        dst[c * 128] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                        dst[c * 128] = p.out_f16 ? make_uint4(pk2<true>(v[0], v[1]), pk2<true>(v[2], v[3]), pk2<true>(v[4], v[5]), pk2<true>(v[6], v[7]))
+                                                 : make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
                     }
                 }
             }
@@ -343,9 +348,9 @@ int launch_frontend_prep_weights(const float* blob, bf16* img, cudaStream_t s) {
 }
 
 int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom& g, const float* lut_dev, const bf16* wimg,
-                    const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, cudaStream_t s, const int* run_flag) {
+                    const float* bias_stem, const float* bias_b00, bf16* y, int num_sms, cudaStream_t s, const int* run_flag, const StageGate& gate) {
     if (nb == 0) return CV_OK;
-    FrontParams p{src, lut_dev, wimg, bias_stem, bias_b00, y, nb * 64, H, run_flag};
+    FrontParams p{src, lut_dev, wimg, bias_stem, bias_b00, y, nb * 64, H, run_flag, gate.f16 ? 1 : 0, gate.flag, gate.want};
     const CropTaps tp = make_taps(g);
     const int grid = p.n_crops < num_sms ? p.n_crops : num_sms;
 #define FE_LAUNCH(KIND)                                                                                              \

@@ -44,7 +44,9 @@ constexpr int NYBUF = 2;                                       // left / right h
 constexpr int NXBUF = 2;                                       // stem operand image, double buffered
 constexpr int W_STEM_BYTES = 4 * 1024;                         // taps x [2 chunks][32 n][8] fp16
 constexpr int W_B00_BYTES = 18 * 1024;                         // (tap, k-step) x [2 chunks][32 n = hi 16 | lo 16][8] bf16
-constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528
+constexpr int W_B00_F16_BYTES = 18 * 512;                      // (tap, k-step) x [2 chunks][16 n][8] fp16 (fp16 mode: one image, N = 16)
+constexpr int W_BYTES = W_STEM_BYTES + W_B00_BYTES;            // 22528: what a CTA holds in shared memory (stem + one blocks.0.0 variant)
+constexpr int W_IMG_BYTES = W_BYTES + W_B00_F16_BYTES;         // global image: stem | blocks.0.0 bf16 hi|lo | blocks.0.0 fp16
 constexpr int NPROD = 384;                                      // 12 resize producer warps (the resize is the longest per-crop job)
 constexpr int MMA_WARP = 8 + NPROD / 32;
 constexpr int TMA_WARP = MMA_WARP + 1;                         // stages the board windows: the tile copy's issue latency stays off the producers' chain
@@ -70,6 +72,8 @@ struct Front3Params {
     int off_raw, off_v, off_y, off_w, off_tab, off_bar, smem_total;
     float na[3], nb[3];               // normalisation v = na[c] * u8 + nb[c]
     const int* skip_flag;             // non-null: the kernel exits at once when *skip_flag != 0 (float source that is not a uint8 image, see below)
+    const int* gate;                  // non-null: run only when (*gate != 0) == gate_want (fp16 pass / bf16 fall-back pass, internal.h StageGate)
+    int gate_want;
     int debug;                        // experiment builds (CV_FE3_DEBUG): 1 / 2 skip the resize passes, 4 / 8 skip epilogue TMEM loads / stores, 16 / 128 / 1024 /
                                       // 2048 skip MMA-thread waits, 32 skip the x_full wait, 64 spin in the epilogue, 256 wait-cycle report, 512 event trace
 };
@@ -95,6 +99,7 @@ __device__ unsigned long long g_fe3_prof[4 * 16];
 #define TRACE(tag)
 #endif
 
+template <bool F16>                   // F16: stem output image, blocks.0.0 weights and the T8 output are fp16; otherwise bf16 (W_hi | W_lo along N)
 __global__ void __launch_bounds__(NTHREADS, 1)
 frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__ Front3Tables tab_param, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -111,6 +116,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
     uint64_t* raw_empty = bars + 35 /*3*/;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (p.skip_flag != nullptr && *p.skip_flag != 0) return;     // uniform over the grid: decided by an earlier kernel of the stream
+    if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;
 
     // ---- one-time setup: zero X / Y (halos stay zero for the whole kernel), tables, barriers, TMEM
     for (int i = threadIdx.x; i < p.n_xbuf * X_ALLOC / 16; i += NTHREADS) reinterpret_cast<uint4*>(X)[i] = make_uint4(0, 0, 0, 0);
@@ -295,12 +301,19 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         // without a warp-wide wait + election + reconvergence per tile.  With 4 MMAs (~160 cycles of tensor-pipe work) per stem tile,
         // that per-block overhead (~150 cycles) had kept the pipe half idle: the pipe queue does not run far ahead of the issuer.
         if (elect_one()) {
-            mbar_arrive_expect_tx(wbar, W_BYTES);
-            bulk_g2s(W, p.wimg, W_BYTES, wbar);
+            constexpr int N1 = F16 ? 16 : 32;                      // blocks.0.0 GEMM width: fp16 W | bf16 W_hi, W_lo
+            if (F16) {
+                mbar_arrive_expect_tx(wbar, W_STEM_BYTES + W_B00_F16_BYTES);
+                bulk_g2s(W, p.wimg, W_STEM_BYTES, wbar);
+                bulk_g2s(W + W_STEM_BYTES, p.wimg + W_BYTES, W_B00_F16_BYTES, wbar);
+            } else {
+                mbar_arrive_expect_tx(wbar, W_BYTES);
+                bulk_g2s(W, p.wimg, W_BYTES, wbar);
+            }
             mbar_wait_spin(wbar, 0);
-            constexpr uint32_t idesc_s = make_idesc_f16(128, 32), idesc_1 = make_idesc_bf16(128, 32);
+            constexpr uint32_t idesc_s = make_idesc_f16(128, 32), idesc_1 = make_idesc_16<F16>(128, N1);
             const uint32_t x_lo = desc_lo(smem_u32(X), X_CHUNK), y_lo = desc_lo(smem_u32(Y), YH_CHUNK);
-            const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), 32 * 16);
+            const uint32_t ws_lo = desc_lo(smem_u32(W), 32 * 16), w1_lo = desc_lo(smem_u32(W + W_STEM_BYTES), N1 * 16);
             constexpr uint32_t x_hi = desc_hi(XP * 16), y_hi = desc_hi(YHP * 16), w_hi = desc_hi(128);
             // stem tiles k = 2 s + h, k in [k0, k1), of the crop in X slot it & xmask: output columns [8s, 8s+8), rows [16h, 16h+16)
             auto issue_stem = [&](int k0, int k1, uint32_t it) {
@@ -334,7 +347,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                     for (int ks = 0; ks < 2; ++ks)
                         mma_f16_ss2(tmem_base + TM_B00 + t * 32,
                                     yb_lo + (uint32_t)(plane * (YH_PLANE >> 4) + ks * 2 * YHPOS + YLEAD + (1 + Dy) * YHP + 1 + Dx), y_hi,
-                                    w1_lo + (tap * 2 + ks) * 64, w_hi, idesc_1, (tap | ks) ? 1u : 0u);
+                                    w1_lo + (tap * 2 + ks) * (N1 * 2), w_hi, idesc_1, (tap | ks) ? 1u : 0u);
                 }
                 mma_commit(e_full + t);
                 TRACE(0x400 + t);
@@ -376,10 +389,11 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             TWAIT(0, mbar_wait(e_full + g, itb & 1u));
             TRACE(0xA00 + g);
             tc_fence_after();
-            uint32_t eh[16], el[16];                             // hi | lo halves of the 16 output channels
+            uint32_t eh[16], el[16];                             // bf16: hi | lo halves of the 16 output channels
             tmem_ld16(trow + TM_B00 + g * 32, eh);
-            tmem_ld16(trow + TM_B00 + g * 32 + 16, el);
+            if (!F16) tmem_ld16(trow + TM_B00 + g * 32 + 16, el);
             tmem_ld_wait();
+
             tc_fence_before();
             __syncwarp();
             const int64_t m = (int64_t)n * 256 + (i >> 3) * 16 + 8 * g + (i & 7);
@@ -390,8 +404,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int e = 8 * c + 2 * q;
-                    w[q] = pack2_relu(__uint_as_float(eh[e]) + __uint_as_float(el[e]) + bb[e],
-                                      __uint_as_float(eh[e + 1]) + __uint_as_float(el[e + 1]) + bb[e + 1]);
+                    const float v0 = F16 ? __uint_as_float(eh[e]) : __uint_as_float(eh[e]) + __uint_as_float(el[e]);
+                    const float v1 = F16 ? __uint_as_float(eh[e + 1]) : __uint_as_float(eh[e + 1]) + __uint_as_float(el[e + 1]);
+                    w[q] = pk2r<F16>(v0 + bb[e], v1 + bb[e + 1]);
                 }
                 dst[c * 128] = make_uint4(w[0], w[1], w[2], w[3]);
             }
@@ -424,14 +439,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
                 uint4 o[4];
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    o[c] = make_uint4(pack2_relu(__uint_as_float(r0[8 * c]), __uint_as_float(r0[8 * c + 1])),
-                                      pack2_relu(__uint_as_float(r0[8 * c + 2]), __uint_as_float(r0[8 * c + 3])),
-                                      pack2_relu(__uint_as_float(r0[8 * c + 4]), __uint_as_float(r0[8 * c + 5])),
-                                      pack2_relu(__uint_as_float(r0[8 * c + 6]), __uint_as_float(r0[8 * c + 7])));
-                    o[2 + c] = make_uint4(pack2_relu(__uint_as_float(r1[8 * c]), __uint_as_float(r1[8 * c + 1])),
-                                          pack2_relu(__uint_as_float(r1[8 * c + 2]), __uint_as_float(r1[8 * c + 3])),
-                                          pack2_relu(__uint_as_float(r1[8 * c + 4]), __uint_as_float(r1[8 * c + 5])),
-                                          pack2_relu(__uint_as_float(r1[8 * c + 6]), __uint_as_float(r1[8 * c + 7])));
+                    o[c] = make_uint4(pk2r<F16>(__uint_as_float(r0[8 * c]), __uint_as_float(r0[8 * c + 1])),
+                                      pk2r<F16>(__uint_as_float(r0[8 * c + 2]), __uint_as_float(r0[8 * c + 3])),
+                                      pk2r<F16>(__uint_as_float(r0[8 * c + 4]), __uint_as_float(r0[8 * c + 5])),
+                                      pk2r<F16>(__uint_as_float(r0[8 * c + 6]), __uint_as_float(r0[8 * c + 7])));
+                    o[2 + c] = make_uint4(pk2r<F16>(__uint_as_float(r1[8 * c]), __uint_as_float(r1[8 * c + 1])),
+                                          pk2r<F16>(__uint_as_float(r1[8 * c + 2]), __uint_as_float(r1[8 * c + 3])),
+                                          pk2r<F16>(__uint_as_float(r1[8 * c + 4]), __uint_as_float(r1[8 * c + 5])),
+                                          pk2r<F16>(__uint_as_float(r1[8 * c + 6]), __uint_as_float(r1[8 * c + 7])));
                 }
                 uint8_t* dst = yb + yoff + (s & 1) * 64;
 #pragma unroll
@@ -478,7 +493,7 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
 __global__ void prep_frontend3_weights_kernel(const float* __restrict__ w_stem /*[27][32]*/, const float* __restrict__ b_stem /*[32]*/,
                                               const float* __restrict__ w_b00 /*[288][16]*/, uint16_t* __restrict__ img, int* __restrict__ flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= W_BYTES / 2) return;
+    if (i >= W_IMG_BYTES / 2) return;
     float v = 0.f;
     if (i < W_STEM_BYTES / 2) {
         const int kk = i & 7, n = (i >> 3) & 31, chunk = (i >> 8) & 1, tap = i >> 9;
@@ -492,24 +507,31 @@ __global__ void prep_frontend3_weights_kernel(const float* __restrict__ w_stem /
         }
         if (!(fabsf(v) <= 65504.f)) atomicOr(flag, 1);
         img[i] = __half_as_ushort(__float2half_rn(v));
-    } else {
+    } else if (i < W_BYTES / 2) {
         const int j = i - W_STEM_BYTES / 2;
         const int kk = j & 7, n = (j >> 3) & 31, chunk = (j >> 8) & 1, ks = (j >> 9) & 1, tap = j >> 10;
         const int ci = ks * 16 + chunk * 8 + kk;
         v = w_b00[(tap * 32 + ci) * 16 + (n & 15)];
         const bf16 hi = __float2bfloat16_rn(v);
         img[i] = __bfloat16_as_ushort(n >= 16 ? __float2bfloat16_rn(v - __bfloat162float(hi)) : hi);
+    } else {                                                           // fp16 blocks.0.0 image: (tap, k-step) x [2 chunks][16 n][8]
+        const int j = i - W_BYTES / 2;
+        const int kk = j & 7, n = (j >> 3) & 15, chunk = (j >> 7) & 1, ks = (j >> 8) & 1, tap = j >> 9;
+        const int ci = ks * 16 + chunk * 8 + kk;
+        v = w_b00[(tap * 32 + ci) * 16 + n];
+        if (!(fabsf(v) <= 65504.f)) atomicOr(flag, 1);
+        img[i] = __half_as_ushort(__float2half_rn(v));
     }
 }
 
 }  // namespace
 
-size_t frontend3_weight_image_bytes() { return W_BYTES; }
+size_t frontend3_weight_image_bytes() { return W_IMG_BYTES; }
 
 int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s) {
     const cv_layer_info* L = cv_layers();
     CV_CUDA(cudaMemsetAsync(flag_dev, 0, sizeof(int), s));
-    prep_frontend3_weights_kernel<<<(W_BYTES / 2 + 255) / 256, 256, 0, s>>>(blob + L[0].w_offset, blob + L[0].b_offset, blob + L[1].w_offset,
+    prep_frontend3_weights_kernel<<<(W_IMG_BYTES / 2 + 255) / 256, 256, 0, s>>>(blob + L[0].w_offset, blob + L[0].b_offset, blob + L[1].w_offset,
                                                                             reinterpret_cast<uint16_t*>(img), flag_dev);
     CV_CHECK_LAUNCH();
     return CV_OK;
@@ -518,7 +540,7 @@ int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev
 // Returns CV_OK and sets *supported = 0 when this kernel cannot take the configuration (the caller then uses an earlier
 // generation): non-affine normalisation table, window too large for shared memory (512x512 boards), > 255 window rows.
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
-                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag) {
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag, const StageGate& gate) {
     *supported = 0;
     if (nb == 0) { *supported = 1; return CV_OK; }
     Front3Params p{};
@@ -590,6 +612,7 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     p.boards = boards_hwc; p.wimg = wimg; p.bias_b00 = bias_b00; p.y = y;
     p.n_crops = nb * 64; p.H = H;
     p.skip_flag = skip_flag;
+    p.gate = gate.flag; p.gate_want = gate.want;
 #if defined(CV_EXPERIMENTS) || defined(CV_FE_PROFILE)   // ablation / timing / trace switches (some change the results): experiment builds only
     { const char* d = getenv("CV_FE3_DEBUG"); p.debug = d ? atoi(d) : 0; }
 #endif
@@ -616,9 +639,10 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
     if (cr != CUDA_SUCCESS) { cv_set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr); return CV_ERR_CUDA; }
     p.box_bytes = max_rows * max_bytes;
     *supported = 1;
-    CV_CUDA(cudaFuncSetAttribute(frontend3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total));
+    auto kern = gate.f16 ? frontend3_kernel<true> : frontend3_kernel<false>;
+    CV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_total));
     const int grid = p.n_crops < num_sms ? p.n_crops : num_sms;
-    frontend3_kernel<<<grid, NTHREADS, p.smem_total, s>>>(p, tab, tmap);
+    kern<<<grid, NTHREADS, p.smem_total, s>>>(p, tab, tmap);
     CV_CHECK_LAUNCH();
 #ifdef CV_FE_PROFILE
     if (p.debug & 256) {                                          // timing experiment: print block 0's wait-cycle counters

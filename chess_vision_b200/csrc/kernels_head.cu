@@ -4,13 +4,17 @@
 //
 // The 30720 -> 64 projection is 99.98 % of the head's work: a skinny GEMM with M = boards, N = 64, K = 30720 whose A operand
 // (the pooled trunk features, 120 KB of fp32 per board) is the only large stream of the whole path after the uint8 boards.
-// It runs as a split-K tcgen05 GEMM in kind::tf32 (fp32 operands read straight from shared memory, fp32 accumulation in
-// TMEM).  The fused tail (kernels_backend.cu, stage D) writes the features directly in the operand layout
+// It runs as a split-K tcgen05 GEMM in kind::tf32 with SPLIT OPERANDS (fp32 accumulation in TMEM): a tf32 operand keeps 10
+// explicit significand bits (the tensor core ignores the low 13 bits of the fp32 word), which alone put 3-5e-3 of relative error
+// on the turn / castling logits (these dot products cancel heavily) -- so features and weights are held as x = hi + lo with
+// hi = x & 0xffffe000 and lo = x - hi (exact), and every k-step issues  A_hi W_hi + A_lo W_hi + A_hi W_lo  (the dropped
+// A_lo W_lo term is 2^-22 relative): fp32-grade products at three MMAs per k-step of a GEMM that is memory-bound anyway.
+// The fused tail (kernels_backend.cu, stage D) writes the two feature planes directly in the operand layout
 //
-//     FT[m_tile][k/4][128 rows = boards][4 floats]          (K-major / no-swizzle UMMA tile per 128 boards)
+//     FT[m_tile][plane hi | lo][k/4][128 rows = boards][4 floats]     (K-major / no-swizzle UMMA tiles per 128 boards)
 //
-// so a K-block of 64 features x 128 boards is one contiguous 32 KB block = ONE TMA bulk copy; the weights are pre-tiled the
-// same way ([k/4][64][4]).  Grid = (board tiles) x (K splits) ~ one CTA per SM; partial sums go to a small fp32 buffer and a
+// so a K-block of 32 features x 128 boards of one plane is one contiguous 16 KB block = ONE TMA bulk copy; the weights are
+// pre-tiled the same way ([plane][k/4][64][4]).  Grid = (board tiles) x (K splits); partial sums go to a small fp32 buffer and a
 // finishing kernel adds them in a fixed order (deterministic), applies bias + ReLU and the 64 -> 1 + 4 output layers.
 #include "internal.h"
 #include "umma.cuh"
@@ -20,9 +24,11 @@ namespace {
 using namespace umma;
 
 constexpr int KCH = 7680;                  // 30720 / 4: 16-byte K chunks
-constexpr int KB_CHUNKS = 16;              // chunks per pipeline stage (64 features)
-constexpr int A_STAGE = KB_CHUNKS * 2048;  // 32768
-constexpr int B_STAGE = KB_CHUNKS * 1024;  // 16384
+constexpr int KB_CHUNKS = 8;               // chunks per pipeline stage (32 features)
+constexpr int A_PLANE = KB_CHUNKS * 2048;  // 16384 per plane
+constexpr int B_PLANE = KB_CHUNKS * 1024;  // 8192 per plane
+constexpr int A_STAGE = 2 * A_PLANE;       // hi | lo
+constexpr int B_STAGE = 2 * B_PLANE;
 constexpr int STAGES = 4;
 constexpr int OFF_B = STAGES * A_STAGE;
 constexpr int OFF_BAR = OFF_B + STAGES * B_STAGE;    // 196608
@@ -42,8 +48,8 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t adesc, uin
 }
 
 struct HeadParams {
-    const float* ft;         // FT features
-    const float* wt;         // tiled global_head weight [KCH][64][4]
+    const float* ft;         // FT features: [m_tile][2 planes][KCH][128][4]
+    const float* wt;         // tiled global_head weight [2 planes][KCH][64][4]
     float* partial;          // [ksplit][m_tiles*128][64]
     int m_tiles, ksplit;
 };
@@ -70,15 +76,17 @@ __global__ void __launch_bounds__(192, 1) global_head_umma_kernel(const __grid_c
     const uint32_t tmem = *tmem_slot;
     if (warp == 0) {
         if (lane == 0) {
-            const uint8_t* a = reinterpret_cast<const uint8_t*>(p.ft) + ((size_t)mt * KCH + chunk0) * 2048;
+            const uint8_t* a = reinterpret_cast<const uint8_t*>(p.ft) + ((size_t)mt * 2 * KCH + chunk0) * 2048;
             const uint8_t* b = reinterpret_cast<const uint8_t*>(p.wt) + (size_t)chunk0 * 1024;
             int stage = 0;
             uint32_t phase = 0;
             for (int kb = 0; kb < blocks; ++kb) {
                 mbar_wait(empty + stage, phase ^ 1u);
                 mbar_arrive_expect_tx(full + stage, A_STAGE + B_STAGE);
-                bulk_g2s(smem + stage * A_STAGE, a + (size_t)kb * A_STAGE, A_STAGE, full + stage);
-                bulk_g2s(smem + OFF_B + stage * B_STAGE, b + (size_t)kb * B_STAGE, B_STAGE, full + stage);
+                for (int pl = 0; pl < 2; ++pl) {
+                    bulk_g2s(smem + stage * A_STAGE + pl * A_PLANE, a + ((size_t)pl * KCH * 2048) + (size_t)kb * A_PLANE, A_PLANE, full + stage);
+                    bulk_g2s(smem + OFF_B + stage * B_STAGE + pl * B_PLANE, b + ((size_t)pl * KCH * 1024) + (size_t)kb * B_PLANE, B_PLANE, full + stage);
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
@@ -92,9 +100,13 @@ __global__ void __launch_bounds__(192, 1) global_head_umma_kernel(const __grid_c
             if (elect_one()) {
                 const uint32_t a0 = smem_u32(smem + stage * A_STAGE), b0 = smem_u32(smem + OFF_B + stage * B_STAGE);
 #pragma unroll
-                for (int j = 0; j < KB_CHUNKS / 2; ++j)        // one MMA = K 8 tf32 = two 16-byte chunks
-                    mma_tf32_ss(tmem, make_smem_desc(a0 + j * 4096, 2048, 128), make_smem_desc(b0 + j * 2048, 1024, 128), idesc,
-                                (kb | j) ? 1u : 0u);
+                for (int j = 0; j < KB_CHUNKS / 2; ++j) {      // one MMA = K 8 tf32 = two 16-byte chunks; three terms per k-step
+                    const uint64_t ah = make_smem_desc(a0 + j * 4096, 2048, 128), al = make_smem_desc(a0 + A_PLANE + j * 4096, 2048, 128);
+                    const uint64_t bh = make_smem_desc(b0 + j * 2048, 1024, 128), bl = make_smem_desc(b0 + B_PLANE + j * 2048, 1024, 128);
+                    mma_tf32_ss(tmem, al, bh, idesc, (kb | j) ? 1u : 0u);       // small terms first
+                    mma_tf32_ss(tmem, ah, bl, idesc, 1u);
+                    mma_tf32_ss(tmem, ah, bh, idesc, 1u);
+                }
                 mma_commit(empty + stage);
             }
             __syncwarp();
@@ -150,11 +162,14 @@ __global__ void __launch_bounds__(256) global_head_finish_kernel(const float* __
     }
 }
 
-__global__ void tile_glob_w_kernel(const float* __restrict__ w /*[64][30720]*/, float* __restrict__ wt) {
+__global__ void tile_glob_w_kernel(const float* __restrict__ w /*[64][30720]*/, float* __restrict__ wt /*[2][KCH][64][4]*/) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 64 * 30720) return;
     const int kk = i & 3, n = (i >> 2) & 63, chunk = i >> 8;
-    wt[i] = w[(size_t)n * 30720 + chunk * 4 + kk];
+    const float v = w[(size_t)n * 30720 + chunk * 4 + kk];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    wt[i] = hi;
+    wt[(size_t)64 * 30720 + i] = v - hi;
 }
 
 // FT -> row-major [board*64 + square][480] (only when the caller asked for the features)
@@ -162,7 +177,8 @@ __global__ void untile_features_kernel(const float4* __restrict__ ft, float4* __
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;      // over B * 7680 float4
     if (i >= (int64_t)B * KCH) return;
     const int b = (int)(i / KCH), chunk = (int)(i - (int64_t)b * KCH);
-    out[i] = ft[((size_t)(b >> 7) * KCH + chunk) * 128 + (b & 127)];
+    const float4 h = ft[((size_t)(b >> 7) * 2 * KCH + chunk) * 128 + (b & 127)], l = ft[((size_t)((b >> 7) * 2 + 1) * KCH + chunk) * 128 + (b & 127)];
+    out[i] = make_float4(h.x + l.x, h.y + l.y, h.z + l.z, h.w + l.w);            // hi + lo is exact
 }
 
 }  // namespace
@@ -175,9 +191,9 @@ int launch_tile_glob_w(const float* glob_w, float* wt, cudaStream_t s) {
 
 // K is always cut into the same KSPLIT ranges, whatever the batch size: a board's logits do not depend on how many other
 // boards are in the call (and the fixed-order finishing sum keeps them bit-reproducible).
-// 16 ranges of 30 K-blocks: a single board (one M tile) still spreads the 7.9 MB weight stream over 16 SMs (54 -> ~15 us, the largest
-// kernel of a one-board call), and a 4096-board chunk gets 512 CTAs instead of 128 on 148 SMs.
-constexpr int KSPLIT = 16;
+// 32 ranges of 30 K-blocks: a single board (one M tile) still spreads the 15.7 MB weight stream (hi + lo planes) over 32 SMs (the
+// largest kernel of a one-board call), and a 4096-board chunk gets 1024 CTAs on 148 SMs.
+constexpr int KSPLIT = 32;
 static_assert((KCH / KB_CHUNKS) % KSPLIT == 0, "K blocks must divide evenly over the splits");
 size_t global_head_partial_floats(int B, int num_sms) {
     (void)num_sms;

@@ -4,6 +4,8 @@
 // tables (cross-checked against the CUTLASS sm100 headers vendored in this image).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace umma {
@@ -158,6 +160,35 @@ __device__ __forceinline__ uint32_t pack2_relu(float lo, float hi) {
     uint32_t d;
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
     return d;
+}
+// ---- 16-bit operand formats of the fused stages: F16 = true -> IEEE fp16 (11-bit significand; the default mode), false -> bf16.
+// pk2 / pk2r: two fp32 -> one packed pair (first argument in bits [0,16)), pk2r with ReLU folded into the conversion;
+// up2: packed pair -> float2.  fp16 overflows to +-inf above 65504: the fused kernels raise a device flag (see cv_square) and the
+// bf16 kernels redo the wave.
+template <bool F16>
+__device__ __forceinline__ uint32_t pk2(float lo, float hi) {
+    uint32_t d;
+    if (F16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pk2r(float lo, float hi) {
+    uint32_t d;
+    if (F16) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <bool F16>
+__device__ __forceinline__ float2 up2(uint32_t p) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&p));
+    return make_float2(__uint_as_float(p << 16), __uint_as_float(p & 0xffff0000u));
+}
+// any fp16 lane of the packed pair is +-inf or NaN (exponent field all ones)
+__device__ __forceinline__ uint32_t f16x2_nonfinite(uint32_t p) { return ((p & 0x7C007C00u) + 0x04000400u) & 0x80008000u; }
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc_16(int M, int N) {
+    return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 // arrives on `bar` once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -49,8 +49,9 @@ class EvalAccumulator:
         per = torch.empty((B, 4), dtype=torch.uint8, device=self.device)
         loss = torch.empty(B, dtype=torch.float32, device=self.device)
         p = _native.ptr
-        _native.check(_native.lib().cv_eval_accumulate(p(sq), p(turn), p(cast), p(lab), p(tl), p(cl), p(lg), B, p(self.counters), p(per), p(loss),
-                                                       _native.stream_ptr(self.device)))
+        with torch.cuda.device(self.device):                  # the launch must target the counters' device, not the caller's current one
+            _native.check(_native.lib().cv_eval_accumulate(p(sq), p(turn), p(cast), p(lab), p(tl), p(cl), p(lg), B, p(self.counters), p(per),
+                                                           p(loss), _native.stream_ptr(self.device)))
         self._per_sample.append(per)
         self._loss.append(loss)
         if keep_predictions:                                  # only for the "worst predictions" list (evaluate.py:147-153)

@@ -23,13 +23,14 @@ class ChessSquareCNN(nn.Module):
     """Per-square chess board recognition (reference: models/square.py:10-114).
 
     Extra, B200-specific surface (not in the reference):
-      ``precision``            "bf16" (tensor-core path, default) or "fp32" (exact path)
+      ``precision``            "fp16" (default: tensor-core path, fp16 operands / fp32 accumulation, automatic bf16 recomputation of a wave
+                               whose activations leave the fp16 range), "bf16" (same kernels, bf16 operands) or "fp32" (exact path)
       ``forward_u8(boards)``   raw uint8 boards, ToTensor+Normalize fused into the crop gather
       ``predict_fen(boards)``  uint8 boards -> list of "placement turn castling" strings
     """
 
     def __init__(self, backbone: nn.Module, feature_dim: int, square_overlap: float = 1.5,
-                 square_input_size: int = 64, head_dropout: float = 0.0, precision: str = "bf16"):
+                 square_input_size: int = 64, head_dropout: float = 0.0, precision: str = "fp16"):
         super().__init__()
         if feature_dim != arch.FEATURE_DIM:
             raise ValueError(f"feature_dim must be {arch.FEATURE_DIM} for the compiled trunk (got {feature_dim})")
@@ -62,16 +63,23 @@ class ChessSquareCNN(nn.Module):
         self._lut = None
         self._wave = 0
         self._sig_tensors = None
+        for m in self.modules():                               # load_state_dict on ANY sub-module (assign=True replaces its tensors)
+            m.register_load_state_dict_post_hook(self._on_submodule_load)
+
+    def _on_submodule_load(self, module, incompatible_keys):
+        self._sig_tensors = None
 
     # ------------------------------------------------------------------ native handle / weights
     def _signature(self):
-        """Cheap change detector of the fp32 masters, evaluated on every call: the in-place version counters of the 288 state_dict
-        tensors (load_state_dict / optimizer steps bump them).  The tensor list itself is cached -- building ``state_dict()`` costs
-        ~250 us, more than a whole single-board forward -- and dropped whenever the module is moved or converted (``_apply``)."""
+        """Cheap change detector of the fp32 masters, evaluated on every call: storage pointer, dtype and in-place version counter of every
+        tensor the packer reads (load_state_dict / in-place edits bump the version; ``.data = ...``, ``sub_module.to()/.half()`` and
+        tensor swaps change the pointer).  The list of tensor OBJECTS is cached -- building ``state_dict()`` costs ~250 us, more than a
+        whole single-board forward -- and dropped whenever this module or a sub-module loads a state_dict or is moved / converted
+        through the top-level ``_apply``.  Replacing a Parameter object of a sub-module by hand needs ``invalidate_packed_weights()``."""
         if self._sig_tensors is None:
-            self._sig_tensors = list(self.state_dict(keep_vars=True).values())
-            self._sig_ptrs = tuple(t.data_ptr() for t in self._sig_tensors)
-        return self._sig_ptrs, tuple(t._version for t in self._sig_tensors)
+            self._sig_tensors = [t for k, t in self.state_dict(keep_vars=True).items()
+                                 if not (k.endswith("num_batches_tracked") or k.startswith(("backbone.conv_head", "backbone.norm_head", "class_to_")))]
+        return tuple((t.data_ptr(), t._version, t.dtype) for t in self._sig_tensors)
 
     def _apply(self, fn, *args, **kwargs):
         self._sig_tensors = None                               # .to() / .cuda() / .float() may replace the parameter tensors
@@ -93,7 +101,12 @@ class ChessSquareCNN(nn.Module):
         if self._handle is not None:
             _native.check(_native.lib().cv_square_set_wave(self._handle, self._wave))
 
-    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS, IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_FRONTEND2, IMPL_DEFAULT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 511
+    # cv_square_set_impl bits (include/chessvision_b200.h; tests/test_boundary.py keeps them in step with the header)
+    IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS = (
+        _native.IMPL_POINTWISE_UMMA, _native.IMPL_DENSE_UMMA, _native.IMPL_DEPTHWISE_VEC, _native.IMPL_SPLIT_WEIGHTS)
+    IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_FRONTEND3 = (
+        _native.IMPL_FRONTEND, _native.IMPL_TAIL, _native.IMPL_MID, _native.IMPL_EARLY, _native.IMPL_FRONTEND3)
+    IMPL_DEFAULT, IMPL_ALL = _native.IMPL_DEFAULT, _native.IMPL_ALL
 
     def set_impl(self, mask: int):
         """Select the bf16 kernels (``cv_square_set_impl``); clearing a bit falls back to the plain CUDA-core
@@ -118,6 +131,7 @@ class ChessSquareCNN(nn.Module):
         h = C.c_void_p()
         _native.check(lib.cv_square_create(idx, C.byref(h)))
         self._handle, self._handle_device = h, idx
+        self._packed_sig = None                              # a new handle holds no weights
         self._lut = weights.norm_lut()                       # keep the host table alive across the C call
         _native.check(lib.cv_square_set_norm_lut(h, _native.ptr(self._lut)))
         if self._wave:
@@ -128,12 +142,17 @@ class ChessSquareCNN(nn.Module):
         sig = self._signature()
         if sig != self._packed_sig:
             blob = weights.pack_state_dict(self.state_dict())
-            self.load_packed_blob(blob.to(dev, non_blocking=False))
+            self.load_packed_blob(blob.to(dev, non_blocking=False), update_masters=False)
         return self._handle
 
-    def load_packed_blob(self, blob_dev: torch.Tensor):
+    def load_packed_blob(self, blob_dev: torch.Tensor, update_masters: bool = True):
         """Install an already packed fp32 blob that lives on this model's device (e.g. received by NCCL
-        broadcast, ``replicas.broadcast_packed_weights``) without re-packing from the state_dict."""
+        broadcast, ``replicas.broadcast_packed_weights``) without re-packing from the state_dict.
+
+        ``update_masters`` (default) also writes an equivalent set of tensors into the fp32 masters (``weights.unpack_blob``: folded conv
+        weights + identity BatchNorm), so ``state_dict()``, checkpoints saved from this model and any later re-pack (device move,
+        dtype round trip, sub-module edits) describe the SAME network as the device copy -- re-packing them reproduces the blob bit
+        for bit.  Internal callers that have just packed the blob from these very masters pass False."""
         dev = self._device()
         self._create_handle(dev)
         assert blob_dev.is_cuda and blob_dev.dtype == torch.float32 and blob_dev.numel() == arch.BLOB_FLOATS
@@ -142,6 +161,11 @@ class ChessSquareCNN(nn.Module):
             _native.check(_native.lib().cv_square_load_weights(self._handle, _native.ptr(blob_dev), blob_dev.numel(),
                                                                _native.stream_ptr(dev)))
         self._blob_dev = blob_dev
+        if update_masters:
+            own = self.state_dict(keep_vars=True)
+            with torch.no_grad():
+                for k, v in weights.unpack_blob(blob_dev).items():
+                    own[k].copy_(v.to(own[k].dtype))
         self._packed_sig = self._signature()
 
     def release(self):
@@ -149,6 +173,7 @@ class ChessSquareCNN(nn.Module):
             _native.lib().cv_square_destroy(self._handle)
             self._handle = None
             self._ws = None
+        self._packed_sig = None                                # the next call creates a handle and packs again
 
     def __del__(self):
         try:
@@ -287,6 +312,15 @@ class ChessSquareCNN(nn.Module):
                 _native.ptr(fen), _native.ptr(fen_len)))
         return fen, fen_len
 
+    def fp16_status(self):
+        """-> (weights_fit, overflowed): whether the loaded weights fit fp16, and whether the last fp16-mode forward had to recompute
+        a wave with the bf16 kernels (``cv_square_fp16_status``; synchronises the device)."""
+        dev = self._device()
+        a, b = C.c_int(0), C.c_int(0)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().cv_square_fp16_status(self._ensure_handle(dev), C.byref(a), C.byref(b)))
+        return bool(a.value), bool(b.value)
+
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_native.lib().cv_square_launch_count(self._handle))
 
@@ -327,7 +361,7 @@ class ChessSquareCNN(nn.Module):
 def build_square(model_cfg: dict) -> ChessSquareCNN:
     """Reference factory (models/square.py:117-138): reads ``name``, ``pretrained`` (default True, which
     cannot work offline and raises), ``freeze_backbone``, ``square_overlap``, ``square_input_size``,
-    ``head_dropout``; plus the B200-only optional key ``precision`` ("bf16" default | "fp32")."""
+    ``head_dropout``; plus the B200-only optional key ``precision`` ("fp16" default | "bf16" | "fp32")."""
     model_name = model_cfg.get("name", "mobilenetv4_conv_small_050.e3000_r224_in1k")
     backbone = create_backbone(model_name, pretrained=model_cfg.get("pretrained", True))
     feature_dim = backbone.num_features
@@ -340,5 +374,5 @@ def build_square(model_cfg: dict) -> ChessSquareCNN:
         square_overlap=model_cfg.get("square_overlap", 1.5),
         square_input_size=model_cfg.get("square_input_size", 64),
         head_dropout=model_cfg.get("head_dropout", 0.0),
-        precision=model_cfg.get("precision", "bf16"),
+        precision=model_cfg.get("precision", "fp16"),
     )

@@ -59,6 +59,44 @@ def pack_state_dict(sd) -> torch.Tensor:
     return torch.from_numpy(blob)
 
 
+def unpack_blob(blob) -> dict:
+    """Packed fp32 blob -> an EQUIVALENT set of state_dict tensors (the inverse of ``pack_state_dict`` up to the BatchNorm fold):
+    every conv gets its folded weight, its BatchNorm becomes the identity scale with the folded bias (weight 1, bias b', running_mean 0,
+    running_var 1 - eps, so that g / sqrt(var + eps) == 1 to 7e-9 -- re-packing reproduces the blob bit for bit).  Used by
+    ``ChessSquareCNN.load_packed_blob`` so that the fp32 masters of a model that received its weights as a blob (NCCL broadcast,
+    ``checkpoint.load_packed``) describe the same network as the device copy.  The unused conv_head / norm_head tensors are not touched."""
+    b = blob.detach().to("cpu", torch.float32).numpy() if isinstance(blob, torch.Tensor) else np.asarray(blob, np.float32)
+    off = {name: (o, n) for name, o, n in arch.BLOB_LAYOUT}
+
+    def get(name):
+        o, n = off[name]
+        return b[o:o + n]
+
+    out = {}
+    for layer in arch.LAYERS:
+        w = get(f"L{layer.index}.w")
+        if layer.kind == arch.DEPTHWISE:
+            conv = w.reshape(layer.k, layer.k, layer.cout).transpose(2, 0, 1)[:, None]                        # (C, 1, k, k)
+        else:
+            conv = w.reshape(layer.k, layer.k, layer.cin, layer.cout).transpose(3, 2, 0, 1)                   # (O, I, k, k)
+        pre = "backbone."
+        out[pre + layer.conv_key] = torch.from_numpy(np.ascontiguousarray(conv))
+        bn = pre + layer.bn_key
+        out[bn + ".weight"] = torch.ones(layer.cout)
+        out[bn + ".bias"] = torch.from_numpy(get(f"L{layer.index}.b").copy())
+        out[bn + ".running_mean"] = torch.zeros(layer.cout)
+        out[bn + ".running_var"] = torch.full((layer.cout,), 1.0 - arch.BN_EPS)
+    hw, hb = get("head_w").reshape(arch.HEAD_ROWS, arch.FEATURE_DIM), get("head_b")
+    out["type_head.1.weight"], out["color_head.1.weight"] = torch.from_numpy(hw[:7].copy()), torch.from_numpy(hw[7:].copy())
+    out["type_head.1.bias"], out["color_head.1.bias"] = torch.from_numpy(hb[:7].copy()), torch.from_numpy(hb[7:].copy())
+    out["global_head.1.weight"] = torch.from_numpy(get("glob_w").reshape(arch.GLOBAL_HIDDEN, arch.GLOBAL_IN).copy())
+    out["global_head.1.bias"] = torch.from_numpy(get("glob_b").copy())
+    tw, tb = get("tc_w").reshape(arch.TC_ROWS, arch.GLOBAL_HIDDEN), get("tc_b")
+    out["turn_head.weight"], out["castling_head.weight"] = torch.from_numpy(tw[:1].copy()), torch.from_numpy(tw[1:].copy())
+    out["turn_head.bias"], out["castling_head.bias"] = torch.from_numpy(tb[:1].copy()), torch.from_numpy(tb[1:].copy())
+    return out
+
+
 def norm_lut() -> torch.Tensor:
     """(3,256) fp32 table of ToTensor+Normalize (dataset.py:177-181) computed with torch's own fp32 ops so the
     fused uint8 path reproduces the reference transform bit for bit."""

@@ -38,7 +38,15 @@ typedef enum cv_status {
     CV_ERR_WORKSPACE = -4   /* workspace too small */
 } cv_status;
 
-enum { CV_PRECISION_FP32 = 0, CV_PRECISION_BF16 = 1 };
+/* Arithmetic of a forward:
+ *   CV_PRECISION_FP32  fp32 activations and weights, fp32 accumulation (CUDA-core kernels): the 1e-5 parity mode;
+ *   CV_PRECISION_FP16  (the default of the Python surface) tensor-core path with IEEE fp16 operands, fp32 accumulation in tensor
+ *                      memory, fp32 residual stream, fp32 pooled features.  Needs the fused kernels (default cv_square_set_impl mask).
+ *                      fp16 overflows above 65504: weights are range-checked when loaded, activations on the device -- a wave in which
+ *                      a value leaves the range is recomputed by the bf16 kernels inside the same call (no host synchronisation;
+ *                      cv_square_fp16_status reports it).  Weights that do not fit make this mode identical to CV_PRECISION_BF16;
+ *   CV_PRECISION_BF16  the same kernels with bf16 operands (8-bit significands, fp32 range; W = W_hi + W_lo in the early stages). */
+enum { CV_PRECISION_FP32 = 0, CV_PRECISION_BF16 = 1, CV_PRECISION_FP16 = 2 };
 enum { CV_LAYOUT_HWC = 0, CV_LAYOUT_CHW = 1 };           /* uint8 board layouts: (B,H,H,3) / (B,3,H,H) */
 enum { CV_DIST_UNIFORM = 0, CV_DIST_STRUCTURED = 1 };    /* synthetic board distributions */
 enum { CV_KIND_DENSE = 0, CV_KIND_POINTWISE = 1, CV_KIND_DEPTHWISE = 2 };
@@ -182,6 +190,11 @@ int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts);
 
 /* Number of kernels this library has launched on behalf of `h` since creation (bench bookkeeping). */
 int64_t cv_square_launch_count(const cv_square* h);
+
+/* CV_PRECISION_FP16 bookkeeping: *weights_fit = 1 when every GEMM weight loaded into `h` fits fp16 (otherwise the mode runs the bf16
+ * kernels), *overflowed = 1 when the LAST CV_PRECISION_FP16 forward on `h` had to recompute a wave with the bf16 kernels.
+ * Synchronises the device (reads a device flag).  Either pointer may be NULL. */
+int cv_square_fp16_status(cv_square* h, int* weights_fit, int* overflowed);
 
 /* ---- on-device evaluation bookkeeping (replaces the per-batch host loop of evaluate.py:74-155) --------------------------
  * One batch of logits (device, fp32: squares (B,832), turn (B,1), castling (B,4)) against labels (device, uint8: class per

@@ -1,7 +1,11 @@
 """Parity of the CUDA path (through the C-ABI) against the CPU oracle and the reference's golden outputs.
 
-Bars (BASELINE.json north_star): crop indices and FEN strings bit-exact; logits within 1e-5 (fp32 mode) and
-1e-2 (bf16 mode) of the reference, measured as max|delta| / max|reference|.
+Bars (BASELINE.json north_star): crop indices and FEN strings bit-exact; logits within 1e-5 (fp32 mode) and 1e-2 (the 16-bit
+tensor-core mode) of the reference, measured as max|delta| / max|reference|.  The 16-bit mode that is timed and shipped as the
+default is "fp16" (fp16 operands, fp32 accumulation): it is held to the 1e-2 bar on every output, on the calibrated weights too.
+"bf16" (the same kernels with bf16 operands) is the fall-back the fp16 mode recomputes a wave with when an activation leaves the
+fp16 range; its 8-bit significands cannot meet 1e-2 on the calibrated weights -- neither can PyTorch's own bf16 execution of the
+reference graph, the yard-stick its tests use -- and its bounds below are what it measures, not the north_star bar.
 """
 import ctypes
 
@@ -17,7 +21,8 @@ from oracle import square_oracle as oracle
 pytestmark = pytest.mark.gpu
 
 FP32_TOL = 1e-5          # north_star: "1e-5 in fp32"
-BF16_TOL = 1e-2          # north_star: "1e-2 relative in bf16"
+BF16_TOL = 1e-2          # north_star: "1e-2 relative" for the 16-bit mode
+F16_TOL = 1e-2           # the default mode (fp16 operands): max|delta| / max|reference| on every output
 
 
 def rel_err(got, ref):
@@ -89,7 +94,7 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("mask", [2047, 1023, 511, 255, 127, 63, 31, 15, 7, 0])
+@pytest.mark.parametrize("mask", [1023, 511, 255, 127, 63, 31, 15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     """bf16 path: fused front end + tensor-core kernels (mask 31, the default), layer-granular tensor-core kernels
     with split hi+lo weights (15), with plain bf16 weights (7), and the plain CUDA-core kernels (0) against the
@@ -107,7 +112,7 @@ def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
             got = gpu_model.tap_layer(xd, l.index, precision="bf16").cpu().numpy()
             ref = taps[l.key].permute(0, 2, 3, 1).numpy()
             e = rel_err(got, ref)
-            assert e < 3e-2, f"mask {mask} layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 storage, 45 layers deep
+            assert e < 3e-2, f"mask {mask} layer {l.index} {l.key}: bf16 rel err {e:.3e}"      # bf16 fall-back mode: 8-bit significands, 45 layers deep
     finally:
         gpu_model.set_impl(1023)
 
@@ -149,20 +154,6 @@ def test_fused_early_stage_matches_layer_granular_kernels(gpu_model, gold_state,
     assert torch.equal(fused["features"], sep["features"]), "same arithmetic (bf16 storage, hi+lo weights, fp32 accumulate): identical bits expected"
 
 
-def test_split_mid_stage_equals_op_synchronous_kernel(gpu_model):
-    """blocks.2 as two independent 8-crop warp groups with a weight-streaming warp (bit 1024, opt-in) vs the op-synchronous kernel:
-    same arithmetic in the same order -> identical bits, for full and ragged tile counts."""
-    for n in (1, 5, 37):
-        bd = torch.from_numpy(boards_u8(256, n, first=400)).cuda()
-        a = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
-        gpu_model.set_impl(2047)
-        try:
-            b = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
-        finally:
-            gpu_model.set_impl(1023)
-        assert all(torch.equal(a[k], b[k]) for k in a), n
-
-
 @pytest.mark.parametrize("n", [1, 7, 80])
 def test_fused_mid_stage_matches_layer_granular_kernels(gpu_model, gold_state, n):
     """blocks.2.* (19 conv layers) as one persistent kernel (bit 64) on top of the fused tail, vs the layer-granular
@@ -181,7 +172,10 @@ def test_fused_mid_stage_matches_layer_granular_kernels(gpu_model, gold_state, n
         e_f, e_s = rel_err(fused[k].cpu().numpy(), ref[k].numpy()), rel_err(sep[k].cpu().numpy(), ref[k].numpy())
         print(f"n={n} {k}: rel err fused mid+tail {e_f:.3e}, fused tail only {e_s:.3e}")
         assert e_f <= 1.25 * e_s + 1e-3, (k, e_f, e_s)
-    assert rel_err(fused["features"].cpu().numpy(), ref["features"].numpy()) < 1.2e-2
+    assert rel_err(fused["features"].cpu().numpy(), ref["features"].numpy()) < 1.2e-2       # bf16 fall-back mode
+    f16 = gpu_model.forward_u8(bd, precision="fp16", return_features=True)                   # the default mode: the north_star bar
+    for k in ("features", "squares"):
+        assert rel_err(f16[k].cpu().numpy(), ref[k].numpy()) < F16_TOL, k
 
 
 @pytest.mark.parametrize("n", [1, 7, 80])
@@ -203,7 +197,7 @@ def test_fused_tail_matches_layer_granular_kernels(gpu_model, gold_state, n):
         e_f, e_s = rel_err(fused[k].cpu().numpy(), ref[k].numpy()), rel_err(sep[k].cpu().numpy(), ref[k].numpy())
         print(f"n={n} {k}: rel err fused tail {e_f:.3e}, layer-granular {e_s:.3e}")
         assert e_f <= 1.25 * e_s + 1e-3, (k, e_f, e_s)
-    assert rel_err(fused["features"].cpu().numpy(), ref["features"].numpy()) < 1.2e-2
+    assert rel_err(fused["features"].cpu().numpy(), ref["features"].numpy()) < 1.2e-2       # bf16 fall-back mode
 
 
 @pytest.mark.parametrize("H,n", [(256, 5), (512, 3), (64, 3)])
@@ -234,21 +228,21 @@ def test_fused_front_end_matches_layer_granular_kernels(gpu_model, gold_state, H
             assert torch.equal(a["features"], b["features"]), layout
     finally:
         gpu_model.set_impl(1023)
-    # second / third generation front ends (uint8 HWC: TMA-staged windows, separable fp16 resize; third generation = fp16 stem
-    # operands, column-slab tiles): same result up to bf16 rounding
+    # third-generation front end (uint8 HWC: TMA-staged windows, separable fp16 resize, fp16 stem operands, column-slab tiles):
+    # same result up to bf16 rounding; in fp16 mode both front ends feed the fp16 stages within the north_star bar
     full = oracle.forward(x, gold_state, return_features=True)["features"].numpy()
     ud = torch.from_numpy(u8).cuda()
     v3 = gpu_model.forward_u8(ud, precision="bf16", return_features=True)["features"].cpu().numpy()
-    gpu_model.set_impl(511)
-    try:
-        v2 = gpu_model.forward_u8(ud, precision="bf16", return_features=True)["features"].cpu().numpy()
-    finally:
-        gpu_model.set_impl(1023)
-    e3, e2, e1 = rel_err(v3, full), rel_err(v2, full), rel_err(b["features"].cpu().numpy(), full)
-    print(f"H={H}: features rel err front end v3 {e3:.3e}, v2 {e2:.3e}, v1 {e1:.3e}")
-    assert e2 <= 1.25 * e1 + 1e-3 and e3 <= 1.25 * e1 + 1e-3
+    e3, e1 = rel_err(v3, full), rel_err(b["features"].cpu().numpy(), full)
+    print(f"H={H}: features rel err front end v3 {e3:.3e}, v1 {e1:.3e}")
+    assert e3 <= 1.25 * e1 + 1e-3
     if H <= 256:
-        assert not np.array_equal(v3, v2)       # the third generation really ran (different rounding points)
+        assert not np.array_equal(v3, b["features"].cpu().numpy())       # the third generation really ran (different rounding points)
+    f3 = gpu_model.forward_u8(ud, precision="fp16", return_features=True)["features"].cpu().numpy()
+    chw = torch.from_numpy(np.ascontiguousarray(u8.transpose(0, 3, 1, 2))).cuda()
+    f1 = gpu_model.forward_u8(chw, layout="chw", precision="fp16", return_features=True)["features"].cpu().numpy()    # first generation, fp16 output
+    print(f"H={H}: fp16 mode features rel err front end v3 {rel_err(f3, full):.3e}, v1 {rel_err(f1, full):.3e}")
+    assert rel_err(f3, full) < F16_TOL and rel_err(f1, full) < F16_TOL
 
 
 @pytest.mark.parametrize("H", [96, 160, 352, 448])
@@ -261,8 +255,9 @@ def test_other_board_sizes(gpu_model, gold_state, H):
     o32 = gpu_model.forward_u8(bd, precision="fp32")
     assert rel_err(o32["squares"].cpu().numpy(), ref["squares"].numpy()) < FP32_TOL
     assert gpu_model.predict_fen(bd, precision="fp32") == oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy())
-    o16 = gpu_model.forward_u8(bd, precision="bf16", return_features=True)
-    assert rel_err(o16["features"].cpu().numpy(), ref["features"].numpy()) < 1e-2
+    o16 = gpu_model.forward_u8(bd, precision="fp16", return_features=True)
+    for k in ("features", "squares"):
+        assert rel_err(o16[k].cpu().numpy(), ref[k].numpy()) < F16_TOL, k
 
 
 # ------------------------------------------------------------------------------------------ full forward
@@ -353,6 +348,63 @@ def test_forward_bf16_on_calibrated_weights(gpu_model, golden, gold_state, H, n)
     assert agree.mean() >= yard_agree
 
 
+@pytest.mark.parametrize("H,n", [(256, 64), (512, 16)])
+def test_forward_fp16_meets_the_north_star_bar_on_calibrated_weights(gpu_model, gold_state, H, n):
+    """The default mode (fp16 operands, fp32 accumulation, split-tf32 global head) on the HARD weights (perturbed
+    BatchNorm statistics, heads calibrated to subtract the feature mean): every output within 1e-2 of the fp32 reference, measured
+    as max|delta| / max|reference| -- the north_star bar, not an RMS figure and not a yard-stick comparison -- with identical argmax
+    on every square whose fp32 top-2 margin exceeds twice the observed logit error, and no fall-back to the bf16 kernels."""
+    u8 = boards_u8(H, n, first=300)
+    ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
+    out = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="fp16", return_features=True)
+    errs = {k: rel_err(out[k].cpu().numpy(), ref[k].numpy()) for k in ("squares", "turn", "castling", "features")}
+    print(f"H={H}: fp16-mode max rel err vs fp32 reference:", errs)
+    for k, e in errs.items():
+        assert e < F16_TOL, (k, e)
+    ref_sq, got_sq = ref["squares"].numpy().reshape(-1, 13), out["squares"].cpu().numpy().reshape(-1, 13)
+    agree = ref_sq.argmax(-1) == got_sq.argmax(-1)
+    srt = np.sort(ref_sq, -1)
+    safe = (srt[:, -1] - srt[:, -2]) > 2 * np.abs(ref_sq - got_sq).max()
+    print(f"fp16 square agreement raw {agree.mean():.4f}, margin-filtered {agree[safe].mean():.4f} on {safe.mean():.2%} of squares")
+    assert agree[safe].all() and agree.mean() > 0.99
+    assert gpu_model.fp16_status() == (True, False)
+
+
+def test_fp16_overflow_falls_back_to_the_bf16_kernels(square_cfg, gold_state):
+    """An activation that leaves the fp16 range (here: one BatchNorm scale blown up 3000x) raises the device flag inside the fp16
+    kernels; the bf16 kernels enqueued behind them recompute the wave in the same call: finite outputs, bit-identical to bf16 mode.
+    The flag is per call: the next forward with ordinary inputs runs fp16 again."""
+    import chess_vision_b200 as cv
+    st = {k: v.clone() for k, v in gold_state.items()}
+    st["backbone.blocks.2.1.pw_exp.bn.weight"] *= 3000.0
+    m = cv.build_model(square_cfg)
+    m.load_state_dict(st, strict=True)
+    m = m.to("cuda").eval()
+    bd = torch.from_numpy(boards_u8(256, 40)).cuda()
+    o16 = m.forward_u8(bd, precision="fp16", return_features=True)
+    assert m.fp16_status() == (True, True)
+    ob = m.forward_u8(bd, precision="bf16", return_features=True)
+    assert all(torch.equal(o16[k], ob[k]) for k in o16) and bool(torch.isfinite(o16["squares"]).all())
+    assert m.predict_fen(bd, precision="fp16") == m.predict_fen(bd, precision="bf16")
+    host = m.predict_fen(bd.cpu().pin_memory(), precision="fp16")                    # host pipeline: pieces + fall-back pass
+    assert host == m.predict_fen(bd, precision="bf16")
+    st["backbone.blocks.2.1.pw_exp.conv.weight"][0, 0, 0, 0] = 1e6                    # a weight outside the fp16 range: bf16 kernels only
+    m.load_state_dict(st, strict=True)
+    o = m.forward_u8(bd, precision="fp16")
+    assert m.fp16_status()[0] is False
+    assert all(torch.equal(o[k], m.forward_u8(bd, precision="bf16")[k]) for k in o)
+
+
+def test_fp16_mode_needs_the_fused_kernels(gpu_model):
+    bd = torch.from_numpy(boards_u8(64, 2)).cuda()
+    gpu_model.set_impl(15)
+    try:
+        with pytest.raises(_native.NativeError, match="fused kernels"):
+            gpu_model.forward_u8(bd, precision="fp16")
+    finally:
+        gpu_model.set_impl(1023)
+
+
 def test_forward_bf16_on_default_init_weights(square_cfg):
     """The reference's own default initialisation (timm conv init, BatchNorm identity statistics, nn.Linear
     defaults -- what build_model() returns): here the north_star tolerance of 1e-2 holds for the bf16 path."""
@@ -377,22 +429,31 @@ def test_forward_bf16_on_default_init_weights(square_cfg):
     assert errs["squares"] < yerr["squares"], (errs, yerr)
     for k in ("turn", "castling"):                   # near-zero scalar heads under default init: bound by the yard-stick
         assert rms[k] < max(BF16_TOL, yrms[k]), (k, rms[k], yrms[k])
+    out16 = m.forward_u8(torch.from_numpy(u8).cuda(), precision="fp16")
+    e16 = {k: rel_err(out16[k].cpu().numpy(), ref[k].numpy()) for k in ("squares", "turn", "castling")}
+    print("fp16-mode max rel err on default-init weights:", e16)
+    for k in ("squares", "turn", "castling"):
+        assert e16[k] < F16_TOL, (k, e16[k])
     out32 = m.forward_u8(torch.from_numpy(u8).cuda(), precision="fp32")
     for k in ("squares", "turn", "castling"):
         assert rel_err(out32[k].cpu().numpy(), ref[k].numpy()) < FP32_TOL, k
 
 
-def test_large_batch_bf16_against_oracle(gpu_model, gold_state):
-    """300 boards = 3 waves of the tensor-core pipeline with many tiles per persistent CTA (multi-stage smem ring,
-    double-buffered TMEM accumulators wrap around): every board's trunk features against the fp32 oracle."""
+@pytest.mark.parametrize("prec,tol", [("fp16", F16_TOL), ("bf16", 1.5e-2)])
+def test_large_batch_16bit_against_oracle(gpu_model, gold_state, prec, tol):
+    """300 boards with many tiles per persistent CTA (multi-stage smem rings, TMEM accumulators wrap around): every board's trunk
+    features and piece logits against the fp32 oracle -- 1e-2 in the default fp16 mode; the bf16 fall-back measures 1.5e-2."""
     n = 300
     u8 = boards_u8(256, n, first=1000)
     ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
-    out = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="bf16", return_features=True)
+    out = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision=prec, return_features=True)
     d = (out["features"].cpu() - ref["features"]).abs().reshape(n, -1).max(1).values / ref["features"].abs().max()
-    print(f"bf16 features rel err over {n} boards: max {float(d.max()):.3e} median {float(d.median()):.3e}")
-    assert float(d.max()) < 1.5e-2
-    small = gpu_model.forward_u8(torch.from_numpy(u8[:2]).cuda(), precision="bf16")
+    print(f"{prec} features rel err over {n} boards: max {float(d.max()):.3e} median {float(d.median()):.3e}")
+    assert float(d.max()) < tol
+    if prec == "fp16":
+        for k in ("squares", "turn", "castling"):
+            assert rel_err(out[k].cpu().numpy(), ref[k].numpy()) < F16_TOL, k
+    small = gpu_model.forward_u8(torch.from_numpy(u8[:2]).cuda(), precision=prec)
     assert torch.equal(small["squares"], out["squares"][:2])          # batch size does not change a board's result
 
 
@@ -489,14 +550,14 @@ def test_predict_from_png_like_reference(gpu_model, golden, tmp_path):
             Image.fromarray(u8[i]).save(p)
             assert cv.predict(gpu_model, str(p), transform, torch.device("cuda")) == meta["predict_png_fen"][i]
     finally:
-        gpu_model.precision = "bf16"
+        gpu_model.precision = "fp16"
 
 
 def test_host_pipeline_many_chunks(gpu_model):
     n = 1100                                                   # > 2 staging chunks of 512
     u8 = torch.from_numpy(boards_u8(64, n, dist=synthetic.DIST_UNIFORM)).pin_memory()    # 64x64 boards keep it quick
-    host = gpu_model.predict_fen(u8, precision="bf16")
-    dev = gpu_model.predict_fen(u8.cuda(), precision="bf16")
+    host = gpu_model.predict_fen(u8, precision="fp16")
+    dev = gpu_model.predict_fen(u8.cuda(), precision="fp16")
     assert host == dev and len(host) == n
 
 
@@ -506,14 +567,14 @@ def test_host_pipeline_pieces_and_fallbacks(gpu_model):
     fp32 mode must all give the strings of the device-resident call."""
     for H, n in ((256, 700), (256, 130), (64, 513), (64, 1)):
         u8 = torch.from_numpy(boards_u8(H, n)).pin_memory()
-        assert gpu_model.predict_fen(u8, precision="bf16") == gpu_model.predict_fen(u8.cuda(), precision="bf16")
+        assert gpu_model.predict_fen(u8, precision="fp16") == gpu_model.predict_fen(u8.cuda(), precision="fp16")
     u8 = torch.from_numpy(boards_u8(64, 600))
     chw = u8.permute(0, 3, 1, 2).contiguous().pin_memory()
-    assert gpu_model.predict_fen(chw, layout="chw", precision="bf16") == gpu_model.predict_fen(chw.cuda(), layout="chw", precision="bf16")
+    assert gpu_model.predict_fen(chw, layout="chw", precision="fp16") == gpu_model.predict_fen(chw.cuda(), layout="chw", precision="fp16")
     assert gpu_model.predict_fen(u8.pin_memory(), precision="fp32") == gpu_model.predict_fen(u8.cuda(), precision="fp32")
     gpu_model.set_wave(128)
     try:
-        assert gpu_model.predict_fen(u8.pin_memory(), precision="bf16") == gpu_model.predict_fen(u8.cuda(), precision="bf16")
+        assert gpu_model.predict_fen(u8.pin_memory(), precision="fp16") == gpu_model.predict_fen(u8.cuda(), precision="fp16")
     finally:
         gpu_model.set_wave(0)
 
@@ -527,20 +588,20 @@ def test_float_entry_takes_the_fast_front_end_only_for_uint8_images(gpu_model):
     mean = torch.tensor(NORM_MEAN, device="cuda").view(1, 3, 1, 1)
     std = torch.tensor(NORM_STD, device="cuda").view(1, 3, 1, 1)
     x = ((u8.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous()          # ToTensor + Normalize, dataset.py:177-181
-    a, b = gpu_model(x, precision="bf16"), gpu_model.forward_u8(u8, precision="bf16")
+    a, b = gpu_model(x, precision="fp16"), gpu_model.forward_u8(u8, precision="fp16")
     assert all(torch.equal(a[k], b[k]) for k in ("squares", "turn", "castling"))
     y = x.clone()
     y[3, 1, 100, 37] += 0.004                                                          # a quarter of a grey level off the grid
     noisy = x + 0.003 * torch.randn_like(x)
     for inp in (y, noisy):
-        got = gpu_model(inp, precision="bf16")
+        got = gpu_model(inp, precision="fp16")
         gpu_model.set_impl(1023 & ~512)
         try:
-            want = gpu_model(inp, precision="bf16")
+            want = gpu_model(inp, precision="fp16")
         finally:
             gpu_model.set_impl(1023)
         assert all(torch.equal(got[k], want[k]) for k in ("squares", "turn", "castling"))
-    assert not torch.equal(gpu_model(y, precision="bf16")["squares"][3], a["squares"][3])   # and the perturbation is not ignored
+    assert not torch.equal(gpu_model(y, precision="fp16")["squares"][3], a["squares"][3])   # and the perturbation is not ignored
 
 
 def test_weight_changes_are_picked_up(square_cfg, gold_state):
@@ -569,19 +630,19 @@ def test_weight_changes_are_picked_up(square_cfg, gold_state):
 
 
 # ------------------------------------------------------------------------------------------ full-size properties
-def test_full_batch_properties_bf16(gpu_model):
-    """BASELINE.json config 2 size (4096 boards, bf16): results must not depend on how the batch is split
+def test_full_batch_properties_16bit(gpu_model):
+    """BASELINE.json config 2 size (4096 boards, the 16-bit default mode): results must not depend on how the batch is split
     (sharding over ranks = slicing the global index range), and the flip re-index is an involution."""
     B = 4096
     L = _native.lib()
     boards = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device="cuda")
     _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 0, B, 256, 1, 1, None, _native.stream_ptr(boards.device)))
-    fen, fen_len = gpu_model.predict_fen_device(boards, precision="bf16")
-    halves = [gpu_model.predict_fen_device(boards[i:i + B // 2].clone(), precision="bf16") for i in (0, B // 2)]
+    fen, fen_len = gpu_model.predict_fen_device(boards, precision="fp16")
+    halves = [gpu_model.predict_fen_device(boards[i:i + B // 2].clone(), precision="fp16") for i in (0, B // 2)]
     assert torch.equal(fen, torch.cat([h[0] for h in halves])) and torch.equal(fen_len, torch.cat([h[1] for h in halves]))
     strs = gpu_model.decode_fen_records(fen, fen_len)
     ones = torch.ones(B, dtype=torch.uint8)
-    fl = gpu_model.predict_fen(boards, flipped=ones, precision="bf16")
+    fl = gpu_model.predict_fen(boards, flipped=ones, precision="fp16")
     for a, b in zip(strs[:256], fl[:256]):
         assert dataset.fen_to_labels(b.split()[0]).tolist() == dataset.fen_to_labels(a.split()[0]).tolist()[::-1]
         assert a.split()[1:] == b.split()[1:]
@@ -605,7 +666,7 @@ def test_config1_64_boards_fp32_fen_matches_cpu(gpu_model, gold_state):
 @pytest.mark.parametrize("B", [1, 2, 3, 17, 64, 257, 1000])
 def test_config4_batch_sweep_with_flips(gpu_model, gold_state, B):
     """configs[3]: flipped-orientation boards + full FEN over a batch sweep.  fp32 mode is bit-exact against the oracle
-    for every batch size; in bf16 mode a board's record must not depend on the batch it travels in."""
+    for every batch size; in the 16-bit mode a board's record must not depend on the batch it travels in."""
     first = 7000
     u8 = boards_u8(256, B, first=first)
     fl = synthetic.synth_flipped(first, B, 1)
@@ -616,10 +677,10 @@ def test_config4_batch_sweep_with_flips(gpu_model, gold_state, B):
     flt = torch.from_numpy(fl)
     got32 = gpu_model.predict_fen(bd, flipped=flt, precision="fp32")
     assert got32[:n_ref] == want
-    got16 = gpu_model.predict_fen(bd, flipped=flt, precision="bf16")
-    alone = gpu_model.predict_fen(bd[B - 1:B], flipped=flt[B - 1:B], precision="bf16")
+    got16 = gpu_model.predict_fen(bd, flipped=flt, precision="fp16")
+    alone = gpu_model.predict_fen(bd[B - 1:B], flipped=flt[B - 1:B], precision="fp16")
     assert alone[0] == got16[B - 1]
-    host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), flipped=flt, precision="bf16")
+    host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), flipped=flt, precision="fp16")
     assert host == got16
 
 
@@ -631,11 +692,11 @@ def test_config4_max_batch_65536_properties(gpu_model):
     boards = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device="cuda")
     flips = torch.empty((B,), dtype=torch.uint8, device="cuda")
     _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 10**6, B, 256, 1, 1, _native.ptr(flips), _native.stream_ptr(boards.device)))
-    fen, fen_len = gpu_model.predict_fen_device(boards, flips, precision="bf16")
+    fen, fen_len = gpu_model.predict_fen_device(boards, flips, precision="fp16")
     for lo in (0, 28672, 61440):
-        f2, l2 = gpu_model.predict_fen_device(boards[lo:lo + 4096].clone(), flips[lo:lo + 4096].clone(), precision="bf16")
+        f2, l2 = gpu_model.predict_fen_device(boards[lo:lo + 4096].clone(), flips[lo:lo + 4096].clone(), precision="fp16")
         assert torch.equal(fen[lo:lo + 4096], f2) and torch.equal(fen_len[lo:lo + 4096], l2)
-    plain, plain_len = gpu_model.predict_fen_device(boards[:512], None, precision="bf16")
+    plain, plain_len = gpu_model.predict_fen_device(boards[:512], None, precision="fp16")
     a = gpu_model.decode_fen_records(plain, plain_len)
     b = gpu_model.decode_fen_records(fen[:512], fen_len[:512])
     fl = flips[:512].cpu().numpy()
@@ -665,15 +726,15 @@ def test_config3_stream_sharding_is_rank_count_independent(gpu_model):
         assert np.array_equal(np.concatenate(parts), rec)
 
 
-def test_config5_512_boards_bf16(gpu_model, gold_state):
-    """configs[4]: 512x512 renders (96 -> 64 down-sampling crops), bf16, a batch larger than one wave."""
+def test_config5_512_boards_16bit(gpu_model, gold_state):
+    """configs[4]: 512x512 renders (96 -> 64 down-sampling crops), 16-bit default mode, a batch larger than one wave."""
     n = 600
     L = _native.lib()
     boards = torch.empty((n, 512, 512, 3), dtype=torch.uint8, device="cuda")
     _native.check(L.cv_synth_boards(_native.ptr(boards), 0, 0, n, 512, 1, 1, None, _native.stream_ptr(boards.device)))
-    out = gpu_model.forward_u8(boards, precision="bf16", return_features=True)
+    out = gpu_model.forward_u8(boards, precision="fp16", return_features=True)
     u8 = boards[:6].cpu().numpy()
     ref = oracle.forward(oracle.normalize_u8(u8), gold_state, return_features=True)
-    assert rms_err(out["features"][:6 * 64].cpu().numpy(), ref["features"].numpy()) < BF16_TOL
-    tail = gpu_model.forward_u8(boards[-3:].clone(), precision="bf16", return_features=True)
+    assert rel_err(out["features"][:6 * 64].cpu().numpy(), ref["features"].numpy()) < F16_TOL
+    tail = gpu_model.forward_u8(boards[-3:].clone(), precision="fp16", return_features=True)
     assert torch.equal(tail["squares"], out["squares"][-3:]) and torch.equal(tail["turn"], out["turn"][-3:])
