@@ -365,6 +365,19 @@ def run_native(args):
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))              # events bracket the host-blocking calls
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    # the ceiling e2e can reach at this rank count: plain copies of the same pinned buffers to the same GPUs, all ranks at the same time
+    # (one box: the ranks share the host's PCIe uplinks and memory; profiles/r02_h2d_concurrent.txt)
+    scratch = torch.empty_like(boards)
+    scratch.copy_(host_boards, non_blocking=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        scratch.copy_(host_boards, non_blocking=True)
+    e1.record()
+    barrier()
+    h2d_ms = max_over_ranks(e0.elapsed_time(e1))
+    h2d_ceiling_gbs = world * B * H * H * 3 * args.steps / (h2d_ms / 1e3) / 1e9
+    del scratch
     fens_host = model.decode_fen_records(host_out[0][:4], host_out[1][:4])
     fens_dev = model.decode_fen_records(fen[:4], fen_len[:4])
     same = fens_host == fens_dev
@@ -498,6 +511,9 @@ def run_native(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 3),
                 "d2h_bytes_per_step": int(world * B * (_native.FEN_STRIDE + 1)), "ms_per_step": e2e_ms / args.steps,
                 "host_equals_device_fen": bool(same),
+                "h2d_gbs": world * B * H * H * 3 * args.steps / (e2e_ms / 1e3) / 1e9,
+                "h2d_ceiling_gbs": h2d_ceiling_gbs,       # measured in this run: concurrent plain cudaMemcpyAsync on all ranks
+                "frac_of_measured_h2d": (world * B * H * H * 3 * args.steps / (e2e_ms / 1e3) / 1e9) / h2d_ceiling_gbs,
                 "host_cpus_bound_to_gpu": (len(host_cpus) if host_cpus else 0)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "weights_agree_across_ranks": bool(weights_agree), "sample_fen": fens_dev[0],
