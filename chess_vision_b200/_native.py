@@ -30,6 +30,10 @@ class LayerInfo(C.Structure):
                [("w_offset", C.c_int64), ("b_offset", C.c_int64)]
 
 
+class NamedTensor(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
 _lib = None
 
 
@@ -82,6 +86,7 @@ def lib():
     _sig(L.cv_synth_boards_host, i32, vp, i32, i64, i32, i32, u32, i32, vp)
     _sig(L.cv_fen_from_classes_host, i32, vp, C.c_float, vp, vp)
     _sig(L.cv_square_launch_count, i64, vp)
+    _sig(L.cv_square_pack_weights, i32, vp, i32, vp, sz)
     _sig(L.cv_square_fp16_status, i32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int))
     _sig(L.cv_square_profile, i32, vp, i32)
     _sig(L.cv_square_profile_read, i32, vp, vp, vp)

@@ -18,6 +18,7 @@ from .models import build_model
 from .weights import pack_state_dict
 
 MAGIC = b"CVB200W1"
+RAW_MAGIC = b"CVB200S1"
 _PREFIXES = ("_orig_mod.", "module.")        # torch.compile / DistributedDataParallel wrappers around the trained model
 
 
@@ -55,6 +56,21 @@ def save_packed(path, state_dict, cfg=None):
     with open(path, "wb") as f:
         f.write(MAGIC + struct.pack("<I", len(header)) + header + raw)
     return zlib.crc32(raw)
+
+
+def save_raw_state_dict(path, state_dict):
+    """The reference state_dict as a flat list of named fp32 tensors, for hosts without Python / torch (examples/c_abi_demo.c
+    feeds it to ``cv_square_pack_weights``): RAW_MAGIC | u32 count | per tensor: u16 name bytes | name | i64 numel | fp32 data.
+    Integer bookkeeping tensors (num_batches_tracked, class_to_*) are not written: the path never reads them."""
+    sd = clean_state_dict(state_dict)
+    items = [(k, v.detach().to("cpu", torch.float32).contiguous().numpy()) for k, v in sd.items()
+             if not (k.endswith("num_batches_tracked") or k.startswith("class_to_"))]
+    with open(path, "wb") as f:
+        f.write(RAW_MAGIC + struct.pack("<I", len(items)))
+        for k, a in items:
+            kb = k.encode()
+            f.write(struct.pack("<H", len(kb)) + kb + struct.pack("<q", a.size) + a.astype("<f4").tobytes())
+    return len(items)
 
 
 def load_packed(path):

@@ -64,6 +64,7 @@ struct cv_square {
     size_t tap_n = 0;
     int64_t launches = 0;
     bool profiling = false;                 // CUDA-event marks before every launch (cv_square_profile)
+    bool prof_suspended = false;            // inside the gated bf16 fall-back pass: its launches are timed as ONE slot (CV_PROF_FALLBACK)
     std::vector<cudaEvent_t> prof_pool;
     std::vector<int> prof_slot;             // slot of the launch that FOLLOWS mark i (-1 = end of a call)
     int out_buf[CV_NUM_LAYERS];   // small-buffer index each layer writes (-1: dedicated stem buffer)
@@ -109,7 +110,7 @@ void plan_buffers(cv_square* h) {
 
 // Profiling mark: an event recorded on the launch stream right before the kernel(s) of `slot`.
 inline int prof_mark(cv_square* h, int slot, cudaStream_t s) {
-    if (!h->profiling) return CV_OK;
+    if (!h->profiling || h->prof_suspended) return CV_OK;
     size_t i = h->prof_slot.size();
     if (i >= h->prof_pool.size()) {
         cudaEvent_t e;
@@ -394,12 +395,14 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 ++h->launches;
             }
             for (int pass = 0; pass < n_passes; ++pass) {
-                rc = prof_mark(h, CV_PROF_FRONTEND, s);
+                rc = prof_mark(h, pass == 0 ? CV_PROF_FRONTEND : CV_PROF_FALLBACK, s);
                 if (rc) return rc;
+                h->prof_suspended = pass > 0;                  // the gated fall-back chain is one profiling slot
                 rc = launch_front(h, src, kind, nb, H, g, front_out, by_pieces && pass == 0, f2u, f2u_flag, passes[pass], s);
-                if (rc) return rc;
-                rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 2,
-                                 passes[pass], s);
+                if (rc == CV_OK)
+                    rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 2,
+                                     passes[pass], s);
+                h->prof_suspended = false;
                 if (rc) return rc;
             }
         }

@@ -3,7 +3,8 @@
 The reference turns every batch into Python scalars on the host (about twenty `.item()` / `.cpu()` synchronisations and an
 O(B*64) loop for the confusion matrix, evaluate.py:87-155).  Here one kernel (`cv_eval_accumulate`, csrc/eval.cu) adds a batch
 to exact int64 counters that stay on the device; the host reads them once at the end.  Same names, same report, same summary
-dict; the grouped-by-manifest tables (evaluate.py:234-300) need the reference's dataset manifest and are out of scope.
+dict; the grouped-by-manifest tables (evaluate.py:233-287) are host dictionary work over the per-sample table the kernel emits
+(`grouped_metrics` / `grouped_report`).
 """
 import numpy as np
 import torch
@@ -112,6 +113,73 @@ class EvalAccumulator:
         return "\n".join(L)
 
 
+# ---- grouped metrics (evaluate.py:30-45, 233-287): accuracy by manifest field, from the per-sample table ---------------------------------
+def piece_count_bucket(count):
+    count = int(count)
+    return "endgame (2-10)" if count <= 10 else "midgame (11-20)" if count <= 20 else "opening (21-32)"
+
+
+def castling_category(castling_str):
+    return "none" if castling_str == "-" else "has_rights"
+
+
+GROUPING_FIELDS = {                                           # field -> bucket function, in the reference's order (evaluate.py:239-246)
+    "piece_count": piece_count_bucket,
+    "castling": castling_category,
+    "turn": lambda x: "white" if x == "w" else "black",
+    "has_highlight": lambda x: "highlighted" if x == "1" else "no highlight",
+    "style": lambda x: x,
+    "flipped": lambda x: "flipped" if x == "1" else "normal",
+}
+
+
+def grouped_metrics(dataset, per_sample):
+    """per_sample: the (N,4) uint8 table of ``EvalAccumulator.results()`` (squares wrong, board correct, turn correct, castling-all
+    correct; 255 = not a legal position, the reference's None) in dataset order -> {field: {bucket: counts}} exactly as
+    evaluate.py:253-272 accumulates them.  Needs ``dataset.use_manifest`` and ``dataset.get_metadata(i)`` like the reference."""
+    if not getattr(dataset, "use_manifest", False):
+        return {}
+    per = np.asarray(per_sample)
+    out = {}
+    first = dataset.get_metadata(0)
+    for field, bucket_fn in GROUPING_FIELDS.items():
+        if field not in first:
+            continue
+        groups = {}
+        for i in range(per.shape[0]):
+            g = groups.setdefault(bucket_fn(dataset.get_metadata(i).get(field, "")),
+                                  {"total": 0, "board_correct": 0, "turn_correct": 0, "turn_total": 0, "castling_correct": 0, "castling_total": 0})
+            g["total"] += 1
+            g["board_correct"] += int(per[i, 1])
+            if per[i, 2] != 255:
+                g["turn_total"] += 1
+                g["turn_correct"] += int(per[i, 2])
+            if per[i, 3] != 255:
+                g["castling_total"] += 1
+                g["castling_correct"] += int(per[i, 3])
+        out[field] = groups
+    return out
+
+
+def grouped_report(dataset, per_sample):
+    """The text evaluate.py:248-287 prints (same lines, same formats); empty string without a manifest."""
+    groups_by_field = grouped_metrics(dataset, per_sample)
+    if not getattr(dataset, "use_manifest", False):
+        return ""
+    L = ["", "=" * 60, "GROUPED METRICS", "=" * 60]
+    for field, groups in groups_by_field.items():
+        L += ["", f"By {field}:"]
+        for bucket in sorted(groups):
+            g = groups[bucket]
+            line = f"  {bucket:>20s}: board_acc={(g['board_correct'] / g['total'] if g['total'] > 0 else 0):.4f} (n={g['total']})"
+            if g["turn_total"] > 0:
+                line += f"  turn={g['turn_correct'] / g['turn_total']:.4f}"
+            if g["castling_total"] > 0:
+                line += f"  castling={g['castling_correct'] / g['castling_total']:.4f}"
+            L.append(line)
+    return "\n".join(L)
+
+
 @torch.no_grad()
 def evaluate(model, dataset, loader, device, verbose=True):
     """Drop-in for evaluate.py:47 `evaluate(model, dataset, loader, device)`: same arguments, same summary dict."""
@@ -123,4 +191,7 @@ def evaluate(model, dataset, loader, device, verbose=True):
         acc.update(outputs, labels, keep_predictions=verbose)
     if verbose:
         print(acc.report())
+        grouped = grouped_report(dataset, acc.results()[1])       # evaluate.py:218
+        if grouped:
+            print(grouped)
     return acc.summary()

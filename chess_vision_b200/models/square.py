@@ -324,8 +324,8 @@ class ChessSquareCNN(nn.Module):
     def launch_count(self) -> int:
         return 0 if self._handle is None else int(_native.lib().cv_square_launch_count(self._handle))
 
-    PROF_SLOTS = 53
-    PROF_NAMES = ["crop_gather"] + [f"L{l.index}:{l.key}" for l in arch.LAYERS] + ["pool_heads", "global_head", "fen", "frontend(crop+stem+b0.0)", "tail(blocks.3+4+pool+heads)", "mid(blocks.2)", "early(blocks.0.1+blocks.1)"]
+    PROF_SLOTS = 54
+    PROF_NAMES = ["crop_gather"] + [f"L{l.index}:{l.key}" for l in arch.LAYERS] + ["pool_heads", "global_head", "fen", "frontend(crop+stem+b0.0)", "tail(blocks.3+4+pool+heads)", "mid(blocks.2)", "early(blocks.0.1+blocks.1)", "bf16 fall-back chain (gated off unless fp16 overflowed)"]
 
     def profile(self, enable: bool):
         """Record a CUDA event before every kernel of the path (``cv_square_profile``)."""
@@ -334,7 +334,7 @@ class ChessSquareCNN(nn.Module):
             _native.check(_native.lib().cv_square_profile(self._ensure_handle(dev), int(enable)))
 
     def profile_read(self):
-        """-> (ms[49], launches[49]) summed since the last read; synchronises the device."""
+        """-> (ms[PROF_SLOTS], launches[PROF_SLOTS]) summed since the last read; synchronises the device."""
         ms = np.zeros(self.PROF_SLOTS, np.float64)
         cnt = np.zeros(self.PROF_SLOTS, np.int64)
         _native.check(_native.lib().cv_square_profile_read(self._handle, ms.ctypes.data, cnt.ctypes.data))

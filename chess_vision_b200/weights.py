@@ -59,6 +59,24 @@ def pack_state_dict(sd) -> torch.Tensor:
     return torch.from_numpy(blob)
 
 
+def pack_state_dict_native(sd) -> torch.Tensor:
+    """Same blob through the C-ABI's host-side packer (``cv_square_pack_weights``, csrc/pack.cu): what a host without Python calls.
+    Bit-identical to ``pack_state_dict`` (tests/test_pack_native.py)."""
+    import ctypes as C
+    from . import _native
+    keep, arr = [], []
+    for k, v in sd.items():
+        if k.endswith("num_batches_tracked") or k.startswith("class_to_"):
+            continue
+        t = v.detach().to("cpu", torch.float32).contiguous()
+        keep.append(t)
+        arr.append(_native.NamedTensor(k.encode(), t.data_ptr(), t.numel()))
+    blob = torch.empty(arch.BLOB_FLOATS, dtype=torch.float32)
+    tensors = (_native.NamedTensor * len(arr))(*arr)
+    _native.check(_native.lib().cv_square_pack_weights(C.cast(tensors, C.c_void_p), len(arr), blob.data_ptr(), blob.numel()))
+    return blob
+
+
 def unpack_blob(blob) -> dict:
     """Packed fp32 blob -> an EQUIVALENT set of state_dict tensors (the inverse of ``pack_state_dict`` up to the BatchNorm fold):
     every conv gets its folded weight, its BatchNorm becomes the identity scale with the folded bias (weight 1, bias b', running_mean 0,

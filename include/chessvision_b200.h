@@ -14,7 +14,10 @@
  *     failure on the calling thread; nothing throws across the boundary;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls only enqueue work
  *     on it -- no device synchronisation unless documented;
- *   - one handle per device; a handle is not re-entrant, distinct handles are independent.
+ *   - one handle per device; a handle is NOT re-entrant and serves ONE stream at a time (its workspace-independent scratch -- overflow and
+ *     recovery flags, staging slots of the host path -- is per handle); distinct handles are independent;
+ *   - device pointers of float inputs should be 16-byte aligned (cudaMalloc / torch allocations are); an unaligned x_nchw is accepted
+ *     and takes a slower front end;
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     CV_ERR_CUDA.
  */
@@ -80,34 +83,37 @@ int cv_square_destroy(cv_square* h);
  * tensor-core operand images.  Synchronises `stream` before returning. */
 int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, void* stream);
 
+/* Host-side packer: the tensors of a reference state_dict (HOST fp32 pointers, named exactly as in the checkpoint's ckpt["model"]:
+ * backbone.conv_stem.weight, backbone.bn1.{weight,bias,running_mean,running_var}, backbone.blocks.S.B. ... , type_head.1.weight, ...;
+ * tensors the path never executes -- conv_head, norm_head, num_batches_tracked, class_to_* -- may be omitted) -> the packed blob in
+ * blob_host (cv_weight_blob_floats() floats, HOST).  Folds eval-mode BatchNorm (eps 1e-5) in double precision exactly like
+ * chess_vision_b200/weights.py: both packers emit the same bits.  Replaces build_model() + load_state_dict() (predict.py:56-57) for a
+ * host that has no Python; copy blob_host to the device and hand it to cv_square_load_weights.  No GPU needed. */
+typedef struct cv_named_tensor { const char* name; const float* data; int64_t numel; } cv_named_tensor;
+int cv_square_pack_weights(const cv_named_tensor* tensors, int n_tensors, float* blob_host, size_t blob_floats);
+
 /* Normalisation table lut[c*256+u] = (u/255 - mean[c]) / std[c] for the uint8 entry points; the default is
  * the timm IMAGENET mean/std the reference reads from pretrained_cfg (dataset.py:157-160).  HOST pointer,
  * 768 floats. */
 int cv_square_set_norm_lut(cv_square* h, const float* lut_host);
 
-/* Which kernels the bf16 path runs (bit mask; default = all): the tcgen05/TMEM GEMMs for the pointwise and dense
- * 3x3 convolutions and the 16-byte-vectorised depthwise kernel.  Clearing a bit selects the plain CUDA-core
- * kernel for that layer class instead -- used by the parity tests to cross-check the tensor-core path.
- * CV_IMPL_SPLIT_WEIGHTS: the GEMM weights are held as W = W_hi + W_lo (two bf16 images, resident in shared
- * memory) and every k-step issues two MMAs, removing the weight-quantisation half of the bf16 error at no
- * HBM cost (tensor throughput is far from the bound on this path).
- * CV_IMPL_FRONTEND: crop gather + conv_stem + blocks.0.0 run as ONE persistent tcgen05 kernel whose crop and stem
- * activations never leave shared memory (kernels_frontend.cu); cleared = three layer-granular kernels.
- * CV_IMPL_TAIL: blocks.3.* + blocks.4.0 + pool + type/color heads + combine run as ONE persistent kernel (21 conv
- * layers; activations in shared memory, residual stream in tensor memory; kernels_backend.cu).
- * CV_IMPL_MID (needs CV_IMPL_TAIL): blocks.2.* (19 conv layers) run as one persistent kernel of the same design.
- * CV_IMPL_EARLY (needs CV_IMPL_MID): blocks.0.1 + blocks.1.0 + blocks.1.1 as one persistent kernel (2 CTAs per SM).
- * CV_IMPL_FRONTEND2 (with CV_IMPL_FRONTEND, uint8 HWC boards): the front end stages board windows by TMA and resizes
- * separably from shared memory (kernels_frontend2.cu); other sources use the first-generation front end.
- * CV_IMPL_FRONTEND3 (with CV_IMPL_FRONTEND, uint8 HWC boards whose crop window fits shared memory: 256x256 and 512x512 do):
- * column-slab M tiles, fp16 stem operands (the resized pixels are bounded), stem output pipelined as half images
- * (kernels_frontend3.cu); falls back to the second generation otherwise.
- * CV_IMPL_MID_SPLIT (with CV_IMPL_MID; NOT in the default mask): the blocks.2 kernel runs the two 8-crop halves of a tile as
- * two independent warp groups with a dedicated weight-streaming warp (same arithmetic, same bits as the op-synchronous
- * kernel).  Measured 3 % slower than the op-synchronous kernel on B200 -- kept as the experiment DESIGN.md section 6 cites. */
+/* Which kernels the 16-bit modes run (bit mask; default = all fused).  Clearing a bit selects a less fused kernel for that part of the
+ * path -- used by the parity tests to cross-check every fused stage against layer-granular kernels.  The layer-granular kernels are
+ * bf16 only, so CV_PRECISION_FP16 needs FRONTEND | EARLY | MID | TAIL.
+ * CV_IMPL_POINTWISE_UMMA / CV_IMPL_DENSE_UMMA / CV_IMPL_DEPTHWISE_VEC: layer-granular tcgen05 GEMMs for the pointwise / dense 3x3
+ *   convolutions and the 16-byte-vectorised depthwise kernel (cleared: plain CUDA-core kernels).
+ * CV_IMPL_SPLIT_WEIGHTS: layer-granular GEMM weights held as W = W_hi + W_lo (two bf16 images, two MMAs per k-step).
+ * CV_IMPL_FRONTEND: crop gather + conv_stem + blocks.0.0 as ONE persistent tcgen05 kernel (crops and stem activations never leave
+ *   shared memory); CV_IMPL_FRONTEND3 (with it, uint8 HWC boards whose crop window fits shared memory: 256x256 and 512x512 do): the
+ *   third-generation kernel (kernels_frontend3.cu: TMA-staged board windows, separable half2 resize, column-slab M tiles, fp16 stem
+ *   operands, pipelined half images); other sources take the first generation (kernels_frontend.cu).
+ * CV_IMPL_TAIL: blocks.3.* + blocks.4.0 + pool + type/color heads + combine as ONE persistent kernel (21 conv layers; activations in
+ *   shared memory, residual stream in tensor memory).  CV_IMPL_MID (needs TAIL): blocks.2.* (19 conv layers) likewise.
+ *   CV_IMPL_EARLY (needs MID): blocks.0.1 + blocks.1.0 + blocks.1.1 likewise (2 CTAs per SM).
+ * Bits 256 and 1024 selected kernels that were retired in round 2 (second-generation front end, warp-group stage C): accepted, ignored. */
 enum { CV_IMPL_POINTWISE_UMMA = 1, CV_IMPL_DENSE_UMMA = 2, CV_IMPL_DEPTHWISE_VEC = 4, CV_IMPL_SPLIT_WEIGHTS = 8,
-       CV_IMPL_FRONTEND = 16, CV_IMPL_TAIL = 32, CV_IMPL_MID = 64, CV_IMPL_EARLY = 128, CV_IMPL_FRONTEND2 = 256, CV_IMPL_FRONTEND3 = 512,
-       CV_IMPL_MID_SPLIT = 1024, CV_IMPL_DEFAULT = 1023, CV_IMPL_ALL = 2047 };
+       CV_IMPL_FRONTEND = 16, CV_IMPL_TAIL = 32, CV_IMPL_MID = 64, CV_IMPL_EARLY = 128, CV_IMPL_RETIRED_256 = 256, CV_IMPL_FRONTEND3 = 512,
+       CV_IMPL_RETIRED_1024 = 1024, CV_IMPL_DEFAULT = 1023, CV_IMPL_ALL = 2047 };
 int cv_square_set_impl(cv_square* h, int mask);
 
 /* Boards per internal wave (the stage hand-offs of one wave share the workspace). 0 = library default (4096 with the fused kernels). */
@@ -184,7 +190,9 @@ int cv_fen_from_classes_host(const int8_t* classes, float turn, const float* cas
  * number of launches since the last read: slot CV_PROF_CROP, CV_PROF_LAYER0 + layer (0..44),
  * CV_PROF_POOL_HEADS, CV_PROF_GLOBAL_HEAD, CV_PROF_FEN, CV_PROF_FRONTEND (fused crop+stem+blocks.0.0).  ms/counts: HOST arrays of CV_PROF_SLOTS. */
 enum { CV_PROF_CROP = 0, CV_PROF_LAYER0 = 1, CV_PROF_POOL_HEADS = 46, CV_PROF_GLOBAL_HEAD = 47, CV_PROF_FEN = 48,
-       CV_PROF_FRONTEND = 49, CV_PROF_TAIL = 50, CV_PROF_MID = 51, CV_PROF_EARLY = 52, CV_PROF_SLOTS = 53 };
+       CV_PROF_FRONTEND = 49, CV_PROF_TAIL = 50, CV_PROF_MID = 51, CV_PROF_EARLY = 52,
+       CV_PROF_FALLBACK = 53 /* the gated bf16 chain of a CV_PRECISION_FP16 wave: ~4 kernels that exit at once unless fp16 overflowed */,
+       CV_PROF_SLOTS = 54 };
 int cv_square_profile(cv_square* h, int enable);
 int cv_square_profile_read(cv_square* h, double* ms, int64_t* counts);
 

@@ -90,3 +90,31 @@ def summary(counters, loss_sum):
             "board_acc": int(c[CORRECT_BOARDS]) / int(c[TOTAL_BOARDS]), "turn_acc": int(c[CORRECT_TURN]) / tl,
             "castling_acc": int(c[CORRECT_CASTLING_ALL]) / tl, "full_fen_acc": int(c[CORRECT_FULL_FEN]) / tl,
             "total_boards": int(c[TOTAL_BOARDS]), "total_legal": int(c[TOTAL_LEGAL])}
+
+
+# ---- grouped metrics (evaluate.py:233-287): seeded manifest rows + per-sample results ---------------------------------------
+def synth_manifest(seed=5, n=97):
+    """Manifest rows (strings, as csv.DictReader yields them; the fields evaluate.py:239-246 groups by) + the per-sample table (N,4) uint8 of
+    EvalAccumulator, seeded: inputs of the grouped-metrics golden (oracle/make_golden_eval_grouped.py, tests/test_eval_cpu.py)."""
+    rng = np.random.default_rng(seed)
+    styles = ["alpha", "cburnett", "merida", "wood"]
+    meta = [{"piece_count": str(int(rng.integers(2, 33))), "castling": ["-", "KQkq", "Kq", "k"][int(rng.integers(0, 4))],
+             "turn": "wb"[int(rng.integers(0, 2))], "has_highlight": str(int(rng.integers(0, 2))), "style": styles[int(rng.integers(0, 4))],
+             "flipped": str(int(rng.integers(0, 2)))} for _ in range(n)]
+    legal = rng.random(n) < 0.8
+    per = np.zeros((n, 4), np.uint8)
+    per[:, 0] = rng.integers(0, 4, n) * (rng.random(n) < 0.4)
+    per[:, 1] = per[:, 0] == 0
+    per[:, 2] = np.where(legal, rng.random(n) < 0.9, 255)
+    per[:, 3] = np.where(legal, rng.random(n) < 0.7, 255)
+    return meta, per
+
+
+class ManifestStub:
+    use_manifest = True
+
+    def __init__(self, meta):
+        self.meta = meta
+
+    def get_metadata(self, i):
+        return self.meta[i]

@@ -45,4 +45,11 @@ def test_c_host_prints_the_same_fens_as_python(tmp_path):
     r = subprocess.run([exe, wpath, str(n)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     u8 = torch.from_numpy(synthetic.synth_boards(0, n, 256, 1, synthetic.DIST_STRUCTURED)).cuda()
-    assert r.stdout.split("\n")[:n] == model.predict_fen(u8, precision="fp32")
+    want = model.predict_fen(u8, precision="fp32")
+    assert r.stdout.split("\n")[:n] == want
+    # the same from the RAW state_dict: the C host folds BatchNorm and packs through cv_square_pack_weights
+    spath = str(tmp_path / "w.cvs")
+    assert checkpoint.save_raw_state_dict(spath, state) == 240
+    r = subprocess.run([exe, spath, str(n)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split("\n")[:n] == want

@@ -79,3 +79,20 @@ def test_counter_layout_matches_header():
     from chess_vision_b200 import evaluate as ev
     for name in ("TOTAL_BOARDS", "CORRECT_FULL_FEN", "PIECE_CORRECT", "PIECE_TOTAL", "CONFUSION", "TURN_CONFUSION", "N_COUNTERS"):
         assert getattr(ev, name) == getattr(eo, name)
+
+
+def test_grouped_report_matches_the_reference_line_for_line():
+    """chess_vision_b200.evaluate.grouped_report (host dictionary work over the kernel's per-sample table) against the text the
+    reference's own print_grouped_metrics (evaluate.py:233-287) printed for the same manifest rows and per-sample results
+    (tests/golden/eval_grouped_reference.json, oracle/make_golden_eval_grouped.py)."""
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "eval_grouped_reference.json")))
+    meta, per = eo.synth_manifest(gold["seed"], gold["n"])
+    from chess_vision_b200.evaluate import grouped_metrics, grouped_report
+    assert grouped_report(eo.ManifestStub(meta), per) + "\n" == gold["report"]
+    g = grouped_metrics(eo.ManifestStub(meta), per)
+    assert list(g) == ["piece_count", "castling", "turn", "has_highlight", "style", "flipped"]
+    assert sum(v["total"] for v in g["flipped"].values()) == gold["n"]
+
+    class NoManifest:
+        use_manifest = False
+    assert grouped_report(NoManifest(), per) == "" and grouped_metrics(NoManifest(), per) == {}
