@@ -1,0 +1,570 @@
+// Baseline JPEG decode for the step BEFORE the hot path: replaces `Image.open(path).convert("RGB")` (predict.py:19,
+// dataset.py ChessDataset) for the files the reference's datagen writes (datagen/generate.js:26-27: JPEG, quality 90).
+//
+// The arithmetic of that call lives in Pillow on libjpeg-turbo with libjpeg's decompression defaults; it is integer work end to end, so
+// the bar is BIT-EXACT (oracle/jpeg_oracle.py pins the restatement to Pillow's own decodes):
+//   entropy decode   baseline sequential Huffman, restart intervals (jdhuff.c)            -> huff_decode_interval  (host AND device)
+//   dequant + IDCT   JDCT_ISLOW, "accurate integer" (jidctint.c jpeg_idct_islow)          -> jpeg_idct_kernel
+//   upsampling       do_fancy_upsampling triangle filters (jdsample.c), replicated edges  -> jpeg_color_kernel (on the fly)
+//   colour           ycc_rgb_convert 16-bit fixed-point tables (jdcolor.c)                -> jpeg_color_kernel
+//
+// Data flow per batch: the COMPRESSED files go over PCIe (about a tenth of the decoded pixels), one device thread per restart interval
+// (or per file) walks its bit stream and writes quantised coefficients [block][64] int16; the IDCT kernel turns 32 blocks per CTA into
+// samples through shared memory (8 threads per block: column pass, row pass); the colour kernel reads the three planes, upsamples
+// chroma on the fly and writes RGB bytes (B, H, W, 3) -- the layout cv_resize_bilinear_u8 / cv_square_predict_u8 take.
+// The same Huffman routine compiled for the host backs cv_jpeg_decode_coefficients_host (no-GPU tests against the oracle).
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "internal.h"
+
+namespace {
+
+// ---- per-file description (built on the host by parse_jpeg) ------------------------------------------------------------------------
+struct HuffTab {
+    uint8_t look_nbits[256];      // 8-bit look-ahead: code length (0 = longer than 8 bits)
+    uint8_t look_sym[256];
+    int32_t maxcode[18];          // largest code of length l (-1 if none), maxcode[17] = sentinel
+    int32_t valoffset[17];        // vals index of the first code of length l minus that code
+    uint8_t vals[256];
+};
+
+struct JpegDesc {
+    int32_t width, height, ncomp;
+    int32_t hs, vs;               // luma sampling factors (chroma is 1x1)
+    int32_t mcux, mcuy;           // MCU grid
+    int32_t restart;              // MCUs per restart interval (0 = none)
+    int32_t dc_sel[3], ac_sel[3], q_sel[3];
+    uint16_t qt[4][64];           // quantisation tables, natural order
+    HuffTab dc[4], ac[4];
+    int64_t data_off, data_len;   // entropy-coded segment inside the staged file bytes (offset from the batch buffer start)
+    int64_t coef_off[3];          // int16 offset of each component's first block inside the batch coefficient buffer
+    int32_t bw[3], bh[3];         // block grid of each component (whole MCUs)
+    int64_t plane_off[3];         // byte offset of each component's sample plane inside the batch plane buffer
+};
+
+struct Interval {                 // one independently decodable run of MCUs
+    int32_t image;
+    int32_t mcu0, n_mcu;
+    int64_t byte0, byte1;         // within the batch buffer
+};
+
+inline const uint8_t* zigzag_tab() {
+    static const uint8_t z[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    return z;
+}
+__constant__ uint8_t kZigzagDev[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+                                       35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+// ---- bit reader + Huffman decode (jdhuff.c semantics: 0xFF00 -> 0xFF, zeros after a marker), shared by host and device --------------
+struct BitReader {
+    const uint8_t* p;
+    const uint8_t* end;
+    uint64_t acc;
+    int n;
+    bool hit_marker;
+    __host__ __device__ inline void fill() {
+        while (n <= 56) {
+            uint32_t b = 0;
+            if (!hit_marker && p < end) {
+                b = *p;
+                if (b == 0xFF) {
+                    if (p + 1 < end && p[1] == 0) p += 2;
+                    else { hit_marker = true; b = 0; }
+                } else ++p;
+            }
+            acc = (acc << 8) | b;
+            n += 8;
+        }
+    }
+    __host__ __device__ inline uint32_t peek(int k) { return (uint32_t)(acc >> (n - k)) & ((1u << k) - 1u); }
+    __host__ __device__ inline void skip(int k) { n -= k; }
+};
+
+__host__ __device__ inline int huff_symbol(BitReader& br, const HuffTab& t) {
+    if (br.n < 32) br.fill();                               // the slow path below peeks up to 17 bits
+    const uint32_t look = br.peek(8);
+    int nb = t.look_nbits[look];
+    if (nb) { br.skip(nb); return t.look_sym[look]; }
+    int32_t code = (int32_t)look;
+    nb = 8;
+    do {
+        ++nb;
+        code = (int32_t)br.peek(nb);
+    } while (nb < 17 && code > t.maxcode[nb]);
+    if (nb > 16) { br.skip(16); return 0; }                 // corrupt code: libjpeg warns and returns 0
+    br.skip(nb);
+    return t.vals[(code + t.valoffset[nb]) & 255];
+}
+
+__host__ __device__ inline int huff_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+// Decodes the MCUs [mcu0, mcu0 + n_mcu) of one file from its own byte range; coefficient blocks are written whole (zeros included).
+__host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const uint8_t* bytes, int64_t byte0, int64_t byte1, int mcu0, int n_mcu,
+                                                    int16_t* coef, const uint8_t* zz) {
+    BitReader br{bytes + byte0, bytes + byte1, 0, 0, false};
+    int pred[3] = {0, 0, 0};
+    for (int m = mcu0; m < mcu0 + n_mcu; ++m) {
+        const int my = m / d.mcux, mx = m - my * d.mcux;
+        for (int c = 0; c < d.ncomp; ++c) {
+            const int ch = c == 0 ? d.hs : 1, cv = c == 0 ? d.vs : 1;
+            const HuffTab& dct = d.dc[d.dc_sel[c]];
+            const HuffTab& act = d.ac[d.ac_sel[c]];
+            for (int by = 0; by < cv; ++by)
+                for (int bx = 0; bx < ch; ++bx) {
+                    alignas(16) int16_t blk[64];
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) blk[i] = 0;
+                    int s = huff_symbol(br, dct);
+                    if (s) {
+                        if (br.n < 16) br.fill();
+                        const int v = (int)br.peek(s);
+                        br.skip(s);
+                        pred[c] += huff_extend(v, s);
+                    }
+                    blk[0] = (int16_t)pred[c];
+                    for (int k = 1; k < 64;) {
+                        const int rs = huff_symbol(br, act);
+                        const int r = rs >> 4;
+                        s = rs & 15;
+                        if (s == 0) {
+                            if (r != 15) break;
+                            k += 16;
+                            continue;
+                        }
+                        k += r;
+                        if (k > 63) break;
+                        if (br.n < 16) br.fill();
+                        const int v = (int)br.peek(s);
+                        br.skip(s);
+                        blk[zz[k]] = (int16_t)huff_extend(v, s);
+                        ++k;
+                    }
+                    int16_t* dst = coef + d.coef_off[c] + ((int64_t)(my * cv + by) * d.bw[c] + (mx * ch + bx)) * 64;
+                    const uint4* src4 = reinterpret_cast<const uint4*>(blk);
+                    uint4* dst4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) dst4[i] = src4[i];
+                }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) jpeg_huffman_kernel(const JpegDesc* __restrict__ descs, const Interval* __restrict__ iv, int n_iv,
+                                                          const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_iv) return;
+    const Interval v = iv[i];
+    huff_decode_interval(descs[v.image], bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, kZigzagDev);
+}
+
+// ---- jidctint.c jpeg_idct_islow --------------------------------------------------------------------------------------------------------
+#define CONST_BITS 13
+#define PASS1_BITS 2
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+// the 8-point pass: d[0..7] -> out[0..7], already descaled by `shift` (32-bit arithmetic: |dequantised coefficient| < 2^15 by construction of
+// JPEG's 11-bit DCT range x 8-bit tables holds for baseline files; the SIMD code Pillow actually runs works in 16/32 bits as well)
+__device__ __forceinline__ void idct8(const int (&d)[8], int (&o)[8], int shift) {
+    int z2 = d[2], z3 = d[6];
+    int z1 = (z2 + z3) * 4433;
+    int tmp2 = z1 + z3 * (-15137);
+    int tmp3 = z1 + z2 * 6270;
+    z2 = d[0]; z3 = d[4];
+    int tmp0 = (z2 + z3) << CONST_BITS;
+    int tmp1 = (z2 - z3) << CONST_BITS;
+    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = d[7]; tmp1 = d[5]; tmp2 = d[3]; tmp3 = d[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int z4 = tmp1 + tmp3;
+    const int z5 = (z3 + z4) * 9633;
+    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
+    z1 *= -7373; z2 *= -20995; z3 = z3 * (-16069) + z5; z4 = z4 * (-3196) + z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    o[0] = descale(tmp10 + tmp3, shift); o[7] = descale(tmp10 - tmp3, shift);
+    o[1] = descale(tmp11 + tmp2, shift); o[6] = descale(tmp11 - tmp2, shift);
+    o[2] = descale(tmp12 + tmp1, shift); o[5] = descale(tmp12 - tmp1, shift);
+    o[3] = descale(tmp13 + tmp0, shift); o[4] = descale(tmp13 - tmp0, shift);
+}
+// sample_range_limit + CENTERJSAMPLE indexed with (v & RANGE_MASK) (jdmaster.c prepare_range_limit_table)
+__device__ __forceinline__ uint32_t range_limit(int v) {
+    const int i = v & 1023;
+    return i < 128 ? i + 128 : i < 512 ? 255 : i < 896 ? 0 : i - 896;
+}
+
+struct IdctJob { int32_t image, comp; int64_t first_block, n_blocks; };      // blocks of one component of one image, consecutive in `coef`
+
+// 256 threads = 32 blocks x 8 threads.  Blocks are addressed through a flat (image, component) job list: block g of the batch.
+__global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDesc* __restrict__ descs, const int64_t* __restrict__ job_start /*[n_jobs+1]*/,
+                                                        const IdctJob* __restrict__ jobs, int n_jobs, const int16_t* __restrict__ coef,
+                                                        uint8_t* __restrict__ planes) {
+    __shared__ int ws[32][8][9];
+    const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const int64_t g = (int64_t)blockIdx.x * 32 + lb;
+    const bool active = g < job_start[n_jobs];
+    int lo = 0;
+    if (active) {                                            // binary search of the job that owns block g
+        int hi = n_jobs;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (job_start[mid] <= g) lo = mid; else hi = mid;
+        }
+    }
+    const IdctJob job = jobs[active ? lo : 0];
+    const JpegDesc& d = descs[job.image];
+    const int64_t b = g - job_start[active ? lo : 0];        // block index inside the component
+    if (active) {                                            // pass 1: column t
+        const int16_t* cb = coef + (job.first_block + b) * 64;
+        const uint16_t* q = d.qt[d.q_sel[job.comp]];
+        int in[8], o[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) in[r] = (int)cb[r * 8 + t] * (int)q[r * 8 + t];
+        idct8(in, o, CONST_BITS - PASS1_BITS);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) ws[lb][r][t] = o[r];
+    }
+    __syncthreads();
+    if (active) {                                            // pass 2: row t -> 8 samples
+        int in[8], o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) in[c] = ws[lb][t][c];
+        idct8(in, o, CONST_BITS + PASS1_BITS + 3);
+        const int bw = d.bw[job.comp];
+        const int by = (int)(b / bw), bx = (int)(b - (int64_t)by * bw);
+        uint8_t* dst = planes + d.plane_off[job.comp] + ((int64_t)(by * 8 + t) * bw + bx) * 8;
+        const uint32_t w0 = range_limit(o[0]) | (range_limit(o[1]) << 8) | (range_limit(o[2]) << 16) | (range_limit(o[3]) << 24);
+        const uint32_t w1 = range_limit(o[4]) | (range_limit(o[5]) << 8) | (range_limit(o[6]) << 16) | (range_limit(o[7]) << 24);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(w0, w1);
+    }
+}
+
+// ---- jdsample.c fancy upsampling (on the fly) + jdcolor.c ycc_rgb_convert ---------------------------------------------------------------
+// One thread per output pixel.  Chroma planes have pitch bw*8; their REAL extent is (dw, dh) = ceil(width / hs), ceil(height / vs): the
+// triangle filters replicate the first / last real row and column (jdmainct.c context rows, the edge cases of h2v*_fancy_upsample).
+__device__ __forceinline__ int chroma_at(const uint8_t* pl, int pitch, int dw, int dh, int hs, int vs, int x, int y) {
+    const int cx = hs == 2 ? x >> 1 : x, cy = vs == 2 ? y >> 1 : y;
+    const bool fancy_h = hs == 2 && dw > 2;                  // jinit_upsampler: fancy only when downsampled_width > 2
+    if (hs == 2 && vs == 2) {
+        if (!fancy_h) return pl[cy * pitch + cx];
+        const int oy = (y & 1) ? min(cy + 1, dh - 1) : max(cy - 1, 0);
+        auto colsum = [&](int c) { return 3 * (int)pl[cy * pitch + c] + (int)pl[oy * pitch + c]; };
+        const int cur = colsum(cx);
+        if (x & 1) return cx == dw - 1 ? (cur * 4 + 7) >> 4 : (cur * 3 + colsum(cx + 1) + 7) >> 4;
+        return cx == 0 ? (cur * 4 + 8) >> 4 : (cur * 3 + colsum(cx - 1) + 8) >> 4;
+    }
+    if (hs == 2) {                                           // h2v1
+        const int cur = pl[cy * pitch + cx];
+        if (!fancy_h) return cur;
+        if (x & 1) return cx == dw - 1 ? cur : (3 * cur + (int)pl[cy * pitch + cx + 1] + 2) >> 2;
+        return cx == 0 ? cur : (3 * cur + (int)pl[cy * pitch + cx - 1] + 1) >> 2;
+    }
+    if (vs == 2) {                                           // h1v2 (libjpeg-turbo h1v2_fancy_upsample)
+        const int cur = pl[cy * pitch + cx];
+        if (y & 1) return (3 * cur + (int)pl[min(cy + 1, dh - 1) * pitch + cx] + 2) >> 2;
+        return (3 * cur + (int)pl[max(cy - 1, 0) * pitch + cx] + 1) >> 2;
+    }
+    return pl[cy * pitch + cx];
+}
+#define FIX16(x) ((int)((x) * 65536.0 + 0.5))
+__global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegDesc* __restrict__ descs, const uint8_t* __restrict__ planes, int W, int H,
+                                                         uint8_t* __restrict__ rgb) {
+    const int img = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const JpegDesc& d = descs[img];
+    const int y = i / W, x = i - y * W;
+    const int Y = planes[d.plane_off[0] + (int64_t)y * d.bw[0] * 8 + x];
+    int r = Y, g = Y, b = Y;
+    if (d.ncomp == 3) {
+        const int dw = (d.width + d.hs - 1) / d.hs, dh = (d.height + d.vs - 1) / d.vs;
+        const int cb = chroma_at(planes + d.plane_off[1], d.bw[1] * 8, dw, dh, d.hs, d.vs, x, y) - 128;
+        const int cr = chroma_at(planes + d.plane_off[2], d.bw[2] * 8, dw, dh, d.hs, d.vs, x, y) - 128;
+        r = Y + ((FIX16(1.40200) * cr + 32768) >> 16);
+        g = Y + ((-FIX16(0.34414) * cb + 32768 - FIX16(0.71414) * cr) >> 16);
+        b = Y + ((FIX16(1.77200) * cb + 32768) >> 16);
+        r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
+    }
+    uint8_t* o = rgb + ((int64_t)img * H * W + i) * 3;
+    o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b;
+}
+
+// ---- host: header parsing (jdmarker.c) ----------------------------------------------------------------------------------------------------
+void build_hufftab(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTab* t) {
+    memset(t, 0, sizeof(*t));
+    memcpy(t->vals, vals, (size_t)std::min(nvals, 256));
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; ++l) {
+        t->valoffset[l] = k - code;
+        if (counts[l - 1]) {
+            for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code)
+                if (l <= 8) {                                // every 8-bit pattern starting with this code
+                    const int first = code << (8 - l);
+                    for (int f = 0; f < (1 << (8 - l)); ++f) { t->look_nbits[first + f] = (uint8_t)l; t->look_sym[first + f] = vals[k]; }
+                }
+            t->maxcode[l] = code - 1;
+        } else {
+            t->maxcode[l] = -1;
+        }
+        code <<= 1;
+    }
+    t->maxcode[17] = 0x7fffffff;
+}
+
+// Returns nullptr on success, otherwise the reason the file is not handled here (the caller may then decode it another way).
+const char* parse_jpeg(const uint8_t* f, size_t size, JpegDesc* d) {
+    memset(d, 0, sizeof(*d));
+    if (size < 4 || f[0] != 0xFF || f[1] != 0xD8) return "not a JPEG (no SOI)";
+    size_t pos = 2;
+    bool have_frame = false, have_q[4] = {false, false, false, false}, have_dc[4] = {}, have_ac[4] = {};
+    int comp_id[3] = {0, 0, 0}, comp_h[3] = {1, 1, 1}, comp_v[3] = {1, 1, 1};
+    int adobe_transform = -1;
+    while (true) {
+        if (pos + 4 > size) return "truncated before SOS";
+        if (f[pos] != 0xFF) return "marker expected";
+        while (pos + 1 < size && f[pos + 1] == 0xFF) ++pos;
+        const int m = f[pos + 1];
+        pos += 2;
+        if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+        if (pos + 2 > size) return "truncated segment";
+        const size_t L = ((size_t)f[pos] << 8) | f[pos + 1];
+        if (L < 2 || pos + L > size) return "truncated segment";
+        const uint8_t* seg = f + pos + 2;
+        const size_t n = L - 2;
+        if (m == 0xDB) {
+            for (size_t i = 0; i < n;) {
+                const int pq = seg[i] >> 4, tq = seg[i] & 15;
+                ++i;
+                if (tq > 3 || i + (pq ? 128 : 64) > n) return "bad DQT";
+                for (int k = 0; k < 64; ++k) {
+                    const int v = pq ? ((seg[i + 2 * k] << 8) | seg[i + 2 * k + 1]) : seg[i + k];
+                    d->qt[tq][zigzag_tab()[k]] = (uint16_t)v;
+                }
+                i += pq ? 128 : 64;
+                have_q[tq] = true;
+            }
+        } else if (m == 0xC4) {
+            for (size_t i = 0; i < n;) {
+                if (i + 17 > n) return "bad DHT";
+                const int tc = seg[i] >> 4, th = seg[i] & 15;
+                int total = 0;
+                for (int k = 0; k < 16; ++k) total += seg[i + 1 + k];
+                if (th > 3 || tc > 1 || total > 256 || i + 17 + total > n) return "bad DHT";
+                build_hufftab(seg + i + 1, seg + i + 17, total, tc == 0 ? &d->dc[th] : &d->ac[th]);
+                (tc == 0 ? have_dc : have_ac)[th] = true;
+                i += 17 + total;
+            }
+        } else if (m == 0xC0 || m == 0xC1) {
+            if (n < 6 || seg[0] != 8) return "only 8-bit samples";
+            d->height = (seg[1] << 8) | seg[2];
+            d->width = (seg[3] << 8) | seg[4];
+            d->ncomp = seg[5];
+            if (d->ncomp != 1 && d->ncomp != 3) return "1 or 3 components only (CMYK?)";
+            if (n < (size_t)(6 + 3 * d->ncomp) || d->width <= 0 || d->height <= 0) return "bad SOF";
+            for (int c = 0; c < d->ncomp; ++c) {
+                comp_id[c] = seg[6 + 3 * c];
+                comp_h[c] = seg[7 + 3 * c] >> 4;
+                comp_v[c] = seg[7 + 3 * c] & 15;
+                d->q_sel[c] = seg[8 + 3 * c];
+                if (d->q_sel[c] > 3) return "bad quantisation table selector";
+            }
+            have_frame = true;
+        } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xC7) || (m >= 0xC9 && m <= 0xCB) || (m >= 0xCD && m <= 0xCF)) {
+            return "progressive / lossless / arithmetic JPEG";
+        } else if (m == 0xDD) {
+            if (n < 2) return "bad DRI";
+            d->restart = (seg[0] << 8) | seg[1];
+        } else if (m == 0xEE && n >= 12 && memcmp(seg, "Adobe", 5) == 0) {
+            adobe_transform = seg[11];
+        } else if (m == 0xDA) {
+            if (!have_frame) return "SOS before SOF";
+            if (n < 1 || seg[0] != d->ncomp || n < (size_t)(1 + 2 * d->ncomp)) return "non-interleaved multi-scan file";
+            for (int k = 0; k < d->ncomp; ++k) {
+                int c = -1;
+                for (int j = 0; j < d->ncomp; ++j) if (comp_id[j] == seg[1 + 2 * k]) c = j;
+                if (c != k) return "scan components out of frame order";
+                d->dc_sel[c] = seg[2 + 2 * k] >> 4;
+                d->ac_sel[c] = seg[2 + 2 * k] & 15;
+                if (d->dc_sel[c] > 3 || d->ac_sel[c] > 3 || !have_dc[d->dc_sel[c]] || !have_ac[d->ac_sel[c]] || !have_q[d->q_sel[c]]) return "missing table";
+            }
+            if (d->ncomp == 3) {
+                if (adobe_transform == 0 || (adobe_transform < 0 && comp_id[0] == 82 && comp_id[1] == 71 && comp_id[2] == 66)) return "RGB-coded JPEG";
+                if ((comp_h[0] != 1 && comp_h[0] != 2) || (comp_v[0] != 1 && comp_v[0] != 2) || comp_h[1] != 1 || comp_v[1] != 1 || comp_h[2] != 1 || comp_v[2] != 1)
+                    return "sampling factors other than full-resolution luma with 1x1 chroma";
+                d->hs = comp_h[0];
+                d->vs = comp_v[0];
+            } else {
+                d->hs = d->vs = 1;                            // a single-component scan is never interleaved: 1 block per MCU
+            }
+            d->mcux = (d->width + 8 * d->hs - 1) / (8 * d->hs);
+            d->mcuy = (d->height + 8 * d->vs - 1) / (8 * d->vs);
+            for (int c = 0; c < d->ncomp; ++c) {
+                d->bw[c] = d->mcux * (c == 0 ? d->hs : 1);
+                d->bh[c] = d->mcuy * (c == 0 ? d->vs : 1);
+            }
+            d->data_off = (int64_t)(pos + L);
+            d->data_len = (int64_t)size - d->data_off;
+            return nullptr;
+        }
+        pos += L;
+    }
+}
+
+// restart intervals of one file: byte ranges between RSTn markers (a stuffed 0xFF00 is data, any other marker ends the scan)
+void split_intervals(const uint8_t* f, const JpegDesc& d, int image, int64_t base, std::vector<Interval>* out) {
+    const int total = d.mcux * d.mcuy;
+    const int64_t end = d.data_off + d.data_len;
+    if (d.restart <= 0) {
+        out->push_back(Interval{image, 0, total, base + d.data_off, base + end});
+        return;
+    }
+    int64_t p = d.data_off, start = d.data_off;
+    int mcu = 0;
+    while (mcu < total) {
+        while (p + 1 < end && !(f[p] == 0xFF && f[p + 1] != 0)) ++p;          // next marker (or the end)
+        const bool rst = p + 1 < end && f[p + 1] >= 0xD0 && f[p + 1] <= 0xD7;
+        const int n = std::min(d.restart, total - mcu);
+        out->push_back(Interval{image, mcu, n, base + start, base + (p + 1 < end ? p : end)});
+        mcu += n;
+        if (!rst) {                                           // EOI / garbage: remaining MCUs (if any) decode from an empty range (zeros)
+            if (mcu < total) out->push_back(Interval{image, mcu, total - mcu, base + end, base + end});
+            break;
+        }
+        p += 2;
+        start = p;
+    }
+}
+
+struct Batch {                     // host-side layout of one decode call
+    std::vector<JpegDesc> descs;
+    std::vector<Interval> intervals;
+    std::vector<IdctJob> jobs;
+    std::vector<int64_t> job_start, file_base;               // file_base[i]: offset of file i inside the staged byte buffer
+    int64_t bytes = 0, coef_elems = 0, plane_bytes = 0;
+};
+
+int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, int H, Batch* b) {
+    b->descs.resize(n);
+    b->job_start.push_back(0);
+    for (int i = 0; i < n; ++i) {
+        JpegDesc& d = b->descs[i];
+        const char* why = parse_jpeg(files[i], sizes[i], &d);
+        if (why) { cv_set_error("cv_jpeg_decode: file %d: %s", i, why); return CV_ERR_ARG; }
+        if (d.width != W || d.height != H) { cv_set_error("cv_jpeg_decode: file %d is %dx%d, the batch is %dx%d", i, d.width, d.height, W, H); return CV_ERR_ARG; }
+        b->file_base.push_back(b->bytes);
+        split_intervals(files[i], d, i, b->bytes, &b->intervals);
+        d.data_off += b->bytes;                               // offsets become batch-relative
+        b->bytes += (int64_t)((sizes[i] + 15) & ~(size_t)15);
+        for (int c = 0; c < d.ncomp; ++c) {
+            const int64_t blocks = (int64_t)d.bw[c] * d.bh[c];
+            d.coef_off[c] = b->coef_elems;
+            d.plane_off[c] = b->plane_bytes;
+            b->jobs.push_back(IdctJob{i, c, b->coef_elems / 64, blocks});
+            b->job_start.push_back(b->job_start.back() + blocks);
+            b->coef_elems += blocks * 64;
+            b->plane_bytes += blocks * 64;
+        }
+    }
+    return CV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cv_jpeg_info(const uint8_t* file_host, size_t size, int* width, int* height, int* components) {
+    CV_ARG(file_host != nullptr, "null file");
+    JpegDesc d;
+    const char* why = parse_jpeg(file_host, size, &d);
+    if (why) { cv_set_error("cv_jpeg_info: %s", why); return CV_ERR_ARG; }
+    if (width) *width = d.width;
+    if (height) *height = d.height;
+    if (components) *components = d.ncomp;
+    return CV_OK;
+}
+
+// Host mirror of the entropy decoder (the same inline routine the device kernel runs): quantised coefficients of one file, natural order,
+// component after component, each as [block rows][block columns][64] over whole MCUs.  For the no-GPU tests.
+int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int16_t* coef_host, size_t capacity, int32_t* block_grid /*[3][2] = (bh, bw)*/) {
+    CV_ARG(file_host != nullptr, "null file");
+    Batch b;
+    JpegDesc probe;
+    const char* why = parse_jpeg(file_host, size, &probe);
+    if (why) { cv_set_error("cv_jpeg_decode_coefficients_host: %s", why); return CV_ERR_ARG; }
+    const uint8_t* files[1] = {file_host};
+    int rc = plan_batch(files, &size, 1, probe.width, probe.height, &b);
+    if (rc) return rc;
+    if (block_grid)
+        for (int c = 0; c < 3; ++c) { block_grid[2 * c] = c < probe.ncomp ? b.descs[0].bh[c] : 0; block_grid[2 * c + 1] = c < probe.ncomp ? b.descs[0].bw[c] : 0; }
+    if (!coef_host) return CV_OK;
+    CV_ARG(capacity >= (size_t)b.coef_elems, "coefficient buffer too small");
+    std::vector<int16_t> aligned((size_t)b.coef_elems + 8);
+    int16_t* dst = reinterpret_cast<int16_t*>((reinterpret_cast<uintptr_t>(aligned.data()) + 15) & ~(uintptr_t)15);
+    for (const Interval& v : b.intervals) huff_decode_interval(b.descs[0], file_host, v.byte0, v.byte1, v.mcu0, v.n_mcu, dst, zigzag_tab());
+    memcpy(coef_host, dst, (size_t)b.coef_elems * sizeof(int16_t));
+    return CV_OK;
+}
+
+// n baseline JPEG files of ONE size (host pointers) -> rgb (DEVICE, uint8 (n, H, W, 3)), bit-exact with PIL.Image.open(f).convert("RGB").
+// entropy_on_host != 0 decodes the Huffman streams with host threads and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
+// compressed bytes; results are identical.  Synchronises `stream` before returning (the staging buffers are per call).
+int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host, void* stream) {
+    CV_ARG(n >= 0, "negative batch");
+    if (n == 0) return CV_OK;
+    CV_ARG(files_host && sizes && rgb, "null argument");
+    CV_ARG(W > 0 && H > 0 && W <= 16384 && H <= 16384, "bad image size");
+    CV_ARG(n <= 65535, "at most 65535 files per call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    Batch b;
+    int rc = plan_batch(files_host, sizes, n, W, H, &b);
+    if (rc) return rc;
+    JpegDesc* d_desc = nullptr;
+    Interval* d_iv = nullptr;
+    IdctJob* d_jobs = nullptr;
+    int64_t* d_jstart = nullptr;
+    uint8_t *d_bytes = nullptr, *d_planes = nullptr, *h_bytes = nullptr;
+    int16_t *d_coef = nullptr, *h_coef = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_desc); cudaFree(d_iv); cudaFree(d_jobs); cudaFree(d_jstart); cudaFree(d_bytes); cudaFree(d_planes); cudaFree(d_coef);
+        if (h_bytes) cudaFreeHost(h_bytes);
+        if (h_coef) cudaFreeHost(h_coef);
+    };
+#define JPEG_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cv_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); cleanup(); return CV_ERR_CUDA; } } while (0)
+    JPEG_CUDA(cudaMalloc(&d_desc, b.descs.size() * sizeof(JpegDesc)));
+    JPEG_CUDA(cudaMalloc(&d_jobs, b.jobs.size() * sizeof(IdctJob)));
+    JPEG_CUDA(cudaMalloc(&d_jstart, b.job_start.size() * sizeof(int64_t)));
+    JPEG_CUDA(cudaMalloc(&d_coef, (size_t)b.coef_elems * sizeof(int16_t)));
+    JPEG_CUDA(cudaMalloc(&d_planes, (size_t)b.plane_bytes));
+    JPEG_CUDA(cudaMemcpyAsync(d_desc, b.descs.data(), b.descs.size() * sizeof(JpegDesc), cudaMemcpyHostToDevice, s));
+    JPEG_CUDA(cudaMemcpyAsync(d_jobs, b.jobs.data(), b.jobs.size() * sizeof(IdctJob), cudaMemcpyHostToDevice, s));
+    JPEG_CUDA(cudaMemcpyAsync(d_jstart, b.job_start.data(), b.job_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (entropy_on_host) {
+        JPEG_CUDA(cudaMallocHost(&h_coef, (size_t)b.coef_elems * sizeof(int16_t)));
+        for (const Interval& v : b.intervals) {
+            const int64_t base = b.file_base[v.image];        // interval byte ranges are batch-relative: rebase them onto this file
+            huff_decode_interval(b.descs[v.image], files_host[v.image], v.byte0 - base, v.byte1 - base, v.mcu0, v.n_mcu, h_coef, zigzag_tab());
+        }
+        JPEG_CUDA(cudaMemcpyAsync(d_coef, h_coef, (size_t)b.coef_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+    } else {
+        JPEG_CUDA(cudaMallocHost(&h_bytes, (size_t)b.bytes + 16));
+        for (int i = 0; i < n; ++i) memcpy(h_bytes + b.file_base[i], files_host[i], sizes[i]);
+        JPEG_CUDA(cudaMalloc(&d_bytes, (size_t)b.bytes + 16));
+        JPEG_CUDA(cudaMalloc(&d_iv, b.intervals.size() * sizeof(Interval)));
+        JPEG_CUDA(cudaMemcpyAsync(d_bytes, h_bytes, (size_t)b.bytes, cudaMemcpyHostToDevice, s));
+        JPEG_CUDA(cudaMemcpyAsync(d_iv, b.intervals.data(), b.intervals.size() * sizeof(Interval), cudaMemcpyHostToDevice, s));
+        const int n_iv = (int)b.intervals.size();
+        jpeg_huffman_kernel<<<(n_iv + 63) / 64, 64, 0, s>>>(d_desc, d_iv, n_iv, d_bytes, d_coef);
+        JPEG_CUDA(cudaGetLastError());
+    }
+    const int64_t total_blocks = b.job_start.back();
+    jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, s>>>(d_desc, d_jstart, d_jobs, (int)b.jobs.size(), d_coef, d_planes);
+    JPEG_CUDA(cudaGetLastError());
+    jpeg_color_kernel<<<dim3((unsigned)((W * H + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, d_planes, W, H, rgb);
+    JPEG_CUDA(cudaGetLastError());
+    JPEG_CUDA(cudaStreamSynchronize(s));
+    cleanup();
+#undef JPEG_CUDA
+    return CV_OK;
+}
+
+}  // extern "C"

@@ -1,11 +1,14 @@
 """GPU side of the reference's input transform: the step right before the hot path.
 
-The reference's eval transform is ``Resize((S, S)) -> ToTensor -> Normalize`` on a PIL image (dataset.py:177-181, fed at
-predict.py:19-20).  Here the decoded RGB bytes go to the device as they are; ``resize_boards`` reproduces Pillow's
-``Image.resize((S, S), BILINEAR)`` bit for bit in one CUDA kernel (csrc/resize.cu), and ToTensor + Normalize are fused into the crop
-gather of the model's uint8 entry points.  JPEG/PNG decoding stays on the host (PIL): it is outside the bit-exact boundary.
+The reference opens a board with ``Image.open(path).convert("RGB")`` and transforms it with ``Resize((S, S)) -> ToTensor -> Normalize``
+(predict.py:19-20, dataset.py:177-181).  Here ``decode_jpegs`` decodes baseline JPEG files -- what the reference's datagen writes --
+on the device, bit for bit what Pillow / libjpeg-turbo decode (csrc/jpeg.cu: the COMPRESSED bytes cross PCIe, Huffman streams, integer
+IDCT, fancy upsampling and colour conversion run in CUDA kernels); ``resize_boards`` reproduces Pillow's ``Image.resize((S, S),
+BILINEAR)`` bit for bit (csrc/resize.cu); ToTensor + Normalize are fused into the crop gather of the model's uint8 entry points.
+Files the decoder does not handle (PNG, progressive or CMYK JPEG) are decoded on the host by PIL, exactly as the reference does.
 
-    boards = resize_boards(images_u8.cuda(), 256)              # (B, h, w, 3) uint8 -> (B, 256, 256, 3) uint8, == PIL
+    images = decode_jpegs([open(p, "rb").read() for p in paths], "cuda")   # (B, h, w, 3) uint8 on the device, == PIL
+    boards = resize_boards(images, 256)                                     # (B, 256, 256, 3) uint8, == PIL
     fens = model.predict_fen(boards)
 
 ``predict_images(model, paths)`` is the batched counterpart of ``predict(model, image_path, transform, device)``.
@@ -52,17 +55,80 @@ def resize_boards(images: torch.Tensor, size, out: torch.Tensor = None) -> torch
     return out
 
 
+def jpeg_info(data: bytes):
+    """(width, height, components) of a JPEG the device decoder handles, or None (with the reason in ``_native.lib().cv_last_error()``)
+    for anything else: not a JPEG, progressive / arithmetic / CMYK / RGB-coded files.  Host only, no GPU."""
+    w, h, c = C.c_int(0), C.c_int(0), C.c_int(0)
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    if _native.lib().cv_jpeg_info(C.cast(buf, C.c_void_p), len(data), C.byref(w), C.byref(h), C.byref(c)) != 0:
+        return None
+    return w.value, h.value, c.value
+
+
+def decode_jpegs(files, device, entropy_on_host: bool = False, out: torch.Tensor = None) -> torch.Tensor:
+    """list of JPEG file contents (bytes, all of ONE image size) -> (B, h, w, 3) uint8 tensor on ``device``, bit-exact with
+    ``PIL.Image.open(f).convert("RGB")`` (``cv_jpeg_decode_batch``).  Raises ``NativeError`` for files the decoder does not handle."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("decode_jpegs needs a CUDA device (chess_vision_b200 has no CPU fallback)")
+    n = len(files)
+    if n == 0:
+        return torch.empty((0, 0, 0, 3), dtype=torch.uint8, device=device)
+    info = jpeg_info(files[0])
+    if info is None:
+        _native.check(-1)
+    w, h, _ = info
+    if out is None:
+        out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
+    bufs = [(C.c_char * len(f)).from_buffer_copy(f) for f in files]
+    ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+    sizes = (C.c_size_t * n)(*[len(f) for f in files])
+    with torch.cuda.device(device):
+        _native.check(_native.lib().cv_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(sizes, C.c_void_p), n, w, h, _native.ptr(out),
+                                                         int(entropy_on_host), _native.stream_ptr(device)))
+    return out
+
+
+def jpeg_coefficients_host(data: bytes):
+    """Quantised DCT coefficients of one file from the HOST build of the product's entropy decoder (no GPU): list per component of
+    int16 arrays (block rows, block columns, 64) in natural order -- the no-GPU tests compare them with the oracle's."""
+    L = _native.lib()
+    buf = (C.c_char * len(data)).from_buffer_copy(data)
+    grid = (C.c_int32 * 6)()
+    _native.check(L.cv_jpeg_decode_coefficients_host(C.cast(buf, C.c_void_p), len(data), None, 0, C.cast(grid, C.c_void_p)))
+    shapes = [(grid[2 * c], grid[2 * c + 1]) for c in range(3) if grid[2 * c]]
+    total = sum(a * b * 64 for a, b in shapes)
+    coef = np.zeros(total, np.int16)
+    _native.check(L.cv_jpeg_decode_coefficients_host(C.cast(buf, C.c_void_p), len(data), coef.ctypes.data_as(C.c_void_p), total, None))
+    out, off = [], 0
+    for a, b in shapes:
+        out.append(coef[off:off + a * b * 64].reshape(a, b, 64))
+        off += a * b * 64
+    return out
+
+
 def predict_images(model, image_paths, input_size: int = 256, flipped=None):
-    """Batched ``predict``: decode on the host (PIL, as predict.py:19), then resize + normalise + crop + trunk + heads + FEN on the
-    device.  Images of different sizes are resized in groups of equal size.  Returns list[str] in the order of ``image_paths``."""
-    from PIL import Image
+    """Batched ``predict`` (predict.py:18-42): baseline JPEG files are decoded on the device (bit-exact with PIL), anything else on the
+    host by PIL as the reference does; then resize + normalise + crop + trunk + heads + FEN on the device.  Images of different
+    sizes are decoded / resized in groups of equal size.  Returns list[str] in the order of ``image_paths``."""
     dev = next(model.parameters()).device
-    arrays = [np.asarray(Image.open(p).convert("RGB")) for p in image_paths]
-    boards = torch.empty((len(arrays), input_size, input_size, 3), dtype=torch.uint8, device=dev)
-    by_shape = {}
-    for i, a in enumerate(arrays):
-        by_shape.setdefault(a.shape, []).append(i)
-    for shape, idx in by_shape.items():
-        batch = torch.from_numpy(np.stack([arrays[i] for i in idx])).to(dev)
-        boards[torch.tensor(idx, device=dev)] = resize_boards(batch, input_size)
+    boards = torch.empty((len(image_paths), input_size, input_size, 3), dtype=torch.uint8, device=dev)
+    jpeg_groups, host_groups = {}, {}
+    for i, p in enumerate(image_paths):
+        with open(p, "rb") as fh:
+            data = fh.read()
+        info = jpeg_info(data) if data[:2] == b"\xff\xd8" else None
+        if info is not None:
+            jpeg_groups.setdefault(info[:2], []).append((i, data))
+        else:
+            import io
+            from PIL import Image
+            a = np.asarray(Image.open(io.BytesIO(data)).convert("RGB"))
+            host_groups.setdefault(a.shape, []).append((i, a))
+    for _, items in jpeg_groups.items():
+        idx = torch.tensor([i for i, _ in items], device=dev)
+        boards[idx] = resize_boards(decode_jpegs([d for _, d in items], dev), input_size)
+    for _, items in host_groups.items():
+        idx = torch.tensor([i for i, _ in items], device=dev)
+        boards[idx] = resize_boards(torch.from_numpy(np.stack([a for _, a in items])).to(dev), input_size)
     return model.predict_fen(boards, flipped=flipped)

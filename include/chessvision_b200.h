@@ -229,6 +229,25 @@ int cv_eval_accumulate(const float* squares, const float* turn, const float* cas
 int cv_resize_bilinear_u8(const uint8_t* src, int B, int in_h, int in_w, uint8_t* dst, int out_h, int out_w, void* stream);
 int cv_resize_coeffs_host(int in_size, int out_size, int* ksize, int32_t* bounds_host, int32_t* coeffs_host, int coeffs_capacity);
 
+/* ---- JPEG decode of the board files (replaces PIL's Image.open(path).convert("RGB"), predict.py:19 / dataset.py ChessDataset, for the
+ * files the reference's datagen writes: datagen/generate.js:26-27) -----------------------------------------------------------------------
+ * BIT-EXACT with Pillow 12.2 on libjpeg-turbo at libjpeg's decompression defaults: baseline / extended-sequential Huffman entropy decoding
+ * with restart intervals (jdhuff.c), JDCT_ISLOW integer IDCT (jidctint.c), "fancy" triangle-filter chroma upsampling with replicated
+ * edges (jdsample.c, jdmainct.c), fixed-point YCbCr -> RGB (jdcolor.c); grayscale files give R = G = B.  Handles 8-bit files with 1 or 3
+ * components and 4:4:4 / 4:2:2 / 4:2:0 / 4:4:0 sampling; anything else (progressive, arithmetic, CMYK, RGB-coded) is refused with
+ * CV_ERR_ARG and a reason in cv_last_error() -- the caller then decodes that file the way the reference does.
+ * cv_jpeg_info: size and component count from the header (HOST pointer, no GPU).
+ * cv_jpeg_decode_batch: n files of ONE size (HOST pointers) -> rgb (DEVICE, uint8 (n, height, width, 3)): the layout
+ *   cv_resize_bilinear_u8 / cv_square_predict_u8 take.  By default the COMPRESSED bytes cross PCIe and the Huffman streams are walked on
+ *   the device (one thread per restart interval); entropy_on_host != 0 walks them on the host and ships coefficients (same result).
+ *   Blocks until the pixels are in `rgb` (staging buffers are per call).
+ * cv_jpeg_decode_coefficients_host: the entropy decoder alone, on the host (the same routine the device kernel runs), for no-GPU tests:
+ *   quantised coefficients in natural order, component after component, [block rows][block columns][64]; block_grid (3 x (rows, cols)). */
+int cv_jpeg_info(const uint8_t* file_host, size_t size, int* width, int* height, int* components);
+int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int width, int height, uint8_t* rgb,
+                         int entropy_on_host, void* stream);
+int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int16_t* coef_host, size_t capacity, int32_t* block_grid);
+
 #ifdef __cplusplus
 }
 #endif
