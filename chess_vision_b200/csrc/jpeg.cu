@@ -14,7 +14,12 @@
 // chroma on the fly and writes RGB bytes (B, H, W, 3) -- the layout cv_resize_bilinear_u8 / cv_square_predict_u8 take.
 // The same Huffman routine compiled for the host backs cv_jpeg_decode_coefficients_host (no-GPU tests against the oracle).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "internal.h"
@@ -36,13 +41,15 @@ struct JpegDesc {
     int32_t mcux, mcuy;           // MCU grid
     int32_t restart;              // MCUs per restart interval (0 = none)
     int32_t dc_sel[3], ac_sel[3], q_sel[3];
+    int32_t tset;                 // index of this file's Huffman table set in the batch (files of one encoder share one set)
     uint16_t qt[4][64];           // quantisation tables, natural order
-    HuffTab dc[4], ac[4];
     int64_t data_off, data_len;   // entropy-coded segment inside the staged file bytes (offset from the batch buffer start)
     int64_t coef_off[3];          // int16 offset of each component's first block inside the batch coefficient buffer
     int32_t bw[3], bh[3];         // block grid of each component (whole MCUs)
     int64_t plane_off[3];         // byte offset of each component's sample plane inside the batch plane buffer
 };
+
+struct TableSet { HuffTab dc[4], ac[4]; };      // 7.3 KB: the DHT segments of one file
 
 struct Interval {                 // one independently decodable run of MCUs
     int32_t image;
@@ -65,15 +72,41 @@ struct BitReader {
     uint64_t acc;
     int n;
     bool hit_marker;
+#ifdef __CUDA_ARCH__
+    // device: the stream is read in aligned 8-byte words (one global load per 8 bytes instead of one dependent load per byte; the
+    // staged buffer is padded, so a word may reach past `end` -- those bytes are never consumed)
+    uint64_t word;
+    int word_left;
+    __device__ inline void init() {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const int skip = (int)(a & 7);
+        word = *reinterpret_cast<const uint64_t*>(a - skip) >> (8 * skip);
+        word_left = 8 - skip;
+    }
+    __device__ inline uint32_t next_raw() {                  // byte at p, p advances
+        if (word_left == 0) { word = *reinterpret_cast<const uint64_t*>(p); word_left = 8; }
+        const uint32_t b = (uint32_t)word & 0xffu;
+        word >>= 8; --word_left; ++p;
+        return b;
+    }
+    __device__ inline uint32_t peek_raw() {                  // byte at p without advancing
+        if (word_left == 0) { word = *reinterpret_cast<const uint64_t*>(p); word_left = 8; }
+        return (uint32_t)word & 0xffu;
+    }
+#else
+    inline void init() {}
+    inline uint32_t next_raw() { return *p++; }
+    inline uint32_t peek_raw() { return *p; }
+#endif
     __host__ __device__ inline void fill() {
         while (n <= 56) {
             uint32_t b = 0;
             if (!hit_marker && p < end) {
-                b = *p;
+                b = next_raw();
                 if (b == 0xFF) {
-                    if (p + 1 < end && p[1] == 0) p += 2;
-                    else { hit_marker = true; b = 0; }
-                } else ++p;
+                    if (p < end && peek_raw() == 0) next_raw();          // stuffed zero
+                    else { hit_marker = true; b = 0; }                    // a marker (or the end): zeros from here on, like jdhuff.c
+                }
             }
             acc = (acc << 8) | b;
             n += 8;
@@ -101,22 +134,35 @@ __host__ __device__ inline int huff_symbol(BitReader& br, const HuffTab& t) {
 
 __host__ __device__ inline int huff_extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
 
-// Decodes the MCUs [mcu0, mcu0 + n_mcu) of one file from its own byte range; coefficient blocks are written whole (zeros included).
-__host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const uint8_t* bytes, int64_t byte0, int64_t byte1, int mcu0, int n_mcu,
-                                                    int16_t* coef, const uint8_t* zz) {
-    BitReader br{bytes + byte0, bytes + byte1, 0, 0, false};
+// Decodes the MCUs [mcu0, mcu0 + n_mcu) of one file from its own byte range.  Every coefficient block is zeroed with eight 16-byte
+// stores and the non-zero coefficients are stored as they are decoded (stores do not stall the thread; no local array).
+__host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const TableSet& ts, const uint8_t* bytes, int64_t byte0, int64_t byte1, int mcu0,
+                                                    int n_mcu, int16_t* coef, const uint8_t* zz) {
+    BitReader br;
+    br.p = bytes + byte0; br.end = bytes + byte1; br.acc = 0; br.n = 0; br.hit_marker = false;
+    br.init();
     int pred[3] = {0, 0, 0};
-    for (int m = mcu0; m < mcu0 + n_mcu; ++m) {
-        const int my = m / d.mcux, mx = m - my * d.mcux;
-        for (int c = 0; c < d.ncomp; ++c) {
-            const int ch = c == 0 ? d.hs : 1, cv = c == 0 ? d.vs : 1;
-            const HuffTab& dct = d.dc[d.dc_sel[c]];
-            const HuffTab& act = d.ac[d.ac_sel[c]];
+    // the fields of the descriptor the loop needs, read once (the coefficient stores below could alias `d` as far as the compiler knows)
+    const int mcux = d.mcux, ncomp = d.ncomp, hs = d.hs, vs = d.vs;
+    const HuffTab* dctab[3] = {&ts.dc[d.dc_sel[0]], &ts.dc[d.dc_sel[1]], &ts.dc[d.dc_sel[2]]};
+    const HuffTab* actab[3] = {&ts.ac[d.ac_sel[0]], &ts.ac[d.ac_sel[1]], &ts.ac[d.ac_sel[2]]};
+    int16_t* cbase[3] = {coef + d.coef_off[0], coef + d.coef_off[1], coef + d.coef_off[2]};
+    const int bws[3] = {d.bw[0], d.bw[1], d.bw[2]};
+    int my = mcu0 / mcux, mx = mcu0 - my * mcux;
+    for (int m = 0; m < n_mcu; ++m, ++mx) {
+        if (mx == mcux) { mx = 0; ++my; }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (c >= ncomp) break;
+            const int ch = c == 0 ? hs : 1, cv = c == 0 ? vs : 1;
+            const HuffTab& dct = *dctab[c];
+            const HuffTab& act = *actab[c];
             for (int by = 0; by < cv; ++by)
                 for (int bx = 0; bx < ch; ++bx) {
-                    alignas(16) int16_t blk[64];
+                    int16_t* blk = cbase[c] + ((int64_t)(my * cv + by) * bws[c] + (mx * ch + bx)) * 64;
+                    uint4* blk4 = reinterpret_cast<uint4*>(blk);
 #pragma unroll
-                    for (int i = 0; i < 64; ++i) blk[i] = 0;
+                    for (int i = 0; i < 8; ++i) blk4[i] = make_uint4(0, 0, 0, 0);
                     int s = huff_symbol(br, dct);
                     if (s) {
                         if (br.n < 16) br.fill();
@@ -142,22 +188,32 @@ __host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const ui
                         blk[zz[k]] = (int16_t)huff_extend(v, s);
                         ++k;
                     }
-                    int16_t* dst = coef + d.coef_off[c] + ((int64_t)(my * cv + by) * d.bw[c] + (mx * ch + bx)) * 64;
-                    const uint4* src4 = reinterpret_cast<const uint4*>(blk);
-                    uint4* dst4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) dst4[i] = src4[i];
                 }
         }
     }
 }
 
-__global__ void __launch_bounds__(64) jpeg_huffman_kernel(const JpegDesc* __restrict__ descs, const Interval* __restrict__ iv, int n_iv,
-                                                          const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef) {
+// One thread per interval.  The Huffman table sets of the batch (files written by one encoder share a set) are copied into shared
+// memory when at most `smem_sets` of them exist: a symbol is then two shared-memory look-ups instead of two L2 round trips.
+constexpr int kHuffThreads = 64;
+__global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegDesc* __restrict__ descs, const TableSet* __restrict__ tsets, int n_sets,
+                                                                    int smem_sets, const Interval* __restrict__ iv, int n_iv,
+                                                                    const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef) {
+    extern __shared__ __align__(16) uint8_t huff_smem[];
+    __shared__ uint8_t zz[64];
+    if (smem_sets > 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(tsets);
+        uint4* dst = reinterpret_cast<uint4*>(huff_smem);
+        for (int i = threadIdx.x; i < (int)(n_sets * sizeof(TableSet) / 16); i += kHuffThreads) dst[i] = src[i];
+    }
+    if (threadIdx.x < 64) zz[threadIdx.x] = kZigzagDev[threadIdx.x];
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_iv) return;
     const Interval v = iv[i];
-    huff_decode_interval(descs[v.image], bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, kZigzagDev);
+    const JpegDesc& d = descs[v.image];
+    const TableSet& ts = smem_sets > 0 ? reinterpret_cast<const TableSet*>(huff_smem)[d.tset] : tsets[d.tset];
+    huff_decode_interval(d, ts, bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, zz);
 }
 
 // ---- jidctint.c jpeg_idct_islow --------------------------------------------------------------------------------------------------------
@@ -312,8 +368,9 @@ void build_hufftab(const uint8_t* counts, const uint8_t* vals, int nvals, HuffTa
 }
 
 // Returns nullptr on success, otherwise the reason the file is not handled here (the caller may then decode it another way).
-const char* parse_jpeg(const uint8_t* f, size_t size, JpegDesc* d) {
+const char* parse_jpeg(const uint8_t* f, size_t size, JpegDesc* d, TableSet* ts) {
     memset(d, 0, sizeof(*d));
+    memset(ts, 0, sizeof(*ts));
     if (size < 4 || f[0] != 0xFF || f[1] != 0xD8) return "not a JPEG (no SOI)";
     size_t pos = 2;
     bool have_frame = false, have_q[4] = {false, false, false, false}, have_dc[4] = {}, have_ac[4] = {};
@@ -350,7 +407,7 @@ const char* parse_jpeg(const uint8_t* f, size_t size, JpegDesc* d) {
                 int total = 0;
                 for (int k = 0; k < 16; ++k) total += seg[i + 1 + k];
                 if (th > 3 || tc > 1 || total > 256 || i + 17 + total > n) return "bad DHT";
-                build_hufftab(seg + i + 1, seg + i + 17, total, tc == 0 ? &d->dc[th] : &d->ac[th]);
+                build_hufftab(seg + i + 1, seg + i + 17, total, tc == 0 ? &ts->dc[th] : &ts->ac[th]);
                 (tc == 0 ? have_dc : have_ac)[th] = true;
                 i += 17 + total;
             }
@@ -437,6 +494,7 @@ void split_intervals(const uint8_t* f, const JpegDesc& d, int image, int64_t bas
 
 struct Batch {                     // host-side layout of one decode call
     std::vector<JpegDesc> descs;
+    std::vector<TableSet> tsets;                             // distinct Huffman table sets of the batch
     std::vector<Interval> intervals;
     std::vector<IdctJob> jobs;
     std::vector<int64_t> job_start, file_base;               // file_base[i]: offset of file i inside the staged byte buffer
@@ -448,8 +506,13 @@ int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, i
     b->job_start.push_back(0);
     for (int i = 0; i < n; ++i) {
         JpegDesc& d = b->descs[i];
-        const char* why = parse_jpeg(files[i], sizes[i], &d);
+        TableSet ts;
+        const char* why = parse_jpeg(files[i], sizes[i], &d, &ts);
         if (why) { cv_set_error("cv_jpeg_decode: file %d: %s", i, why); return CV_ERR_ARG; }
+        d.tset = -1;
+        for (int k = (int)b->tsets.size() - 1; k >= 0 && k >= (int)b->tsets.size() - 8 && d.tset < 0; --k)      // look at the most recent sets
+            if (memcmp(&b->tsets[k], &ts, sizeof(ts)) == 0) d.tset = k;
+        if (d.tset < 0) { b->tsets.push_back(ts); d.tset = (int)b->tsets.size() - 1; }
         if (d.width != W || d.height != H) { cv_set_error("cv_jpeg_decode: file %d is %dx%d, the batch is %dx%d", i, d.width, d.height, W, H); return CV_ERR_ARG; }
         b->file_base.push_back(b->bytes);
         split_intervals(files[i], d, i, b->bytes, &b->intervals);
@@ -468,6 +531,39 @@ int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, i
     return CV_OK;
 }
 
+// Staging memory of cv_jpeg_decode_batch, per device, grow-only (cudaMallocHost / cudaMalloc cost milliseconds: never per call).
+struct Scratch {
+    uint8_t *h_stage = nullptr, *d_stage = nullptr, *d_planes = nullptr;
+    int16_t* d_coef = nullptr;
+    size_t stage_cap = 0, coef_cap = 0, plane_cap = 0;
+    int reserve(size_t stage, size_t coef, size_t planes) {
+        if (stage > stage_cap) {
+            if (h_stage) cudaFreeHost(h_stage);
+            if (d_stage) cudaFree(d_stage);
+            h_stage = d_stage = nullptr; stage_cap = 0;
+            const size_t cap = stage + stage / 4;
+            CV_CUDA(cudaMallocHost(&h_stage, cap));
+            CV_CUDA(cudaMalloc(&d_stage, cap));
+            stage_cap = cap;
+        }
+        if (coef > coef_cap) {
+            if (d_coef) cudaFree(d_coef);
+            d_coef = nullptr; coef_cap = 0;
+            CV_CUDA(cudaMalloc(&d_coef, coef + coef / 4));
+            coef_cap = coef + coef / 4;
+        }
+        if (planes > plane_cap) {
+            if (d_planes) cudaFree(d_planes);
+            d_planes = nullptr; plane_cap = 0;
+            CV_CUDA(cudaMalloc(&d_planes, planes + planes / 4));
+            plane_cap = planes + planes / 4;
+        }
+        return CV_OK;
+    }
+};
+std::mutex g_scratch_mutex;
+std::map<int, Scratch> g_scratch;
+
 }  // namespace
 
 extern "C" {
@@ -475,7 +571,8 @@ extern "C" {
 int cv_jpeg_info(const uint8_t* file_host, size_t size, int* width, int* height, int* components) {
     CV_ARG(file_host != nullptr, "null file");
     JpegDesc d;
-    const char* why = parse_jpeg(file_host, size, &d);
+    TableSet ts;
+    const char* why = parse_jpeg(file_host, size, &d, &ts);
     if (why) { cv_set_error("cv_jpeg_info: %s", why); return CV_ERR_ARG; }
     if (width) *width = d.width;
     if (height) *height = d.height;
@@ -489,7 +586,8 @@ int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int1
     CV_ARG(file_host != nullptr, "null file");
     Batch b;
     JpegDesc probe;
-    const char* why = parse_jpeg(file_host, size, &probe);
+    TableSet probe_ts;
+    const char* why = parse_jpeg(file_host, size, &probe, &probe_ts);
     if (why) { cv_set_error("cv_jpeg_decode_coefficients_host: %s", why); return CV_ERR_ARG; }
     const uint8_t* files[1] = {file_host};
     int rc = plan_batch(files, &size, 1, probe.width, probe.height, &b);
@@ -500,14 +598,15 @@ int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int1
     CV_ARG(capacity >= (size_t)b.coef_elems, "coefficient buffer too small");
     std::vector<int16_t> aligned((size_t)b.coef_elems + 8);
     int16_t* dst = reinterpret_cast<int16_t*>((reinterpret_cast<uintptr_t>(aligned.data()) + 15) & ~(uintptr_t)15);
-    for (const Interval& v : b.intervals) huff_decode_interval(b.descs[0], file_host, v.byte0, v.byte1, v.mcu0, v.n_mcu, dst, zigzag_tab());
+    for (const Interval& v : b.intervals) huff_decode_interval(b.descs[0], b.tsets[0], file_host, v.byte0, v.byte1, v.mcu0, v.n_mcu, dst, zigzag_tab());
     memcpy(coef_host, dst, (size_t)b.coef_elems * sizeof(int16_t));
     return CV_OK;
 }
 
 // n baseline JPEG files of ONE size (host pointers) -> rgb (DEVICE, uint8 (n, H, W, 3)), bit-exact with PIL.Image.open(f).convert("RGB").
-// entropy_on_host != 0 decodes the Huffman streams with host threads and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
-// compressed bytes; results are identical.  Synchronises `stream` before returning (the staging buffers are per call).
+// entropy_on_host != 0 decodes the Huffman streams on the host and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
+// compressed bytes; results are identical.  Synchronises `stream` before returning.  Staging memory (pinned host + device) is kept
+// per device for the life of the process and only grows: a steady stream of equal batches allocates once.
 int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host, void* stream) {
     CV_ARG(n >= 0, "negative batch");
     if (n == 0) return CV_OK;
@@ -515,55 +614,79 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     CV_ARG(W > 0 && H > 0 && W <= 16384 && H <= 16384, "bad image size");
     CV_ARG(n <= 65535, "at most 65535 files per call");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+#ifdef CV_EXPERIMENTS                 // CV_JPEG_TRACE=1: wall-clock split of one call (stream synchronised after every stage)
+    const bool trace = getenv("CV_JPEG_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  jpeg %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
+#else
+    auto mark = [](const char*) {};
+#endif
     Batch b;
     int rc = plan_batch(files_host, sizes, n, W, H, &b);
     if (rc) return rc;
-    JpegDesc* d_desc = nullptr;
-    Interval* d_iv = nullptr;
-    IdctJob* d_jobs = nullptr;
-    int64_t* d_jstart = nullptr;
-    uint8_t *d_bytes = nullptr, *d_planes = nullptr, *h_bytes = nullptr;
-    int16_t *d_coef = nullptr, *h_coef = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(d_desc); cudaFree(d_iv); cudaFree(d_jobs); cudaFree(d_jstart); cudaFree(d_bytes); cudaFree(d_planes); cudaFree(d_coef);
-        if (h_bytes) cudaFreeHost(h_bytes);
-        if (h_coef) cudaFreeHost(h_coef);
-    };
-#define JPEG_CUDA(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cv_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); cleanup(); return CV_ERR_CUDA; } } while (0)
-    JPEG_CUDA(cudaMalloc(&d_desc, b.descs.size() * sizeof(JpegDesc)));
-    JPEG_CUDA(cudaMalloc(&d_jobs, b.jobs.size() * sizeof(IdctJob)));
-    JPEG_CUDA(cudaMalloc(&d_jstart, b.job_start.size() * sizeof(int64_t)));
-    JPEG_CUDA(cudaMalloc(&d_coef, (size_t)b.coef_elems * sizeof(int16_t)));
-    JPEG_CUDA(cudaMalloc(&d_planes, (size_t)b.plane_bytes));
-    JPEG_CUDA(cudaMemcpyAsync(d_desc, b.descs.data(), b.descs.size() * sizeof(JpegDesc), cudaMemcpyHostToDevice, s));
-    JPEG_CUDA(cudaMemcpyAsync(d_jobs, b.jobs.data(), b.jobs.size() * sizeof(IdctJob), cudaMemcpyHostToDevice, s));
-    JPEG_CUDA(cudaMemcpyAsync(d_jstart, b.job_start.data(), b.job_start.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    mark("parse headers + plan");
+    int dev = 0;
+    CV_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    Scratch& sc = g_scratch[dev];
+    const size_t desc_b = b.descs.size() * sizeof(JpegDesc), ts_b = b.tsets.size() * sizeof(TableSet), iv_b = b.intervals.size() * sizeof(Interval),
+                 job_b = b.jobs.size() * sizeof(IdctJob), js_b = b.job_start.size() * sizeof(int64_t);
+    // one pinned staging block: [descs | table sets | intervals | jobs | job starts | payload], mirrored by one device block
+    size_t off = 0;
+    auto place = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_desc = place(desc_b), o_ts = place(ts_b), o_iv = place(iv_b), o_job = place(job_b), o_js = place(js_b);
+    const size_t payload = entropy_on_host ? (size_t)b.coef_elems * sizeof(int16_t) : (size_t)b.bytes + 16;
+    const size_t o_pay = place(payload);
+    rc = sc.reserve(off, (size_t)b.coef_elems * sizeof(int16_t), (size_t)b.plane_bytes);
+    if (rc) return rc;
+    memcpy(sc.h_stage + o_desc, b.descs.data(), desc_b);
+    memcpy(sc.h_stage + o_ts, b.tsets.data(), ts_b);
+    memcpy(sc.h_stage + o_iv, b.intervals.data(), iv_b);
+    memcpy(sc.h_stage + o_job, b.jobs.data(), job_b);
+    memcpy(sc.h_stage + o_js, b.job_start.data(), js_b);
+    const JpegDesc* d_desc = reinterpret_cast<const JpegDesc*>(sc.d_stage + o_desc);
+    const TableSet* d_ts = reinterpret_cast<const TableSet*>(sc.d_stage + o_ts);
+    const Interval* d_iv = reinterpret_cast<const Interval*>(sc.d_stage + o_iv);
+    const IdctJob* d_jobs = reinterpret_cast<const IdctJob*>(sc.d_stage + o_job);
+    const int64_t* d_jstart = reinterpret_cast<const int64_t*>(sc.d_stage + o_js);
+    const int16_t* d_coef = sc.d_coef;
     if (entropy_on_host) {
-        JPEG_CUDA(cudaMallocHost(&h_coef, (size_t)b.coef_elems * sizeof(int16_t)));
+        int16_t* h_coef = reinterpret_cast<int16_t*>(sc.h_stage + o_pay);
         for (const Interval& v : b.intervals) {
             const int64_t base = b.file_base[v.image];        // interval byte ranges are batch-relative: rebase them onto this file
-            huff_decode_interval(b.descs[v.image], files_host[v.image], v.byte0 - base, v.byte1 - base, v.mcu0, v.n_mcu, h_coef, zigzag_tab());
+            huff_decode_interval(b.descs[v.image], b.tsets[b.descs[v.image].tset], files_host[v.image], v.byte0 - base, v.byte1 - base, v.mcu0, v.n_mcu,
+                                 h_coef, zigzag_tab());
         }
-        JPEG_CUDA(cudaMemcpyAsync(d_coef, h_coef, (size_t)b.coef_elems * sizeof(int16_t), cudaMemcpyHostToDevice, s));
+        mark("entropy decode (host)");
+        CV_CUDA(cudaMemcpyAsync(sc.d_stage, sc.h_stage, off, cudaMemcpyHostToDevice, s));       // tables + coefficients in one copy
+        d_coef = reinterpret_cast<const int16_t*>(sc.d_stage + o_pay);
+        mark("H2D tables + coefficients");
     } else {
-        JPEG_CUDA(cudaMallocHost(&h_bytes, (size_t)b.bytes + 16));
-        for (int i = 0; i < n; ++i) memcpy(h_bytes + b.file_base[i], files_host[i], sizes[i]);
-        JPEG_CUDA(cudaMalloc(&d_bytes, (size_t)b.bytes + 16));
-        JPEG_CUDA(cudaMalloc(&d_iv, b.intervals.size() * sizeof(Interval)));
-        JPEG_CUDA(cudaMemcpyAsync(d_bytes, h_bytes, (size_t)b.bytes, cudaMemcpyHostToDevice, s));
-        JPEG_CUDA(cudaMemcpyAsync(d_iv, b.intervals.data(), b.intervals.size() * sizeof(Interval), cudaMemcpyHostToDevice, s));
-        const int n_iv = (int)b.intervals.size();
-        jpeg_huffman_kernel<<<(n_iv + 63) / 64, 64, 0, s>>>(d_desc, d_iv, n_iv, d_bytes, d_coef);
-        JPEG_CUDA(cudaGetLastError());
+        for (int i = 0; i < n; ++i) memcpy(sc.h_stage + o_pay + b.file_base[i], files_host[i], sizes[i]);
+        CV_CUDA(cudaMemcpyAsync(sc.d_stage, sc.h_stage, off, cudaMemcpyHostToDevice, s));       // tables + compressed bytes in one copy
+        mark("stage + H2D compressed bytes");
+        const int n_iv = (int)b.intervals.size(), n_sets = (int)b.tsets.size();
+        const int smem_sets = n_sets <= 6 ? n_sets : 0;          // up to 44 KB of shared memory for the table sets
+        const size_t smem = (size_t)smem_sets * sizeof(TableSet);
+        if (smem > 48 * 1024 - 1024) CV_CUDA(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jpeg_huffman_kernel<<<(n_iv + kHuffThreads - 1) / kHuffThreads, kHuffThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, n_iv,
+                                                                                              sc.d_stage + o_pay, sc.d_coef);
+        CV_CHECK_LAUNCH();
+        mark("entropy decode (device)");
     }
     const int64_t total_blocks = b.job_start.back();
-    jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, s>>>(d_desc, d_jstart, d_jobs, (int)b.jobs.size(), d_coef, d_planes);
-    JPEG_CUDA(cudaGetLastError());
-    jpeg_color_kernel<<<dim3((unsigned)((W * H + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, d_planes, W, H, rgb);
-    JPEG_CUDA(cudaGetLastError());
-    JPEG_CUDA(cudaStreamSynchronize(s));
-    cleanup();
-#undef JPEG_CUDA
+    jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, s>>>(d_desc, d_jstart, d_jobs, (int)b.jobs.size(), d_coef, sc.d_planes);
+    CV_CHECK_LAUNCH();
+    jpeg_color_kernel<<<dim3((unsigned)((W * H + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, sc.d_planes, W, H, rgb);
+    CV_CHECK_LAUNCH();
+    CV_CUDA(cudaStreamSynchronize(s));        // the staging block is reused by the next call
+    mark("idct + colour");
     return CV_OK;
 }
 

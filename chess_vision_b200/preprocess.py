@@ -80,8 +80,8 @@ def decode_jpegs(files, device, entropy_on_host: bool = False, out: torch.Tensor
     w, h, _ = info
     if out is None:
         out = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
-    bufs = [(C.c_char * len(f)).from_buffer_copy(f) for f in files]
-    ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+    files = [bytes(f) if not isinstance(f, bytes) else f for f in files]
+    ptrs = (C.c_char_p * n)(*files)                           # pointers INTO the bytes objects (no copy; `files` keeps them alive)
     sizes = (C.c_size_t * n)(*[len(f) for f in files])
     with torch.cuda.device(device):
         _native.check(_native.lib().cv_jpeg_decode_batch(C.cast(ptrs, C.c_void_p), C.cast(sizes, C.c_void_p), n, w, h, _native.ptr(out),
