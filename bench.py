@@ -504,7 +504,7 @@ def run_native(args):
                  for i in order]
 
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------------
-    cpu = None
+    cpu = exact = None
     if world == 1 and not args.no_cpu_baseline:
         sample = args.cpu_sample
         cb = synthetic.synth_boards(0, sample, H, 1, dist_kind)
@@ -539,6 +539,20 @@ def run_native(args):
         cpu[f"fen_agreement_{prec}_vs_cpu_margin_filtered"] = {"value": float(same_t[clear].mean()) if clear.any() else None,
                                                                "boards": int(clear.sum()), "of": sample}
         cpu[f"square_agreement_{prec}_vs_cpu"] = float((got["squares"].cpu().view(sample, 64, 13).argmax(-1) == ref["squares"].view(sample, 64, 13).argmax(-1)).float().mean())
+        # the EXACT mode (fp32 kernels: logits 1e-5, FEN strings identical to the CPU arm) timed on the same sample: what 100 % agreement costs
+        xb = boards[:sample]
+        model.predict_fen_device(xb, precision="fp32")
+        torch.cuda.synchronize()
+        x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x0.record()
+        for _ in range(3):
+            model.predict_fen_device(xb, precision="fp32")
+        x1.record()
+        torch.cuda.synchronize()
+        got32 = model.forward_u8(xb, precision="fp32")
+        exact = {"value": 3 * sample / (x0.elapsed_time(x1) / 1e3), "unit": UNIT, "boards": sample, "precision": "fp32 (CUDA-core kernels)",
+                 "fen_agreement_vs_cpu": cpu["fen_agreement_fp32_vs_cpu"],
+                 "logit_rel_err_vs_cpu": {k: float((got32[k].cpu() - ref[k]).abs().max() / ref[k].abs().max()) for k in ("squares", "turn", "castling")}}
 
     # ---- the step before the path: board resize kernel against its HBM roofline, Pillow beside it ----
     pre = post = jpg = None
@@ -568,7 +582,7 @@ def run_native(args):
                 "host_cpus_bound_to_gpu": (len(host_cpus) if host_cpus else 0)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "kernel_breakdown": breakdown, "weights_agree_across_ranks": bool(weights_agree), "sample_fen": fens_dev[0],
-        "preprocess": pre, "evaluate": post, "jpeg_input": jpg,
+        "exact_mode": exact, "preprocess": pre, "evaluate": post, "jpeg_input": jpg,
     }
     print(json.dumps(line))
     if world > 1:

@@ -56,6 +56,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t polls = 0;
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
+#ifdef CV_WAIT_SLEEP_NS
+        __nanosleep(CV_WAIT_SLEEP_NS);
+#endif
         if ((++polls & 4095u) == 0) {
             const uint64_t now = global_ns();
             if (t0 == 0) t0 = now;
