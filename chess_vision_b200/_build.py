@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libchessvision_b200.so")
-SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_frontend.cu", "kernels_frontend3.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu", "eval.cu", "resize.cu", "pack.cu", "jpeg.cu"]
+SOURCES = ["api.cu", "kernels_generic.cu", "kernels_umma.cu", "kernels_exact.cu", "kernels_frontend.cu", "kernels_frontend3.cu", "kernels_backend.cu", "kernels_head.cu", "fen.cu", "synth.cu", "eval.cu", "resize.cu", "pack.cu", "jpeg.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr"]
 

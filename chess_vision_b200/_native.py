@@ -10,11 +10,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # CV_B200_LIB: an experiment build of the same library (tools/, -DCV_FE_PROFILE ...); never a fallback
 LIB_PATH = os.environ.get("CV_B200_LIB") or os.path.join(_HERE, "libchessvision_b200.so")
 
-PRECISION_FP32, PRECISION_BF16, PRECISION_FP16 = 0, 1, 2
+PRECISION_FP32, PRECISION_BF16, PRECISION_FP16, PRECISION_FP32_SPLIT = 0, 1, 2, 3
 LAYOUT_HWC, LAYOUT_CHW = 0, 1
 FEN_STRIDE = 80
 PRECISIONS = {"fp32": PRECISION_FP32, "float32": PRECISION_FP32, "bf16": PRECISION_BF16, "bfloat16": PRECISION_BF16,
-              "fp16": PRECISION_FP16, "float16": PRECISION_FP16}
+              "fp16": PRECISION_FP16, "float16": PRECISION_FP16, "fp32_split": PRECISION_FP32_SPLIT, "split": PRECISION_FP32_SPLIT}
 # cv_square_set_impl bits (include/chessvision_b200.h; kept in step by tests/test_boundary.py)
 IMPL_POINTWISE_UMMA, IMPL_DENSE_UMMA, IMPL_DEPTHWISE_VEC, IMPL_SPLIT_WEIGHTS = 1, 2, 4, 8
 IMPL_FRONTEND, IMPL_TAIL, IMPL_MID, IMPL_EARLY, IMPL_FRONTEND3 = 16, 32, 64, 128, 512

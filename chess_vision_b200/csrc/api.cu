@@ -24,7 +24,7 @@ namespace {
 
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
-constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512;   // fused stages: persistent kernels want many tiles per SM
+constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512, DEFAULT_WAVE_SPLIT = 128;   // fused stages: persistent kernels want many tiles per SM
 // all four fused stages: only the 8 / 4 / 1.5 KB per crop hand-offs live in the workspace, and every kernel boundary costs ~13 us of
 // drained SMs, so a wave is a whole chunk (measured per 4096 boards: 13.81 ms at 512, 13.64 at 1024, 13.55 at 2048, 13.45 at 4096)
 constexpr int DEFAULT_WAVE_ALL_FUSED = 4096;
@@ -56,6 +56,8 @@ struct cv_square {
     int* flags = nullptr;         // device ints: [0] a weight of stages B-D does not fit fp16, [1] fp16 overflow of the current call (StageGate),
                                   // [2] float entry point: "the input is not a uint8 image"
     bool f16_ok = false;          // every GEMM weight of the fused stages fits fp16 (checked when the weights are packed)
+    uint16_t* x2_wimg = nullptr;  // split-fp16 weight images of the 30 GEMM layers (kernels_exact.cu): [K/8][hi N | lo N][8], scaled by 2^s
+    float x2_unscale[CV_NUM_LAYERS];   // 2^-s per layer
     int num_sms = 148;
     int impl = CV_IMPL_DEFAULT;   // which bf16 kernels run (cv_square_set_impl)
     int wave = 0;                 // boards per wave, 0 = default per precision
@@ -132,9 +134,9 @@ struct WavePlan {
 // inputs, one wave of H x H x 3 bytes per board): it lives in the caller's workspace, so a forward never allocates.
 WavePlan make_plan(const cv_square* h, int max_boards, int precision, int H) {
     WavePlan p;
-    const bool bf = precision != CV_PRECISION_FP32;
+    const bool bf = precision == CV_PRECISION_BF16 || precision == CV_PRECISION_FP16;
     const int all_fused = CV_IMPL_FRONTEND | CV_IMPL_EARLY | CV_IMPL_MID | CV_IMPL_TAIL;
-    int def = !bf ? DEFAULT_WAVE_FP32 : (h->impl & all_fused) == all_fused ? DEFAULT_WAVE_ALL_FUSED : (h->impl & CV_IMPL_TAIL) ? DEFAULT_WAVE_FUSED : DEFAULT_WAVE_BF16;
+    int def = precision == CV_PRECISION_FP32_SPLIT ? DEFAULT_WAVE_SPLIT : !bf ? DEFAULT_WAVE_FP32 : (h->impl & all_fused) == all_fused ? DEFAULT_WAVE_ALL_FUSED : (h->impl & CV_IMPL_TAIL) ? DEFAULT_WAVE_FUSED : DEFAULT_WAVE_BF16;
     p.wave = h->wave > 0 ? h->wave : def;
     if (p.wave > max_boards) p.wave = std::max(max_boards, 1);
     p.es = bf ? 2 : 4;
@@ -430,12 +432,80 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
     return prof_mark(h, -1, s);
 }
 
+// CV_PRECISION_FP32_SPLIT: crop gather in fp32 (bit-exact with the reference), then the 45 layers as layer-granular tensor-core kernels on
+// split fp16 operands (kernels_exact.cu), pooling + heads, fp64-accumulating global head.  Activations are X2 tensors: 4 bytes per element,
+// so the fp32 plan of the workspace is the right size.
+int forward_split(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layout, int B, int H, float* squares, float* turn, float* castling,
+                  float* features, void* workspace, size_t ws_bytes, cudaStream_t s) {
+    CropGeom g;
+    int rc = cv_make_crop_geom(H, &g);
+    if (rc) return rc;
+    const WavePlan p = make_plan(h, B, CV_PRECISION_FP32_SPLIT, 0);
+    if (ws_bytes < p.total) { cv_set_error("workspace too small: need %zu bytes, got %zu", p.total, ws_bytes); return CV_ERR_WORKSPACE; }
+    char* ws = static_cast<char*>(workspace);
+    float* crops = reinterpret_cast<float*>(ws + p.off_crops);
+    float* feat = reinterpret_cast<float*>(ws + p.off_feat);
+    int* ovf = h->flags + 1;
+    CV_CUDA(cudaMemsetAsync(ovf, 0, sizeof(int), s));
+    if (h->n_pieces > 0)
+        for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
+    auto buf_of = [&](int layer) -> uint16_t* {
+        return reinterpret_cast<uint16_t*>(ws + (h->out_buf[layer] < 0 ? p.off_stem : p.off_small[h->out_buf[layer]]));
+    };
+    for (int c0 = 0; c0 < B; c0 += MAX_CHUNK) {
+        const int cb = std::min(MAX_CHUNK, B - c0);
+        for (int w0 = 0; w0 < cb; w0 += p.wave) {
+            const int b0 = c0 + w0, nb = std::min(p.wave, cb - w0);
+            const int64_t n = (int64_t)nb * 64;
+            rc = prof_mark(h, CV_PROF_CROP, s);
+            if (rc) return rc;
+            if (x_u8) rc = launch_crop_u8<float>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+            else rc = launch_crop_f32<float>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+            if (rc) return rc;
+            ++h->launches;
+            for (int i = 0; i < CV_NUM_LAYERS; ++i) {
+                const cv_layer_info& L = kLayers[i];
+                rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
+                if (rc) return rc;
+                uint16_t* out = buf_of(i);
+                const uint16_t* in = i > 0 ? buf_of(i - 1) : nullptr;
+                const float* bias = h->blob + L.b_offset;
+                if (L.kind == CV_KIND_DEPTHWISE) rc = launch_depthwise_x2(L, in, h->blob + L.w_offset, bias, out, n, ovf, s);
+                else if (L.kind == CV_KIND_DENSE)
+                    rc = launch_dense_x2(L, in, i == 0 ? crops : nullptr, h->x2_wimg + x2_weight_image_offset(i), bias, h->x2_unscale[i], out, n, h->num_sms, ovf, s);
+                else
+                    rc = launch_pointwise_x2(L, in, h->x2_wimg + x2_weight_image_offset(i), bias, h->x2_unscale[i], L.skip >= 0 ? buf_of(L.skip) : nullptr,
+                                             out, n, h->num_sms, ovf, s);
+                if (rc) return rc;
+                ++h->launches;
+                if (b0 == 0 && h->tap_layer == i && h->tap_dst) {
+                    const size_t cnt = std::min(h->tap_n, (size_t)n * L.hout * L.hout * L.cout);
+                    rc = launch_x2_to_f32(out, h->tap_dst, cnt, L.cout, s);
+                    if (rc) return rc;
+                }
+            }
+            rc = prof_mark(h, CV_PROF_POOL_HEADS, s);
+            if (rc) return rc;
+            rc = launch_pool_heads_x2(buf_of(CV_NUM_LAYERS - 1), h->head_w, h->head_w + 4800, n, feat + (size_t)w0 * 30720, squares + (size_t)b0 * 832, s);
+            if (rc) return rc;
+            ++h->launches;
+        }
+        rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
+        if (rc) return rc;
+        rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0, castling + (size_t)c0 * 4, true, s);
+        if (rc) return rc;
+        ++h->launches;
+        if (features) CV_CUDA(cudaMemcpyAsync(features + (size_t)c0 * 30720, feat, (size_t)cb * 30720 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return prof_mark(h, -1, s);
+}
+
 int check_forward_args(const cv_square* h, const void* x, int B, int H, int precision, const void* squares,
                        const void* turn, const void* castling, const void* ws) {
     if (!h) { cv_set_error("null handle"); return CV_ERR_ARG; }
     if (!h->loaded) { cv_set_error("weights not loaded: call cv_square_load_weights first"); return CV_ERR_STATE; }
     if (B < 0) { cv_set_error("negative batch"); return CV_ERR_ARG; }
-    if (precision != CV_PRECISION_FP32 && precision != CV_PRECISION_BF16 && precision != CV_PRECISION_FP16) { cv_set_error("bad precision %d", precision); return CV_ERR_ARG; }
+    if (precision < CV_PRECISION_FP32 || precision > CV_PRECISION_FP32_SPLIT) { cv_set_error("bad precision %d", precision); return CV_ERR_ARG; }
     if (H < 32 || H % 32) { cv_set_error("board side H=%d must be a positive multiple of 32", H); return CV_ERR_ARG; }
     if (B > 0 && (!x || !squares || !turn || !castling || !ws)) { cv_set_error("null data pointer"); return CV_ERR_ARG; }
     return CV_OK;
@@ -500,6 +570,7 @@ int cv_square_create(int device, cv_square** out) {
         CV_CUDA(cudaMalloc(&h->sc_img[f], stageC_image_bytes()));
         CV_CUDA(cudaMalloc(&h->sb_img[f], stageB_image_bytes()));
     }
+    CV_CUDA(cudaMalloc(&h->x2_wimg, x2_weight_image_elems() * sizeof(uint16_t)));
     CV_CUDA(cudaMalloc(&h->flags, 4 * sizeof(int)));
     CV_CUDA(cudaMemset(h->flags, 0, 4 * sizeof(int)));
     CV_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -512,7 +583,7 @@ int cv_square_create(int device, cv_square** out) {
 int cv_square_destroy(cv_square* h) {
     if (!h) return CV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe3_wimg); cudaFree(h->flags);
+    cudaFree(h->blob); cudaFree(h->glob_wt); cudaFree(h->glob_wtile); cudaFree(h->head_w); cudaFree(h->lut); cudaFree(h->wimg); cudaFree(h->fe_wimg); cudaFree(h->fe3_wimg); cudaFree(h->flags); cudaFree(h->x2_wimg);
     for (int f = 0; f < 2; ++f) { cudaFree(h->sd_img[f]); cudaFree(h->sc_img[f]); cudaFree(h->sb_img[f]); }
     for (int i = 0; i < cv_square::kStages; ++i) {
         if (h->stage[i]) cudaFree(h->stage[i]);
@@ -556,6 +627,8 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
     if (rc) return rc;
     int* fe3_flag = reinterpret_cast<int*>(h->fe3_wimg + frontend3_weight_image_bytes());
     rc = launch_frontend3_prep_weights(h->blob, h->fe3_wimg, fe3_flag, s);
+    if (rc) return rc;
+    rc = launch_x2_prep_weights(h->blob, h->x2_wimg, h->x2_unscale, s);
     if (rc) return rc;
     CV_CUDA(cudaMemsetAsync(h->flags, 0, 4 * sizeof(int), s));
     for (int f = 0; f < 2; ++f) {                 // bf16 images, then fp16 images (+ the fp16 range check of every GEMM weight)
@@ -609,6 +682,7 @@ int cv_square_forward_f32(cv_square* h, const float* x, int B, int H, int precis
     if (B == 0) return CV_OK;
     CV_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == CV_PRECISION_FP32_SPLIT) return forward_split(h, x, nullptr, 0, B, H, squares, turn, castling, features, ws, ws_bytes, s);
     if (precision == CV_PRECISION_FP32)
         return forward_impl<float>(h, x, nullptr, 0, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
     return forward_impl<bf16>(h, x, nullptr, 0, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
@@ -622,6 +696,7 @@ int cv_square_forward_u8(cv_square* h, const uint8_t* boards, int layout, int B,
     if (B == 0) return CV_OK;
     CV_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (precision == CV_PRECISION_FP32_SPLIT) return forward_split(h, nullptr, boards, layout, B, H, squares, turn, castling, features, ws, ws_bytes, s);
     if (precision == CV_PRECISION_FP32)
         return forward_impl<float>(h, nullptr, boards, layout, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);
     return forward_impl<bf16>(h, nullptr, boards, layout, B, H, precision, squares, turn, castling, features, ws, ws_bytes, s);

@@ -194,3 +194,18 @@ int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g
                      const StageGate& gate = StageGate());
 // float NCHW boards that are Normalize(ToTensor(uint8)) -> the uint8 HWC image + a device flag (1 = some value is not on the uint8 grid)
 int launch_f32_to_u8_boards(const float* x_nchw, int nb, int H, const float* lut_host, uint8_t* out_hwc, int* flag_dev, cudaStream_t s);
+
+// ---- kernels_exact.cu: fp32-grade layer-granular trunk on the tensor cores, split fp16 operands (CV_PRECISION_FP32_SPLIT) --------------
+//   X2 layout of a C-channel tensor = T8 layout of 2C channels: per 128-row tile C/8 chunks of hi = fp16(x), then C/8 chunks of lo = fp16(x - hi)
+size_t x2_weight_image_elems();
+int64_t x2_weight_image_offset(int layer);
+int launch_x2_prep_weights(const float* blob, uint16_t* wimg, float* unscale_host /*[cv_num_layers()]*/, cudaStream_t s);
+int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_t* wimg, const float* bias, float unscale, const uint16_t* skip,
+                        uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s);
+int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint16_t* wimg, const float* bias, float unscale,
+                    uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s);
+int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* w, const float* bias, uint16_t* y, int64_t n_crops, int* ovf,
+                        cudaStream_t s);
+int launch_pool_heads_x2(const uint16_t* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features, float* squares,
+                         cudaStream_t s);
+int launch_x2_to_f32(const uint16_t* src, float* dst, size_t n, int C, cudaStream_t s);

@@ -1,0 +1,603 @@
+// fp32-grade arithmetic on the tensor cores: the layer-granular trunk with SPLIT fp16 operands (CV_PRECISION_FP32_SPLIT).
+//
+// The exact mode of the path (logits within 1e-5 of the reference, identical FEN strings: predict.py:24-42 runs the model in fp32) used to
+// mean CUDA-core kernels.  Here every activation and every weight is carried as x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22
+// significant bits; weights are pre-scaled by a per-layer power of two so that their lo part stays a normal fp16), and every GEMM
+// k-step issues three tcgen05 MMAs into fp32 TMEM accumulators:
+//
+//      D0 += A_hi W_hi        D0 += A_lo W_hi        D1 += A_hi W_lo              (the dropped A_lo W_lo term is 2^-22 relative)
+//
+// Layout "X2": a tensor with C channels lives in HBM as the T8 layout of 2C channels -- per 128-row tile, C/8 chunks of hi values
+// followed by C/8 chunks of lo values -- so a tile is still ONE contiguous block = one TMA bulk copy = the K-major / no-swizzle
+// UMMA A operand of both halves.  Same byte count as fp32 activations.
+//   pointwise_x2_kernel   the 27 pointwise convs (+bias, ReLU, residual): TMA producer | MMA issuer | 4 epilogue warps
+//   dense_x2_kernel       the 3 dense 3x3 stride-2 convs as implicit GEMMs (software im2col of both halves; the stem reads the fp32 crops)
+//   depthwise_x2_kernel   the 15 depthwise convs on the CUDA cores in fp32 (hi + lo summed on load, split on store)
+//   pool_heads_x2_kernel  2x2 mean, type / color heads, type + color combine (square.py:87-104, common.py:24)
+// fp16 overflows above 65504: every store of a hi value checks for non-finite lanes and raises the handle's overflow flag
+// (cv_square_fp16_status); the caller then re-runs with CV_PRECISION_FP32 (the CUDA-core kernels have fp32 range).
+#include <cmath>
+#include <vector>
+
+#include "internal.h"
+#include "umma.cuh"
+
+namespace {
+
+using namespace umma;
+
+constexpr int TILE_M = 128;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 227 * 1024 - 2048;
+
+struct X2Params {
+    const uint16_t* x;        // A source: X2 tiles (pointwise / dense) ...
+    const float* x_f32;       // ... or the fp32 NHWC crops [N,64,64,3] (stem)
+    const uint16_t* wimg;     // B image [K/8][2N][8] fp16: columns [0,N) = hi(W * 2^s), [N,2N) = lo
+    const float* bias;        // [N]
+    const uint16_t* skip;     // X2 tiles [M][N] or nullptr
+    uint16_t* y;              // X2 tiles [M][N]
+    int* ovf;
+    float unscale;            // 2^-s
+    int m_tiles, K, N, relu, stages, n_split, n_tile, num_acc;
+    int groups;               // the large term A_hi W_hi is accumulated in `groups` separate TMEM ranges (k-steps dealt round robin), summed in the epilogue
+    int hin, hout, cin;       // dense only
+};
+
+struct Plan { uint32_t b_bytes, a_bytes, off_a, off_bias, off_bar, total; };
+__host__ __device__ inline Plan plan_smem(int K, int N, int stages) {
+    Plan s;
+    s.b_bytes = (uint32_t)K * 2u * N * 2u;
+    s.a_bytes = (uint32_t)TILE_M * K * 4u;
+    s.off_a = (s.b_bytes + 127u) & ~127u;
+    s.off_bias = s.off_a + stages * s.a_bytes;
+    s.off_bar = (s.off_bias + N * 4 + 15u) & ~15u;
+    s.total = s.off_bar + (2 * stages + 5) * 8 + 16;
+    return s;
+}
+struct Pipe {
+    uint8_t *b, *a;
+    float* bias;
+    uint64_t *full, *empty, *tfull, *tempty, *wbar;
+    uint32_t* tmem_slot;
+};
+__device__ __forceinline__ Pipe carve(uint8_t* smem, const X2Params& p) {
+    const Plan s = plan_smem(p.K, p.N, p.stages);
+    Pipe q;
+    q.b = smem;
+    q.a = smem + s.off_a;
+    q.bias = reinterpret_cast<float*>(smem + s.off_bias);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + s.off_bar);
+    q.full = bars; q.empty = bars + p.stages; q.tfull = bars + 2 * p.stages; q.tempty = q.tfull + 2; q.wbar = q.tempty + 2;
+    q.tmem_slot = reinterpret_cast<uint32_t*>(q.wbar + 1);
+    return q;
+}
+
+// x -> (hi, lo) fp16 pair of two values each: hi = fp16(x), lo = fp16(x - hi)
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pk2<true>(a, b);
+    const float2 h = up2<true>(hi);
+    lo = pk2<true>(a - h.x, b - h.y);
+}
+__device__ __forceinline__ void join8(const uint4& hi, const uint4& lo, float (&f)[8]) {
+    const float2 a = up2<true>(hi.x), b = up2<true>(hi.y), c = up2<true>(hi.z), d = up2<true>(hi.w);
+    const float2 e = up2<true>(lo.x), g = up2<true>(lo.y), h = up2<true>(lo.z), i = up2<true>(lo.w);
+    f[0] = a.x + e.x; f[1] = a.y + e.y; f[2] = b.x + g.x; f[3] = b.y + g.y;
+    f[4] = c.x + h.x; f[5] = c.y + h.y; f[6] = d.x + i.x; f[7] = d.y + i.y;
+}
+__device__ __forceinline__ uint32_t split8(const float (&v)[8], uint4& hi, uint4& lo) {
+    split2(v[0], v[1], hi.x, lo.x); split2(v[2], v[3], hi.y, lo.y); split2(v[4], v[5], hi.z, lo.z); split2(v[6], v[7], hi.w, lo.w);
+    return f16x2_nonfinite(hi.x) | f16x2_nonfinite(hi.y) | f16x2_nonfinite(hi.z) | f16x2_nonfinite(hi.w);
+}
+
+// ---- MMA issuer: work items = (tile, N split); the A stage of a tile serves all of its splits --------------------------------------
+__device__ __forceinline__ void mma_role(const X2Params& p, const Pipe& q, uint32_t tmem_base) {
+    const uint32_t idesc = make_idesc_f16(TILE_M, p.n_tile);
+    const uint32_t a_lbo = TILE_M * 16, b_lbo = (uint32_t)(2 * p.N) * 16;
+    const Plan s = plan_smem(p.K, p.N, p.stages);
+    mbar_wait(q.wbar, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const int k8 = p.K >> 3;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        mbar_wait(q.full + stage, phase);
+        for (int nt = 0; nt < p.n_split; ++nt) {
+            mbar_wait(q.tempty + acc, acc_phase ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_base = smem_u32(q.a + (size_t)stage * s.a_bytes), b_base = smem_u32(q.b);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 256), d1 = d0 + (uint32_t)(p.groups * p.n_tile);
+                for (int k = 0, g = 0; k < p.K / 16; ++k, g = (g + 1 == p.groups ? 0 : g + 1)) {
+                    const uint64_t ah = make_smem_desc(a_base + (2 * k) * a_lbo, a_lbo, 128);
+                    const uint64_t al = make_smem_desc(a_base + (k8 + 2 * k) * a_lbo, a_lbo, 128);
+                    const uint64_t bh = make_smem_desc(b_base + (2 * k) * b_lbo + (uint32_t)(nt * p.n_tile) * 16, b_lbo, 128);
+                    const uint64_t bl = make_smem_desc(b_base + (2 * k) * b_lbo + (uint32_t)(p.N + nt * p.n_tile) * 16, b_lbo, 128);
+                    // The tensor core rounds every accumulation toward zero, so the number of MMAs that touch a LARGE accumulator sets the
+                    // error of the sum (measured): the large term A_hi W_hi goes to its own accumulators -- `groups` of
+                    // them, k-steps dealt round robin, added in the epilogue with round-to-nearest -- and both small terms share D1.
+                    mma_bf16_ss(d0 + (uint32_t)(g * p.n_tile), ah, bh, idesc, k >= p.groups ? 1u : 0u);       // (kind::f16: the idesc selects fp16 operands)
+                    mma_bf16_ss(d1, al, bh, idesc, k ? 1u : 0u);
+                    mma_bf16_ss(d1, ah, bl, idesc, 1u);
+                }
+                if (nt == p.n_split - 1) mma_commit(q.empty + stage);
+                mma_commit(q.tfull + acc);
+            }
+            __syncwarp();
+            if (p.num_acc == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1u; } else { acc_phase ^= 1u; }
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+}
+
+// ---- epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows -------------------------------------------------------------
+__device__ __forceinline__ void epilogue_role(const X2Params& p, const Pipe& q, uint32_t tmem_base, int warp, int lane) {
+    const int row = warp * 32 + lane, n8 = p.N >> 3;
+    int acc = 0;
+    uint32_t acc_phase = 0, bad = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        uint4* yt = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 * n8) * TILE_M + row;
+        const uint4* st = p.skip ? reinterpret_cast<const uint4*>(p.skip) + ((size_t)tile * 2 * n8) * TILE_M + row : nullptr;
+        for (int nt = 0; nt < p.n_split; ++nt) {
+            mbar_wait(q.tfull + acc, acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                uint32_t r0[16], r1[16];
+                tmem_ld16(taddr + c0, r0);
+                tmem_ld16(taddr + p.groups * p.n_tile + c0, r1);
+                tmem_ld_wait();
+                for (int g = 1; g < p.groups; ++g) {              // large-term partial sums, fixed order
+                    uint32_t rg[16];
+                    tmem_ld16(taddr + g * p.n_tile + c0, rg);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) + __uint_as_float(rg[i]));
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int col = nt * p.n_tile + c0 + 8 * j, chunk = col >> 3;
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        v[i] = fmaf(__uint_as_float(r0[8 * j + i]) + __uint_as_float(r1[8 * j + i]), p.unscale, q.bias[col + i]);
+                        if (p.relu) v[i] = fmaxf(v[i], 0.f);
+                    }
+                    if (st) {
+                        float sk[8];
+                        join8(__ldg(st + (size_t)chunk * TILE_M), __ldg(st + (size_t)(n8 + chunk) * TILE_M), sk);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] += sk[i];
+                    }
+                    uint4 hi, lo;
+                    bad |= split8(v, hi, lo);
+                    yt[(size_t)chunk * TILE_M] = hi;
+                    yt[(size_t)(n8 + chunk) * TILE_M] = lo;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q.tempty + acc);
+            if (p.num_acc == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1u; } else { acc_phase ^= 1u; }
+        }
+    }
+    if (bad) atomicOr(p.ovf, 1);
+}
+
+__device__ __forceinline__ uint32_t gemm_setup(const X2Params& p, const Pipe& q, int warp, int mma_warp, int full_count) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(q.full + i, full_count); mbar_init(q.empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(q.tfull + i, 1); mbar_init(q.tempty + i, 4); }
+        mbar_init(q.wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == mma_warp) tmem_alloc(q.tmem_slot, TMEM_COLS);
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) q.bias[i] = p.bias[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *q.tmem_slot;
+}
+
+// 6 warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer (+ TMEM owner)
+__global__ void __launch_bounds__(192, 1) pointwise_x2_kernel(const __grid_constant__ X2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Pipe q = carve(smem, p);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_base = gemm_setup(p, q, warp, 5, 1);
+    const Plan s = plan_smem(p.K, p.N, p.stages);
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q.wbar, s.b_bytes);
+            bulk_g2s(q.b, p.wimg, s.b_bytes, q.wbar);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+                mbar_wait(q.empty + stage, phase ^ 1u);
+                mbar_arrive_expect_tx(q.full + stage, s.a_bytes);
+                bulk_g2s(q.a + (size_t)stage * s.a_bytes, reinterpret_cast<const uint8_t*>(p.x) + (size_t)tile * s.a_bytes, s.a_bytes, q.full + stage);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 5) {
+        mma_role(p, q, tmem_base);
+    } else {
+        epilogue_role(p, q, tmem_base, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// 9 warps: 0-3 epilogue, 4-7 im2col gather (thread = tile row), 8 MMA issuer (+ TMEM owner).  K index = (ky*3+kx)*Cin + ci.
+// CIN8 = Cin/8 (0: the 3-channel stem on fp32 crops, K 27 -> 32).  A tile: K/8 hi chunks, then K/8 lo chunks.
+template <int CIN8>
+__global__ void __launch_bounds__(288, 1) dense_x2_kernel(const __grid_constant__ X2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const Pipe q = carve(smem, p);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_base = gemm_setup(p, q, warp, 8, 128);
+    const Plan s = plan_smem(p.K, p.N, p.stages);
+    if (warp >= 4 && warp < 8) {
+        const int r = threadIdx.x - 128;
+        if (r == 0) {
+            mbar_arrive_expect_tx(q.wbar, s.b_bytes);
+            bulk_g2s(q.b, p.wimg, s.b_bytes, q.wbar);
+        }
+        const int hw = p.hout * p.hout, k8 = p.K >> 3;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+            mbar_wait(q.empty + stage, phase ^ 1u);
+            const int64_t m = (int64_t)tile * TILE_M + r;
+            const int64_t n = m / hw;
+            const int rem = (int)(m - n * hw);
+            const int oy = rem / p.hout, ox = rem - oy * p.hout;
+            uint4* dst = reinterpret_cast<uint4*>(q.a + (size_t)stage * s.a_bytes) + r;
+            if (CIN8 > 0) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.x);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int iy = 2 * oy - 1 + t / 3, ix = 2 * ox - 1 + t % 3;
+                    const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
+                    const int64_t pin = (n * p.hin + iy) * p.hin + ix;
+                    const size_t base = ((size_t)(pin >> 7) * 2 * CIN8) * TILE_M + (pin & 127);      // X2 tile: hi chunks [0,CIN8), lo [CIN8,2 CIN8)
+#pragma unroll
+                    for (int c = 0; c < CIN8; ++c) {
+                        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+                        if (ok) { vh = __ldg(src + base + (size_t)c * TILE_M); vl = __ldg(src + base + (size_t)(CIN8 + c) * TILE_M); }
+                        dst[(size_t)(t * CIN8 + c) * TILE_M] = vh;
+                        dst[(size_t)(k8 + t * CIN8 + c) * TILE_M] = vl;
+                    }
+                }
+            } else {
+                float vals[32];
+#pragma unroll
+                for (int i = 27; i < 32; ++i) vals[i] = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    const int iy = 2 * oy - 1 + t / 3, ix = 2 * ox - 1 + t % 3;
+                    const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
+                    const int64_t pin = ((n * p.hin + iy) * p.hin + ix) * 3;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) vals[t * 3 + c] = ok ? __ldg(p.x_f32 + pin + c) : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float v[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = vals[8 * c + i];
+                    uint4 hi, lo;
+                    split8(v, hi, lo);                         // normalised pixels: |v| < 3, no overflow possible
+                    dst[(size_t)c * TILE_M] = hi;
+                    dst[(size_t)(k8 + c) * TILE_M] = lo;
+                }
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(q.full + stage);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+    } else if (warp == 8) {
+        mma_role(p, q, tmem_base);
+    } else {
+        epilogue_role(p, q, tmem_base, warp, lane);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// Depthwise KxK on square maps of side HIN (8, 4 or 2): thread = one OUTPUT ROW of one crop and one 8-channel chunk (the row-tiled
+// scheme of kernels_umma.cu), on X2 tensors: hi + lo are summed on load (fp32), the taps accumulate in fp32 in the reference's order
+// (bias, then taps in (ky, kx) order), the result is split on store.
+template <int K, int S, int HIN>
+__global__ void __launch_bounds__(128)
+depthwise_x2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ y,
+                    int64_t total_rows, int C, int relu, int* __restrict__ ovf) {
+    constexpr int HOUT = HIN / S, PAD = ((S - 1) + (K - 1)) / 2, GROUPS = TILE_M / HOUT;
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total_rows) return;
+    const int c8n = C >> 3;
+    const int g = (int)(t % GROUPS);
+    const int64_t tc = t / GROUPS;
+    const int c = (int)(tc % c8n);
+    const int64_t m_out = (tc / c8n) * TILE_M + (int64_t)g * HOUT;
+    const int64_t crop = m_out / (HOUT * HOUT);
+    const int oy = (int)(m_out - crop * (HOUT * HOUT)) / HOUT;
+    float acc[HOUT][8];
+    {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8) + 1);
+#pragma unroll
+        for (int ox = 0; ox < HOUT; ++ox) {
+            acc[ox][0] = b0.x; acc[ox][1] = b0.y; acc[ox][2] = b0.z; acc[ox][3] = b0.w;
+            acc[ox][4] = b1.x; acc[ox][5] = b1.y; acc[ox][6] = b1.z; acc[ox][7] = b1.w;
+        }
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(x);
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+        const int iy = oy * S - PAD + ky;
+        if (iy < 0 || iy >= HIN) continue;
+        const int64_t m_in = (crop * HIN + iy) * HIN;
+        const uint4* row = src + ((size_t)(m_in >> 7) * 2 * c8n + c) * TILE_M + (m_in & 127);
+        float px[HIN][8];
+#pragma unroll
+        for (int i = 0; i < HIN; ++i) join8(__ldg(row + i), __ldg(row + (size_t)c8n * TILE_M + i), px[i]);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+            const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c * 8);
+            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+#pragma unroll
+            for (int ox = 0; ox < HOUT; ++ox) {
+                const int ix = ox * S - PAD + kx;
+                if (ix < 0 || ix >= HIN) continue;
+                acc[ox][0] = fmaf(px[ix][0], w0.x, acc[ox][0]); acc[ox][1] = fmaf(px[ix][1], w0.y, acc[ox][1]);
+                acc[ox][2] = fmaf(px[ix][2], w0.z, acc[ox][2]); acc[ox][3] = fmaf(px[ix][3], w0.w, acc[ox][3]);
+                acc[ox][4] = fmaf(px[ix][4], w1.x, acc[ox][4]); acc[ox][5] = fmaf(px[ix][5], w1.y, acc[ox][5]);
+                acc[ox][6] = fmaf(px[ix][6], w1.z, acc[ox][6]); acc[ox][7] = fmaf(px[ix][7], w1.w, acc[ox][7]);
+            }
+        }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(m_out >> 7) * 2 * c8n + c) * TILE_M + (m_out & 127);
+    uint32_t bad = 0;
+#pragma unroll
+    for (int ox = 0; ox < HOUT; ++ox) {
+        if (relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[ox][i] = fmaxf(acc[ox][i], 0.f);
+        }
+        uint4 hi, lo;
+        bad |= split8(acc[ox], hi, lo);
+        dst[ox] = hi;
+        dst[(size_t)c8n * TILE_M + ox] = lo;
+    }
+    if (bad) atomicOr(ovf, 1);
+}
+
+// One warp per crop: mean over the 2x2 map (reference order), the 7 + 3 head dot products, type + color -> 13 joint logits.
+__global__ void __launch_bounds__(256)
+pool_heads_x2_kernel(const uint16_t* __restrict__ fmap /* X2 [n_crops*4 rows][480] */, const float* __restrict__ head_w, const float* __restrict__ head_b,
+                     int64_t n_crops, float* __restrict__ features, float* __restrict__ squares) {
+    const int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (n >= n_crops) return;
+    const int kT[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6}, kC[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};      // dataset.py:31-32
+    float part[10];
+#pragma unroll
+    for (int r = 0; r < 10; ++r) part[r] = 0.f;
+    const __half* f = reinterpret_cast<const __half*>(fmap);
+    auto at = [&](int64_t m, int ch) {                        // value (row m, channel ch) of the X2 tensor with 480 channels
+        const size_t base = (((size_t)(m >> 7) * 120 + (ch >> 3)) * TILE_M + (m & 127)) * 8 + (ch & 7);
+        return __half2float(f[base]) + __half2float(f[base + (size_t)60 * TILE_M * 8]);
+    };
+    for (int c = lane; c < 480; c += 32) {
+        const float m = ((at(n * 4, c) + at(n * 4 + 1, c)) + (at(n * 4 + 2, c) + at(n * 4 + 3, c))) * 0.25f;
+        features[n * 480 + c] = m;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) part[r] = fmaf(m, __ldg(head_w + r * 480 + c), part[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
+        part[r] += __ldg(head_b + r);
+    }
+    if (lane < 13) {
+        float t = 0.f, cl = 0.f;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) if (r == kT[lane]) t = part[r];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) if (r == kC[lane]) cl = part[7 + r];
+        squares[n * 13 + lane] = t + cl;
+    }
+}
+
+// X2 -> row-major fp32 [rows][C] (debug taps)
+__global__ void x2_to_f32_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, size_t n, int C) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t m = i / C;
+    const int ch = (int)(i - m * C);
+    const __half* f = reinterpret_cast<const __half*>(src);
+    const size_t base = (((m >> 7) * (size_t)(2 * (C >> 3)) + (ch >> 3)) * TILE_M + (m & 127)) * 8 + (ch & 7);
+    dst[i] = __half2float(f[base]) + __half2float(f[base + (size_t)(C >> 3) * TILE_M * 8]);
+}
+
+// ---- weight images: [K/8][2N][8] fp16, columns [0,N) hi(w * 2^s), [N,2N) lo ----------------------------------------------------------
+__global__ void prep_x2_weight_kernel(const float* __restrict__ w, uint16_t* __restrict__ img, int K, int Kpad, int N, float scale) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Kpad * N) return;
+    const int kk = i & 7, n = (i >> 3) % N, chunk = (i >> 3) / N;
+    const int k = chunk * 8 + kk;
+    const float v = (k < K ? w[(size_t)k * N + n] : 0.f) * scale;
+    const __half hi = __float2half_rn(v);
+    const size_t row = (size_t)chunk * 2 * N;
+    img[(row + n) * 8 + kk] = __half_as_ushort(hi);
+    img[(row + N + n) * 8 + kk] = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
+}
+__global__ void absmax_kernel(const float* __restrict__ w, int n, float* __restrict__ out) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+    __shared__ float red[256];
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+inline int gemm_k(const cv_layer_info& L) { return L.k * L.k * L.cin; }
+inline int gemm_kpad(const cv_layer_info& L) { return (gemm_k(L) + 15) / 16 * 16; }
+
+int fill_params(const cv_layer_info& L, X2Params* p, int64_t n_crops) {
+    p->K = gemm_kpad(L);
+    p->N = L.cout;
+    p->relu = L.relu;
+    const int64_t rows = n_crops * L.hout * L.hout;
+    if (rows % TILE_M != 0) { cv_set_error("x2: row count %lld is not a multiple of 128", (long long)rows); return CV_ERR_ARG; }
+    p->m_tiles = (int)(rows / TILE_M);
+    // two accumulator ranges (D0, D1) of n_tile columns each per work item, 256 TMEM columns per accumulator buffer
+    p->n_tile = p->N;
+    p->n_split = 1;
+    if (p->N > 128) {
+        p->n_tile = p->N % 96 == 0 ? 96 : 128;
+        if (p->N % p->n_tile != 0) { cv_set_error("x2: unsupported N=%d", p->N); return CV_ERR_ARG; }
+        p->n_split = p->N / p->n_tile;
+    }
+    if (p->n_tile % 16 != 0) { cv_set_error("x2: unsupported N=%d", p->N); return CV_ERR_ARG; }
+    p->num_acc = 2;
+    {   // (groups + 1) accumulator ranges of n_tile columns inside one 256-column buffer
+        int g = 256 / p->n_tile - 1;
+        const int steps = p->K / 16;
+        g = g > steps ? steps : g;
+        p->groups = g < 1 ? 1 : (g > 6 ? 6 : g);
+    }
+    const Plan one = plan_smem(p->K, p->N, 1);
+    int stages = 1 + (int)((SMEM_LIMIT - (int)one.total) / (int)one.a_bytes);
+    if ((int)one.total > SMEM_LIMIT) { cv_set_error("x2: layer K=%d N=%d does not fit shared memory", p->K, p->N); return CV_ERR_ARG; }
+    p->stages = stages < 1 ? 1 : (stages > 4 ? 4 : stages);
+    p->hin = L.hin; p->hout = L.hout; p->cin = L.cin;
+    return CV_OK;
+}
+
+}  // namespace
+
+size_t x2_weight_image_elems() {
+    size_t n = 0;
+    const cv_layer_info* L = cv_layers();
+    for (int i = 0; i < cv_num_layers(); ++i)
+        if (L[i].kind != CV_KIND_DEPTHWISE) n += 2 * (size_t)gemm_kpad(L[i]) * L[i].cout;
+    return n;
+}
+int64_t x2_weight_image_offset(int layer) {
+    const cv_layer_info* L = cv_layers();
+    int64_t n = 0;
+    for (int i = 0; i < layer; ++i)
+        if (L[i].kind != CV_KIND_DEPTHWISE) n += 2 * (int64_t)gemm_kpad(L[i]) * L[i].cout;
+    return n;
+}
+
+// Builds every GEMM layer's image; unscale[layer] (host array of cv_num_layers()) receives 2^-s.  Synchronises `s` (reads the maxima).
+int launch_x2_prep_weights(const float* blob, uint16_t* wimg, float* unscale_host, cudaStream_t s) {
+    const cv_layer_info* L = cv_layers();
+    const int nl = cv_num_layers();
+    float* d_max = nullptr;
+    CV_CUDA(cudaMalloc(&d_max, nl * sizeof(float)));
+    CV_CUDA(cudaMemsetAsync(d_max, 0, nl * sizeof(float), s));
+    for (int i = 0; i < nl; ++i)
+        if (L[i].kind != CV_KIND_DEPTHWISE) absmax_kernel<<<1, 256, 0, s>>>(blob + L[i].w_offset, gemm_k(L[i]) * L[i].cout, d_max + i);
+    std::vector<float> mx(nl, 0.f);
+    CV_CUDA(cudaMemcpyAsync(mx.data(), d_max, nl * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CV_CUDA(cudaStreamSynchronize(s));
+    CV_CUDA(cudaFree(d_max));
+    for (int i = 0; i < nl; ++i) {
+        unscale_host[i] = 1.f;
+        if (L[i].kind == CV_KIND_DEPTHWISE) continue;
+        // largest power of two that keeps |w| * 2^s <= 16384: hi stays far from the fp16 limit, lo = w - hi (2^-11 of it) stays normal
+        int e = 0;
+        if (mx[i] > 0.f && std::isfinite(mx[i])) {
+            e = (int)std::floor(std::log2(16384.0 / (double)mx[i]));
+            e = e < -14 ? -14 : (e > 24 ? 24 : e);
+        }
+        const float scale = std::ldexp(1.f, e);
+        unscale_host[i] = std::ldexp(1.f, -e);
+        const int K = gemm_k(L[i]), Kp = gemm_kpad(L[i]), N = L[i].cout;
+        prep_x2_weight_kernel<<<(Kp * N + 255) / 256, 256, 0, s>>>(blob + L[i].w_offset, wimg + x2_weight_image_offset(i), K, Kp, N, scale);
+        CV_CHECK_LAUNCH();
+    }
+    return CV_OK;
+}
+
+int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_t* wimg, const float* bias, float unscale, const uint16_t* skip,
+                        uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    X2Params p{};
+    int rc = fill_params(L, &p, n_crops);
+    if (rc) return rc;
+    p.x = x; p.wimg = wimg; p.bias = bias; p.skip = skip; p.y = y; p.ovf = ovf; p.unscale = unscale;
+    const Plan sp = plan_smem(p.K, p.N, p.stages);
+    CV_CUDA(cudaFuncSetAttribute(pointwise_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+    pointwise_x2_kernel<<<grid, 192, sp.total, s>>>(p);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint16_t* wimg, const float* bias, float unscale,
+                    uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    if (L.k != 3 || L.stride != 2) { cv_set_error("dense_x2: only 3x3 stride 2"); return CV_ERR_ARG; }
+    X2Params p{};
+    int rc = fill_params(L, &p, n_crops);
+    if (rc) return rc;
+    p.x = x; p.x_f32 = x_f32_crops; p.wimg = wimg; p.bias = bias; p.skip = nullptr; p.y = y; p.ovf = ovf; p.unscale = unscale;
+    const Plan sp = plan_smem(p.K, p.N, p.stages);
+    const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+#define DENSE_LAUNCH(C8)                                                                                                   \
+    {                                                                                                                      \
+        CV_CUDA(cudaFuncSetAttribute(dense_x2_kernel<C8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
+        dense_x2_kernel<C8><<<grid, 288, sp.total, s>>>(p);                                                                \
+    }
+    if (x_f32_crops && L.cin == 3) DENSE_LAUNCH(0)
+    else if (!x_f32_crops && L.cin == 16) DENSE_LAUNCH(2)
+    else if (!x_f32_crops && L.cin == 32) DENSE_LAUNCH(4)
+    else { cv_set_error("dense_x2: unsupported Cin=%d", L.cin); return CV_ERR_ARG; }
+#undef DENSE_LAUNCH
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* w, const float* bias, uint16_t* y, int64_t n_crops, int* ovf,
+                        cudaStream_t s) {
+    const int64_t total = n_crops * L.hout * L.hout * (L.cout / 8);
+    if (total == 0) return CV_OK;
+    if ((n_crops * L.hout * L.hout) % TILE_M != 0 || L.hin != L.hout * L.stride) { cv_set_error("depthwise_x2: crop count / shape not tiled"); return CV_ERR_ARG; }
+    const int64_t rows = total / L.hout;
+    const unsigned grid = (unsigned)((rows + 127) / 128);
+#define DW_ROWS(KK, SS, HH)                                                                                                 \
+    if (L.k == KK && L.stride == SS && L.hin == HH) {                                                                       \
+        depthwise_x2_kernel<KK, SS, HH><<<grid, 128, 0, s>>>(x, w, bias, y, rows, L.cout, L.relu, ovf);                     \
+        CV_CHECK_LAUNCH();                                                                                                  \
+        return CV_OK;                                                                                                       \
+    }
+    DW_ROWS(5, 1, 8) DW_ROWS(5, 2, 8) DW_ROWS(3, 1, 4) DW_ROWS(3, 2, 4) DW_ROWS(5, 1, 2) DW_ROWS(3, 1, 2)
+#undef DW_ROWS
+    cv_set_error("depthwise_x2: unsupported k=%d stride=%d hin=%d", L.k, L.stride, L.hin);
+    return CV_ERR_ARG;
+}
+
+int launch_pool_heads_x2(const uint16_t* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features, float* squares,
+                         cudaStream_t s) {
+    if (n_crops == 0) return CV_OK;
+    pool_heads_x2_kernel<<<(unsigned)((n_crops + 7) / 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features, squares);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+int launch_x2_to_f32(const uint16_t* src, float* dst, size_t n, int C, cudaStream_t s) {
+    if (n == 0) return CV_OK;
+    x2_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, dst, n, C);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}

@@ -24,7 +24,9 @@ class ChessSquareCNN(nn.Module):
 
     Extra, B200-specific surface (not in the reference):
       ``precision``            "fp16" (default: tensor-core path, fp16 operands / fp32 accumulation, automatic bf16 recomputation of a wave
-                               whose activations leave the fp16 range), "bf16" (same kernels, bf16 operands) or "fp32" (exact path)
+                               whose activations leave the fp16 range), "bf16" (same kernels, bf16 operands), "fp32" (exact path, CUDA-core
+                               kernels) or "fp32_split" (fp32-grade results on the tensor cores: split fp16 operands; activations must
+                               stay below 65504, see ``fp16_status``)
       ``forward_u8(boards)``   raw uint8 boards, ToTensor+Normalize fused into the crop gather
       ``predict_fen(boards)``  uint8 boards -> list of "placement turn castling" strings
     """

@@ -94,6 +94,55 @@ def test_every_layer_matches_oracle_fp32(gpu_model, gold_state):
     print(f"worst per-layer fp32 rel err {worst:.3e}")
 
 
+def test_every_layer_matches_oracle_fp32_split(gpu_model, gold_state):
+    """fp32-grade mode on the tensor cores (split fp16 operands, three MMAs per k-step, kernels_exact.cu): every layer's output
+    within 1e-5 of the fp32 oracle, like the CUDA-core exact mode above."""
+    x = oracle.normalize_u8(boards_u8(256, 2))
+    taps = {}
+    oracle.forward(x, gold_state, taps=taps)
+    xd = x.cuda()
+    worst = 0.0
+    for l in arch.LAYERS:
+        got = gpu_model.tap_layer(xd, l.index, precision="fp32_split").cpu().numpy()
+        ref = taps[l.key].permute(0, 2, 3, 1).numpy()
+        assert got.shape == ref.shape, l.key
+        e = rel_err(got, ref)
+        worst = max(worst, e)
+        assert e < FP32_TOL, f"layer {l.index} {l.key}: rel err {e:.3e}"
+    print(f"worst per-layer fp32_split rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("H,n", [(256, 64), (512, 8), (96, 3)])
+def test_forward_fp32_split_matches_reference(gpu_model, golden, gold_state, H, n):
+    """The same bars as the CUDA-core exact mode (test_forward_fp32_matches_reference): piece logits and trunk features within 1e-5
+    of the fp32 oracle and of the fp64 evaluation of the graph, turn / castling (30720-term dot products whose fp32 CPU evaluation
+    itself carries ~1e-5 of summation noise) within 3e-5, FEN strings identical to the reference's, no fp16 overflow."""
+    arrays, meta = golden
+    u8 = boards_u8(H, n, meta["board_seed"])
+    x = oracle.normalize_u8(u8)
+    ref = oracle.forward(x, gold_state, return_features=True)
+    truth = oracle.forward(x, gold_state, return_features=True, dtype=torch.float64)
+    out = gpu_model.forward_u8(torch.from_numpy(u8).cuda(), precision="fp32_split", return_features=True)
+    keys = ("squares", "turn", "castling", "features")
+    errs = {k: rel_err(out[k].cpu().numpy(), ref[k].numpy()) for k in keys}
+    terr = {k: rel_err(out[k].cpu().numpy(), truth[k].numpy()) for k in keys}
+    print(f"H={H} fp32_split vs fp32 oracle:", errs, "vs fp64 truth:", terr)
+    for k in ("squares", "features"):
+        assert errs[k] < FP32_TOL and terr[k] < FP32_TOL, (k, errs[k], terr[k])
+    for k in ("turn", "castling"):
+        assert errs[k] < 3e-5 and terr[k] < 3e-5, (k, errs[k], terr[k])
+    want = oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy())
+    assert fen_from_outputs(out) == want
+    if H in (256, 512):
+        ng = len(meta[f"fen{H}"])
+        assert want[:ng] == meta[f"fen{H}"][:n]
+    assert gpu_model.fp16_status()[1] is False
+    outf = gpu_model(x.cuda(), precision="fp32_split")                              # float entry point: same crops, same bits
+    assert all(torch.equal(outf[k], out[k]) for k in ("squares", "turn", "castling"))
+    host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), precision="fp32_split")
+    assert host == want
+
+
 @pytest.mark.parametrize("mask", [1023, 511, 255, 127, 63, 31, 15, 7, 0])
 def test_every_layer_matches_oracle_bf16(gpu_model, gold_state, mask):
     """bf16 path: fused front end + tensor-core kernels (mask 31, the default), layer-granular tensor-core kernels
@@ -653,12 +702,14 @@ def test_full_batch_properties_16bit(gpu_model):
 
 
 # ------------------------------------------------------------------------------------------ BASELINE.json configs 1, 3, 4
-def test_config1_64_boards_fp32_fen_matches_cpu(gpu_model, gold_state):
-    """configs[0]: 64 synthetic 256x256 boards, fp32: every FEN string equals the CPU oracle's (100 % agreement)."""
+@pytest.mark.parametrize("prec", ["fp32", "fp32_split"])
+def test_config1_64_boards_fp32_fen_matches_cpu(gpu_model, gold_state, prec):
+    """configs[0]: 64 synthetic 256x256 boards, fp32 (CUDA-core kernels, and the fp32-grade tensor-core mode): every FEN string equals
+    the CPU oracle's (100 % agreement)."""
     u8 = boards_u8(256, 64, first=4000)
     ref = oracle.forward(oracle.normalize_u8(u8), gold_state)
     want = oracle.fen_strings(ref["squares"].numpy(), ref["turn"].numpy(), ref["castling"].numpy())
-    got = gpu_model.predict_fen(torch.from_numpy(u8).cuda(), precision="fp32")
+    got = gpu_model.predict_fen(torch.from_numpy(u8).cuda(), precision=prec)
     assert got == want
     assert len(set(got)) == 64                              # non-degenerate: every board reads differently
 

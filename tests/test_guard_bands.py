@@ -39,7 +39,7 @@ class Arena:
         return bool((host[mask] == CANARY).all())
 
 
-@pytest.mark.parametrize("prec", ["fp16", "bf16", "fp32"])
+@pytest.mark.parametrize("prec", ["fp16", "bf16", "fp32", "fp32_split"])
 @pytest.mark.parametrize("B,H", [(1, 256), (3, 64), (37, 256), (130, 96)])
 def test_no_write_outside_the_declared_buffers(gpu_model, prec, B, H):
     L = _native.lib()
