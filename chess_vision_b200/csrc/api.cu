@@ -24,7 +24,7 @@ namespace {
 
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
-constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512, DEFAULT_WAVE_SPLIT = 128;   // fused stages: persistent kernels want many tiles per SM
+constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512, DEFAULT_WAVE_SPLIT = 512;   // fused stages: persistent kernels want many tiles per SM
 // all four fused stages: only the 8 / 4 / 1.5 KB per crop hand-offs live in the workspace, and every kernel boundary costs ~13 us of
 // drained SMs, so a wave is a whole chunk (measured per 4096 boards: 13.81 ms at 512, 13.64 at 1024, 13.55 at 2048, 13.45 at 4096)
 constexpr int DEFAULT_WAVE_ALL_FUSED = 4096;
@@ -150,7 +150,8 @@ WavePlan make_plan(const cv_square* h, int max_boards, int precision, int H) {
     // pooled features of one chunk: row-major, or FT-tiled (whole 128-board tiles) for the tensor-core global head
     const bool tiled = bf && (h->impl & CV_IMPL_TAIL);
     p.off_feat = off; off = align_up(off + (tiled ? ft_floats((int)chunk) : chunk * 64 * 480) * sizeof(float));
-    p.off_partial = off; off = align_up(off + (tiled ? global_head_partial_floats((int)chunk, h->num_sms) * sizeof(float) : 0));
+    p.off_partial = off; off = align_up(off + (tiled ? global_head_partial_floats((int)chunk, h->num_sms) * sizeof(float)
+                                                     : !bf ? global_head_f64_partial_bytes((int)chunk) : 0));
     // scratch logits for the predict entry points (whole batch)
     p.off_sq = off; off = align_up(off + (size_t)max_boards * 832 * sizeof(float));
     p.off_turn = off; off = align_up(off + (size_t)max_boards * sizeof(float));
@@ -420,8 +421,14 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 if (rc) return rc;
             }
         } else {
-            rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0,
-                                    castling + (size_t)c0 * 4, precision == CV_PRECISION_FP32, s);
+            if (precision == CV_PRECISION_FP32) {
+                rc = launch_global_head_f64_split(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb,
+                                                  reinterpret_cast<double*>(ws + p.off_partial), turn + c0, castling + (size_t)c0 * 4, s);
+                ++h->launches;
+            } else {
+                rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0,
+                                        castling + (size_t)c0 * 4, false, s);
+            }
             if (rc) return rc;
             ++h->launches;
             if (features)
@@ -442,6 +449,7 @@ int forward_split(cv_square* h, const float* x_f32, const uint8_t* x_u8, int lay
     if (rc) return rc;
     const WavePlan p = make_plan(h, B, CV_PRECISION_FP32_SPLIT, 0);
     if (ws_bytes < p.total) { cv_set_error("workspace too small: need %zu bytes, got %zu", p.total, ws_bytes); return CV_ERR_WORKSPACE; }
+    const CropTaps taps = make_taps(g);
     char* ws = static_cast<char*>(workspace);
     float* crops = reinterpret_cast<float*>(ws + p.off_crops);
     float* feat = reinterpret_cast<float*>(ws + p.off_feat);
@@ -457,12 +465,18 @@ int forward_split(cv_square* h, const float* x_f32, const uint8_t* x_u8, int lay
         for (int w0 = 0; w0 < cb; w0 += p.wave) {
             const int b0 = c0 + w0, nb = std::min(p.wave, cb - w0);
             const int64_t n = (int64_t)nb * 64;
-            rc = prof_mark(h, CV_PROF_CROP, s);
-            if (rc) return rc;
-            if (x_u8) rc = launch_crop_u8<float>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
-            else rc = launch_crop_f32<float>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
-            if (rc) return rc;
-            ++h->launches;
+            // uint8 HWC boards: the crop gather is fused into the stem's im2col gather (the fp32 crops never exist); other sources go
+            // through the crop kernel first
+            const bool fused_crop = x_u8 != nullptr && layout == CV_LAYOUT_HWC;
+            const uint8_t* wave_boards = fused_crop ? x_u8 + (size_t)b0 * H * H * 3 : nullptr;
+            if (!fused_crop) {
+                rc = prof_mark(h, CV_PROF_CROP, s);
+                if (rc) return rc;
+                if (x_u8) rc = launch_crop_u8<float>(x_u8 + (size_t)b0 * H * H * 3, layout, nb, H, g, h->lut, crops, nullptr, s);
+                else rc = launch_crop_f32<float>(x_f32 + (size_t)b0 * 3 * H * H, nb, H, g, crops, nullptr, s);
+                if (rc) return rc;
+                ++h->launches;
+            }
             for (int i = 0; i < CV_NUM_LAYERS; ++i) {
                 const cv_layer_info& L = kLayers[i];
                 rc = prof_mark(h, CV_PROF_LAYER0 + i, s);
@@ -472,7 +486,8 @@ int forward_split(cv_square* h, const float* x_f32, const uint8_t* x_u8, int lay
                 const float* bias = h->blob + L.b_offset;
                 if (L.kind == CV_KIND_DEPTHWISE) rc = launch_depthwise_x2(L, in, h->blob + L.w_offset, bias, out, n, ovf, s);
                 else if (L.kind == CV_KIND_DENSE)
-                    rc = launch_dense_x2(L, in, i == 0 ? crops : nullptr, h->x2_wimg + x2_weight_image_offset(i), bias, h->x2_unscale[i], out, n, h->num_sms, ovf, s);
+                    rc = launch_dense_x2(L, in, i == 0 && !fused_crop ? crops : nullptr, i == 0 ? wave_boards : nullptr, H, h->lut, &taps,
+                                         h->x2_wimg + x2_weight_image_offset(i), bias, h->x2_unscale[i], out, n, h->num_sms, ovf, s);
                 else
                     rc = launch_pointwise_x2(L, in, h->x2_wimg + x2_weight_image_offset(i), bias, h->x2_unscale[i], L.skip >= 0 ? buf_of(L.skip) : nullptr,
                                              out, n, h->num_sms, ovf, s);
@@ -492,9 +507,10 @@ int forward_split(cv_square* h, const float* x_f32, const uint8_t* x_u8, int lay
         }
         rc = prof_mark(h, CV_PROF_GLOBAL_HEAD, s);
         if (rc) return rc;
-        rc = launch_global_head(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb, turn + c0, castling + (size_t)c0 * 4, true, s);
+        rc = launch_global_head_f64_split(feat, h->glob_wt, h->head_w + 4816, h->head_w + 4880, h->head_w + 5200, cb,
+                                          reinterpret_cast<double*>(ws + p.off_partial), turn + c0, castling + (size_t)c0 * 4, s);
         if (rc) return rc;
-        ++h->launches;
+        h->launches += 2;
         if (features) CV_CUDA(cudaMemcpyAsync(features + (size_t)c0 * 30720, feat, (size_t)cb * 30720 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
     return prof_mark(h, -1, s);

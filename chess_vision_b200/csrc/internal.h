@@ -105,6 +105,9 @@ int launch_pool_heads(const T* feat_map /*[N,2,2,480]*/, const float* head_w, co
 int launch_global_head(const float* features /*[B,30720]*/, const float* glob_wt /*[30720,64]*/,
                        const float* glob_b, const float* tc_w, const float* tc_b, int B, float* turn,
                        float* castling, bool exact_fp64_accumulate, cudaStream_t s);
+size_t global_head_f64_partial_bytes(int B);            // the same fp64 head with the K reduction spread over the grid (deterministic partial sums)
+int launch_global_head_f64_split(const float* features, const float* glob_wt, const float* glob_b, const float* tc_w, const float* tc_b, int B,
+                                 double* partial, float* turn, float* castling, cudaStream_t s);
 template <typename T>
 int launch_to_f32(const T* src, float* dst, size_t n, int C, bool t8, cudaStream_t s);   // -> row-major fp32
 int launch_transpose_f32(const float* src, float* dst, int rows, int cols, cudaStream_t s);   // dst[c][r]=src[r][c]
@@ -202,8 +205,9 @@ int64_t x2_weight_image_offset(int layer);
 int launch_x2_prep_weights(const float* blob, uint16_t* wimg, float* unscale_host /*[cv_num_layers()]*/, cudaStream_t s);
 int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_t* wimg, const float* bias, float unscale, const uint16_t* skip,
                         uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s);
-int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint16_t* wimg, const float* bias, float unscale,
-                    uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s);
+int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint8_t* boards_hwc, int H, const float* lut_dev,
+                    const CropTaps* taps, const uint16_t* wimg, const float* bias, float unscale, uint16_t* y, int64_t n_crops, int num_sms, int* ovf,
+                    cudaStream_t s);
 int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* w, const float* bias, uint16_t* y, int64_t n_crops, int* ovf,
                         cudaStream_t s);
 int launch_pool_heads_x2(const uint16_t* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features, float* squares,

@@ -17,6 +17,7 @@
 // fp16 overflows above 65504: every store of a hi value checks for non-finite lanes and raises the handle's overflow flag
 // (cv_square_fp16_status); the caller then re-runs with CV_PRECISION_FP32 (the CUDA-core kernels have fp32 range).
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "internal.h"
@@ -40,19 +41,27 @@ struct X2Params {
     int* ovf;
     float unscale;            // 2^-s
     int m_tiles, K, N, relu, stages, n_split, n_tile, num_acc;
+    int slices;               // dense kernels: the K extent of a tile passes through the smem ring in `slices` pieces (one filter row each)
+    const uint8_t* boards;    // stem with the crop gather fused in: uint8 HWC boards, normalisation table, board side
+    const float* lut;
+    int H;
     int groups;               // the large term A_hi W_hi is accumulated in `groups` separate TMEM ranges (k-steps dealt round robin), summed in the epilogue
     int hin, hout, cin;       // dense only
 };
 
-struct Plan { uint32_t b_bytes, a_bytes, off_a, off_bias, off_bar, total; };
-__host__ __device__ inline Plan plan_smem(int K, int N, int stages) {
+// fused crop gather (stem only): normalisation table + tap tables + one crop patch per gather group behind the barriers
+constexpr int PATCH_ROWS = 9, PATCH_COLS = 65, PATCH_BYTES = (PATCH_ROWS * PATCH_COLS * 3 * 4 + 15) & ~15, MAX_GG = 4;
+constexpr int CROP_SMEM = 768 * 4 + (((int)sizeof(CropTaps) + 15) & ~15) + MAX_GG * PATCH_BYTES;
+struct Plan { uint32_t b_bytes, a_bytes, off_a, off_bias, off_bar, off_crop, total; };
+__host__ __device__ inline Plan plan_smem(int K, int N, int stages, int slices = 1, bool crop = false) {
     Plan s;
     s.b_bytes = (uint32_t)K * 2u * N * 2u;
-    s.a_bytes = (uint32_t)TILE_M * K * 4u;
+    s.a_bytes = (uint32_t)TILE_M * (K / slices) * 4u;       // one ring stage = one K slice of a tile, hi chunks then lo chunks
     s.off_a = (s.b_bytes + 127u) & ~127u;
     s.off_bias = s.off_a + stages * s.a_bytes;
     s.off_bar = (s.off_bias + N * 4 + 15u) & ~15u;
-    s.total = s.off_bar + (2 * stages + 5) * 8 + 16;
+    s.off_crop = (s.off_bar + (2 * stages + 5) * 8 + 16 + 15u) & ~15u;
+    s.total = s.off_crop + (crop ? CROP_SMEM : 0);
     return s;
 }
 struct Pipe {
@@ -62,7 +71,7 @@ struct Pipe {
     uint32_t* tmem_slot;
 };
 __device__ __forceinline__ Pipe carve(uint8_t* smem, const X2Params& p) {
-    const Plan s = plan_smem(p.K, p.N, p.stages);
+    const Plan s = plan_smem(p.K, p.N, p.stages, p.slices);
     Pipe q;
     q.b = smem;
     q.a = smem + s.off_a;
@@ -228,82 +237,171 @@ __global__ void __launch_bounds__(192, 1) pointwise_x2_kernel(const __grid_const
     if (warp == 5) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// 9 warps: 0-3 epilogue, 4-7 im2col gather (thread = tile row), 8 MMA issuer (+ TMEM owner).  K index = (ky*3+kx)*Cin + ci.
-// CIN8 = Cin/8 (0: the 3-channel stem on fp32 crops, K 27 -> 32).  A tile: K/8 hi chunks, then K/8 lo chunks.
-template <int CIN8>
-__global__ void __launch_bounds__(288, 1) dense_x2_kernel(const __grid_constant__ X2Params p) {
+// MMA issuer of the dense kernels: the ring stages are K SLICES (one filter row = 3 taps each); a tile's accumulators collect its slices.
+__device__ __forceinline__ void mma_role_dense(const X2Params& p, const Pipe& q, uint32_t tmem_base) {
+    const uint32_t idesc = make_idesc_f16(TILE_M, p.N);
+    const uint32_t a_lbo = TILE_M * 16, b_lbo = (uint32_t)(2 * p.N) * 16;
+    const Plan s = plan_smem(p.K, p.N, p.stages, p.slices);
+    mbar_wait(q.wbar, 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    const int ksl = (p.K / 16) / p.slices, kc = (p.K >> 3) / p.slices;       // k-steps and hi chunks per slice
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int sl = 0; sl < p.slices; ++sl) {
+            mbar_wait(q.full + stage, phase);
+            if (sl == 0) mbar_wait(q.tempty + acc, acc_phase ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_base = smem_u32(q.a + (size_t)stage * s.a_bytes), b_base = smem_u32(q.b);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 256), d1 = d0 + (uint32_t)(p.groups * p.N);
+                for (int kk = 0; kk < ksl; ++kk) {
+                    const int k = sl * ksl + kk, g = k % p.groups;
+                    const uint64_t ah = make_smem_desc(a_base + (2 * kk) * a_lbo, a_lbo, 128);
+                    const uint64_t al = make_smem_desc(a_base + (kc + 2 * kk) * a_lbo, a_lbo, 128);
+                    const uint64_t bh = make_smem_desc(b_base + (2 * k) * b_lbo, b_lbo, 128);
+                    const uint64_t bl = make_smem_desc(b_base + (2 * k) * b_lbo + (uint32_t)p.N * 16, b_lbo, 128);
+                    mma_bf16_ss(d0 + (uint32_t)(g * p.N), ah, bh, idesc, k >= p.groups ? 1u : 0u);
+                    mma_bf16_ss(d1, al, bh, idesc, k ? 1u : 0u);
+                    mma_bf16_ss(d1, ah, bl, idesc, 1u);
+                }
+                mma_commit(q.empty + stage);
+                if (sl == p.slices - 1) mma_commit(q.tfull + acc);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+    }
+}
+
+// 13 warps: 0-3 epilogue, 4-7 and 8-11 two im2col gather groups (thread = tile row; the groups take alternate ring stages, so two
+// gathers are in flight: the kernel is bound by the latency of the gather, not by bandwidth), 12 MMA issuer (+ TMEM owner).
+// K index = (ky*3+kx)*Cin + ci.  CIN8 = Cin/8: one ring stage = filter row ky of one tile = 3 taps x CIN8 hi chunks, then as many lo
+// chunks.  CIN8 == 0: the 3-channel stem (K 27 -> 32, one stage per tile), SRC 0 = from the fp32 NHWC crops, SRC 1 = with the crop gather
+// fused in: every tap value is the bilinear blend of four uint8 board pixels (ChessSquareCNN._crop_squares, square.py:43-74; the same
+// crop_blend() in the same order as crop_kernel, so the values are the reference's bit for bit) -- the 48 KB per crop of fp32 crops never exist.
+template <int CIN8, int SRC, int GG /* gather groups of 4 warps */>
+__global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __grid_constant__ X2Params p, const __grid_constant__ CropTaps tp_param) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Pipe q = carve(smem, p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tmem_base = gemm_setup(p, q, warp, 8, 128);
-    const Plan s = plan_smem(p.K, p.N, p.stages);
-    if (warp >= 4 && warp < 8) {
-        const int r = threadIdx.x - 128;
-        if (r == 0) {
+    const Plan s = plan_smem(p.K, p.N, p.stages, p.slices, CIN8 == 0 && SRC == 1);
+    float* lut_s = reinterpret_cast<float*>(smem + s.off_crop);
+    const CropTaps& tp = *reinterpret_cast<const CropTaps*>(smem + s.off_crop + 768 * 4);
+    float* patches = reinterpret_cast<float*>(smem + s.off_crop + 768 * 4 + (((int)sizeof(CropTaps) + 15) & ~15));
+    if (CIN8 == 0 && SRC == 1) {
+        for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_s[i] = p.lut[i];
+        for (int i = threadIdx.x; i < (int)(sizeof(CropTaps) / 4); i += blockDim.x)
+            reinterpret_cast<uint32_t*>(smem + s.off_crop + 768 * 4)[i] = reinterpret_cast<const uint32_t*>(&tp_param)[i];
+    }
+    constexpr int MMA_WARP = 4 + 4 * GG;
+    const uint32_t tmem_base = gemm_setup(p, q, warp, MMA_WARP, 128);
+    if (warp >= 4 && warp < MMA_WARP) {
+        const int grp = (warp - 4) >> 2, r = (threadIdx.x - 128) & 127;
+        if (threadIdx.x == 128) {
             mbar_arrive_expect_tx(q.wbar, s.b_bytes);
             bulk_g2s(q.b, p.wimg, s.b_bytes, q.wbar);
         }
-        const int hw = p.hout * p.hout, k8 = p.K >> 3;
-        int stage = 0;
-        uint32_t phase = 0;
+        const int hw = p.hout * p.hout, kc = CIN8 > 0 ? 3 * CIN8 : 4;
+        int64_t item = 0;                                    // ring stage counter: (tile iteration, slice)
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-            mbar_wait(q.empty + stage, phase ^ 1u);
             const int64_t m = (int64_t)tile * TILE_M + r;
             const int64_t n = m / hw;
             const int rem = (int)(m - n * hw);
             const int oy = rem / p.hout, ox = rem - oy * p.hout;
-            uint4* dst = reinterpret_cast<uint4*>(q.a + (size_t)stage * s.a_bytes) + r;
-            if (CIN8 > 0) {
-                const uint4* src = reinterpret_cast<const uint4*>(p.x);
+            for (int sl = 0; sl < p.slices; ++sl, ++item) {
+                if ((int)(item % GG) != grp) continue;
+                const int stage = (int)(item % p.stages);
+                const uint32_t phase = (uint32_t)((item / p.stages) & 1);
+                mbar_wait(q.empty + stage, phase ^ 1u);
+                uint4* dst = reinterpret_cast<uint4*>(q.a + (size_t)stage * s.a_bytes) + r;
+                if (CIN8 > 0) {
+                    const uint4* src = reinterpret_cast<const uint4*>(p.x);
+                    const int iy = 2 * oy - 1 + sl;          // slice = filter row ky
 #pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int iy = 2 * oy - 1 + t / 3, ix = 2 * ox - 1 + t % 3;
-                    const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
-                    const int64_t pin = (n * p.hin + iy) * p.hin + ix;
-                    const size_t base = ((size_t)(pin >> 7) * 2 * CIN8) * TILE_M + (pin & 127);      // X2 tile: hi chunks [0,CIN8), lo [CIN8,2 CIN8)
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int ix = 2 * ox - 1 + kx;
+                        const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
+                        const int64_t pin = (n * p.hin + iy) * p.hin + ix;
+                        const size_t base = ((size_t)(pin >> 7) * 2 * CIN8) * TILE_M + (pin & 127);      // X2 tile: hi chunks [0,CIN8), lo [CIN8,2 CIN8)
 #pragma unroll
-                    for (int c = 0; c < CIN8; ++c) {
-                        uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
-                        if (ok) { vh = __ldg(src + base + (size_t)c * TILE_M); vl = __ldg(src + base + (size_t)(CIN8 + c) * TILE_M); }
-                        dst[(size_t)(t * CIN8 + c) * TILE_M] = vh;
-                        dst[(size_t)(k8 + t * CIN8 + c) * TILE_M] = vl;
+                        for (int c = 0; c < CIN8; ++c) {
+                            uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+                            if (ok) { vh = __ldg(src + base + (size_t)c * TILE_M); vl = __ldg(src + base + (size_t)(CIN8 + c) * TILE_M); }
+                            dst[(size_t)(kx * CIN8 + c) * TILE_M] = vh;
+                            dst[(size_t)(kc + kx * CIN8 + c) * TILE_M] = vl;
+                        }
+                    }
+                } else {
+                    float vals[32];
+#pragma unroll
+                    for (int i = 27; i < 32; ++i) vals[i] = 0.f;
+                    if (SRC == 0) {
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const int iy = 2 * oy - 1 + t / 3, ix = 2 * ox - 1 + t % 3;
+                            const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
+                            const int64_t pin = ((n * p.hin + iy) * p.hin + ix) * 3;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) vals[t * 3 + c] = ok ? __ldg(p.x_f32 + pin + c) : 0.f;
+                        }
+                    } else {
+                        // The 128 rows of a tile are 4 output rows x 32 columns of ONE crop: their 3x3 stride-2 windows cover crop rows
+                        // [2 oy0 - 1, 2 oy0 + 7] and columns [-1, 63].  The group computes that patch once (every crop pixel = the bilinear
+                        // blend of four board pixels, crop_blend() as in crop_kernel: the reference's values bit for bit) and each thread then
+                        // picks its 27 taps from shared memory -- 2.6x fewer instructions than blending per tap.
+                        float* P = patches + grp * (PATCH_BYTES / 4);
+                        const int col = (int)(n & 7), row = (int)((n >> 3) & 7);
+                        const uint8_t* board = p.boards + (n >> 6) * (int64_t)p.H * p.H * 3;
+                        const int oy0 = oy - (r >> 5);                       // first output row of the tile (r >> 5 = this thread's row inside it)
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");          // the previous tile's readers are done with P
+                        for (int e = r; e < PATCH_ROWS * PATCH_COLS; e += 128) {
+                            const int pr = e / PATCH_COLS, pc = e - pr * PATCH_COLS;
+                            const int iy = 2 * oy0 - 1 + pr, ix = pc - 1;
+                            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                            if (iy >= 0 && iy < 64 && ix >= 0) {
+                                const int y0 = tp.p0[row][iy], y1 = tp.p1[row][iy], x0 = tp.p0[col][ix], x1 = tp.p1[col][ix];
+                                const float ly = tp.lam[iy], lx = tp.lam[ix];
+                                const uint8_t *p00 = board + (y0 * p.H + x0) * 3, *p01 = board + (y0 * p.H + x1) * 3, *p10 = board + (y1 * p.H + x0) * 3,
+                                              *p11 = board + (y1 * p.H + x1) * 3;
+                                v0 = crop_blend(lut_s[__ldg(p00)], lut_s[__ldg(p01)], lut_s[__ldg(p10)], lut_s[__ldg(p11)], lx, ly);
+                                v1 = crop_blend(lut_s[256 + __ldg(p00 + 1)], lut_s[256 + __ldg(p01 + 1)], lut_s[256 + __ldg(p10 + 1)], lut_s[256 + __ldg(p11 + 1)], lx, ly);
+                                v2 = crop_blend(lut_s[512 + __ldg(p00 + 2)], lut_s[512 + __ldg(p01 + 2)], lut_s[512 + __ldg(p10 + 2)], lut_s[512 + __ldg(p11 + 2)], lx, ly);
+                            }
+                            P[e * 3] = v0; P[e * 3 + 1] = v1; P[e * 3 + 2] = v2;
+                        }
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");          // patch complete
+                        const int oyl = r >> 5;
+#pragma unroll
+                        for (int t = 0; t < 9; ++t) {
+                            const float* src = P + ((2 * oyl + t / 3) * PATCH_COLS + 2 * ox + t % 3) * 3;
+                            vals[t * 3] = src[0]; vals[t * 3 + 1] = src[1]; vals[t * 3 + 2] = src[2];
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = vals[8 * c + i];
+                        uint4 hi, lo;
+                        split8(v, hi, lo);                         // normalised pixels: |v| < 3, no overflow possible
+                        dst[(size_t)c * TILE_M] = hi;
+                        dst[(size_t)(kc + c) * TILE_M] = lo;
                     }
                 }
-            } else {
-                float vals[32];
-#pragma unroll
-                for (int i = 27; i < 32; ++i) vals[i] = 0.f;
-#pragma unroll
-                for (int t = 0; t < 9; ++t) {
-                    const int iy = 2 * oy - 1 + t / 3, ix = 2 * ox - 1 + t % 3;
-                    const bool ok = iy >= 0 && iy < p.hin && ix >= 0 && ix < p.hin;
-                    const int64_t pin = ((n * p.hin + iy) * p.hin + ix) * 3;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) vals[t * 3 + c] = ok ? __ldg(p.x_f32 + pin + c) : 0.f;
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float v[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = vals[8 * c + i];
-                    uint4 hi, lo;
-                    split8(v, hi, lo);                         // normalised pixels: |v| < 3, no overflow possible
-                    dst[(size_t)c * TILE_M] = hi;
-                    dst[(size_t)(k8 + c) * TILE_M] = lo;
-                }
+                fence_proxy_async_smem();
+                mbar_arrive(q.full + stage);
             }
-            fence_proxy_async_smem();
-            mbar_arrive(q.full + stage);
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-    } else if (warp == 8) {
-        mma_role(p, q, tmem_base);
+    } else if (warp == MMA_WARP) {
+        mma_role_dense(p, q, tmem_base);
     } else {
         epilogue_role(p, q, tmem_base, warp, lane);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, TMEM_COLS);
+    if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // Depthwise KxK on square maps of side HIN (8, 4 or 2): thread = one OUTPUT ROW of one crop and one 8-channel chunk (the row-tiled
@@ -467,16 +565,20 @@ int fill_params(const cv_layer_info& L, X2Params* p, int64_t n_crops) {
     }
     if (p->n_tile % 16 != 0) { cv_set_error("x2: unsupported N=%d", p->N); return CV_ERR_ARG; }
     p->num_acc = 2;
+    p->slices = L.kind == CV_KIND_DENSE && L.cin >= 8 ? 3 : 1;
     {   // (groups + 1) accumulator ranges of n_tile columns inside one 256-column buffer
         int g = 256 / p->n_tile - 1;
         const int steps = p->K / 16;
         g = g > steps ? steps : g;
         p->groups = g < 1 ? 1 : (g > 6 ? 6 : g);
     }
-    const Plan one = plan_smem(p->K, p->N, 1);
-    int stages = 1 + (int)((SMEM_LIMIT - (int)one.total) / (int)one.a_bytes);
+    const Plan one = plan_smem(p->K, p->N, 1, p->slices);
+    int stages = 1 + (int)((SMEM_LIMIT - (int)one.total) / ((int)one.a_bytes + 16));
     if ((int)one.total > SMEM_LIMIT) { cv_set_error("x2: layer K=%d N=%d does not fit shared memory", p->K, p->N); return CV_ERR_ARG; }
-    p->stages = stages < 1 ? 1 : (stages > 4 ? 4 : stages);
+    p->stages = stages < 1 ? 1 : (stages > 6 ? 6 : stages);
+    // blocks.0.0: the im2col gather re-reads every input pixel 2.25 times; with three 48 KB stages instead of four the L1 that is left
+    // (the shared-memory carve-out follows the request) holds a tile's input region and L2 traffic drops (3.8 -> 3.0 ms per 1024 boards)
+    if (p->slices == 3 && one.a_bytes > 40000 && p->stages > 3) p->stages = 3;
     p->hin = L.hin; p->hout = L.hout; p->cin = L.cin;
     return CV_OK;
 }
@@ -544,25 +646,31 @@ int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_
     return CV_OK;
 }
 
-int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint16_t* wimg, const float* bias, float unscale,
-                    uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
+// x_f32_crops non-null: stem from the fp32 crops; boards non-null: stem with the crop gather fused in (uint8 HWC boards, `taps` of the board size)
+int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint8_t* boards, int H, const float* lut, const CropTaps* taps,
+                    const uint16_t* wimg, const float* bias, float unscale, uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (L.k != 3 || L.stride != 2) { cv_set_error("dense_x2: only 3x3 stride 2"); return CV_ERR_ARG; }
     X2Params p{};
     int rc = fill_params(L, &p, n_crops);
     if (rc) return rc;
-    p.x = x; p.x_f32 = x_f32_crops; p.wimg = wimg; p.bias = bias; p.skip = nullptr; p.y = y; p.ovf = ovf; p.unscale = unscale;
-    const Plan sp = plan_smem(p.K, p.N, p.stages);
+    p.x = x; p.x_f32 = x_f32_crops; p.boards = boards; p.H = H; p.lut = lut;
+    p.wimg = wimg; p.bias = bias; p.skip = nullptr; p.y = y; p.ovf = ovf; p.unscale = unscale;
+    const Plan sp = plan_smem(p.K, p.N, p.stages, p.slices, L.cin == 3 && boards && taps);
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
-#define DENSE_LAUNCH(C8)                                                                                                   \
-    {                                                                                                                      \
-        CV_CUDA(cudaFuncSetAttribute(dense_x2_kernel<C8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));      \
-        dense_x2_kernel<C8><<<grid, 288, sp.total, s>>>(p);                                                                \
+    static const CropTaps no_taps{};
+    const CropTaps& tp = taps ? *taps : no_taps;
+#define DENSE_LAUNCH(C8, SRC, GGR)                                                                                              \
+    {                                                                                                                           \
+        CV_CUDA(cudaFuncSetAttribute(dense_x2_kernel<C8, SRC, GGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); \
+        dense_x2_kernel<C8, SRC, GGR><<<grid, (5 + 4 * GGR) * 32, sp.total, s>>>(p, tp);                                        \
     }
-    if (x_f32_crops && L.cin == 3) DENSE_LAUNCH(0)
-    else if (!x_f32_crops && L.cin == 16) DENSE_LAUNCH(2)
-    else if (!x_f32_crops && L.cin == 32) DENSE_LAUNCH(4)
-    else { cv_set_error("dense_x2: unsupported Cin=%d", L.cin); return CV_ERR_ARG; }
+    const bool stem = L.cin == 3;
+    if (stem && boards && taps) DENSE_LAUNCH(0, 1, 4)        // measured: 4 gather groups 5.8 ms per 1024 boards, 2 groups 6.7 (blend per tap)
+    else if (stem && x_f32_crops) DENSE_LAUNCH(0, 0, 2)
+    else if (!stem && x && L.cin == 16) DENSE_LAUNCH(2, 0, 2)
+    else if (!stem && x && L.cin == 32) DENSE_LAUNCH(4, 0, 2)
+    else { cv_set_error("dense_x2: unsupported Cin=%d / source", L.cin); return CV_ERR_ARG; }
 #undef DENSE_LAUNCH
     CV_CHECK_LAUNCH();
     return CV_OK;

@@ -244,6 +244,61 @@ global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
     }
 }
 
+// The same fp64 head with the 30720-term reduction cut into KS ranges over the grid (blocks = board tiles x KS): a batch of 1024 boards
+// gives 128 blocks of 8 warps with the kernel above -- one per SM, latency-bound (1.4 ms) -- and 8 times as many here.  Partial sums
+// (double) go to `partial[ks][board][64]`; the finishing kernel adds them in a fixed order (deterministic), then bias, ReLU, 64 -> 1 + 4.
+constexpr int HEAD_KS = 8;
+__global__ void __launch_bounds__(256)
+global_head_f64_partial_kernel(const float* __restrict__ feat, const float* __restrict__ wt, int B, double* __restrict__ partial) {
+    __shared__ float sf[GB][GK];
+    __shared__ double red[4][GB][64];
+    const int j = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int b0 = blockIdx.x * GB, ks = blockIdx.y;
+    const int k_lo = ks * (30720 / HEAD_KS), k_hi = k_lo + 30720 / HEAD_KS;
+    double acc[GB];
+#pragma unroll
+    for (int i = 0; i < GB; ++i) acc[i] = 0;
+    for (int k0 = k_lo; k0 < k_hi; k0 += GK) {
+        const int gk = min(GK, k_hi - k0);
+        for (int t = threadIdx.x; t < GB * gk / 4; t += 256) {
+            const int bi = t / (gk / 4), kk = t % (gk / 4);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (b0 + bi < B) v = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)(b0 + bi) * 30720 + k0) + kk);
+            reinterpret_cast<float4*>(&sf[bi][0])[kk] = v;
+        }
+        __syncthreads();
+        for (int kk = slice; kk < gk; kk += 4) {
+            const double wv = (double)__ldg(wt + (int64_t)(k0 + kk) * 64 + j);
+#pragma unroll
+            for (int i = 0; i < GB; ++i) acc[i] += (double)sf[i][kk] * wv;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < GB; ++i) red[slice][i][j] = acc[i];
+    __syncthreads();
+    for (int t = threadIdx.x; t < GB * 64; t += 256) {
+        const int bi = t >> 6, jj = t & 63;
+        if (b0 + bi < B) partial[((size_t)ks * B + b0 + bi) * 64 + jj] = (red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj]);
+    }
+}
+__global__ void __launch_bounds__(64)
+global_head_f64_finish_kernel(const double* __restrict__ partial, const float* __restrict__ gb, const float* __restrict__ tc_w, const float* __restrict__ tc_b,
+                              int B, float* __restrict__ turn, float* __restrict__ castling) {
+    __shared__ float hid[64];
+    const int b = blockIdx.x, j = threadIdx.x;
+    double v = 0;
+    for (int ks = 0; ks < HEAD_KS; ++ks) v += partial[((size_t)ks * B + b) * 64 + j];
+    hid[j] = fmaxf((float)(v + (double)gb[j]), 0.f);
+    __syncthreads();
+    if (j < 5) {
+        double o = 0;
+        for (int jj = 0; jj < 64; ++jj) o += (double)hid[jj] * (double)tc_w[j * 64 + jj];
+        o += (double)tc_b[j];
+        if (j == 0) turn[b] = (float)o; else castling[(int64_t)b * 4 + (j - 1)] = (float)o;
+    }
+}
+
 template <typename T, typename L>
 __global__ void to_f32_kernel(const T* __restrict__ s, float* __restrict__ d, size_t n, int C) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -374,6 +429,18 @@ int launch_global_head(const float* features, const float* glob_wt, const float*
         global_head_kernel<double><<<blocks_for(B, GB), 256, 0, s>>>(features, glob_wt, glob_b, tc_w, tc_b, B, turn, castling);
     else
         global_head_kernel<float><<<blocks_for(B, GB), 256, 0, s>>>(features, glob_wt, glob_b, tc_w, tc_b, B, turn, castling);
+    CV_CHECK_LAUNCH();
+    return CV_OK;
+}
+
+size_t global_head_f64_partial_bytes(int B) { return (size_t)HEAD_KS * B * 64 * sizeof(double); }
+int launch_global_head_f64_split(const float* features, const float* glob_wt, const float* glob_b, const float* tc_w, const float* tc_b, int B,
+                                 double* partial, float* turn, float* castling, cudaStream_t s) {
+    if (B == 0) return CV_OK;
+    static_assert((30720 / HEAD_KS) % 4 == 0, "K ranges must be float4 aligned");
+    global_head_f64_partial_kernel<<<dim3((unsigned)blocks_for(B, GB), HEAD_KS), 256, 0, s>>>(features, glob_wt, B, partial);
+    CV_CHECK_LAUNCH();
+    global_head_f64_finish_kernel<<<B, 64, 0, s>>>(partial, glob_b, tc_w, tc_b, B, turn, castling);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
