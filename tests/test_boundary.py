@@ -179,3 +179,25 @@ def test_fen_host_hook_matches_reference(golden):
     assert n == 78 and rec.raw[:n].decode() == "/".join(["k" * 8] * 8) + " b KQkq"   # longest record
     bad = np.full(64, 13, np.int8)
     assert L.cv_fen_from_classes_host(bad.ctypes.data, ctypes.c_float(0.0), none, rec) == -1
+
+
+def test_python_constants_follow_the_header():
+    """The enums of include/chessvision_b200.h and their Python mirrors (_native.py, ChessSquareCNN.IMPL_*, evaluate.py counters) must
+    not drift apart (round 1 shipped IMPL_DEFAULT = 511 against CV_IMPL_DEFAULT = 1023)."""
+    import os
+    import re
+    from chess_vision_b200 import _native, evaluate
+    from chess_vision_b200.models.square import ChessSquareCNN
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "chessvision_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    enums = {k: int(v) for k, v in re.findall(r"\b(CV_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)}
+    assert (enums["CV_PRECISION_FP32"], enums["CV_PRECISION_BF16"], enums["CV_PRECISION_FP16"], enums["CV_PRECISION_FP32_SPLIT"]) == \
+        (_native.PRECISION_FP32, _native.PRECISION_BF16, _native.PRECISION_FP16, _native.PRECISION_FP32_SPLIT)
+    assert (enums["CV_LAYOUT_HWC"], enums["CV_LAYOUT_CHW"], enums["CV_FEN_STRIDE"]) == (_native.LAYOUT_HWC, _native.LAYOUT_CHW, _native.FEN_STRIDE)
+    for name in ("POINTWISE_UMMA", "DENSE_UMMA", "DEPTHWISE_VEC", "SPLIT_WEIGHTS", "FRONTEND", "TAIL", "MID", "EARLY", "FRONTEND3", "DEFAULT", "ALL"):
+        assert enums["CV_IMPL_" + name] == getattr(_native, "IMPL_" + name) == getattr(ChessSquareCNN, "IMPL_" + name), name
+    assert enums["CV_PROF_SLOTS"] == ChessSquareCNN.PROF_SLOTS == len(ChessSquareCNN.PROF_NAMES)
+    assert enums["CV_EVAL_COUNTERS"] == evaluate.N_COUNTERS and enums["CV_EVAL_CONFUSION"] == evaluate.CONFUSION
+    assert enums["CV_EVAL_TURN_CONFUSION"] == evaluate.TURN_CONFUSION and enums["CV_EVAL_PIECE_TOTAL"] == evaluate.PIECE_TOTAL
+    assert _native.lib().cv_abi_version() == int(re.search(r"#define CV_ABI_VERSION (\d+)", hdr).group(1))
+
