@@ -251,7 +251,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
                 ++h->launches;
             }
             rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img[fi], h->sc_off[fi], h->sc_bytes[fi], reinterpret_cast<bf16*>(p8),
-                               h->num_sms, gate, s);
+                               h->num_sms, gate, nb, s);
             if (rc) return rc;
             ++h->launches;
             rc = prof_mark(h, CV_PROF_TAIL, s);
@@ -265,7 +265,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
             ++h->launches;
         }
         rc = launch_stageD(reinterpret_cast<const bf16*>(p8), n, h->sd_img[fi], h->sd_off[fi], h->sd_bytes[fi], feat_chunk, 1, crop_base, squares,
-                           h->num_sms, gate, s);
+                           h->num_sms, gate, fused_mid ? nb : 0, s);
         if (rc) return rc;
         ++h->launches;
         return CV_OK;

@@ -161,7 +161,8 @@ int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, c
 // features: row-major [crops][480] (tiled == 0, indexed from this launch's first crop) or the FT operand layout of the
 // tensor-core global head (tiled == 1: `features` is the chunk's FT base and crop_base the launch's first crop in the chunk).
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes,
-                  float* features, int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate, cudaStream_t s);
+                  float* features, int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate,
+                  int perm_boards /* > 0: input in the permuted crop order stage C wrote for a launch of this many boards */, cudaStream_t s);
 
 // stage C = blocks.2.* (19 conv layers).  Input: "P2" tiles (128 rows = 2 crops at 8x8, row = pixel*2 + crop_local, 32 ch);
 // output: the P8 tiles stage D consumes.
@@ -170,7 +171,7 @@ size_t stageC_image_bytes();
 int build_stageC_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag, cudaStream_t s);
 int launch_permute_p2(const bf16* in_t8, bf16* out_p2, int64_t n_crops, int C, cudaStream_t s);
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8,
-                  int num_sms, const StageGate& gate, cudaStream_t s);
+                  int num_sms, const StageGate& gate, int perm_boards, cudaStream_t s);
 
 // stage B = blocks.0.1 + blocks.1.0 + blocks.1.1.  Input: the front end's T8 output (rows = crop*256 + pixel, 16 ch); output: P2 tiles.
 size_t stageB_image_bytes();

@@ -48,6 +48,33 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
+// Crop order of the stage C -> stage D hand-off ("square-major inside groups of 32 boards").  Stage D's tile is 32 consecutive crops and
+// its pooled features go to the operand layout of the global head, which interleaves 128 BOARDS at 16-byte granularity: with crops in
+// board order a tile is half of ONE board and every lane's 16-byte store lands 245 KB from its neighbour's.  In the permuted order a tile
+// is one square of 32 consecutive boards, and a warp's store is 512 contiguous bytes.  Stage C's last epilogue does the permutation (its
+// 1.5 KB per crop is the smallest tensor of the path); position n' of crop (b, sq) in a launch of nb boards:
+//   full groups g = b / 32 < nb / 32:  n' = g * 2048 + sq * 32 + b % 32;      last partial group of r = nb % 32 boards:  n' = full * 2048 + sq * r + (b - 32 full)
+__device__ __forceinline__ int64_t perm_pos(int64_t n, int nb) {
+    const int64_t b = n >> 6;
+    const int sq = (int)(n & 63), full = nb >> 5;
+    const int64_t g = b >> 5;
+    if (g < full) return g * 2048 + sq * 32 + (b & 31);
+    return (int64_t)full * 2048 + (int64_t)sq * (nb & 31) + (b - (int64_t)full * 32);
+}
+__device__ __forceinline__ void perm_inv(int64_t np, int nb, int64_t& b, int& sq) {
+    const int full = nb >> 5;
+    const int64_t g = np >> 11;
+    if (g < full) {
+        const int rem = (int)(np & 2047);
+        sq = rem >> 5;
+        b = g * 32 + (rem & 31);
+    } else {
+        const int rem = (int)(np - (int64_t)full * 2048), r = nb & 31;
+        sq = rem / r;
+        b = (int64_t)full * 32 + (rem - sq * r);
+    }
+}
+
 // One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
 // A: shared-memory operand tile [K/8][128 rows][8] 16-bit (K-major, no swizzle; LBO 2048 B, SBO 128 B).
 // B: weight image [K/8][n_total][8] 16-bit, columns [n0, n0+n).  D: fp32 TMEM columns starting at d_tmem.
@@ -251,6 +278,7 @@ struct StageDParams {
     int n_tiles;              // n_crops / 32
     int tiled;
     long long crop_base;      // tiled: index of this launch's first crop inside the chunk that `features` (FT base) covers
+    int perm_boards;          // > 0: the input tiles are in the permuted crop order of a launch of this many boards (perm_pos)
     uint32_t off[sd::NOPS], bytes[sd::NOPS];
     int debug;                // CV_SD_DEBUG ablation bits (timing experiments only: results are wrong)
     const int* gate;          // non-null: the kernel runs only when (*gate != 0) == gate_want (fp16 pass: want 0; bf16 fall-back pass: want 1)
@@ -455,7 +483,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 #pragma unroll
             for (int r = 0; r < 10; ++r) part_acc[r] = 0.f;
             float* xbuf = reinterpret_cast<float*>(BIG) + (size_t)cs * 4 * 16 * 32;      // [pixel][16 ch][32 crops] of this slice
-            const int64_t crop = (int64_t)tile * 32 + lane;
+            int64_t crop = (int64_t)tile * 32 + lane;                                    // position in the launch -> crop index b * 64 + square
+            if (p.perm_boards > 0) {
+                int64_t pb;
+                int psq;
+                perm_inv(crop, p.perm_boards, pb, psq);
+                crop = pb * 64 + psq;
+            }
             for (int g = cs; g < ((p.debug & 8) ? 0 : 30); g += 4) {
                 uint32_t rr[16];
                 tmem_ld16(trow + (uint32_t)(g * 16), rr);
@@ -507,7 +541,14 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                     t += red[(w * 32 + c) * 10 + ti];
                     cl += red[(w * 32 + c) * 10 + ci];
                 }
-                p.squares[((int64_t)tile * 32 + c) * 13 + cls] = t + cl;
+                int64_t oc = (int64_t)tile * 32 + c;
+                if (p.perm_boards > 0) {
+                    int64_t pb;
+                    int psq;
+                    perm_inv(oc, p.perm_boards, pb, psq);
+                    oc = pb * 64 + psq;
+                }
+                p.squares[oc * 13 + cls] = t + cl;
             }
             const int next = tile + gridDim.x;
             __syncthreads();                     // heads blob and partials fully consumed
@@ -528,8 +569,9 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 // stage C: blocks.2.0 .. blocks.2.5 (19 conv layers), 8x8 -> 4x4 maps.  Tile = 16 crops.
 // =====================================================================================================================
 // TMEM accumulator columns -> (+bias) -> 16-bit -> global T8-chunked tile dst[chunk][128 rows][8] (coalesced 16-byte stores).
+// `dst` already points at this thread's row slot (tile base + row, or the permuted position of its crop); chunks are 128 slots apart.
 template <bool F16>
-__device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int row, int cs, int n_slices,
+__device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols, const float* bias, uint4* dst, int cs, int n_slices,
                                               uint32_t& bad) {
     for (int g = cs; g < (ncols >> 4); g += n_slices) {
         uint32_t r[16];
@@ -543,7 +585,7 @@ __device__ __forceinline__ void epi_to_global(uint32_t trow, int col0, int ncols
             for (int i = 0; i < 8; ++i) v[i] += __uint_as_float(r[8 * j + i]);
             const uint4 o = pack8<F16>(v);
             if (F16) bad |= f16x2_nonfinite(o.x) | f16x2_nonfinite(o.y) | f16x2_nonfinite(o.z) | f16x2_nonfinite(o.w);
-            dst[(size_t)(g * 2 + j) * 128 + row] = o;
+            dst[(size_t)(g * 2 + j) * 128] = o;
         }
     }
 }
@@ -689,6 +731,7 @@ struct StageCParams {
     const uint8_t* wimg;
     bf16* y;                  // stage output: P8 tiles (128 rows = 8 crops, row = pix*8 + crop) x 48 ch  == stage D input
     int n_tiles;              // n_crops / 16
+    int perm_boards;          // > 0: write the output tiles in the permuted crop order of a launch of this many boards (perm_pos)
     uint32_t off[sc::NOPS], bytes[sc::NOPS];
     int debug;                // CV_SC_DEBUG ablation bits (timing experiments only: results are wrong): 1 no dw5x5, 2 no dw5x5s2, 4 no dw3x3,
                               // 32 no MMA / epilogue in the 4x4 phase (what is left is the per-op barrier + weight-stream cost), 256 section timers
@@ -976,8 +1019,11 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                 mma_commit(mbar);
             }
             if (!(p.debug & 32)) wait_mma();
-            uint4* dst = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 + mt) * 6 * 128;
-            if (!(p.debug & 32)) epi_to_global<F16>(trow, S_COL + 48 * mt, 48, cum23, dst, row, half, 2, bad);
+            // row = pixel * 8 + crop_local of M-tile mt; its P8 slot in the hand-off: the same position, or the crop's permuted position
+            int64_t pos = ((int64_t)tile * 2 + mt) * 8 + (row & 7);
+            if (p.perm_boards > 0) pos = perm_pos(pos, p.perm_boards);
+            uint4* dst = reinterpret_cast<uint4*>(p.y) + (pos >> 3) * 6 * 128 + (row >> 3) * 8 + (pos & 7);
+            if (!(p.debug & 32)) epi_to_global<F16>(trow, S_COL + 48 * mt, 48, cum23, dst, half, 2, bad);
             SC_MARK(8 + op); ++op;
         }
         const int next = tile + gridDim.x;
@@ -1301,12 +1347,12 @@ int launch_permute_p8(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, float* features,
-                  int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate, cudaStream_t s) {
+                  int tiled, int64_t crop_base, float* squares, int num_sms, const StageGate& gate, int perm_boards, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 32 != 0) { cv_set_error("stage D: crop count %lld is not a multiple of 32", (long long)n_crops); return CV_ERR_ARG; }
     StageDParams p{};
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
-    p.tiled = tiled; p.crop_base = crop_base;
+    p.tiled = tiled; p.crop_base = crop_base; p.perm_boards = perm_boards;
     p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
 #ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SD_DEBUG"); p.debug = d ? atoi(d) : 0; }
@@ -1412,11 +1458,11 @@ int launch_permute_p2(const bf16* in, bf16* out, int64_t n_crops, int C, cudaStr
 }
 
 int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const uint32_t* off, const uint32_t* bytes, bf16* y_p8, int num_sms,
-                  const StageGate& gate, cudaStream_t s) {
+                  const StageGate& gate, int perm_boards, cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
     if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
     StageCParams p{};
-    p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16);
+    p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16); p.perm_boards = perm_boards;
     p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
 #ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
     { const char* d = getenv("CV_SC_DEBUG"); p.debug = d ? atoi(d) : 0; }
