@@ -582,8 +582,8 @@ int cv_square_create(int device, cv_square** out) {
     CV_CUDA(cudaMalloc(&h->fe_wimg, frontend_weight_image_elems() * sizeof(bf16)));
     CV_CUDA(cudaMalloc(&h->fe3_wimg, frontend3_weight_image_bytes() + 16));
     for (int f = 0; f < 2; ++f) {
-        CV_CUDA(cudaMalloc(&h->sd_img[f], stageD_image_bytes()));
-        CV_CUDA(cudaMalloc(&h->sc_img[f], stageC_image_bytes()));
+        CV_CUDA(cudaMalloc(&h->sd_img[f], stageD_image_bytes() * CV_W_REPLICAS));
+        CV_CUDA(cudaMalloc(&h->sc_img[f], stageC_image_bytes() * CV_W_REPLICAS));
         CV_CUDA(cudaMalloc(&h->sb_img[f], stageB_image_bytes()));
     }
     CV_CUDA(cudaMalloc(&h->x2_wimg, x2_weight_image_elems() * sizeof(uint16_t)));
@@ -653,6 +653,10 @@ int cv_square_load_weights(cv_square* h, const float* blob, size_t n_floats, voi
         if (rc) return rc;
         rc = build_stageC_image(h->blob, h->sc_img[f], h->sc_off[f], h->sc_bytes[f], chk, s);
         if (rc) return rc;
+        for (int r = 1; r < CV_W_REPLICAS; ++r) {
+            CV_CUDA(cudaMemcpyAsync(h->sd_img[f] + r * stageD_image_bytes(), h->sd_img[f], stageD_image_bytes(), cudaMemcpyDeviceToDevice, s));
+            CV_CUDA(cudaMemcpyAsync(h->sc_img[f] + r * stageC_image_bytes(), h->sc_img[f], stageC_image_bytes(), cudaMemcpyDeviceToDevice, s));
+        }
         rc = build_stageB_image(h->blob, h->sb_img[f], chk, s);
         if (rc) return rc;
     }

@@ -155,6 +155,10 @@ int launch_frontend(const void* src, int src_kind, int nb, int H, const CropGeom
 // stage D = blocks.3.* + blocks.4.0 + average pool + type/color heads + combine.  Input: "P8" tiles (128 rows = 8 crops,
 // row = pixel*8 + crop_local, 48 channels, T8 chunking); output: features [crops][480] fp32, squares [crops][13] fp32.
 enum { CV_STAGE_D_OPS = 24 };
+// Stages C and D stream their weights L2 -> shared memory once per tile, every CTA at about the same time: their images are kept
+// in CV_W_REPLICAS copies (stageX_image_bytes() apart) and CTA b reads copy b % replicas, which spreads the requests over the L2.
+enum { CV_W_REPLICAS = 8 };
+int weight_replicas();                      // how many of the copies the kernels use (CV_W_REPLICAS; experiment builds: CV_W_REP)
 size_t stageD_image_bytes();
 int build_stageD_image(const float* blob, uint8_t* img, uint32_t* off, uint32_t* bytes, int* f16_flag /* non-null: fp16 images */, cudaStream_t s);
 int launch_permute_p8(const bf16* in_t8, bf16* out_p8, int64_t n_crops, int C, cudaStream_t s);

@@ -272,7 +272,9 @@ constexpr int S_COL = 448;                      // TMEM columns [448,512): fp32 
 
 struct StageDParams {
     const bf16* x;            // stage input: T8 tiles of 128 P8 rows x 48 ch (one tile = 8 crops)
-    const uint8_t* wimg;      // stage weight image (build_stageD_image)
+    const uint8_t* wimg;      // stage weight image (build_stageD_image), CV_W_REPLICAS copies w_stride bytes apart
+    int w_rep;                // CTA b streams its weights from copy b % w_rep (see CV_W_REPLICAS)
+    uint32_t w_stride;
     float* features;          // pooled trunk features (square.py:90): [n_crops][480], or the FT layout of kernels_head.cu (tiled)
     float* squares;           // [n_crops][13]  combined type+color logits (common.py:24)
     int n_tiles;              // n_crops / 32
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
     extern __shared__ __align__(1024) uint8_t smem[];
     if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;      // uniform over the grid up to races that only skip redundant work
     uint32_t bad = 0;
+    const uint8_t* wsrc = p.wimg + (size_t)(blockIdx.x % p.w_rep) * p.w_stride;
     uint8_t* IN = smem + OFF_IN;
     uint8_t* A24 = smem + OFF_A24;
     uint8_t* EH = smem + OFF_EH;
@@ -322,9 +325,9 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
 
     auto load_head_weights = [&]() {            // thread 0: the three blobs that stay resident during the 4x4 phase
         mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
-        bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
-        bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
-        bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
+        bulk_g2s(WA, wsrc + p.off[0], p.bytes[0], wbar);
+        bulk_g2s(WA + H_OFF1, wsrc + p.off[1], p.bytes[1], wbar);
+        bulk_g2s(WA + H_OFF2, wsrc + p.off[2], p.bytes[2], wbar);
     };
     auto load_in = [&](int tile, int t) {       // thread 0: sub-tile t (8 crops) of `tile` into ring slot t&1
         uint64_t* b = inbar + (t & 1);
@@ -338,12 +341,14 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
     auto prefetch = [&](int nx) {                // any one thread: op nx -> slot nx & 1
         uint64_t* b = wbar + (nx & 1);
         mbar_arrive_expect_tx(b, p.bytes[nx]);
-        bulk_g2s(WA + ((nx & 1) ? W_SLOT1 : 0), p.wimg + p.off[nx], p.bytes[nx], b);
+        bulk_g2s(WA + ((nx & 1) ? W_SLOT1 : 0), wsrc + p.off[nx], p.bytes[nx], b);
     };
-    // pf false: the GEMM op issues the prefetch itself, behind its tcgen05.commit (the bulk copy's issue latency then runs under the
-    // tensor-pipe round trip instead of in front of the CTA barrier that precedes the MMA issue)
+    // pf false: a GEMM op issues the prefetch after the CTA barrier that precedes its MMA issue, from a warp that is NOT the MMA issuer
+    // (the bulk copy's issue latency, a few hundred cycles, then runs while that warp would wait for the tensor pipe anyway; on the
+    // issuing warp it delayed the op's epilogue, and every closing barrier waits for the slowest warp)
+    constexpr int PF_WARP = 15;
     auto begin_op = [&](int op, bool pf = true) -> uint8_t* {
-        if (pf && tid == 0 && op + 1 < NOPS) prefetch(op + 1);
+        if (pf && warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
         if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
         return WA + ((op & 1) ? W_SLOT1 : 0);
     };
@@ -373,12 +378,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
         const uint32_t w25 = smem_u32(WA + H_OFF1 + 288 * 4);
         const float* b26 = reinterpret_cast<const float*>(WA + H_OFF2);
         const float* w26 = b26 + 288;
-        if (tid == 0) {                          // blocks.3.0.pw_proj weights -> slot 1 while the 4x4 phase runs
+        const bool loader = warp == PF_WARP && elect_one();      // the depthwise of this phase has 96 tasks: the last warp is idle in it
+        if (loader) {                            // blocks.3.0.pw_proj weights -> slot 1 while the 4x4 phase runs
             mbar_arrive_expect_tx(wbar + 1, p.bytes[3]);
-            bulk_g2s(WA + W_SLOT1, p.wimg + p.off[3], p.bytes[3], wbar + 1);
+            bulk_g2s(WA + W_SLOT1, wsrc + p.off[3], p.bytes[3], wbar + 1);
         }
         for (int t = 0; t < 4; ++t) {
-            if (tid == 0 && t < 3) load_in(tile, t + 1);
+            if (loader && t < 3) load_in(tile, t + 1);
             wait_in(t & 1);
             const uint8_t* in = IN + (t & 1) * 12288;
             if (!(p.debug & 1)) dw3x3_p8_rt<F16, false>(in, A24, 6 * 16, 6, w24, b24, tid);    // L24 dw_start (no act)
@@ -407,8 +413,8 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 tc_fence_after();
                 issue_gemm<F16>(smem_u32(BIG), 288, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, false);
                 mma_commit(mbar);
-                if (op + 1 < NOPS) prefetch(op + 1);
             }
+            if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
             wait_mma();
             epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
             __syncthreads();
@@ -421,8 +427,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw2x2_pm<F16>(X16, 8, b + 64, b, false, tid);
-                __syncthreads();
-                ++op;
+                ++op;                            // no closing barrier: pw_exp opens with sync_before_mma()
             }
             {   // pw_exp 64 -> cexp (+ReLU)
                 uint8_t* wb = begin_op(op, false);
@@ -431,8 +436,8 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                     tc_fence_after();
                     issue_gemm<F16>(smem_u32(X16), 64, smem_u32(wb + cexp * 4), cexp, 0, cexp, tmem, false);
                     mma_commit(mbar);
-                    if (op + 1 < NOPS) prefetch(op + 1);
                 }
+                if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
                 wait_mma();
                 epi_to_tile<F16, true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs, 4, bad);
                 __syncthreads();
@@ -442,8 +447,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw2x2_pm<F16>(BIG, cexp >> 3, b + cexp, b, true, tid);
-                __syncthreads();                 // every warp is done with this slot's weights before the next prefetch targets it
-                ++op;
+                ++op;                            // no closing barrier: pw_proj opens with sync_before_mma(), and prefetches behind it
             }
             {   // pw_proj cexp -> 64, accumulated onto the residual stream in TMEM (skip connection)
                 uint8_t* wb = begin_op(op, false);
@@ -452,12 +456,11 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                     tc_fence_after();
                     issue_gemm<F16>(smem_u32(BIG), cexp, smem_u32(wb + 256), 64, 0, 64, tmem + S_COL, true);
                     mma_commit(mbar);
-                    if (op + 1 < NOPS) prefetch(op + 1);
                 }
+                if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
                 wait_mma();
                 epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);   // + cumulative bias
-                __syncthreads();
-                ++op;
+                ++op;                            // no closing barrier: the next op (pw_exp / blocks.4.0) opens with sync_before_mma()
             }
         }
         // ------------------------------ blocks.4.0 (64 -> 480, ReLU) + average pool + heads -------------------------------------
@@ -468,8 +471,8 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 tc_fence_after();
                 issue_gemm<F16>(smem_u32(X16), 64, smem_u32(wb), 160, 0, 160, tmem + 160 * part, false);
                 mma_commit(mbar);
-                if (op + 1 < NOPS) prefetch(op + 1);
             }
+            if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
             wait_mma();
         }
         {
@@ -728,7 +731,9 @@ constexpr int S_COL = 400;
 
 struct StageCParams {
     const bf16* x;            // stage input: P2 tiles (128 rows = 2 crops, row = pix*2 + crop) x 32 ch, T8 chunking
-    const uint8_t* wimg;
+    const uint8_t* wimg;      // CV_W_REPLICAS copies w_stride bytes apart; CTA b streams from copy b % w_rep
+    int w_rep;
+    uint32_t w_stride;
     bf16* y;                  // stage output: P8 tiles (128 rows = 8 crops, row = pix*8 + crop) x 48 ch  == stage D input
     int n_tiles;              // n_crops / 16
     int perm_boards;          // > 0: write the output tiles in the permuted crop order of a launch of this many boards (perm_pos)
@@ -756,6 +761,7 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     extern __shared__ __align__(1024) uint8_t smem[];
     if (p.gate != nullptr && (*p.gate != 0) != (p.gate_want != 0)) return;
     uint32_t bad = 0;
+    const uint8_t* wsrc = p.wimg + (size_t)(blockIdx.x % p.w_rep) * p.w_stride;
     constexpr int WP = F16 ? 1 : 2;                 // weight images per pointwise blob: fp16 W | bf16 W_hi, W_lo
     uint8_t* IN = smem + OFF_IN;
     uint8_t* A5 = smem + OFF_A5;
@@ -794,9 +800,9 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
 
     auto load_head_weights = [&]() {
         mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
-        bulk_g2s(WA, p.wimg + p.off[0], p.bytes[0], wbar);
-        bulk_g2s(WA + H_OFF1, p.wimg + p.off[1], p.bytes[1], wbar);
-        bulk_g2s(WA + H_OFF2, p.wimg + p.off[2], p.bytes[2], wbar);
+        bulk_g2s(WA, wsrc + p.off[0], p.bytes[0], wbar);
+        bulk_g2s(WA + H_OFF1, wsrc + p.off[1], p.bytes[1], wbar);
+        bulk_g2s(WA + H_OFF2, wsrc + p.off[2], p.bytes[2], wbar);
     };
     auto load_in = [&](int tile) {             // the whole tile's stage input: 8 sub-tiles = one 64 KB bulk copy
         mbar_arrive_expect_tx(inbar, 65536);
@@ -810,16 +816,27 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
     auto prefetch = [&](int op) {
         const int sl = slot_of(op);
         mbar_arrive_expect_tx(wbar + sl, p.bytes[op]);
-        bulk_g2s(slot_ptr(sl), p.wimg + p.off[op], p.bytes[op], wbar + sl);
+        bulk_g2s(slot_ptr(sl), wsrc + p.off[op], p.bytes[op], wbar + sl);
     };
     auto wait_slot = [&](int sl) {
+#ifdef CV_SC_PROFILE
+        if (prof_on) {                           // how often, and for how long, the weights of an op are NOT there when it begins
+            const long long t = clock64();
+            if (!mbar_try_wait(wbar + sl, (wph >> sl) & 1u)) { ++pacc[6]; mbar_wait(wbar + sl, (wph >> sl) & 1u); }
+            pacc[5] += clock64() - t; ++pacc[7];
+            wph ^= 1u << sl;
+            return;
+        }
+#endif
         mbar_wait(wbar + sl, (wph >> sl) & 1u);
         wph ^= 1u << sl;
     };
-    // The bulk copy of op + 2 is issued by the MMA-issuing thread right after its tcgen05.commit (`pf` false here), so that the issue
-    // latency runs under the tensor-pipe round trip; ops without a GEMM issue it up front from thread 0.
+    // Issuing a bulk copy costs its thread a few hundred cycles.  GEMM ops (`pf` false here): a warp that is NOT the MMA issuer does it
+    // right after the barrier that precedes the MMA issue, while it would otherwise wait for the tensor pipe (the issuing warp is the
+    // one every op's closing barrier waits for); depthwise ops: the last warp, which has no depthwise task (384 tasks on 512 threads).
+    constexpr int PF_WARP = 15;
     auto begin_op = [&](int op, bool pf) -> uint8_t* {
-        if (pf && tid == 0 && op + 2 < NOPS) prefetch(op + 2);
+        if (pf && warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
         const int sl = slot_of(op);
         wait_slot(sl);
         return slot_ptr(sl);
@@ -859,25 +876,31 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
         const uint32_t w6 = smem_u32(WA + H_OFF1 + 96 * 4);
         const float* b7 = reinterpret_cast<const float*>(WA + H_OFF2);
         const float* w7 = b7 + 96;
-        if (tid == 0) { prefetch(3); prefetch(4); }     // first two ops of the 4x4 phase -> slots 1, 2 while the 8x8 phase runs
         mbar_wait(inbar, inph); inph ^= 1u;
         SC_MARK(0);
         if (!(p.debug & 1)) dw5x5_rows<F16>(IN, A5, w5, b5, tid);                                // L5 dw_start 5x5 (no act), all 16 crops
         sync_before_mma();
         SC_MARK(1);
-        for (int j = 0; j < 4; ++j) {
+        // L6 pw_exp 32 -> 96 on sub-tiles 2j, 2j+1 into accumulator set j & 1: the GEMMs of pair j + 1 are issued BEFORE the depthwise
+        // of pair j (they only read A5), so their round trip through the tensor pipe runs under it instead of in front of every epilogue.
+        auto issue_pw6 = [&](int j) {
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
-                for (int m = 0; m < 2; ++m)                                                  // L6 pw_exp 32 -> 96 on sub-tiles 2j, 2j+1
-                    issue_gemm<F16>(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 96 * m, false, WP);
+                for (int m = 0; m < 2; ++m)
+                    issue_gemm<F16>(smem_u32(A5 + (2 * j + m) * 8192), 32, w6, 96, 0, 96, tmem + ACC + 192 * (j & 1) + 96 * m, false, WP);
                 mma_commit(mbar);
             }
+        };
+        issue_pw6(0);
+        if (warp == PF_WARP && elect_one()) { prefetch(3); prefetch(4); }   // first two ops of the 4x4 phase -> slots 1, 2 while the 8x8 phase runs
+        for (int j = 0; j < 4; ++j) {
             wait_mma();
             SC_MARK(2);
-            epi_to_e6<F16>(trow, ACC + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
+            epi_to_e6<F16>(trow, ACC + 192 * (j & 1) + 96 * mt, b6, mt ? X16 : E6, row, half, 2);
             tc_fence_before();
             __syncthreads();
             SC_MARK(3);
+            if (j < 3) issue_pw6(j + 1);                // set (j + 1) & 1 was drained by the epilogue of pair j - 1, two barriers ago
             if (!(p.debug & 2)) dw5x5s2_rows<F16>(E6, X16, A7 + (j >> 1) * 24576, (4 * j) & 7, w7, b7, tid);   // L7 dw_mid 5x5 s2 (+ReLU) -> 4x4 P8 tile
             __syncthreads();
             SC_MARK(4);
@@ -893,45 +916,52 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                     issue_gemm<F16>(smem_u32(A7 + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
-                if (op + 2 < NOPS) prefetch(op + 2);
             }
+            if (warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
             if (!(p.debug & 32)) {
                 wait_mma();
                 epi_to_tile<F16, false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
                 wait_mma2();
                 epi_to_tile<F16, false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4, bad);
             }
-            __syncthreads();
-            SC_MARK(8 + op); ++op;
+            SC_MARK(8 + op); ++op;                       // no closing barrier: the next op opens with sync_before_mma()
         }
 #pragma unroll 1
         for (int blk = 1; blk <= 4; ++blk) {
             {   // pw_exp 48 -> 96 (+ReLU)
                 uint8_t* wb = begin_op(op, false);
+                SC_MARK(28);
                 sync_before_mma();
+                SC_MARK(29);
                 if (!(p.debug & 32) && warp == 0 && elect_one()) {
                     tc_fence_after();
                     for (int m = 0; m < 2; ++m) {
                         issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 96 * m, false, WP);
                         mma_commit(m ? mbar2 : mbar);
                     }
-                    if (op + 2 < NOPS) prefetch(op + 2);
                 }
+                if (warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
+                SC_MARK(30);
                 if (!(p.debug & 32)) {
                     wait_mma();
+                    SC_MARK(31);
                     epi_to_tile<F16, true>(trow, ACC, 96, reinterpret_cast<const float*>(wb), R, 0, row, cs, 4, bad);
+                    SC_MARK(32);
                     wait_mma2();
+                    SC_MARK(33);
                     epi_to_tile<F16, true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb), R + 24576, 0, row, cs2, 4, bad);
+                    SC_MARK(34);
                 }
                 __syncthreads();
                 SC_MARK(8 + op); ++op;
             }
             {   // dw_mid 3x3 (+ReLU), in place on both M-tiles
                 uint8_t* wb = begin_op(op, true);
+                SC_MARK(35);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw3x3_p8_rt<F16, true>(R, R, 2 * 12 * 16, 12, b + 96, b, tid);
-                __syncthreads();
-                SC_MARK(8 + op); ++op;
+                SC_MARK(36);
+                SC_MARK(8 + op); ++op;                   // no closing barrier: pw_proj opens with sync_before_mma()
             }
             {   // pw_proj 96 -> 48 accumulated onto the residual stream
                 uint8_t* wb = begin_op(op, false);
@@ -942,15 +972,15 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                         issue_gemm<F16>(smem_u32(R + m * 24576), 96, smem_u32(wb + 192), 48, 0, 48, tmem + S_COL + 48 * m, true, WP);
                         mma_commit(m ? mbar2 : mbar);
                     }
-                    if (op + 2 < NOPS) prefetch(op + 2);
                 }
+                if (warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
                 if (!(p.debug & 32)) {
                     wait_mma();
                     epi_to_tile<F16, false>(trow, S_COL, 48, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
                     wait_mma2();
                     epi_to_tile<F16, false>(trow, S_COL + 48, 48, reinterpret_cast<const float*>(wb), X16 + 12288, 0, row, cs2, 4, bad);
                 }
-                __syncthreads();
+                if (blk == 4) __syncthreads();           // blocks.2.5.dw_start reads X16 next; the other blocks go on with sync_before_mma()
                 SC_MARK(8 + op); ++op;
             }
         }
@@ -968,15 +998,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                     issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 1920 + 384), 96, 0, 96, tmem + ACC + 96 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
-                if (op + 2 < NOPS) prefetch(op + 2);
             }
+            if (warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
             if (!(p.debug & 32)) {
                 wait_mma();
                 epi_to_tile<F16, true>(trow, ACC, 96, reinterpret_cast<const float*>(wb + 1920), E22a, 0, row, cs, 4, bad);
                 wait_mma2();
                 epi_to_tile<F16, true>(trow, ACC + 96, 96, reinterpret_cast<const float*>(wb + 1920), E22a + 24576, 0, row, cs2, 4, bad);
             }
-            __syncthreads();
             SC_MARK(8 + op); ++op;
         }
         {   // op 17: W22 columns 96..191
@@ -988,15 +1017,14 @@ __global__ void __launch_bounds__(NT, 1) stageC_kernel(const __grid_constant__ S
                     issue_gemm<F16>(smem_u32(X16 + m * 12288), 48, smem_u32(wb + 384), 96, 0, 96, tmem + ACC + 192 + 96 * m, false, WP);
                     mma_commit(m ? mbar2 : mbar);
                 }
-                if (op + 2 < NOPS) prefetch(op + 2);
             }
+            if (warp == PF_WARP && op + 2 < NOPS && elect_one()) prefetch(op + 2);
             if (!(p.debug & 32)) {
                 wait_mma();
                 epi_to_tile<F16, true>(trow, ACC + 192, 96, reinterpret_cast<const float*>(wb), E22b, 0, row, cs, 4, bad);
                 wait_mma2();
                 epi_to_tile<F16, true>(trow, ACC + 192 + 96, 96, reinterpret_cast<const float*>(wb), E22b + 24576, 0, row, cs2, 4, bad);
             }
-            __syncthreads();
             SC_MARK(8 + op); ++op;
         }
         const float* cum23;
@@ -1351,6 +1379,7 @@ int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const 
     if (n_crops == 0) return CV_OK;
     if (n_crops % 32 != 0) { cv_set_error("stage D: crop count %lld is not a multiple of 32", (long long)n_crops); return CV_ERR_ARG; }
     StageDParams p{};
+    p.w_rep = weight_replicas(); p.w_stride = (uint32_t)stageD_image_bytes();
     p.x = x_p8; p.wimg = wimg; p.features = features; p.squares = squares; p.n_tiles = (int)(n_crops / 32);
     p.tiled = tiled; p.crop_base = crop_base; p.perm_boards = perm_boards;
     p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
@@ -1386,6 +1415,13 @@ uint32_t cop_bytes(int op, bool f16) {
     }
 }
 }  // namespace
+
+int weight_replicas() {
+#ifdef CV_EXPERIMENTS
+    if (const char* e = getenv("CV_W_REP")) { const int r = atoi(e); if (r >= 1 && r <= CV_W_REPLICAS) return r; }
+#endif
+    return CV_W_REPLICAS;
+}
 
 size_t stageC_image_bytes() {               // the larger (bf16) variant
     size_t n = 0;
@@ -1462,6 +1498,7 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
     if (n_crops == 0) return CV_OK;
     if (n_crops % 16 != 0) { cv_set_error("stage C: crop count %lld is not a multiple of 16", (long long)n_crops); return CV_ERR_ARG; }
     StageCParams p{};
+    p.w_rep = weight_replicas(); p.w_stride = (uint32_t)stageC_image_bytes();
     p.x = x_p2; p.wimg = wimg; p.y = y_p8; p.n_tiles = (int)(n_crops / 16); p.perm_boards = perm_boards;
     p.gate = gate.flag; p.gate_want = gate.want; p.ovf = gate.ovf;
 #ifdef CV_EXPERIMENTS                 // ablation / timing switches change the results: compiled in only with -DCV_EXPERIMENTS (CV_NVCC_EXTRA)
@@ -1484,6 +1521,8 @@ int launch_stageC(const bf16* x_p2, int64_t n_crops, const uint8_t* wimg, const 
         double sum = 0;
         for (int op = 3; op < 20; ++op) { fprintf(stderr, " %.0f", h[8 + op] / tiles); sum += h[8 + op] / tiles; }
         fprintf(stderr, "  (sum %.0f)\n", sum);
+        fprintf(stderr, "   inside the four pw_exp ops (sums; the op figures above hold only their trailing barrier): weights %.0f | fence+bar %.0f | issue %.0f | wait m0 %.0f | epi m0 %.0f | wait m1 %.0f | epi m1 %.0f"
+                        "   dw3x3: weights %.0f | work %.0f\n   weight waits per tile: %.1f of %.1f not ready at first poll, %.0f cycles in all\n", h[28] / tiles, h[29] / tiles, h[30] / tiles, h[31] / tiles, h[32] / tiles, h[33] / tiles, h[34] / tiles, h[35] / tiles, h[36] / tiles, h[6] / tiles, h[7] / tiles, h[5] / tiles);
     }
 #endif
     return CV_OK;
