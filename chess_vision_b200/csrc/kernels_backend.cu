@@ -117,6 +117,54 @@ __device__ __forceinline__ void epi_to_tile(uint32_t trow, int col0, int ncols, 
     }
 }
 
+// Depthwise 3x3 stride 1 on the 4x4 maps of ONE 128-row P8 tile, src -> dst (not in place), a task per OUTPUT ROW: (chunk, output row,
+// crop, channel half) = 64 tasks per chunk, four times the parallelism of dw3x3_p8_rt for the price of reading every input row up to
+// three times.  For the small layers (blocks.3.0.dw_start: 48 channels = 96 whole-map tasks, three warps of sixteen) the latency of
+// the load -> convert -> FMA chain is what counts, not the instruction total.  The output row is warp-uniform (no divergence).
+template <bool F16, bool RELU>
+__device__ __forceinline__ void dw3x3_p8_rows(const uint8_t* src, uint8_t* dst, int C8, const float* w, const float* bias, int tid) {
+    const int C = C8 * 8;
+    for (int task = tid; task < C8 * 64; task += NT) {
+        const int l = task & 15, crop = l >> 1, half = l & 1, oy = (task >> 5) & 3, c = ((task >> 7) << 1) | ((task >> 4) & 1);
+        if (c >= C8) continue;
+        const uint8_t* sbase = src + (size_t)c * 2048 + crop * 16 + half * 8;
+        const float* wp = w + c * 8 + half * 4;
+        const float4 b = *reinterpret_cast<const float4*>(bias + c * 8 + half * 4);
+        float2 acc[4][2];
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) { acc[ox][0] = lo2(b); acc[ox][1] = hi2(b); }
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = oy - 1 + ky;
+            if (iy < 0 || iy > 3) continue;
+            uint2 in[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) in[x] = *reinterpret_cast<const uint2*>(sbase + (iy * 4 + x) * 128);
+            float4 wt[3];
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) wt[kx] = *reinterpret_cast<const float4*>(wp + (ky * 3 + kx) * C);
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int ix = ox - 1 + kx;
+                    if (ix < 0 || ix > 3) continue;
+                    acc[ox][0] = fma2(up2<F16>(in[ix].x), lo2(wt[kx]), acc[ox][0]);
+                    acc[ox][1] = fma2(up2<F16>(in[ix].y), hi2(wt[kx]), acc[ox][1]);
+                }
+            }
+        }
+        uint8_t* dp = dst + (size_t)c * 2048 + crop * 16 + half * 8 + oy * 4 * 128;
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) {
+            uint2 o;
+            if (RELU) { o.x = pk2r<F16>(acc[ox][0].x, acc[ox][0].y); o.y = pk2r<F16>(acc[ox][1].x, acc[ox][1].y); }
+            else { o.x = pk2<F16>(acc[ox][0].x, acc[ox][0].y); o.y = pk2<F16>(acc[ox][1].x, acc[ox][1].y); }
+            *reinterpret_cast<uint2*>(dp + ox * 128) = o;
+        }
+    }
+}
+
 // Depthwise 3x3 stride 1 on 4x4 maps, P8 rows, IN PLACE over consecutive 128-row tiles of C8 chunks, register tiled.
 // Task = (tile*C8 + chunk, crop, channel half): the thread loads the whole 4x4 map of 4 channels of one crop (16 x 8 bytes,
 // a half warp reads 128 contiguous bytes per pixel), converts it once, computes all 16 outputs from registers (static border
@@ -222,29 +270,29 @@ __device__ __forceinline__ void dw2x2_pm(uint8_t* buf, int C8, const float* wq, 
     for (int task = tid; task < 32 * C8; task += NT) {
         const int c = task >> 5, crop = task & 31;
         uint8_t* base = buf + (((size_t)c * 128 + crop) << 4);
-        float x[4][8];
+        float2 x[4][4];                          // packed fp32 pairs: the 128 multiply-adds of a task are 64 FFMA2
 #pragma unroll
-        for (int q = 0; q < 4; ++q) unpack8<F16>(*reinterpret_cast<const uint4*>(base + q * 512), x[q]);
-        float b[8];
-        load8(bias + c * 8, b);
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = *reinterpret_cast<const uint4*>(base + q * 512);
+            x[q][0] = up2<F16>(v.x); x[q][1] = up2<F16>(v.y); x[q][2] = up2<F16>(v.z); x[q][3] = up2<F16>(v.w);
+        }
+        const float4 b0 = *reinterpret_cast<const float4*>(bias + c * 8), b1 = *reinterpret_cast<const float4*>(bias + c * 8 + 4);
         const float* wc = wq + c * 128;
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) {
-            float acc[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = b[i];
+            float2 acc[4] = {lo2(b0), hi2(b0), lo2(b1), hi2(b1)};
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                float ww[8];
-                load8(wc + (pp * 4 + q) * 8, ww);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[q][i], ww[i], acc[i]);
+                const float4 w0 = *reinterpret_cast<const float4*>(wc + (pp * 4 + q) * 8), w1 = *reinterpret_cast<const float4*>(wc + (pp * 4 + q) * 8 + 4);
+                acc[0] = fma2(x[q][0], lo2(w0), acc[0]);
+                acc[1] = fma2(x[q][1], hi2(w0), acc[1]);
+                acc[2] = fma2(x[q][2], lo2(w1), acc[2]);
+                acc[3] = fma2(x[q][3], hi2(w1), acc[3]);
             }
-            if (relu) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] = fmaxf(acc[i], 0.f);
-            }
-            *reinterpret_cast<uint4*>(base + pp * 512) = pack8<F16>(acc);
+            uint4 o;                             // ReLU rides on the conversion (cvt.rn.relu), same values as max(acc, 0) then round
+            if (relu) o = make_uint4(pk2r<F16>(acc[0].x, acc[0].y), pk2r<F16>(acc[1].x, acc[1].y), pk2r<F16>(acc[2].x, acc[2].y), pk2r<F16>(acc[3].x, acc[3].y));
+            else o = make_uint4(pk2<F16>(acc[0].x, acc[0].y), pk2<F16>(acc[1].x, acc[1].y), pk2<F16>(acc[2].x, acc[2].y), pk2<F16>(acc[3].x, acc[3].y));
+            *reinterpret_cast<uint4*>(base + pp * 512) = o;
         }
     }
 }
@@ -291,6 +339,14 @@ struct StageDParams {
 __constant__ int kTypeOf[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6};     // dataset.py:31
 __constant__ int kColorOf[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};    // dataset.py:32
 
+// Timing experiments (-DCV_SC_PROFILE, CV_SD_DEBUG & 256): cycles thread 0 of CTA 0 spends per section of a stage D tile (same caveats as SC_MARK).
+#ifdef CV_SC_PROFILE
+__device__ unsigned long long g_sd_prof[40];
+#define SD_MARK(k) do { if (prof_on) { const long long _n = clock64(); pacc[k] += _n - plast; plast = _n; } } while (0)
+#else
+#define SD_MARK(k)
+#endif
+
 template <bool F16>
 __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ StageDParams p) {
     using namespace sd;
@@ -322,6 +378,12 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
     const uint32_t tmem = *tmem_slot;
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     uint32_t wph0 = 0, wph1 = 0, inph0 = 0, inph1 = 0, mph = 0;
+#ifdef CV_SC_PROFILE
+    const bool prof_on = (p.debug & 256) && blockIdx.x == 0 && tid == 0;
+    long long pacc[40];
+    for (int i = 0; i < 40; ++i) pacc[i] = 0;
+    long long plast = clock64();
+#endif
 
     auto load_head_weights = [&]() {            // thread 0: the three blobs that stay resident during the 4x4 phase
         mbar_arrive_expect_tx(wbar, p.bytes[0] + p.bytes[1] + p.bytes[2]);
@@ -349,6 +411,15 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
     constexpr int PF_WARP = 15;
     auto begin_op = [&](int op, bool pf = true) -> uint8_t* {
         if (pf && warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
+#ifdef CV_SC_PROFILE
+        if (prof_on) {                           // how often, and for how long, the weights of an op are NOT there when it begins
+            const long long t = clock64();
+            if (!mbar_try_wait(wbar + (op & 1), (op & 1) ? wph1 : wph0)) { ++pacc[33]; mbar_wait(wbar + (op & 1), (op & 1) ? wph1 : wph0); }
+            pacc[32] += clock64() - t; ++pacc[34];
+            if (op & 1) wph1 ^= 1u; else wph0 ^= 1u;
+            return WA + ((op & 1) ? W_SLOT1 : 0);
+        }
+#endif
         if (op & 1) { mbar_wait(wbar + 1, wph1); wph1 ^= 1u; } else { mbar_wait(wbar, wph0); wph0 ^= 1u; }
         return WA + ((op & 1) ? W_SLOT1 : 0);
     };
@@ -367,10 +438,12 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
     if (tid == 0 && blockIdx.x < p.n_tiles) {
         load_head_weights();
         load_in(blockIdx.x, 0);
+        load_in(blockIdx.x, 1);
     }
 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         // ------------------------------ blocks.3.0 at 4x4: four sub-tiles of 8 crops -----------------------------------
+        SD_MARK(39);
         mbar_wait(wbar, wph0); wph0 ^= 1u;
         const float* b24 = reinterpret_cast<const float*>(WA);
         const float* w24 = b24 + 48;
@@ -384,11 +457,16 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             bulk_g2s(WA + W_SLOT1, wsrc + p.off[3], p.bytes[3], wbar + 1);
         }
         for (int t = 0; t < 4; ++t) {
-            if (loader && t < 3) load_in(tile, t + 1);
             wait_in(t & 1);
+            SD_MARK(0);
             const uint8_t* in = IN + (t & 1) * 12288;
-            if (!(p.debug & 1)) dw3x3_p8_rt<F16, false>(in, A24, 6 * 16, 6, w24, b24, tid);    // L24 dw_start (no act)
+            if (!(p.debug & 1)) dw3x3_p8_rows<F16, false>(in, A24, 6, w24, b24, tid);          // L24 dw_start (no act)
+            SD_MARK(1);
             sync_before_mma();
+            if (loader) {                        // ring slot t & 1 is consumed: sub-tile t + 2 (of this tile, or the next tile's first two) -> it
+                const int tn = t < 2 ? tile : tile + (int)gridDim.x;
+                if (tn < p.n_tiles) load_in(tn, (t + 2) & 3);
+            }
             if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 issue_gemm<F16>(smem_u32(A24), 48, w25, 288, 0, 144, tmem, false);             // L25 pw_exp 48 -> 288
@@ -396,11 +474,15 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 mma_commit(mbar);
             }
             wait_mma();
+            SD_MARK(2);
             for (int h = 0; h < 2; ++h) {
                 epi_to_tile<F16, true>(trow, 144 * h, 144, b25 + 144 * h, EH, 0, row, cs, 4, bad);
+                SD_MARK(3);
                 __syncthreads();
                 if (!(p.debug & 2)) dw3x3s2_p8_rt<F16>(EH, BIG, 18, 288, 18 * h, 8 * t, w26, b26, tid);   // L26 dw_mid s2 (+ReLU) -> rows of the 2x2 tile
+                SD_MARK(4);
                 __syncthreads();
+                SD_MARK(5);
             }
         }
         // ------------------------------ 2x2 phase: 128 rows = 32 crops ------------------------------------------------------
@@ -418,7 +500,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             wait_mma();
             epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);
             __syncthreads();
-            ++op;
+            SD_MARK(6 + op); ++op;
         }
 #pragma unroll 1
         for (int blk = 1; blk <= 5; ++blk) {
@@ -427,7 +509,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw2x2_pm<F16>(X16, 8, b + 64, b, false, tid);
-                ++op;                            // no closing barrier: pw_exp opens with sync_before_mma()
+                SD_MARK(6 + op); ++op;           // no closing barrier: pw_exp opens with sync_before_mma()
             }
             {   // pw_exp 64 -> cexp (+ReLU)
                 uint8_t* wb = begin_op(op, false);
@@ -441,13 +523,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 wait_mma();
                 epi_to_tile<F16, true>(trow, 0, cexp, reinterpret_cast<const float*>(wb), BIG, 0, row, cs, 4, bad);
                 __syncthreads();
-                ++op;
+                SD_MARK(6 + op); ++op;
             }
             {   // dw_mid 5x5 / 3x3 (+ReLU), in place
                 uint8_t* wb = begin_op(op);
                 const float* b = reinterpret_cast<const float*>(wb);
                 if (!(p.debug & 4)) dw2x2_pm<F16>(BIG, cexp >> 3, b + cexp, b, true, tid);
-                ++op;                            // no closing barrier: pw_proj opens with sync_before_mma(), and prefetches behind it
+                SD_MARK(6 + op); ++op;           // no closing barrier: pw_proj opens with sync_before_mma(), and prefetches behind it
             }
             {   // pw_proj cexp -> 64, accumulated onto the residual stream in TMEM (skip connection)
                 uint8_t* wb = begin_op(op, false);
@@ -460,7 +542,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
                 wait_mma();
                 epi_to_tile<F16, false>(trow, S_COL, 64, reinterpret_cast<const float*>(wb), X16, 0, row, cs, 4, bad);   // + cumulative bias
-                ++op;                            // no closing barrier: the next op (pw_exp / blocks.4.0) opens with sync_before_mma()
+                SD_MARK(6 + op); ++op;           // no closing barrier: the next op (pw_exp / blocks.4.0) opens with sync_before_mma()
             }
         }
         // ------------------------------ blocks.4.0 (64 -> 480, ReLU) + average pool + heads -------------------------------------
@@ -474,7 +556,11 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
             }
             if (warp == PF_WARP && op + 1 < NOPS && elect_one()) prefetch(op + 1);
             wait_mma();
+            SD_MARK(6 + op);
         }
+        // Weight slot 0 (last used by op 22, whose MMAs have completed) is free from here on: the next tile's resident weights arrive
+        // under the pool + heads epilogue instead of after it (its first two input sub-tiles were requested in the 4x4 phase).
+        if (warp == PF_WARP && tile + (int)gridDim.x < p.n_tiles && elect_one()) load_head_weights();
         {
             uint8_t* wb = begin_op(op);          // op 23 (slot 1): [head_b 16][head_w 10x480][blocks.4.0 bias 480] fp32
             const float* hb = reinterpret_cast<const float*>(wb);
@@ -530,6 +616,7 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                     part_acc[r] = fmaf(f4[0], w4.x, fmaf(f4[1], w4.y, fmaf(f4[2], w4.z, fmaf(f4[3], w4.w, part_acc[r]))));
                 }
             }
+            SD_MARK(30);
             float* red = reinterpret_cast<float*>(EH + 16384);               // [16 warps][32 crops][10]
 #pragma unroll
             for (int r = 0; r < 10; ++r) red[(warp * 32 + lane) * 10 + r] = part_acc[r];
@@ -553,14 +640,13 @@ __global__ void __launch_bounds__(NT, 1) stageD_kernel(const __grid_constant__ S
                 }
                 p.squares[oc * 13 + cls] = t + cl;
             }
-            const int next = tile + gridDim.x;
+            SD_MARK(31);
             __syncthreads();                     // heads blob and partials fully consumed
-            if (tid == 0 && next < p.n_tiles) {  // next tile's resident weights + first input sub-tile
-                load_head_weights();
-                load_in(next, 0);
-            }
         }
     }
+#ifdef CV_SC_PROFILE
+    if (prof_on) for (int i = 0; i < 40; ++i) g_sd_prof[i] = (unsigned long long)pacc[i];
+#endif
     if (F16 && bad != 0) atomicOr(p.ovf, 1);
     tc_fence_before();
     __syncthreads();
@@ -1392,6 +1478,20 @@ int launch_stageD(const bf16* x_p8, int64_t n_crops, const uint8_t* wimg, const 
     const int grid = p.n_tiles < num_sms ? p.n_tiles : num_sms;
     kern<<<grid, NT, sd::SMEM, s>>>(p);
     CV_CHECK_LAUNCH();
+#ifdef CV_SC_PROFILE
+    if (p.debug & 256) {
+        unsigned long long h[40];
+        CV_CUDA(cudaStreamSynchronize(s));
+        CV_CUDA(cudaMemcpyFromSymbol(h, g_sd_prof, sizeof(h)));
+        const double tiles = (double)((p.n_tiles + grid - 1) / grid);
+        fprintf(stderr, "stageD cycles per 32-crop tile: wait w %.0f | 4x4 phase (4 sub-tiles): wait in %.0f, dw24 %.0f, bar+pw25 %.0f, epi %.0f, dw26 %.0f, its closing barrier %.0f\n   2x2 ops 3..22:",
+                h[39] / tiles, h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, h[4] / tiles, h[5] / tiles);
+        double sum = 0;
+        for (int op = 3; op < 23; ++op) { fprintf(stderr, " %.0f", h[6 + op] / tiles); sum += h[6 + op] / tiles; }
+        fprintf(stderr, "  (sum %.0f) | pool + heads %.0f | combine %.0f\n   weight waits per tile: %.1f of %.1f not ready at first poll, %.0f cycles in all\n", sum, h[30] / tiles, h[31] / tiles,
+                h[33] / tiles, h[34] / tiles, h[32] / tiles);
+    }
+#endif
     return CV_OK;
 }
 
