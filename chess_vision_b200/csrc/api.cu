@@ -195,7 +195,7 @@ int run_layer<bf16>(cv_square* h, int i, const bf16* in, const bf16* skip, bf16*
 
 template <typename T>
 int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, float* feat, float* feat_chunk, int64_t crop_base,
-             bool first_wave, int first_layer, const StageGate& gate, cudaStream_t s) {
+             bool first_wave, int first_layer, const StageGate& gate, bool fe_permuted, cudaStream_t s) {
     const int fi = gate.f16 ? 1 : 0;                   // which weight images the fused stages read
     const bool t8 = sizeof(T) == 2;
     const int64_t n = (int64_t)nb * 64;
@@ -251,7 +251,7 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
                 ++h->launches;
             }
             rc = launch_stageC(reinterpret_cast<const bf16*>(p2), n, h->sc_img[fi], h->sc_off[fi], h->sc_bytes[fi], reinterpret_cast<bf16*>(p8),
-                               h->num_sms, gate, nb, s);
+                               h->num_sms, gate, fe_permuted ? 0 : nb /* the crops arrive in board order: stage C permutes its hand-off */, s);
             if (rc) return rc;
             ++h->launches;
             rc = prof_mark(h, CV_PROF_TAIL, s);
@@ -282,9 +282,13 @@ int run_wave(cv_square* h, const WavePlan& p, char* ws, int nb, float* squares, 
 // third generation for uint8 HWC boards (piece by piece behind the host path's copies when `by_pieces`), first generation for the
 // other sources and for windows the third cannot stage; float sources that are uint8 images in disguise take the third generation
 // on the recovered bytes (f2u: recovered by the caller once per wave; its device flag picks exactly one of the two kernels).
+// permute: the third-generation kernel may write the crops in the pipeline's permuted order (umma.cuh perm_pos; *permuted says whether
+// it did -- only uint8 HWC sources it supports, and pieces that are whole groups of 32 boards).
 int launch_front(cv_square* h, const void* src, int kind, int nb, int H, const CropGeom& g, bf16* front_out, bool by_pieces,
-                 const uint8_t* f2u, const int* f2u_flag, const StageGate& gate, cudaStream_t s) {
+                 const uint8_t* f2u, const int* f2u_flag, const StageGate& gate, bool permute, bool* permuted, cudaStream_t s) {
     int rc = CV_OK, done = 0;
+    *permuted = false;
+    if (by_pieces && h->piece_boards % 32 != 0 && h->piece_boards < nb) permute = false;
     const bool v3 = (h->impl & CV_IMPL_FRONTEND3) && h->fe3_ok;
     const float* bias_b00 = h->blob + kLayers[1].b_offset;
     if (kind == CV_SRC_U8_HWC && v3) {
@@ -293,7 +297,7 @@ int launch_front(cv_square* h, const void* src, int kind, int nb, int H, const C
                 const int qn = std::min(h->piece_boards, nb - q0);
                 CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
                 rc = launch_frontend3(static_cast<const uint8_t*>(src) + (size_t)q0 * H * H * 3, qn, H, g, h->lut_host, h->fe3_wimg, bias_b00,
-                                      front_out + (size_t)q0 * 64 * 256 * 16, h->num_sms, &done, s, nullptr, gate);
+                                      front_out + (size_t)q0 * 64 * 256 * 16, h->num_sms, &done, s, nullptr, gate, permute ? qn : 0);
                 if (rc) return rc;
                 if (!done) break;                              // configuration not supported: nothing was launched
                 ++h->launches;
@@ -302,10 +306,11 @@ int launch_front(cv_square* h, const void* src, int kind, int nb, int H, const C
                 for (int i = 0; i < h->n_pieces; ++i) CV_CUDA(cudaStreamWaitEvent(s, h->piece_ev[i], 0));
         } else {
             rc = launch_frontend3(static_cast<const uint8_t*>(src), nb, H, g, h->lut_host, h->fe3_wimg, bias_b00, front_out, h->num_sms, &done, s,
-                                  nullptr, gate);
+                                  nullptr, gate, permute ? nb : 0);
             if (rc) return rc;
             h->launches += done;
         }
+        *permuted = permute && done;
     }
     const int* v1_run_flag = nullptr;
     if (kind == CV_SRC_F32_NCHW && f2u != nullptr) {
@@ -385,7 +390,7 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 if (rc) return rc;
                 ++h->launches;
                 rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 0,
-                                 StageGate(), s);
+                                 StageGate(), false, s);
                 if (rc) return rc;
                 continue;
             }
@@ -401,10 +406,13 @@ int forward_impl(cv_square* h, const float* x_f32, const uint8_t* x_u8, int layo
                 rc = prof_mark(h, pass == 0 ? CV_PROF_FRONTEND : CV_PROF_FALLBACK, s);
                 if (rc) return rc;
                 h->prof_suspended = pass > 0;                  // the gated fall-back chain is one profiling slot
-                rc = launch_front(h, src, kind, nb, H, g, front_out, by_pieces && pass == 0, f2u, f2u_flag, passes[pass], s);
+                // crop order: the front end gathers in the permuted order when the whole fused chain follows it and nobody taps a layer
+                const bool permute = (h->impl & all_fused) == all_fused && !(h->tap_dst && h->tap_layer >= 0);
+                bool permuted = false;
+                rc = launch_front(h, src, kind, nb, H, g, front_out, by_pieces && pass == 0, f2u, f2u_flag, passes[pass], permute, &permuted, s);
                 if (rc == CV_OK)
                     rc = run_wave<T>(h, p, ws, nb, squares + (size_t)b0 * 832, feat + (size_t)w0 * 30720, feat, (int64_t)w0 * 64, b0 == 0, 2,
-                                     passes[pass], s);
+                                     passes[pass], permuted, s);
                 h->prof_suspended = false;
                 if (rc) return rc;
             }

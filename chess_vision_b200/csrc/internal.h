@@ -199,7 +199,8 @@ size_t frontend3_weight_image_bytes();
 int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev, cudaStream_t s);
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
                      const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag = nullptr,
-                     const StageGate& gate = StageGate());
+                     const StageGate& gate = StageGate(),
+                     int perm_boards = 0 /* > 0: write the crops in the permuted order of a launch of this many boards (umma.cuh perm_pos) */);
 // float NCHW boards that are Normalize(ToTensor(uint8)) -> the uint8 HWC image + a device flag (1 = some value is not on the uint8 grid)
 int launch_f32_to_u8_boards(const float* x_nchw, int nb, int H, const float* lut_host, uint8_t* out_hwc, int* flag_dev, cudaStream_t s);
 

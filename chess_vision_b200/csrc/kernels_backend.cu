@@ -48,32 +48,6 @@ __device__ __forceinline__ void load8(const float* p, float (&f)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
-// Crop order of the stage C -> stage D hand-off ("square-major inside groups of 32 boards").  Stage D's tile is 32 consecutive crops and
-// its pooled features go to the operand layout of the global head, which interleaves 128 BOARDS at 16-byte granularity: with crops in
-// board order a tile is half of ONE board and every lane's 16-byte store lands 245 KB from its neighbour's.  In the permuted order a tile
-// is one square of 32 consecutive boards, and a warp's store is 512 contiguous bytes.  Stage C's last epilogue does the permutation (its
-// 1.5 KB per crop is the smallest tensor of the path); position n' of crop (b, sq) in a launch of nb boards:
-//   full groups g = b / 32 < nb / 32:  n' = g * 2048 + sq * 32 + b % 32;      last partial group of r = nb % 32 boards:  n' = full * 2048 + sq * r + (b - 32 full)
-__device__ __forceinline__ int64_t perm_pos(int64_t n, int nb) {
-    const int64_t b = n >> 6;
-    const int sq = (int)(n & 63), full = nb >> 5;
-    const int64_t g = b >> 5;
-    if (g < full) return g * 2048 + sq * 32 + (b & 31);
-    return (int64_t)full * 2048 + (int64_t)sq * (nb & 31) + (b - (int64_t)full * 32);
-}
-__device__ __forceinline__ void perm_inv(int64_t np, int nb, int64_t& b, int& sq) {
-    const int full = nb >> 5;
-    const int64_t g = np >> 11;
-    if (g < full) {
-        const int rem = (int)(np & 2047);
-        sq = rem >> 5;
-        b = g * 32 + (rem & 31);
-    } else {
-        const int rem = (int)(np - (int64_t)full * 2048), r = nb & 31;
-        sq = rem / r;
-        b = (int64_t)full * 32 + (rem - sq * r);
-    }
-}
 
 // One 128-row GEMM on the tensor core, issued by ONE thread:  D[128 x n] (+)= A[128 x K] * B[n x K]^T.
 // A: shared-memory operand tile [K/8][128 rows][8] 16-bit (K-major, no swizzle; LBO 2048 B, SBO 128 B).

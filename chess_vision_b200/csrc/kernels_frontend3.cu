@@ -63,6 +63,7 @@ struct Front3Tables {                 // per launch, copied to shared memory
 };
 
 struct Front3Params {
+    int perm_boards;                                              // > 0: output position n holds the crop perm_inv(n, perm_boards) names (umma.cuh)
     const uint8_t* boards;            // (B, H, H, 3) uint8
     const uint8_t* wimg;
     const float* bias_b00;
@@ -163,7 +164,9 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
         uint32_t it = 0, rphase = 0;
         int rslot = 0;
         for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
-            const int r = (n >> 3) & 7, c = n & 7;
+            int sq = n & 63;                                             // square of the crop that output position n holds
+            if (p.perm_boards > 0) { int64_t pb; perm_inv(n, p.perm_boards, pb, sq); }
+            const int r = sq >> 3, c = sq & 7;
             const uint8_t* raw = RAW + rslot * p.raw_bytes;
             TRACE_WINDOW(it);
             TWAIT(0, mbar_wait(raw_full + rslot, rphase));
@@ -285,11 +288,14 @@ frontend3_kernel(const __grid_constant__ Front3Params p, const __grid_constant__
             int slot = 0;
             for (int n = blockIdx.x; n < p.n_crops; n += gridDim.x, ++it) {
                 if ((int)it >= p.n_rawbuf) mbar_wait(raw_empty + slot, phase ^ 1u);      // the slot's previous use (one round ago) has been consumed
-                const int b = n >> 6, rr = (n >> 3) & 7, cc = n & 7;
+                int64_t b = n >> 6;
+                int sq = n & 63;
+                if (p.perm_boards > 0) perm_inv(n, p.perm_boards, b, sq);
+                const int rr = sq >> 3, cc = sq & 7;
                 uint64_t* bar = raw_full + slot;
                 mbar_arrive_expect_tx(bar, (uint32_t)p.box_bytes);
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                             ::"r"(smem_u32(RAW + slot * p.raw_bytes)), "l"(&tmap), "r"(tab.byte0[cc] >> 2), "r"(b * p.H + tab.row0[rr]), "r"(smem_u32(bar))
+                             ::"r"(smem_u32(RAW + slot * p.raw_bytes)), "l"(&tmap), "r"(tab.byte0[cc] >> 2), "r"((int)b * p.H + tab.row0[rr]), "r"(smem_u32(bar))
                              : "memory");
                 if (++slot == p.n_rawbuf) { slot = 0; phase ^= 1u; }
             }
@@ -540,10 +546,12 @@ int launch_frontend3_prep_weights(const float* blob, uint8_t* img, int* flag_dev
 // Returns CV_OK and sets *supported = 0 when this kernel cannot take the configuration (the caller then uses an earlier
 // generation): non-affine normalisation table, window too large for shared memory (512x512 boards), > 255 window rows.
 int launch_frontend3(const uint8_t* boards_hwc, int nb, int H, const CropGeom& g, const float* lut_host, const uint8_t* wimg,
-                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag, const StageGate& gate) {
+                     const float* bias_b00, bf16* y, int num_sms, int* supported, cudaStream_t s, const int* skip_flag, const StageGate& gate,
+                     int perm_boards) {
     *supported = 0;
     if (nb == 0) { *supported = 1; return CV_OK; }
     Front3Params p{};
+    p.perm_boards = perm_boards;
     // normalisation must be affine in the byte value: v = na*u + nb (true for ToTensor + Normalize)
     for (int c = 0; c < 3; ++c) {
         const float* l = lut_host + c * 256;
