@@ -89,6 +89,7 @@ def lib():
     _sig(L.cv_jpeg_info, i32, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int))
     _sig(L.cv_jpeg_decode_batch, i32, vp, vp, i32, i32, i32, vp, i32, vp)
     _sig(L.cv_jpeg_decode_coefficients_host, i32, vp, sz, vp, sz, vp)
+    _sig(L.cv_jpeg_decode_coefficients_host_chunked, i32, vp, sz, vp, sz, i32, i32, vp)
     _sig(L.cv_square_pack_weights, i32, vp, i32, vp, sz)
     _sig(L.cv_square_fp16_status, i32, vp, C.POINTER(C.c_int), C.POINTER(C.c_int))
     _sig(L.cv_square_profile, i32, vp, i32)

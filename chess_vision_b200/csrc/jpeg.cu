@@ -71,6 +71,7 @@ struct BitReader {
     const uint8_t* end;
     uint64_t acc;
     int n;
+    int fake;                     // of the n unread bits, how many are zeros fed after a marker / the end of the range (the youngest ones)
     bool hit_marker;
 #ifdef __CUDA_ARCH__
     // device: the stream is read in aligned 8-byte words (one global load per 8 bytes instead of one dependent load per byte; the
@@ -105,8 +106,10 @@ struct BitReader {
                 b = next_raw();
                 if (b == 0xFF) {
                     if (p < end && peek_raw() == 0) next_raw();          // stuffed zero
-                    else { hit_marker = true; b = 0; }                    // a marker (or the end): zeros from here on, like jdhuff.c
+                    else { hit_marker = true; b = 0; fake += 8; }         // a marker (or the end): zeros from here on, like jdhuff.c
                 }
+            } else {
+                fake += 8;
             }
             acc = (acc << 8) | b;
             n += 8;
@@ -139,7 +142,7 @@ __host__ __device__ inline int huff_extend(int v, int s) { return v < (1 << (s -
 __host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const TableSet& ts, const uint8_t* bytes, int64_t byte0, int64_t byte1, int mcu0,
                                                     int n_mcu, int16_t* coef, const uint8_t* zz) {
     BitReader br;
-    br.p = bytes + byte0; br.end = bytes + byte1; br.acc = 0; br.n = 0; br.hit_marker = false;
+    br.p = bytes + byte0; br.end = bytes + byte1; br.acc = 0; br.n = 0; br.fake = 0; br.hit_marker = false;
     br.init();
     int pred[3] = {0, 0, 0};
     // the fields of the descriptor the loop needs, read once (the coefficient stores below could alias `d` as far as the compiler knows)
@@ -193,12 +196,136 @@ __host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const Ta
     }
 }
 
+// ---- intra-file parallelism: speculative decoding of fixed-size chunks of the entropy-coded bytes ------------------------------------------
+// A baseline Huffman stream has no entry points (the reference's files carry no restart markers), so one thread per file leaves the
+// device nearly empty (4096 files = 4096 threads, ~10 ms whatever the batch).  Chunk i of an interval = the symbols (a Huffman code
+// with its extra bits) that START in raw bits [i*S*8, (i+1)*S*8).  The decoder state at a symbol boundary is (bit position, block index
+// inside the MCU, next zig-zag index).  Round 0 decodes every chunk from a GUESS (chunk start, state 0); Huffman streams resynchronise
+// after a few symbols (and the block / component phase after a few MCUs), so most exit states are already the true ones.  Round r
+// re-decodes chunk i from the exit state of chunk i-1 wherever that changed.  After a fixed number of rounds a chain
+// "entry(i) == exit(i-1) for all i, entry(0) = the true start" PROVES every chunk was decoded from its true state (induction), a prefix
+// sum of the per-chunk block counts places each chunk in the coefficient buffer, and a final pass decodes again and writes.  Intervals
+// whose chain is still broken fall back to the one-thread kernel.  DC values are written as differences and prefix-summed per
+// component afterwards (the predictor is the only state that runs across chunks).  Same routine on host and device.
+struct IvChunks { int32_t chunk0, n_chunks, chunk_bytes; };     // chunks of one interval inside the batch's chunk arrays; their size
+
+__host__ __device__ inline uint64_t pack_state(int64_t bit, int c, int z) { return ((uint64_t)bit << 16) | ((uint64_t)c << 8) | (uint64_t)z; }
+
+// raw bit position (relative to `base`, stuffed bytes counted) of the next unread bit
+__host__ __device__ inline int64_t raw_bitpos(const BitReader& br, const uint8_t* base) {
+    const int real = br.n - br.fake;
+    if (real <= 0) return (int64_t)(br.p - base) * 8;       // everything read (or the range ran out): where the reader stands
+    const uint8_t* q = br.p - (br.hit_marker && br.p[-1] == 0xFF ? 1 : 0);   // the 0xFF of the marker that ended the data was consumed, it is not data
+    for (int j = (real + 7) >> 3; j > 0; --j) {              // walk back over the unread DATA bytes; a 0x00 behind a 0xFF is stuffing
+        --q;
+        if (*q == 0 && q > base && q[-1] == 0xFF) --q;
+    }
+    return (int64_t)(q - base) * 8 + ((8 - (real & 7)) & 7);
+}
+
+// Decodes chunk symbols from `entry` until a symbol boundary at or beyond end_bit (or, WRITE, until block blk_end of the interval).
+// WRITE: coefficients go to their blocks (the buffer was zeroed), DC as the DIFFERENCE; blk0 = blocks of the interval completed before
+// `entry`.  Returns the exit state; *n_done = blocks completed.
+template <bool WRITE>
+__host__ __device__ inline uint64_t huff_decode_chunk(const JpegDesc& d, const TableSet& ts, const uint8_t* bytes, int64_t byte0, int64_t byte1,
+                                                     uint64_t entry, int64_t end_bit, int mcu0, int64_t blk0, int64_t blk_end, int16_t* coef,
+                                                     const uint8_t* zz, int* n_done) {
+    const uint8_t* base = bytes + byte0;
+    const int64_t bit0 = (int64_t)(entry >> 16);
+    int c = (int)(entry >> 8) & 0xff, z = (int)entry & 0xff;
+    BitReader br;
+    br.p = base + (bit0 >> 3); br.end = bytes + byte1; br.acc = 0; br.n = 0; br.fake = 0; br.hit_marker = false;
+    br.init();
+    br.fill();
+    br.skip((int)(bit0 & 7));
+    const int hs = d.hs, vs = d.vs, nlum = hs * vs, bpm = nlum + d.ncomp - 1, mcux = d.mcux;
+    const HuffTab* dctab[3] = {&ts.dc[d.dc_sel[0]], &ts.dc[d.dc_sel[1]], &ts.dc[d.dc_sel[2]]};
+    const HuffTab* actab[3] = {&ts.ac[d.ac_sel[0]], &ts.ac[d.ac_sel[1]], &ts.ac[d.ac_sel[2]]};
+    int comp = c < nlum ? 0 : c - nlum + 1;
+    int64_t blk_i = blk0;                                    // index (inside the interval) of the block in progress
+    int mx = 0, my = 0;
+    int16_t* blk = nullptr;
+    auto locate = [&]() {                                    // WRITE: the block in progress -> its place in the coefficient buffer
+        const int ch = comp == 0 ? hs : 1, cv = comp == 0 ? vs : 1;
+        const int by = comp == 0 ? c / hs : 0, bx = comp == 0 ? c - by * hs : 0;
+        blk = coef + d.coef_off[comp] + ((int64_t)(my * cv + by) * d.bw[comp] + (mx * ch + bx)) * 64;
+    };
+    if (WRITE) {
+        const int mcu = mcu0 + (int)(blk0 / bpm);
+        my = mcu / mcux; mx = mcu - my * mcux;
+        locate();
+    }
+    int done = 0;
+    int64_t pos = bit0;
+    for (;;) {
+        if (WRITE && blk_i >= blk_end) break;
+        if ((int64_t)(br.p - base) * 8 - (br.n - br.fake) >= end_bit) {      // an upper bound of the position: the exact one only near the end
+            pos = raw_bitpos(br, base);
+            if (pos >= end_bit) break;
+        }
+        bool block_done = false;
+        if (z == 0) {
+            const int s = huff_symbol(br, *dctab[comp]);
+            int diff = 0;
+            if (s) {
+                if (br.n < 16) br.fill();
+                const int v = (int)br.peek(s);
+                br.skip(s);
+                diff = huff_extend(v, s);
+            }
+            if (WRITE) blk[0] = (int16_t)diff;
+            z = 1;
+        } else {
+            const int rs = huff_symbol(br, *actab[comp]);
+            const int r = rs >> 4, s = rs & 15;
+            if (s == 0) {
+                if (r != 15) block_done = true;
+                else { z += 16; block_done = z > 63; }
+            } else {
+                z += r;
+                if (z > 63) block_done = true;
+                else {
+                    if (br.n < 16) br.fill();
+                    const int v = (int)br.peek(s);
+                    br.skip(s);
+                    if (WRITE) blk[zz[z]] = (int16_t)huff_extend(v, s);
+                    block_done = ++z > 63;
+                }
+            }
+        }
+        if (block_done) {
+            z = 0; ++done; ++blk_i;
+            if (++c == bpm) { c = 0; if (++mx == mcux) { mx = 0; ++my; } }
+            comp = c < nlum ? 0 : c - nlum + 1;
+            if (WRITE) locate();
+        }
+    }
+    if (WRITE && blk_i >= blk_end) pos = raw_bitpos(br, base);
+    *n_done = done;
+    return pack_state(pos, c, z);
+}
+
+// the guess a chunk starts from in round 0: its first byte (past a stuffed zero), state 0
+__host__ __device__ inline uint64_t chunk_guess(const uint8_t* base, int64_t byte_off) {
+    if (byte_off > 0 && base[byte_off] == 0 && base[byte_off - 1] == 0xFF) ++byte_off;
+    return pack_state(byte_off * 8, 0, 0);
+}
+
+// DC differences -> DC values: blocks of component `comp` of an interval in decode order (MCU by MCU, rows of the MCU, columns)
+__host__ __device__ inline int16_t* dc_block(const JpegDesc& d, int16_t* coef, int comp, int mcu0, int64_t j) {
+    const int ch = comp == 0 ? d.hs : 1, cv = comp == 0 ? d.vs : 1, nb = ch * cv;
+    const int mcu = mcu0 + (int)(j / nb), sub = (int)(j % nb);
+    const int my = mcu / d.mcux, mx = mcu - my * d.mcux, by = sub / ch, bx = sub - by * ch;
+    return coef + d.coef_off[comp] + ((int64_t)(my * cv + by) * d.bw[comp] + (mx * ch + bx)) * 64;
+}
+
 // One thread per interval.  The Huffman table sets of the batch (files written by one encoder share a set) are copied into shared
 // memory when at most `smem_sets` of them exist: a symbol is then two shared-memory look-ups instead of two L2 round trips.
 constexpr int kHuffThreads = 64;
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegDesc* __restrict__ descs, const TableSet* __restrict__ tsets, int n_sets,
                                                                     int smem_sets, const Interval* __restrict__ iv, int n_iv,
-                                                                    const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef) {
+                                                                    const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef,
+                                                                    const int* __restrict__ only_failed /* non-null: intervals with a 0 here are skipped */) {
     extern __shared__ __align__(16) uint8_t huff_smem[];
     __shared__ uint8_t zz[64];
     if (smem_sets > 0) {
@@ -210,10 +337,127 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegDe
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_iv) return;
+    if (only_failed != nullptr && only_failed[i] == 0) return;
     const Interval v = iv[i];
     const JpegDesc& d = descs[v.image];
     const TableSet& ts = smem_sets > 0 ? reinterpret_cast<const TableSet*>(huff_smem)[d.tset] : tsets[d.tset];
     huff_decode_interval(d, ts, bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, zz);
+}
+
+// Chunked decoding (see huff_decode_chunk): one thread per chunk.  Per-chunk state lives in four arrays of the batch.
+struct ChunkArrays {
+    uint64_t* used_entry;         // the entry state a chunk was last decoded from
+    uint64_t* exit_state;         // where that decode ended = the entry of the next chunk
+    int32_t* count;               // blocks it completed
+    int32_t* blk0;                // blocks of the interval completed before the chunk (prefix sum, jpeg_chunk_scan_kernel)
+    int32_t* failed;              // per interval: the chain did not close in the rounds given
+};
+constexpr int kChunkThreads = 128;
+
+__device__ __forceinline__ void load_table_sets(const TableSet* tsets, int n_sets, int smem_sets, uint8_t* huff_smem, uint8_t* zz) {
+    if (smem_sets > 0) {
+        const uint4* src = reinterpret_cast<const uint4*>(tsets);
+        uint4* dst = reinterpret_cast<uint4*>(huff_smem);
+        for (int i = threadIdx.x; i < (int)(n_sets * sizeof(TableSet) / 16); i += blockDim.x) dst[i] = src[i];
+    }
+    if (threadIdx.x < 64) zz[threadIdx.x] = kZigzagDev[threadIdx.x];
+    __syncthreads();
+}
+
+// round 0: every chunk but the last of its interval from its guess; later rounds: only chunks whose predecessor's exit state changed
+__global__ void __launch_bounds__(kChunkThreads) jpeg_spec_kernel(const JpegDesc* __restrict__ descs, const TableSet* __restrict__ tsets, int n_sets,
+                                                                  int smem_sets, const Interval* __restrict__ iv, const IvChunks* __restrict__ ivc,
+                                                                  const int32_t* __restrict__ chunk_iv, int n_chunks, const uint8_t* __restrict__ bytes,
+                                                                  int round, ChunkArrays a) {
+    extern __shared__ __align__(16) uint8_t huff_smem[];
+    __shared__ uint8_t zz[64];
+    load_table_sets(tsets, n_sets, smem_sets, huff_smem, zz);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    const int vi = chunk_iv[g];
+    const IvChunks ic = ivc[vi];
+    const int i = g - ic.chunk0;
+    if (i == ic.n_chunks - 1) return;                        // nobody needs the exit state of the last chunk
+    const Interval v = iv[vi];
+    uint64_t entry;
+    if (i == 0) entry = pack_state(0, 0, 0);
+    else if (round == 0) entry = chunk_guess(bytes + v.byte0, (int64_t)i * ic.chunk_bytes);
+    else entry = a.exit_state[g - 1];                        // a neighbour may be rewriting it right now: either value is a legal entry
+    if (round > 0 && entry == a.used_entry[g]) return;
+    const JpegDesc& d = descs[v.image];
+    const TableSet& ts = smem_sets > 0 ? reinterpret_cast<const TableSet*>(huff_smem)[d.tset] : tsets[d.tset];
+    int done = 0;
+    const uint64_t ex = huff_decode_chunk<false>(d, ts, bytes, v.byte0, v.byte1, entry, (int64_t)(i + 1) * ic.chunk_bytes * 8, v.mcu0, 0, 0, nullptr, zz, &done);
+    a.used_entry[g] = entry;
+    a.exit_state[g] = ex;
+    a.count[g] = done;
+}
+
+// per interval: does the chain close (entry(i) == exit(i-1))?  Block offsets of the chunks.
+__global__ void jpeg_chunk_scan_kernel(const IvChunks* __restrict__ ivc, int n_iv, ChunkArrays a) {
+    const int vi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vi >= n_iv) return;
+    const IvChunks ic = ivc[vi];
+    int ok = 1, run = 0;
+    for (int i = 0; i < ic.n_chunks; ++i) {
+        const int g = ic.chunk0 + i;
+        a.blk0[g] = run;
+        if (i < ic.n_chunks - 1) {
+            if (i > 0 && a.used_entry[g] != a.exit_state[g - 1]) ok = 0;
+            run += a.count[g];
+        }
+    }
+    a.failed[vi] = !ok;
+}
+
+__global__ void __launch_bounds__(kChunkThreads) jpeg_write_kernel(const JpegDesc* __restrict__ descs, const TableSet* __restrict__ tsets, int n_sets,
+                                                                   int smem_sets, const Interval* __restrict__ iv, const IvChunks* __restrict__ ivc,
+                                                                   const int32_t* __restrict__ chunk_iv, int n_chunks, const uint8_t* __restrict__ bytes,
+                                                                   ChunkArrays a, int16_t* __restrict__ coef) {
+    extern __shared__ __align__(16) uint8_t huff_smem[];
+    __shared__ uint8_t zz[64];
+    load_table_sets(tsets, n_sets, smem_sets, huff_smem, zz);
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    const int vi = chunk_iv[g];
+    if (a.failed[vi]) return;                                // the one-thread kernel decodes this interval
+    const IvChunks ic = ivc[vi];
+    const int i = g - ic.chunk0;
+    const Interval v = iv[vi];
+    const JpegDesc& d = descs[v.image];
+    const TableSet& ts = smem_sets > 0 ? reinterpret_cast<const TableSet*>(huff_smem)[d.tset] : tsets[d.tset];
+    const uint64_t entry = i == 0 ? pack_state(0, 0, 0) : a.exit_state[g - 1];
+    const int64_t end_bit = i == ic.n_chunks - 1 ? ((int64_t)1 << 46) : (int64_t)(i + 1) * ic.chunk_bytes * 8;
+    const int64_t blk_end = (int64_t)v.n_mcu * (d.hs * d.vs + d.ncomp - 1);
+    int done = 0;
+    huff_decode_chunk<true>(d, ts, bytes, v.byte0, v.byte1, entry, end_bit, v.mcu0, a.blk0[g], blk_end, coef, zz, &done);
+}
+
+// DC differences -> DC values: one warp per (interval, component); a lane sums a run of consecutive blocks, the warp scans the run sums
+__global__ void __launch_bounds__(128) jpeg_dc_scan_kernel(const JpegDesc* __restrict__ descs, const Interval* __restrict__ iv, int n_iv,
+                                                           const int32_t* __restrict__ failed, int16_t* __restrict__ coef) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int vi = w / 3, comp = w - vi * 3;
+    if (vi >= n_iv || failed[vi]) return;                    // the one-thread kernel wrote absolute values
+    const Interval v = iv[vi];
+    const JpegDesc& d = descs[v.image];
+    if (comp >= d.ncomp) return;
+    const int64_t total = (int64_t)v.n_mcu * (comp == 0 ? d.hs * d.vs : 1);
+    const int64_t per = (total + 31) / 32, j0 = lane * per, j1 = j0 + per < total ? j0 + per : total;
+    int sum = 0;
+    for (int64_t j = j0; j < j1; ++j) sum += dc_block(d, coef, comp, v.mcu0, j)[0];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    int run = incl - sum;
+    for (int64_t j = j0; j < j1; ++j) {
+        int16_t* b = dc_block(d, coef, comp, v.mcu0, j);
+        run += b[0];
+        b[0] = (int16_t)run;
+    }
 }
 
 // ---- jidctint.c jpeg_idct_islow --------------------------------------------------------------------------------------------------------
@@ -498,8 +742,31 @@ struct Batch {                     // host-side layout of one decode call
     std::vector<Interval> intervals;
     std::vector<IdctJob> jobs;
     std::vector<int64_t> job_start, file_base;               // file_base[i]: offset of file i inside the staged byte buffer
+    std::vector<IvChunks> ivc;                               // chunked entropy decoding: chunks of every interval ...
+    std::vector<int32_t> chunk_iv;                           // ... and the interval of every chunk
     int64_t bytes = 0, coef_elems = 0, plane_bytes = 0;
 };
+
+// Chunk size of an interval: what resynchronises is the bit stream (a few symbols) AND the block / component phase (a few MCUs), so the
+// size follows the interval's bytes per MCU: chunk_mcus MCUs' worth, at least min_bytes (chunk_mcus = 0: min_bytes for everyone).
+// Measured on the host (tests/test_jpeg_cpu.py): 8 MCUs close the chain in 2-4 rounds from board files (37 B / MCU) to noise (230 B / MCU).
+void plan_chunks(Batch* b, int min_bytes, int chunk_mcus) {
+    b->ivc.clear(); b->chunk_iv.clear();
+    for (size_t i = 0; i < b->intervals.size(); ++i) {
+        const Interval& v = b->intervals[i];
+        const int64_t len = v.byte1 - v.byte0;
+        int64_t cb = min_bytes;
+        if (chunk_mcus > 0 && v.n_mcu > 0) cb = std::max<int64_t>(cb, ((int64_t)chunk_mcus * len / v.n_mcu + 63) / 64 * 64);
+        cb = std::min<int64_t>(cb, 1 << 20);
+        const int n = (int)std::max<int64_t>(1, (len + cb - 1) / cb);
+        b->ivc.push_back(IvChunks{(int32_t)b->chunk_iv.size(), n, (int32_t)cb});
+        b->chunk_iv.insert(b->chunk_iv.end(), n, (int32_t)i);
+    }
+}
+
+// defaults of the chunked decoder (experiment builds: CV_JPEG_CHUNK bytes, CV_JPEG_MCUS, CV_JPEG_ROUNDS; CV_JPEG_CHUNK=0 = the one-thread
+// kernel).  A round in which nothing changed costs a chunk two loads, so spare rounds are nearly free.
+constexpr int kChunkBytes = 256, kChunkMcus = 8, kSpecRounds = 6;
 
 int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, int H, Batch* b) {
     b->descs.resize(n);
@@ -533,9 +800,18 @@ int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, i
 
 // Staging memory of cv_jpeg_decode_batch, per device, grow-only (cudaMallocHost / cudaMalloc cost milliseconds: never per call).
 struct Scratch {
-    uint8_t *h_stage = nullptr, *d_stage = nullptr, *d_planes = nullptr;
+    uint8_t *h_stage = nullptr, *d_stage = nullptr, *d_planes = nullptr, *d_chunks = nullptr;
     int16_t* d_coef = nullptr;
-    size_t stage_cap = 0, coef_cap = 0, plane_cap = 0;
+    size_t stage_cap = 0, coef_cap = 0, plane_cap = 0, chunk_cap = 0;
+    int reserve_chunks(size_t bytes) {
+        if (bytes > chunk_cap) {
+            if (d_chunks) cudaFree(d_chunks);
+            d_chunks = nullptr; chunk_cap = 0;
+            CV_CUDA(cudaMalloc(&d_chunks, bytes + bytes / 4));
+            chunk_cap = bytes + bytes / 4;
+        }
+        return CV_OK;
+    }
     int reserve(size_t stage, size_t coef, size_t planes) {
         if (stage > stage_cap) {
             if (h_stage) cudaFreeHost(h_stage);
@@ -603,6 +879,90 @@ int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int1
     return CV_OK;
 }
 
+// The chunked decoder (huff_decode_chunk: what the device runs by default) executed on the host, round by round as the kernels do it
+// (every round reads the exit states of the round before).  Output = cv_jpeg_decode_coefficients_host's.  stats (nullable, int32[4]):
+// chunks, chunk decodes over all rounds, intervals whose chain did not close (decoded serially instead), last round that changed a state.
+int cv_jpeg_decode_coefficients_host_chunked(const uint8_t* file_host, size_t size, int16_t* coef_host, size_t capacity, int chunk_bytes, int rounds,
+                                             int32_t* stats) {
+    CV_ARG(file_host != nullptr && coef_host != nullptr, "null argument");
+    CV_ARG((chunk_bytes >= 16 || chunk_bytes == -1) && rounds >= 1, "chunk_bytes >= 16 (or -1: the device path's own rule) and rounds >= 1");
+    Batch b;
+    JpegDesc probe;
+    TableSet probe_ts;
+    const char* why = parse_jpeg(file_host, size, &probe, &probe_ts);
+    if (why) { cv_set_error("cv_jpeg_decode_coefficients_host_chunked: %s", why); return CV_ERR_ARG; }
+    const uint8_t* files[1] = {file_host};
+    int rc = plan_batch(files, &size, 1, probe.width, probe.height, &b);
+    if (rc) return rc;
+    CV_ARG(capacity >= (size_t)b.coef_elems, "coefficient buffer too small");
+    if (chunk_bytes == -1) plan_chunks(&b, kChunkBytes, kChunkMcus);
+    else plan_chunks(&b, chunk_bytes, 0);
+    const JpegDesc& d = b.descs[0];
+    const TableSet& ts = b.tsets[0];
+    const size_t nc = b.chunk_iv.size();
+    std::vector<uint64_t> used(nc, ~0ull), ex(nc, 0), ex_prev;
+    std::vector<int32_t> count(nc, 0), blk0(nc, 0);
+    std::vector<int16_t> aligned((size_t)b.coef_elems + 8, 0);
+    int16_t* dst = reinterpret_cast<int16_t*>((reinterpret_cast<uintptr_t>(aligned.data()) + 15) & ~(uintptr_t)15);
+    int decodes = 0, last_change = -1, failed = 0;
+    for (int r = 0; r < rounds; ++r) {
+        ex_prev = ex;
+        for (size_t g = 0; g < nc; ++g) {
+            const int vi = b.chunk_iv[g];
+            const IvChunks ic = b.ivc[vi];
+            const Interval& v = b.intervals[vi];
+            const int i = (int)g - ic.chunk0;
+            if (i == ic.n_chunks - 1) continue;
+            const uint64_t entry = i == 0 ? pack_state(0, 0, 0) : r == 0 ? chunk_guess(file_host + v.byte0, (int64_t)i * ic.chunk_bytes) : ex_prev[g - 1];
+            if (r > 0 && entry == used[g]) continue;
+            int done = 0;
+            ex[g] = huff_decode_chunk<false>(d, ts, file_host, v.byte0, v.byte1, entry, (int64_t)(i + 1) * ic.chunk_bytes * 8, v.mcu0, 0, 0, nullptr,
+                                             zigzag_tab(), &done);
+            used[g] = entry; count[g] = done;
+            ++decodes; last_change = r;
+        }
+    }
+    for (size_t vi = 0; vi < b.intervals.size(); ++vi) {
+        const IvChunks ic = b.ivc[vi];
+        const Interval& v = b.intervals[vi];
+        bool ok = true;
+        int run = 0;
+        for (int i = 0; i < ic.n_chunks; ++i) {
+            const int g = ic.chunk0 + i;
+            blk0[g] = run;
+            if (i < ic.n_chunks - 1) {
+                if (i > 0 && used[g] != ex[g - 1]) ok = false;
+                run += count[g];
+            }
+        }
+        if (!ok) {
+            ++failed;
+            huff_decode_interval(d, ts, file_host, v.byte0, v.byte1, v.mcu0, v.n_mcu, dst, zigzag_tab());
+            continue;
+        }
+        const int64_t blk_end = (int64_t)v.n_mcu * (d.hs * d.vs + d.ncomp - 1);
+        for (int i = 0; i < ic.n_chunks; ++i) {
+            const int g = ic.chunk0 + i;
+            int done = 0;
+            huff_decode_chunk<true>(d, ts, file_host, v.byte0, v.byte1, i == 0 ? pack_state(0, 0, 0) : ex[g - 1],
+                                    i == ic.n_chunks - 1 ? ((int64_t)1 << 46) : (int64_t)(i + 1) * ic.chunk_bytes * 8, v.mcu0, blk0[g], blk_end, dst,
+                                    zigzag_tab(), &done);
+        }
+        for (int c = 0; c < d.ncomp; ++c) {
+            const int64_t total = (int64_t)v.n_mcu * (c == 0 ? d.hs * d.vs : 1);
+            int run_dc = 0;
+            for (int64_t j = 0; j < total; ++j) {
+                int16_t* blk = dc_block(d, dst, c, v.mcu0, j);
+                run_dc += blk[0];
+                blk[0] = (int16_t)run_dc;
+            }
+        }
+    }
+    memcpy(coef_host, dst, (size_t)b.coef_elems * sizeof(int16_t));
+    if (stats) { stats[0] = (int32_t)nc; stats[1] = decodes; stats[2] = failed; stats[3] = last_change; }
+    return CV_OK;
+}
+
 // n baseline JPEG files of ONE size (host pointers) -> rgb (DEVICE, uint8 (n, H, W, 3)), bit-exact with PIL.Image.open(f).convert("RGB").
 // entropy_on_host != 0 decodes the Huffman streams on the host and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
 // compressed bytes; results are identical.  Synchronises `stream` before returning.  Staging memory (pinned host + device) is kept
@@ -630,6 +990,14 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     Batch b;
     int rc = plan_batch(files_host, sizes, n, W, H, &b);
     if (rc) return rc;
+    int chunk_bytes = kChunkBytes, chunk_mcus = kChunkMcus, spec_rounds = kSpecRounds;
+#ifdef CV_EXPERIMENTS
+    if (const char* e = getenv("CV_JPEG_CHUNK")) chunk_bytes = atoi(e);
+    if (const char* e = getenv("CV_JPEG_MCUS")) chunk_mcus = atoi(e);
+    if (const char* e = getenv("CV_JPEG_ROUNDS")) spec_rounds = std::max(1, atoi(e));
+#endif
+    const bool chunked = !entropy_on_host && chunk_bytes >= 16;
+    if (chunked) plan_chunks(&b, chunk_bytes, chunk_mcus);
     mark("parse headers + plan");
     int dev = 0;
     CV_CUDA(cudaGetDevice(&dev));
@@ -641,6 +1009,8 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     size_t off = 0;
     auto place = [&](size_t bytes) { const size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
     const size_t o_desc = place(desc_b), o_ts = place(ts_b), o_iv = place(iv_b), o_job = place(job_b), o_js = place(js_b);
+    const size_t ivc_b = b.ivc.size() * sizeof(IvChunks), civ_b = b.chunk_iv.size() * sizeof(int32_t);
+    const size_t o_ivc = place(ivc_b), o_civ = place(civ_b);
     const size_t payload = entropy_on_host ? (size_t)b.coef_elems * sizeof(int16_t) : (size_t)b.bytes + 16;
     const size_t o_pay = place(payload);
     rc = sc.reserve(off, (size_t)b.coef_elems * sizeof(int16_t), (size_t)b.plane_bytes);
@@ -650,6 +1020,8 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     memcpy(sc.h_stage + o_iv, b.intervals.data(), iv_b);
     memcpy(sc.h_stage + o_job, b.jobs.data(), job_b);
     memcpy(sc.h_stage + o_js, b.job_start.data(), js_b);
+    if (ivc_b) memcpy(sc.h_stage + o_ivc, b.ivc.data(), ivc_b);
+    if (civ_b) memcpy(sc.h_stage + o_civ, b.chunk_iv.data(), civ_b);
     const JpegDesc* d_desc = reinterpret_cast<const JpegDesc*>(sc.d_stage + o_desc);
     const TableSet* d_ts = reinterpret_cast<const TableSet*>(sc.d_stage + o_ts);
     const Interval* d_iv = reinterpret_cast<const Interval*>(sc.d_stage + o_iv);
@@ -674,10 +1046,60 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
         const int n_iv = (int)b.intervals.size(), n_sets = (int)b.tsets.size();
         const int smem_sets = n_sets <= 6 ? n_sets : 0;          // up to 44 KB of shared memory for the table sets
         const size_t smem = (size_t)smem_sets * sizeof(TableSet);
-        if (smem > 48 * 1024 - 1024) CV_CUDA(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        jpeg_huffman_kernel<<<(n_iv + kHuffThreads - 1) / kHuffThreads, kHuffThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, n_iv,
-                                                                                              sc.d_stage + o_pay, sc.d_coef);
+        const uint8_t* d_bytes = sc.d_stage + o_pay;
+        if (smem > 48 * 1024 - 1024) {
+            CV_CUDA(cudaFuncSetAttribute(jpeg_huffman_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CV_CUDA(cudaFuncSetAttribute(jpeg_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CV_CUDA(cudaFuncSetAttribute(jpeg_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        const int* only_failed = nullptr;
+        if (chunked) {
+            // speculative rounds -> chain check + block offsets -> writing pass -> DC prefix sums; the one-thread kernel behind them
+            // takes the intervals whose chain did not close (none, normally: it exits at once)
+            const int n_ch = (int)b.chunk_iv.size();
+            const size_t per_chunk = 2 * sizeof(uint64_t) + 2 * sizeof(int32_t);
+            rc = sc.reserve_chunks((size_t)n_ch * per_chunk + (size_t)n_iv * sizeof(int32_t) + 64);
+            if (rc) return rc;
+            ChunkArrays a;
+            a.used_entry = reinterpret_cast<uint64_t*>(sc.d_chunks);
+            a.exit_state = a.used_entry + n_ch;
+            a.count = reinterpret_cast<int32_t*>(a.exit_state + n_ch);
+            a.blk0 = a.count + n_ch;
+            a.failed = a.blk0 + n_ch;
+            const IvChunks* d_ivc = reinterpret_cast<const IvChunks*>(sc.d_stage + o_ivc);
+            const int32_t* d_civ = reinterpret_cast<const int32_t*>(sc.d_stage + o_civ);
+            CV_CUDA(cudaMemsetAsync(sc.d_coef, 0, (size_t)b.coef_elems * sizeof(int16_t), s));
+            mark("  chunked: zero coefficients");
+            const int grid = (n_ch + kChunkThreads - 1) / kChunkThreads;
+            for (int r = 0; r < spec_rounds; ++r) {
+                jpeg_spec_kernel<<<grid, kChunkThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, d_ivc, d_civ, n_ch, d_bytes, r, a);
+                CV_CHECK_LAUNCH();
+                mark("  chunked: speculative round");
+            }
+            jpeg_chunk_scan_kernel<<<(n_iv + 127) / 128, 128, 0, s>>>(d_ivc, n_iv, a);
+            CV_CHECK_LAUNCH();
+            mark("  chunked: chain check + offsets");
+            jpeg_write_kernel<<<grid, kChunkThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, d_ivc, d_civ, n_ch, d_bytes, a, sc.d_coef);
+            CV_CHECK_LAUNCH();
+            mark("  chunked: writing pass");
+            jpeg_dc_scan_kernel<<<(n_iv * 3 * 32 + 127) / 128, 128, 0, s>>>(d_desc, d_iv, n_iv, a.failed, sc.d_coef);
+            CV_CHECK_LAUNCH();
+            mark("  chunked: DC prefix sums");
+            only_failed = a.failed;
+        }
+        jpeg_huffman_kernel<<<(n_iv + kHuffThreads - 1) / kHuffThreads, kHuffThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, n_iv, d_bytes,
+                                                                                              sc.d_coef, only_failed);
         CV_CHECK_LAUNCH();
+#ifdef CV_EXPERIMENTS
+        if (trace && chunked) {
+            std::vector<int32_t> f(n_iv);
+            cudaStreamSynchronize(s);
+            cudaMemcpy(f.data(), only_failed, n_iv * sizeof(int32_t), cudaMemcpyDeviceToHost);
+            int nf = 0;
+            for (int v : f) nf += v != 0;
+            fprintf(stderr, "  jpeg chunked: %zu chunks (>= %d bytes, %d MCUs), %d rounds, %d of %d intervals fell back\n", b.chunk_iv.size(), chunk_bytes, chunk_mcus, spec_rounds, nf, n_iv);
+        }
+#endif
         mark("entropy decode (device)");
     }
     const int64_t total_blocks = b.job_start.back();

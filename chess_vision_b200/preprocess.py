@@ -89,9 +89,11 @@ def decode_jpegs(files, device, entropy_on_host: bool = False, out: torch.Tensor
     return out
 
 
-def jpeg_coefficients_host(data: bytes):
+def jpeg_coefficients_host(data: bytes, chunk_bytes: int = 0, rounds: int = 4, stats: list = None):
     """Quantised DCT coefficients of one file from the HOST build of the product's entropy decoder (no GPU): list per component of
-    int16 arrays (block rows, block columns, 64) in natural order -- the no-GPU tests compare them with the oracle's."""
+    int16 arrays (block rows, block columns, 64) in natural order -- the no-GPU tests compare them with the oracle's.
+    chunk_bytes > 0 (or -1 = the device path's own size rule): through the chunked scheme of the device path (speculative rounds, chain check, writing pass, DC prefix sums) run on
+    the host; ``stats`` (a list) then receives [chunks, chunk decodes, intervals that fell back, last round that changed a state]."""
     L = _native.lib()
     buf = (C.c_char * len(data)).from_buffer_copy(data)
     grid = (C.c_int32 * 6)()
@@ -99,7 +101,14 @@ def jpeg_coefficients_host(data: bytes):
     shapes = [(grid[2 * c], grid[2 * c + 1]) for c in range(3) if grid[2 * c]]
     total = sum(a * b * 64 for a, b in shapes)
     coef = np.zeros(total, np.int16)
-    _native.check(L.cv_jpeg_decode_coefficients_host(C.cast(buf, C.c_void_p), len(data), coef.ctypes.data_as(C.c_void_p), total, None))
+    if chunk_bytes != 0:
+        st = (C.c_int32 * 4)()
+        _native.check(L.cv_jpeg_decode_coefficients_host_chunked(C.cast(buf, C.c_void_p), len(data), coef.ctypes.data_as(C.c_void_p), total,
+                                                                 chunk_bytes, rounds, C.cast(st, C.c_void_p)))
+        if stats is not None:
+            stats[:] = list(st)
+    else:
+        _native.check(L.cv_jpeg_decode_coefficients_host(C.cast(buf, C.c_void_p), len(data), coef.ctypes.data_as(C.c_void_p), total, None))
     out, off = [], 0
     for a, b in shapes:
         out.append(coef[off:off + a * b * 64].reshape(a, b, 64))

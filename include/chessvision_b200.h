@@ -244,14 +244,22 @@ int cv_resize_coeffs_host(int in_size, int out_size, int* ksize, int32_t* bounds
  * cv_jpeg_info: size and component count from the header (HOST pointer, no GPU).
  * cv_jpeg_decode_batch: n files of ONE size (HOST pointers) -> rgb (DEVICE, uint8 (n, height, width, 3)): the layout
  *   cv_resize_bilinear_u8 / cv_square_predict_u8 take.  By default the COMPRESSED bytes cross PCIe and the Huffman streams are walked on
- *   the device (one thread per restart interval); entropy_on_host != 0 walks them on the host and ships coefficients (same result).
+ *   the device, 256-byte chunks of every file in parallel: each chunk is decoded speculatively from its first byte, re-decoded from its
+ *   predecessor's exit state until the chain of states closes (a Huffman stream resynchronises by itself), then decoded once more into
+ *   the coefficient buffer; a file whose chain does not close within the rounds is walked by one thread instead (same result either
+ *   way).  entropy_on_host != 0 walks the streams on the host and ships coefficients (same result; the quicker way for a few files).
  *   Blocks until the pixels are in `rgb` (staging buffers are per call).
  * cv_jpeg_decode_coefficients_host: the entropy decoder alone, on the host (the same routine the device kernel runs), for no-GPU tests:
- *   quantised coefficients in natural order, component after component, [block rows][block columns][64]; block_grid (3 x (rows, cols)). */
+ *   quantised coefficients in natural order, component after component, [block rows][block columns][64]; block_grid (3 x (rows, cols)).
+ * cv_jpeg_decode_coefficients_host_chunked: the same coefficients through the chunked scheme of the device path, run on the host round by
+ *   round (no-GPU tests of the scheme itself); stats (nullable, int32[4]) = chunks, chunk decodes over all rounds, intervals that fell back
+ *   to the serial walk, last round that changed a state. */
 int cv_jpeg_info(const uint8_t* file_host, size_t size, int* width, int* height, int* components);
 int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int width, int height, uint8_t* rgb,
                          int entropy_on_host, void* stream);
 int cv_jpeg_decode_coefficients_host(const uint8_t* file_host, size_t size, int16_t* coef_host, size_t capacity, int32_t* block_grid);
+int cv_jpeg_decode_coefficients_host_chunked(const uint8_t* file_host, size_t size, int16_t* coef_host, size_t capacity, int chunk_bytes,
+                                             int rounds, int32_t* stats);
 
 #ifdef __cplusplus
 }

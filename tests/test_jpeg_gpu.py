@@ -77,3 +77,25 @@ def test_predict_images_on_jpeg_files_equals_reference_predict(gpu_model, tmp_pa
     finally:
         gpu_model.precision = "fp16"
     assert got == want
+
+
+def test_chunked_device_entropy_decoder_on_hard_streams():
+    """Files whose Huffman streams are slow to resynchronise (noise at quality 100: the chain of chunk states needs many rounds, some
+    files fall back to the one-thread kernel) and files far larger than a chunk, many per call: still Pillow's pixels, byte for byte."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(9)
+    files, want = [], []
+    for k in range(40):
+        img = rng.integers(0, 256, (208, 176, 3), dtype=np.uint8)
+        if k % 4 == 1:
+            img = (img // 8 + resize_oracle.synth_image(900 + k, 208, 176) // 2).astype(np.uint8)
+        b = io.BytesIO()
+        Image.fromarray(img).save(b, "JPEG", quality=(100, 97, 90, 35)[k % 4], subsampling=(0, 2, 1, 2)[(k // 4) % 4])
+        files.append(b.getvalue())
+        want.append(np.asarray(Image.open(io.BytesIO(files[-1])).convert("RGB")))
+    got = preprocess.decode_jpegs(files, "cuda").cpu().numpy()
+    assert np.array_equal(got, np.stack(want))
+    again = preprocess.decode_jpegs(files, "cuda").cpu().numpy()          # scratch arrays are reused: stale chunk states must not matter
+    assert np.array_equal(again, got)
+    host = preprocess.decode_jpegs(files, "cuda", entropy_on_host=True).cpu().numpy()
+    assert np.array_equal(host, got)
