@@ -14,12 +14,14 @@
 // chroma on the fly and writes RGB bytes (B, H, W, 3) -- the layout cv_resize_bilinear_u8 / cv_square_predict_u8 take.
 // The same Huffman routine compiled for the host backs cv_jpeg_decode_coefficients_host (no-GPU tests against the oracle).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -100,6 +102,18 @@ struct BitReader {
     inline uint32_t peek_raw() { return *p; }
 #endif
     __host__ __device__ inline void fill() {
+#ifdef __CUDA_ARCH__
+        // device fast path: four stream bytes at once when none of them is 0xFF (no stuffing, no marker) and the accumulator has room
+        if (n <= 32 && !hit_marker && word_left >= 4 && p + 4 <= end) {
+            const uint32_t x = (uint32_t)word, y = ~x;
+            if (((y - 0x01010101u) & x & 0x80808080u) == 0) {             // no byte of y is zero <=> no byte of x is 0xFF
+                acc = (acc << 32) | __byte_perm(x, 0, 0x0123);
+                n += 32;
+                word >>= 32; word_left -= 4; p += 4;
+                return;
+            }
+        }
+#endif
         while (n <= 56) {
             uint32_t b = 0;
             if (!hit_marker && p < end) {
@@ -140,7 +154,7 @@ __host__ __device__ inline int huff_extend(int v, int s) { return v < (1 << (s -
 // Decodes the MCUs [mcu0, mcu0 + n_mcu) of one file from its own byte range.  Every coefficient block is zeroed with eight 16-byte
 // stores and the non-zero coefficients are stored as they are decoded (stores do not stall the thread; no local array).
 __host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const TableSet& ts, const uint8_t* bytes, int64_t byte0, int64_t byte1, int mcu0,
-                                                    int n_mcu, int16_t* coef, const uint8_t* zz) {
+                                                    int n_mcu, int16_t* coef, const uint8_t* zz, int16_t* dcbuf = nullptr /* DC of block k also to dcbuf[k] */) {
     BitReader br;
     br.p = bytes + byte0; br.end = bytes + byte1; br.acc = 0; br.n = 0; br.fake = 0; br.hit_marker = false;
     br.init();
@@ -174,6 +188,7 @@ __host__ __device__ inline void huff_decode_interval(const JpegDesc& d, const Ta
                         pred[c] += huff_extend(v, s);
                     }
                     blk[0] = (int16_t)pred[c];
+                    if (dcbuf != nullptr) dcbuf[(blk - coef) >> 6] = (int16_t)pred[c];
                     for (int k = 1; k < 64;) {
                         const int rs = huff_symbol(br, act);
                         const int r = rs >> 4;
@@ -229,7 +244,7 @@ __host__ __device__ inline int64_t raw_bitpos(const BitReader& br, const uint8_t
 template <bool WRITE>
 __host__ __device__ inline uint64_t huff_decode_chunk(const JpegDesc& d, const TableSet& ts, const uint8_t* bytes, int64_t byte0, int64_t byte1,
                                                      uint64_t entry, int64_t end_bit, int mcu0, int64_t blk0, int64_t blk_end, int16_t* coef,
-                                                     const uint8_t* zz, int* n_done) {
+                                                     const uint8_t* zz, int* n_done, int16_t* dcbuf = nullptr /* WRITE: DC differences go to dcbuf[block] */) {
     const uint8_t* base = bytes + byte0;
     const int64_t bit0 = (int64_t)(entry >> 16);
     int c = (int)(entry >> 8) & 0xff, z = (int)entry & 0xff;
@@ -263,36 +278,24 @@ __host__ __device__ inline uint64_t huff_decode_chunk(const JpegDesc& d, const T
             pos = raw_bitpos(br, base);
             if (pos >= end_bit) break;
         }
-        bool block_done = false;
-        if (z == 0) {
-            const int s = huff_symbol(br, *dctab[comp]);
-            int diff = 0;
-            if (s) {
-                if (br.n < 16) br.fill();
-                const int v = (int)br.peek(s);
-                br.skip(s);
-                diff = huff_extend(v, s);
-            }
-            if (WRITE) blk[0] = (int16_t)diff;
-            z = 1;
-        } else {
-            const int rs = huff_symbol(br, *actab[comp]);
-            const int r = rs >> 4, s = rs & 15;
-            if (s == 0) {
-                if (r != 15) block_done = true;
-                else { z += 16; block_done = z > 63; }
-            } else {
-                z += r;
-                if (z > 63) block_done = true;
-                else {
-                    if (br.n < 16) br.fill();
-                    const int v = (int)br.peek(s);
-                    br.skip(s);
-                    if (WRITE) blk[zz[z]] = (int16_t)huff_extend(v, s);
-                    block_done = ++z > 63;
-                }
+        // one symbol per iteration, the same instruction path for DC and AC symbols (a warp's lanes are in different states)
+        const bool dc = z == 0;
+        const int sym = huff_symbol(br, dc ? *dctab[comp] : *actab[comp]);
+        const int r = dc ? 0 : sym >> 4, s = dc ? sym : sym & 15;
+        const int zi = z + r;                                // zig-zag index of the coefficient this symbol carries (DC: 0)
+        const bool has_value = s != 0 && zi <= 63;           // run past the block's end (corrupt / speculative garbage): no value bits, block over
+        if (has_value) {
+            if (br.n < 16) br.fill();
+            const int v = (int)br.peek(s);
+            br.skip(s);
+            if (WRITE) {                                                  // DC: the DIFFERENCE (a zero difference is what the buffers hold)
+                if (dc && dcbuf != nullptr) dcbuf[(blk - coef) >> 6] = (int16_t)huff_extend(v, s);
+                else blk[zz[zi]] = (int16_t)huff_extend(v, s);
             }
         }
+        const bool eob = !dc && s == 0 && r != 15;
+        z = (!dc && s == 0) ? z + 16 : zi + 1;               // ZRL skips 16; everything else moves behind the coefficient
+        const bool block_done = eob || z > 63;
         if (block_done) {
             z = 0; ++done; ++blk_i;
             if (++c == bpm) { c = 0; if (++mx == mcux) { mx = 0; ++my; } }
@@ -312,11 +315,11 @@ __host__ __device__ inline uint64_t chunk_guess(const uint8_t* base, int64_t byt
 }
 
 // DC differences -> DC values: blocks of component `comp` of an interval in decode order (MCU by MCU, rows of the MCU, columns)
-__host__ __device__ inline int16_t* dc_block(const JpegDesc& d, int16_t* coef, int comp, int mcu0, int64_t j) {
+__host__ __device__ inline int16_t* dc_block(const JpegDesc& d, int16_t* coef, int comp, int mcu0, int64_t j, int stride = 64 /* 1: compact DC buffer */) {
     const int ch = comp == 0 ? d.hs : 1, cv = comp == 0 ? d.vs : 1, nb = ch * cv;
     const int mcu = mcu0 + (int)(j / nb), sub = (int)(j % nb);
     const int my = mcu / d.mcux, mx = mcu - my * d.mcux, by = sub / ch, bx = sub - by * ch;
-    return coef + d.coef_off[comp] + ((int64_t)(my * cv + by) * d.bw[comp] + (mx * ch + bx)) * 64;
+    return coef + (d.coef_off[comp] / 64 + ((int64_t)(my * cv + by) * d.bw[comp] + (mx * ch + bx))) * stride;
 }
 
 // One thread per interval.  The Huffman table sets of the batch (files written by one encoder share a set) are copied into shared
@@ -325,7 +328,8 @@ constexpr int kHuffThreads = 64;
 __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegDesc* __restrict__ descs, const TableSet* __restrict__ tsets, int n_sets,
                                                                     int smem_sets, const Interval* __restrict__ iv, int n_iv,
                                                                     const uint8_t* __restrict__ bytes, int16_t* __restrict__ coef,
-                                                                    const int* __restrict__ only_failed /* non-null: intervals with a 0 here are skipped */) {
+                                                                    const int* __restrict__ only_failed /* non-null: intervals with a 0 here are skipped */,
+                                                                    int16_t* __restrict__ dcbuf /* non-null: DC values also go there */) {
     extern __shared__ __align__(16) uint8_t huff_smem[];
     __shared__ uint8_t zz[64];
     if (smem_sets > 0) {
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kHuffThreads) jpeg_huffman_kernel(const JpegDe
     const Interval v = iv[i];
     const JpegDesc& d = descs[v.image];
     const TableSet& ts = smem_sets > 0 ? reinterpret_cast<const TableSet*>(huff_smem)[d.tset] : tsets[d.tset];
-    huff_decode_interval(d, ts, bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, zz);
+    huff_decode_interval(d, ts, bytes, v.byte0, v.byte1, v.mcu0, v.n_mcu, coef, zz, dcbuf);
 }
 
 // Chunked decoding (see huff_decode_chunk): one thread per chunk.  Per-chunk state lives in four arrays of the batch.
@@ -351,6 +355,7 @@ struct ChunkArrays {
     int32_t* count;               // blocks it completed
     int32_t* blk0;                // blocks of the interval completed before the chunk (prefix sum, jpeg_chunk_scan_kernel)
     int32_t* failed;              // per interval: the chain did not close in the rounds given
+    int16_t* dcbuf;               // DC of block k of the batch (differences, then values): the IDCT kernel reads it instead of coefficient 0
 };
 constexpr int kChunkThreads = 128;
 
@@ -430,12 +435,12 @@ __global__ void __launch_bounds__(kChunkThreads) jpeg_write_kernel(const JpegDes
     const int64_t end_bit = i == ic.n_chunks - 1 ? ((int64_t)1 << 46) : (int64_t)(i + 1) * ic.chunk_bytes * 8;
     const int64_t blk_end = (int64_t)v.n_mcu * (d.hs * d.vs + d.ncomp - 1);
     int done = 0;
-    huff_decode_chunk<true>(d, ts, bytes, v.byte0, v.byte1, entry, end_bit, v.mcu0, a.blk0[g], blk_end, coef, zz, &done);
+    huff_decode_chunk<true>(d, ts, bytes, v.byte0, v.byte1, entry, end_bit, v.mcu0, a.blk0[g], blk_end, coef, zz, &done, a.dcbuf);
 }
 
 // DC differences -> DC values: one warp per (interval, component); a lane sums a run of consecutive blocks, the warp scans the run sums
 __global__ void __launch_bounds__(128) jpeg_dc_scan_kernel(const JpegDesc* __restrict__ descs, const Interval* __restrict__ iv, int n_iv,
-                                                           const int32_t* __restrict__ failed, int16_t* __restrict__ coef) {
+                                                           const int32_t* __restrict__ failed, int16_t* __restrict__ dcbuf) {
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int vi = w / 3, comp = w - vi * 3;
     if (vi >= n_iv || failed[vi]) return;                    // the one-thread kernel wrote absolute values
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(128) jpeg_dc_scan_kernel(const JpegDesc* __res
     const int64_t total = (int64_t)v.n_mcu * (comp == 0 ? d.hs * d.vs : 1);
     const int64_t per = (total + 31) / 32, j0 = lane * per, j1 = j0 + per < total ? j0 + per : total;
     int sum = 0;
-    for (int64_t j = j0; j < j1; ++j) sum += dc_block(d, coef, comp, v.mcu0, j)[0];
+    for (int64_t j = j0; j < j1; ++j) sum += dc_block(d, dcbuf, comp, v.mcu0, j, 1)[0];
     int incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(128) jpeg_dc_scan_kernel(const JpegDesc* __res
     }
     int run = incl - sum;
     for (int64_t j = j0; j < j1; ++j) {
-        int16_t* b = dc_block(d, coef, comp, v.mcu0, j);
+        int16_t* b = dc_block(d, dcbuf, comp, v.mcu0, j, 1);
         run += b[0];
         b[0] = (int16_t)run;
     }
@@ -498,6 +503,7 @@ struct IdctJob { int32_t image, comp; int64_t first_block, n_blocks; };      // 
 // 256 threads = 32 blocks x 8 threads.  Blocks are addressed through a flat (image, component) job list: block g of the batch.
 __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDesc* __restrict__ descs, const int64_t* __restrict__ job_start /*[n_jobs+1]*/,
                                                         const IdctJob* __restrict__ jobs, int n_jobs, const int16_t* __restrict__ coef,
+                                                        const int16_t* __restrict__ dcbuf /* non-null: DC of block k of the batch = dcbuf[k] */,
                                                         uint8_t* __restrict__ planes) {
     __shared__ int ws[32][8][9];
     const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
@@ -514,12 +520,24 @@ __global__ void __launch_bounds__(256) jpeg_idct_kernel(const JpegDesc* __restri
     const IdctJob job = jobs[active ? lo : 0];
     const JpegDesc& d = descs[job.image];
     const int64_t b = g - job_start[active ? lo : 0];        // block index inside the component
-    if (active) {                                            // pass 1: column t
+    if (active) {                                            // row t of the block: one 16-byte load (a block is 128 contiguous bytes), dequantised
         const int16_t* cb = coef + (job.first_block + b) * 64;
-        const uint16_t* q = d.qt[d.q_sel[job.comp]];
+        const uint4 raw = *reinterpret_cast<const uint4*>(cb + t * 8);
+        const uint2* qrow = reinterpret_cast<const uint2*>(d.qt[d.q_sel[job.comp]] + t * 8);       // the tables are 8-byte aligned inside JpegDesc
+        const uint2 q0 = qrow[0], q1 = qrow[1];
+        const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w}, qq[4] = {q0.x, q0.y, q1.x, q1.y};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            ws[lb][t][2 * c] = (int)(int16_t)(rw[c] & 0xffffu) * (int)(qq[c] & 0xffffu);
+            ws[lb][t][2 * c + 1] = (int)(int16_t)(rw[c] >> 16) * (int)(qq[c] >> 16);
+        }
+        if (dcbuf != nullptr && t == 0) ws[lb][0][0] = (int)dcbuf[job.first_block + b] * (int)(qq[0] & 0xffffu);
+    }
+    __syncthreads();
+    if (active) {                                            // pass 1: column t (read and written back by the same thread)
         int in[8], o[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) in[r] = (int)cb[r * 8 + t] * (int)q[r * 8 + t];
+        for (int r = 0; r < 8; ++r) in[r] = ws[lb][r][t];
         idct8(in, o, CONST_BITS - PASS1_BITS);
 #pragma unroll
         for (int r = 0; r < 8; ++r) ws[lb][r][t] = o[r];
@@ -587,6 +605,64 @@ __global__ void __launch_bounds__(256) jpeg_color_kernel(const JpegDesc* __restr
     }
     uint8_t* o = rgb + ((int64_t)img * H * W + i) * 3;
     o[0] = (uint8_t)r; o[1] = (uint8_t)g; o[2] = (uint8_t)b;
+}
+
+// Four horizontally consecutive pixels per thread (image width a multiple of 4): the luma bytes are one word, the h2v2 column sums
+// 3 * near + far are computed once for the four chroma columns the pixels touch (17 loads per 4 pixels instead of 36), and the twelve
+// output bytes leave as three words.  Other samplings take chroma_at() per pixel.  Same arithmetic as jpeg_color_kernel.
+__device__ __forceinline__ void ycc_to_rgb(int Y, int cb, int cr, int& r, int& g, int& b) {
+    r = Y + ((FIX16(1.40200) * cr + 32768) >> 16);
+    g = Y + ((-FIX16(0.34414) * cb + 32768 - FIX16(0.71414) * cr) >> 16);
+    b = Y + ((FIX16(1.77200) * cb + 32768) >> 16);
+    r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
+}
+__device__ __forceinline__ void h2v2_fancy4(const uint8_t* pl, int pitch, int dw, int dh, int x0, int y, int (&out)[4]) {
+    const int cy = y >> 1, oy = (y & 1) ? min(cy + 1, dh - 1) : max(cy - 1, 0), cx0 = x0 >> 1;
+    const uint8_t* near = pl + cy * pitch;
+    const uint8_t* far = pl + oy * pitch;
+    int cs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = min(max(cx0 - 1 + k, 0), dw - 1);
+        cs[k] = 3 * (int)near[c] + (int)far[c];
+    }
+    out[0] = cx0 == 0 ? (cs[1] * 4 + 8) >> 4 : (cs[1] * 3 + cs[0] + 8) >> 4;
+    out[1] = cx0 == dw - 1 ? (cs[1] * 4 + 7) >> 4 : (cs[1] * 3 + cs[2] + 7) >> 4;
+    out[2] = (cs[2] * 3 + cs[1] + 8) >> 4;
+    out[3] = cx0 + 1 == dw - 1 ? (cs[2] * 4 + 7) >> 4 : (cs[2] * 3 + cs[3] + 7) >> 4;
+}
+__global__ void __launch_bounds__(256) jpeg_color4_kernel(const JpegDesc* __restrict__ descs, const uint8_t* __restrict__ planes, int W, int H,
+                                                          uint8_t* __restrict__ rgb) {
+    const int img = blockIdx.y;
+    const int g4 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g4 >= (W * H) >> 2) return;
+    const JpegDesc& d = descs[img];
+    const int i0 = g4 << 2, y = i0 / W, x0 = i0 - y * W;
+    const uint32_t yw = *reinterpret_cast<const uint32_t*>(planes + d.plane_off[0] + (int64_t)y * d.bw[0] * 8 + x0);
+    int r[4], g[4], b[4];
+    if (d.ncomp == 3) {
+        const int dw = (d.width + d.hs - 1) / d.hs, dh = (d.height + d.vs - 1) / d.vs;
+        int cb[4], cr[4];
+        if (d.hs == 2 && d.vs == 2 && dw > 2) {
+            h2v2_fancy4(planes + d.plane_off[1], d.bw[1] * 8, dw, dh, x0, y, cb);
+            h2v2_fancy4(planes + d.plane_off[2], d.bw[2] * 8, dw, dh, x0, y, cr);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                cb[k] = chroma_at(planes + d.plane_off[1], d.bw[1] * 8, dw, dh, d.hs, d.vs, x0 + k, y);
+                cr[k] = chroma_at(planes + d.plane_off[2], d.bw[2] * 8, dw, dh, d.hs, d.vs, x0 + k, y);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ycc_to_rgb((int)((yw >> (8 * k)) & 0xffu), cb[k] - 128, cr[k] - 128, r[k], g[k], b[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = g[k] = b[k] = (int)((yw >> (8 * k)) & 0xffu);
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(rgb + ((int64_t)img * H * W + i0) * 3);
+    o[0] = (uint32_t)r[0] | ((uint32_t)g[0] << 8) | ((uint32_t)b[0] << 16) | ((uint32_t)r[1] << 24);
+    o[1] = (uint32_t)g[1] | ((uint32_t)b[1] << 8) | ((uint32_t)r[2] << 16) | ((uint32_t)g[2] << 24);
+    o[2] = (uint32_t)b[2] | ((uint32_t)r[3] << 8) | ((uint32_t)g[3] << 16) | ((uint32_t)b[3] << 24);
 }
 
 // ---- host: header parsing (jdmarker.c) ----------------------------------------------------------------------------------------------------
@@ -768,18 +844,56 @@ void plan_chunks(Batch* b, int min_bytes, int chunk_mcus) {
 // kernel).  A round in which nothing changed costs a chunk two loads, so spare rounds are nearly free.
 constexpr int kChunkBytes = 256, kChunkMcus = 8, kSpecRounds = 6;
 
+// fn(first, last) over [0, n) on up to 8 host threads (parsing and staging a few thousand files is milliseconds of memory-bound work)
+template <typename F>
+void parallel_ranges(int n, int min_per_thread, F fn) {
+    int t = (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    t = std::min(t, std::max(1, n / std::max(1, min_per_thread)));
+    if (t <= 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    const int per = (n + t - 1) / t;
+    for (int k = 1; k < t; ++k) pool.emplace_back(fn, std::min(n, k * per), std::min(n, (k + 1) * per));
+    fn(0, std::min(n, per));
+    for (auto& th : pool) th.join();
+}
+
 int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, int H, Batch* b) {
     b->descs.resize(n);
     b->job_start.push_back(0);
+    // headers in parallel; a file whose Huffman tables equal those of the file before it (the usual case: one encoder) is only marked so,
+    // the others leave their set in ts_new for the sequential pass below (7.3 KB per set: not one per file)
+    std::vector<const char*> why_of(n, nullptr);
+    std::vector<int32_t> ts_ref(n, -1);                      // index into ts_new, or -1 = same tables as file i - 1
+    std::vector<std::vector<TableSet>> ts_new_of;
+    ts_new_of.reserve(16);
+    for (int k = 0; k < 16; ++k) ts_new_of.emplace_back();
+    std::atomic<int> next_slot{0};
+    std::vector<int32_t> slot_of(n, 0);
+    parallel_ranges(n, 128, [&](int i0, int i1) {
+        const int slot = next_slot.fetch_add(1);
+        std::vector<TableSet>& mine = ts_new_of[slot];
+        TableSet ts;
+        for (int i = i0; i < i1; ++i) {
+            why_of[i] = parse_jpeg(files[i], sizes[i], &b->descs[i], &ts);
+            slot_of[i] = slot;
+            if (why_of[i]) continue;
+            if (i > i0 && !mine.empty() && memcmp(&mine.back(), &ts, sizeof(ts)) == 0) { ts_ref[i] = -1; continue; }
+            mine.push_back(ts);
+            ts_ref[i] = (int32_t)mine.size() - 1;
+        }
+    });
     for (int i = 0; i < n; ++i) {
         JpegDesc& d = b->descs[i];
-        TableSet ts;
-        const char* why = parse_jpeg(files[i], sizes[i], &d, &ts);
-        if (why) { cv_set_error("cv_jpeg_decode: file %d: %s", i, why); return CV_ERR_ARG; }
-        d.tset = -1;
-        for (int k = (int)b->tsets.size() - 1; k >= 0 && k >= (int)b->tsets.size() - 8 && d.tset < 0; --k)      // look at the most recent sets
-            if (memcmp(&b->tsets[k], &ts, sizeof(ts)) == 0) d.tset = k;
-        if (d.tset < 0) { b->tsets.push_back(ts); d.tset = (int)b->tsets.size() - 1; }
+        if (why_of[i]) { cv_set_error("cv_jpeg_decode: file %d: %s", i, why_of[i]); return CV_ERR_ARG; }
+        if (ts_ref[i] < 0) {
+            d.tset = b->descs[i - 1].tset;                    // same tables as the file before (same parsing thread)
+        } else {
+            const TableSet& ts = ts_new_of[slot_of[i]][ts_ref[i]];
+            d.tset = -1;
+            for (int k = (int)b->tsets.size() - 1; k >= 0 && k >= (int)b->tsets.size() - 8 && d.tset < 0; --k)      // look at the most recent sets
+                if (memcmp(&b->tsets[k], &ts, sizeof(ts)) == 0) d.tset = k;
+            if (d.tset < 0) { b->tsets.push_back(ts); d.tset = (int)b->tsets.size() - 1; }
+        }
         if (d.width != W || d.height != H) { cv_set_error("cv_jpeg_decode: file %d is %dx%d, the batch is %dx%d", i, d.width, d.height, W, H); return CV_ERR_ARG; }
         b->file_base.push_back(b->bytes);
         split_intervals(files[i], d, i, b->bytes, &b->intervals);
@@ -800,11 +914,32 @@ int plan_batch(const uint8_t* const* files, const size_t* sizes, int n, int W, i
 
 // Staging memory of cv_jpeg_decode_batch, per device, grow-only (cudaMallocHost / cudaMalloc cost milliseconds: never per call).
 struct Scratch {
-    uint8_t *h_stage = nullptr, *d_stage = nullptr, *d_planes = nullptr, *d_chunks = nullptr;
+    // two staging slots: the host fills slot k & 1 for sub-batch k while the device still works on sub-batch k - 1 out of the other
+    uint8_t *h_stage2[2] = {nullptr, nullptr}, *d_stage2[2] = {nullptr, nullptr};
+    size_t stage_cap2[2] = {0, 0};
+    cudaEvent_t h2d_done[2] = {nullptr, nullptr};     // the copy out of h_stage2[i] has completed (the host may overwrite it)
+    bool h2d_pending[2] = {false, false};
+    uint8_t *h_stage = nullptr, *d_stage = nullptr;   // the slot in use (set by use_slot)
+    uint8_t *d_planes = nullptr, *d_chunks = nullptr;
     int16_t* d_coef = nullptr;
     size_t stage_cap = 0, coef_cap = 0, plane_cap = 0, chunk_cap = 0;
+    int slot = 0;
+    int use_slot(int i) {                             // waits until the host may write the slot's pinned block again
+        if (h_stage) { h_stage2[slot] = h_stage; d_stage2[slot] = d_stage; stage_cap2[slot] = stage_cap; }
+        slot = i;
+        if (!h2d_done[i]) CV_CUDA(cudaEventCreateWithFlags(&h2d_done[i], cudaEventDisableTiming));
+        if (h2d_pending[i]) { CV_CUDA(cudaEventSynchronize(h2d_done[i])); h2d_pending[i] = false; }
+        h_stage = h_stage2[i]; d_stage = d_stage2[i]; stage_cap = stage_cap2[i];
+        return CV_OK;
+    }
+    int copied(cudaStream_t s) {                      // call right after enqueuing the H2D copy of the slot in use
+        CV_CUDA(cudaEventRecord(h2d_done[slot], s));
+        h2d_pending[slot] = true;
+        return CV_OK;
+    }
     int reserve_chunks(size_t bytes) {
         if (bytes > chunk_cap) {
+            CV_CUDA(cudaDeviceSynchronize());
             if (d_chunks) cudaFree(d_chunks);
             d_chunks = nullptr; chunk_cap = 0;
             CV_CUDA(cudaMalloc(&d_chunks, bytes + bytes / 4));
@@ -813,6 +948,7 @@ struct Scratch {
         return CV_OK;
     }
     int reserve(size_t stage, size_t coef, size_t planes) {
+        if (stage > stage_cap || coef > coef_cap || planes > plane_cap) CV_CUDA(cudaDeviceSynchronize());     // nothing in flight uses what is freed below
         if (stage > stage_cap) {
             if (h_stage) cudaFreeHost(h_stage);
             if (d_stage) cudaFree(d_stage);
@@ -963,17 +1099,11 @@ int cv_jpeg_decode_coefficients_host_chunked(const uint8_t* file_host, size_t si
     return CV_OK;
 }
 
-// n baseline JPEG files of ONE size (host pointers) -> rgb (DEVICE, uint8 (n, H, W, 3)), bit-exact with PIL.Image.open(f).convert("RGB").
-// entropy_on_host != 0 decodes the Huffman streams on the host and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
-// compressed bytes; results are identical.  Synchronises `stream` before returning.  Staging memory (pinned host + device) is kept
-// per device for the life of the process and only grows: a steady stream of equal batches allocates once.
-int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host, void* stream) {
-    CV_ARG(n >= 0, "negative batch");
-    if (n == 0) return CV_OK;
-    CV_ARG(files_host && sizes && rgb, "null argument");
-    CV_ARG(W > 0 && H > 0 && W <= 16384 && H <= 16384, "bad image size");
-    CV_ARG(n <= 65535, "at most 65535 files per call");
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
+}  // extern "C"
+
+namespace {
+int decode_sub(Scratch& sc, int slot, const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host,
+               cudaStream_t s) {
 #ifdef CV_EXPERIMENTS                 // CV_JPEG_TRACE=1: wall-clock split of one call (stream synchronised after every stage)
     const bool trace = getenv("CV_JPEG_TRACE") != nullptr;
     auto t_last = std::chrono::steady_clock::now();
@@ -999,10 +1129,8 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     const bool chunked = !entropy_on_host && chunk_bytes >= 16;
     if (chunked) plan_chunks(&b, chunk_bytes, chunk_mcus);
     mark("parse headers + plan");
-    int dev = 0;
-    CV_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_scratch_mutex);
-    Scratch& sc = g_scratch[dev];
+    rc = sc.use_slot(slot);
+    if (rc) return rc;
     const size_t desc_b = b.descs.size() * sizeof(JpegDesc), ts_b = b.tsets.size() * sizeof(TableSet), iv_b = b.intervals.size() * sizeof(Interval),
                  job_b = b.jobs.size() * sizeof(IdctJob), js_b = b.job_start.size() * sizeof(int64_t);
     // one pinned staging block: [descs | table sets | intervals | jobs | job starts | payload], mirrored by one device block
@@ -1028,6 +1156,7 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     const IdctJob* d_jobs = reinterpret_cast<const IdctJob*>(sc.d_stage + o_job);
     const int64_t* d_jstart = reinterpret_cast<const int64_t*>(sc.d_stage + o_js);
     const int16_t* d_coef = sc.d_coef;
+    int16_t* d_dcbuf = nullptr;                              // chunked device decoding: DC values live in a compact array
     if (entropy_on_host) {
         int16_t* h_coef = reinterpret_cast<int16_t*>(sc.h_stage + o_pay);
         for (const Interval& v : b.intervals) {
@@ -1037,11 +1166,17 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
         }
         mark("entropy decode (host)");
         CV_CUDA(cudaMemcpyAsync(sc.d_stage, sc.h_stage, off, cudaMemcpyHostToDevice, s));       // tables + coefficients in one copy
+        rc = sc.copied(s);
+        if (rc) return rc;
         d_coef = reinterpret_cast<const int16_t*>(sc.d_stage + o_pay);
         mark("H2D tables + coefficients");
     } else {
-        for (int i = 0; i < n; ++i) memcpy(sc.h_stage + o_pay + b.file_base[i], files_host[i], sizes[i]);
+        parallel_ranges(n, 256, [&](int i0, int i1) {
+            for (int i = i0; i < i1; ++i) memcpy(sc.h_stage + o_pay + b.file_base[i], files_host[i], sizes[i]);
+        });
         CV_CUDA(cudaMemcpyAsync(sc.d_stage, sc.h_stage, off, cudaMemcpyHostToDevice, s));       // tables + compressed bytes in one copy
+        rc = sc.copied(s);
+        if (rc) return rc;
         mark("stage + H2D compressed bytes");
         const int n_iv = (int)b.intervals.size(), n_sets = (int)b.tsets.size();
         const int smem_sets = n_sets <= 6 ? n_sets : 0;          // up to 44 KB of shared memory for the table sets
@@ -1058,7 +1193,8 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
             // takes the intervals whose chain did not close (none, normally: it exits at once)
             const int n_ch = (int)b.chunk_iv.size();
             const size_t per_chunk = 2 * sizeof(uint64_t) + 2 * sizeof(int32_t);
-            rc = sc.reserve_chunks((size_t)n_ch * per_chunk + (size_t)n_iv * sizeof(int32_t) + 64);
+            const size_t n_blocks = (size_t)(b.coef_elems / 64);
+            rc = sc.reserve_chunks((size_t)n_ch * per_chunk + (size_t)n_iv * sizeof(int32_t) + n_blocks * sizeof(int16_t) + 64);
             if (rc) return rc;
             ChunkArrays a;
             a.used_entry = reinterpret_cast<uint64_t*>(sc.d_chunks);
@@ -1066,6 +1202,9 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
             a.count = reinterpret_cast<int32_t*>(a.exit_state + n_ch);
             a.blk0 = a.count + n_ch;
             a.failed = a.blk0 + n_ch;
+            a.dcbuf = reinterpret_cast<int16_t*>(a.failed + n_iv);
+            d_dcbuf = a.dcbuf;
+            CV_CUDA(cudaMemsetAsync(a.dcbuf, 0, n_blocks * sizeof(int16_t), s));
             const IvChunks* d_ivc = reinterpret_cast<const IvChunks*>(sc.d_stage + o_ivc);
             const int32_t* d_civ = reinterpret_cast<const int32_t*>(sc.d_stage + o_civ);
             CV_CUDA(cudaMemsetAsync(sc.d_coef, 0, (size_t)b.coef_elems * sizeof(int16_t), s));
@@ -1082,13 +1221,13 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
             jpeg_write_kernel<<<grid, kChunkThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, d_ivc, d_civ, n_ch, d_bytes, a, sc.d_coef);
             CV_CHECK_LAUNCH();
             mark("  chunked: writing pass");
-            jpeg_dc_scan_kernel<<<(n_iv * 3 * 32 + 127) / 128, 128, 0, s>>>(d_desc, d_iv, n_iv, a.failed, sc.d_coef);
+            jpeg_dc_scan_kernel<<<(n_iv * 3 * 32 + 127) / 128, 128, 0, s>>>(d_desc, d_iv, n_iv, a.failed, a.dcbuf);
             CV_CHECK_LAUNCH();
             mark("  chunked: DC prefix sums");
             only_failed = a.failed;
         }
         jpeg_huffman_kernel<<<(n_iv + kHuffThreads - 1) / kHuffThreads, kHuffThreads, smem, s>>>(d_desc, d_ts, n_sets, smem_sets, d_iv, n_iv, d_bytes,
-                                                                                              sc.d_coef, only_failed);
+                                                                                              sc.d_coef, only_failed, d_dcbuf);
         CV_CHECK_LAUNCH();
 #ifdef CV_EXPERIMENTS
         if (trace && chunked) {
@@ -1103,12 +1242,49 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
         mark("entropy decode (device)");
     }
     const int64_t total_blocks = b.job_start.back();
-    jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, s>>>(d_desc, d_jstart, d_jobs, (int)b.jobs.size(), d_coef, sc.d_planes);
+    jpeg_idct_kernel<<<(unsigned)((total_blocks + 31) / 32), 256, 0, s>>>(d_desc, d_jstart, d_jobs, (int)b.jobs.size(), d_coef, d_dcbuf, sc.d_planes);
     CV_CHECK_LAUNCH();
-    jpeg_color_kernel<<<dim3((unsigned)((W * H + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, sc.d_planes, W, H, rgb);
+    mark("idct");
+    if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 3) == 0)
+        jpeg_color4_kernel<<<dim3((unsigned)((W * H / 4 + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, sc.d_planes, W, H, rgb);
+    else
+        jpeg_color_kernel<<<dim3((unsigned)((W * H + 255) / 256), (unsigned)n), 256, 0, s>>>(d_desc, sc.d_planes, W, H, rgb);
     CV_CHECK_LAUNCH();
-    CV_CUDA(cudaStreamSynchronize(s));        // the staging block is reused by the next call
-    mark("idct + colour");
+    mark("upsampling + colour");
+    return CV_OK;
+}
+}  // namespace
+
+extern "C" {
+// n baseline JPEG files of ONE size (host pointers) -> rgb (DEVICE, uint8 (n, H, W, 3)), bit-exact with PIL.Image.open(f).convert("RGB").
+// entropy_on_host != 0 decodes the Huffman streams on the host and ships coefficients (3 bytes per pixel at 4:2:0) instead of the
+// compressed bytes; results are identical.  Synchronises `stream` before returning.  Staging memory (pinned host + device) is kept
+// per device for the life of the process and only grows: a steady stream of equal batches allocates once.
+int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host, void* stream) {
+    CV_ARG(n >= 0, "negative batch");
+    if (n == 0) return CV_OK;
+    CV_ARG(files_host && sizes && rgb, "null argument");
+    CV_ARG(W > 0 && H > 0 && W <= 16384 && H <= 16384, "bad image size");
+    CV_ARG(n <= 65535, "at most 65535 files per call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    CV_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mutex);
+    Scratch& sc = g_scratch[dev];
+    // Sub-batches through two staging slots: the host parses and stages sub-batch k + 1 while the device decodes sub-batch k (the
+    // coefficient / plane / chunk-state buffers are shared: the kernels of all sub-batches run in stream order).
+    int sub = n;
+    if (n > 4096) sub = 4096;                                // bounds the scratch memory (0.3 MB per 256x256 file) and overlaps host and device work
+#ifdef CV_EXPERIMENTS
+    if (const char* e = getenv("CV_JPEG_SUB")) sub = std::max(1, atoi(e));
+#endif
+    int rc = CV_OK;
+    for (int k = 0, i0 = 0; i0 < n && rc == CV_OK; ++k, i0 += sub)
+        rc = decode_sub(sc, k & 1, files_host + i0, sizes + i0, std::min(sub, n - i0), W, H, rgb + (size_t)i0 * W * H * 3, entropy_on_host, s);
+    const cudaError_t e = cudaStreamSynchronize(s);        // the pixels are in `rgb`; the staging slots are free for the next call
+    sc.h2d_pending[0] = sc.h2d_pending[1] = false;
+    if (rc) return rc;
+    CV_CUDA(e);
     return CV_OK;
 }
 
