@@ -101,34 +101,44 @@ struct BitReader {
     inline uint32_t next_raw() { return *p++; }
     inline uint32_t peek_raw() { return *p; }
 #endif
-    __host__ __device__ inline void fill() {
-#ifdef __CUDA_ARCH__
-        // device fast path: four stream bytes at once when none of them is 0xFF (no stuffing, no marker) and the accumulator has room
-        if (n <= 32 && !hit_marker && word_left >= 4 && p + 4 <= end) {
-            const uint32_t x = (uint32_t)word, y = ~x;
-            if (((y - 0x01010101u) & x & 0x80808080u) == 0) {             // no byte of y is zero <=> no byte of x is 0xFF
-                acc = (acc << 32) | __byte_perm(x, 0, 0x0123);
-                n += 32;
-                word >>= 32; word_left -= 4; p += 4;
-                return;
+    __host__ __device__ inline void step_byte() {            // one stream byte into the accumulator, the careful way (stuffing, markers, the end)
+        uint32_t b = 0;
+        if (!hit_marker && p < end) {
+            b = next_raw();
+            if (b == 0xFF) {
+                if (p < end && peek_raw() == 0) next_raw();              // stuffed zero
+                else { hit_marker = true; b = 0; fake += 8; }             // a marker (or the end): zeros from here on, like jdhuff.c
             }
+        } else {
+            fake += 8;
         }
-#endif
-        while (n <= 56) {
-            uint32_t b = 0;
-            if (!hit_marker && p < end) {
-                b = next_raw();
-                if (b == 0xFF) {
-                    if (p < end && peek_raw() == 0) next_raw();          // stuffed zero
-                    else { hit_marker = true; b = 0; fake += 8; }         // a marker (or the end): zeros from here on, like jdhuff.c
+        acc = (acc << 8) | b;
+        n += 8;
+    }
+#ifdef __CUDA_ARCH__
+    // device: until more than 32 bits are unread (a symbol takes at most 16 + 16; callers refill below 32 / 16).  Four stream bytes at
+    // once whenever none of them is 0xFF (no stuffing, no marker); single careful bytes otherwise.  (The byte-at-a-time loop of the
+    // host version was 55 % of the decoder's instructions at 3.4 active lanes: ncu, profiles/r02_jpeg_*.)
+    __device__ inline void fill() {
+        while (n <= 32) {
+            if (!hit_marker && p + 4 <= end) {
+                if (word_left == 0) { word = *reinterpret_cast<const uint64_t*>(p); word_left = 8; }
+                const uint32_t x = (uint32_t)word, y = ~x;
+                if (word_left >= 4 && ((y - 0x01010101u) & x & 0x80808080u) == 0) {      // no byte of y is zero <=> no byte of x is 0xFF
+                    acc = (acc << 32) | __byte_perm(x, 0, 0x0123);
+                    n += 32;
+                    word >>= 32; word_left -= 4; p += 4;
+                    return;
                 }
-            } else {
-                fake += 8;
             }
-            acc = (acc << 8) | b;
-            n += 8;
+            step_byte();
         }
     }
+#else
+    inline void fill() {
+        while (n <= 56) step_byte();
+    }
+#endif
     __host__ __device__ inline uint32_t peek(int k) { return (uint32_t)(acc >> (n - k)) & ((1u << k) - 1u); }
     __host__ __device__ inline void skip(int k) { n -= k; }
 };
@@ -1105,7 +1115,7 @@ namespace {
 int decode_sub(Scratch& sc, int slot, const uint8_t* const* files_host, const size_t* sizes, int n, int W, int H, uint8_t* rgb, int entropy_on_host,
                cudaStream_t s) {
 #ifdef CV_EXPERIMENTS                 // CV_JPEG_TRACE=1: wall-clock split of one call (stream synchronised after every stage)
-    const bool trace = getenv("CV_JPEG_TRACE") != nullptr;
+    const bool trace = getenv("CV_JPEG_TRACE") != nullptr && atoi(getenv("CV_JPEG_TRACE")) == 1;
     auto t_last = std::chrono::steady_clock::now();
     auto mark = [&](const char* what) {
         if (!trace) return;
@@ -1279,9 +1289,22 @@ int cv_jpeg_decode_batch(const uint8_t* const* files_host, const size_t* sizes, 
     if (const char* e = getenv("CV_JPEG_SUB")) sub = std::max(1, atoi(e));
 #endif
     int rc = CV_OK;
-    for (int k = 0, i0 = 0; i0 < n && rc == CV_OK; ++k, i0 += sub)
+#ifdef CV_EXPERIMENTS                 // CV_JPEG_TRACE=2: host-side timeline of the sub-batches (no extra synchronisation)
+    const char* tr = getenv("CV_JPEG_TRACE");
+    const bool timeline = tr && atoi(tr) == 2;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+#endif
+    for (int k = 0, i0 = 0; i0 < n && rc == CV_OK; ++k, i0 += sub) {
         rc = decode_sub(sc, k & 1, files_host + i0, sizes + i0, std::min(sub, n - i0), W, H, rgb + (size_t)i0 * W * H * 3, entropy_on_host, s);
+#ifdef CV_EXPERIMENTS
+        if (timeline) fprintf(stderr, "  jpeg sub-batch %d enqueued at %.3f ms\n", k, since());
+#endif
+    }
     const cudaError_t e = cudaStreamSynchronize(s);        // the pixels are in `rgb`; the staging slots are free for the next call
+#ifdef CV_EXPERIMENTS
+    if (timeline) fprintf(stderr, "  jpeg all done at %.3f ms\n", since());
+#endif
     sc.h2d_pending[0] = sc.h2d_pending[1] = false;
     if (rc) return rc;
     CV_CUDA(e);
