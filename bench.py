@@ -256,17 +256,30 @@ def jpeg_leg(model, dev, peaks, n=4096, size=256):
     for _ in range(reps):
         preprocess.decode_jpegs(batch, dev, out=out)           # blocking: decode alone
     dt_dec = (time.perf_counter() - t0) / reps
+    # steady state: four chunks through preprocess.predict_jpeg_files (a helper thread decodes chunk k + 1 while the forward of chunk k runs)
+    many = batch * 4
+    preprocess.predict_jpeg_files(model, many[:2 * n], size, chunk=n, device_records=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fen_p, _ = preprocess.predict_jpeg_files(model, many, size, chunk=n, device_records=True)
+    torch.cuda.synchronize()
+    dt_pipe = (time.perf_counter() - t0) / 4
+    same = bool(torch.equal(fen_p[:n], fen))
     t0 = time.perf_counter()
     for f in files[:32]:
         np.asarray(Image.open(io.BytesIO(f)).convert("RGB"))
     pil = 32 / (time.perf_counter() - t0)
     per_board = float(np.mean([len(f) for f in files]))
-    return {"workload": f"{n} JPEG files {size}x{size} (quality 90, 4:2:0) in host memory -> device decode -> FEN records on the device",
-            "value": n / dt, "unit": "boards/s", "ms": dt * 1e3, "decode_only_files_per_s": n / dt_dec, "decode_only_ms": dt_dec * 1e3,
+    return {"workload": f"JPEG files {size}x{size} (quality 90, 4:2:0) in host memory -> device decode -> FEN records on the device, {n} files per chunk",
+            "value": n / dt, "unit": "boards/s", "ms": dt * 1e3,
+            "pipelined": {"value": n / dt_pipe, "unit": "boards/s", "ms_per_chunk": dt_pipe * 1e3, "same_records": same,
+                          "what": "steady state of preprocess.predict_jpeg_files over 4 chunks: a helper thread parses / stages / decodes chunk k + 1 "
+                                  "while the forward of chunk k runs (the device is the bound either way: ~6 ms of decode + 12.4 ms of path per chunk)"},
+            "decode_only_files_per_s": n / dt_dec, "decode_only_ms": dt_dec * 1e3,
             "pcie_bytes_per_board": per_board, "raw_board_bytes": size * size * 3,
             "bit_exact_vs_pillow": exact,
-            "note": "wall clock around the blocking decode call followed by the path (not overlapped); one device thread walks each file's Huffman "
-                    "stream, so the entropy stage costs one file's latency (~10 ms) per call whatever the batch size",
+            "note": "value: wall clock around one blocking decode call followed by the path; the entropy stage decodes ~300-byte chunks of every "
+                    "file in parallel (speculative chunk decoding with a closing chain of decoder states, DESIGN section 7)",
             "cpu_baseline": {"value": pil, "unit": "boards/s", "cores": 1, "kind": "reference",
                              "sample": f"32 files, PIL.Image.open(...).convert('RGB') (Pillow {__import__('PIL').__version__}), one thread, decode only"}}
 

@@ -99,3 +99,29 @@ def test_chunked_device_entropy_decoder_on_hard_streams():
     assert np.array_equal(again, got)
     host = preprocess.decode_jpegs(files, "cuda", entropy_on_host=True).cpu().numpy()
     assert np.array_equal(host, got)
+
+
+def test_pipelined_jpeg_prediction_equals_the_plain_path(gpu_model, tmp_path):
+    """`predict_jpeg_files` (decode of chunk k + 1 on a helper thread under the forward of chunk k, ragged last chunk, a resize in between,
+    flipped boards) and `predict_images` on the same files as paths: the strings of decode -> resize -> predict_fen done plainly."""
+    Image = pytest.importorskip("PIL.Image")
+    from chess_vision_b200 import synthetic
+    u8 = synthetic.synth_boards(0, 37, 256, 1, synthetic.DIST_STRUCTURED)
+    files, paths = [], []
+    for i in range(37):
+        b = io.BytesIO()
+        Image.fromarray(u8[i]).resize((320, 320), Image.BILINEAR).save(b, "JPEG", quality=90, subsampling=2)
+        files.append(b.getvalue())
+        p = tmp_path / f"b{i}.jpg"
+        p.write_bytes(files[-1])
+        paths.append(str(p))
+    flipped = [i % 3 == 0 for i in range(37)]
+    boards = preprocess.resize_boards(preprocess.decode_jpegs(files, "cuda"), 256)
+    want = gpu_model.predict_fen(boards, flipped=torch.tensor(flipped, dtype=torch.uint8))
+    assert preprocess.predict_jpeg_files(gpu_model, files, 256, flipped=flipped, chunk=16) == want
+    assert preprocess.predict_jpeg_files(gpu_model, files, 256, flipped=flipped) == want
+    assert preprocess.predict_images(gpu_model, paths, 256, flipped=flipped) == want
+    fen, ln = preprocess.predict_jpeg_files(gpu_model, files[:5], 256, device_records=True)
+    assert fen.is_cuda and fen.shape == (5, 80) and gpu_model.decode_fen_records(fen, ln) == gpu_model.predict_fen(boards[:5])
+    with pytest.raises(_native.NativeError):
+        preprocess.predict_jpeg_files(gpu_model, files[:20] + [b"\x89PNG not a jpeg"] + files[20:], 256, chunk=8)
