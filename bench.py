@@ -551,6 +551,23 @@ def run_native(args):
         cpu[f"fen_agreement_{prec}_vs_cpu"] = float(same_t.mean())
         cpu[f"fen_agreement_{prec}_vs_cpu_margin_filtered"] = {"value": float(same_t[clear].mean()) if clear.any() else None,
                                                                "boards": int(clear.sum()), "of": sample}
+        # the same question per DECISION (sample x (64 argmax + turn + 4 castling signs)): of the decisions the fp32 reference takes with a
+        # margin above twice the observed logit error, how many does the timed mode take differently (0 expected), and how thin were
+        # the reference's margins where the two disagree (relative to the largest logit: decisions the reference itself does not hold
+        # against fp32 summation-order noise times a few hundred)
+        g_sq = got["squares"].cpu().view(sample, 64, 13).numpy()
+        m_sq = (srt[..., -1] - srt[..., -2]).reshape(-1)
+        d_sq = (g_sq.argmax(-1) != sq.argmax(-1)).reshape(-1)
+        r_tc = np.concatenate([ref["turn"].numpy().reshape(-1), ref["castling"].numpy().reshape(-1)])
+        g_tc = np.concatenate([got["turn"].cpu().numpy().reshape(-1), got["castling"].cpu().numpy().reshape(-1)])
+        d_tc = (r_tc > 0) != (g_tc > 0)
+        clear_d = np.concatenate([m_sq > 2 * e_sq, np.abs(r_tc) > 2 * e_tc])
+        diff_d = np.concatenate([d_sq, d_tc])
+        thin = np.concatenate([m_sq[d_sq] / np.abs(sq).max(), np.abs(r_tc[d_tc]) / max(np.abs(r_tc).max(), 1e-30)])
+        cpu[f"decision_agreement_{prec}_vs_cpu"] = {
+            "decisions": int(diff_d.size), "differ": int(diff_d.sum()),
+            "clear_decisions": int(clear_d.sum()), "clear_differ": int((diff_d & clear_d).sum()),
+            "max_rel_margin_where_differ": float(thin.max()) if thin.size else 0.0}
         cpu[f"square_agreement_{prec}_vs_cpu"] = float((got["squares"].cpu().view(sample, 64, 13).argmax(-1) == ref["squares"].view(sample, 64, 13).argmax(-1)).float().mean())
         # the EXACT modes timed beside it: what 100 % FEN agreement costs.  "fp32_split" = fp32-grade results on the tensor cores (split fp16
         # operands, three MMAs per k-step, layer-granular kernels); "fp32" = the CUDA-core kernels.  Both on 1024 device-resident boards; logit
