@@ -24,7 +24,7 @@ namespace {
 
 constexpr int NBUF_SMALL = 4;
 constexpr int64_t EL_CROPS = 64 * 64 * 3, EL_STEM = 32 * 32 * 32, EL_SMALL = 6144;
-constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512, DEFAULT_WAVE_SPLIT = 512;   // fused stages: persistent kernels want many tiles per SM
+constexpr int DEFAULT_WAVE_FP32 = 64, DEFAULT_WAVE_BF16 = 128, DEFAULT_WAVE_FUSED = 512, DEFAULT_WAVE_SPLIT = 1024;   // fused stages: persistent kernels want many tiles per SM
 // all four fused stages: only the 8 / 4 / 1.5 KB per crop hand-offs live in the workspace, and every kernel boundary costs ~13 us of
 // drained SMs, so a wave is a whole chunk (measured per 4096 boards: 13.81 ms at 512, 13.64 at 1024, 13.55 at 2048, 13.45 at 4096)
 constexpr int DEFAULT_WAVE_ALL_FUSED = 4096;

@@ -16,6 +16,7 @@
 //   pool_heads_x2_kernel  2x2 mean, type / color heads, type + color combine (square.py:87-104, common.py:24)
 // fp16 overflows above 65504: every store of a hi value checks for non-finite lanes and raises the handle's overflow flag
 // (cv_square_fp16_status); the caller then re-runs with CV_PRECISION_FP32 (the CUDA-core kernels have fp32 range).
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -138,19 +139,32 @@ __device__ __forceinline__ void mma_role(const X2Params& p, const Pipe& q, uint3
     }
 }
 
-// ---- epilogue: 4 warps, warp w owns TMEM lanes [32w, 32w+32) = tile rows -------------------------------------------------------------
-__device__ __forceinline__ void epilogue_role(const X2Params& p, const Pipe& q, uint32_t tmem_base, int warp, int lane) {
+// ---- epilogue: groups of 4 warps, warp w of a group owns TMEM lanes [32w, 32w+32) = tile rows.  With two groups (pointwise kernel) group g
+//      drains accumulator buffer g, i.e. every other work item: an epilogue is a chain of TMEM loads, global skip loads and stores whose
+//      latency one group of four warps cannot hide (pw_proj layers sat at 40 % of the HBM peak), two groups work on two tiles at a time.
+//      The skip tile of a work item (N <= 64: the pw_proj layers) is fetched into registers BEFORE the accumulator wait, under the MMAs.
+template <bool PW>   // PW: pointwise kernel (two groups, skip prefetch); the dense kernels have one group and no residual
+__device__ __forceinline__ void epilogue_role(const X2Params& p, const Pipe& q, uint32_t tmem_base, int warp, int lane, int group, int n_groups) {
     const int row = warp * 32 + lane, n8 = p.N >> 3;
-    int acc = 0;
-    uint32_t acc_phase = 0, bad = 0;
+    uint32_t bad = 0, it = 0;
+    const bool pre = PW && p.skip != nullptr && p.n_split == 1 && n8 <= 8;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         uint4* yt = reinterpret_cast<uint4*>(p.y) + ((size_t)tile * 2 * n8) * TILE_M + row;
-        const uint4* st = p.skip ? reinterpret_cast<const uint4*>(p.skip) + ((size_t)tile * 2 * n8) * TILE_M + row : nullptr;
-        for (int nt = 0; nt < p.n_split; ++nt) {
+        const uint4* st = PW && p.skip ? reinterpret_cast<const uint4*>(p.skip) + ((size_t)tile * 2 * n8) * TILE_M + row : nullptr;
+        for (int nt = 0; nt < p.n_split; ++nt, ++it) {
+            const int acc = (int)(it & 1u);
+            if (n_groups == 2 && acc != group) continue;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            uint4 skh[8], skl[8];
+            if (PW && pre) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < n8) { skh[c] = __ldg(st + (size_t)c * TILE_M); skl[c] = __ldg(st + (size_t)(n8 + c) * TILE_M); }
+            }
             mbar_wait(q.tfull + acc, acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+            auto block16 = [&](int c0, const uint4* sh, const uint4* sl) {       // 16 accumulator columns from c0; sh / sl: prefetched skip chunks or null
                 uint32_t r0[16], r1[16];
                 tmem_ld16(taddr + c0, r0);
                 tmem_ld16(taddr + p.groups * p.n_tile + c0, r1);
@@ -173,7 +187,8 @@ __device__ __forceinline__ void epilogue_role(const X2Params& p, const Pipe& q, 
                     }
                     if (st) {
                         float sk[8];
-                        join8(__ldg(st + (size_t)chunk * TILE_M), __ldg(st + (size_t)(n8 + chunk) * TILE_M), sk);
+                        if (sh) join8(sh[j], sl[j], sk);
+                        else join8(__ldg(st + (size_t)chunk * TILE_M), __ldg(st + (size_t)(n8 + chunk) * TILE_M), sk);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] += sk[i];
                     }
@@ -182,11 +197,17 @@ __device__ __forceinline__ void epilogue_role(const X2Params& p, const Pipe& q, 
                     yt[(size_t)chunk * TILE_M] = hi;
                     yt[(size_t)(n8 + chunk) * TILE_M] = lo;
                 }
+            };
+            if (PW && pre) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (b * 16 < p.n_tile) block16(b * 16, skh + 2 * b, skl + 2 * b);
+            } else {
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16) block16(c0, nullptr, nullptr);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(q.tempty + acc);
-            if (p.num_acc == 2) { acc ^= 1; if (acc == 0) acc_phase ^= 1u; } else { acc_phase ^= 1u; }
         }
     }
     if (bad) atomicOr(p.ovf, 1);
@@ -207,8 +228,8 @@ __device__ __forceinline__ uint32_t gemm_setup(const X2Params& p, const Pipe& q,
     return *q.tmem_slot;
 }
 
-// 6 warps: 0-3 epilogue, 4 TMA producer, 5 MMA issuer (+ TMEM owner)
-__global__ void __launch_bounds__(192, 1) pointwise_x2_kernel(const __grid_constant__ X2Params p) {
+// 10 warps: 0-3 epilogue group 0, 4 TMA producer, 5 MMA issuer (+ TMEM owner), 6-9 epilogue group 1
+__global__ void __launch_bounds__(320, 1) pointwise_x2_kernel(const __grid_constant__ X2Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const Pipe q = carve(smem, p);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -230,7 +251,7 @@ __global__ void __launch_bounds__(192, 1) pointwise_x2_kernel(const __grid_const
     } else if (warp == 5) {
         mma_role(p, q, tmem_base);
     } else {
-        epilogue_role(p, q, tmem_base, warp, lane);
+        epilogue_role<true>(p, q, tmem_base, warp & 3 /* TMEM lane quadrant = warp % 4: warps 6-9 own quadrants 2, 3, 0, 1 */, lane, warp >= 6 ? 1 : 0, 2);
     }
     tc_fence_before();
     __syncthreads();
@@ -397,7 +418,7 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
     } else if (warp == MMA_WARP) {
         mma_role_dense(p, q, tmem_base);
     } else {
-        epilogue_role(p, q, tmem_base, warp, lane);
+        epilogue_role<false>(p, q, tmem_base, warp, lane, 0, 1);
     }
     tc_fence_before();
     __syncthreads();
@@ -467,6 +488,93 @@ depthwise_x2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w,
         bad |= split8(acc[ox], hi, lo);
         dst[ox] = hi;
         dst[(size_t)c8n * TILE_M + ox] = lo;
+    }
+    if (bad) atomicOr(ovf, 1);
+}
+
+// Depthwise, second generation: the input tile goes through shared memory.  The row-per-thread kernel above reads its rows straight
+// from global memory -- 128-byte pieces at a 128-byte lane stride, 150-180 registers, 8 warps per SM: latency-bound at 20-45 % of the
+// HBM peak.  Here a CTA owns one INPUT tile (128 rows = 128 / HIN^2 crops) and a group of `cg` channel chunks: all threads copy the
+// 2 x cg chunk planes (hi, lo) with 16-byte cp.async (coalesced: consecutive threads, consecutive rows) into an image whose rows are
+// padded by one 16-byte unit (row pitch HIN + 1 units, plane pitch odd: the lanes of a warp -- consecutive image rows -- spread over all
+// bank groups, every LDS.128 at its 4-wavefront minimum), then thread = (chunk, crop, output row) runs the same fp32 arithmetic in the
+// same order (bias, taps in (ky, kx) order) from shared memory.  Several CTAs per SM overlap each other's copy and compute phases.
+template <int K, int S, int HIN>
+__global__ void __launch_bounds__(128)
+depthwise_x2_smem_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ y,
+                         int C, int cg, int relu, int* __restrict__ ovf) {
+    constexpr int HOUT = HIN / S, PAD = ((S - 1) + (K - 1)) / 2, ROWS = TILE_M / HIN, RP = HIN + 1, PU = (ROWS * RP) | 1;
+    constexpr int TPC = ROWS / S;                          // tasks per chunk: (crop, output row) pairs of the tile
+    extern __shared__ __align__(16) uint8_t dsm[];
+    uint4* img = reinterpret_cast<uint4*>(dsm);            // [hi | lo][cg][PU] 16-byte units
+    const int c8n = C >> 3, n_grp = c8n / cg;
+    const int tile = blockIdx.x / n_grp, c0 = (blockIdx.x - tile * n_grp) * cg;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(x) + (size_t)tile * 2 * c8n * TILE_M;
+        const uint32_t base = smem_u32(img);
+        for (int i = threadIdx.x; i < 2 * cg * TILE_M; i += blockDim.x) {
+            const int m = i & (TILE_M - 1), pc = i >> 7, part = pc >= cg ? 1 : 0, cl = pc - part * cg;
+            const uint4* g = src + ((size_t)(part * c8n + c0 + cl)) * TILE_M + m;
+            const uint32_t d = base + (uint32_t)((pc * PU + (m / HIN) * RP + (m % HIN)) * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t bad = 0;
+    for (int task = threadIdx.x; task < cg * TPC; task += blockDim.x) {
+        const int cl = task / TPC, rt = task - cl * TPC, crop_l = rt / HOUT, oy = rt - crop_l * HOUT, c = c0 + cl;
+        float acc[HOUT][8];
+        {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8) + 1);
+#pragma unroll
+            for (int ox = 0; ox < HOUT; ++ox) {
+                acc[ox][0] = b0.x; acc[ox][1] = b0.y; acc[ox][2] = b0.z; acc[ox][3] = b0.w;
+                acc[ox][4] = b1.x; acc[ox][5] = b1.y; acc[ox][6] = b1.z; acc[ox][7] = b1.w;
+            }
+        }
+        const uint4* hi = img + cl * PU + crop_l * HIN * RP;
+        const uint4* lo = hi + cg * PU;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int iy = oy * S - PAD + ky;
+            if (iy < 0 || iy >= HIN) continue;
+            float wk[K][8];                                  // the K taps of this filter row
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c * 8);
+                const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                wk[kx][0] = w0.x; wk[kx][1] = w0.y; wk[kx][2] = w0.z; wk[kx][3] = w0.w;
+                wk[kx][4] = w1.x; wk[kx][5] = w1.y; wk[kx][6] = w1.z; wk[kx][7] = w1.w;
+            }
+            // input pixels left to right: pixel ix feeds output ox through tap kx = ix - ox S + PAD, so every accumulator still
+            // receives its taps in increasing kx order
+#pragma unroll
+            for (int ix = 0; ix < HIN; ++ix) {
+                float px[8];
+                join8(hi[iy * RP + ix], lo[iy * RP + ix], px);
+#pragma unroll
+                for (int ox = 0; ox < HOUT; ++ox) {
+                    const int kx = ix - ox * S + PAD;
+                    if (kx < 0 || kx >= K) continue;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[ox][e] = fmaf(px[e], wk[kx][e], acc[ox][e]);
+                }
+            }
+        }
+        const int64_t m_out = ((int64_t)tile * (TILE_M / (HIN * HIN)) + crop_l) * (HOUT * HOUT) + oy * HOUT;
+        uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(m_out >> 7) * 2 * c8n + c) * TILE_M + (m_out & 127);
+#pragma unroll
+        for (int ox = 0; ox < HOUT; ++ox) {
+            if (relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[ox][e] = fmaxf(acc[ox][e], 0.f);
+            }
+            uint4 h4, l4;
+            bad |= split8(acc[ox], h4, l4);
+            dst[ox] = h4;
+            dst[(size_t)c8n * TILE_M + ox] = l4;
+        }
     }
     if (bad) atomicOr(ovf, 1);
 }
@@ -641,7 +749,7 @@ int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_
     const Plan sp = plan_smem(p.K, p.N, p.stages);
     CV_CUDA(cudaFuncSetAttribute(pointwise_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
-    pointwise_x2_kernel<<<grid, 192, sp.total, s>>>(p);
+    pointwise_x2_kernel<<<grid, 320, sp.total, s>>>(p);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }
@@ -681,6 +789,31 @@ int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* 
     const int64_t total = n_crops * L.hout * L.hout * (L.cout / 8);
     if (total == 0) return CV_OK;
     if ((n_crops * L.hout * L.hout) % TILE_M != 0 || L.hin != L.hout * L.stride) { cv_set_error("depthwise_x2: crop count / shape not tiled"); return CV_ERR_ARG; }
+    const int64_t in_tiles = n_crops * L.hin * L.hin / TILE_M;
+#ifdef CV_EXPERIMENTS
+    static const bool old_kernel = getenv("CV_X2_DW_ROWS") != nullptr;     // the first-generation kernel (experiment builds: A/B timing)
+#else
+    const bool old_kernel = false;
+#endif
+    if (!old_kernel && in_tiles * (L.cout / 8) < (int64_t)1 << 31) {
+        // chunk group: the largest divisor of C / 8 that keeps a CTA at <= 128 tasks (tasks per chunk = 128 / HIN / stride)
+        const int c8n = L.cout / 8, tpc = TILE_M / L.hin / L.stride;
+        int cg = 1;
+        for (int d = 1; d <= c8n; ++d)
+            if (c8n % d == 0 && d * tpc <= 128) cg = d;
+        const int threads = std::min(128, (cg * tpc + 31) / 32 * 32);
+        const unsigned grid = (unsigned)(in_tiles * (c8n / cg));
+        const size_t smem = (size_t)2 * cg * (((TILE_M / L.hin) * (L.hin + 1)) | 1) * 16;
+#define DW_SMEM(KK, SS, HH)                                                                                                              \
+        if (L.k == KK && L.stride == SS && L.hin == HH) {                                                                                \
+            if (smem > 48 * 1024) CV_CUDA(cudaFuncSetAttribute(depthwise_x2_smem_kernel<KK, SS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            depthwise_x2_smem_kernel<KK, SS, HH><<<grid, threads, smem, s>>>(x, w, bias, y, L.cout, cg, L.relu, ovf);                   \
+            CV_CHECK_LAUNCH();                                                                                                           \
+            return CV_OK;                                                                                                                \
+        }
+        DW_SMEM(5, 1, 8) DW_SMEM(5, 2, 8) DW_SMEM(3, 1, 4) DW_SMEM(3, 2, 4) DW_SMEM(5, 1, 2) DW_SMEM(3, 1, 2)
+#undef DW_SMEM
+    }
     const int64_t rows = total / L.hout;
     const unsigned grid = (unsigned)((rows + 127) / 128);
 #define DW_ROWS(KK, SS, HH)                                                                                                 \
