@@ -46,13 +46,15 @@ struct X2Params {
     const uint8_t* boards;    // stem with the crop gather fused in: uint8 HWC boards, normalisation table, board side
     const float* lut;
     int H;
+    int raw_ok;               // the board pointer is 4-byte aligned: the patch rows can be staged with word loads
     int groups;               // the large term A_hi W_hi is accumulated in `groups` separate TMEM ranges (k-steps dealt round robin), summed in the epilogue
     int hin, hout, cin;       // dense only
 };
 
 // fused crop gather (stem only): normalisation table + tap tables + one crop patch per gather group behind the barriers
 constexpr int PATCH_ROWS = 9, PATCH_COLS = 65, PATCH_BYTES = (PATCH_ROWS * PATCH_COLS * 3 * 4 + 15) & ~15, MAX_GG = 4;
-constexpr int CROP_SMEM = 768 * 4 + (((int)sizeof(CropTaps) + 15) & ~15) + MAX_GG * PATCH_BYTES;
+constexpr int RAW_ROWS = 16, RAW_WORDS = 80;          // staged board rows under a patch, per gather group (fits 512-pixel boards: 14 rows x 75 words)
+constexpr int CROP_SMEM = 768 * 4 + (((int)sizeof(CropTaps) + 15) & ~15) + MAX_GG * PATCH_BYTES + MAX_GG * RAW_ROWS * RAW_WORDS * 4;
 struct Plan { uint32_t b_bytes, a_bytes, off_a, off_bias, off_bar, off_crop, total; };
 __host__ __device__ inline Plan plan_smem(int K, int N, int stages, int slices = 1, bool crop = false) {
     Plan s;
@@ -324,17 +326,22 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
             mbar_arrive_expect_tx(q.wbar, s.b_bytes);
             bulk_g2s(q.b, p.wimg, s.b_bytes, q.wbar);
         }
-        const int hw = p.hout * p.hout, kc = CIN8 > 0 ? 3 * CIN8 : 4;
-        int64_t item = 0;                                    // ring stage counter: (tile iteration, slice)
+        const int kc = CIN8 > 0 ? 3 * CIN8 : 4;
+        const int lh = 31 - __clz(p.hout);                   // hout is 32, 16 or 8: shifts, not the 64-bit divisions this loop used to spend 12 % of its instructions on
+        // ring position of the current item = (tile iteration, slice): every gather thread counts all items, its group fills every GG-th
+        int stage = 0, turn = 0;
+        uint32_t phase = 0;
+        auto next_item = [&]() {
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (++turn == GG) turn = 0;
+        };
         for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
             const int64_t m = (int64_t)tile * TILE_M + r;
-            const int64_t n = m / hw;
-            const int rem = (int)(m - n * hw);
-            const int oy = rem / p.hout, ox = rem - oy * p.hout;
-            for (int sl = 0; sl < p.slices; ++sl, ++item) {
-                if ((int)(item % GG) != grp) continue;
-                const int stage = (int)(item % p.stages);
-                const uint32_t phase = (uint32_t)((item / p.stages) & 1);
+            const int64_t n = m >> (2 * lh);
+            const int rem = (int)m & ((1 << (2 * lh)) - 1);
+            const int oy = rem >> lh, ox = rem & (p.hout - 1);
+            for (int sl = 0; sl < p.slices; ++sl, next_item()) {
+                if (turn != grp) continue;
                 mbar_wait(q.empty + stage, phase ^ 1u);
                 uint4* dst = reinterpret_cast<uint4*>(q.a + (size_t)stage * s.a_bytes) + r;
                 if (CIN8 > 0) {
@@ -376,7 +383,25 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
                         const int col = (int)(n & 7), row = (int)((n >> 3) & 7);
                         const uint8_t* board = p.boards + (n >> 6) * (int64_t)p.H * p.H * 3;
                         const int oy0 = oy - (r >> 5);                       // first output row of the tile (r >> 5 = this thread's row inside it)
-                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");          // the previous tile's readers are done with P
+                        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");          // the previous tile's readers are done with P and the staged rows
+                        // The board rows under the patch (<= RAW_ROWS rows of <= RAW_WORDS aligned words: 9 x 39 for 256-pixel boards) are staged
+                        // first -- about three coalesced word loads per thread and ONE exposed global latency per tile, where blending straight
+                        // from global memory cost every thread five dependent rounds of twelve byte loads (26 % of the kernel's stall samples).
+                        const int iyA = max(2 * oy0 - 1, 0), iyB = min(2 * oy0 + 7, 63);
+                        const int yb0 = tp.p0[row][iyA], nrows = tp.p1[row][iyB] - yb0 + 1;
+                        const int xw0 = (tp.p0[col][0] * 3) >> 2, nwords = ((tp.p1[col][63] * 3 + 3 + 3) >> 2) - xw0;
+                        const bool staged = p.raw_ok && nrows <= RAW_ROWS && nwords <= RAW_WORDS;
+                        uint32_t* RW = reinterpret_cast<uint32_t*>(patches + MAX_GG * (PATCH_BYTES / 4)) + grp * (RAW_ROWS * RAW_WORDS);
+                        if (staged) {
+                            const uint32_t* bw = reinterpret_cast<const uint32_t*>(board);
+                            const int hw4 = p.H * 3 / 4;                          // words per board row (H % 32 == 0)
+                            for (int i = r; i < nrows * RAW_WORDS; i += 128) {
+                                const int rr = i / RAW_WORDS, ww = i - rr * RAW_WORDS;
+                                if (ww < nwords) RW[i] = __ldg(bw + (size_t)(yb0 + rr) * hw4 + xw0 + ww);
+                            }
+                            asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+                        }
+                        const uint8_t* RB = reinterpret_cast<const uint8_t*>(RW);
                         for (int e = r; e < PATCH_ROWS * PATCH_COLS; e += 128) {
                             const int pr = e / PATCH_COLS, pc = e - pr * PATCH_COLS;
                             const int iy = 2 * oy0 - 1 + pr, ix = pc - 1;
@@ -384,11 +409,19 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
                             if (iy >= 0 && iy < 64 && ix >= 0) {
                                 const int y0 = tp.p0[row][iy], y1 = tp.p1[row][iy], x0 = tp.p0[col][ix], x1 = tp.p1[col][ix];
                                 const float ly = tp.lam[iy], lx = tp.lam[ix];
-                                const uint8_t *p00 = board + (y0 * p.H + x0) * 3, *p01 = board + (y0 * p.H + x1) * 3, *p10 = board + (y1 * p.H + x0) * 3,
-                                              *p11 = board + (y1 * p.H + x1) * 3;
-                                v0 = crop_blend(lut_s[__ldg(p00)], lut_s[__ldg(p01)], lut_s[__ldg(p10)], lut_s[__ldg(p11)], lx, ly);
-                                v1 = crop_blend(lut_s[256 + __ldg(p00 + 1)], lut_s[256 + __ldg(p01 + 1)], lut_s[256 + __ldg(p10 + 1)], lut_s[256 + __ldg(p11 + 1)], lx, ly);
-                                v2 = crop_blend(lut_s[512 + __ldg(p00 + 2)], lut_s[512 + __ldg(p01 + 2)], lut_s[512 + __ldg(p10 + 2)], lut_s[512 + __ldg(p11 + 2)], lx, ly);
+                                if (staged) {
+                                    const uint8_t *r0 = RB + (y0 - yb0) * (RAW_WORDS * 4) - xw0 * 4, *r1 = RB + (y1 - yb0) * (RAW_WORDS * 4) - xw0 * 4;
+                                    const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
+                                    v0 = crop_blend(lut_s[p00[0]], lut_s[p01[0]], lut_s[p10[0]], lut_s[p11[0]], lx, ly);
+                                    v1 = crop_blend(lut_s[256 + p00[1]], lut_s[256 + p01[1]], lut_s[256 + p10[1]], lut_s[256 + p11[1]], lx, ly);
+                                    v2 = crop_blend(lut_s[512 + p00[2]], lut_s[512 + p01[2]], lut_s[512 + p10[2]], lut_s[512 + p11[2]], lx, ly);
+                                } else {
+                                    const uint8_t *p00 = board + (y0 * p.H + x0) * 3, *p01 = board + (y0 * p.H + x1) * 3, *p10 = board + (y1 * p.H + x0) * 3,
+                                                  *p11 = board + (y1 * p.H + x1) * 3;
+                                    v0 = crop_blend(lut_s[__ldg(p00)], lut_s[__ldg(p01)], lut_s[__ldg(p10)], lut_s[__ldg(p11)], lx, ly);
+                                    v1 = crop_blend(lut_s[256 + __ldg(p00 + 1)], lut_s[256 + __ldg(p01 + 1)], lut_s[256 + __ldg(p10 + 1)], lut_s[256 + __ldg(p11 + 1)], lx, ly);
+                                    v2 = crop_blend(lut_s[512 + __ldg(p00 + 2)], lut_s[512 + __ldg(p01 + 2)], lut_s[512 + __ldg(p10 + 2)], lut_s[512 + __ldg(p11 + 2)], lx, ly);
+                                }
                             }
                             P[e * 3] = v0; P[e * 3 + 1] = v1; P[e * 3 + 2] = v2;
                         }
@@ -579,42 +612,55 @@ depthwise_x2_smem_kernel(const uint16_t* __restrict__ x, const float* __restrict
     if (bad) atomicOr(ovf, 1);
 }
 
-// One warp per crop: mean over the 2x2 map (reference order), the 7 + 3 head dot products, type + color -> 13 joint logits.
+// Pool + heads.  Thread = one ROW of the final 2x2 map (lane = crop_local * 4 + pixel: a warp covers 8 crops and its LDG.128 of a chunk plane
+// is 512 contiguous bytes; the first version walked single halves with one warp per crop).  Per 8-channel chunk: hi + lo joined, the 2x2
+// mean by two xor-shuffles -- (a0 + a1) + (a2 + a3), the reference's order -- after which all four lanes of a crop hold it; lane p stores
+// channels 2p, 2p + 1 of the pooled features and accumulates its share of the 7 + 3 head dot products (p = 0: type 0-2, 1: type 3-5,
+// 2: type 6 + color 0, 3: color 1-2); type + color -> 13 joint logits at the end (square.py:87-104, common.py:24).
 __global__ void __launch_bounds__(256)
 pool_heads_x2_kernel(const uint16_t* __restrict__ fmap /* X2 [n_crops*4 rows][480] */, const float* __restrict__ head_w, const float* __restrict__ head_b,
                      int64_t n_crops, float* __restrict__ features, float* __restrict__ squares) {
-    const int64_t n = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (n >= n_crops) return;
+    const int lane = threadIdx.x & 31, px = lane & 3;
+    const int64_t m = (blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5)) * 32 + lane;      // row of the X2 tensor
+    const int64_t n = m >> 2;
+    if ((m & ~(int64_t)31) >= n_crops * 4) return;                    // whole warps only (n_crops * 4 is a multiple of 128)
+    const uint4* src = reinterpret_cast<const uint4*>(fmap) + ((size_t)(m >> 7) * 120) * TILE_M + (m & 127);
+    const int h0 = px == 0 ? 0 : px == 1 ? 3 : px == 2 ? 6 : 8, nh = px < 2 ? 3 : 2;      // this lane's heads [h0, h0 + nh)
+    float part[3] = {0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int ch = 0; ch < 60; ++ch) {
+        float v[8];
+        join8(__ldg(src + (size_t)ch * TILE_M), __ldg(src + (size_t)(60 + ch) * TILE_M), v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 1);
+            v[e] += __shfl_xor_sync(0xffffffffu, v[e], 2);
+            v[e] *= 0.25f;
+        }
+        float2 mine = px == 0 ? make_float2(v[0], v[1]) : px == 1 ? make_float2(v[2], v[3]) : px == 2 ? make_float2(v[4], v[5]) : make_float2(v[6], v[7]);
+        *reinterpret_cast<float2*>(features + n * 480 + ch * 8 + px * 2) = mine;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            if (r < nh) {
+                const float4* wp = reinterpret_cast<const float4*>(head_w + (h0 + r) * 480 + ch * 8);
+                const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                part[r] = fmaf(v[0], w0.x, part[r]); part[r] = fmaf(v[1], w0.y, part[r]); part[r] = fmaf(v[2], w0.z, part[r]); part[r] = fmaf(v[3], w0.w, part[r]);
+                part[r] = fmaf(v[4], w1.x, part[r]); part[r] = fmaf(v[5], w1.y, part[r]); part[r] = fmaf(v[6], w1.z, part[r]); part[r] = fmaf(v[7], w1.w, part[r]);
+            }
+        }
+    }
+    // all ten head outputs on every lane of the crop: head h lives on lane base + (h < 3 ? 0 : h < 6 ? 1 : h < 8 ? 2 : 3), slot h - h0
+    float head[10];
+    const int base = lane & ~3;
+#pragma unroll
+    for (int h = 0; h < 10; ++h) {
+        const int owner = h < 3 ? 0 : h < 6 ? 1 : h < 8 ? 2 : 3, slot = h - (owner == 0 ? 0 : owner == 1 ? 3 : owner == 2 ? 6 : 8);
+        head[h] = __shfl_sync(0xffffffffu, part[slot], base + owner) + __ldg(head_b + h);
+    }
     const int kT[13] = {0, 1, 2, 3, 4, 5, 6, 1, 2, 3, 4, 5, 6}, kC[13] = {0, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2};      // dataset.py:31-32
-    float part[10];
 #pragma unroll
-    for (int r = 0; r < 10; ++r) part[r] = 0.f;
-    const __half* f = reinterpret_cast<const __half*>(fmap);
-    auto at = [&](int64_t m, int ch) {                        // value (row m, channel ch) of the X2 tensor with 480 channels
-        const size_t base = (((size_t)(m >> 7) * 120 + (ch >> 3)) * TILE_M + (m & 127)) * 8 + (ch & 7);
-        return __half2float(f[base]) + __half2float(f[base + (size_t)60 * TILE_M * 8]);
-    };
-    for (int c = lane; c < 480; c += 32) {
-        const float m = ((at(n * 4, c) + at(n * 4 + 1, c)) + (at(n * 4 + 2, c) + at(n * 4 + 3, c))) * 0.25f;
-        features[n * 480 + c] = m;
-#pragma unroll
-        for (int r = 0; r < 10; ++r) part[r] = fmaf(m, __ldg(head_w + r * 480 + c), part[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part[r] += __shfl_xor_sync(0xffffffffu, part[r], o);
-        part[r] += __ldg(head_b + r);
-    }
-    if (lane < 13) {
-        float t = 0.f, cl = 0.f;
-#pragma unroll
-        for (int r = 0; r < 7; ++r) if (r == kT[lane]) t = part[r];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) if (r == kC[lane]) cl = part[7 + r];
-        squares[n * 13 + lane] = t + cl;
-    }
+    for (int o = 0; o < 13; ++o)
+        if ((o & 3) == px) squares[n * 13 + o] = head[kT[o]] + head[7 + kC[o]];
 }
 
 // X2 -> row-major fp32 [rows][C] (debug taps)
@@ -763,6 +809,7 @@ int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f3
     int rc = fill_params(L, &p, n_crops);
     if (rc) return rc;
     p.x = x; p.x_f32 = x_f32_crops; p.boards = boards; p.H = H; p.lut = lut;
+    p.raw_ok = boards != nullptr && (reinterpret_cast<uintptr_t>(boards) & 3) == 0 && H % 4 == 0;
     p.wimg = wimg; p.bias = bias; p.skip = nullptr; p.y = y; p.ovf = ovf; p.unscale = unscale;
     const Plan sp = plan_smem(p.K, p.N, p.stages, p.slices, L.cin == 3 && boards && taps);
     const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
@@ -831,7 +878,8 @@ int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* 
 int launch_pool_heads_x2(const uint16_t* fmap, const float* head_w, const float* head_b, int64_t n_crops, float* features, float* squares,
                          cudaStream_t s) {
     if (n_crops == 0) return CV_OK;
-    pool_heads_x2_kernel<<<(unsigned)((n_crops + 7) / 8), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features, squares);
+    if ((n_crops * 4) % TILE_M != 0) { cv_set_error("pool_heads_x2: crop count not tiled"); return CV_ERR_ARG; }
+    pool_heads_x2_kernel<<<(unsigned)((n_crops * 4 + 255) / 256), 256, 0, s>>>(fmap, head_w, head_b, n_crops, features, squares);
     CV_CHECK_LAUNCH();
     return CV_OK;
 }

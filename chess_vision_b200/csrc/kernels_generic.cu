@@ -244,42 +244,57 @@ global_head_kernel(const float* __restrict__ feat, const float* __restrict__ wt,
     }
 }
 
-// The same fp64 head with the 30720-term reduction cut into KS ranges over the grid (blocks = board tiles x KS): a batch of 1024 boards
-// gives 128 blocks of 8 warps with the kernel above -- one per SM, latency-bound (1.4 ms) -- and 8 times as many here.  Partial sums
-// (double) go to `partial[ks][board][64]`; the finishing kernel adds them in a fixed order (deterministic), then bias, ReLU, 64 -> 1 + 4.
-constexpr int HEAD_KS = 8;
+// The fp64 head as a register-tiled GEMM: partial[ks][b][j] = sum over K range ks of feat[b][k] * wt[k][j], products and sums in double.
+// CTA = 64 boards x 64 outputs x one of HEAD_KS K ranges (1024 boards: 16 x 30 CTAs, three per SM); thread = 4 boards x 4 outputs (j, j + 16,
+// j + 32, j + 48: a warp's weight loads are 128 contiguous bytes).  Features and weights are converted to double ONCE when a 32-deep K slab
+// is staged in shared memory (the feature slab transposed, rows padded to 65 doubles: conflict-free both ways), so the inner loop is
+// 8 LDS.64 per 16 DFMA -- the first version converted both operands in front of every DFMA and ran at 2.4 TFLOP/s (0.8 ms per 1024 boards).
+// The finishing kernel adds the partial sums in a fixed order (deterministic), then bias, ReLU, 64 -> 1 + 4.
+constexpr int HEAD_KS = 30, HEAD_BT = 64, HEAD_KC = 32;
 __global__ void __launch_bounds__(256)
 global_head_f64_partial_kernel(const float* __restrict__ feat, const float* __restrict__ wt, int B, double* __restrict__ partial) {
-    __shared__ float sf[GB][GK];
-    __shared__ double red[4][GB][64];
-    const int j = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    const int b0 = blockIdx.x * GB, ks = blockIdx.y;
+    __shared__ double fs[HEAD_KC][HEAD_BT + 1];
+    __shared__ double ws[HEAD_KC][64];
+    const int tj = threadIdx.x & 15, tb = threadIdx.x >> 4;
+    const int b0 = blockIdx.x * HEAD_BT, ks = blockIdx.y;
     const int k_lo = ks * (30720 / HEAD_KS), k_hi = k_lo + 30720 / HEAD_KS;
-    double acc[GB];
+    double acc[4][4];
 #pragma unroll
-    for (int i = 0; i < GB; ++i) acc[i] = 0;
-    for (int k0 = k_lo; k0 < k_hi; k0 += GK) {
-        const int gk = min(GK, k_hi - k0);
-        for (int t = threadIdx.x; t < GB * gk / 4; t += 256) {
-            const int bi = t / (gk / 4), kk = t % (gk / 4);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int k0 = k_lo; k0 < k_hi; k0 += HEAD_KC) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {                      // 64 boards x 8 float4 of features, 32 x 16 float4 of weights
+            const int idx = threadIdx.x + 256 * t;
+            const int bi = idx >> 3, kq = idx & 7;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (b0 + bi < B) v = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)(b0 + bi) * 30720 + k0) + kk);
-            reinterpret_cast<float4*>(&sf[bi][0])[kk] = v;
+            if (b0 + bi < B) v = __ldg(reinterpret_cast<const float4*>(feat + (int64_t)(b0 + bi) * 30720 + k0) + kq);
+            fs[kq * 4 + 0][bi] = (double)v.x; fs[kq * 4 + 1][bi] = (double)v.y; fs[kq * 4 + 2][bi] = (double)v.z; fs[kq * 4 + 3][bi] = (double)v.w;
+            const int kk = idx >> 4, jq = idx & 15;
+            const float4 u = __ldg(reinterpret_cast<const float4*>(wt + (int64_t)(k0 + kk) * 64) + jq);
+            ws[kk][jq * 4 + 0] = (double)u.x; ws[kk][jq * 4 + 1] = (double)u.y; ws[kk][jq * 4 + 2] = (double)u.z; ws[kk][jq * 4 + 3] = (double)u.w;
         }
         __syncthreads();
-        for (int kk = slice; kk < gk; kk += 4) {
-            const double wv = (double)__ldg(wt + (int64_t)(k0 + kk) * 64 + j);
+#pragma unroll 8
+        for (int kk = 0; kk < HEAD_KC; ++kk) {
+            double f[4], w4[4];
 #pragma unroll
-            for (int i = 0; i < GB; ++i) acc[i] += (double)sf[i][kk] * wv;
+            for (int i = 0; i < 4; ++i) { f[i] = fs[kk][tb * 4 + i]; w4[i] = ws[kk][tj + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(f[i], w4[j], acc[i][j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < GB; ++i) red[slice][i][j] = acc[i];
-    __syncthreads();
-    for (int t = threadIdx.x; t < GB * 64; t += 256) {
-        const int bi = t >> 6, jj = t & 63;
-        if (b0 + bi < B) partial[((size_t)ks * B + b0 + bi) * 64 + jj] = (red[0][bi][jj] + red[1][bi][jj]) + (red[2][bi][jj] + red[3][bi][jj]);
+    for (int i = 0; i < 4; ++i) {
+        const int b = b0 + tb * 4 + i;
+        if (b < B) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) partial[((size_t)ks * B + b) * 64 + tj + 16 * j] = acc[i][j];
+        }
     }
 }
 __global__ void __launch_bounds__(64)
@@ -437,8 +452,8 @@ size_t global_head_f64_partial_bytes(int B) { return (size_t)HEAD_KS * B * 64 * 
 int launch_global_head_f64_split(const float* features, const float* glob_wt, const float* glob_b, const float* tc_w, const float* tc_b, int B,
                                  double* partial, float* turn, float* castling, cudaStream_t s) {
     if (B == 0) return CV_OK;
-    static_assert((30720 / HEAD_KS) % 4 == 0, "K ranges must be float4 aligned");
-    global_head_f64_partial_kernel<<<dim3((unsigned)blocks_for(B, GB), HEAD_KS), 256, 0, s>>>(features, glob_wt, B, partial);
+    static_assert(30720 % HEAD_KS == 0 && (30720 / HEAD_KS) % HEAD_KC == 0, "K ranges must be whole slabs");
+    global_head_f64_partial_kernel<<<dim3((unsigned)blocks_for(B, HEAD_BT), HEAD_KS), 256, 0, s>>>(features, glob_wt, B, partial);
     CV_CHECK_LAUNCH();
     global_head_f64_finish_kernel<<<B, 64, 0, s>>>(partial, glob_b, tc_w, tc_b, B, turn, castling);
     CV_CHECK_LAUNCH();
