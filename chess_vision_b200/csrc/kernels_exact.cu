@@ -458,6 +458,165 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
     if (warp == MMA_WARP) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// blocks.0.0 (3x3 stride 2, 32 -> 16 channels, 32x32 -> 16x16) as an IMPLICIT GEMM: no im2col copy.  The gather kernel above rebuilds
+// every tile's K = 288 operand image from global memory -- each stem pixel is fetched 2.25 times through L1 / L2 and stored again to
+// shared memory -- and sits at half of the HBM roofline, bound by the latency of its gathers.  Here a work item is a COLUMN SLAB of one
+// crop's output (16 rows x 8 columns = 128 GEMM rows, as in the 16-bit front end): its input region -- 32 rows x 17 columns x 8 chunk
+// planes (4 hi, 4 lo), 70 KB -- is copied ONCE with 16-byte cp.async into a parity-split image: per plane 33 rows (row 0 = the zero
+// padding above the crop) of 9 odd-column units then 8 even-column units.  With that order every filter tap's A operand is a plain
+// K-major descriptor into the image: the 8 rows of a core matrix (output columns 8s .. 8s+7, input columns 2 ox - 1 + kx) are 8
+// consecutive units of one parity, successive core matrices (output rows) are two image rows apart (SBO), the two K core matrices of a
+// k-step are one plane apart (LBO).  Two slab images in flight; the MMA issue order, the split scheme (A_hi W_hi in `groups` accumulators
+// dealt round robin, A_lo W_hi + A_hi W_lo in another) and the weight image are those of dense_x2_kernel, so the results are bit-identical.
+// 21 warps: 0-3 epilogue, 4-19 loaders (two groups of 8, warp = plane), 20 MMA issuer (+ TMEM owner).
+namespace b00 {
+constexpr int RPU = 17, ROWS = 33, PLU = RPU * ROWS, PLANES = 8, STAGE_BYTES = PLANES * PLU * 16, NSTAGE = 2;   // units of 16 bytes
+constexpr int W_BYTES = 288 * 2 * 16 * 2;
+constexpr int OFF_STAGE = (W_BYTES + 127) & ~127, OFF_BIAS = OFF_STAGE + NSTAGE * STAGE_BYTES, OFF_BAR = OFF_BIAS + 64, SMEM = OFF_BAR + 96;
+constexpr int LOADERS = 256;
+}
+__global__ void __launch_bounds__(672, 1) dense_b00_x2_kernel(const __grid_constant__ X2Params p) {
+    using namespace b00;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* wimg_s = smem;
+    uint8_t* stage_s = smem + OFF_STAGE;
+    float* bias_s = reinterpret_cast<float*>(smem + OFF_BIAS);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+    uint64_t *full = bars, *empty = bars + 2, *tfull = bars + 4, *tempty = bars + 6, *wbar = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int N = 16, GROUPS = 6, KSTEPS = 18;
+    const int n_items = p.m_tiles;                           // 2 slabs per crop = the layer's 128-row tile count
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(full + i, LOADERS); mbar_init(empty + i, 1); mbar_init(tfull + i, 1); mbar_init(tempty + i, 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 20) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (threadIdx.x < N) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    for (int i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0u, 0u, 0u, 0u);   // row 0 of every plane stays zero
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4 && warp < 20) {
+        // ---- loaders: two groups of 8 warps (group g fills image g with every other item, so two items' loads are in flight), warp = plane
+        //      (part = plane >> 2, chunk = plane & 3); 17 rounds of 32 units = the plane's 32 rows x 17 columns, all loads of a thread issued
+        //      before its first store.  (16-byte cp.async instead of LDG + STS: 3.6 ms per 1024 boards against 3.0 for the gather kernel --
+        //      the issuing warps stall on every cp.async.)
+        const int grp = (warp - 4) >> 3, plane = (warp - 4) & 7, part = plane >> 2, ch = plane & 3;
+        if (threadIdx.x == 128) {
+            mbar_arrive_expect_tx(wbar, W_BYTES);
+            bulk_g2s(wimg_s, p.wimg, W_BYTES, wbar);
+        }
+        const uint4* src = reinterpret_cast<const uint4*>(p.x);
+        uint4* dst0 = reinterpret_cast<uint4*>(stage_s + (size_t)grp * STAGE_BYTES) + plane * PLU + RPU;      // image row 1 = crop row 0
+        int i = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+            if ((i & 1) != grp) continue;
+            const int64_t n = item >> 1;
+            const int sl = item & 1;
+            uint4 v[17];
+#pragma unroll
+            for (int it = 0; it < 17; ++it) {
+                const int u = it * 32 + lane, iy = u / 17, ixl = u - iy * 17;        // ixl: column 16 sl - 1 + ixl
+                const int ix = 16 * sl - 1 + ixl;
+                const int64_t pin = n * 1024 + iy * 32 + (ix < 0 ? 0 : ix);
+                v[it] = __ldg(src + ((size_t)(pin >> 7) * 8 + part * 4 + ch) * TILE_M + (pin & 127));
+                if (ix < 0) v[it] = make_uint4(0u, 0u, 0u, 0u);                      // the column left of the crop
+            }
+            mbar_wait(empty + grp, ((uint32_t)(i >> 1) & 1u) ^ 1u);                 // the MMAs of item i - 2 have read this image
+#pragma unroll
+            for (int it = 0; it < 17; ++it) {
+                const int u = it * 32 + lane, iy = u / 17, ixl = u - iy * 17;
+                dst0[iy * RPU + ((ixl & 1) ? 9 + (ixl >> 1) : (ixl >> 1))] = v[it];
+            }
+            fence_proxy_async_smem();
+            mbar_arrive(full + grp);
+        }
+    } else if (warp == 20) {
+        // ---- MMA issuer
+        const uint32_t idesc = make_idesc_f16(TILE_M, N);
+        constexpr uint32_t b_lbo = 2 * N * 16;
+        mbar_wait(wbar, 0);
+        int i = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+            const int stage = i & 1, acc = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(full + stage, ph);
+            mbar_wait(tempty + acc, ph ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t img = smem_u32(stage_s + (size_t)stage * STAGE_BYTES), b_base = smem_u32(wimg_s);
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * 256), d1 = d0 + GROUPS * N;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                    const int tap = k >> 1, kk = k & 1, ky = tap / 3, kx = tap % 3, g = k % GROUPS;
+                    const int xoff = kx == 0 ? 0 : kx == 1 ? 9 : 1;
+                    const uint32_t a_hi = img + (uint32_t)((2 * kk) * PLU + ky * RPU + xoff) * 16, a_lo = a_hi + 4 * PLU * 16;
+                    const uint64_t ah = make_smem_desc(a_hi, PLU * 16, 2 * RPU * 16), al = make_smem_desc(a_lo, PLU * 16, 2 * RPU * 16);
+                    const uint64_t bh = make_smem_desc(b_base + (2 * k) * b_lbo, b_lbo, 128);
+                    const uint64_t bl = make_smem_desc(b_base + (2 * k) * b_lbo + N * 16, b_lbo, 128);
+                    mma_bf16_ss(d0 + (uint32_t)(g * N), ah, bh, idesc, k >= GROUPS ? 1u : 0u);
+                    mma_bf16_ss(d1, al, bh, idesc, k ? 1u : 0u);
+                    mma_bf16_ss(d1, ah, bl, idesc, 1u);
+                }
+                mma_commit(empty + stage);
+                mma_commit(tfull + acc);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- epilogue: TMEM lane = tile row = output row (lane >> 3) + 4 warp, output column 8 slab + (lane & 7)
+        uint32_t bad = 0;
+        int i = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
+            const int acc = i & 1;
+            const int64_t n = item >> 1;
+            const int oy = 4 * warp + (lane >> 3), ox = 8 * (item & 1) + (lane & 7);
+            const int64_t m = n * 256 + oy * 16 + ox;
+            uint4* yt = reinterpret_cast<uint4*>(p.y) + ((size_t)(m >> 7) * 4) * TILE_M + (m & 127);
+            mbar_wait(tfull + acc, (uint32_t)(i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * 256);
+            uint32_t r0[16], r1[16];
+            tmem_ld16(taddr, r0);
+            tmem_ld16(taddr + GROUPS * N, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int g = 1; g < GROUPS; ++g) {                   // large-term partial sums, fixed order
+                uint32_t rg[16];
+                tmem_ld16(taddr + g * N, rg);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r0[e] = __float_as_uint(__uint_as_float(r0[e]) + __uint_as_float(rg[e]));
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + acc);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = fmaf(__uint_as_float(r0[8 * j + e]) + __uint_as_float(r1[8 * j + e]), p.unscale, bias_s[8 * j + e]);
+                    if (p.relu) v[e] = fmaxf(v[e], 0.f);
+                }
+                uint4 hi, lo;
+                bad |= split8(v, hi, lo);
+                yt[(size_t)j * TILE_M] = hi;
+                yt[(size_t)(2 + j) * TILE_M] = lo;
+            }
+        }
+        if (bad) atomicOr(p.ovf, 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 20) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 // Depthwise KxK on square maps of side HIN (8, 4 or 2): thread = one OUTPUT ROW of one crop and one 8-channel chunk (the row-tiled
 // scheme of kernels_umma.cu), on X2 tensors: hi + lo are summed on load (fp32), the taps accumulate in fp32 in the reference's order
 // (bias, then taps in (ky, kx) order), the result is split on store.
@@ -800,6 +959,15 @@ int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_
     return CV_OK;
 }
 
+static bool x2_old_dense() {
+#ifdef CV_EXPERIMENTS
+    static const bool v = getenv("CV_X2_B00_GATHER") != nullptr;     // experiment builds: the gather kernel for blocks.0.0 (A/B timing, bit-identity check)
+    return v;
+#else
+    return false;
+#endif
+}
+
 // x_f32_crops non-null: stem from the fp32 crops; boards non-null: stem with the crop gather fused in (uint8 HWC boards, `taps` of the board size)
 int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint8_t* boards, int H, const float* lut, const CropTaps* taps,
                     const uint16_t* wimg, const float* bias, float unscale, uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
@@ -821,6 +989,12 @@ int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f3
         dense_x2_kernel<C8, SRC, GGR><<<grid, (5 + 4 * GGR) * 32, sp.total, s>>>(p, tp);                                        \
     }
     const bool stem = L.cin == 3;
+    if (!stem && x && L.cin == 32 && L.cout == 16 && L.hin == 32 && L.hout == 16 && p.groups == 6 && !x2_old_dense()) {      // blocks.0.0: implicit GEMM
+        CV_CUDA(cudaFuncSetAttribute(dense_b00_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b00::SMEM));
+        dense_b00_x2_kernel<<<grid, 672, b00::SMEM, s>>>(p);
+        CV_CHECK_LAUNCH();
+        return CV_OK;
+    }
     if (stem && boards && taps) DENSE_LAUNCH(0, 1, 4)        // measured: 4 gather groups 5.8 ms per 1024 boards, 2 groups 6.7 (blend per tap)
     else if (stem && x_f32_crops) DENSE_LAUNCH(0, 0, 2)
     else if (!stem && x && L.cin == 16) DENSE_LAUNCH(2, 0, 2)
