@@ -317,6 +317,7 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
         for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_s[i] = p.lut[i];
         for (int i = threadIdx.x; i < (int)(sizeof(CropTaps) / 4); i += blockDim.x)
             reinterpret_cast<uint32_t*>(smem + s.off_crop + 768 * 4)[i] = reinterpret_cast<const uint32_t*>(&tp_param)[i];
+        for (int i = threadIdx.x; i < MAX_GG * (PATCH_BYTES / 4); i += blockDim.x) patches[i] = 0.f;      // patch column ix = -1 (conv padding) stays zero
     }
     constexpr int MMA_WARP = 4 + 4 * GG;
     const uint32_t tmem_base = gemm_setup(p, q, warp, MMA_WARP, 128);
@@ -402,6 +403,30 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
                             asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
                         }
                         const uint8_t* RB = reinterpret_cast<const uint8_t*>(RW);
+                        if (staged) {
+                            // thread = crop column ix = r & 63 and every other patch row: the column's taps, weights and byte offsets are
+                            // loop-invariant (the zero column ix = -1 of the patch is written once at kernel start)
+                            const int ix = r & 63;
+                            const int x0 = tp.p0[col][ix] * 3 - xw0 * 4, x1 = tp.p1[col][ix] * 3 - xw0 * 4;
+                            const float lx = tp.lam[ix];
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                const int pr = (r >> 6) + 2 * k;
+                                if (pr >= PATCH_ROWS) break;
+                                const int iy = 2 * oy0 - 1 + pr;
+                                float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                                if (iy >= 0 && iy < 64) {
+                                    const uint8_t *r0 = RB + (tp.p0[row][iy] - yb0) * (RAW_WORDS * 4), *r1 = RB + (tp.p1[row][iy] - yb0) * (RAW_WORDS * 4);
+                                    const float ly = tp.lam[iy];
+                                    const uint8_t *p00 = r0 + x0, *p01 = r0 + x1, *p10 = r1 + x0, *p11 = r1 + x1;
+                                    v0 = crop_blend(lut_s[p00[0]], lut_s[p01[0]], lut_s[p10[0]], lut_s[p11[0]], lx, ly);
+                                    v1 = crop_blend(lut_s[256 + p00[1]], lut_s[256 + p01[1]], lut_s[256 + p10[1]], lut_s[256 + p11[1]], lx, ly);
+                                    v2 = crop_blend(lut_s[512 + p00[2]], lut_s[512 + p01[2]], lut_s[512 + p10[2]], lut_s[512 + p11[2]], lx, ly);
+                                }
+                                float* o = P + (pr * PATCH_COLS + ix + 1) * 3;
+                                o[0] = v0; o[1] = v1; o[2] = v2;
+                            }
+                        } else
                         for (int e = r; e < PATCH_ROWS * PATCH_COLS; e += 128) {
                             const int pr = e / PATCH_COLS, pc = e - pr * PATCH_COLS;
                             const int iy = 2 * oy0 - 1 + pr, ix = pc - 1;
@@ -409,19 +434,11 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
                             if (iy >= 0 && iy < 64 && ix >= 0) {
                                 const int y0 = tp.p0[row][iy], y1 = tp.p1[row][iy], x0 = tp.p0[col][ix], x1 = tp.p1[col][ix];
                                 const float ly = tp.lam[iy], lx = tp.lam[ix];
-                                if (staged) {
-                                    const uint8_t *r0 = RB + (y0 - yb0) * (RAW_WORDS * 4) - xw0 * 4, *r1 = RB + (y1 - yb0) * (RAW_WORDS * 4) - xw0 * 4;
-                                    const uint8_t *p00 = r0 + x0 * 3, *p01 = r0 + x1 * 3, *p10 = r1 + x0 * 3, *p11 = r1 + x1 * 3;
-                                    v0 = crop_blend(lut_s[p00[0]], lut_s[p01[0]], lut_s[p10[0]], lut_s[p11[0]], lx, ly);
-                                    v1 = crop_blend(lut_s[256 + p00[1]], lut_s[256 + p01[1]], lut_s[256 + p10[1]], lut_s[256 + p11[1]], lx, ly);
-                                    v2 = crop_blend(lut_s[512 + p00[2]], lut_s[512 + p01[2]], lut_s[512 + p10[2]], lut_s[512 + p11[2]], lx, ly);
-                                } else {
-                                    const uint8_t *p00 = board + (y0 * p.H + x0) * 3, *p01 = board + (y0 * p.H + x1) * 3, *p10 = board + (y1 * p.H + x0) * 3,
-                                                  *p11 = board + (y1 * p.H + x1) * 3;
-                                    v0 = crop_blend(lut_s[__ldg(p00)], lut_s[__ldg(p01)], lut_s[__ldg(p10)], lut_s[__ldg(p11)], lx, ly);
-                                    v1 = crop_blend(lut_s[256 + __ldg(p00 + 1)], lut_s[256 + __ldg(p01 + 1)], lut_s[256 + __ldg(p10 + 1)], lut_s[256 + __ldg(p11 + 1)], lx, ly);
-                                    v2 = crop_blend(lut_s[512 + __ldg(p00 + 2)], lut_s[512 + __ldg(p01 + 2)], lut_s[512 + __ldg(p10 + 2)], lut_s[512 + __ldg(p11 + 2)], lx, ly);
-                                }
+                                const uint8_t *p00 = board + (y0 * p.H + x0) * 3, *p01 = board + (y0 * p.H + x1) * 3, *p10 = board + (y1 * p.H + x0) * 3,
+                                              *p11 = board + (y1 * p.H + x1) * 3;
+                                v0 = crop_blend(lut_s[__ldg(p00)], lut_s[__ldg(p01)], lut_s[__ldg(p10)], lut_s[__ldg(p11)], lx, ly);
+                                v1 = crop_blend(lut_s[256 + __ldg(p00 + 1)], lut_s[256 + __ldg(p01 + 1)], lut_s[256 + __ldg(p10 + 1)], lut_s[256 + __ldg(p11 + 1)], lx, ly);
+                                v2 = crop_blend(lut_s[512 + __ldg(p00 + 2)], lut_s[512 + __ldg(p01 + 2)], lut_s[512 + __ldg(p10 + 2)], lut_s[512 + __ldg(p11 + 2)], lx, ly);
                             }
                             P[e * 3] = v0; P[e * 3 + 1] = v1; P[e * 3 + 2] = v2;
                         }

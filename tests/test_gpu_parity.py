@@ -112,7 +112,7 @@ def test_every_layer_matches_oracle_fp32_split(gpu_model, gold_state):
     print(f"worst per-layer fp32_split rel err {worst:.3e}")
 
 
-@pytest.mark.parametrize("H,n", [(256, 64), (512, 8), (96, 3)])
+@pytest.mark.parametrize("H,n", [(256, 64), (512, 8), (96, 3), (1024, 2)])     # 1024: the stem blends straight from global memory (patch rows too long to stage)
 def test_forward_fp32_split_matches_reference(gpu_model, golden, gold_state, H, n):
     """The same bars as the CUDA-core exact mode (test_forward_fp32_matches_reference): piece logits and trunk features within 1e-5
     of the fp32 oracle and of the fp64 evaluation of the graph, turn / castling (30720-term dot products whose fp32 CPU evaluation
@@ -141,6 +141,21 @@ def test_forward_fp32_split_matches_reference(gpu_model, golden, gold_state, H, 
     assert all(torch.equal(outf[k], out[k]) for k in ("squares", "turn", "castling"))
     host = gpu_model.predict_fen(torch.from_numpy(u8).pin_memory(), precision="fp32_split")
     assert host == want
+
+
+def test_fp32_split_unaligned_boards(gpu_model, golden, gold_state):
+    """A board pointer that is not 4-byte aligned (a C caller's buffer, a torch view with an odd storage offset) cannot be staged with word
+    loads: the stem falls back to byte loads from global memory and must give the same bits."""
+    arrays, meta = golden
+    u8 = torch.from_numpy(boards_u8(256, 3, meta["board_seed"])).cuda()
+    ref = gpu_model.forward_u8(u8, precision="fp32_split")
+    buf = torch.empty(u8.numel() + 16, dtype=torch.uint8, device="cuda")
+    for off in (1, 2, 3):
+        view = buf[off:off + u8.numel()].view(u8.shape)
+        view.copy_(u8)
+        assert view.data_ptr() % 4 == off
+        got = gpu_model.forward_u8(view, precision="fp32_split")
+        assert all(torch.equal(got[k], ref[k]) for k in ("squares", "turn", "castling")), off
 
 
 @pytest.mark.parametrize("mask", [1023, 511, 255, 127, 63, 31, 15, 7, 0])
