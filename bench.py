@@ -485,9 +485,10 @@ def run_native(args):
     alg_bytes, alg_flops = per_crop_bytes * crops_per_launch, per_crop_flops * crops_per_launch
     achieved = alg_bytes / (per_launch_ms / 1e3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum per crop of the fused kernels, from the `ncu --set full` capture of a 512-board
-    # launch at 256x256 (profiles/r01h_fused_kernels_ncu_summary.txt); scaled to this launch's crop count
-    ncu_traffic_per_crop = {49: (100.74e6 + 211.25e6) / 32768, 52: (268.53e6 + 106.75e6) / 32768, 51: (134.59e6 + 28.30e6) / 32768,
-                            50: (51.34e6 + 13.76e6) / 32768}
+    # launch at 256x256 (profiles/r02c_fused_kernels_ncu_summary.txt: fp16 kernels; stage D now also writes the lo feature plane of the
+    # split-tf32 global head); scaled to this launch's crop count
+    ncu_traffic_per_crop = {49: (100.73e6 + 211.95e6) / 32768, 52: (268.50e6 + 106.23e6) / 32768, 51: (135.63e6 + 29.16e6) / 32768,
+                            50: (54.93e6 + 70.28e6) / 32768}
     traffic = ncu_traffic_per_crop[top] * crops_per_launch if (top in ncu_traffic_per_crop and H == 256 and prec in ("bf16", "fp16")) else None
     tflops = alg_flops / (per_launch_ms / 1e3) / 1e12
     hbm_frac, tensor_frac = achieved / peaks["hbm_gbs"], tflops / peaks["bf16_tflops_sustained"]
@@ -500,7 +501,7 @@ def run_native(args):
                 "unit": "TFLOP/s" if tensor_bound else "GB/s",
                 "frac": tensor_frac if tensor_bound else hbm_frac, "traffic": traffic, "peak_source": peaks["source"],
                 "peak_kind": "sustained dense bf16 (kernel timed inside a long step)" if tensor_bound else "copy bandwidth",
-                "traffic_source": "ncu capture of one 512-board launch (profiles/r01h_fused_kernels_ncu_summary.txt), per crop x crops per launch",
+                "traffic_source": "ncu capture of one 512-board launch (profiles/r02c_fused_kernels_ncu_summary.txt), per crop x crops per launch",
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_flops_per_launch": alg_flops,
                 "launch_ms": per_launch_ms, "share_of_step": float(prof_ms[top] / prof_ms.sum()),
                 "tflops": tflops, "tensor_frac_of_sustained": tensor_frac,
