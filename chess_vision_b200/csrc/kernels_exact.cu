@@ -489,7 +489,7 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
 namespace b00 {
 constexpr int RPU = 17, ROWS = 33, PLU = RPU * ROWS, PLANES = 8, STAGE_BYTES = PLANES * PLU * 16, NSTAGE = 2;   // units of 16 bytes
 constexpr int W_BYTES = 288 * 2 * 16 * 2;
-constexpr int OFF_STAGE = (W_BYTES + 127) & ~127, OFF_BIAS = OFF_STAGE + NSTAGE * STAGE_BYTES, OFF_BAR = OFF_BIAS + 64, SMEM = OFF_BAR + 96;
+constexpr int OFF_STAGE = (W_BYTES + 127) & ~127, OFF_BIAS = OFF_STAGE + NSTAGE * STAGE_BYTES, OFF_BAR = OFF_BIAS + 64, OFF_PK = OFF_BAR + 96, SMEM = OFF_PK + 17 * 32 * 4;
 constexpr int LOADERS = 256;
 }
 __global__ void __launch_bounds__(672, 1) dense_b00_x2_kernel(const __grid_constant__ X2Params p) {
@@ -511,6 +511,17 @@ __global__ void __launch_bounds__(672, 1) dense_b00_x2_kernel(const __grid_const
     }
     if (warp == 20) tmem_alloc(tmem_slot, TMEM_COLS);
     if (threadIdx.x < N) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+    uint32_t* pk_s = reinterpret_cast<uint32_t*>(smem + OFF_PK);
+    for (int u = threadIdx.x; u < 17 * 32; u += blockDim.x) {              // loader table, entry u = it * 32 + lane (see the loaders)
+        const int iy = u / 17, ixl = u - iy * 17;
+        pk_s[u] = (uint32_t)((iy >> 2) * 1024 + (iy & 3) * 32 + ixl) | ((uint32_t)(iy * RPU + ((ixl & 1) ? 9 + (ixl >> 1) : (ixl >> 1))) << 16);
+    }
+    auto zmask_of = [](int lane) {                                         // bit it: unit it * 32 + lane is column -1 of slab 0 (zero)
+        uint32_t z = 0;
+#pragma unroll
+        for (int it = 0; it < 17; ++it) z |= ((it * 32 + lane) % 17 == 0 ? 1u : 0u) << it;
+        return z;
+    };
     for (int i = threadIdx.x; i < NSTAGE * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(stage_s)[i] = make_uint4(0u, 0u, 0u, 0u);   // row 0 of every plane stays zero
     fence_proxy_async_smem();
     tc_fence_before();
@@ -523,33 +534,34 @@ __global__ void __launch_bounds__(672, 1) dense_b00_x2_kernel(const __grid_const
         //      (part = plane >> 2, chunk = plane & 3); 17 rounds of 32 units = the plane's 32 rows x 17 columns, all loads of a thread issued
         //      before its first store.  (16-byte cp.async instead of LDG + STS: 3.6 ms per 1024 boards against 3.0 for the gather kernel --
         //      the issuing warps stall on every cp.async.)
-        const int grp = (warp - 4) >> 3, plane = (warp - 4) & 7, part = plane >> 2, ch = plane & 3;
+        const int grp = (warp - 4) >> 3, plane = (warp - 4) & 7;            // plane = part * 4 + chunk: hi planes 0-3, lo 4-7
         if (threadIdx.x == 128) {
             mbar_arrive_expect_tx(wbar, W_BYTES);
             bulk_g2s(wimg_s, p.wimg, W_BYTES, wbar);
         }
         const uint4* src = reinterpret_cast<const uint4*>(p.x);
         uint4* dst0 = reinterpret_cast<uint4*>(stage_s + (size_t)grp * STAGE_BYTES) + plane * PLU + RPU;      // image row 1 = crop row 0
+        // Unit u = it * 32 + lane of the plane: image row iy = u / 17, column ixl = u % 17 (crop column 16 slab - 1 + ixl).  Its global unit
+        // offset inside the crop's 8 input tiles and its place in the image do not depend on the item: packed once (16 bits each), so a
+        // copy costs an add and a load -- computing them per item took 9 k warp instructions and spread a thread's 17 loads over ~2.5 k cycles.
+        //      (the table lives in shared memory: 17 registers more per thread do not fit beside the 68 of the loads in flight at 21 warps)
+        const uint32_t* pk = pk_s + lane;
+        const uint32_t zmask = zmask_of(lane);
         int i = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++i) {
             if ((i & 1) != grp) continue;
-            const int64_t n = item >> 1;
             const int sl = item & 1;
+            const uint4* base = src + (size_t)(item >> 1) * 8192 + plane * 128 + 16 * sl - 1;
+            const uint32_t zm = sl ? 0u : zmask;
             uint4 v[17];
 #pragma unroll
             for (int it = 0; it < 17; ++it) {
-                const int u = it * 32 + lane, iy = u / 17, ixl = u - iy * 17;        // ixl: column 16 sl - 1 + ixl
-                const int ix = 16 * sl - 1 + ixl;
-                const int64_t pin = n * 1024 + iy * 32 + (ix < 0 ? 0 : ix);
-                v[it] = __ldg(src + ((size_t)(pin >> 7) * 8 + part * 4 + ch) * TILE_M + (pin & 127));
-                if (ix < 0) v[it] = make_uint4(0u, 0u, 0u, 0u);                      // the column left of the crop
+                v[it] = make_uint4(0u, 0u, 0u, 0u);
+                if (!((zm >> it) & 1u)) v[it] = __ldg(base + (pk[it * 32] & 0xFFFFu));
             }
             mbar_wait(empty + grp, ((uint32_t)(i >> 1) & 1u) ^ 1u);                 // the MMAs of item i - 2 have read this image
 #pragma unroll
-            for (int it = 0; it < 17; ++it) {
-                const int u = it * 32 + lane, iy = u / 17, ixl = u - iy * 17;
-                dst0[iy * RPU + ((ixl & 1) ? 9 + (ixl >> 1) : (ixl >> 1))] = v[it];
-            }
+            for (int it = 0; it < 17; ++it) dst0[pk[it * 32] >> 16] = v[it];
             fence_proxy_async_smem();
             mbar_arrive(full + grp);
         }
