@@ -10,10 +10,11 @@
 // Layout "X2": a tensor with C channels lives in HBM as the T8 layout of 2C channels -- per 128-row tile, C/8 chunks of hi values
 // followed by C/8 chunks of lo values -- so a tile is still ONE contiguous block = one TMA bulk copy = the K-major / no-swizzle
 // UMMA A operand of both halves.  Same byte count as fp32 activations.
-//   pointwise_x2_kernel   the 27 pointwise convs (+bias, ReLU, residual): TMA producer | MMA issuer | 4 epilogue warps
-//   dense_x2_kernel       the 3 dense 3x3 stride-2 convs as implicit GEMMs (software im2col of both halves; the stem reads the fp32 crops)
-//   depthwise_x2_kernel   the 15 depthwise convs on the CUDA cores in fp32 (hi + lo summed on load, split on store)
-//   pool_heads_x2_kernel  2x2 mean, type / color heads, type + color combine (square.py:87-104, common.py:24)
+//   pointwise_x2_kernel       the 27 pointwise convs (+bias, ReLU, residual): TMA producer | MMA issuer | two epilogue groups of 4 warps
+//   dense_x2_kernel           the stem (crop gather fused in) and blocks.1.0: 3x3 stride-2 convs by software im2col of both halves
+//   dense_b00_x2_kernel       blocks.0.0: 3x3 stride-2 conv as an implicit GEMM over a parity-split slab image (no im2col copy)
+//   depthwise_x2_smem_kernel  the 15 depthwise convs on the CUDA cores in fp32 (hi + lo summed on load, split on store), tile staged in smem
+//   pool_heads_x2_kernel      2x2 mean, type / color heads, type + color combine (square.py:87-104, common.py:24)
 // fp16 overflows above 65504: every store of a hi value checks for non-finite lanes and raises the handle's overflow flag
 // (cv_square_fp16_status); the caller then re-runs with CV_PRECISION_FP32 (the CUDA-core kernels have fp32 range).
 #include <algorithm>
@@ -646,76 +647,10 @@ __global__ void __launch_bounds__(672, 1) dense_b00_x2_kernel(const __grid_const
     if (warp == 20) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// Depthwise KxK on square maps of side HIN (8, 4 or 2): thread = one OUTPUT ROW of one crop and one 8-channel chunk (the row-tiled
-// scheme of kernels_umma.cu), on X2 tensors: hi + lo are summed on load (fp32), the taps accumulate in fp32 in the reference's order
-// (bias, then taps in (ky, kx) order), the result is split on store.
-template <int K, int S, int HIN>
-__global__ void __launch_bounds__(128)
-depthwise_x2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, uint16_t* __restrict__ y,
-                    int64_t total_rows, int C, int relu, int* __restrict__ ovf) {
-    constexpr int HOUT = HIN / S, PAD = ((S - 1) + (K - 1)) / 2, GROUPS = TILE_M / HOUT;
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= total_rows) return;
-    const int c8n = C >> 3;
-    const int g = (int)(t % GROUPS);
-    const int64_t tc = t / GROUPS;
-    const int c = (int)(tc % c8n);
-    const int64_t m_out = (tc / c8n) * TILE_M + (int64_t)g * HOUT;
-    const int64_t crop = m_out / (HOUT * HOUT);
-    const int oy = (int)(m_out - crop * (HOUT * HOUT)) / HOUT;
-    float acc[HOUT][8];
-    {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c * 8) + 1);
-#pragma unroll
-        for (int ox = 0; ox < HOUT; ++ox) {
-            acc[ox][0] = b0.x; acc[ox][1] = b0.y; acc[ox][2] = b0.z; acc[ox][3] = b0.w;
-            acc[ox][4] = b1.x; acc[ox][5] = b1.y; acc[ox][6] = b1.z; acc[ox][7] = b1.w;
-        }
-    }
-    const uint4* src = reinterpret_cast<const uint4*>(x);
-#pragma unroll
-    for (int ky = 0; ky < K; ++ky) {
-        const int iy = oy * S - PAD + ky;
-        if (iy < 0 || iy >= HIN) continue;
-        const int64_t m_in = (crop * HIN + iy) * HIN;
-        const uint4* row = src + ((size_t)(m_in >> 7) * 2 * c8n + c) * TILE_M + (m_in & 127);
-        float px[HIN][8];
-#pragma unroll
-        for (int i = 0; i < HIN; ++i) join8(__ldg(row + i), __ldg(row + (size_t)c8n * TILE_M + i), px[i]);
-#pragma unroll
-        for (int kx = 0; kx < K; ++kx) {
-            const float4* wp = reinterpret_cast<const float4*>(w + (size_t)(ky * K + kx) * C + c * 8);
-            const float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-#pragma unroll
-            for (int ox = 0; ox < HOUT; ++ox) {
-                const int ix = ox * S - PAD + kx;
-                if (ix < 0 || ix >= HIN) continue;
-                acc[ox][0] = fmaf(px[ix][0], w0.x, acc[ox][0]); acc[ox][1] = fmaf(px[ix][1], w0.y, acc[ox][1]);
-                acc[ox][2] = fmaf(px[ix][2], w0.z, acc[ox][2]); acc[ox][3] = fmaf(px[ix][3], w0.w, acc[ox][3]);
-                acc[ox][4] = fmaf(px[ix][4], w1.x, acc[ox][4]); acc[ox][5] = fmaf(px[ix][5], w1.y, acc[ox][5]);
-                acc[ox][6] = fmaf(px[ix][6], w1.z, acc[ox][6]); acc[ox][7] = fmaf(px[ix][7], w1.w, acc[ox][7]);
-            }
-        }
-    }
-    uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)(m_out >> 7) * 2 * c8n + c) * TILE_M + (m_out & 127);
-    uint32_t bad = 0;
-#pragma unroll
-    for (int ox = 0; ox < HOUT; ++ox) {
-        if (relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[ox][i] = fmaxf(acc[ox][i], 0.f);
-        }
-        uint4 hi, lo;
-        bad |= split8(acc[ox], hi, lo);
-        dst[ox] = hi;
-        dst[(size_t)c8n * TILE_M + ox] = lo;
-    }
-    if (bad) atomicOr(ovf, 1);
-}
-
-// Depthwise, second generation: the input tile goes through shared memory.  The row-per-thread kernel above reads its rows straight
-// from global memory -- 128-byte pieces at a 128-byte lane stride, 150-180 registers, 8 warps per SM: latency-bound at 20-45 % of the
-// HBM peak.  Here a CTA owns one INPUT tile (128 rows = 128 / HIN^2 crops) and a group of `cg` channel chunks: all threads copy the
+// Depthwise KxK on square maps of side HIN (8, 4 or 2) on X2 tensors: hi + lo are summed on load (fp32), the taps accumulate in fp32 in
+// the reference's order (bias, then taps in (ky, kx) order), the result is split on store.  The input tile goes through shared memory (the
+// first version, a thread per output row reading its rows straight from global memory -- 128-byte pieces at a 128-byte lane stride, 150-180
+// registers, 8 warps per SM -- was latency-bound at 20-45 % of the HBM peak).  A CTA owns one INPUT tile (128 rows = 128 / HIN^2 crops) and a group of `cg` channel chunks: all threads copy the
 // 2 x cg chunk planes (hi, lo) with 16-byte cp.async (coalesced: consecutive threads, consecutive rows) into an image whose rows are
 // padded by one 16-byte unit (row pitch HIN + 1 units, plane pitch odd: the lanes of a warp -- consecutive image rows -- spread over all
 // bank groups, every LDS.128 at its 4-wavefront minimum), then thread = (chunk, crop, output row) runs the same fp32 arithmetic in the
@@ -988,15 +923,6 @@ int launch_pointwise_x2(const cv_layer_info& L, const uint16_t* x, const uint16_
     return CV_OK;
 }
 
-static bool x2_old_dense() {
-#ifdef CV_EXPERIMENTS
-    static const bool v = getenv("CV_X2_B00_GATHER") != nullptr;     // experiment builds: the gather kernel for blocks.0.0 (A/B timing, bit-identity check)
-    return v;
-#else
-    return false;
-#endif
-}
-
 // x_f32_crops non-null: stem from the fp32 crops; boards non-null: stem with the crop gather fused in (uint8 HWC boards, `taps` of the board size)
 int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f32_crops, const uint8_t* boards, int H, const float* lut, const CropTaps* taps,
                     const uint16_t* wimg, const float* bias, float unscale, uint16_t* y, int64_t n_crops, int num_sms, int* ovf, cudaStream_t s) {
@@ -1018,7 +944,7 @@ int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f3
         dense_x2_kernel<C8, SRC, GGR><<<grid, (5 + 4 * GGR) * 32, sp.total, s>>>(p, tp);                                        \
     }
     const bool stem = L.cin == 3;
-    if (!stem && x && L.cin == 32 && L.cout == 16 && L.hin == 32 && L.hout == 16 && p.groups == 6 && !x2_old_dense()) {      // blocks.0.0: implicit GEMM
+    if (!stem && x && L.cin == 32 && L.cout == 16 && L.hin == 32 && L.hout == 16 && p.groups == 6) {      // blocks.0.0: implicit GEMM
         CV_CUDA(cudaFuncSetAttribute(dense_b00_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, b00::SMEM));
         dense_b00_x2_kernel<<<grid, 672, b00::SMEM, s>>>(p);
         CV_CHECK_LAUNCH();
@@ -1027,7 +953,6 @@ int launch_dense_x2(const cv_layer_info& L, const uint16_t* x, const float* x_f3
     if (stem && boards && taps) DENSE_LAUNCH(0, 1, 4)        // measured: 4 gather groups 5.8 ms per 1024 boards, 2 groups 6.7 (blend per tap)
     else if (stem && x_f32_crops) DENSE_LAUNCH(0, 0, 2)
     else if (!stem && x && L.cin == 16) DENSE_LAUNCH(2, 0, 2)
-    else if (!stem && x && L.cin == 32) DENSE_LAUNCH(4, 0, 2)
     else { cv_set_error("dense_x2: unsupported Cin=%d / source", L.cin); return CV_ERR_ARG; }
 #undef DENSE_LAUNCH
     CV_CHECK_LAUNCH();
@@ -1040,41 +965,25 @@ int launch_depthwise_x2(const cv_layer_info& L, const uint16_t* x, const float* 
     if (total == 0) return CV_OK;
     if ((n_crops * L.hout * L.hout) % TILE_M != 0 || L.hin != L.hout * L.stride) { cv_set_error("depthwise_x2: crop count / shape not tiled"); return CV_ERR_ARG; }
     const int64_t in_tiles = n_crops * L.hin * L.hin / TILE_M;
-#ifdef CV_EXPERIMENTS
-    static const bool old_kernel = getenv("CV_X2_DW_ROWS") != nullptr;     // the first-generation kernel (experiment builds: A/B timing)
-#else
-    const bool old_kernel = false;
-#endif
-    if (!old_kernel && in_tiles * (L.cout / 8) < (int64_t)1 << 31) {
-        // chunk group: the largest divisor of C / 8 that keeps a CTA at <= 64 tasks (tasks per chunk = 128 / HIN / stride): two-warp CTAs, many
-        // per SM, overlap copy and compute best (128 tasks: 0.55 ms for blocks.2.0.dw_mid, 64: 0.50, 32: 0.51)
-        const int c8n = L.cout / 8, tpc = TILE_M / L.hin / L.stride;
-        int cg = 1;
-        for (int d = 1; d <= c8n; ++d)
-            if (c8n % d == 0 && d * tpc <= 64) cg = d;
-        const int threads = std::min(128, (cg * tpc + 31) / 32 * 32);
-        const unsigned grid = (unsigned)(in_tiles * (c8n / cg));
-        const size_t smem = (size_t)2 * cg * (((TILE_M / L.hin) * (L.hin + 1)) | 1) * 16;
+    // chunk group: the largest divisor of C / 8 that keeps a CTA at <= 64 tasks (tasks per chunk = 128 / HIN / stride): two-warp CTAs, many
+    // per SM, overlap copy and compute best (128 tasks: 0.55 ms for blocks.2.0.dw_mid, 64: 0.50, 32: 0.51)
+    const int c8n = L.cout / 8, tpc = TILE_M / L.hin / L.stride;
+    int cg = 1;
+    for (int d = 1; d <= c8n; ++d)
+        if (c8n % d == 0 && d * tpc <= 64) cg = d;
+    if (in_tiles * (c8n / cg) >= (int64_t)1 << 31) { cv_set_error("depthwise_x2: wave too large"); return CV_ERR_ARG; }
+    const int threads = std::min(128, (cg * tpc + 31) / 32 * 32);
+    const unsigned grid = (unsigned)(in_tiles * (c8n / cg));
+    const size_t smem = (size_t)2 * cg * (((TILE_M / L.hin) * (L.hin + 1)) | 1) * 16;
 #define DW_SMEM(KK, SS, HH)                                                                                                              \
-        if (L.k == KK && L.stride == SS && L.hin == HH) {                                                                                \
-            if (smem > 48 * 1024) CV_CUDA(cudaFuncSetAttribute(depthwise_x2_smem_kernel<KK, SS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            depthwise_x2_smem_kernel<KK, SS, HH><<<grid, threads, smem, s>>>(x, w, bias, y, L.cout, cg, L.relu, ovf);                   \
-            CV_CHECK_LAUNCH();                                                                                                           \
-            return CV_OK;                                                                                                                \
-        }
-        DW_SMEM(5, 1, 8) DW_SMEM(5, 2, 8) DW_SMEM(3, 1, 4) DW_SMEM(3, 2, 4) DW_SMEM(5, 1, 2) DW_SMEM(3, 1, 2)
+    if (L.k == KK && L.stride == SS && L.hin == HH) {                                                                                    \
+        if (smem > 48 * 1024) CV_CUDA(cudaFuncSetAttribute(depthwise_x2_smem_kernel<KK, SS, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        depthwise_x2_smem_kernel<KK, SS, HH><<<grid, threads, smem, s>>>(x, w, bias, y, L.cout, cg, L.relu, ovf);                       \
+        CV_CHECK_LAUNCH();                                                                                                               \
+        return CV_OK;                                                                                                                    \
+    }
+    DW_SMEM(5, 1, 8) DW_SMEM(5, 2, 8) DW_SMEM(3, 1, 4) DW_SMEM(3, 2, 4) DW_SMEM(5, 1, 2) DW_SMEM(3, 1, 2)
 #undef DW_SMEM
-    }
-    const int64_t rows = total / L.hout;
-    const unsigned grid = (unsigned)((rows + 127) / 128);
-#define DW_ROWS(KK, SS, HH)                                                                                                 \
-    if (L.k == KK && L.stride == SS && L.hin == HH) {                                                                       \
-        depthwise_x2_kernel<KK, SS, HH><<<grid, 128, 0, s>>>(x, w, bias, y, rows, L.cout, L.relu, ovf);                     \
-        CV_CHECK_LAUNCH();                                                                                                  \
-        return CV_OK;                                                                                                       \
-    }
-    DW_ROWS(5, 1, 8) DW_ROWS(5, 2, 8) DW_ROWS(3, 1, 4) DW_ROWS(3, 2, 4) DW_ROWS(5, 1, 2) DW_ROWS(3, 1, 2)
-#undef DW_ROWS
     cv_set_error("depthwise_x2: unsupported k=%d stride=%d hin=%d", L.k, L.stride, L.hin);
     return CV_ERR_ARG;
 }
