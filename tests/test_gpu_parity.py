@@ -729,6 +729,25 @@ def test_config1_64_boards_fp32_fen_matches_cpu(gpu_model, gold_state, prec):
     assert len(set(got)) == 64                              # non-degenerate: every board reads differently
 
 
+def test_fp32_split_is_batch_invariant_across_waves(gpu_model):
+    """fp32_split at more than one 1024-board wave with a ragged tail (2100 boards): every board's logits equal, bit for bit, what the same
+    board gives in a call of its own window -- tiles, slabs and chunk groups never mix boards, the head's split-K order is fixed."""
+    B = 2100
+    boards = torch.empty((B, 256, 256, 3), dtype=torch.uint8, device="cuda")
+    _native.check(_native.lib().cv_synth_boards(_native.ptr(boards), 0, 31337, B, 256, 1, 1, None, _native.stream_ptr(boards.device)))
+    whole = gpu_model.forward_u8(boards, precision="fp32_split")
+    again = gpu_model.forward_u8(boards, precision="fp32_split")
+    for k in ("squares", "turn", "castling"):
+        assert torch.equal(whole[k], again[k]), k                      # deterministic
+    for lo, n in ((0, 3), (1000, 100), (2047, 53)):
+        part = gpu_model.forward_u8(boards[lo:lo + n].clone(), precision="fp32_split")
+        for k in ("squares", "turn", "castling"):
+            assert torch.equal(whole[k][lo:lo + n], part[k]), (k, lo)
+    assert gpu_model.fp16_status()[1] is False
+    del boards
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("B", [1, 2, 3, 17, 64, 257, 1000])
 def test_config4_batch_sweep_with_flips(gpu_model, gold_state, B):
     """configs[3]: flipped-orientation boards + full FEN over a batch sweep.  fp32 mode is bit-exact against the oracle
