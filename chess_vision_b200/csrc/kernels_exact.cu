@@ -330,20 +330,27 @@ __global__ void __launch_bounds__((5 + 4 * GG) * 32, 1) dense_x2_kernel(const __
         }
         const int kc = CIN8 > 0 ? 3 * CIN8 : 4;
         const int lh = 31 - __clz(p.hout);                   // hout is 32, 16 or 8: shifts, not the 64-bit divisions this loop used to spend 12 % of its instructions on
-        // ring position of the current item = (tile iteration, slice): every gather thread counts all items, its group fills every GG-th
-        int stage = 0, turn = 0;
-        uint32_t phase = 0;
+        // ring position of the current item = (tile iteration, slice); a group fills every GG-th item.  Stem (one item per tile): the group
+        // walks ITS tiles only and advances the ring by GG items at a time; the other layers count all items and skip the foreign ones.
+        constexpr bool OWN = CIN8 == 0;
+        int stage = OWN ? grp % p.stages : 0, turn = 0;
+        uint32_t phase = OWN ? (uint32_t)(grp / p.stages) & 1u : 0u;
         auto next_item = [&]() {
-            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            if (++turn == GG) turn = 0;
+            if (OWN) {
+                stage += GG;
+                while (stage >= p.stages) { stage -= p.stages; phase ^= 1u; }
+            } else {
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                if (++turn == GG) turn = 0;
+            }
         };
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int tile = blockIdx.x + (OWN ? grp * (int)gridDim.x : 0); tile < p.m_tiles; tile += (OWN ? GG : 1) * (int)gridDim.x) {
             const int64_t m = (int64_t)tile * TILE_M + r;
             const int64_t n = m >> (2 * lh);
             const int rem = (int)m & ((1 << (2 * lh)) - 1);
             const int oy = rem >> lh, ox = rem & (p.hout - 1);
             for (int sl = 0; sl < p.slices; ++sl, next_item()) {
-                if (turn != grp) continue;
+                if (!OWN && turn != grp) continue;
                 mbar_wait(q.empty + stage, phase ^ 1u);
                 uint4* dst = reinterpret_cast<uint4*>(q.a + (size_t)stage * s.a_bytes) + r;
                 if (CIN8 > 0) {
