@@ -855,6 +855,7 @@ int fill_params(const cv_layer_info& L, X2Params* p, int64_t n_crops) {
         const int steps = p->K / 16;
         g = g > steps ? steps : g;
         p->groups = g < 1 ? 1 : (g > 6 ? 6 : g);
+        if (steps <= 2) p->groups = 1;               // stem (K = 32): two MMAs per large-term accumulator is fewer than any other layer gets; its epilogue is issue-bound
     }
     const Plan one = plan_smem(p->K, p->N, 1, p->slices);
     int stages = 1 + (int)((SMEM_LIMIT - (int)one.total) / ((int)one.a_bytes + 16));
