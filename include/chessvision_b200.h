@@ -52,7 +52,7 @@ typedef enum cv_status {
  *   CV_PRECISION_FP32_SPLIT  fp32-grade results on the tensor cores: every activation and weight is carried as fp16 hi + lo (22 significant
  *                      bits) and every GEMM k-step issues three MMAs into fp32 accumulators (A_hi W_hi + A_lo W_hi + A_hi W_lo); depthwise
  *                      convolutions and the crop gather stay fp32.  Logits within 1e-5 of the reference and identical FEN strings like
- *                      CV_PRECISION_FP32, at 76 k boards/s against 7 k.  Activations must stay below 65504 in magnitude: cv_square_fp16_status
+ *                      CV_PRECISION_FP32, at 77 k boards/s against 7 k.  Activations must stay below 65504 in magnitude: cv_square_fp16_status
  *                      reports an overflow of the last call (re-run it with CV_PRECISION_FP32, whose kernels have fp32 range). */
 enum { CV_PRECISION_FP32 = 0, CV_PRECISION_BF16 = 1, CV_PRECISION_FP16 = 2, CV_PRECISION_FP32_SPLIT = 3 };
 enum { CV_LAYOUT_HWC = 0, CV_LAYOUT_CHW = 1 };           /* uint8 board layouts: (B,H,H,3) / (B,3,H,H) */
